@@ -1,0 +1,220 @@
+/*
+ * zeroshape_b200 -- C ABI of the B200 (sm_100a) implementation of ZeroShape's per-image hot path.
+ *
+ * This header is the drop-in boundary.  The reference (zxhuang1698/ZeroShape) is pure Python over
+ * PyTorch plus one pybind11 CUDA extension; it has no FFI registry, so each entry point below cites
+ * the reference Python/CUDA function (file:line under the reference tree) whose arithmetic it
+ * replaces.  The Python host package `zeroshape_b200` binds these symbols with ctypes and re-exposes
+ * the reference's own module surface (model.compute_graph.graph_shape.Graph, utils.eval_3D.*,
+ * external.chamfer3D.dist_chamfer_3D.chamfer_3DDist) -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are dense, row-major, fp32 unless stated; image tensors are NHWC inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); nothing synchronises;
+ *   - nothing allocates: callers pass outputs and (where stated) a workspace;
+ *   - return value: 0 = ok, negative = error (message via zs_last_error(), thread-local);
+ *   - all functions are re-entrant and may be called from several host threads.
+ */
+#ifndef ZEROSHAPE_B200_H
+#define ZEROSHAPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS_OK 0
+#define ZS_ERR_ARG (-1)
+#define ZS_ERR_CUDA (-2)
+#define ZS_ERR_UNSUPPORTED (-3)
+
+/* activation codes for fused epilogues */
+#define ZS_ACT_NONE 0
+#define ZS_ACT_RELU 1
+#define ZS_ACT_GELU 2      /* exact erf GELU (torch.nn.GELU default) */
+#define ZS_ACT_SOFTPLUS100 3 /* torch Softplus(beta=100, threshold=20): model/shape/implicit.py:166 */
+#define ZS_ACT_SIGMOID 4
+
+/* residual placement in the fused epilogue: y = act(acc + bias [+ res]) [+ res] */
+#define ZS_RES_NONE 0
+#define ZS_RES_BEFORE_ACT 1
+#define ZS_RES_AFTER_ACT 2
+
+const char* zs_last_error(void);
+int zs_abi_version(void);
+/* compute capability (major*10+minor) of the current device, or negative error */
+int zs_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense building blocks (replace the cuBLAS/cuDNN calls PyTorch issues for nn.Linear / nn.Conv2d /
+ * LayerNorm / GroupNorm / F.interpolate / MaxPool on the hot path; SURVEY.md section 2.3 last row).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* C[M,N] = epilogue( A[M,K] * W[N,K]^T ), fp32 accumulate in fp32 FFMA (bit-faithful path).
+ * Replaces F.linear (e.g. model/shape/implicit.py:30,74,178-181; timm Block qkv/proj/fc1/fc2). */
+int zs_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                const float* res, int ldres, int res_mode, float* C, int ldc,
+                int M, int N, int K, int act, void* stream);
+
+/* NHWC convolution as implicit GEMM: y[b,oh,ow,co] = epi( sum x[b,oh*s+kh-pt,ow*s+kw-pl,ci] w[co,kh,kw,ci] ).
+ * `pre_relu` applies ReLU to x on load (ResidualConvUnit_custom: model/depth/blocks.py:274-281).
+ * Replaces nn.Conv2d in model/depth/blocks.py:58-70,247-253,305, dpt_depth.py:100-108,
+ * utils/layers.py:79-82, torchvision resnet50 and the timm ResNetV2 stem/stages. */
+int zs_conv2d_nhwc_f32(const float* x, int B, int H, int W, int Cin,
+                       const float* w, const float* bias, const float* res, int res_mode,
+                       float* y, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                       int OH, int OW, int act, int pre_relu, void* stream);
+
+/* LayerNorm over the last dim (eps given).  Replaces nn.LayerNorm in timm Block / implicit.py:89,95,225 */
+int zs_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                     int rows, int cols, float eps, void* stream);
+
+/* GroupNorm (+optional ReLU) on NHWC.  Replaces timm GroupNormAct in the ResNetV2 stem/stages. */
+int zs_groupnorm_nhwc_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
+                          int B, int HW, int C, int groups, float eps, int relu, void* stream);
+
+/* Per-channel affine y = act(x*scale[c] + shift[c] (+res)) on [rows, C] (eval-mode BatchNorm). */
+int zs_channel_affine_f32(const float* x, const float* scale, const float* shift, const float* res,
+                          float* y, int64_t rows, int C, int act, void* stream);
+
+/* Elementwise: y = act(a*alpha + b*beta) (b may be NULL). */
+int zs_axpby_f32(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, int act, void* stream);
+
+/* Max-pool 3x3 stride 2 on NHWC with explicit top/left padding (pad value -inf). */
+int zs_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int pad_top, int pad_left,
+                             int OH, int OW, void* stream);
+
+/* Global average pool NHWC [B,HW,C] -> [B,C].  (nn.AdaptiveAvgPool2d((1,1)), graph_shape.py:25) */
+int zs_avgpool_nhwc_f32(const float* x, float* y, int B, int HW, int C, void* stream);
+
+/* Bilinear resize NHWC (align_corners 0/1).  model/depth/blocks.py:336-338, dpt_depth.py:102,
+ * model/depth/vit.py:110 (pos-embed), utils/util.py:341-342. */
+int zs_bilinear_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int OH, int OW,
+                         int align_corners, void* stream);
+
+/* NCHW <-> NHWC */
+int zs_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, float scale, float shift, void* stream);
+int zs_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
+
+/* Multi-head self-attention over T tokens from a packed qkv buffer [B,T,3,heads,hd] -> out [B,T,heads*hd].
+ * softmax(q k^T * scale) v.  Replaces timm Attention.forward and the latent branch implicit.py:65-71. */
+int zs_mha_f32(const float* qkv, float* out, int B, int T, int heads, int hd, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit decoder (model/shape/implicit.py:251-288), query-point side.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Point-to-latent attention of ImplFuncAttention (implicit.py:38-57): each query point attends to the
+ * L latent tokens and to itself.  qkv_p [B,P,3,heads,hd]; k_lat,v_lat [B,L,heads*hd] (row stride ld_lat).
+ * out [B,P,heads*hd].  attn (optional) [B,P,L] accumulates `attn_scale` * mean-over-heads probability. */
+int zs_point_attention_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat,
+                           float* out, float* attn, float attn_scale, int attn_accumulate,
+                           int B, int P, int L, int heads, int hd, float scale, void* stream);
+
+/* Dense query grid of utils/eval_3D.py:10-20 for x-slices [x0,x1): out [x1-x0, n, n, 3], n = N+1,
+ * coordinates = linspace(rmin,rmax,n) exactly as torch.linspace computes them. */
+int zs_dense_grid_f32(float* out, int n, float rmin, float rmax, int x0, int x1, void* stream);
+
+/* concat-and-divide used by MLPBlocks skip layers (implicit.py:179-180): y[r,:] = [a[r,:Ca], b[r,:Cb]] / s */
+int zs_concat2_f32(const float* a, int lda, int Ca, const float* b, int ldb, int Cb, float s, float* y, int ldy,
+                   int64_t rows, void* stream);
+
+/* Fused tcgen05 decoder (the hot kernel).  See DESIGN.md "K1".  `packed` is produced by
+ * zs_implicit_pack; `kv` by zs_implicit_latent_kv_pack.  Points are either streamed (points != NULL,
+ * [B,P,3]) or generated in-kernel from the dense grid description (points == NULL). */
+typedef struct {
+  const float* point_proj_w;  /* [256,3]   */
+  const float* point_proj_b;  /* [256]     */
+  const float* norm1_w[2];    /* [256]     */
+  const float* norm1_b[2];
+  const float* qkv_w[2];      /* [768,256] */
+  const float* qkv_b[2];
+  const float* proj_w[2];     /* [256,256] */
+  const float* proj_b[2];
+  const float* norm2_w[2];
+  const float* norm2_b[2];
+  const float* fc1_w[2];      /* [1024,256] */
+  const float* fc1_b[2];
+  const float* fc2_w[2];      /* [256,1024] */
+  const float* fc2_b[2];
+  const float* norm_w;        /* final LayerNorm */
+  const float* norm_b;
+  const float* mlp_w[9];      /* impl_mlp.layers.{0..8}: [256,259],[256,256],[256,515],... ,[1,256] */
+  const float* mlp_b[9];
+} ZsImplicitWeights;
+
+size_t zs_implicit_packed_bytes(void);
+int zs_implicit_pack(const ZsImplicitWeights* w_host, void* packed, void* stream);
+/* per-image latent K/V of both blocks -> tensor-core operand images. k,v: [B,L,256] fp32 per block. */
+size_t zs_implicit_kv_bytes(int B, int L);
+int zs_implicit_kv_pack(const float* k0, const float* v0, const float* k1, const float* v1,
+                        int B, int L, void* kv, void* stream);
+/* precision: 0 = bf16x3 split (parity mode, ~fp32 accuracy), 1 = single-pass bf16 (fast mode). */
+int zs_implicit_fused_fwd(const void* packed, const void* kv, int L,
+                          const float* points, int B, int64_t P,
+                          int grid_n, float rmin, float rmax, int x0, int x1,
+                          float* logits, int apply_sigmoid, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry glue (utils/camera.py:52-108, model/compute_graph/graph_shape.py:89-144, utils/util.py:336-345)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* intr_param2mtx (graph_shape.py:89-113): params [B,3] -> K [B,3,3]. */
+int zs_intr_param2mtx_f32(const float* params, float* K, int B, int H, int W, void* stream);
+
+/* unproj_depth + valid_norm_fac + normalise + zero background (graph_shape.py:136-141), no host sync.
+ * depth [B,H*W], mask [B,H*W] (valid iff > 0.5), K [B,3,3] -> seen_points [B,H*W,3], mean [B,3], scale [B].
+ * mask == NULL: raw unprojection only (utils/camera.py:88-108), mean/scale untouched.
+ * workspace: zs_unproject_ws_bytes(B) bytes (currently 0). */
+size_t zs_unproject_ws_bytes(int B);
+int zs_unproject_normalize_f32(const float* depth, const float* mask, const float* K,
+                               float* seen_points, float* mean, float* scale,
+                               int B, int H, int W, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chamfer (external/chamfer3D/chamfer3D.cu:12-196, external/chamfer3D/chamfer_cuda.cpp:17-32)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bidirectional nearest neighbour: squared distances + int32 argmin (lowest index on ties), exactly the
+ * contract of chamfer_3D.forward(xyz1,xyz2,dist1,dist2,idx1,idx2) but on the caller's stream and with all
+ * SMs busy at b=1.  ws: zs_chamfer_ws_bytes(b,n,m) bytes of scratch (packed 64-bit min keys). */
+size_t zs_chamfer_ws_bytes(int b, int n, int m);
+int zs_chamfer_nn_fwd(const float* xyz1, const float* xyz2, int b, int n, int m,
+                      float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws, void* stream);
+/* chamfer_3D.backward: gradients are ACCUMULATED into gradxyz1/gradxyz2 (caller zero-fills), like the reference. */
+int zs_chamfer_nn_bwd(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                      const int32_t* idx1, const int32_t* idx2, int b, int n, int m,
+                      float* gradxyz1, float* gradxyz2, void* stream);
+/* compute_fscore + means (utils/eval_3D.py:131-137,215-231) from squared distances: sqrt, mean, and
+ * strict-< threshold fractions.  `squared`=1: inputs are squared distances (sqrt taken first, like
+ * eval_3D.py:268-269), 0: already sqrt-ed.  mean1/2 [b], frac1/2 [b,T]. */
+int zs_chamfer_stats(const float* sqdist1, const float* sqdist2, int b, int n, int m,
+                     const float* thresholds, int T, int squared, float* mean1, float* mean2, float* frac1, float* frac2,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Marching cubes + surface sampling (utils/eval_3D.py:233-263; PyMCubes 0.1.4 / trimesh 4.0.8 semantics)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Pass 1: count.  vol [n,n,n] fp32 (index order i,j,k = x,y,z); a corner is "inside" iff vol <= iso
+ * (PyMCubes).  Writes counts[0] = #vertices (one per crossed grid edge, welded), counts[1] = #triangles.
+ * ws: zs_mc_ws_bytes(n). */
+size_t zs_mc_ws_bytes(int n);
+int zs_mc_count(const float* vol, int n, float iso, void* ws, int32_t* counts, void* stream);
+/* Pass 2: emit (after the caller read counts and allocated).  verts [V,3] fp32 in array-index units,
+ * faces [F,3] int32.  Deterministic ordering (by edge id / cell id). */
+int zs_mc_emit(const float* vol, int n, float iso, void* ws, float* verts, int32_t* faces, void* stream);
+/* Area-weighted surface sampling with an explicit counter-based RNG seed (replaces trimesh.sample).
+ * ws: zs_mesh_sample_ws_bytes(F). points [S,3]; vertices are scaled v*vscale+voffset first
+ * (eval_3D.py:252-255). */
+size_t zs_mesh_sample_ws_bytes(int F);
+int zs_mesh_sample(const float* verts, const int32_t* faces, int V, int F, float vscale, float voffset,
+                   int S, uint64_t seed, void* ws, float* points, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEROSHAPE_B200_H */

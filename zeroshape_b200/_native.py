@@ -1,0 +1,99 @@
+"""ctypes binding of libzeroshape_b200.so (the C ABI declared in include/zeroshape_b200.h).
+
+The product has NO fallback: if the library is missing or a symbol is absent, importing this
+module raises.  Nothing here imports `oracle/`.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("ZEROSHAPE_B200_LIB", os.path.join(_HERE, "libzeroshape_b200.so"))
+
+P = c_void_p  # device pointer
+
+
+class ZsImplicitWeights(ctypes.Structure):
+    _fields_ = [
+        ("point_proj_w", P), ("point_proj_b", P),
+        ("norm1_w", P * 2), ("norm1_b", P * 2),
+        ("qkv_w", P * 2), ("qkv_b", P * 2),
+        ("proj_w", P * 2), ("proj_b", P * 2),
+        ("norm2_w", P * 2), ("norm2_b", P * 2),
+        ("fc1_w", P * 2), ("fc1_b", P * 2),
+        ("fc2_w", P * 2), ("fc2_b", P * 2),
+        ("norm_w", P), ("norm_b", P),
+        ("mlp_w", P * 9), ("mlp_b", P * 9),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/zeroshape_b200.h
+SIGNATURES = {
+    "zs_last_error": (c_char_p, []),
+    "zs_abi_version": (c_int, []),
+    "zs_device_cc": (c_int, []),
+    "zs_gemm_f32": (c_int, [P, c_int, P, c_int, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_conv2d_nhwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_layernorm_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_float, P]),
+    "zs_groupnorm_nhwc_f32": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    "zs_channel_affine_f32": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P]),
+    "zs_axpby_f32": (c_int, [P, c_float, P, c_float, P, c_int64, c_int, P]),
+    "zs_maxpool3x3s2_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_avgpool_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "zs_bilinear_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_nchw_to_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_float, P]),
+    "zs_nhwc_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    "zs_mha_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_point_attention_f32": (c_int, [P, P, P, c_int, P, P, c_float, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_float, P]),
+    "zs_dense_grid_f32": (c_int, [P, c_int, c_float, c_float, c_int, c_int, P]),
+    "zs_concat2_f32": (c_int, [P, c_int, c_int, P, c_int, c_int, c_float, P, c_int, c_int64, P]),
+    "zs_implicit_packed_bytes": (c_size_t, []),
+    "zs_implicit_pack": (c_int, [ctypes.POINTER(ZsImplicitWeights), P, P]),
+    "zs_implicit_kv_bytes": (c_size_t, [c_int, c_int]),
+    "zs_implicit_kv_pack": (c_int, [P, P, P, P, c_int, c_int, P, P]),
+    "zs_implicit_fused_fwd": (c_int, [P, P, c_int, P, c_int, c_int64, c_int, c_float, c_float, c_int, c_int,
+                                      P, c_int, c_int, P]),
+    "zs_intr_param2mtx_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "zs_unproject_ws_bytes": (c_size_t, [c_int]),
+    "zs_unproject_normalize_f32": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P]),
+    "zs_chamfer_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "zs_chamfer_nn_fwd": (c_int, [P, P, c_int, c_int, c_int, P, P, P, P, P, P]),
+    "zs_chamfer_nn_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
+    "zs_chamfer_stats": (c_int, [P, P, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P]),
+    "zs_mc_ws_bytes": (c_size_t, [c_int]),
+    "zs_mc_count": (c_int, [P, c_int, c_float, P, P, P]),
+    "zs_mc_emit": (c_int, [P, c_int, c_float, P, P, P, P]),
+    "zs_mesh_sample_ws_bytes": (c_size_t, [c_int]),
+    "zs_mesh_sample": (c_int, [P, P, c_int, c_int, c_float, c_float, c_int, c_uint64, P, P, P]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"zeroshape_b200: CUDA library not found at {LIB_PATH}. Build it with "
+            f"`python -m zeroshape_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"zeroshape_b200: {LIB_PATH} does not export `{name}` (stale build?)") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib.zs_last_error()
+        raise NativeError(f"{what or 'zeroshape_b200'} failed ({status}): {msg.decode() if msg else ''}")

@@ -1,0 +1,214 @@
+// Chamfer nearest-neighbour kernels for sm_100a.
+//
+// Replaces external/chamfer3D/chamfer3D.cu (NmDistanceKernel :12-134, NmDistanceGradKernel :155-174).
+// Contract kept: squared L2 distance to, and int32 index of, the nearest neighbour in the other cloud,
+// lowest index on ties; gradients accumulated with atomicAdd.  Differences by design:
+//   * the reference launches dim3(32,16,1)x512 -> at b=1 only 16 CTAs work; here the (query tile x
+//     target segment x batch) grid is sized to fill every SM, partial results are merged with one
+//     64-bit atomicMin on (float_bits(dist) << 32 | index) which preserves the lowest-index tie-break;
+//   * launches go to the caller's stream (the reference uses the legacy default stream);
+//   * distance arithmetic is pinned to what nvcc 12.9 emits for the reference expression
+//     `x2*x2+y2*y2+z2*z2` (chamfer3D.cu:32): fma(z2,z2, fma(x2,x2, y2*y2)) with (target - query)
+//     differences, so distances are bit-identical to the reference kernel built for sm_100a.
+#include "common.cuh"
+
+namespace zs {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_QPT = 4;                       // queries per thread
+constexpr int CH_QTILE = CH_THREADS * CH_QPT;   // 1024 queries per CTA
+constexpr int CH_TTILE = 1024;                  // targets staged in smem per step (16 KB as float4)
+
+__device__ __forceinline__ float sqdist_ref(float tx, float ty, float tz, float qx, float qy, float qz) {
+  float x2 = tx - qx, y2 = ty - qy, z2 = tz - qz;
+  return __fmaf_rn(z2, z2, __fmaf_rn(x2, x2, __fmul_rn(y2, y2)));
+}
+
+__global__ void chamfer_init_kernel(unsigned long long* keys, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = ~0ULL;
+}
+
+// grid: x = query tiles, y = target segments, z = batch
+__global__ void __launch_bounds__(CH_THREADS)
+chamfer_nn_kernel(const float* __restrict__ q, int nq, const float* __restrict__ t, int nt, int seg_len,
+                  unsigned long long* __restrict__ keys) {
+  __shared__ float4 tile[CH_TTILE];
+  const int b = blockIdx.z;
+  const float* qb = q + (int64_t)b * nq * 3;
+  const float* tb = t + (int64_t)b * nt * 3;
+  const int t_begin = blockIdx.y * seg_len;
+  const int t_end = min(nt, t_begin + seg_len);
+  float qx[CH_QPT], qy[CH_QPT], qz[CH_QPT], best[CH_QPT];
+  int besti[CH_QPT];
+#pragma unroll
+  for (int i = 0; i < CH_QPT; ++i) {
+    int qi = blockIdx.x * CH_QTILE + i * CH_THREADS + threadIdx.x;
+    bool ok = qi < nq;
+    qx[i] = ok ? qb[qi * 3 + 0] : 0.f;
+    qy[i] = ok ? qb[qi * 3 + 1] : 0.f;
+    qz[i] = ok ? qb[qi * 3 + 2] : 0.f;
+    best[i] = INFINITY;
+    besti[i] = 0x7fffffff;
+  }
+  for (int t0 = t_begin; t0 < t_end; t0 += CH_TTILE) {
+    int cnt = min(CH_TTILE, t_end - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += CH_THREADS) {
+      const float* p = tb + (int64_t)(t0 + j) * 3;
+      tile[j] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      float4 tp = tile[j];
+#pragma unroll
+      for (int i = 0; i < CH_QPT; ++i) {
+        float d = sqdist_ref(tp.x, tp.y, tp.z, qx[i], qy[i], qz[i]);
+        if (d < best[i]) { best[i] = d; besti[i] = t0 + j; }   // strict <: lowest index wins inside a segment
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CH_QPT; ++i) {
+    int qi = blockIdx.x * CH_QTILE + i * CH_THREADS + threadIdx.x;
+    if (qi < nq && besti[i] != 0x7fffffff) {
+      unsigned long long key = ((unsigned long long)__float_as_uint(best[i]) << 32) | (unsigned)besti[i];
+      atomicMin(keys + (int64_t)b * nq + qi, key);
+    }
+  }
+}
+
+__global__ void chamfer_unpack_kernel(const unsigned long long* __restrict__ keys, float* __restrict__ dist,
+                                      int32_t* __restrict__ idx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long k = keys[i];
+    if (k == ~0ULL) { dist[i] = 0.f; idx[i] = 0; }   // empty target cloud: the reference leaves its zero-fill
+    else { dist[i] = __uint_as_float((unsigned)(k >> 32)); idx[i] = (int32_t)(k & 0xffffffffu); }
+  }
+}
+
+__global__ void chamfer_grad_kernel(const float* __restrict__ xyz1, int n, const float* __restrict__ xyz2, int m,
+                                    const float* __restrict__ gd1, const int32_t* __restrict__ idx1,
+                                    float* __restrict__ g1, float* __restrict__ g2) {
+  int b = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float* p1 = xyz1 + ((int64_t)b * n + j) * 3;
+    int j2 = idx1[(int64_t)b * n + j];
+    const float* p2 = xyz2 + ((int64_t)b * m + j2) * 3;
+    float g = gd1[(int64_t)b * n + j] * 2;
+    float dx = p1[0] - p2[0], dy = p1[1] - p2[1], dz = p1[2] - p2[2];
+    float* o1 = g1 + ((int64_t)b * n + j) * 3;
+    float* o2 = g2 + ((int64_t)b * m + j2) * 3;
+    atomicAdd(o1 + 0, g * dx); atomicAdd(o1 + 1, g * dy); atomicAdd(o1 + 2, g * dz);
+    atomicAdd(o2 + 0, -(g * dx)); atomicAdd(o2 + 1, -(g * dy)); atomicAdd(o2 + 2, -(g * dz));
+  }
+}
+
+// one CTA per (batch, which cloud): sqrt-mean and strict-< threshold fractions
+__global__ void chamfer_stats_kernel(const float* __restrict__ sq1, const float* __restrict__ sq2, int n, int m,
+                                     const float* __restrict__ thr, int T, int squared, float* __restrict__ mean1,
+                                     float* __restrict__ mean2, float* __restrict__ frac1, float* __restrict__ frac2) {
+  const int b = blockIdx.x, which = blockIdx.y;
+  const float* sq = which == 0 ? sq1 + (int64_t)b * n : sq2 + (int64_t)b * m;
+  const int cnt = which == 0 ? n : m;
+  __shared__ float red[32];
+  __shared__ float sthr[16];
+  if (threadIdx.x < T) sthr[threadIdx.x] = thr[threadIdx.x];
+  __syncthreads();
+  float sum = 0.f;
+  int hits[16];
+  for (int k = 0; k < 16; ++k) hits[k] = 0;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    float d = squared ? sqrtf(sq[i]) : sq[i];
+    sum += d;
+    for (int k = 0; k < T; ++k) hits[k] += d < sthr[k];
+  }
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float tot = 0.f;
+    if (threadIdx.x < 32) {
+      tot = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      tot = warp_sum(tot);
+    }
+    return tot;
+  };
+  float tot = block_sum(sum);
+  if (threadIdx.x == 0) (which == 0 ? mean1 : mean2)[b] = tot / (float)cnt;
+  for (int k = 0; k < T; ++k) {
+    float h = block_sum((float)hits[k]);
+    if (threadIdx.x == 0) (which == 0 ? frac1 : frac2)[(int64_t)b * T + k] = h / (float)cnt;
+  }
+}
+
+static int nn_one_direction(const float* q, int nq, const float* t, int nt, int b, unsigned long long* keys,
+                            float* dist, int32_t* idx, cudaStream_t st) {
+  int64_t tot = (int64_t)b * nq;
+  int g = (int)((tot + 255) / 256);
+  if (g > 4096) g = 4096;
+  chamfer_init_kernel<<<g, 256, 0, st>>>(keys, tot);
+  if (nt > 0) {
+    int qtiles = (nq + CH_QTILE - 1) / CH_QTILE;
+    int want = (4 * sm_count() + b * qtiles - 1) / (b * qtiles);
+    int max_segs = (nt + 255) / 256;
+    int segs = want < 1 ? 1 : (want > max_segs ? max_segs : want);
+    int seg_len = (nt + segs - 1) / segs;
+    segs = (nt + seg_len - 1) / seg_len;
+    dim3 grid(qtiles, segs, b);
+    chamfer_nn_kernel<<<grid, CH_THREADS, 0, st>>>(q, nq, t, nt, seg_len, keys);
+  }
+  chamfer_unpack_kernel<<<g, 256, 0, st>>>(keys, dist, idx, tot);
+  return 0;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" size_t zs_chamfer_ws_bytes(int b, int n, int m) {
+  return (size_t)b * ((size_t)(n > 0 ? n : 0) + (size_t)(m > 0 ? m : 0)) * sizeof(unsigned long long) + 16;
+}
+
+extern "C" int zs_chamfer_nn_fwd(const float* xyz1, const float* xyz2, int b, int n, int m,
+                                 float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, void* ws, void* stream) {
+  ZS_REQUIRE(b >= 0 && n >= 0 && m >= 0, "zs_chamfer_nn_fwd: negative size");
+  if (b == 0) return ZS_OK;
+  ZS_REQUIRE((n == 0 || (xyz1 && dist1 && idx1)) && (m == 0 || (xyz2 && dist2 && idx2)), "zs_chamfer_nn_fwd: null pointer");
+  ZS_REQUIRE(ws != nullptr, "zs_chamfer_nn_fwd: workspace is NULL (zs_chamfer_ws_bytes)");
+  ZS_REQUIRE(b <= 65535, "zs_chamfer_nn_fwd: batch %d > 65535", b);
+  unsigned long long* k1 = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(ws) + 7) & ~uintptr_t(7));
+  unsigned long long* k2 = k1 + (size_t)b * n;
+  cudaStream_t st = as_stream(stream);
+  if (n > 0) nn_one_direction(xyz1, n, xyz2, m, b, k1, dist1, idx1, st);
+  if (m > 0) nn_one_direction(xyz2, m, xyz1, n, b, k2, dist2, idx2, st);
+  ZS_CUDA_CHECK_LAUNCH("zs_chamfer_nn_fwd");
+  return ZS_OK;
+}
+
+extern "C" int zs_chamfer_nn_bwd(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                                 const int32_t* idx1, const int32_t* idx2, int b, int n, int m,
+                                 float* gradxyz1, float* gradxyz2, void* stream) {
+  ZS_REQUIRE(b >= 0 && n >= 0 && m >= 0, "zs_chamfer_nn_bwd: negative size");
+  if (b == 0 || n == 0 || m == 0) return ZS_OK;
+  ZS_REQUIRE(xyz1 && xyz2 && graddist1 && graddist2 && idx1 && idx2 && gradxyz1 && gradxyz2, "zs_chamfer_nn_bwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  dim3 g1((n + 255) / 256, b), g2((m + 255) / 256, b);
+  chamfer_grad_kernel<<<g1, 256, 0, st>>>(xyz1, n, xyz2, m, graddist1, idx1, gradxyz1, gradxyz2);
+  chamfer_grad_kernel<<<g2, 256, 0, st>>>(xyz2, m, xyz1, n, graddist2, idx2, gradxyz2, gradxyz1);
+  ZS_CUDA_CHECK_LAUNCH("zs_chamfer_nn_bwd");
+  return ZS_OK;
+}
+
+extern "C" int zs_chamfer_stats(const float* sqdist1, const float* sqdist2, int b, int n, int m,
+                                const float* thresholds, int T, int squared, float* mean1, float* mean2, float* frac1, float* frac2,
+                                void* stream) {
+  ZS_REQUIRE(sqdist1 && sqdist2 && mean1 && mean2 && b > 0 && n > 0 && m > 0, "zs_chamfer_stats: bad args");
+  ZS_REQUIRE(T >= 0 && T <= 16 && (T == 0 || (thresholds && frac1 && frac2)), "zs_chamfer_stats: 0 <= T <= 16");
+  dim3 grid(b, 2);
+  chamfer_stats_kernel<<<grid, 512, 0, as_stream(stream)>>>(sqdist1, sqdist2, n, m, thresholds, T, squared, mean1, mean2, frac1, frac2);
+  ZS_CUDA_CHECK_LAUNCH("zs_chamfer_stats");
+  return ZS_OK;
+}

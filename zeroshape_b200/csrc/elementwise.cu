@@ -1,0 +1,347 @@
+// HBM-bound helpers: normalisations, pooling, resampling, layout changes, error plumbing.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace zs {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static thread_local int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// ---- LayerNorm: one warp per row ------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
+                                 const float* __restrict__ b, float* __restrict__ y, int ldy, int rows, int cols,
+                                 float eps) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += xr[c];
+  float mean = warp_sum(s) / cols;
+  float v = 0.f;
+  for (int c = lane; c < cols; c += 32) { float d = xr[c] - mean; v += d * d; }
+  float rstd = rsqrtf(warp_sum(v) / cols + eps);
+  float* yr = y + (int64_t)row * ldy;
+  for (int c = lane; c < cols; c += 32) yr[c] = (xr[c] - mean) * rstd * g[c] + b[c];
+}
+
+// ---- GroupNorm NHWC: one CTA per (b, group): two-pass over HW x (C/groups) -------------------
+__global__ void groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const float* __restrict__ res,
+                                      float* __restrict__ y, int HW, int C, int groups, float eps, int relu) {
+  int b = blockIdx.x / groups, gi = blockIdx.x % groups;
+  int cg = C / groups;
+  const float* xb = x + (int64_t)b * HW * C + gi * cg;
+  float* yb = y + (int64_t)b * HW * C + gi * cg;
+  const float* rb = res ? res + (int64_t)b * HW * C + gi * cg : nullptr;
+  int64_t n = (int64_t)HW * cg;
+  __shared__ float sh[34];
+  // pass 1: mean
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += xb[(i / cg) * C + (i % cg)];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sh[32] = t / (float)n;
+  }
+  __syncthreads();
+  float mean = sh[32];
+  float v = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { float d = xb[(i / cg) * C + (i % cg)] - mean; v += d * d; }
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) sh[33] = rsqrtf(t / (float)n + eps);
+  }
+  __syncthreads();
+  float rstd = sh[33];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    int c = (int)(i % cg);
+    int64_t off = (i / cg) * C + c;
+    float o = (xb[off] - mean) * rstd * gamma[gi * cg + c] + beta[gi * cg + c];
+    if (rb) o += rb[off];
+    yb[off] = relu ? fmaxf(o, 0.f) : o;
+  }
+}
+
+__global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                      const float* __restrict__ sh, const float* __restrict__ res,
+                                      float* __restrict__ y, int64_t n, int C, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float v = x[i] * sc[c] + sh[c];
+    if (res) v += res[i];
+    y[i] = apply_act(v, act);
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+                             float* __restrict__ y, int64_t n, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = a[i] * alpha;
+    if (b) v += b[i] * beta;
+    y[i] = apply_act(v, act);
+  }
+}
+
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C,
+                                    int pt, int pl, int OH, int OW) {
+  int64_t total = (int64_t)B * OH * OW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int ow = (int)(t % OW); t /= OW;
+    int oh = (int)(t % OH);
+    int b = (int)(t / OH);
+    float m = -INFINITY;
+    for (int kh = 0; kh < 3; ++kh) {
+      int ih = oh * 2 - pt + kh;
+      if ((unsigned)ih >= (unsigned)H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int iw = ow * 2 - pl + kw;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        m = fmaxf(m, x[(((int64_t)b * H + ih) * W + iw) * C + c]);
+      }
+    }
+    y[i] = m;
+  }
+}
+
+__global__ void avgpool_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  int b = blockIdx.y;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* xb = x + (int64_t)b * HW * C + c;
+  float s = 0.f;
+  for (int i = 0; i < HW; ++i) s += xb[(int64_t)i * C];
+  y[(int64_t)b * C + c] = s / (float)HW;
+}
+
+// PyTorch upsample_bilinear2d source-index rules (aten/native/UpSample.h):
+//   align_corners: src = dst * (in-1)/(out-1)      (0 if out==1)
+//   else         : src = max((dst+0.5)*in/out - 0.5, 0)
+__device__ __forceinline__ void bilinear_src(int dst, int in, int out, int align, int& i0, int& i1, float& l1) {
+  float src;
+  if (align) {
+    float sc = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = sc * dst;
+  } else {
+    float sc = (float)in / (float)out;
+    src = sc * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  l1 = src - (float)i0;
+}
+
+__global__ void bilinear_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C,
+                                     int OH, int OW, int align) {
+  int64_t total = (int64_t)B * OH * OW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int ow = (int)(t % OW); t /= OW;
+    int oh = (int)(t % OH);
+    int b = (int)(t / OH);
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_src(oh, H, OH, align, h0, h1, lh);
+    bilinear_src(ow, W, OW, align, w0, w1, lw);
+    const float* xb = x + (int64_t)b * H * W * C + c;
+    float v00 = xb[((int64_t)h0 * W + w0) * C], v01 = xb[((int64_t)h0 * W + w1) * C];
+    float v10 = xb[((int64_t)h1 * W + w0) * C], v11 = xb[((int64_t)h1 * W + w1) * C];
+    float hh0 = 1.f - lh, ww0 = 1.f - lw;
+    y[i] = hh0 * (ww0 * v00 + lw * v01) + lh * (ww0 * v10 + lw * v11);
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W,
+                                    float scale, float shift) {
+  int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int b = (int)(t / H);
+    y[i] = x[(((int64_t)b * C + c) * H + h) * W + w] * scale + shift;
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W) {
+  int64_t total = (int64_t)B * C * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    int64_t t = i / W;
+    int h = (int)(t % H); t /= H;
+    int c = (int)(t % C);
+    int b = (int)(t / C);
+    y[i] = x[(((int64_t)b * H + h) * W + w) * C + c];
+  }
+}
+
+__global__ void concat2_kernel(const float* __restrict__ a, int lda, int Ca, const float* __restrict__ b, int ldb, int Cb,
+                               float s, float* __restrict__ y, int ldy, int64_t rows) {
+  int Ct = Ca + Cb;
+  int64_t total = rows * Ct;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % Ct);
+    int64_t r = i / Ct;
+    float v = c < Ca ? a[r * lda + c] : b[r * ldb + (c - Ca)];
+    y[r * ldy + c] = v / s;
+  }
+}
+
+// torch.linspace(start,end,steps) fp32 CPU/CUDA kernel semantics: step=(end-start)/(steps-1);
+// i < steps/2 ? start + step*i : end - step*(steps-1-i)
+__global__ void dense_grid_kernel(float* __restrict__ out, int n, float rmin, float rmax, int x0, int x1) {
+  int64_t total = (int64_t)(x1 - x0) * n * n;
+  float step = (rmax - rmin) / (float)(n - 1);
+  int half = n / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int k = (int)(i % n);
+    int64_t t = i / n;
+    int j = (int)(t % n);
+    int ii = (int)(t / n) + x0;
+    auto lin = [&](int q) { return q < half ? rmin + step * (float)q : rmax - step * (float)(n - 1 - q); };
+    out[i * 3 + 0] = lin(ii);
+    out[i * 3 + 1] = lin(j);
+    out[i * 3 + 2] = lin(k);
+  }
+}
+
+static inline int grid_for(int64_t n, int threads = 256) {
+  int64_t g = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" const char* zs_last_error(void) { return zs::g_err; }
+extern "C" int zs_abi_version(void) { return 1; }
+extern "C" int zs_device_cc(void) {
+  int dev = 0, maj = 0, min = 0;
+  ZS_CUDA_CALL(cudaGetDevice(&dev));
+  ZS_CUDA_CALL(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  ZS_CUDA_CALL(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  return maj * 10 + min;
+}
+
+extern "C" int zs_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                                int rows, int cols, float eps, void* stream) {
+  ZS_REQUIRE(x && gamma && beta && y && rows >= 0 && cols > 0, "zs_layernorm_f32: bad args");
+  if (rows == 0) return ZS_OK;
+  int wpb = 8;
+  layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, as_stream(stream)>>>(x, ldx, gamma, beta, y, ldy, rows, cols, eps);
+  ZS_CUDA_CHECK_LAUNCH("zs_layernorm_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_groupnorm_nhwc_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
+                                     int B, int HW, int C, int groups, float eps, int relu, void* stream) {
+  ZS_REQUIRE(x && gamma && beta && y && B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0,
+             "zs_groupnorm_nhwc_f32: bad args");
+  groupnorm_nhwc_kernel<<<B * groups, 512, 0, as_stream(stream)>>>(x, gamma, beta, res, y, HW, C, groups, eps, relu);
+  ZS_CUDA_CHECK_LAUNCH("zs_groupnorm_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_channel_affine_f32(const float* x, const float* scale, const float* shift, const float* res,
+                                     float* y, int64_t rows, int C, int act, void* stream) {
+  ZS_REQUIRE(x && scale && shift && y && rows >= 0 && C > 0, "zs_channel_affine_f32: bad args");
+  if (rows == 0) return ZS_OK;
+  channel_affine_kernel<<<grid_for(rows * C), 256, 0, as_stream(stream)>>>(x, scale, shift, res, y, rows * C, C, act);
+  ZS_CUDA_CHECK_LAUNCH("zs_channel_affine_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_axpby_f32(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, int act, void* stream) {
+  ZS_REQUIRE(a && y && n >= 0, "zs_axpby_f32: bad args");
+  if (n == 0) return ZS_OK;
+  axpby_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(a, alpha, b, beta, y, n, act);
+  ZS_CUDA_CHECK_LAUNCH("zs_axpby_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int pad_top, int pad_left,
+                                        int OH, int OW, void* stream) {
+  ZS_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_maxpool3x3s2_nhwc_f32: bad args");
+  maxpool3x3s2_kernel<<<grid_for((int64_t)B * OH * OW * C), 256, 0, as_stream(stream)>>>(x, y, B, H, W, C, pad_top, pad_left, OH, OW);
+  ZS_CUDA_CHECK_LAUNCH("zs_maxpool3x3s2_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_avgpool_nhwc_f32(const float* x, float* y, int B, int HW, int C, void* stream) {
+  ZS_REQUIRE(x && y && B > 0 && HW > 0 && C > 0, "zs_avgpool_nhwc_f32: bad args");
+  dim3 grid((C + 127) / 128, B);
+  avgpool_nhwc_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, y, HW, C);
+  ZS_CUDA_CHECK_LAUNCH("zs_avgpool_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_bilinear_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int OH, int OW,
+                                    int align_corners, void* stream) {
+  ZS_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_bilinear_nhwc_f32: bad args");
+  bilinear_nhwc_kernel<<<grid_for((int64_t)B * OH * OW * C), 256, 0, as_stream(stream)>>>(x, y, B, H, W, C, OH, OW, align_corners);
+  ZS_CUDA_CHECK_LAUNCH("zs_bilinear_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, float scale, float shift, void* stream) {
+  ZS_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "zs_nchw_to_nhwc_f32: bad args");
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)B * C * H * W), 256, 0, as_stream(stream)>>>(x, y, B, C, H, W, scale, shift);
+  ZS_CUDA_CHECK_LAUNCH("zs_nchw_to_nhwc_f32");
+  return ZS_OK;
+}
+extern "C" int zs_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  ZS_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0, "zs_nhwc_to_nchw_f32: bad args");
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)B * C * H * W), 256, 0, as_stream(stream)>>>(x, y, B, C, H, W);
+  ZS_CUDA_CHECK_LAUNCH("zs_nhwc_to_nchw_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_concat2_f32(const float* a, int lda, int Ca, const float* b, int ldb, int Cb, float s, float* y, int ldy,
+                              int64_t rows, void* stream) {
+  ZS_REQUIRE(a && b && y && Ca > 0 && Cb > 0 && rows >= 0 && ldy >= Ca + Cb, "zs_concat2_f32: bad args");
+  if (rows == 0) return ZS_OK;
+  concat2_kernel<<<grid_for(rows * (Ca + Cb)), 256, 0, as_stream(stream)>>>(a, lda, Ca, b, ldb, Cb, s, y, ldy, rows);
+  ZS_CUDA_CHECK_LAUNCH("zs_concat2_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_dense_grid_f32(float* out, int n, float rmin, float rmax, int x0, int x1, void* stream) {
+  ZS_REQUIRE(out && n >= 2 && x0 >= 0 && x1 <= n && x0 <= x1, "zs_dense_grid_f32: bad args");
+  if (x0 == x1) return ZS_OK;
+  dense_grid_kernel<<<grid_for((int64_t)(x1 - x0) * n * n), 256, 0, as_stream(stream)>>>(out, n, rmin, rmax, x0, x1);
+  ZS_CUDA_CHECK_LAUNCH("zs_dense_grid_f32");
+  return ZS_OK;
+}

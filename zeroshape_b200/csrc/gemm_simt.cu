@@ -1,0 +1,302 @@
+// fp32 FFMA GEMM / implicit-GEMM convolution with fused epilogue.
+//
+// This is the bit-faithful (plain fp32) path of the library: every nn.Linear / nn.Conv2d of the
+// hot path can run through it with results that differ from the PyTorch fp32 reference only by
+// summation order.  It is the first correct CUDA path of every stage and the in-library ground
+// truth the tcgen05 kernels are compared against on the GPU.
+//
+//   C[m,n] = epi( sum_k A(m,k) * W[n,k] )         A(m,k) either a dense row-major matrix or an
+//                                                  on-the-fly NHWC im2col gather.
+// Tiling: 128x128x16 CTA tile, 256 threads, 8x8 register tile per thread, double-buffered smem.
+#include "common.cuh"
+
+namespace zs {
+
+struct DenseA {
+  const float* A;
+  int lda;
+  int M, K;
+  bool vec;  // lda%4==0 && K%4==0 && 16B aligned
+  struct Row { const float* p; bool ok; };
+  __device__ __forceinline__ Row row(int m) const { return {A + (int64_t)m * lda, m < M}; }
+  __device__ __forceinline__ float4 load4(const Row& r, int k) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!r.ok) return v;
+    if (vec) {
+      if (k < K) v = __ldg(reinterpret_cast<const float4*>(r.p + k));
+    } else {
+      if (k + 0 < K) v.x = __ldg(r.p + k + 0);
+      if (k + 1 < K) v.y = __ldg(r.p + k + 1);
+      if (k + 2 < K) v.z = __ldg(r.p + k + 2);
+      if (k + 3 < K) v.w = __ldg(r.p + k + 3);
+    }
+    return v;
+  }
+};
+
+struct ConvA {
+  const float* x;
+  int B, H, W, Cin, KH, KW, stride, pad_top, pad_left, OH, OW;
+  int M, K;
+  bool vec;  // Cin%4==0
+  bool pre_relu;
+  struct Row { int b, ih0, iw0; bool ok; };
+  __device__ __forceinline__ Row row(int m) const {
+    Row r;
+    r.ok = m < M;
+    int ow = m % OW;
+    int t = m / OW;
+    int oh = t % OH;
+    r.b = t / OH;
+    r.ih0 = oh * stride - pad_top;
+    r.iw0 = ow * stride - pad_left;
+    return r;
+  }
+  __device__ __forceinline__ float elem(const Row& r, int k) const {
+    if (k >= K) return 0.f;
+    int ci = k % Cin;
+    int t = k / Cin;
+    int kw = t % KW, kh = t / KW;
+    int ih = r.ih0 + kh, iw = r.iw0 + kw;
+    if ((unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) return 0.f;
+    float v = __ldg(x + (((int64_t)r.b * H + ih) * W + iw) * Cin + ci);
+    return pre_relu ? fmaxf(v, 0.f) : v;
+  }
+  __device__ __forceinline__ float4 load4(const Row& r, int k) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!r.ok) return v;
+    if (vec) {
+      if (k >= K) return v;
+      int ci = k % Cin;
+      int t = k / Cin;
+      int kw = t % KW, kh = t / KW;
+      int ih = r.ih0 + kh, iw = r.iw0 + kw;
+      if ((unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) return v;
+      v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)r.b * H + ih) * W + iw) * Cin + ci));
+      if (pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    } else {
+      v.x = elem(r, k); v.y = elem(r, k + 1); v.z = elem(r, k + 2); v.w = elem(r, k + 3);
+    }
+    return v;
+  }
+};
+
+struct Epilogue {
+  const float* bias;
+  const float* res;
+  int ldres;
+  int res_mode;
+  float* C;
+  int ldc;
+  int act;
+};
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8, NTHREADS = 256;
+constexpr int PADM = 4;  // smem row padding (floats)
+
+template <class ALoader>
+__global__ void __launch_bounds__(NTHREADS, 2)
+gemm_f32_kernel(ALoader a, const float* __restrict__ Wt, int ldw, bool wvec, int M, int N, int K, Epilogue ep) {
+  __shared__ __align__(16) float As[2][BK][BM + PADM];
+  __shared__ __align__(16) float Bs[2][BK][BN + PADM];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // loader mapping: each thread loads 2 float4 of A and 2 of W per k-tile
+  const int lrow = tid >> 2;         // 0..63
+  const int lk = (tid & 3) * 4;      // 0,4,8,12
+  typename ALoader::Row ar0 = a.row(m0 + lrow), ar1 = a.row(m0 + lrow + 64);
+  DenseA wl{Wt, ldw, N, K, wvec};
+  DenseA::Row wr0 = wl.row(n0 + lrow), wr1 = wl.row(n0 + lrow + 64);
+
+  const int tx = tid & 15, ty = tid >> 4;  // 16x16 thread grid, each 8x8 outputs (split 4+4 for conflict-free LDS.128)
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra0, ra1, rb0, rb1;
+  auto gload = [&](int k0) {
+    ra0 = a.load4(ar0, k0 + lk);
+    ra1 = a.load4(ar1, k0 + lk);
+    rb0 = wl.load4(wr0, k0 + lk);
+    rb1 = wl.load4(wr1, k0 + lk);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra0.x; As[buf][lk + 1][lrow] = ra0.y; As[buf][lk + 2][lrow] = ra0.z; As[buf][lk + 3][lrow] = ra0.w;
+    As[buf][lk + 0][lrow + 64] = ra1.x; As[buf][lk + 1][lrow + 64] = ra1.y; As[buf][lk + 2][lrow + 64] = ra1.z; As[buf][lk + 3][lrow + 64] = ra1.w;
+    Bs[buf][lk + 0][lrow] = rb0.x; Bs[buf][lk + 1][lrow] = rb0.y; Bs[buf][lk + 2][lrow] = rb0.z; Bs[buf][lk + 3][lrow] = rb0.w;
+    Bs[buf][lk + 0][lrow + 64] = rb1.x; Bs[buf][lk + 1][lrow + 64] = rb1.y; Bs[buf][lk + 2][lrow + 64] = rb1.z; Bs[buf][lk + 3][lrow + 64] = rb1.w;
+  };
+
+  const int nk = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 64]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 64]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: rows m0 + ty*4 + {0..3} and +64; cols n0 + tx*4 + {0..3} and +64
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+    if (m >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      int nb = n0 + tx * 4 + jh * 64;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = nb + j;
+        if (n >= N) continue;
+        float v = acc[i][jh * 4 + j];
+        if (ep.bias) v += __ldg(ep.bias + n);
+        if (ep.res_mode == ZS_RES_BEFORE_ACT) v += __ldg(ep.res + (int64_t)m * ep.ldres + n);
+        v = apply_act(v, ep.act);
+        if (ep.res_mode == ZS_RES_AFTER_ACT) v += __ldg(ep.res + (int64_t)m * ep.ldres + n);
+        ep.C[(int64_t)m * ep.ldc + n] = v;
+      }
+    }
+  }
+}
+
+// small-N / small-M friendly variant: 32x32 tile, 4x... used when the 128x128 grid would leave
+// most SMs idle (e.g. M=197 tokens) -- 64x64x16 tile, 256 threads, 4x4 per thread.
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+template <class ALoader>
+__global__ void __launch_bounds__(256, 3)
+gemm_f32_small_kernel(ALoader a, const float* __restrict__ Wt, int ldw, bool wvec, int M, int N, int K, Epilogue ep) {
+  __shared__ __align__(16) float As[2][SBK][SBM + PADM];
+  __shared__ __align__(16) float Bs[2][SBK][SBN + PADM];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  const int lrow = tid >> 2;     // 0..63
+  const int lk = (tid & 3) * 4;  // 0..12
+  typename ALoader::Row ar0 = a.row(m0 + lrow);
+  DenseA wl{Wt, ldw, N, K, wvec};
+  DenseA::Row wr0 = wl.row(n0 + lrow);
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 ra0, rb0;
+  auto gload = [&](int k0) { ra0 = a.load4(ar0, k0 + lk); rb0 = wl.load4(wr0, k0 + lk); };
+  auto sstore = [&](int buf) {
+    As[buf][lk + 0][lrow] = ra0.x; As[buf][lk + 1][lrow] = ra0.y; As[buf][lk + 2][lrow] = ra0.z; As[buf][lk + 3][lrow] = ra0.w;
+    Bs[buf][lk + 0][lrow] = rb0.x; Bs[buf][lk + 1][lrow] = rb0.y; Bs[buf][lk + 2][lrow] = rb0.z; Bs[buf][lk + 3][lrow] = rb0.w;
+  };
+  const int nk = (K + SBK - 1) / SBK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * SBK);
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      float av[4] = {a0.x, a0.y, a0.z, a0.w};
+      float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ep.bias) v += __ldg(ep.bias + n);
+      if (ep.res_mode == ZS_RES_BEFORE_ACT) v += __ldg(ep.res + (int64_t)m * ep.ldres + n);
+      v = apply_act(v, ep.act);
+      if (ep.res_mode == ZS_RES_AFTER_ACT) v += __ldg(ep.res + (int64_t)m * ep.ldres + n);
+      ep.C[(int64_t)m * ep.ldc + n] = v;
+    }
+  }
+}
+
+template <class ALoader>
+static int launch_gemm(const ALoader& a, const float* W, int ldw, int M, int N, int K, const Epilogue& ep,
+                       cudaStream_t st, const char* what) {
+  bool wvec = (ldw % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  long big_ctas = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (big_ctas >= 2L * sm_count()) {
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    gemm_f32_kernel<ALoader><<<grid, NTHREADS, 0, st>>>(a, W, ldw, wvec, M, N, K, ep);
+  } else {
+    dim3 grid((N + SBN - 1) / SBN, (M + SBM - 1) / SBM);
+    gemm_f32_small_kernel<ALoader><<<grid, 256, 0, st>>>(a, W, ldw, wvec, M, N, K, ep);
+  }
+  ZS_CUDA_CHECK_LAUNCH(what);
+  return ZS_OK;
+}
+
+}  // namespace zs
+
+extern "C" int zs_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                           const float* res, int ldres, int res_mode, float* C, int ldc,
+                           int M, int N, int K, int act, void* stream) {
+  using namespace zs;
+  ZS_REQUIRE(A && W && C, "zs_gemm_f32: null pointer");
+  ZS_REQUIRE(M >= 0 && N > 0 && K > 0, "zs_gemm_f32: bad shape M=%d N=%d K=%d", M, N, K);
+  ZS_REQUIRE(lda >= K && ldw >= K && ldc >= N, "zs_gemm_f32: bad leading dims");
+  ZS_REQUIRE(res_mode == ZS_RES_NONE || res != nullptr, "zs_gemm_f32: residual requested but res==NULL");
+  if (M == 0) return ZS_OK;
+  DenseA a{A, lda, M, K, (lda % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0)};
+  Epilogue ep{bias, res, ldres, res_mode, C, ldc, act};
+  return launch_gemm(a, W, ldw, M, N, K, ep, as_stream(stream), "zs_gemm_f32");
+}
+
+extern "C" int zs_conv2d_nhwc_f32(const float* x, int B, int H, int W, int Cin,
+                                  const float* w, const float* bias, const float* res, int res_mode,
+                                  float* y, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
+                                  int OH, int OW, int act, int pre_relu, void* stream) {
+  using namespace zs;
+  ZS_REQUIRE(x && w && y, "zs_conv2d_nhwc_f32: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_f32: bad shape");
+  ZS_REQUIRE(res_mode == ZS_RES_NONE || res != nullptr, "zs_conv2d_nhwc_f32: residual requested but res==NULL");
+  int64_t M64 = (int64_t)B * OH * OW;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_f32: too many output pixels");
+  int M = (int)M64, K = KH * KW * Cin;
+  Epilogue ep{bias, res, Cout, res_mode, y, Cout, act};
+  if (KH == 1 && KW == 1 && stride == 1 && pad_top == 0 && pad_left == 0 && !pre_relu) {
+    DenseA a{x, Cin, M, K, (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)};
+    return launch_gemm(a, w, K, M, Cout, K, ep, as_stream(stream), "zs_conv2d_nhwc_f32(1x1)");
+  }
+  ConvA a{x, B, H, W, Cin, KH, KW, stride, pad_top, pad_left, OH, OW, M, K,
+          (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0), pre_relu != 0};
+  return launch_gemm(a, w, K, M, Cout, K, ep, as_stream(stream), "zs_conv2d_nhwc_f32");
+}

@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's `model/shape/implicit.py` (same class name, constructor
+arguments, parameter names/shapes and forward contract), with all math in the CUDA library.
+
+    Implicit.forward(latent_depth, latent_semantic, points_3D) -> (logits [B,P], attn [B,P,L])
+                                                   (reference: model/shape/implicit.py:251-288)
+
+B200-first restructuring (results identical to the reference's):
+  * the latent tokens never attend to the query points (implicit.py:65-71), so everything on the
+    latent side -- latent_proj, +pos_embed, block-0 self-attention/MLP over the 197 latents and the
+    K/V of both blocks -- is computed ONCE per image (`prepare_latents`) instead of once per grid
+    slice (utils/eval_3D.py:37-43 calls the whole module 129 times);
+  * the query-point side runs either through the fused tcgen05 kernel (`engine="fused"`) or through
+    the chain of plain-fp32 kernels (`engine="f32"`, the bit-faithful path used for parity pinning);
+  * `grid_occupancy` generates the (N+1)^3 query points on the fly (no [B,N,N,N,3] tensor).
+
+Inference only in this revision: calling it with autograd enabled on inputs that require grad
+raises NotImplementedError (training path = SURVEY.md section 8 row a13, scheduled next).
+"""
+import math
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._native import lib, check, ZsImplicitWeights
+
+SQRT2 = float(np.sqrt(2))
+
+
+def _sincos_2d(dim, grid, cls_token=True):
+    """Fixed 2-D sin-cos position table (reference: utils/pos_embed.py:21-68)."""
+    def axis(d, pos):
+        omega = 1.0 / 10000 ** (np.arange(d // 2, dtype=np.float32) / (d / 2.0))
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+    g = np.arange(grid, dtype=np.float32)
+    mesh = np.stack(np.meshgrid(g, g), axis=0).reshape(2, 1, grid, grid)
+    emb = np.concatenate([axis(dim // 2, mesh[0]), axis(dim // 2, mesh[1])], axis=1)
+    return np.concatenate([np.zeros([1, dim]), emb], axis=0) if cls_token else emb
+
+
+class _Holder(nn.Module):
+    """Parameter container; never called."""
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container")
+
+
+def _block_params(dim, mlp_ratio, norm_layer):
+    blk = _Holder()
+    blk.norm1 = norm_layer(dim)
+    blk.attn = _Holder()
+    blk.attn.qkv = nn.Linear(dim, dim * 3, bias=True)
+    blk.attn.proj = nn.Linear(dim, dim)
+    blk.norm2 = norm_layer(dim)
+    blk.mlp = _Holder()
+    blk.mlp.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
+    blk.mlp.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
+    return blk
+
+
+class Implicit(nn.Module):
+    """Implicit occupancy decoder conditioned on depth latents (reference class of the same name,
+    model/shape/implicit.py:186-288).  Constructor signature kept."""
+
+    def __init__(self, num_patches, latent_dim=768, semantic=False, n_channels=512, n_blocks_attn=2,
+                 n_layers_mlp=6, num_heads=16, posenc_3D=0, mlp_ratio=4.,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_path=0.1, skip_in=[], pos_perlayer=True):
+        super().__init__()
+        if semantic:
+            raise NotImplementedError("semantic (RGB) branch is disabled in the shipped config (options/shape.yaml:32)")
+        if posenc_3D != 0:
+            raise NotImplementedError("posenc_3D != 0 is not used by the shipped config (options/shape.yaml:43)")
+        if n_layers_mlp <= 0:
+            raise NotImplementedError("pred_head variant (mlp_layers=0) is not used by the shipped config")
+        self.num_patches, self.pos_perlayer, self.semantic = num_patches, pos_perlayer, semantic
+        self.num_heads, self.n_channels, self.skip_in = num_heads, n_channels, list(skip_in)
+        self.drop_path = drop_path
+        self.point_proj = _Holder()
+        self.point_proj.proj = nn.Linear(3, n_channels)
+        self.latent_proj = nn.Linear(latent_dim, n_channels, bias=True)
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, n_channels), requires_grad=False)
+        self.blocks_attn = nn.ModuleList([_block_params(n_channels, mlp_ratio, norm_layer) for _ in range(n_blocks_attn)])
+        self.norm = norm_layer(n_channels)
+        dims = [3 + n_channels] + [n_channels] * n_layers_mlp + [1]
+        self.impl_mlp = _Holder()
+        self.impl_mlp.layers = nn.ModuleList([
+            nn.Linear(dims[l] + (dims[0] if l in self.skip_in else 0), dims[l + 1]) for l in range(len(dims) - 1)])
+        self.engine = "auto"          # "auto" | "fused" | "f32"
+        self.precision = "bf16x3"     # fused-engine operand precision: "bf16x3" (parity) | "bf16" (fast)
+        self.point_chunk = 1 << 16    # query points per pass of the f32 engine
+        self._packed = None           # (version key, packed weight blob) for the fused engine
+        self.initialize_weights()
+
+    # -- init (reference: implicit.py:235-249) ---------------------------------------------------
+    def initialize_weights(self):
+        grid = int(self.num_patches ** .5)
+        self.pos_embed.data.copy_(torch.from_numpy(_sincos_2d(self.pos_embed.shape[-1], grid)).float().unsqueeze(0))
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    @staticmethod
+    def _ln(x, m):
+        return ops.layernorm(x, m.weight, m.bias, m.eps)
+
+    def _check_inference(self, *tensors):
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+            raise NotImplementedError(
+                "zeroshape_b200.Implicit: backward is not implemented in this revision (inference only); "
+                "wrap the call in torch.no_grad()")
+        if self.training and self.drop_path > 0 and torch.is_grad_enabled():
+            raise NotImplementedError("train-mode DropPath requires the training path (not in this revision)")
+
+    def prepare_latents(self, latent_depth):
+        """Per-image latent-side work -> dict with K/V views of both blocks ([B,L,C], row stride 3C)."""
+        C = self.n_channels
+        lat = ops.linear(latent_depth.float().contiguous(), self.latent_proj.weight, self.latent_proj.bias)
+        kv = []
+        nb = len(self.blocks_attn)
+        for l, blk in enumerate(self.blocks_attn):
+            if self.pos_perlayer or l == 0:
+                lat = ops.axpby(lat, 1.0, self.pos_embed.expand_as(lat).contiguous(), 1.0)
+            qkv = ops.linear(self._ln(lat, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias)
+            kv.append((qkv[..., C:2 * C], qkv[..., 2 * C:]))
+            if l == nb - 1:
+                break
+            att = ops.mha(qkv, self.num_heads)
+            lat = ops.linear(att, blk.attn.proj.weight, blk.attn.proj.bias, res=lat)
+            h = ops.linear(self._ln(lat, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
+            lat = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=lat)
+        return {"kv": kv, "B": latent_depth.shape[0], "L": latent_depth.shape[1]}
+
+    # -- f32 engine: chain of plain-fp32 kernels over a chunk of points ---------------------------
+    def _points_f32(self, lat, pts, attn_out=None):
+        """pts [B,P,3] contiguous -> logits [B,P]; optionally fills attn_out [B,P,L]."""
+        B, P, _ = pts.shape
+        C = self.n_channels
+        nb = len(self.blocks_attn)
+        x = ops.linear(pts, self.point_proj.proj.weight, self.point_proj.proj.bias)
+        for l, blk in enumerate(self.blocks_attn):
+            k_lat, v_lat = lat["kv"][l]
+            qkv = ops.linear(self._ln(x, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias)
+            a = ops.point_attention(qkv, k_lat, v_lat, self.num_heads, attn=attn_out, attn_scale=1.0 / nb,
+                                    attn_accumulate=(l > 0))
+            del qkv
+            x = ops.linear(a, blk.attn.proj.weight, blk.attn.proj.bias, res=x)
+            h = ops.linear(self._ln(x, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
+            x = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=x)
+            del h
+        feat = self._ln(x, self.norm)
+        inputs = ops.concat2(pts.reshape(B * P, 3), feat.reshape(B * P, C), 1.0)
+        h = inputs
+        n_layers = len(self.impl_mlp.layers)
+        for l, lin in enumerate(self.impl_mlp.layers):
+            if l in self.skip_in:
+                h = ops.concat2(h, inputs, SQRT2)
+            h = ops.gemm(h, lin.weight, lin.bias, act=ops.ACT_SOFTPLUS100 if l < n_layers - 1 else ops.ACT_NONE)
+        return h.reshape(B, P)
+
+    # -- fused engine ------------------------------------------------------------------------------
+    def fused_available(self):
+        return lib.zs_implicit_packed_bytes() > 0 and self.n_channels == 256 and self.num_heads == 8 \
+            and len(self.blocks_attn) == 2 and len(self.impl_mlp.layers) == 9 and self.skip_in == [2, 4, 6] \
+            and not self.pos_perlayer
+
+    def _weights_struct(self):
+        w = ZsImplicitWeights()
+        keep = []
+
+        def ptr(t):
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        w.point_proj_w, w.point_proj_b = ptr(self.point_proj.proj.weight), ptr(self.point_proj.proj.bias)
+        for l, blk in enumerate(self.blocks_attn):
+            w.norm1_w[l], w.norm1_b[l] = ptr(blk.norm1.weight), ptr(blk.norm1.bias)
+            w.qkv_w[l], w.qkv_b[l] = ptr(blk.attn.qkv.weight), ptr(blk.attn.qkv.bias)
+            w.proj_w[l], w.proj_b[l] = ptr(blk.attn.proj.weight), ptr(blk.attn.proj.bias)
+            w.norm2_w[l], w.norm2_b[l] = ptr(blk.norm2.weight), ptr(blk.norm2.bias)
+            w.fc1_w[l], w.fc1_b[l] = ptr(blk.mlp.fc1.weight), ptr(blk.mlp.fc1.bias)
+            w.fc2_w[l], w.fc2_b[l] = ptr(blk.mlp.fc2.weight), ptr(blk.mlp.fc2.bias)
+        w.norm_w, w.norm_b = ptr(self.norm.weight), ptr(self.norm.bias)
+        for l, lin in enumerate(self.impl_mlp.layers):
+            w.mlp_w[l], w.mlp_b[l] = ptr(lin.weight), ptr(lin.bias)
+        return w, keep
+
+    def _packed_weights(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or self._packed[0] != key:
+            dev = self.latent_proj.weight.device
+            blob = torch.empty(lib.zs_implicit_packed_bytes(), device=dev, dtype=torch.uint8)
+            w, keep = self._weights_struct()
+            check(lib.zs_implicit_pack(w, blob.data_ptr(), torch.cuda.current_stream().cuda_stream), "zs_implicit_pack")
+            self._packed = (key, blob)
+        return self._packed[1]
+
+    def _kv_packed(self, lat):
+        if "kv_packed" not in lat:
+            (k0, v0), (k1, v1) = lat["kv"]
+            B, L = lat["B"], lat["L"]
+            buf = torch.empty(lib.zs_implicit_kv_bytes(B, L), device=k0.device, dtype=torch.uint8)
+            c = [t.contiguous() for t in (k0, v0, k1, v1)]
+            check(lib.zs_implicit_kv_pack(c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(), c[3].data_ptr(), B, L,
+                                          buf.data_ptr(), torch.cuda.current_stream().cuda_stream), "zs_implicit_kv_pack")
+            lat["kv_packed"] = buf
+        return lat["kv_packed"]
+
+    def _fused(self, lat, pts, B, P, grid=None, sigmoid=False):
+        out = torch.empty(B, P, device=self.latent_proj.weight.device, dtype=torch.float32)
+        n, rmin, rmax, x0, x1 = grid if grid is not None else (0, 0.0, 0.0, 0, 0)
+        prec = {"bf16x3": 0, "bf16": 1}[self.precision]
+        check(lib.zs_implicit_fused_fwd(self._packed_weights().data_ptr(), self._kv_packed(lat).data_ptr(), lat["L"],
+                                        None if pts is None else pts.data_ptr(), B, P, n, rmin, rmax, x0, x1,
+                                        out.data_ptr(), int(sigmoid), prec, torch.cuda.current_stream().cuda_stream),
+              "zs_implicit_fused_fwd")
+        return out
+
+    def _use_fused(self):
+        if self.engine == "f32":
+            return False
+        ok = self.fused_available()
+        if self.engine == "fused" and not ok:
+            raise RuntimeError("engine='fused' requested but the fused kernel does not support this configuration")
+        return ok
+
+    # -- public API --------------------------------------------------------------------------------
+    def forward(self, latent_depth, latent_semantic, points_3D, need_attn=True):
+        self._check_inference(latent_depth, points_3D)
+        assert latent_semantic is None
+        with torch.no_grad():
+            pts = points_3D.float().contiguous()
+            B, P, _ = pts.shape
+            lat = self.prepare_latents(latent_depth)
+            L = lat["L"]
+            attn = torch.empty(B, P, L, device=pts.device, dtype=torch.float32) if need_attn else None
+            if self._use_fused() and not need_attn:
+                return self._fused(lat, pts, B, P), None
+            logits = torch.empty(B, P, device=pts.device, dtype=torch.float32)
+            for s in range(0, P, self.point_chunk):
+                e = min(P, s + self.point_chunk)
+                pc = pts[:, s:e].contiguous()
+                ac = torch.empty(B, e - s, L, device=pts.device, dtype=torch.float32) if need_attn else None
+                logits[:, s:e] = self._points_f32(lat, pc, ac)
+                if need_attn:
+                    attn[:, s:e] = ac
+            if self._use_fused():   # attention map from the f32 chain, logits from the hot kernel
+                logits = self._fused(lat, pts, B, P)
+            return logits, attn
+
+    @torch.no_grad()
+    def grid_occupancy(self, latent_depth, n, rmin, rmax, x0=0, x1=None, sigmoid=True, lat=None):
+        """Occupancy over x-slices [x0,x1) of the dense (n)^3 grid of utils/eval_3D.py:10-20:
+        returns [B, x1-x0, n, n] (sigmoid(logit) like compute_level_grid, eval_3D.py:46)."""
+        x1 = n if x1 is None else x1
+        lat = lat if lat is not None else self.prepare_latents(latent_depth)
+        B = lat["B"]
+        if self._use_fused():
+            out = self._fused(lat, None, B, (x1 - x0) * n * n, grid=(n, float(rmin), float(rmax), x0, x1), sigmoid=sigmoid)
+            return out.view(B, x1 - x0, n, n)
+        out = torch.empty(B, x1 - x0, n, n, device=latent_depth.device, dtype=torch.float32)
+        slices = max(1, self.point_chunk // (n * n * max(B, 1)))
+        for s in range(x0, x1, slices):
+            e = min(x1, s + slices)
+            pts = ops.dense_grid(n, rmin, rmax, s, e, latent_depth.device).view(1, -1, 3).expand(B, -1, -1).contiguous()
+            lg = self._points_f32(lat, pts)
+            out[:, s - x0:e - x0] = (ops.axpby(lg, 1.0, act=ops.ACT_SIGMOID) if sigmoid else lg).view(B, e - s, n, n)
+        return out

@@ -1,0 +1,305 @@
+"""Thin torch-tensor wrappers over the C ABI (device memory + streams come from PyTorch; the math
+is in libzeroshape_b200.so).  Every wrapper launches on torch's current CUDA stream.
+
+Image tensors are NHWC fp32 contiguous unless noted.
+"""
+import math
+
+import torch
+
+from . import _native
+from ._native import lib, check
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS100, ACT_SIGMOID = 0, 1, 2, 3, 4
+RES_NONE, RES_BEFORE_ACT, RES_AFTER_ACT = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{name}: expected a CUDA tensor (zeroshape_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+
+
+def device_cc():
+    return lib.zs_device_cc()
+
+
+def gemm(a, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None):
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T).  `a`/`out`/`res` may be 2-D row-strided views (last dim contiguous)."""
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    for t, n in ((a, "a"), (w, "w"), (res, "res"), (out, "out")):
+        if t is not None:
+            if not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1:
+                raise TypeError(f"gemm: bad tensor {n}")
+    _chk(bias, "bias")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if res is None:
+        res_mode = RES_NONE
+    elif res_mode == RES_NONE:
+        res_mode = RES_AFTER_ACT
+    check(lib.zs_gemm_f32(_p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(res),
+                          res.stride(0) if res is not None else 0, res_mode, _p(out), out.stride(0),
+                          M, N, K, act, _stream()), "zs_gemm_f32")
+    return out
+
+
+def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE):
+    """F.linear on the last dim of a contiguous tensor."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    r2 = res.reshape(-1, w.shape[0]) if res is not None else None
+    y = gemm(x2, w, bias, r2, res_mode, act)
+    return y.reshape(*shp[:-1], w.shape[0])
+
+
+def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=None, res_mode=RES_NONE,
+                pre_relu=False):
+    """x [B,H,W,Cin]; w [Cout,KH,KW,Cin]; pad = (top, bottom, left, right)."""
+    _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias"); _chk(res, "res")
+    B, H, W, Cin = x.shape
+    Cout, KH, KW, Cin2 = w.shape
+    assert Cin == Cin2, (x.shape, w.shape)
+    pt, pb, pl, pr = pad
+    OH = (H + pt + pb - KH) // stride + 1
+    OW = (W + pl + pr - KW) // stride + 1
+    y = torch.empty(B, OH, OW, Cout, device=x.device, dtype=torch.float32)
+    if res is None:
+        res_mode = RES_NONE
+    elif res_mode == RES_NONE:
+        res_mode = RES_AFTER_ACT
+    check(lib.zs_conv2d_nhwc_f32(_p(x), B, H, W, Cin, _p(w), _p(bias), _p(res), res_mode, _p(y), Cout, KH, KW,
+                                 stride, pt, pl, OH, OW, act, int(pre_relu), _stream()), "zs_conv2d_nhwc_f32")
+    return y
+
+
+def layernorm(x, gamma, beta, eps):
+    _chk(x, "x"); _chk(gamma, "gamma"); _chk(beta, "beta")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    check(lib.zs_layernorm_f32(_p(x), C, _p(gamma), _p(beta), _p(y), C, rows, C, eps, _stream()), "zs_layernorm_f32")
+    return y
+
+
+def groupnorm_nhwc(x, gamma, beta, groups, eps, relu, res=None):
+    _chk(x, "x"); _chk(res, "res")
+    B, H, W, C = x.shape
+    y = torch.empty_like(x)
+    check(lib.zs_groupnorm_nhwc_f32(_p(x), _p(gamma), _p(beta), _p(res), _p(y), B, H * W, C, groups, eps, int(relu),
+                                    _stream()), "zs_groupnorm_nhwc_f32")
+    return y
+
+
+def channel_affine(x, scale, shift, act=ACT_NONE, res=None):
+    _chk(x, "x"); _chk(scale, "scale"); _chk(shift, "shift"); _chk(res, "res")
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    check(lib.zs_channel_affine_f32(_p(x), _p(scale), _p(shift), _p(res), _p(y), x.numel() // C, C, act, _stream()),
+          "zs_channel_affine_f32")
+    return y
+
+
+def axpby(a, alpha=1.0, b=None, beta=1.0, act=ACT_NONE):
+    _chk(a, "a"); _chk(b, "b")
+    y = torch.empty_like(a)
+    check(lib.zs_axpby_f32(_p(a), alpha, _p(b), beta, _p(y), a.numel(), act, _stream()), "zs_axpby_f32")
+    return y
+
+
+def maxpool3x3s2_nhwc(x, pad_top, pad_left, OH, OW):
+    _chk(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty(B, OH, OW, C, device=x.device, dtype=torch.float32)
+    check(lib.zs_maxpool3x3s2_nhwc_f32(_p(x), _p(y), B, H, W, C, pad_top, pad_left, OH, OW, _stream()),
+          "zs_maxpool3x3s2_nhwc_f32")
+    return y
+
+
+def avgpool_nhwc(x):
+    _chk(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, device=x.device, dtype=torch.float32)
+    check(lib.zs_avgpool_nhwc_f32(_p(x), _p(y), B, H * W, C, _stream()), "zs_avgpool_nhwc_f32")
+    return y
+
+
+def bilinear_nhwc(x, OH, OW, align_corners):
+    _chk(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty(B, OH, OW, C, device=x.device, dtype=torch.float32)
+    check(lib.zs_bilinear_nhwc_f32(_p(x), _p(y), B, H, W, C, OH, OW, int(align_corners), _stream()),
+          "zs_bilinear_nhwc_f32")
+    return y
+
+
+def nchw_to_nhwc(x, scale=1.0, shift=0.0):
+    _chk(x, "x")
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32)
+    check(lib.zs_nchw_to_nhwc_f32(_p(x), _p(y), B, C, H, W, scale, shift, _stream()), "zs_nchw_to_nhwc_f32")
+    return y
+
+
+def nhwc_to_nchw(x):
+    _chk(x, "x")
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+    check(lib.zs_nhwc_to_nchw_f32(_p(x), _p(y), B, C, H, W, _stream()), "zs_nhwc_to_nchw_f32")
+    return y
+
+
+def mha(qkv, heads):
+    """qkv [B,T,3*C] -> [B,T,C] (timm Attention core, softmax(q k^T / sqrt(hd)) v)."""
+    _chk(qkv, "qkv")
+    B, T, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    out = torch.empty(B, T, C, device=qkv.device, dtype=torch.float32)
+    check(lib.zs_mha_f32(_p(qkv), _p(out), B, T, heads, hd, hd ** -0.5, _stream()), "zs_mha_f32")
+    return out
+
+
+def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False):
+    """qkv_p [B,P,3C]; k_lat/v_lat [B,L,C] views with row stride; returns [B,P,C]."""
+    _chk(qkv_p, "qkv_p")
+    B, Pn, C3 = qkv_p.shape
+    C = C3 // 3
+    L = k_lat.shape[1]
+    assert k_lat.stride(2) == 1 and v_lat.stride(2) == 1 and k_lat.stride(1) == v_lat.stride(1)
+    assert k_lat.stride(0) == L * k_lat.stride(1) and v_lat.stride(0) == L * v_lat.stride(1)
+    out = torch.empty(B, Pn, C, device=qkv_p.device, dtype=torch.float32)
+    _chk(attn, "attn")
+    check(lib.zs_point_attention_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(out), _p(attn), attn_scale,
+                                     int(attn_accumulate), B, Pn, L, heads, C // heads, (C // heads) ** -0.5, _stream()),
+          "zs_point_attention_f32")
+    return out
+
+
+def dense_grid(n, rmin, rmax, x0, x1, device):
+    out = torch.empty(x1 - x0, n, n, 3, device=device, dtype=torch.float32)
+    check(lib.zs_dense_grid_f32(_p(out), n, rmin, rmax, x0, x1, _stream()), "zs_dense_grid_f32")
+    return out
+
+
+def concat2(a, b, s=1.0):
+    """s * cat([a, b], -1) for 2-D row-strided inputs."""
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0]
+    rows = a.shape[0]
+    y = torch.empty(rows, a.shape[1] + b.shape[1], device=a.device, dtype=torch.float32)
+    check(lib.zs_concat2_f32(_p(a), a.stride(0), a.shape[1], _p(b), b.stride(0), b.shape[1], s, _p(y), y.stride(0),
+                             rows, _stream()), "zs_concat2_f32")
+    return y
+
+
+def intr_param2mtx(params, H, W):
+    _chk(params, "params")
+    B = params.shape[0]
+    K = torch.empty(B, 3, 3, device=params.device, dtype=torch.float32)
+    check(lib.zs_intr_param2mtx_f32(_p(params), _p(K), B, H, W, _stream()), "zs_intr_param2mtx_f32")
+    return K
+
+
+def unproject_normalize(depth, mask, K):
+    """depth, mask [B,1,H,W] (or [B,H,W]); K [B,3,3] -> seen_points [B,HW,3], mean [B,3], scale [B]."""
+    depth = depth.contiguous(); mask = mask.contiguous().float(); K = K.contiguous()
+    _chk(depth, "depth"); _chk(mask, "mask"); _chk(K, "K")
+    B = depth.shape[0]
+    H, W = depth.shape[-2:]
+    pts = torch.empty(B, H * W, 3, device=depth.device, dtype=torch.float32)
+    mean = torch.empty(B, 3, device=depth.device, dtype=torch.float32)
+    scale = torch.empty(B, device=depth.device, dtype=torch.float32)
+    check(lib.zs_unproject_normalize_f32(_p(depth), _p(mask), _p(K), _p(pts), _p(mean), _p(scale), B, H, W, None,
+                                         _stream()), "zs_unproject_normalize_f32")
+    return pts, mean, scale
+
+
+def unproject(depth, K):
+    """Raw unprojection: depth [B,1,H,W], K [B,3,3] -> [B,HW,3] (utils/camera.py:88-108)."""
+    depth = depth.contiguous(); K = K.contiguous()
+    _chk(depth, "depth"); _chk(K, "K")
+    B = depth.shape[0]
+    H, W = depth.shape[-2:]
+    pts = torch.empty(B, H * W, 3, device=depth.device, dtype=torch.float32)
+    check(lib.zs_unproject_normalize_f32(_p(depth), None, _p(K), _p(pts), None, None, B, H, W, None, _stream()),
+          "zs_unproject_normalize_f32")
+    return pts
+
+
+def chamfer_nn(xyz1, xyz2):
+    """-> dist1 [b,n], dist2 [b,m] (squared), idx1, idx2 (int32)."""
+    _chk(xyz1, "xyz1"); _chk(xyz2, "xyz2")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dev = xyz1.device
+    d1 = torch.empty(b, n, device=dev); d2 = torch.empty(b, m, device=dev)
+    i1 = torch.empty(b, n, device=dev, dtype=torch.int32); i2 = torch.empty(b, m, device=dev, dtype=torch.int32)
+    ws = torch.empty(lib.zs_chamfer_ws_bytes(b, n, m), device=dev, dtype=torch.uint8)
+    check(lib.zs_chamfer_nn_fwd(_p(xyz1), _p(xyz2), b, n, m, _p(d1), _p(d2), _p(i1), _p(i2), _p(ws), _stream()),
+          "zs_chamfer_nn_fwd")
+    return d1, d2, i1, i2
+
+
+def chamfer_nn_bwd(xyz1, xyz2, g1, g2, i1, i2):
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    gx1 = torch.zeros_like(xyz1); gx2 = torch.zeros_like(xyz2)
+    check(lib.zs_chamfer_nn_bwd(_p(xyz1), _p(xyz2), _p(g1), _p(g2), _p(i1), _p(i2), b, n, m, _p(gx1), _p(gx2),
+                                _stream()), "zs_chamfer_nn_bwd")
+    return gx1, gx2
+
+
+def chamfer_stats(sq1, sq2, thresholds, squared=True):
+    _chk(sq1, "sq1"); _chk(sq2, "sq2")
+    b, n = sq1.shape
+    m = sq2.shape[1]
+    dev = sq1.device
+    thr = torch.tensor(list(thresholds), device=dev, dtype=torch.float32)
+    T = thr.numel()
+    mean1 = torch.empty(b, device=dev); mean2 = torch.empty(b, device=dev)
+    f1 = torch.empty(b, T, device=dev); f2 = torch.empty(b, T, device=dev)
+    check(lib.zs_chamfer_stats(_p(sq1), _p(sq2), b, n, m, _p(thr), T, int(squared), _p(mean1), _p(mean2), _p(f1), _p(f2), _stream()),
+          "zs_chamfer_stats")
+    return mean1, mean2, f1, f2
+
+
+def marching_cubes(vol, iso):
+    """vol [n,n,n] fp32 CUDA -> (verts [V,3] fp32 in index units, faces [F,3] int32), both on device."""
+    _chk(vol, "vol")
+    n = vol.shape[0]
+    assert vol.shape == (n, n, n)
+    dev = vol.device
+    ws = torch.empty(lib.zs_mc_ws_bytes(n), device=dev, dtype=torch.uint8)
+    counts = torch.empty(2, device=dev, dtype=torch.int32)
+    check(lib.zs_mc_count(_p(vol), n, float(iso), _p(ws), _p(counts), _stream()), "zs_mc_count")
+    V, F = counts.tolist()   # the one host sync of the mesh path (sizes of the outputs)
+    verts = torch.empty(V, 3, device=dev, dtype=torch.float32)
+    faces = torch.empty(F, 3, device=dev, dtype=torch.int32)
+    if V > 0:
+        check(lib.zs_mc_emit(_p(vol), n, float(iso), _p(ws), _p(verts), _p(faces), _stream()), "zs_mc_emit")
+    return verts, faces
+
+
+def mesh_sample(verts, faces, num, vscale=1.0, voffset=0.0, seed=0):
+    dev = verts.device
+    F = faces.shape[0]
+    pts = torch.empty(num, 3, device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.zs_mesh_sample_ws_bytes(F), device=dev, dtype=torch.uint8)
+    check(lib.zs_mesh_sample(_p(verts) if F else None, _p(faces) if F else None, verts.shape[0], F, vscale, voffset,
+                             num, seed, _p(ws), _p(pts), _stream()), "zs_mesh_sample")
+    return pts

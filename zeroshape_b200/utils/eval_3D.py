@@ -1,0 +1,236 @@
+"""Drop-in for the reference's utils/eval_3D.py: same function names, arguments and `var` side
+effects, with the dense-grid decoder pass, marching cubes, surface sampling, Chamfer and F-score
+all on the GPU (no device->host->device hop, no Python loop over grid slices).
+
+Reference functions mirrored (file:line in the reference tree):
+  get_dense_3D_grid      utils/eval_3D.py:10-20      compute_level_grid    :22-81
+  normalize_pc           :93-102                     eval_metrics_default  :104-138
+  brute_force_search     :140-170                    eval_metrics_BF       :172-207
+  eval_metrics           :209-213                    compute_fscore        :215-231
+  convert_to_explicit    :233-263                    chamfer_distance      :265-269
+Not mirrored: ICP (:271-284, off by default, options/shape.yaml:53) and the attention movie
+(:47-80, visualisation).
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from ..external.chamfer3D.dist_chamfer_3D import chamfer_3DDist
+from .camera import get_rotation_sphere
+
+
+class Mesh:
+    """Minimal stand-in for the trimesh.Trimesh surface the reference hands around
+    (attributes used by utils/util_vis.py:104-127: vertices, faces, triangles, sample, export,
+    apply_transform).  Device tensors are kept alongside for the GPU sampler."""
+
+    def __init__(self, verts_dev, faces_dev, vscale=1.0, voffset=0.0):
+        self._v, self._f = verts_dev, faces_dev
+        self._vscale, self._voffset = float(vscale), float(voffset)
+        self._np = None
+
+    def _host(self):
+        if self._np is None:
+            v = (self._v.double() * self._vscale + self._voffset).cpu().numpy()
+            self._np = (v, self._f.cpu().numpy().astype(np.int64))
+        return self._np
+
+    @property
+    def vertices(self):
+        return self._host()[0]
+
+    @property
+    def faces(self):
+        return self._host()[1]
+
+    @property
+    def triangles(self):
+        v, f = self._host()
+        return v[f]
+
+    def sample(self, count, seed=0, device_out=False):
+        pts = ops.mesh_sample(self._v, self._f, count, self._vscale, self._voffset, seed)
+        return pts if device_out else pts.cpu().numpy().astype(np.float64)
+
+    def apply_transform(self, T):
+        v, f = self._host()
+        T = np.asarray(T, dtype=np.float64)
+        self._np = (v @ T[:3, :3].T + T[:3, 3], f)
+        self._v = torch.from_numpy(self._np[0]).float().to(self._v.device)
+        self._vscale, self._voffset = 1.0, 0.0
+        return self
+
+    def export(self, path):
+        v, f = self._host()
+        with open(path, "w") as fh:
+            fh.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                     "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(v), len(f)))
+            for p in v:
+                fh.write("%.7g %.7g %.7g\n" % tuple(p))
+            for t in f:
+                fh.write("3 %d %d %d\n" % tuple(t))
+
+
+@torch.no_grad()
+def get_dense_3D_grid(opt, var, N=None):
+    """[B, N+1, N+1, N+1, 3] query grid (API parity; the fast path never materialises it)."""
+    batch_size = len(var.idx)
+    N = N or opt.eval.vox_res
+    rmin, rmax = opt.eval.range
+    g = ops.dense_grid(N + 1, float(rmin), float(rmax), 0, N + 1, opt.device)
+    return g.unsqueeze(0).repeat(batch_size, 1, 1, 1, 1)
+
+
+def _grid_from_points(points_3D):
+    """Recover (n, rmin, rmax) when points_3D is the regular grid get_dense_3D_grid builds."""
+    n = points_3D.shape[1]
+    rmin = float(points_3D[0, 0, 0, 0, 0])
+    rmax = float(points_3D[0, -1, -1, -1, 0])
+    return n, rmin, rmax
+
+
+@torch.no_grad()
+def compute_level_grid(opt, impl_network, latent_depth, latent_semantic, points_3D, images, vis_attn=False):
+    """-> (occ [B,n,n,n] = sigmoid(logit), None).  One latent-side pass per image + one fused grid
+    pass instead of the reference's n sequential slices."""
+    if vis_attn:
+        raise NotImplementedError("attention movie (utils/eval_3D.py:47-80) is out of scope (SURVEY.md 8f rank 2)")
+    latent_depth = latent_depth.to(torch.float32)
+    B, n = points_3D.shape[0], points_3D.shape[1]
+    assert n == points_3D.shape[2] == points_3D.shape[3] and points_3D.shape[4] == 3
+    if hasattr(impl_network, "grid_occupancy"):
+        check_n, rmin, rmax = _grid_from_points(points_3D)
+        ref = ops.dense_grid(n, rmin, rmax, 0, n, points_3D.device)
+        if torch.equal(ref, points_3D[0]):
+            return impl_network.grid_occupancy(latent_depth, n, rmin, rmax, 0, n, sigmoid=True), None
+    # arbitrary point sets / foreign networks: slice loop like the reference
+    pts = points_3D.view(B, n, n * n, 3)
+    occ = torch.stack([impl_network(latent_depth, latent_semantic, pts[:, i])[0] for i in range(n)], dim=1)
+    return torch.sigmoid(occ.view(B, n, n, n)), None
+
+
+@torch.no_grad()
+def normalize_pc(pc):
+    """Centre and scale by max(x-extent, y-extent) + 1e-7 (utils/eval_3D.py:93-102; z ignored)."""
+    assert pc.dim() == 3
+    z = pc - pc.mean(dim=1, keepdim=True)
+    lx = z[:, :, 0].max(dim=-1)[0] - z[:, :, 0].min(dim=-1)[0]
+    ly = z[:, :, 1].max(dim=-1)[0] - z[:, :, 1].min(dim=-1)[0]
+    return z / (torch.stack([lx, ly], dim=-1).max(dim=-1)[0].view(-1, 1, 1) + 1.e-7)
+
+
+def compute_fscore(dist1, dist2, thresholds=[0.005, 0.01, 0.02, 0.05, 0.1, 0.2]):
+    """F = 2PR/(P+R) at each threshold on (already sqrt'ed) distances, NaN -> 0 (eval_3D.py:215-231)."""
+    _, _, p, r = ops.chamfer_stats(dist1.contiguous(), dist2.contiguous(), thresholds, squared=False)
+    f = 2 * p * r / (p + r)
+    f[torch.isnan(f)] = 0
+    return f
+
+
+def convert_to_explicit(opt, level_grids, isoval=0., to_pointcloud=False, seed=0):
+    """level_grids: list of [n,n,n] arrays (numpy, as the reference passes, or CUDA tensors).
+    -> meshes (and [B, num_points, 3] numpy point clouds).  GPU marching cubes; vertices scaled with
+    the reference's `v / S * (max-min) + min`, S = n (utils/eval_3D.py:252-255)."""
+    rmin, rmax = opt.eval.range
+    meshes, clouds = [], []
+    for i, vol in enumerate(level_grids):
+        if not isinstance(vol, torch.Tensor):
+            vol = torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32)).to(opt.device)
+        vol = vol.float().contiguous()
+        S = vol.shape[0]
+        v, f = ops.marching_cubes(vol, isoval)
+        mesh = Mesh(v, f, (rmax - rmin) / S, rmin)
+        meshes.append(mesh)
+        if to_pointcloud:
+            clouds.append(mesh.sample(opt.eval.num_points, seed=seed + i, device_out=True))
+    if to_pointcloud:
+        return meshes, torch.stack(clouds, dim=0).cpu().numpy()
+    return meshes
+
+
+def chamfer_distance(opt, X1, X2):
+    """sqrt'ed bidirectional NN distances + indices (utils/eval_3D.py:265-269)."""
+    assert X1.shape[2] == 3
+    d1, d2, i1, i2 = chamfer_3DDist()(X1, X2)
+    return d1.sqrt(), d2.sqrt(), i1, i2
+
+
+def _predict_clouds(opt, var, impl_network, seed=0):
+    points_n = opt.eval.vox_res + 1
+    rmin, rmax = opt.eval.range
+    B = len(var.idx)
+    if hasattr(impl_network, "grid_occupancy"):
+        level_vox = impl_network.grid_occupancy(var.latent_depth.float(), points_n, float(rmin), float(rmax))
+    else:
+        level_vox, _ = compute_level_grid(opt, impl_network, var.latent_depth, var.latent_semantic,
+                                          get_dense_3D_grid(opt, var), var.rgb_input_map, False)
+    meshes, clouds = [], []
+    for b in range(B):
+        v, f = ops.marching_cubes(level_vox[b].contiguous(), 0.5)
+        mesh = Mesh(v, f, (rmax - rmin) / points_n, rmin)
+        meshes.append(mesh)
+        clouds.append(mesh.sample(opt.eval.num_points, seed=seed + b, device_out=True))
+    var.mesh_pred = meshes
+    var.dpc_pred = torch.stack(clouds, dim=0)
+    R_gt = var.pose_gt[..., :3]
+    var.dpc.points = (R_gt @ var.dpc.points.permute(0, 2, 1)).permute(0, 2, 1).contiguous()
+    if opt.data.dataset_test == 'pix3d':
+        var.dpc.points[:, :, :2] *= -1
+    return level_vox
+
+
+@torch.no_grad()
+def eval_metrics_default(opt, var, impl_network, vis_only=False):
+    _predict_clouds(opt, var, impl_network)
+    var.dpc_pred = normalize_pc(var.dpc_pred)
+    var.dpc.points = normalize_pc(var.dpc.points)
+    if vis_only:
+        return
+    dist_acc, dist_comp, _, _ = chamfer_distance(opt, X1=var.dpc_pred, X2=var.dpc.points)
+    var.f_score = compute_fscore(dist_acc, dist_comp, opt.eval.f_thresholds)
+    assert dist_acc.shape[1] == opt.eval.num_points
+    var.cd_acc = dist_acc.mean(dim=1)
+    var.cd_comp = dist_comp.mean(dim=1)
+    return dist_acc.mean(), dist_comp.mean()
+
+
+@torch.no_grad()
+def brute_force_search(pc_pred, pc_gt, f_thresholds=[0.005, 0.01, 0.02, 0.05, 0.1, 0.2], device="cuda", batch_size=24):
+    """6912-rotation pose search (utils/eval_3D.py:140-170); running argmin kept on the device."""
+    pc_pred = pc_pred.to(device).unsqueeze(0).float()
+    pc_gt = normalize_pc(pc_gt.to(device).unsqueeze(0).float().contiguous())
+    rotations = get_rotation_sphere(azim_sample=24, elev_sample=24, roll_sample=12, scales=[1.0], device=device)
+    best = None
+    for i in range(0, len(rotations), batch_size):
+        R = rotations[i:i + batch_size]
+        rot = normalize_pc((R @ pc_pred.permute(0, 2, 1)).permute(0, 2, 1)).contiguous()
+        d1, d2, _, _ = ops.chamfer_nn(rot, pc_gt.expand(R.shape[0], -1, -1).contiguous())
+        acc, comp, p, r = ops.chamfer_stats(d1, d2, f_thresholds)
+        cd = (acc + comp) / 2
+        j = int(torch.argmin(cd))            # first minimum == the reference's strict-< scan order
+        if best is None or cd[j] < best[0]:
+            f = 2 * p[j] * r[j] / (p[j] + r[j])
+            f[torch.isnan(f)] = 0
+            best = (cd[j].clone(), acc[j].clone(), comp[j].clone(), f, rot[j].clone())
+    return best[1], best[2], best[3], best[4], pc_gt
+
+
+@torch.no_grad()
+def eval_metrics_BF(opt, var, impl_network, vis_only=False):
+    _predict_clouds(opt, var, impl_network)
+    if vis_only:
+        return
+    cd_acc, cd_comp, f_score = [], [], []
+    for i in range(len(var.idx)):
+        a, c, f, best_pred, best_gt = brute_force_search(var.dpc_pred[i], var.dpc.points[i], opt.eval.f_thresholds, opt.device)
+        var.dpc_pred[i] = best_pred
+        var.dpc.points[i] = best_gt[0]
+        cd_acc.append(a); cd_comp.append(c); f_score.append(f)
+    var.cd_acc, var.cd_comp, var.f_score = torch.stack(cd_acc), torch.stack(cd_comp), torch.stack(f_score)
+    return var.cd_acc.mean(), var.cd_comp.mean()
+
+
+def eval_metrics(opt, var, impl_network, vis_only=False):
+    if opt.eval.brute_force:
+        return eval_metrics_BF(opt, var, impl_network, vis_only)
+    return eval_metrics_default(opt, var, impl_network, vis_only)
