@@ -47,6 +47,8 @@ const char* zs_last_error(void);
 int zs_abi_version(void);
 /* compute capability (major*10+minor) of the current device, or negative error */
 int zs_device_cc(void);
+/* number of CUDA kernels this library has launched since it was loaded (all threads) */
+long long zs_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense building blocks (replace the cuBLAS/cuDNN calls PyTorch issues for nn.Linear / nn.Conv2d /
@@ -58,6 +60,15 @@ int zs_device_cc(void);
 int zs_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
                 const float* res, int ldres, int res_mode, float* C, int ldc,
                 int M, int N, int K, int act, void* stream);
+
+/* Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA bulk-copied weights) with the same epilogue.
+ * Weights are packed once (fp32 W[N,K] -> (hi,lo) bf16 tiles in the UMMA 128B-swizzled K-major smem image).
+ * precision 0 = "bf16x3" (Ah*Wh + Ah*Wl + Al*Wh, ~2^-16 relative: parity mode), 1 = "bf16" (single pass). */
+size_t zs_gemm_tc_packed_bytes(int N, int K);
+int zs_gemm_tc_pack(const float* W, int ldw, int N, int K, void* packed, void* stream);
+int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, const float* bias,
+                   const float* res, int ldres, int res_mode, float* C, int ldc,
+                   int M, int N, int K, int act, int precision, void* stream);
 
 /* NHWC convolution as implicit GEMM: y[b,oh,ow,co] = epi( sum x[b,oh*s+kh-pt,ow*s+kw-pl,ci] w[co,kh,kw,ci] ).
  * `pre_relu` applies ReLU to x on load (ResidualConvUnit_custom: model/depth/blocks.py:274-281).

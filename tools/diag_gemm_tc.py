@@ -1,0 +1,85 @@
+"""Diagnostics for the tcgen05 GEMM on a real B200 (run under gpurun; prints structured evidence so a
+layout/descriptor bug can be identified from one run).  Not a test; writes gpurun_out/diag_gemm_tc.txt."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zeroshape_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+out_lines = []
+
+
+def log(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True)
+    out_lines.append(s)
+
+
+def run(M, N, K, prec, a=None, w=None, tag=""):
+    g = torch.Generator().manual_seed(1)
+    a = torch.randint(-4, 5, (M, K), generator=g).float() if a is None else a
+    w = torch.randint(-4, 5, (N, K), generator=g).float() if w is None else w
+    ref = a.double() @ w.double().T
+    out = ops.gemm_tc(a.to(dev), ops.PackedWeight(w.to(dev)), precision=prec)
+    torch.cuda.synchronize()
+    o = out.cpu().double()
+    err = (o - ref).abs()
+    log(f"[{tag}] M={M} N={N} K={K} prec={prec}: max|err|={err.max().item():.4g} mismatches={(err > 1e-3 * (ref.abs().max().item() + 1)).sum().item()}/{M * N}")
+    return o, ref
+
+
+log("device", torch.cuda.get_device_name(0), "cc", ops.device_cc())
+# 1. identity weight: C[m,n] = A[m,n] for n < K -- any permutation of rows/cols/k is directly visible
+K = 64
+a = (torch.arange(128).view(-1, 1) * 100 + torch.arange(K).view(1, -1)).float()   # value encodes (row, k)
+a = a % 251                                                                          # exact in bf16
+w = torch.zeros(256, K)
+w[torch.arange(K), torch.arange(K)] = 1
+o, ref = run(128, 256, K, "bf16", a, w, "identity")
+if (o - ref).abs().max() > 0:
+    log("row0 got ", o[0, :16].tolist())
+    log("row0 want", ref[0, :16].tolist())
+    log("row1 got ", o[1, :16].tolist())
+    log("row9 got ", o[9, :16].tolist())
+    log("col-sum got", o.sum(0)[:8].tolist(), "want", ref.sum(0)[:8].tolist())
+for prec in ("bf16", "bf16x3"):
+    run(128, 256, 64, prec, tag="ints")
+    run(128, 256, 256, prec, tag="ints-k256")
+    run(1000, 768, 259, prec, tag="ints-ragged")
+g = torch.Generator().manual_seed(2)
+a = torch.randn(4096, 256, generator=g); w = torch.randn(1024, 256, generator=g) / 16
+for prec in ("bf16", "bf16x3"):
+    o, ref = run(4096, 1024, 256, prec, a, w, "randn")
+    log(f"   rel err vs fp64: {((o - ref).abs().max() / ref.abs().max()).item():.3e}")
+# timing
+for (M, N, K) in ((148 * 128 * 8, 256, 256), (148 * 128 * 8, 1024, 256), (148 * 128 * 8, 256, 1024), (148 * 128 * 8, 768, 256)):
+    a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev)
+    pw = ops.PackedWeight(w)
+    c = torch.empty(M, N, device=dev)
+    for prec in ("bf16x3", "bf16"):
+        for _ in range(3):
+            ops.gemm_tc(a, pw, out=c, precision=prec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.gemm_tc(a, pw, out=c, precision=prec)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        log(f"[time] M={M} N={N} K={K} {prec}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s (algorithmic)")
+    for _ in range(3):
+        ops.gemm(a, w, out=c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        ops.gemm(a, w, out=c)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    log(f"[time] M={M} N={N} K={K} f32-ffma: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+os.makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/diag_gemm_tc.txt", "w").write("\n".join(out_lines) + "\n")

@@ -32,7 +32,11 @@ SIGNATURES = {
     "zs_last_error": (c_char_p, []),
     "zs_abi_version": (c_int, []),
     "zs_device_cc": (c_int, []),
+    "zs_launch_count": (ctypes.c_longlong, []),
     "zs_gemm_f32": (c_int, [P, c_int, P, c_int, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_gemm_tc_packed_bytes": (c_size_t, [c_int, c_int]),
+    "zs_gemm_tc_pack": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "zs_gemm_tc_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_conv2d_nhwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_layernorm_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_float, P]),

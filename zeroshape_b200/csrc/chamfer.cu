@@ -182,8 +182,9 @@ extern "C" int zs_chamfer_nn_fwd(const float* xyz1, const float* xyz2, int b, in
   unsigned long long* k1 = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(ws) + 7) & ~uintptr_t(7));
   unsigned long long* k2 = k1 + (size_t)b * n;
   cudaStream_t st = as_stream(stream);
-  if (n > 0) nn_one_direction(xyz1, n, xyz2, m, b, k1, dist1, idx1, st);
-  if (m > 0) nn_one_direction(xyz2, m, xyz1, n, b, k2, dist2, idx2, st);
+  if (n > 0) { nn_one_direction(xyz1, n, xyz2, m, b, k1, dist1, idx1, st); count_launches(m > 0 ? 3 : 2); }
+  if (m > 0) { nn_one_direction(xyz2, m, xyz1, n, b, k2, dist2, idx2, st); count_launches(n > 0 ? 3 : 2); }
+  count_launches(-1);
   ZS_CUDA_CHECK_LAUNCH("zs_chamfer_nn_fwd");
   return ZS_OK;
 }
@@ -198,6 +199,7 @@ extern "C" int zs_chamfer_nn_bwd(const float* xyz1, const float* xyz2, const flo
   dim3 g1((n + 255) / 256, b), g2((m + 255) / 256, b);
   chamfer_grad_kernel<<<g1, 256, 0, st>>>(xyz1, n, xyz2, m, graddist1, idx1, gradxyz1, gradxyz2);
   chamfer_grad_kernel<<<g2, 256, 0, st>>>(xyz2, m, xyz1, n, graddist2, idx2, gradxyz2, gradxyz1);
+  count_launches(1);
   ZS_CUDA_CHECK_LAUNCH("zs_chamfer_nn_bwd");
   return ZS_OK;
 }

@@ -9,6 +9,8 @@
 namespace zs {
 
 void set_error(const char* fmt, ...);
+// kernels launched by this library since load (for bench.py's `gpu_launches` claim)
+void count_launches(int n);
 
 #define ZS_REQUIRE(cond, ...)                                   \
   do {                                                          \
@@ -25,6 +27,7 @@ void set_error(const char* fmt, ...);
       zs::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));   \
       return ZS_ERR_CUDA;                                                           \
     }                                                                               \
+    zs::count_launches(1);                                                          \
   } while (0)
 
 #define ZS_CUDA_CALL(expr)                                                          \

@@ -1,9 +1,13 @@
 // HBM-bound helpers: normalisations, pooling, resampling, layout changes, error plumbing.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace zs {
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -248,6 +252,7 @@ using namespace zs;
 
 extern "C" const char* zs_last_error(void) { return zs::g_err; }
 extern "C" int zs_abi_version(void) { return 1; }
+extern "C" long long zs_launch_count(void) { return zs::g_launches.load(std::memory_order_relaxed); }
 extern "C" int zs_device_cc(void) {
   int dev = 0, maj = 0, min = 0;
   ZS_CUDA_CALL(cudaGetDevice(&dev));

@@ -1,0 +1,317 @@
+// tcgen05 GEMM with split-bf16 operands (fp32-grade accuracy on the bf16 tensor pipe) and fused epilogue.
+//
+//   C[M,N] = epi( A[M,K] * W[N,K]^T ),  A fp32 row-major in global memory, W pre-packed (zs_gemm_tc_pack).
+//
+// Precision modes
+//   0 "bf16x3": A = Ah + Al, W = Wh + Wl (bf16 each); D += Ah*Wh + Ah*Wl + Al*Wh in fp32 TMEM accumulators
+//               -> ~2^-16 relative error per product (parity mode, meets the 1e-3 bar with margin)
+//   1 "bf16"  : D += Ah*Wh only (fast mode, ~1e-2 relative on the decoder logits -- not parity)
+//
+// CTA = 320 threads, persistent over 128x256 output tiles, warp-specialised:
+//   warps 0-3  A producers : fp32 rows -> (hi,lo) bf16 -> 128B-swizzled K-major smem tiles (generic proxy
+//                             stores + fence.proxy.async), one row per thread
+//   warps 4-7  epilogue    : tcgen05.ld accumulator rows -> bias / activation / residual -> fp32 global
+//   warp  8    MMA issuer  : one elected lane issues tcgen05.mma (M=128,N=256,K=16), commits to mbarriers
+//   warp  9    W loader    : cp.async.bulk (TMA 1-D) of pre-swizzled weight tiles, complete_tx on mbarriers
+// smem: 2 stages x (A_hi 16K + A_lo 16K + W_hi 32K + W_lo 32K) = 192 KB; TMEM: 2 x 256 fp32 columns
+// (accumulator double buffer: the epilogue of tile i overlaps the MMAs of tile i+1).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace zs {
+using namespace tc;
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB (one of hi/lo)
+constexpr int TC_B_TILE = TC_BN * TC_BK * 2;   // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_TILE + 2 * TC_B_TILE;  // 96 KB
+constexpr int TC_THREADS = 320;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcParams {
+  const float* A; int lda;
+  const uint8_t* Wp;          // packed: [n_tiles][k_chunks][hi 32K | lo 32K]
+  const float* bias;
+  const float* res; int ldres; int res_mode;
+  float* C; int ldc;
+  int M, N, K;
+  int act;
+  int precision;
+  int m_tiles, n_tiles, k_chunks;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 1024-aligned operand tiles
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // barriers: full[2], empty[2], tmem_full[2], tmem_empty[2], then tmem base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 64u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 128 + 1);   // 128 A-producer threads + 1 expect_tx arrival of the W loader
+      mbar_init(empty_bar(s), 1);        // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);        // one tcgen05.commit
+      mbar_init(tempty_bar(a), 128);     // 128 epilogue threads
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp < 4) {
+    // ================= A producers =================
+    const int r = threadIdx.x;  // row inside the tile
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m = (t / p.n_tiles) * TC_BM + r;
+      const bool row_ok = m < p.M;
+      const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda;
+      const bool vec_ok = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* a_hi = smem_gen + stage * TC_STAGE_BYTES;
+        uint8_t* a_lo = a_hi + TC_A_TILE;
+        const int k0 = kc * TC_BK;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 elements (16 B of bf16)
+          float v[8];
+          const int k = k0 + c * 8;
+          if (row_ok && vec_ok && k + 8 <= p.K) {
+            float4 x0 = __ldg(reinterpret_cast<const float4*>(arow + k));
+            float4 x1 = __ldg(reinterpret_cast<const float4*>(arow + k + 4));
+            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (row_ok && k + e < p.K) ? __ldg(arow + k + e) : 0.f;
+          }
+          uint4 hi, lo;
+          split_bf16x2(v[0], v[1], hi.x, lo.x);
+          split_bf16x2(v[2], v[3], hi.y, lo.y);
+          split_bf16x2(v[4], v[5], hi.z, lo.z);
+          split_bf16x2(v[6], v[7], hi.w, lo.w);
+          const uint32_t off = swizzle128_offset(r, c);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(full_bar(stage));
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ================= W loader =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t bytes = split ? 2u * TC_B_TILE : (uint32_t)TC_B_TILE;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint8_t* src = p.Wp + ((size_t)nt * p.k_chunks + kc) * (2u * TC_B_TILE);
+          const uint32_t dst = smem_base + stage * TC_STAGE_BYTES + 2 * TC_A_TILE;
+          mbar_arrive_expect_tx(full_bar(stage), bytes);
+          bulk_g2s(dst, src, TC_B_TILE, full_bar(stage));
+          if (split) bulk_g2s(dst + TC_B_TILE, src + TC_B_TILE, TC_B_TILE, full_bar(stage));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TC_A_TILE);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_A_TILE), b_lo = umma_desc_sw128(sa + 2 * TC_A_TILE + TC_B_TILE);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 B along K inside the swizzle atom
+            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kc | k) != 0);
+            if (split) {
+              umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
+              umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
+            }
+          }
+          umma_commit(empty_bar(stage));                 // smem stage reusable when these MMAs retire
+          if (kc == p.k_chunks - 1) umma_commit(tfull_bar(acc));
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 4..7 -> TMEM lane quarters 0..3) =================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+      const int m = mt * TC_BM + q * 32 + lane;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + c0, rr);
+        tmem_ld_wait();
+        const int n0 = nt * TC_BN + c0;
+        if (m < p.M && n0 < p.N) {
+          float* crow = p.C + (int64_t)m * p.ldc + n0;
+          const float* rrow = p.res_mode != ZS_RES_NONE ? p.res + (int64_t)m * p.ldres + n0 : nullptr;
+          const bool full = n0 + 32 <= p.N;
+          const bool vec_c = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+          const bool vec_r = rrow && full && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (full || n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+          }
+          float rv[32];
+          if (rrow) {
+            if (vec_r) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 x = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+                rv[4 * j] = x.x; rv[4 * j + 1] = x.y; rv[4 * j + 2] = x.z; rv[4 * j + 3] = x.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) rv[j] = (n0 + j < p.N) ? __ldg(rrow + j) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j];
+            if (p.res_mode == ZS_RES_BEFORE_ACT) x += rv[j];
+            x = apply_act(x, p.act);
+            if (p.res_mode == ZS_RES_AFTER_ACT) x += rv[j];
+            v[j] = x;
+          }
+          if (vec_c) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) crow[j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- weight packing: fp32 W[N,K] -> per (n_tile, k_chunk) [hi | lo] swizzled bf16 tiles --------------
+__global__ void gemm_tc_pack_kernel(const float* __restrict__ W, int ldw, int N, int K, uint8_t* __restrict__ out,
+                                    int n_tiles, int k_chunks) {
+  // one thread per (tile row, 16-byte chunk)
+  int64_t total = (int64_t)n_tiles * k_chunks * TC_BN * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i & 7);
+    int64_t t = i >> 3;
+    int r = (int)(t % TC_BN); t /= TC_BN;
+    int kc = (int)(t % k_chunks);
+    int nt = (int)(t / k_chunks);
+    int n = nt * TC_BN + r, k = kc * TC_BK + c * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (n < N && k + e < K) ? W[(int64_t)n * ldw + k + e] : 0.f;
+    uint4 hi, lo;
+    tc::split_bf16x2(v[0], v[1], hi.x, lo.x);
+    tc::split_bf16x2(v[2], v[3], hi.y, lo.y);
+    tc::split_bf16x2(v[4], v[5], hi.z, lo.z);
+    tc::split_bf16x2(v[6], v[7], hi.w, lo.w);
+    uint8_t* tile = out + ((size_t)nt * k_chunks + kc) * (2u * TC_B_TILE);
+    uint32_t off = tc::swizzle128_offset(r, c);
+    *reinterpret_cast<uint4*>(tile + off) = hi;
+    *reinterpret_cast<uint4*>(tile + TC_B_TILE + off) = lo;
+  }
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" size_t zs_gemm_tc_packed_bytes(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  size_t nt = (N + TC_BN - 1) / TC_BN, kc = (K + TC_BK - 1) / TC_BK;
+  return nt * kc * 2u * TC_B_TILE;
+}
+
+extern "C" int zs_gemm_tc_pack(const float* W, int ldw, int N, int K, void* packed, void* stream) {
+  ZS_REQUIRE(W && packed && N > 0 && K > 0 && ldw >= K, "zs_gemm_tc_pack: bad args");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "zs_gemm_tc_pack: packed buffer must be 16-byte aligned");
+  int nt = (N + TC_BN - 1) / TC_BN, kc = (K + TC_BK - 1) / TC_BK;
+  int64_t total = (int64_t)nt * kc * TC_BN * 8;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 4096) grid = 4096;
+  gemm_tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, ldw, N, K, reinterpret_cast<uint8_t*>(packed), nt, kc);
+  ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_pack");
+  return ZS_OK;
+}
+
+extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, const float* bias,
+                              const float* res, int ldres, int res_mode, float* C, int ldc,
+                              int M, int N, int K, int act, int precision, void* stream) {
+  ZS_REQUIRE(A && Wpacked && C, "zs_gemm_tc_f32: null pointer");
+  ZS_REQUIRE(M >= 0 && N > 0 && K > 0 && lda >= K && ldc >= N, "zs_gemm_tc_f32: bad shape");
+  ZS_REQUIRE(res_mode == ZS_RES_NONE || res != nullptr, "zs_gemm_tc_f32: residual requested but res==NULL");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_gemm_tc_f32: precision must be 0 (bf16x3) or 1 (bf16)");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wpacked) & 15) == 0, "zs_gemm_tc_f32: packed weights must be 16-byte aligned");
+  if (M == 0) return ZS_OK;
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  TcParams p;
+  p.A = A; p.lda = lda; p.Wp = reinterpret_cast<const uint8_t*>(Wpacked); p.bias = bias;
+  p.res = res; p.ldres = ldres; p.res_mode = res_mode; p.C = C; p.ldc = ldc;
+  p.M = M; p.N = N; p.K = K; p.act = act; p.precision = precision;
+  p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = (N + TC_BN - 1) / TC_BN; p.k_chunks = (K + TC_BK - 1) / TC_BK;
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_f32");
+  return ZS_OK;
+}

@@ -257,6 +257,7 @@ extern "C" int zs_mc_count(const float* vol, int n, float iso, void* ws, int32_t
   mc_classify_kernel<<<grid_for(n3), 256, 0, st>>>(vol, n, iso, w);
   exclusive_scan<int32_t>(w.vcnt, w.vcnt, w.vbs, n3, counts + 0, st);
   exclusive_scan<int32_t>(w.tcnt, w.tcnt, w.tbs, n3, counts + 1, st);
+  count_launches(6);
   ZS_CUDA_CHECK_LAUNCH("zs_mc_count");
   return ZS_OK;
 }
@@ -292,6 +293,7 @@ extern "C" int zs_mesh_sample(const float* verts, const int32_t* faces, int V, i
   double* total = reinterpret_cast<double*>(p);
   face_area_kernel<<<grid_for(F), 256, 0, st>>>(verts, faces, F, vscale, voffset, area);
   exclusive_scan<double>(area, area, bsum, F, total, st);
+  count_launches(4);
   mesh_sample_kernel<<<grid_for(S), 256, 0, st>>>(verts, faces, F, vscale, voffset, area, total, S, seed, points);
   ZS_CUDA_CHECK_LAUNCH("zs_mesh_sample");
   return ZS_OK;

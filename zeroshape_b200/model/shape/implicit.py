@@ -87,8 +87,9 @@ class Implicit(nn.Module):
         self.impl_mlp = _Holder()
         self.impl_mlp.layers = nn.ModuleList([
             nn.Linear(dims[l] + (dims[0] if l in self.skip_in else 0), dims[l + 1]) for l in range(len(dims) - 1)])
-        self.engine = "auto"          # "auto" | "fused" | "f32"
-        self.precision = "bf16x3"     # fused-engine operand precision: "bf16x3" (parity) | "bf16" (fast)
+        self.engine = "auto"          # "auto" | "fused" | "tc" | "f32"
+        self.precision = "bf16x3"     # tensor-core operand precision: "bf16x3" (parity) | "bf16" (fast)
+        self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         self.point_chunk = 1 << 16    # query points per pass of the f32 engine
         self._packed = None           # (version key, packed weight blob) for the fused engine
         self.initialize_weights()
@@ -138,32 +139,52 @@ class Implicit(nn.Module):
             lat = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=lat)
         return {"kv": kv, "B": latent_depth.shape[0], "L": latent_depth.shape[1]}
 
-    # -- f32 engine: chain of plain-fp32 kernels over a chunk of points ---------------------------
-    def _points_f32(self, lat, pts, attn_out=None):
+    # -- per-layer engines: chain of kernels over a chunk of points --------------------------------
+    #    "f32": plain-fp32 FFMA GEMMs (bit-faithful);  "tc": tcgen05 split-bf16 GEMMs (zs_gemm_tc_f32)
+    def _lin(self, x2d, mod, tc, act=ops.ACT_NONE, res=None):
+        if tc and mod.weight.shape[0] >= 64:
+            pw = self._pw.get(id(mod))
+            if pw is None or pw.src is not mod.weight:
+                pw = self._pw[id(mod)] = ops.PackedWeight(mod.weight)
+            return ops.gemm_tc(x2d, pw, mod.bias, res=res, act=act, precision=self.precision)
+        return ops.gemm(x2d, mod.weight, mod.bias, res=res, act=act)
+
+    def _points_chain(self, lat, pts, attn_out=None, tc=False):
         """pts [B,P,3] contiguous -> logits [B,P]; optionally fills attn_out [B,P,L]."""
         B, P, _ = pts.shape
         C = self.n_channels
         nb = len(self.blocks_attn)
-        x = ops.linear(pts, self.point_proj.proj.weight, self.point_proj.proj.bias)
+        x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
             k_lat, v_lat = lat["kv"][l]
-            qkv = ops.linear(self._ln(x, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias)
-            a = ops.point_attention(qkv, k_lat, v_lat, self.num_heads, attn=attn_out, attn_scale=1.0 / nb,
-                                    attn_accumulate=(l > 0))
+            qkv = self._lin(self._ln(x, blk.norm1), blk.attn.qkv, tc)
+            a = ops.point_attention(qkv.view(B, P, 3 * C), k_lat, v_lat, self.num_heads, attn=attn_out,
+                                    attn_scale=1.0 / nb, attn_accumulate=(l > 0)).view(B * P, C)
             del qkv
-            x = ops.linear(a, blk.attn.proj.weight, blk.attn.proj.bias, res=x)
-            h = ops.linear(self._ln(x, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
-            x = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=x)
+            x = self._lin(a, blk.attn.proj, tc, res=x)
+            h = self._lin(self._ln(x, blk.norm2), blk.mlp.fc1, tc, act=ops.ACT_GELU)
+            x = self._lin(h, blk.mlp.fc2, tc, res=x)
             del h
         feat = self._ln(x, self.norm)
-        inputs = ops.concat2(pts.reshape(B * P, 3), feat.reshape(B * P, C), 1.0)
+        inputs = ops.concat2(pts.reshape(B * P, 3), feat, 1.0)
         h = inputs
         n_layers = len(self.impl_mlp.layers)
         for l, lin in enumerate(self.impl_mlp.layers):
             if l in self.skip_in:
                 h = ops.concat2(h, inputs, SQRT2)
-            h = ops.gemm(h, lin.weight, lin.bias, act=ops.ACT_SOFTPLUS100 if l < n_layers - 1 else ops.ACT_NONE)
+            h = self._lin(h, lin, tc, act=ops.ACT_SOFTPLUS100 if l < n_layers - 1 else ops.ACT_NONE)
         return h.reshape(B, P)
+
+    def _points_f32(self, lat, pts, attn_out=None):
+        return self._points_chain(lat, pts, attn_out, tc=self._use_tc())
+
+    def _use_tc(self):
+        if self.engine == "f32":
+            return False
+        ok = ops.device_cc() == 100
+        if self.engine == "tc" and not ok:
+            raise RuntimeError("engine='tc' needs an sm_100 device")
+        return ok
 
     # -- fused engine ------------------------------------------------------------------------------
     def fused_available(self):
@@ -224,7 +245,7 @@ class Implicit(nn.Module):
         return out
 
     def _use_fused(self):
-        if self.engine == "f32":
+        if self.engine in ("f32", "tc"):
             return False
         ok = self.fused_available()
         if self.engine == "fused" and not ok:

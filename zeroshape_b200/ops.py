@@ -59,6 +59,53 @@ def gemm(a, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None):
     return out
 
 
+class PackedWeight:
+    """fp32 W[N,K] packed for the tcgen05 GEMM (hi/lo bf16, UMMA swizzled tiles).  Re-packs itself when the
+    source tensor is modified in place (optimizer step / load_state_dict)."""
+
+    def __init__(self, w):
+        self.src = w
+        self.key = None
+        self.blob = None
+
+    def get(self):
+        w = self.src
+        key = (w.data_ptr(), w._version, tuple(w.shape))
+        if self.key != key:
+            wd = w.detach()
+            if wd.dtype != torch.float32 or wd.stride(-1) != 1 or not wd.is_cuda:
+                raise TypeError("PackedWeight: expected a CUDA fp32 matrix with contiguous rows")
+            N, K = wd.shape
+            self.blob = torch.empty(lib.zs_gemm_tc_packed_bytes(N, K), device=wd.device, dtype=torch.uint8)
+            check(lib.zs_gemm_tc_pack(_p(wd), wd.stride(0), N, K, _p(self.blob), _stream()), "zs_gemm_tc_pack")
+            self.key = key
+        return self.blob
+
+
+PRECISIONS = {"bf16x3": 0, "bf16": 1}
+
+
+def gemm_tc(a, pw, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None, precision="bf16x3"):
+    """Tensor-core variant of `gemm`: `pw` is a PackedWeight of W[N,K]."""
+    N, K = pw.src.shape
+    assert a.dim() == 2 and a.shape[1] == K
+    for t, n in ((a, "a"), (res, "res"), (out, "out")):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1):
+            raise TypeError(f"gemm_tc: bad tensor {n}")
+    _chk(bias, "bias")
+    M = a.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if res is None:
+        res_mode = RES_NONE
+    elif res_mode == RES_NONE:
+        res_mode = RES_AFTER_ACT
+    check(lib.zs_gemm_tc_f32(_p(a), a.stride(0), _p(pw.get()), _p(bias), _p(res), res.stride(0) if res is not None else 0,
+                             res_mode, _p(out), out.stride(0), M, N, K, act, PRECISIONS[precision], _stream()),
+          "zs_gemm_tc_f32")
+    return out
+
+
 def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE):
     """F.linear on the last dim of a contiguous tensor."""
     shp = x.shape
