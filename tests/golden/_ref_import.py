@@ -111,9 +111,12 @@ def install_shims():
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REF_ROOT}")
     if "timm" not in sys.modules:
+        import importlib.machinery
         timm = types.ModuleType("timm")
         timm.models = types.ModuleType("timm.models")
         vt = types.ModuleType("timm.models.vision_transformer")
+        for m_ in (timm, timm.models, vt):      # importlib.util.find_spec() rejects modules without a spec
+            m_.__spec__ = importlib.machinery.ModuleSpec(m_.__name__, None)
         vt.Mlp, vt.DropPath, vt.Block, vt.PatchEmbed, vt.Attention = _Mlp, _DropPath, _Block, _PatchEmbed, _Attention
         timm.models.vision_transformer = vt
 
@@ -168,3 +171,143 @@ def fill_deterministic(module_or_sd, seed):
     if isinstance(module_or_sd, nn.Module):
         module_or_sd.load_state_dict(out, strict=True)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stand-in for timm.create_model("vit_base_resnet50_384") so that the reference's OWN glue code
+# (model/depth/vit.py forward_flex + hooks + act_postprocess, blocks.py, dpt_depth.py, graph_shape.py)
+# can be executed for real on CPU.  Sub-module names reproduce timm 0.6.12's, so the state_dict keys
+# under `dpt_depth.pretrained.model.*` are the ones SURVEY.md section 8(b) lists.
+import math as _math
+import torch.nn.functional as _F
+
+
+class _StdConv2dSame(nn.Conv2d):
+    def __init__(self, cin, cout, k, stride=1, eps=1e-8):
+        super().__init__(cin, cout, k, stride=stride, padding=0, bias=False)
+        self.eps = eps
+
+    def forward(self, x):
+        def pad(i, k, s):
+            return max((_math.ceil(i / s) - 1) * s + (k - 1) + 1 - i, 0)
+        ph, pw = pad(x.shape[-2], self.kernel_size[0], self.stride[0]), pad(x.shape[-1], self.kernel_size[1], self.stride[1])
+        x = _F.pad(x, [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2])
+        w = _F.batch_norm(self.weight.reshape(1, self.out_channels, -1), None, None, training=True, momentum=0.,
+                          eps=self.eps).reshape_as(self.weight)
+        return _F.conv2d(x, w, None, self.stride)
+
+
+class _GroupNormAct(nn.GroupNorm):
+    def __init__(self, c, act=True):
+        super().__init__(32, c, eps=1e-5)
+        self.apply_act = act
+
+    def forward(self, x):
+        x = _F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
+        return _F.relu(x) if self.apply_act else x
+
+
+class _MaxPoolSame(nn.Module):
+    def forward(self, x):
+        def pad(i):
+            return max((_math.ceil(i / 2) - 1) * 2 + 2 + 1 - i, 0)
+        ph, pw = pad(x.shape[-2]), pad(x.shape[-1])
+        x = _F.pad(x, [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2], value=float("-inf"))
+        return _F.max_pool2d(x, 3, 2)
+
+
+class _DownsampleConv(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv = _StdConv2dSame(cin, cout, 1, stride)
+        self.norm = _GroupNormAct(cout, act=False)
+
+    def forward(self, x):
+        return self.norm(self.conv(x))
+
+
+class _BottleneckV2(nn.Module):
+    def __init__(self, cin, cout, stride, first):
+        super().__init__()
+        mid = cout // 4
+        self.downsample = _DownsampleConv(cin, cout, stride) if first else None
+        self.conv1, self.norm1 = _StdConv2dSame(cin, mid, 1), _GroupNormAct(mid)
+        self.conv2, self.norm2 = _StdConv2dSame(mid, mid, 3, stride), _GroupNormAct(mid)
+        self.conv3, self.norm3 = _StdConv2dSame(mid, cout, 1), _GroupNormAct(cout, act=False)
+
+    def forward(self, x):
+        s = x if self.downsample is None else self.downsample(x)
+        x = self.norm3(self.conv3(self.norm2(self.conv2(self.norm1(self.conv1(x))))))
+        return _F.relu(x + s)
+
+
+class _Stage(nn.Module):
+    def __init__(self, cin, cout, stride, depth):
+        super().__init__()
+        self.blocks = nn.Sequential(*[_BottleneckV2(cin if b == 0 else cout, cout, stride if b == 0 else 1, b == 0)
+                                      for b in range(depth)])
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class _ResNetV2(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.stem = nn.Sequential()
+        self.stem.add_module("conv", _StdConv2dSame(3, 64, 7, 2))
+        self.stem.add_module("norm", _GroupNormAct(64))
+        self.stem.add_module("pool", _MaxPoolSame())
+        self.stages = nn.Sequential(_Stage(64, 256, 1, 3), _Stage(256, 512, 2, 4), _Stage(512, 1024, 2, 9))
+        self.norm = nn.Identity()
+
+    def forward(self, x):
+        return self.norm(self.stages(self.stem(x)))
+
+
+class _HybridEmbed(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.backbone = _ResNetV2()
+        self.proj = nn.Conv2d(1024, 768, 1)
+
+
+class FakeTimmHybridViT(nn.Module):
+    """Attribute surface the reference touches: patch_embed.{backbone,proj}, cls_token, pos_embed,
+    pos_drop, blocks, norm (+ unused head)."""
+
+    def __init__(self):
+        super().__init__()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, 768))
+        self.pos_embed = nn.Parameter(torch.zeros(1, 577, 768))
+        self.pos_drop = nn.Dropout(0.0)
+        self.patch_embed = _HybridEmbed()
+        self.blocks = nn.Sequential(*[_Block(768, 12, 4.0, qkv_bias=True, norm_layer=lambda d: nn.LayerNorm(d, eps=1e-6))
+                                      for _ in range(12)])
+        self.norm = nn.LayerNorm(768, eps=1e-6)
+        self.head = nn.Linear(768, 1000)
+
+
+def install_fake_timm_factory():
+    install_shims()
+    sys.modules["timm"].create_model = lambda name, pretrained=False, **k: FakeTimmHybridViT()
+
+
+def reference_opt(device="cpu"):
+    """EasyDict with the fields graph_shape.Graph / Loss read (options/shape.yaml defaults)."""
+    from utils.util import EasyDict as edict
+    return edict(dict(
+        device=device, H=224, W=224,
+        pretrain=dict(depth=None),
+        arch=dict(num_heads=8, latent_dim=256, win_size=16,
+                  depth=dict(encoder="resnet", n_blocks=12, dsp=2, pretrained=None), rgb=dict(encoder=None, n_blocks=12),
+                  impl=dict(n_channels=256, att_blocks=2, mlp_ratio=4., posenc_perlayer=False, mlp_layers=8, posenc_3D=0,
+                            skip_in=[2, 4, 6])),
+        optim=dict(fix_dpt=False),
+        training=dict(depth_loss=dict(grad_reg=0.1, depth_inv=True, mask_shrink=False),
+                      shape_loss=dict(impt_weight=1, impt_thres=0.01)),
+        loss_weight=dict(shape=1, depth=None, intr=None),
+        eval=dict(vox_res=64, range=[-1.5, 1.5], num_points=10000, brute_force=False, icp=False,
+                  f_thresholds=[0.005, 0.01, 0.02, 0.05, 0.1, 0.2]),
+        data=dict(dataset_test="synthetic"),
+    ))

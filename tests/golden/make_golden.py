@@ -48,20 +48,10 @@ def g_implicit_init():
 GENERATORS = {"implicit": g_implicit, "implicit_init": g_implicit_init}
 
 
-def register(name):
-    def deco(fn):
-        GENERATORS[name] = fn
-        return fn
-    return deco
-
-
 def main(names):
     install_shims()
-    for mod in ("make_golden_extra",):
-        try:
-            __import__(mod)
-        except ImportError:
-            pass
+    import make_golden_extra
+    GENERATORS.update(make_golden_extra.GENERATORS)
     for name in names or sorted(GENERATORS):
         out = GENERATORS[name]()
         path = os.path.join(HERE, f"{name}.npz")
