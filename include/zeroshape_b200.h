@@ -37,6 +37,7 @@ extern "C" {
 #define ZS_ACT_GELU 2      /* exact erf GELU (torch.nn.GELU default) */
 #define ZS_ACT_SOFTPLUS100 3 /* torch Softplus(beta=100, threshold=20): model/shape/implicit.py:166 */
 #define ZS_ACT_SIGMOID 4
+#define ZS_ACT_CLAMP01 5    /* relu then clamp(max=1): DPT depth head, model/depth/dpt_depth.py:106,119 */
 
 /* residual placement in the fused epilogue: y = act(acc + bias [+ res]) [+ res] */
 #define ZS_RES_NONE 0

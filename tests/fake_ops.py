@@ -1,0 +1,173 @@
+"""CPU stand-ins for the C-ABI wrappers of zeroshape_b200.ops (TEST INFRASTRUCTURE): same signatures and
+layout conventions (NHWC, OHWI filters), implemented with PyTorch CPU ops.  They let the `-m "not gpu"`
+suite execute the product's HOST orchestration (layer order, packing, strides, residual placement) against
+the oracle without a GPU.  Never used by the product."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACTS = {0: lambda x: x, 1: F.relu, 2: F.gelu, 3: lambda x: F.softplus(x, beta=100), 4: torch.sigmoid,
+        5: lambda x: x.clamp(0, 1)}
+
+
+def _epi(y, bias, res, res_mode, act):
+    if bias is not None:
+        y = y + bias
+    if res is not None and res_mode == 0:
+        res_mode = 2
+    if res is not None and res_mode == 1:
+        y = y + res
+    y = ACTS[act](y)
+    if res is not None and res_mode == 2:
+        y = y + res
+    return y
+
+
+def gemm(a, w, bias=None, res=None, res_mode=0, act=0, out=None):
+    y = _epi(a @ w.T, bias, res, res_mode, act)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y.contiguous()
+
+
+def linear(x, w, bias=None, act=0, res=None, res_mode=0):
+    return _epi(F.linear(x, w), bias, res, res_mode, act).contiguous()
+
+
+class PackedWeight:
+    def __init__(self, w):
+        self.src = w
+
+
+def gemm_tc(a, pw, bias=None, res=None, res_mode=0, act=0, out=None, precision="bf16x3"):
+    return gemm(a, pw.src, bias, res, res_mode, act, out)
+
+
+def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, res=None, res_mode=0, pre_relu=False):
+    xn = x.permute(0, 3, 1, 2)
+    if pre_relu:
+        xn = F.relu(xn)
+    xn = F.pad(xn, (pad[2], pad[3], pad[0], pad[1]))
+    y = F.conv2d(xn, w.permute(0, 3, 1, 2), None, stride).permute(0, 2, 3, 1)
+    return _epi(y, bias, res, res_mode, act).contiguous()
+
+
+def layernorm(x, g, b, eps):
+    return F.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+def groupnorm_nhwc(x, g, b, groups, eps, relu, res=None):
+    y = F.group_norm(x.permute(0, 3, 1, 2), groups, g, b, eps).permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res
+    return (F.relu(y) if relu else y).contiguous()
+
+
+def channel_affine(x, scale, shift, act=0, res=None):
+    y = x * scale + shift
+    if res is not None:
+        y = y + res
+    return ACTS[act](y)
+
+
+def axpby(a, alpha=1.0, b=None, beta=1.0, act=0):
+    y = a * alpha
+    if b is not None:
+        y = y + b * beta
+    return ACTS[act](y)
+
+
+def maxpool3x3s2_nhwc(x, pt, pl, OH, OW):
+    H, W = x.shape[1], x.shape[2]
+    pb, pr = (OH - 1) * 2 + 3 - H - pt, (OW - 1) * 2 + 3 - W - pl
+    xn = F.pad(x.permute(0, 3, 1, 2), (pl, max(pr, 0), pt, max(pb, 0)), value=float("-inf"))
+    return F.max_pool2d(xn, 3, 2)[:, :, :OH, :OW].permute(0, 2, 3, 1).contiguous()
+
+
+def avgpool_nhwc(x):
+    return x.mean(dim=(1, 2))
+
+
+def bilinear_nhwc(x, OH, OW, align):
+    return F.interpolate(x.permute(0, 3, 1, 2), size=(OH, OW), mode="bilinear", align_corners=bool(align)).permute(0, 2, 3, 1).contiguous()
+
+
+def nchw_to_nhwc(x, scale=1.0, shift=0.0):
+    return (x * scale + shift).permute(0, 2, 3, 1).contiguous()
+
+
+def nhwc_to_nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def mha(qkv, heads):
+    B, T, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    q, k, v = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    return (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C)
+
+
+def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False):
+    B, P, C3 = qkv_p.shape
+    C = C3 // 3
+    hd = C // heads
+    q, k, v = qkv_p.reshape(B, P, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    L = k_lat.shape[1]
+    kl = k_lat.reshape(B, L, heads, hd).permute(0, 2, 1, 3)
+    vl = v_lat.reshape(B, L, heads, hd).permute(0, 2, 1, 3)
+    s = torch.cat([(q @ kl.transpose(-2, -1)), (q * k).sum(-1, keepdim=True)], -1) * hd ** -0.5
+    a = s.softmax(-1)
+    out = (a[..., :L] @ vl + a[..., L:] * v).transpose(1, 2).reshape(B, P, C)
+    if attn is not None:
+        vis = a[..., :L].mean(1) * attn_scale
+        if attn_accumulate:
+            attn += vis
+        else:
+            attn.copy_(vis)
+    return out
+
+
+def dense_grid(n, rmin, rmax, x0, x1, device):
+    g = torch.linspace(rmin, rmax, n)
+    return torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1)[x0:x1].contiguous()
+
+
+def concat2(a, b, s=1.0):
+    return torch.cat([a, b.expand(a.shape[0], -1) if b.shape[0] != a.shape[0] else b], -1) / s
+
+
+def intr_param2mtx(params, H, W):
+    from oracle.backbone import intr_param2mtx as ref
+    return ref(params, H, W)
+
+
+def unproject(depth, K):
+    from oracle.backbone import unproj_depth
+    return unproj_depth(depth, K)
+
+
+def unproject_normalize(depth, mask, K):
+    from oracle.backbone import unproj_depth, valid_norm_fac
+    B = depth.shape[0]
+    pts = unproj_depth(depth, K)
+    mean, scale = valid_norm_fac(pts, mask > 0.5)
+    seen = (pts - mean.unsqueeze(1)) / scale.view(B, 1, 1)
+    seen[(mask <= 0.5).view(B, -1)] = 0
+    return seen, mean, scale
+
+
+def device_cc():
+    return 0
+
+
+def install(monkeypatch):
+    """Patch zeroshape_b200.ops in place (pytest monkeypatch restores it)."""
+    import zeroshape_b200.ops as ops
+    g = globals()
+    for name in ("gemm", "linear", "PackedWeight", "gemm_tc", "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "channel_affine",
+                 "axpby", "maxpool3x3s2_nhwc", "avgpool_nhwc", "bilinear_nhwc", "nchw_to_nhwc", "nhwc_to_nchw", "mha",
+                 "point_attention", "dense_grid", "concat2", "intr_param2mtx", "unproject", "unproject_normalize", "device_cc"):
+        monkeypatch.setattr(ops, name, g[name])

@@ -61,6 +61,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case ZS_ACT_GELU: return act_gelu_erf(x);
     case ZS_ACT_SOFTPLUS100: return act_softplus100(x);
     case ZS_ACT_SIGMOID: return act_sigmoid(x);
+    case ZS_ACT_CLAMP01: return fminf(fmaxf(x, 0.0f), 1.0f);
     default: return x;
   }
 }

@@ -80,39 +80,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // ================= A producers =================
     const int r = threadIdx.x;  // row inside the tile
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const bool vec_ok = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+    // All 64 fp32 of a K-chunk are fetched into registers BEFORE waiting for the smem slot (also across
+    // tile boundaries), so the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
+    float4 buf[16];
+    auto fetch = [&](int t, int kc) {
       const int m = (t / p.n_tiles) * TC_BM + r;
       const bool row_ok = m < p.M;
       const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda;
-      const bool vec_ok = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+      const int k0 = kc * TC_BK;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int k = k0 + c * 4;
+        if (row_ok && vec_ok && k + 4 <= p.K) {
+          buf[c] = __ldg(reinterpret_cast<const float4*>(arow + k));
+        } else {
+          float tt[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) tt[e] = (row_ok && k + e < p.K) ? __ldg(arow + k + e) : 0.f;
+          buf[c] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+        }
+      }
+    };
+    if (blockIdx.x < total_tiles) fetch(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         uint8_t* a_hi = smem_gen + stage * TC_STAGE_BYTES;
         uint8_t* a_lo = a_hi + TC_A_TILE;
-        const int k0 = kc * TC_BK;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 elements (16 B of bf16)
-          float v[8];
-          const int k = k0 + c * 8;
-          if (row_ok && vec_ok && k + 8 <= p.K) {
-            float4 x0 = __ldg(reinterpret_cast<const float4*>(arow + k));
-            float4 x1 = __ldg(reinterpret_cast<const float4*>(arow + k + 4));
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (row_ok && k + e < p.K) ? __ldg(arow + k + e) : 0.f;
-          }
+          const float4 x0 = buf[2 * c], x1 = buf[2 * c + 1];
           uint4 hi, lo;
-          split_bf16x2(v[0], v[1], hi.x, lo.x);
-          split_bf16x2(v[2], v[3], hi.y, lo.y);
-          split_bf16x2(v[4], v[5], hi.z, lo.z);
-          split_bf16x2(v[6], v[7], hi.w, lo.w);
+          split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+          split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+          split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+          split_bf16x2(x1.z, x1.w, hi.w, lo.w);
           const uint32_t off = swizzle128_offset(r, c);
           *reinterpret_cast<uint4*>(a_hi + off) = hi;
           if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
         }
         fence_proxy_async_smem();
         mbar_arrive(full_bar(stage));
+        if (kc + 1 < p.k_chunks) fetch(t, kc + 1);
+        else if (t + (int)gridDim.x < total_tiles) fetch(t + gridDim.x, 0);
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }

@@ -1,0 +1,43 @@
+"""Host-side mirror of the reference's depth-only compute graph (model/compute_graph/graph_depth.py:61-97):
+DPT depth + intrinsics head -> var.depth_pred, var.intr_pred, var.seen_points_pred.  BASELINE config (1).
+Inference only in this revision."""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...packing import PackCache
+from ...utils.layers import Bottleneck_Conv
+from ...utils.util import EasyDict as edict
+from ..depth.dpt_depth import DPTDepthModel
+
+
+class Graph(nn.Module):
+
+    def __init__(self, opt):
+        super().__init__()
+        self.dpt_depth = DPTDepthModel(backbone="vitb_rn50_384")
+        self.with_intr = opt.loss_weight.intr is not None
+        if self.with_intr:
+            self.intr_feat_channels = 768
+            self.intr_head = nn.Sequential(Bottleneck_Conv(768, kernel_size=3), Bottleneck_Conv(768, kernel_size=3))
+            self.intr_pool = nn.AdaptiveAvgPool2d((1, 1))
+            self.intr_proj = nn.Linear(768, 3)
+            nn.init.zeros_(self.intr_proj.weight)
+            nn.init.zeros_(self.intr_proj.bias)
+            self._intr_cache = PackCache(self.intr_head)
+
+    def forward(self, opt, var, training=False, get_loss=True):
+        if training:
+            raise NotImplementedError("training path is not implemented in this revision")
+        B = len(var.idx)
+        with torch.no_grad():
+            var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
+            if self.with_intr:
+                self._intr_cache.refresh()
+                f = self.intr_head[0].run_nhwc(self.dpt_depth.last_feat_nhwc, self._intr_cache, "h0")
+                f = self.intr_head[1].run_nhwc(f, self._intr_cache, "h1")
+                params = ops.linear(ops.avgpool_nhwc(f), self.intr_proj.weight, self.intr_proj.bias)
+                var.intr_pred = ops.intr_param2mtx(params, opt.H, opt.W)
+                mask = var.mask_input_map.float().contiguous()
+                var.seen_points_pred, _, _ = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
+        return (var, edict()) if get_loss else var

@@ -1,0 +1,105 @@
+"""Host-side mirror of the reference's `model/compute_graph/graph_shape.py` Graph: same constructor,
+sub-module attribute names (dpt_depth, intr_head, intr_pool, intr_proj, coord_encoder, rgb_encoder,
+impl_network, loss_fns), state_dict keys and `forward(opt, var, training, get_loss)` contract; all layer
+math runs in libzeroshape_b200.so.
+
+    forward fills var.{latent_semantic, depth_pred, intr_pred, validity_mask, seen_points, latent_depth, pose}
+    (reference: model/compute_graph/graph_shape.py:115-192)
+
+Inference only in this revision (SURVEY.md section 8 row a13 -- training forward/backward -- is "next"):
+`training=True` / `get_loss=True` with a GT batch raises NotImplementedError instead of silently
+running a different code path.
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...utils.layers import Bottleneck_Conv
+from ...utils.util import EasyDict as edict
+from ..depth.dpt_depth import DPTDepthModel
+from ..shape.implicit import Implicit
+from ..shape.seen_coord_enc import CoordEncRes
+
+
+class Graph(nn.Module):
+
+    def __init__(self, opt):
+        super().__init__()
+        self.intr_feat_channels = 768
+        self.intr_head = nn.Sequential(Bottleneck_Conv(768, kernel_size=3), Bottleneck_Conv(768, kernel_size=3))
+        self.intr_pool = nn.AdaptiveAvgPool2d((1, 1))          # attribute kept; pooling runs in the library
+        self.intr_proj = nn.Linear(768, 3)
+        nn.init.zeros_(self.intr_proj.weight)                  # graph_shape.py:27-28
+        nn.init.zeros_(self.intr_proj.bias)
+        self.dpt_depth = DPTDepthModel(backbone="vitb_rn50_384")
+        self.load_pretrained_depth(opt)
+        if opt.optim.fix_dpt:
+            for m in (self.dpt_depth, self.intr_head, self.intr_proj):
+                for p in m.parameters():
+                    p.requires_grad_(False)
+        if opt.arch.depth.encoder == "resnet":
+            opt.arch.depth.dsp = 1                              # graph_shape.py:41-43
+            self.coord_encoder = CoordEncRes(opt)
+        else:
+            raise NotImplementedError("transformer seen-surface encoder (CoordEncAtt) is not the shipped "
+                                      "configuration (options/shape.yaml:26); SURVEY.md section 8f rank 4")
+        if opt.arch.rgb.encoder:
+            raise NotImplementedError("RGB branch is 'not used in final model' (graph_shape.py:48)")
+        self.rgb_encoder = None
+        feat_res = opt.H // opt.arch.win_size
+        self.impl_network = Implicit(feat_res ** 2, latent_dim=opt.arch.latent_dim, semantic=False,
+                                     n_channels=opt.arch.impl.n_channels, n_blocks_attn=opt.arch.impl.att_blocks,
+                                     n_layers_mlp=opt.arch.impl.mlp_layers, num_heads=opt.arch.num_heads,
+                                     posenc_3D=opt.arch.impl.posenc_3D, mlp_ratio=opt.arch.impl.mlp_ratio,
+                                     skip_in=opt.arch.impl.skip_in, pos_perlayer=opt.arch.impl.posenc_perlayer)
+        self.loss_fns = None    # utils/loss.py (BCE / MiDaS) belongs to the training path
+
+    def load_pretrained_depth(self, opt):
+        """graph_shape.py:69-87 (checkpoint bootstrap of the depth sub-network)."""
+        def child(sd, prefix):
+            return {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+        if opt.pretrain.depth:
+            ckpt = torch.load(opt.pretrain.depth, map_location="cpu")
+            self.dpt_depth.load_state_dict(child(ckpt["graph"], "dpt_depth"))
+            self.intr_head.load_state_dict(child(ckpt["graph"], "intr_head"))
+            self.intr_proj.load_state_dict(child(ckpt["graph"], "intr_proj"))
+        elif opt.arch.depth.pretrained:
+            ckpt = torch.load(opt.arch.depth.pretrained, map_location="cpu")
+            self.dpt_depth.load_state_dict(ckpt["model_state_dict"])
+
+    def intr_param2mtx(self, opt, intr_params):
+        """[B,3] -> [B,3,3] (graph_shape.py:89-113)."""
+        return ops.intr_param2mtx(intr_params.float().contiguous(), opt.H, opt.W)
+
+    def forward(self, opt, var, training=False, get_loss=True):
+        if training or ("gt_sample_points" in var and "gt_sample_sdf" in var):
+            raise NotImplementedError("zeroshape_b200 Graph: the training branch (GT points, losses, backward; "
+                                      "graph_shape.py:155-202) is not implemented in this revision")
+        batch_size = len(var.idx)
+        with torch.no_grad():
+            var.latent_semantic = None
+            var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
+            feat = self.dpt_depth.last_feat_nhwc                                   # layer_4 [B,7,7,768] NHWC
+            cache = self.dpt_depth._cache                                          # intr head shares the pack cache policy
+            if not hasattr(self, "_intr_cache"):
+                from ...packing import PackCache
+                self._intr_cache = PackCache(self.intr_head)
+            self._intr_cache.refresh()
+            f = self.intr_head[0].run_nhwc(feat, self._intr_cache, "h0")
+            f = self.intr_head[1].run_nhwc(f, self._intr_cache, "h1")
+            intr_params = ops.linear(ops.avgpool_nhwc(f), self.intr_proj.weight, self.intr_proj.bias)
+            var.intr_pred = self.intr_param2mtx(opt, intr_params)
+            mask = var.mask_input_map.float().contiguous()
+            var.validity_mask = (mask > 0.5).float().view(batch_size, -1)
+            # unproject + masked mean / max-norm + normalise + zero background: one launch, no host sync
+            var.seen_points, self.last_mean, self.last_scale = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
+            # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
+            coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
+            var.latent_depth = self.coord_encoder.forward_nhwc(coord)
+            var.pose = var.pose_gt if "pose_gt" in var else False
+        if get_loss:
+            return var, edict()
+        return var
+
+    def compute_loss(self, opt, var, training=False):
+        raise NotImplementedError("losses belong to the training path (not in this revision)")

@@ -1,0 +1,104 @@
+"""Host-side mirror of the reference's ResNet-50 seen-surface encoder (the configured one:
+options/shape.yaml:26 `arch.depth.encoder: resnet`), every layer in the CUDA library.
+
+    CoordEncRes(opt).forward(coord_obj [B,3,H,W], mask_obj [B,1,H,W]) -> latent [B, 1+H/16*W/16, latent_dim]
+    (reference: model/shape/seen_coord_enc.py:141-194 over torchvision resnet50)
+
+state_dict keys = torchvision's (`encoder.conv1/bn1/layerN.M.{conv,bn}K/downsample.{0,1}`) plus
+`encoder.fc.{0,1}` Bottleneck_Conv(2048), `encoder.fc.2` Linear and `depth_feat_proj.{0,1,2}`.
+Eval-mode BatchNorm is folded into the (OHWI) filters once per weight version; conv+BN+ReLU and
+conv+BN+add+ReLU are single launches.  The transformer variant (CoordEncAtt) is not the shipped
+configuration and is not mirrored.
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...packing import PackCache, fold_bn_ohwi, ohwi
+from ...utils.layers import Bottleneck_Conv
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container")
+
+
+def _tv_bottleneck(cin, width, stride, down):
+    b = _Holder()
+    b.conv1, b.bn1 = nn.Conv2d(cin, width, 1, bias=False), nn.BatchNorm2d(width)
+    b.conv2, b.bn2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, bias=False), nn.BatchNorm2d(width)
+    b.conv3, b.bn3 = nn.Conv2d(width, width * 4, 1, bias=False), nn.BatchNorm2d(width * 4)
+    if down:
+        b.downsample = nn.Sequential(nn.Conv2d(cin, width * 4, 1, stride=stride, bias=False), nn.BatchNorm2d(width * 4))
+    b.stride = stride
+    return b
+
+
+def _tv_resnet50():
+    r = _Holder()
+    r.conv1, r.bn1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False), nn.BatchNorm2d(64)
+    cin = 64
+    for li, (depth, width, stride) in enumerate(((3, 64, 1), (4, 128, 2), (6, 256, 2), (3, 512, 2)), start=1):
+        blocks = []
+        for b in range(depth):
+            blocks.append(_tv_bottleneck(cin, width, stride if b == 0 else 1, b == 0))
+            cin = width * 4
+        setattr(r, f"layer{li}", nn.ModuleList(blocks))
+    for m in r.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+    return r
+
+
+class CoordEncRes(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        assert opt.arch.depth.dsp == 1
+        if opt.arch.win_size != 16:
+            raise NotImplementedError("win_size 32 variant is not the shipped configuration (options/shape.yaml:23)")
+        latent = opt.arch.latent_dim
+        self.encoder = _tv_resnet50()
+        self.encoder.fc = nn.Sequential(Bottleneck_Conv(2048), Bottleneck_Conv(2048), nn.Linear(2048, latent))
+        self.depth_feat_proj = nn.Sequential(Bottleneck_Conv(1024), Bottleneck_Conv(1024), nn.Conv2d(1024, latent, 1))
+        self._cache = PackCache(self)
+
+    def _cbr(self, x, conv, bn, tag, act, stride=1, pad=0, res=None):
+        w, b = self._cache.get(tag, lambda: fold_bn_ohwi(conv.weight, bn))
+        return ops.conv2d_nhwc(x, w, b, stride, (pad, pad, pad, pad), act=act, res=res,
+                               res_mode=ops.RES_BEFORE_ACT if res is not None else ops.RES_NONE)
+
+    def forward_nhwc(self, coord_nhwc):
+        """coord_nhwc [B,H,W,3] (already multiplied by the mask) -> [B,197,latent]."""
+        if self.training:
+            raise NotImplementedError("CoordEncRes: batch-statistics BatchNorm (training) is not in this revision")
+        self._cache.refresh()
+        enc = self.encoder
+        B = coord_nhwc.shape[0]
+        x = self._cbr(coord_nhwc, enc.conv1, enc.bn1, "stem", ops.ACT_RELU, 2, 3)
+        x = ops.maxpool3x3s2_nhwc(x, 1, 1, (x.shape[1] + 2 - 3) // 2 + 1, (x.shape[2] + 2 - 3) // 2 + 1)
+        feats = {}
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(enc, f"layer{li}")):
+                t = f"l{li}b{bi}"
+                idt = x
+                if hasattr(blk, "downsample"):
+                    idt = self._cbr(x, blk.downsample[0], blk.downsample[1], t + "d", ops.ACT_NONE, blk.stride)
+                y = self._cbr(x, blk.conv1, blk.bn1, t + "c1", ops.ACT_RELU)
+                y = self._cbr(y, blk.conv2, blk.bn2, t + "c2", ops.ACT_RELU, blk.stride, 1)
+                x = self._cbr(y, blk.conv3, blk.bn3, t + "c3", ops.ACT_RELU, res=idt)
+            feats[li] = x
+        g = ops.avgpool_nhwc(feats[4])                                    # [B,2048]
+        g = enc.fc[0].run_nhwc(g, self._cache, "fc0")
+        g = enc.fc[1].run_nhwc(g, self._cache, "fc1")
+        g = ops.linear(g, enc.fc[2].weight, enc.fc[2].bias).unsqueeze(1)  # [B,1,latent]
+        y = self.depth_feat_proj[0].run_nhwc(feats[3], self._cache, "p0")
+        y = self.depth_feat_proj[1].run_nhwc(y, self._cache, "p1")
+        pc = self.depth_feat_proj[2]
+        y = ops.conv2d_nhwc(y, self._cache.get("p2", lambda: ohwi(pc.weight)), pc.bias)
+        return torch.cat([g, y.view(B, -1, y.shape[-1])], dim=1).contiguous()
+
+    def forward(self, coord_obj, mask_obj):
+        assert coord_obj.dim() == 4 and mask_obj.dim() == 4
+        with torch.no_grad():
+            x = ops.nchw_to_nhwc((coord_obj * mask_obj.float()).float().contiguous())
+            return self.forward_nhwc(x)

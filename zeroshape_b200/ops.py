@@ -10,7 +10,7 @@ import torch
 from . import _native
 from ._native import lib, check
 
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS100, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SOFTPLUS100, ACT_SIGMOID, ACT_CLAMP01 = 0, 1, 2, 3, 4, 5
 RES_NONE, RES_BEFORE_ACT, RES_AFTER_ACT = 0, 1, 2
 
 
