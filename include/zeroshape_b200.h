@@ -71,6 +71,23 @@ int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, const float* bi
                    const float* res, int ldres, int res_mode, float* C, int ldc,
                    int M, int N, int K, int act, int precision, void* stream);
 
+/* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
+ * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack
+ * (N=256 rows, K padded to 64) and concatenated:
+ *   mlp: for g in 0..3: fc1.weight[256g:256g+256, :] (K=256), fc2.weight[:, 256g:256g+256] (K=256)
+ *   occ: layer l = 0..7 of impl_mlp with K reordered to [feat(256) | xyz(3)] for the `inputs` part and the
+ *        skip layers' 1/sqrt(2) folded in:  l0: [W0[:,3:259] | W0[:,0:3]] ; odd l: W_l ;
+ *        l in {2,4,6}: [W_l[:,259:515] | W_l[:,256:259]]/sqrt2 then W_l[:,0:256]/sqrt2.
+ * zs_chain_mlp_fwd:  x <- x + fc2(GELU(fc1(LayerNorm(x))))           (model/shape/implicit.py:94-108, timm Mlp)
+ * zs_chain_occ_fwd:  out = MLPBlocks([xyz, LayerNorm(x)]) (+sigmoid)  (model/shape/implicit.py:275,168-184) */
+size_t zs_chain_mlp_blob_bytes(void);
+size_t zs_chain_occ_blob_bytes(void);
+int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
+                     const void* blob, const float* b1, const float* b2, int precision, void* stream);
+int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
+                     float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
+                     float* out, int apply_sigmoid, int precision, void* stream);
+
 /* NHWC convolution as implicit GEMM: y[b,oh,ow,co] = epi( sum x[b,oh*s+kh-pt,ow*s+kw-pl,ci] w[co,kh,kw,ci] ).
  * `pre_relu` applies ReLU to x on load (ResidualConvUnit_custom: model/depth/blocks.py:274-281).
  * Replaces nn.Conv2d in model/depth/blocks.py:58-70,247-253,305, dpt_depth.py:100-108,

@@ -1,0 +1,92 @@
+"""GPU: chained tcgen05 kernels (csrc/chain_tc.cu) against fp64 CPU math and the decoder oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_sm100():
+    from zeroshape_b200 import ops
+    if ops.device_cc() != 100:
+        pytest.skip("tcgen05 path needs sm_100")
+
+
+@pytest.mark.parametrize("M", [128, 1000, 19000])
+def test_chain_mlp_matches_fp64(cuda, M):
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 256, generator=g) * 1.5 + 0.3
+    w1, b1 = torch.randn(1024, 256, generator=g) / 16, torch.randn(1024, generator=g) * 0.1
+    w2, b2 = torch.randn(256, 1024, generator=g) / 32, torch.randn(256, generator=g) * 0.1
+    lw, lb = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    xd = x.double()
+    h = F.layer_norm(xd, (256,), lw.double(), lb.double(), 1e-6)
+    ref = xd + F.linear(F.gelu(F.linear(h, w1.double(), b1.double())), w2.double(), b2.double())
+    mats = []
+    for gi in range(4):
+        mats += [w1[256 * gi:256 * (gi + 1), :].to(cuda), w2[:, 256 * gi:256 * (gi + 1)].to(cuda)]
+    blob = ops.pack_tiles(mats)
+    for prec, tol in (("bf16x3", 3e-5), ("bf16", 3e-2)):
+        xc = x.clone().to(cuda)
+        ops.chain_mlp(xc, lw.to(cuda), lb.to(cuda), 1e-6, blob, b1.to(cuda), b2.to(cuda), prec)
+        err = (xc.cpu().double() - ref).abs().max().item()
+        assert err < tol * ref.abs().max().item(), (prec, err)
+
+
+@pytest.mark.parametrize("P", [1, 130, 5000])
+def test_chain_occ_matches_oracle_mlp(cuda, P):
+    _need_sm100()
+    from oracle.implicit import implicit_init, _occupancy_mlp, _ln
+    from zeroshape_b200.model.shape.implicit import Implicit
+    sd = implicit_init(seed=11)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(P)
+    x = torch.randn(P, 256, generator=g)
+    pts = torch.rand(P, 3, generator=g) * 3 - 1.5
+    with torch.no_grad():
+        sdd = {k: v.double() for k, v in sd.items()}
+        ref = _occupancy_mlp(pts.double(), _ln(x.double(), sdd, "norm"), sdd, "impl_mlp").squeeze(-1)
+    _, _, occ_blob, biases, w8, b8 = m._chain_blobs()
+    out = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8)
+    d = (out.cpu().double() - ref).abs()
+    rms = ref.pow(2).mean().sqrt().item()
+    assert d.max().item() < 1e-3 * max(ref.abs().max().item(), 0.1 * rms), (d.max().item(), rms)
+    assert (d / ref.abs().clamp_min(0.1 * rms)).max().item() < 1e-3
+    sig = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8, sigmoid=True)
+    assert (sig.cpu().double() - torch.sigmoid(ref)).abs().max().item() < 1e-5
+
+
+def test_decoder_chain_engine_parity_and_voxels(cuda):
+    _need_sm100()
+    from oracle.implicit import implicit_forward, implicit_init
+    from oracle import eval3d as E
+    from zeroshape_b200.model.shape.implicit import Implicit
+    sd = implicit_init(seed=12)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    m.engine = "chain"
+    g = torch.Generator().manual_seed(2)
+    lat, pts = torch.randn(2, 197, 256, generator=g), torch.rand(2, 3000, 3, generator=g) * 3 - 1.5
+    with torch.no_grad():
+        ref, _ = implicit_forward(sd, lat, pts)
+    out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
+    d = (out.cpu().double() - ref.double()).abs()
+    rms = ref.double().pow(2).mean().sqrt().item()
+    rel = (d / ref.double().abs().clamp_min(0.1 * rms)).max().item()
+    normwise = (d.pow(2).sum().sqrt() / ref.double().pow(2).sum().sqrt()).item()
+    print(f"chain max abs {d.max().item():.3e} max rel {rel:.3e} normwise {normwise:.3e}")
+    assert rel < 1e-3 and normwise < 1e-4
+    n = 21
+    occ_ref = E.level_grid(sd, lat[:1], n, -1.5, 1.5)
+    occ = m.grid_occupancy(lat[:1].to(cuda), n, -1.5, 1.5).cpu()
+    band = (occ_ref - 0.5).abs() > 2.5e-4
+    assert torch.equal((occ > 0.5)[band], (occ_ref > 0.5)[band]) and band.float().mean() > 0.99

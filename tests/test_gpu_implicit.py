@@ -25,9 +25,10 @@ def _module(sd, cuda, engine):
 
 
 def rel_err(a, b):
-    """max |a-b| / max(|b|, 1e-2 * max|b|): relative to the value, floored at 1% of the field's range."""
+    """Parity metric of DESIGN.md: max |a-b| / max(|b|, 0.1*rms(b)) -- relative error with a floor that keeps the
+    ratio defined where the logit crosses zero (the iso-surface)."""
     a, b = a.double().cpu(), b.double().cpu()
-    return ((a - b).abs() / b.abs().clamp_min(1e-2 * b.abs().max())).max().item()
+    return ((a - b).abs() / b.abs().clamp_min(0.1 * b.pow(2).mean().sqrt())).max().item()
 
 
 def test_state_dict_is_reference_compatible(cuda):
@@ -47,7 +48,7 @@ def test_f32_engine_matches_reference_golden(cuda):
     sd = fill_deterministic(implicit_init(0, recentre=False), int(g["seed"]))
     m = _module(sd, cuda, "f32")
     logits, attn = m(torch.from_numpy(g["latent"]).to(cuda), None, torch.from_numpy(g["points"]).to(cuda))
-    assert rel_err(logits, torch.from_numpy(g["logits"])) < 1e-5
+    assert rel_err(logits, torch.from_numpy(g["logits"])) < 1e-4      # plain-fp32 engine: 10x inside the 1e-3 bar
     np.testing.assert_allclose(attn.cpu().numpy(), g["attn"], rtol=0, atol=2e-7)
 
 
@@ -60,7 +61,7 @@ def test_f32_engine_matches_oracle_ragged(cuda, P):
     with torch.no_grad():
         ref, ref_attn = implicit_forward(sd, lat, pts)
     logits, attn = m(lat.to(cuda), None, pts.to(cuda))
-    assert rel_err(logits, ref) < 1e-5
+    assert rel_err(logits, ref) < 1e-4
     assert (attn.cpu() - ref_attn).abs().max() < 2e-7
     lg2, none = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
     assert none is None and torch.equal(lg2, logits)

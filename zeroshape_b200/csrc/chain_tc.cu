@@ -1,0 +1,492 @@
+// Chained tcgen05 kernels of the implicit decoder: consecutive layers of a 128-point tile stay on chip.
+//
+//   zs_chain_mlp_fwd : x <- x + fc2( GELU( fc1( LayerNorm(x) ) ) )           (timm Mlp inside ImplFuncBlock,
+//                                                                              model/shape/implicit.py:94-108)
+//   zs_chain_occ_fwd : logit = MLPBlocks([xyz, LayerNorm(x)])                 (final norm + impl_mlp,
+//                                                                              implicit.py:275,168-184)
+// Both are instances of one dataflow.  Per 128-row tile a sequence of GEMM steps D[128 x 256] (+)= A * W^T
+// runs on the tensor pipe; every A operand is a stream of 64-wide K-chunks in one of two smem rings:
+//   ring L : chunks converted from global fp32 (LayerNorm applied on the fly) by 4 loader warps,
+//   ring E : chunks written by the 8 epilogue warps straight from the previous step's TMEM accumulator
+//            (bias + GELU / Softplus + bf16 hi/lo split), i.e. layer l+1 consumes layer l without touching HBM/L2.
+// Accumulators ping-pong between the two 256-column halves of TMEM, so the epilogue of step s overlaps the MMAs
+// of step s+1 chunk by chunk.  Weights stream through a 3-slot ring of 32 KB tiles (cp.async.bulk / TMA 1-D) from
+// a blob that lists the (hi, lo) tiles in exactly the order the MMA warp consumes them.
+// Split-bf16 arithmetic as in gemm_tc.cu (precision 0: Ah*Wh + Al*Wh + Ah*Wl; 1: Ah*Wh).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace zs {
+using namespace tc;
+
+constexpr int CT_THREADS = 448;                 // warps: 0-3 loader, 4-11 epilogue, 12 MMA, 13 W loader
+constexpr int CT_TILE_BYTES = 256 * 64 * 2;     // one W tile (hi or lo): 256 rows x 64 bf16 = 32 KB
+constexpr int CT_A_HALF = 128 * 64 * 2;         // A chunk hi (or lo): 16 KB
+constexpr int CT_WSLOTS = 3, CT_LSLOTS = 2, CT_ESLOTS = 2;
+constexpr int CT_OFF_W = 0;
+constexpr int CT_OFF_L = CT_OFF_W + CT_WSLOTS * CT_TILE_BYTES;          // 96 KB
+constexpr int CT_OFF_E = CT_OFF_L + CT_LSLOTS * 2 * CT_A_HALF;          // +64 KB
+constexpr int CT_OFF_BAR = CT_OFF_E + CT_ESLOTS * 2 * CT_A_HALF;        // +64 KB = 224 KB
+constexpr int CT_SMEM = CT_OFF_BAR + 256 + 1024 /*row scratch*/ + 1024 /*align slack*/;
+
+struct ChainParams {
+  float* x; int ldx;             // [M, 256] residual stream (MLP: in/out; OCC: in)
+  const float* points;           // OCC: [M,3]
+  int M;
+  const float* ln_w; const float* ln_b; float ln_eps;
+  const uint8_t* blob;           // weight tiles in consumption order: [pair][hi 32K | lo 32K]
+  const float* bias;             // MLP: b1[1024] ; OCC: [8][256]
+  const float* bias2;            // MLP: b2[256]  ; OCC: w8[256]
+  float b8;                      // OCC: last-layer bias
+  float* out;                    // OCC: [M]
+  int apply_sigmoid;
+  int precision;
+};
+
+struct Bars {
+  uint32_t base;
+  __device__ uint32_t wfull(int i) const { return base + 8u * i; }
+  __device__ uint32_t wempty(int i) const { return base + 24u + 8u * i; }
+  __device__ uint32_t lfull(int i) const { return base + 48u + 8u * i; }
+  __device__ uint32_t lempty(int i) const { return base + 64u + 8u * i; }
+  __device__ uint32_t efull(int i) const { return base + 80u + 8u * i; }
+  __device__ uint32_t eempty(int i) const { return base + 96u + 8u * i; }
+  __device__ uint32_t tfull(int i) const { return base + 112u + 8u * i; }
+  __device__ uint32_t tempty(int i) const { return base + 128u + 8u * i; }
+  __device__ uint32_t tmem_slot() const { return base + 144u; }
+};
+
+struct Ring {   // index/phase walker of an n-slot mbarrier ring
+  int idx = 0; uint32_t phase = 0; int n;
+  __device__ explicit Ring(int n_) : n(n_) {}
+  __device__ void advance() { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+__device__ __forceinline__ float fast_softplus100(float x) {
+  // torch Softplus(beta=100, threshold=20) = x if 100x > 20 else log1p(exp(100x))/100
+  const float bx = 100.0f * x;
+  if (bx > 20.0f) return x;
+  const float u = __expf(bx);
+  const float l = u < 0.03125f ? u * (1.0f - u * (0.5f - u * (0.33333334f - 0.25f * u))) : __logf(1.0f + u);
+  return l * 0.01f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// common prologue: barriers + TMEM
+__device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen, uint32_t smem_base, int warp) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < CT_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
+    for (int i = 0; i < CT_LSLOTS; ++i) { mbar_init(B.lfull(i), 128); mbar_init(B.lempty(i), 1); }
+    for (int i = 0; i < CT_ESLOTS; ++i) { mbar_init(B.efull(i), 256); mbar_init(B.eempty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.tfull(i), 1); mbar_init(B.tempty(i), 256); }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(B.tmem_slot(), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
+}
+
+// MMA warp: consume one A chunk (hi at a_addr, lo at a_addr + 16K) against the next weight tile pair
+__device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Ring& wr, uint32_t a_addr, uint32_t d_tmem,
+                                          bool first, bool split, uint32_t a_empty_bar) {
+  const uint32_t idesc = umma_idesc_bf16(128, 256);
+  const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+  mbar_wait(B.wfull(wr.idx), wr.phase);
+  tc_fence_after();
+  {
+    const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      umma_bf16(d_tmem, a_hi + 2 * k, w + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+      if (split) umma_bf16(d_tmem, a_lo + 2 * k, w + 2 * k, idesc, 1u);
+    }
+    umma_commit(B.wempty(wr.idx));
+    wr.advance();
+  }
+  if (split) {
+    mbar_wait(B.wfull(wr.idx), wr.phase);
+    tc_fence_after();
+    const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, w + 2 * k, idesc, 1u);
+    umma_commit(B.wempty(wr.idx));
+    wr.advance();
+  }
+  umma_commit(a_empty_bar);
+}
+
+// W loader warp (one lane): stream `pairs` (hi,lo) tile pairs of the blob through the W ring
+__device__ __forceinline__ void w_stream(const Bars& B, uint32_t smem_base, Ring& wr, const uint8_t* blob, int pairs, bool split) {
+  for (int i = 0; i < pairs; ++i) {
+    const uint8_t* src = blob + (size_t)i * 2 * CT_TILE_BYTES;
+    for (int h = 0; h < (split ? 2 : 1); ++h) {
+      mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
+      mbar_arrive_expect_tx(B.wfull(wr.idx), CT_TILE_BYTES);
+      bulk_g2s(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES, src + (size_t)h * CT_TILE_BYTES, CT_TILE_BYTES, B.wfull(wr.idx));
+      wr.advance();
+    }
+  }
+}
+
+// loader thread: LayerNorm statistics of its row (two sweeps over L2-resident data)
+__device__ __forceinline__ void row_ln_stats(const float* xrow, bool ok, float eps, float& mean, float& rstd) {
+  float s = 0.f;
+  if (ok) {
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) { float4 v = __ldg(reinterpret_cast<const float4*>(xrow) + c); s += (v.x + v.y) + (v.z + v.w); }
+  }
+  mean = s * (1.0f / 256.0f);
+  float q = 0.f;
+  if (ok) {
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(xrow) + c);
+      float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  rstd = rsqrtf(q * (1.0f / 256.0f) + eps);
+}
+
+// loader thread: write 64 values (already in registers as 16 float4) as a swizzled (hi,lo) chunk row
+__device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const float4* buf, bool split) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 x0 = buf[2 * c], x1 = buf[2 * c + 1];
+    uint4 hi, lo;
+    split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+    split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+    split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+    split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(r, c);
+    *reinterpret_cast<uint4*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+
+// loader thread: fetch normalised x[:, 64kc .. 64kc+63] of its row into registers
+__device__ __forceinline__ void fetch_ln_chunk(const float* xrow, bool ok, int kc, float mean, float rstd,
+                                               const float* __restrict__ g, const float* __restrict__ b, float4* buf) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + kc * 64) + c);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + kc * 64) + c);
+    v.x = (v.x - mean) * rstd * gg.x + bb.x; v.y = (v.y - mean) * rstd * gg.y + bb.y;
+    v.z = (v.z - mean) * rstd * gg.z + bb.z; v.w = (v.w - mean) * rstd * gg.w + bb.w;
+    buf[c] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// epilogue thread: 32 accumulator columns -> act(d + bias) -> (hi,lo) bf16 -> its 4 16-byte chunks of a ring-E row
+template <int ACT>
+__device__ __forceinline__ void epi_to_ring(uint8_t* slot, int row, int hsel, const uint32_t (&rr)[32], const float* __restrict__ bias,
+                                            bool split) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = __uint_as_float(rr[c * 8 + j]) + __ldg(bias + c * 8 + j);
+      v[j] = ACT == ZS_ACT_GELU ? act_gelu_erf(t) : fast_softplus100(t);
+    }
+    uint4 hi, lo;
+    split_bf16x2(v[0], v[1], hi.x, lo.x);
+    split_bf16x2(v[2], v[3], hi.y, lo.y);
+    split_bf16x2(v[4], v[5], hi.z, lo.z);
+    split_bf16x2(v[6], v[7], hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(row, hsel * 4 + c);
+    *reinterpret_cast<uint4*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+
+// ===============================================================================================================
+// x <- x + fc2(GELU(fc1(LN(x))))      blob order: for g in 0..3: fc1[g] (4 pairs), fc2[:, g] (4 pairs)
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  Bars B{smem_base + CT_OFF_BAR};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
+  const int n_tiles = (p.M + 127) / 128;
+
+  if (warp < 4) {
+    // ---------------- loader: LN(x) chunks, 4 groups x 4 chunks per tile ----------------
+    const int r = threadIdx.x;
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + r;
+      const bool ok = m < p.M;
+      const float* xrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
+      float mean, rstd;
+      row_ln_stats(xrow, ok, p.ln_eps, mean, rstd);
+      fetch_ln_chunk(xrow, ok, 0, mean, rstd, p.ln_w, p.ln_b, buf);
+      for (int i = 0; i < 16; ++i) {
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (i + 1 < 16) fetch_ln_chunk(xrow, ok, (i + 1) & 3, mean, rstd, p.ln_w, p.ln_b, buf);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream(B, smem_base, wr, p.blob, 32, split);
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS), lr(CT_LSLOTS), er(CT_ESLOTS);
+      uint32_t te_phase[2] = {0, 0};
+      const uint32_t d0 = tmem_base, d1 = tmem_base + 256;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int g = 0; g < 4; ++g) {
+          mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
+          tc_fence_after();
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, d0, kc == 0, split, B.lempty(lr.idx));
+            lr.advance();
+          }
+          umma_commit(B.tfull(0));
+          if (g == 0) { mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1; tc_fence_after(); }
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.efull(er.idx), er.phase);
+            tc_fence_after();
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF, d1, g == 0 && kc == 0, split, B.eempty(er.idx));
+            er.advance();
+          }
+        }
+        umma_commit(B.tfull(1));
+      }
+    }
+  } else {
+    // ---------------- epilogue: 8 warps; lane quarter q, column half hsel ----------------
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    Ring er(CT_ESLOTS);
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + row;
+      for (int g = 0; g < 4; ++g) {
+        mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
+          tmem_ld_wait();
+          mbar_wait(B.eempty(er.idx), er.phase ^ 1);
+          epi_to_ring<ZS_ACT_GELU>(smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF, row, hsel, rr,
+                                   p.bias + g * 256 + c * 64 + hsel * 32, split);
+          fence_proxy_async_smem();
+          mbar_arrive(B.efull(er.idx));
+          er.advance();
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(0));
+      }
+      mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
+      tc_fence_after();
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + 256 + lane_off + c * 64 + hsel * 32, rr);
+        tmem_ld_wait();
+        if (m < p.M) {
+          float* xr = p.x + (int64_t)m * p.ldx + c * 64 + hsel * 32;
+          const float* b2 = p.bias2 + c * 64 + hsel * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(b2) + j);
+            xv.x += __uint_as_float(rr[4 * j + 0]) + bv.x; xv.y += __uint_as_float(rr[4 * j + 1]) + bv.y;
+            xv.z += __uint_as_float(rr[4 * j + 2]) + bv.z; xv.w += __uint_as_float(rr[4 * j + 3]) + bv.w;
+            *reinterpret_cast<float4*>(xr + 4 * j) = xv;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(B.tempty(1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ===============================================================================================================
+// logit = MLPBlocks([xyz, LN(x)])   (8 hidden layers, skips at 2,4,6, Softplus(100), last layer 256 -> 1)
+// A chunks of ring L: 4 x LN(x) then 1 x [xyz, 0...]  (K order = [feat | xyz]; weights permuted to match at pack time)
+// blob order: l0: 5 pairs (feat 4, xyz 1); l1: 4; l2: 5 (inputs) + 4 (h); l3: 4; l4: 5+4; l5: 4; l6: 5+4; l7: 4   = 48 pairs
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  Bars B{smem_base + CT_OFF_BAR};
+  float* row_scratch = reinterpret_cast<float*>(smem_gen + CT_OFF_BAR + 256);   // [128] partial dots
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
+  const int n_tiles = (p.M + 127) / 128;
+
+  if (warp < 4) {
+    const int r = threadIdx.x;
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + r;
+      const bool ok = m < p.M;
+      const float* xrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
+      float mean, rstd;
+      row_ln_stats(xrow, ok, p.ln_eps, mean, rstd);
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (ok) { px = __ldg(p.points + (int64_t)m * 3); py = __ldg(p.points + (int64_t)m * 3 + 1); pz = __ldg(p.points + (int64_t)m * 3 + 2); }
+      for (int rep = 0; rep < 4; ++rep) {
+        for (int kc = 0; kc < 5; ++kc) {
+          if (kc < 4) {
+            fetch_ln_chunk(xrow, ok, kc, mean, rstd, p.ln_w, p.ln_b, buf);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            buf[0] = make_float4(px, py, pz, 0.f);
+          }
+          mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+          store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+          fence_proxy_async_smem();
+          mbar_arrive(B.lfull(lr.idx));
+          lr.advance();
+        }
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream(B, smem_base, wr, p.blob, 48, split);
+    }
+  } else if (warp == 12) {
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS), lr(CT_LSLOTS), er(CT_ESLOTS);
+      uint32_t te_phase[2] = {0, 0};
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int l = 0; l < 8; ++l) {
+          const int half = l & 1;
+          const uint32_t d = tmem_base + half * 256;
+          mbar_wait(B.tempty(half), te_phase[half] ^ 1); te_phase[half] ^= 1;
+          tc_fence_after();
+          const int nL = (l & 1) ? 0 : 5, nE = l == 0 ? 0 : 4;
+          for (int i = 0; i < nL; ++i) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, d, i == 0, split, B.lempty(lr.idx));
+            lr.advance();
+          }
+          for (int i = 0; i < nE; ++i) {
+            mbar_wait(B.efull(er.idx), er.phase);
+            tc_fence_after();
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF, d, nL == 0 && i == 0, split, B.eempty(er.idx));
+            er.advance();
+          }
+          umma_commit(B.tfull(half));
+        }
+      }
+    }
+  } else {
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    Ring er(CT_ESLOTS);
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + row;
+      for (int l = 0; l < 8; ++l) {
+        const int half = l & 1;
+        mbar_wait(B.tfull(half), tf_phase[half]); tf_phase[half] ^= 1;
+        tc_fence_after();
+        float dot = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + half * 256 + lane_off + c * 64 + hsel * 32, rr);
+          tmem_ld_wait();
+          const float* bl = p.bias + l * 256 + c * 64 + hsel * 32;
+          if (l < 7) {
+            mbar_wait(B.eempty(er.idx), er.phase ^ 1);
+            epi_to_ring<ZS_ACT_SOFTPLUS100>(smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF, row, hsel, rr, bl, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.efull(er.idx));
+            er.advance();
+          } else {
+            const float* w8 = p.bias2 + c * 64 + hsel * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(fast_softplus100(__uint_as_float(rr[j]) + __ldg(bl + j)), __ldg(w8 + j), dot);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(half));
+        if (l == 7) {
+          // combine the two column halves of each row: hsel 1 publishes, hsel 0 finishes (named barrier 1, 256 threads)
+          if (hsel == 1) row_scratch[row] = dot;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (hsel == 0 && m < p.M) {
+            float v = dot + row_scratch[row] + p.b8;
+            p.out[m] = p.apply_sigmoid ? 1.0f / (1.0f + __expf(-v)) : v;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static int chain_launch(void (*kern)(ChainParams), const ChainParams& p, cudaStream_t st, const char* name) {
+  ZS_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+  int tiles = (p.M + 127) / 128;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, CT_THREADS, CT_SMEM, st>>>(p);
+  ZS_CUDA_CHECK_LAUNCH(name);
+  return ZS_OK;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" size_t zs_chain_mlp_blob_bytes(void) { return (size_t)32 * 2 * CT_TILE_BYTES; }
+extern "C" size_t zs_chain_occ_blob_bytes(void) { return (size_t)48 * 2 * CT_TILE_BYTES; }
+
+extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
+                                const void* blob, const float* b1, const float* b2, int precision, void* stream) {
+  ZS_REQUIRE(x && ln_w && ln_b && blob && b1 && b2 && M >= 0, "zs_chain_mlp_fwd: null pointer");
+  ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_mlp_fwd: x must be 16B aligned, ldx%4==0");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (precision == 0 || precision == 1), "zs_chain_mlp_fwd: bad blob/precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = x; p.ldx = ldx; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
+  p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
+  return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
+}
+
+extern "C" int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
+                                float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
+                                float* out, int apply_sigmoid, int precision, void* stream) {
+  ZS_REQUIRE(x && points && ln_w && ln_b && blob && biases && w8 && out && M >= 0, "zs_chain_occ_fwd: null pointer");
+  ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_occ_fwd: x must be 16B aligned, ldx%4==0");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (precision == 0 || precision == 1), "zs_chain_occ_fwd: bad blob/precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = const_cast<float*>(x); p.ldx = ldx; p.points = points; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
+  p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = biases; p.bias2 = w8; p.b8 = b8; p.out = out;
+  p.apply_sigmoid = apply_sigmoid; p.precision = precision;
+  return chain_launch(chain_occ_kernel, p, as_stream(stream), "zs_chain_occ_fwd");
+}

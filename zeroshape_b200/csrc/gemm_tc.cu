@@ -7,12 +7,12 @@
 //               -> ~2^-16 relative error per product (parity mode, meets the 1e-3 bar with margin)
 //   1 "bf16"  : D += Ah*Wh only (fast mode, ~1e-2 relative on the decoder logits -- not parity)
 //
-// CTA = 320 threads, persistent over 128x256 output tiles, warp-specialised:
-//   warps 0-3  A producers : fp32 rows -> (hi,lo) bf16 -> 128B-swizzled K-major smem tiles (generic proxy
-//                             stores + fence.proxy.async), one row per thread
-//   warps 4-7  epilogue    : tcgen05.ld accumulator rows -> bias / activation / residual -> fp32 global
-//   warp  8    MMA issuer  : one elected lane issues tcgen05.mma (M=128,N=256,K=16), commits to mbarriers
-//   warp  9    W loader    : cp.async.bulk (TMA 1-D) of pre-swizzled weight tiles, complete_tx on mbarriers
+// CTA = 448 threads, persistent over 128x256 output tiles, warp-specialised:
+//   warps 0-3   A producers : fp32 rows -> (hi,lo) bf16 -> 128B-swizzled K-major smem tiles (generic proxy
+//                              stores + fence.proxy.async), one row per thread
+//   warps 4-11  epilogue    : tcgen05.ld accumulator rows -> bias / activation / residual -> fp32 global
+//   warp  12    MMA issuer  : one elected lane issues tcgen05.mma (M=128,N=256,K=16), commits to mbarriers
+//   warp  13    W loader    : cp.async.bulk (TMA 1-D) of pre-swizzled weight tiles, complete_tx on mbarriers
 // smem: 2 stages x (A_hi 16K + A_lo 16K + W_hi 32K + W_lo 32K) = 192 KB; TMEM: 2 x 256 fp32 columns
 // (accumulator double buffer: the epilogue of tile i overlaps the MMAs of tile i+1).
 #include "common.cuh"
@@ -26,7 +26,7 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB (one of hi/lo)
 constexpr int TC_B_TILE = TC_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_TILE + 2 * TC_B_TILE;  // 96 KB
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;   // warps 0-3 A producers, 4-11 epilogue, 12 MMA issuer, 13 W loader
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TcParams {
@@ -40,6 +40,82 @@ struct TcParams {
   int precision;
   int m_tiles, n_tiles, k_chunks;
 };
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  if (ACT == ZS_ACT_RELU) return fmaxf(x, 0.0f);
+  if (ACT == ZS_ACT_GELU) return act_gelu_erf(x);
+  if (ACT == ZS_ACT_SOFTPLUS100) return act_softplus100(x);
+  if (ACT == ZS_ACT_SIGMOID) return act_sigmoid(x);
+  if (ACT == ZS_ACT_CLAMP01) return fminf(fmaxf(x, 0.0f), 1.0f);
+  return x;
+}
+
+// one epilogue thread: its row, 128 accumulator columns starting at `taddr`, in 4 pieces of 32
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t taddr, int m, int nbase) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+    const int n0 = nbase + c0;
+    if (m < p.M && n0 < p.N) {
+      float* crow = p.C + (int64_t)m * p.ldc + n0;
+      const float* rrow = p.res_mode != ZS_RES_NONE ? p.res + (int64_t)m * p.ldres + n0 : nullptr;
+      const bool full = n0 + 32 <= p.N;
+      const bool vec_c = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      const bool vec_r = rrow && full && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      if (p.bias) {
+        if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        }
+      }
+      float rv[32];
+      if (rrow) {
+        if (vec_r) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+            rv[4 * j] = x.x; rv[4 * j + 1] = x.y; rv[4 * j + 2] = x.z; rv[4 * j + 3] = x.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rv[j] = (n0 + j < p.N) ? __ldg(rrow + j) : 0.f;
+        }
+        if (p.res_mode == ZS_RES_BEFORE_ACT) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = act_ct<ACT>(v[j] + rv[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = act_ct<ACT>(v[j]) + rv[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_ct<ACT>(v[j]);
+      }
+      if (vec_c) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) crow[j] = v[j];
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -64,11 +140,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);        // one tcgen05.commit
-      mbar_init(tempty_bar(a), 128);     // 128 epilogue threads
+      mbar_init(tempty_bar(a), 256);     // 256 epilogue threads
     }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ================= W loader =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -145,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ================= MMA issuer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -178,65 +254,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
       }
     }
   } else {
-    // ================= epilogue (warps 4..7 -> TMEM lane quarters 0..3) =================
-    const int q = warp & 3;
+    // ================= epilogue: 8 warps; warp e -> TMEM lane quarter e&3, column half e>>2 =================
+    // (two warps per SM sub-partition and a compile-time activation: a single warp per scheduler running a
+    //  jump-table per element was latency-bound at ~0.2 IPC -- profiles/r1_gemm_tc_v0.md)
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
       const int m = mt * TC_BM + q * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(taddr + c0, rr);
-        tmem_ld_wait();
-        const int n0 = nt * TC_BN + c0;
-        if (m < p.M && n0 < p.N) {
-          float* crow = p.C + (int64_t)m * p.ldc + n0;
-          const float* rrow = p.res_mode != ZS_RES_NONE ? p.res + (int64_t)m * p.ldres + n0 : nullptr;
-          const bool full = n0 + 32 <= p.N;
-          const bool vec_c = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-          const bool vec_r = rrow && full && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (full || n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
-          }
-          float rv[32];
-          if (rrow) {
-            if (vec_r) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 x = __ldg(reinterpret_cast<const float4*>(rrow) + j);
-                rv[4 * j] = x.x; rv[4 * j + 1] = x.y; rv[4 * j + 2] = x.z; rv[4 * j + 3] = x.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) rv[j] = (n0 + j < p.N) ? __ldg(rrow + j) : 0.f;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = v[j];
-            if (p.res_mode == ZS_RES_BEFORE_ACT) x += rv[j];
-            x = apply_act(x, p.act);
-            if (p.res_mode == ZS_RES_AFTER_ACT) x += rv[j];
-            v[j] = x;
-          }
-          if (vec_c) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) crow[j] = v[j];
-          }
-        }
+      const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16) + hsel * 128;
+      const int nbase = nt * TC_BN + hsel * 128;
+      switch (p.act) {
+        case ZS_ACT_RELU: tc_epilogue_half<ZS_ACT_RELU>(p, taddr, m, nbase); break;
+        case ZS_ACT_GELU: tc_epilogue_half<ZS_ACT_GELU>(p, taddr, m, nbase); break;
+        case ZS_ACT_SOFTPLUS100: tc_epilogue_half<ZS_ACT_SOFTPLUS100>(p, taddr, m, nbase); break;
+        case ZS_ACT_SIGMOID: tc_epilogue_half<ZS_ACT_SIGMOID>(p, taddr, m, nbase); break;
+        case ZS_ACT_CLAMP01: tc_epilogue_half<ZS_ACT_CLAMP01>(p, taddr, m, nbase); break;
+        default: tc_epilogue_half<ZS_ACT_NONE>(p, taddr, m, nbase); break;
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -246,7 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -149,11 +149,43 @@ class Implicit(nn.Module):
             return ops.gemm_tc(x2d, pw, mod.bias, res=res, act=act, precision=self.precision)
         return ops.gemm(x2d, mod.weight, mod.bias, res=res, act=act)
 
-    def _points_chain(self, lat, pts, attn_out=None, tc=False):
+    # chained tcgen05 kernels (csrc/chain_tc.cu): weight blobs in MMA consumption order, rebuilt on weight change
+    def _chain_ok(self):
+        return self.n_channels == 256 and len(self.impl_mlp.layers) == 9 and self.skip_in == [2, 4, 6] and \
+            all(b.mlp.fc1.weight.shape == (1024, 256) for b in self.blocks_attn)
+
+    def _chain_blobs(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_chain_cache", None) is None or self._chain_cache[0] != key:
+            mlp = []
+            for blk in self.blocks_attn:
+                w1, w2 = blk.mlp.fc1.weight.detach(), blk.mlp.fc2.weight.detach()
+                mats = []
+                for g in range(4):
+                    mats += [w1[256 * g:256 * (g + 1), :], w2[:, 256 * g:256 * (g + 1)]]
+                mlp.append(ops.pack_tiles(mats))
+            L = [lin.weight.detach() for lin in self.impl_mlp.layers]
+            s = 1.0 / SQRT2
+            mats = [torch.cat([L[0][:, 3:259], L[0][:, 0:3]], dim=1)]            # K order [feat | xyz]
+            for l in range(1, 8):
+                if l in self.skip_in:                                             # cat([h, xyz, feat]) / sqrt(2)
+                    mats += [torch.cat([L[l][:, 259:515], L[l][:, 256:259]], dim=1) * s, L[l][:, 0:256] * s]
+                else:
+                    mats.append(L[l])
+            occ = ops.pack_tiles(mats)
+            biases = torch.stack([lin.bias.detach() for lin in self.impl_mlp.layers[:8]]).contiguous()
+            w8 = self.impl_mlp.layers[8].weight.detach().reshape(-1).contiguous()
+            self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()))
+        return self._chain_cache
+
+    def _points_chain(self, lat, pts, attn_out=None, tc=False, sigmoid=False):
         """pts [B,P,3] contiguous -> logits [B,P]; optionally fills attn_out [B,P,L]."""
         B, P, _ = pts.shape
         C = self.n_channels
         nb = len(self.blocks_attn)
+        chain = tc and self.engine != "tc" and self._chain_ok()
+        if chain:
+            _, mlp_blobs, occ_blob, occ_biases, w8, b8 = self._chain_blobs()
         x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
             k_lat, v_lat = lat["kv"][l]
@@ -162,9 +194,17 @@ class Implicit(nn.Module):
                                     attn_scale=1.0 / nb, attn_accumulate=(l > 0)).view(B * P, C)
             del qkv
             x = self._lin(a, blk.attn.proj, tc, res=x)
+            if chain:
+                ops.chain_mlp(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, mlp_blobs[l], blk.mlp.fc1.bias,
+                              blk.mlp.fc2.bias, self.precision)
+                continue
             h = self._lin(self._ln(x, blk.norm2), blk.mlp.fc1, tc, act=ops.ACT_GELU)
             x = self._lin(h, blk.mlp.fc2, tc, res=x)
             del h
+        if chain:
+            out = ops.chain_occ(x, pts.reshape(B * P, 3), self.norm.weight, self.norm.bias, self.norm.eps, occ_blob,
+                                occ_biases, w8, b8, sigmoid=sigmoid, precision=self.precision)
+            return out.reshape(B, P)
         feat = self._ln(x, self.norm)
         inputs = ops.concat2(pts.reshape(B * P, 3), feat, 1.0)
         h = inputs

@@ -106,6 +106,38 @@ def gemm_tc(a, pw, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=Non
     return out
 
 
+def pack_tiles(mats):
+    """Concatenate zs_gemm_tc_pack images of fp32 matrices [256, K] (K padded to 64) -> uint8 blob."""
+    blobs = []
+    for w in mats:
+        w = w.detach().float().contiguous()
+        assert w.shape[0] == 256, w.shape
+        b = torch.empty(lib.zs_gemm_tc_packed_bytes(256, w.shape[1]), device=w.device, dtype=torch.uint8)
+        check(lib.zs_gemm_tc_pack(_p(w), w.stride(0), 256, w.shape[1], _p(b), _stream()), "zs_gemm_tc_pack")
+        blobs.append(b)
+    return torch.cat(blobs)
+
+
+def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
+    """In place: x[M,256] <- x + fc2(GELU(fc1(LayerNorm(x)))) on the chained tcgen05 kernel."""
+    assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+    assert blob.numel() == lib.zs_chain_mlp_blob_bytes()
+    check(lib.zs_chain_mlp_fwd(_p(x), x.stride(0), x.shape[0], _p(ln_w), _p(ln_b), ln_eps, _p(blob), _p(b1), _p(b2),
+                               PRECISIONS[precision], _stream()), "zs_chain_mlp_fwd")
+    return x
+
+
+def chain_occ(x, points, ln_w, ln_b, ln_eps, blob, biases, w8, b8, sigmoid=False, precision="bf16x3"):
+    """logits[M] = MLPBlocks([points, LayerNorm(x)]) on the chained tcgen05 kernel."""
+    assert x.dim() == 2 and x.shape[1] == 256 and x.stride(1) == 1 and points.shape == (x.shape[0], 3)
+    _chk(points, "points"); _chk(biases, "biases"); _chk(w8, "w8")
+    assert blob.numel() == lib.zs_chain_occ_blob_bytes()
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    check(lib.zs_chain_occ_fwd(_p(x), x.stride(0), _p(points), x.shape[0], _p(ln_w), _p(ln_b), ln_eps, _p(blob), _p(biases),
+                               _p(w8), float(b8), _p(out), int(sigmoid), PRECISIONS[precision], _stream()), "zs_chain_occ_fwd")
+    return out
+
+
 def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE):
     """F.linear on the last dim of a contiguous tensor."""
     shp = x.shape
