@@ -121,6 +121,8 @@ def run_ours(args, rank, world, dev):
     net = graph.impl_network
     net.engine = args.engine
     net.precision = args.precision
+    if args.attention:
+        net.attention = args.attention
     rgb_host, mask_host = synthetic_images(args.shapes, 1000 + rank)
     rgb_host, mask_host = rgb_host.pin_memory(), mask_host.pin_memory()
     rgb_dev, mask_dev = rgb_host.to(dev), mask_host.to(dev)
@@ -131,7 +133,7 @@ def run_ours(args, rank, world, dev):
         lg, _ = net(var.latent_depth, None, probe, need_attn=False)
         net.impl_mlp.layers[-1].bias -= lg.median()
         assert torch.isfinite(var.latent_depth).all() and torch.isfinite(lg).all(), "synthetic model is degenerate"
-    engine = "fused" if net._use_fused() else ("tc" if net._use_tc() else "f32")
+    engine = "fused" if net._use_fused() else (("tc" if net.engine == "tc" else "chain") if net._use_tc() else "f32")
     out_host = torch.empty(args.shapes, 10000, 3).pin_memory()
     dec_events, enc_events = [], []
 
@@ -215,7 +217,7 @@ def run_ours(args, rank, world, dev):
         "config": {"workload": f"demo.py/evaluate.py hot path per shape: 224x224 RGB+mask -> DPT-hybrid depth + intrinsics -> unproject/"
                                f"normalise -> CoordEncRes latents -> implicit decoder over the ({args.vox_res}+1)^3 grid -> marching cubes "
                                f"-> 10k-point surface sample; {args.shapes} shape(s)/GPU/step, random-init weights",
-                   "vox_res": args.vox_res, "query_points_per_shape": pts, "engine": engine, "shapes_per_gpu": args.shapes,
+                   "vox_res": args.vox_res, "query_points_per_shape": pts, "engine": engine, "attention": net.attention, "shapes_per_gpu": args.shapes,
                    "parallelism": f"shape-per-GPU x{world}", "l2_policy": "grid outputs (8.6 MB/shape) + workspaces exceed nothing; "
                    "per-step working set re-written each step, inputs regenerated in-kernel (no cached outputs)"},
         "decoder_points_per_s": pts / (dec_avg * 1e-3) * world,
@@ -313,8 +315,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vox-res", type=int, default=128)
     ap.add_argument("--shapes", type=int, default=1, help="shapes per GPU per step")
-    ap.add_argument("--engine", default="auto", choices=["auto", "fused", "tc", "f32"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--attention", default=None, choices=["tc", "f32"])
     ap.add_argument("--cpu-slices", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

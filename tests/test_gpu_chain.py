@@ -90,3 +90,50 @@ def test_decoder_chain_engine_parity_and_voxels(cuda):
     occ = m.grid_occupancy(lat[:1].to(cuda), n, -1.5, 1.5).cpu()
     band = (occ_ref - 0.5).abs() > 2.5e-4
     assert torch.equal((occ > 0.5)[band], (occ_ref > 0.5)[band]) and band.float().mean() > 0.99
+
+
+@pytest.mark.parametrize("M", [128, 1000, 4224])
+def test_tensor_core_attention_matches_f32_kernel_and_reference_math(cuda, M):
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    L, C, H = 197, 256, 8
+    qkv = torch.randn(M, 3 * C, generator=g)
+    lat_qkv = torch.randn(1, L, 3 * C, generator=g)
+    k_lat, v_lat = lat_qkv[..., C:2 * C], lat_qkv[..., 2 * C:]
+    # reference math (model/shape/implicit.py:38-57) in fp64
+    q, k, v = [t.double().reshape(M, H, 32).permute(1, 0, 2) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])]
+    kl = k_lat[0].double().reshape(L, H, 32).permute(1, 0, 2)
+    vl = v_lat[0].double().reshape(L, H, 32).permute(1, 0, 2)
+    s = torch.cat([q @ kl.transpose(1, 2), (q * k).sum(-1, keepdim=True)], -1) * 32 ** -0.5
+    a = s.softmax(-1)
+    ref = (a[..., :L] @ vl + a[..., L:] * v).permute(1, 0, 2).reshape(M, C)
+    lat_dev = lat_qkv.to(cuda)
+    kp, vp = ops.attn_pack_kv(lat_dev[0, :, C:2 * C], lat_dev[0, :, 2 * C:], H)
+    out = ops.attn_tc(qkv.to(cuda), kp, vp, L, 32 ** -0.5)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5 * ref.abs().max().item(), err
+    f32 = ops.point_attention(qkv.to(cuda).view(1, M, 3 * C), lat_dev[..., C:2 * C], lat_dev[..., 2 * C:], H)
+    assert (f32.view(M, C).cpu().double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
+def test_decoder_with_tensor_core_attention(cuda):
+    _need_sm100()
+    from oracle.implicit import implicit_forward, implicit_init
+    from zeroshape_b200.model.shape.implicit import Implicit
+    sd = implicit_init(seed=13)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    m.engine, m.attention = "chain", "tc"
+    g = torch.Generator().manual_seed(3)
+    lat, pts = torch.randn(2, 197, 256, generator=g), torch.rand(2, 2000, 3, generator=g) * 3 - 1.5
+    with torch.no_grad():
+        ref, _ = implicit_forward(sd, lat, pts)
+    out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
+    d = (out.cpu().double() - ref.double()).abs()
+    rms = ref.double().pow(2).mean().sqrt().item()
+    rel = (d / ref.double().abs().clamp_min(0.1 * rms)).max().item()
+    print(f"chain+tc-attn max abs {d.max().item():.3e} max rel {rel:.3e}")
+    assert rel < 1e-3

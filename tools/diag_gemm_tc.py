@@ -83,3 +83,47 @@ for (M, N, K) in ((148 * 128 * 8, 256, 256), (148 * 128 * 8, 1024, 256), (148 * 
     log(f"[time] M={M} N={N} K={K} f32-ffma: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 os.makedirs("gpurun_out", exist_ok=True)
 open("gpurun_out/diag_gemm_tc.txt", "w").write("\n".join(out_lines) + "\n")
+
+# ---- chained kernels ------------------------------------------------------------------------------------
+try:
+    M = 148 * 128 * 8
+    g = torch.Generator().manual_seed(3)
+    w1 = (torch.randn(1024, 256, generator=g) / 16).to(dev); w2 = (torch.randn(256, 1024, generator=g) / 32).to(dev)
+    b1 = torch.zeros(1024, device=dev); b2 = torch.zeros(256, device=dev)
+    lw, lb = torch.ones(256, device=dev), torch.zeros(256, device=dev)
+    mats = []
+    for gi in range(4):
+        mats += [w1[256 * gi:256 * (gi + 1), :], w2[:, 256 * gi:256 * (gi + 1)]]
+    blob = ops.pack_tiles(mats)
+    x0 = torch.randn(M, 256, device=dev)
+    for prec in ("bf16x3", "bf16"):
+        x = x0.clone()
+        for _ in range(2):
+            ops.chain_mlp(x, lw, lb, 1e-6, blob, b1, b2, prec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.chain_mlp(x, lw, lb, 1e-6, blob, b1, b2, prec)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        log(f"[time] chain_mlp M={M} {prec}: {ms:.3f} ms  {2 * M * 2 * 256 * 1024 / ms / 1e9:.1f} TFLOP/s (algorithmic)  {M / ms / 1e3:.1f} Mpts/s")
+    from zeroshape_b200.model.shape.implicit import Implicit
+    net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                   pos_perlayer=False).to(dev).eval()
+    _, _, occ_blob, biases, w8, b8 = net._chain_blobs()
+    pts = torch.rand(M, 3, device=dev)
+    for prec in ("bf16x3", "bf16"):
+        for _ in range(2):
+            ops.chain_occ(x0, pts, net.norm.weight, net.norm.bias, 1e-6, occ_blob, biases, w8, b8, precision=prec)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ops.chain_occ(x0, pts, net.norm.weight, net.norm.bias, 1e-6, occ_blob, biases, w8, b8, precision=prec)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        log(f"[time] chain_occ M={M} {prec}: {ms:.3f} ms  {2 * M * 724224 / ms / 1e9:.1f} TFLOP/s (algorithmic)  {M / ms / 1e3:.1f} Mpts/s")
+except Exception as ex:
+    log("chain diag failed:", repr(ex))
+open("gpurun_out/diag_gemm_tc.txt", "w").write("\n".join(out_lines) + "\n")

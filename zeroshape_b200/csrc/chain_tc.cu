@@ -64,11 +64,15 @@ struct Ring {   // index/phase walker of an n-slot mbarrier ring
 
 __device__ __forceinline__ float fast_softplus100(float x) {
   // torch Softplus(beta=100, threshold=20) = x if 100x > 20 else log1p(exp(100x))/100
+  // Accurate to ~1e-7 relative with ~20 instructions: log1p(e^t) = max(t,0) + log1p(e^-|t|); log1p(u), u in (0,1], via
+  // 2*atanh(u/(2+u)) (odd series, z <= 1/3) -- avoids the cancellation of log(1+u) for small u.
   const float bx = 100.0f * x;
   if (bx > 20.0f) return x;
-  const float u = __expf(bx);
-  const float l = u < 0.03125f ? u * (1.0f - u * (0.5f - u * (0.33333334f - 0.25f * u))) : __logf(1.0f + u);
-  return l * 0.01f;
+  const float u = exp2f(-fabsf(bx) * 1.4426950408889634f);
+  const float z = __fdividef(u, 2.0f + u);
+  const float z2 = z * z;
+  const float l = 2.0f * z * (1.0f + z2 * (0.33333334f + z2 * (0.2f + z2 * (0.14285715f + z2 * (0.11111111f + z2 * (0.09090909f + z2 * 0.07692308f))))));
+  return (fmaxf(bx, 0.0f) + l) * 0.01f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

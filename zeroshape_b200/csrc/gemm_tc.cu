@@ -27,7 +27,7 @@ constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB (one of hi/lo)
 constexpr int TC_B_TILE = TC_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_TILE + 2 * TC_B_TILE;  // 96 KB
 constexpr int TC_THREADS = 448;   // warps 0-3 A producers, 4-11 epilogue, 12 MMA issuer, 13 W loader
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*softmax exchange*/;
 
 struct TcParams {
   const float* A; int lda;
@@ -39,6 +39,12 @@ struct TcParams {
   int act;
   int precision;
   int m_tiles, n_tiles, k_chunks;
+  // grouped mode (attention): n-tile `nt` reads its A columns from nt*a_nt_off and writes its C columns at
+  // nt*c_nt_off; only n_tile_valid (<= 256) columns of a tile are real and the MMA runs with N = mma_n.
+  int a_nt_off, c_nt_off, n_tile_valid, mma_n;
+  uint32_t w_tile_bytes;       // bytes of one (hi or lo) weight tile actually needed: mma_n rows x 128 B
+  int epi_mode;                // 0: bias / activation / residual;  1: attention softmax (tc_epilogue_softmax)
+  const float* qkv; int ld_qkv; float* R; float scale; int n_keys;
 };
 
 template <int ACT>
@@ -51,26 +57,29 @@ __device__ __forceinline__ float act_ct(float x) {
   return x;
 }
 
-// one epilogue thread: its row, 128 accumulator columns starting at `taddr`, in 4 pieces of 32
+// one epilogue thread: its row, the 128 accumulator columns [hsel*128, hsel*128+128) of n-tile `nt`, in 4 pieces of 32
 template <int ACT>
-__device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t taddr, int m, int nbase) {
+__device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t taddr, int m, int nt, int hsel) {
 #pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
     uint32_t rr[32];
     tmem_ld_32x32(taddr + c0, rr);
     tmem_ld_wait();
-    const int n0 = nbase + c0;
-    if (m < p.M && n0 < p.N) {
+    const int lc = hsel * 128 + c0;                       // column inside the tile
+    const int n0 = nt * p.c_nt_off + lc;                  // column in C / bias / residual
+    int nvalid = p.n_tile_valid - lc;
+    if (p.N - n0 < nvalid) nvalid = p.N - n0;
+    if (m < p.M && nvalid > 0) {
       float* crow = p.C + (int64_t)m * p.ldc + n0;
       const float* rrow = p.res_mode != ZS_RES_NONE ? p.res + (int64_t)m * p.ldres + n0 : nullptr;
-      const bool full = n0 + 32 <= p.N;
-      const bool vec_c = full && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-      const bool vec_r = rrow && full && ((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0);
+      const bool full = nvalid >= 32;
+      const bool vec_c = full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
+      const bool vec_r = rrow && full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
       if (p.bias) {
-        if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+        if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
@@ -78,7 +87,7 @@ __device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t tad
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] += (j < nvalid) ? __ldg(p.bias + n0 + j) : 0.f;
         }
       }
       float rv[32];
@@ -91,7 +100,7 @@ __device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t tad
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) rv[j] = (n0 + j < p.N) ? __ldg(rrow + j) : 0.f;
+          for (int j = 0; j < 32; ++j) rv[j] = (j < nvalid) ? __ldg(rrow + j) : 0.f;
         }
         if (p.res_mode == ZS_RES_BEFORE_ACT) {
 #pragma unroll
@@ -111,8 +120,86 @@ __device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t tad
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.N) crow[j] = v[j];
+          if (j < nvalid) crow[j] = v[j];
       }
+    }
+  }
+}
+
+// Attention scores epilogue (model/shape/implicit.py:38-57).  The accumulator row holds the raw scores q_h . k_j of
+// one query point against the n_keys latent keys of head `nt`; the softmax also runs over the point's own key
+// (s_self = q_h . k_p,h).  The two threads that share a row (column halves) exchange max / sum through `xch`.
+// Writes normalised probabilities P[m, nt*c_nt_off + j] (0 for the padding columns) and the self-value term
+// R[m, 32*nt + d] = p_self * v_p,h[d], which the P.V GEMM adds as its residual.
+__device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t taddr, int m, int nt, int hsel, int row,
+                                                    float* xch) {
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const bool ok = m < p.M;
+  const float* qrow = p.qkv + (int64_t)(ok ? m : 0) * p.ld_qkv + nt * 32;      // q | k (+256) | v (+512)
+  float s_self = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; d += 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(qrow + d));
+    const float4 k = __ldg(reinterpret_cast<const float4*>(qrow + 256 + d));
+    s_self = fmaf(q.x, k.x, s_self); s_self = fmaf(q.y, k.y, s_self); s_self = fmaf(q.z, k.z, s_self); s_self = fmaf(q.w, k.w, s_self);
+  }
+  const int lc0 = hsel * 128;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (lc0 + c0 + j < p.n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
+  }
+  xch[hsel * 128 + row] = mx;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  mx = fmaxf(fmaxf(xch[row], xch[128 + row]), s_self);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (lc0 + c0 + j < p.n_keys) sum += exp2f((__uint_as_float(rr[j]) - mx) * sl2);
+  }
+  xch[hsel * 128 + row] = sum;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float e_self = exp2f((s_self - mx) * sl2);
+  const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+    const int lc = lc0 + c0;
+    const int nvalid = p.n_tile_valid - lc;
+    if (ok && nvalid > 0) {
+      float* prow = p.C + (int64_t)m * p.ldc + nt * p.c_nt_off + lc;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (lc + j < p.n_keys) ? exp2f((__uint_as_float(rr[j]) - mx) * sl2) * inv : 0.f;
+      if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(prow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(prow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < nvalid) prow[j] = v[j];
+      }
+    }
+  }
+  if (hsel == 0 && ok) {
+    const float ps = e_self * inv;
+    float* rrow = p.R + (int64_t)m * 256 + nt * 32;
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+      const float4 vv = __ldg(reinterpret_cast<const float4*>(qrow + 512 + d));
+      *reinterpret_cast<float4*>(rrow + d) = make_float4(ps * vv.x, ps * vv.y, ps * vv.z, ps * vv.w);
     }
   }
 }
@@ -156,14 +243,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // ================= A producers =================
     const int r = threadIdx.x;  // row inside the tile
     int stage = 0; uint32_t phase = 0;
-    const bool vec_ok = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+    const bool vec_ok = ((p.lda & 3) == 0) && ((p.a_nt_off & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
     // All 64 fp32 of a K-chunk are fetched into registers BEFORE waiting for the smem slot (also across
     // tile boundaries), so the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
     float4 buf[16];
     auto fetch = [&](int t, int kc) {
       const int m = (t / p.n_tiles) * TC_BM + r;
       const bool row_ok = m < p.M;
-      const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda;
+      const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda + (t % p.n_tiles) * p.a_nt_off;
       const int k0 = kc * TC_BK;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
@@ -207,7 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // ================= W loader =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t bytes = split ? 2u * TC_B_TILE : (uint32_t)TC_B_TILE;
+      const uint32_t bytes = split ? 2u * p.w_tile_bytes : p.w_tile_bytes;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -215,8 +302,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
           const uint8_t* src = p.Wp + ((size_t)nt * p.k_chunks + kc) * (2u * TC_B_TILE);
           const uint32_t dst = smem_base + stage * TC_STAGE_BYTES + 2 * TC_A_TILE;
           mbar_arrive_expect_tx(full_bar(stage), bytes);
-          bulk_g2s(dst, src, TC_B_TILE, full_bar(stage));
-          if (split) bulk_g2s(dst + TC_B_TILE, src + TC_B_TILE, TC_B_TILE, full_bar(stage));
+          bulk_g2s(dst, src, p.w_tile_bytes, full_bar(stage));
+          if (split) bulk_g2s(dst + TC_B_TILE, src + TC_B_TILE, p.w_tile_bytes, full_bar(stage));
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, (uint32_t)p.mma_n);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
@@ -258,6 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // (two warps per SM sub-partition and a compile-time activation: a single warp per scheduler running a
     //  jump-table per element was latency-bound at ~0.2 IPC -- profiles/r1_gemm_tc_v0.md)
     const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    float* xch = reinterpret_cast<float*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 256);   // [2][128] softmax exchange
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
@@ -265,14 +353,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16) + hsel * 128;
-      const int nbase = nt * TC_BN + hsel * 128;
-      switch (p.act) {
-        case ZS_ACT_RELU: tc_epilogue_half<ZS_ACT_RELU>(p, taddr, m, nbase); break;
-        case ZS_ACT_GELU: tc_epilogue_half<ZS_ACT_GELU>(p, taddr, m, nbase); break;
-        case ZS_ACT_SOFTPLUS100: tc_epilogue_half<ZS_ACT_SOFTPLUS100>(p, taddr, m, nbase); break;
-        case ZS_ACT_SIGMOID: tc_epilogue_half<ZS_ACT_SIGMOID>(p, taddr, m, nbase); break;
-        case ZS_ACT_CLAMP01: tc_epilogue_half<ZS_ACT_CLAMP01>(p, taddr, m, nbase); break;
-        default: tc_epilogue_half<ZS_ACT_NONE>(p, taddr, m, nbase); break;
+      if (p.epi_mode == 1) {
+        tc_epilogue_softmax(p, taddr, m, nt, hsel, q * 32 + lane, xch);
+      } else {
+        switch (p.act) {
+          case ZS_ACT_RELU: tc_epilogue_half<ZS_ACT_RELU>(p, taddr, m, nt, hsel); break;
+          case ZS_ACT_GELU: tc_epilogue_half<ZS_ACT_GELU>(p, taddr, m, nt, hsel); break;
+          case ZS_ACT_SOFTPLUS100: tc_epilogue_half<ZS_ACT_SOFTPLUS100>(p, taddr, m, nt, hsel); break;
+          case ZS_ACT_SIGMOID: tc_epilogue_half<ZS_ACT_SIGMOID>(p, taddr, m, nt, hsel); break;
+          case ZS_ACT_CLAMP01: tc_epilogue_half<ZS_ACT_CLAMP01>(p, taddr, m, nt, hsel); break;
+          default: tc_epilogue_half<ZS_ACT_NONE>(p, taddr, m, nt, hsel); break;
+        }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -356,9 +447,66 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.res = res; p.ldres = ldres; p.res_mode = res_mode; p.C = C; p.ldc = ldc;
   p.M = M; p.N = N; p.K = K; p.act = act; p.precision = precision;
   p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = (N + TC_BN - 1) / TC_BN; p.k_chunks = (K + TC_BK - 1) / TC_BK;
+  p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.scale = 0.f; p.n_keys = 0;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_f32");
+  return ZS_OK;
+}
+
+// ---- attention on the tensor cores (two grouped launches of gemm_tc_kernel) ------------------------------------
+// scores + softmax:  P[m, h*208 + j] = softmax_j( scale * q_h(m) . k_lat_h(j)  (+ the point's own key) ),  R = p_self * v_p
+// `Kpacked`: 8 tiles (one per head) packed with zs_gemm_tc_pack from K_lat_h [208 (197 + zero rows), 32].
+extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpacked, int M, int n_keys, float scale,
+                                 float* P, float* R, int precision, void* stream) {
+  ZS_REQUIRE(qkv && Kpacked && P && R && M >= 0, "zs_attn_scores_tc: null pointer");
+  ZS_REQUIRE(n_keys > 0 && n_keys <= 208, "zs_attn_scores_tc: n_keys must be in [1, 208]");
+  ZS_REQUIRE((ld_qkv & 3) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
+             "zs_attn_scores_tc: qkv / R must be 16-byte aligned with ld % 4 == 0");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_attn_scores_tc: bad precision");
+  if (M == 0) return ZS_OK;
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  TcParams p{};
+  p.A = qkv; p.lda = ld_qkv; p.Wp = reinterpret_cast<const uint8_t*>(Kpacked); p.bias = nullptr;
+  p.res = nullptr; p.ldres = 0; p.res_mode = ZS_RES_NONE; p.C = P; p.ldc = 8 * 208;
+  p.M = M; p.N = 8 * 208; p.K = 32; p.act = ZS_ACT_NONE; p.precision = precision;
+  p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = 8; p.k_chunks = 1;
+  p.a_nt_off = 32; p.c_nt_off = 208; p.n_tile_valid = 208; p.mma_n = 208; p.w_tile_bytes = 208 * 128; p.epi_mode = 1;
+  p.qkv = qkv; p.ld_qkv = ld_qkv; p.R = R; p.scale = scale; p.n_keys = n_keys;
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_attn_scores_tc");
+  return ZS_OK;
+}
+
+// O[m, 32h + d] = sum_j P[m, h*208 + j] * v_lat_h[j, d] + R[m, 32h + d]
+// `Vpacked`: 8 heads x 4 K-chunks, packed with zs_gemm_tc_pack from V_lat_h^T [32, 208].
+extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, float* O, int M, int precision, void* stream) {
+  ZS_REQUIRE(P && Vpacked && R && O && M >= 0, "zs_attn_pv_tc: null pointer");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(P) & 15) == 0, "zs_attn_pv_tc: P must be 16-byte aligned");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_attn_pv_tc: bad precision");
+  if (M == 0) return ZS_OK;
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  TcParams p{};
+  p.A = P; p.lda = 8 * 208; p.Wp = reinterpret_cast<const uint8_t*>(Vpacked); p.bias = nullptr;
+  p.res = R; p.ldres = 256; p.res_mode = ZS_RES_AFTER_ACT; p.C = O; p.ldc = 256;
+  p.M = M; p.N = 256; p.K = 208; p.act = ZS_ACT_NONE; p.precision = precision;
+  p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = 8; p.k_chunks = 4;
+  p.a_nt_off = 208; p.c_nt_off = 32; p.n_tile_valid = 32; p.mma_n = 32; p.w_tile_bytes = 32 * 128; p.epi_mode = 0;
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_attn_pv_tc");
   return ZS_OK;
 }

@@ -118,6 +118,39 @@ def pack_tiles(mats):
     return torch.cat(blobs)
 
 
+def pack_generic(w):
+    """zs_gemm_tc_pack image of one fp32 matrix [N, K] (N tiles of 256 rows, K padded to 64)."""
+    w = w.detach().float().contiguous()
+    b = torch.empty(lib.zs_gemm_tc_packed_bytes(w.shape[0], w.shape[1]), device=w.device, dtype=torch.uint8)
+    check(lib.zs_gemm_tc_pack(_p(w), w.stride(0), w.shape[0], w.shape[1], _p(b), _stream()), "zs_gemm_tc_pack")
+    return b
+
+
+def attn_pack_kv(k_lat, v_lat, heads=8):
+    """Per-image latent keys/values [L, C] (row-strided views) -> (Kpacked, Vpacked) tensor-core operand images."""
+    L, C = k_lat.shape
+    hd = C // heads
+    assert hd == 32 and L <= 208
+    kp = torch.zeros(heads, 208, hd, device=k_lat.device, dtype=torch.float32)
+    kp[:, :L] = k_lat.reshape(L, heads, hd).permute(1, 0, 2)
+    vp = torch.zeros(heads, hd, 208, device=v_lat.device, dtype=torch.float32)
+    vp[:, :, :L] = v_lat.reshape(L, heads, hd).permute(1, 2, 0)
+    return torch.cat([pack_generic(kp[h]) for h in range(heads)]), torch.cat([pack_generic(vp[h]) for h in range(heads)])
+
+
+def attn_tc(qkv, kpacked, vpacked, n_keys, scale, precision="bf16x3"):
+    """qkv [M,768] (q|k|v of the query points) -> attention output [M,256] on the tensor cores (one image)."""
+    assert qkv.dim() == 2 and qkv.shape[1] == 768 and qkv.stride(1) == 1 and qkv.is_cuda and qkv.dtype == torch.float32
+    M = qkv.shape[0]
+    P = torch.empty(M, 8 * 208, device=qkv.device, dtype=torch.float32)
+    R = torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
+    O = torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
+    check(lib.zs_attn_scores_tc(_p(qkv), qkv.stride(0), _p(kpacked), M, n_keys, scale, _p(P), _p(R), PRECISIONS[precision],
+                                _stream()), "zs_attn_scores_tc")
+    check(lib.zs_attn_pv_tc(_p(P), _p(vpacked), _p(R), _p(O), M, PRECISIONS[precision], _stream()), "zs_attn_pv_tc")
+    return O
+
+
 def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
     """In place: x[M,256] <- x + fc2(GELU(fc1(LayerNorm(x)))) on the chained tcgen05 kernel."""
     assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
