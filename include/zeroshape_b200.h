@@ -72,14 +72,16 @@ int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, const float* bi
                    int M, int N, int K, int act, int precision, void* stream);
 
 /* Point-to-latent attention on the tensor cores (model/shape/implicit.py:38-57), two grouped tcgen05 launches:
- *   zs_attn_scores_tc: P[m, 208h + j] = softmax over {latent keys j < n_keys} U {the point's own key} of
- *                      scale * q_h(m).k ; R[m, 32h + d] = p_self * v_p,h[d]          (qkv [M,768] fp32 = q|k|v)
- *   zs_attn_pv_tc    : O[m, 32h + d] = sum_j P[m, 208h + j] * v_lat_h[j, d] + R[m, 32h + d]
+ *   zs_attn_scores_tc: P[m, 208h + j] = exp(scale*(q_h(m).k_lat_h(j) - rowmax)) (softmax numerators over the latent keys
+ *                      j < n_keys; the row max / sum also cover the point's own key), Rinv[m, h] = 1/sum,
+ *                      R[m, 32h + d] = p_self * v_p,h[d]                               (qkv [M,768] fp32 = q|k|v)
+ *   zs_attn_pv_tc    : O[m, 32h + d] = Rinv[m,h] * sum_j P[m, 208h + j] * v_lat_h[j, d] + R[m, 32h + d]
  * Kpacked: 8 head tiles from zs_gemm_tc_pack(K_lat_h [208 rows (n_keys real, rest 0), 32]);
- * Vpacked: 8 heads x 4 K-chunks from zs_gemm_tc_pack(V_lat_h^T [32, 208]).  P is [M, 1664], R and O [M, 256]. */
+ * Vpacked: 8 heads x 4 K-chunks from zs_gemm_tc_pack(V_lat_h^T [32, 208]).  P is [M, 1664], R and O [M, 256], Rinv [M, 8]. */
 int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpacked, int M, int n_keys, float scale,
-                      float* P, float* R, int precision, void* stream);
-int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, float* O, int M, int precision, void* stream);
+                      float* P, float* R, float* Rinv, int precision, void* stream);
+int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, const float* Rinv, float* O, int M, int precision,
+                  void* stream);
 
 /* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
  * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack

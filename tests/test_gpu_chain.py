@@ -55,10 +55,8 @@ def test_chain_occ_matches_oracle_mlp(cuda, P):
         ref = _occupancy_mlp(pts.double(), _ln(x.double(), sdd, "norm"), sdd, "impl_mlp").squeeze(-1)
     _, _, occ_blob, biases, w8, b8 = m._chain_blobs()
     out = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8)
-    d = (out.cpu().double() - ref).abs()
-    rms = ref.pow(2).mean().sqrt().item()
-    assert d.max().item() < 1e-3 * max(ref.abs().max().item(), 0.1 * rms), (d.max().item(), rms)
-    assert (d / ref.abs().clamp_min(0.1 * rms)).max().item() < 1e-3
+    from parity import parity_rel
+    assert parity_rel(out, ref) < 1e-3
     sig = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8, sigmoid=True)
     assert (sig.cpu().double() - torch.sigmoid(ref)).abs().max().item() < 1e-5
 
@@ -79,12 +77,10 @@ def test_decoder_chain_engine_parity_and_voxels(cuda):
     with torch.no_grad():
         ref, _ = implicit_forward(sd, lat, pts)
     out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
-    d = (out.cpu().double() - ref.double()).abs()
-    rms = ref.double().pow(2).mean().sqrt().item()
-    rel = (d / ref.double().abs().clamp_min(0.1 * rms)).max().item()
-    normwise = (d.pow(2).sum().sqrt() / ref.double().pow(2).sum().sqrt()).item()
-    print(f"chain max abs {d.max().item():.3e} max rel {rel:.3e} normwise {normwise:.3e}")
-    assert rel < 1e-3 and normwise < 1e-4
+    from parity import parity_rel, normwise
+    rel, nw = parity_rel(out, ref), normwise(out, ref)
+    print(f"chain max abs {(out.cpu() - ref).abs().max().item():.3e} parity rel {rel:.3e} normwise {nw:.3e}")
+    assert rel < 1e-3 and nw < 1e-4
     n = 21
     occ_ref = E.level_grid(sd, lat[:1], n, -1.5, 1.5)
     occ = m.grid_occupancy(lat[:1].to(cuda), n, -1.5, 1.5).cpu()
@@ -132,8 +128,7 @@ def test_decoder_with_tensor_core_attention(cuda):
     with torch.no_grad():
         ref, _ = implicit_forward(sd, lat, pts)
     out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
-    d = (out.cpu().double() - ref.double()).abs()
-    rms = ref.double().pow(2).mean().sqrt().item()
-    rel = (d / ref.double().abs().clamp_min(0.1 * rms)).max().item()
-    print(f"chain+tc-attn max abs {d.max().item():.3e} max rel {rel:.3e}")
-    assert rel < 1e-3
+    from parity import parity_rel, normwise
+    rel, nw = parity_rel(out, ref), normwise(out, ref)
+    print(f"chain+tc-attn max abs {(out.cpu() - ref).abs().max().item():.3e} parity rel {rel:.3e} normwise {nw:.3e}")
+    assert rel < 1e-3 and nw < 1e-4

@@ -87,14 +87,10 @@ def test_decoder_tc_engine_meets_parity_bar(cuda, precision, tol):
     with torch.no_grad():
         ref, _ = implicit_forward(sd, lat, pts)
     out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
-    # parity metric (DESIGN.md "Parity bar"): elementwise |d| <= 1e-3 * max(|ref|, 0.1*rms(ref)) -- the floor keeps
-    # the ratio defined where the logit crosses zero (the iso-surface) -- plus a normwise bound.
-    d = (out.cpu().double() - ref.double()).abs()
-    rms = ref.double().pow(2).mean().sqrt().item()
-    rel = (d / ref.double().abs().clamp_min(0.1 * rms)).max().item()
-    normwise = (d.pow(2).sum().sqrt() / ref.double().pow(2).sum().sqrt()).item()
-    print(f"tc[{precision}] max abs {d.max().item():.3e} max rel {rel:.3e} normwise {normwise:.3e} rms {rms:.3f}")
-    assert rel < tol and normwise < 1e-4
+    from parity import parity_rel, normwise
+    rel, nw = parity_rel(out, ref), normwise(out, ref)
+    print(f"tc[{precision}] max abs {(out.cpu() - ref).abs().max().item():.3e} parity rel {rel:.3e} normwise {nw:.3e}")
+    assert rel < tol and nw < 1e-4
     # thresholded voxel grid identical outside the error band
     n = 21
     occ_ref = E.level_grid(sd, lat[:1], n, -1.5, 1.5)

@@ -25,10 +25,8 @@ def _module(sd, cuda, engine):
 
 
 def rel_err(a, b):
-    """Parity metric of DESIGN.md: max |a-b| / max(|b|, 0.1*rms(b)) -- relative error with a floor that keeps the
-    ratio defined where the logit crosses zero (the iso-surface)."""
-    a, b = a.double().cpu(), b.double().cpu()
-    return ((a - b).abs() / b.abs().clamp_min(0.1 * b.pow(2).mean().sqrt())).max().item()
+    from parity import parity_rel
+    return parity_rel(a, b)
 
 
 def test_state_dict_is_reference_compatible(cuda):

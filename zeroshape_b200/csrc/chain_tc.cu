@@ -75,6 +75,23 @@ __device__ __forceinline__ float fast_softplus100(float x) {
   return (fmaxf(bx, 0.0f) + l) * 0.01f;
 }
 
+// exact-erf GELU (torch.nn.GELU default) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. the
+// same order as the rounding of torch's own fp32 erff path: measured 4.7e-7 max abs on GELU vs fp64, torch fp32 1.2e-6):
+// ~17 instructions (1 MUFU.RCP + 1 MUFU.EX2) instead of ~35 for erff.
+__device__ __forceinline__ float fast_gelu_erf(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-az * az * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, z));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // common prologue: barriers + TMEM
 __device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen, uint32_t smem_base, int warp) {
@@ -191,10 +208,13 @@ __device__ __forceinline__ void epi_to_ring(uint8_t* slot, int row, int hsel, co
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float v[8];
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = __uint_as_float(rr[c * 8 + j]) + __ldg(bias + c * 8 + j);
-      v[j] = ACT == ZS_ACT_GELU ? act_gelu_erf(t) : fast_softplus100(t);
+      float t = __uint_as_float(rr[c * 8 + j]) + bb[j];
+      v[j] = ACT == ZS_ACT_GELU ? fast_gelu_erf(t) : fast_softplus100(t);
     }
     uint4 hi, lo;
     split_bf16x2(v[0], v[1], hi.x, lo.x);

@@ -44,7 +44,8 @@ struct TcParams {
   int a_nt_off, c_nt_off, n_tile_valid, mma_n;
   uint32_t w_tile_bytes;       // bytes of one (hi or lo) weight tile actually needed: mma_n rows x 128 B
   int epi_mode;                // 0: bias / activation / residual;  1: attention softmax (tc_epilogue_softmax)
-  const float* qkv; int ld_qkv; float* R; float scale; int n_keys;
+  const float* qkv; int ld_qkv; float* R; float* R_inv; float scale; int n_keys;
+  const float* rowscale;       // optional [M, n_tiles]: accumulator row scale applied before bias/residual (P.V normalisation)
 };
 
 template <int ACT>
@@ -76,8 +77,14 @@ __device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t tad
       const bool vec_c = full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0);
       const bool vec_r = rrow && full && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
       float v[32];
+      if (p.rowscale) {
+        const float rs = __ldg(p.rowscale + (int64_t)m * p.n_tiles + nt);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * rs;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+      }
       if (p.bias) {
         if (full && ((reinterpret_cast<uintptr_t>(p.bias + n0) & 15) == 0)) {
 #pragma unroll
@@ -150,27 +157,22 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
     uint32_t rr[32];
     tmem_ld_32x32(taddr + c0, rr);
     tmem_ld_wait();
+    if (lc0 + c0 + 32 <= p.n_keys) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (lc0 + c0 + j < p.n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (lc0 + c0 + j < p.n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
   }
   xch[hsel * 128 + row] = mx;
   asm volatile("bar.sync 1, 256;" ::: "memory");
   mx = fmaxf(fmaxf(xch[row], xch[128 + row]), s_self);
   asm volatile("bar.sync 1, 256;" ::: "memory");
+  // single sweep: unnormalised e_j = exp(scale*(s_j - max)) goes to P, the row sum is applied later as a per-(row, head)
+  // scale in the P.V epilogue (p.rowscale there) -- one exp per score, no third TMEM pass.
   float sum = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
-    uint32_t rr[32];
-    tmem_ld_32x32(taddr + c0, rr);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) if (lc0 + c0 + j < p.n_keys) sum += exp2f((__uint_as_float(rr[j]) - mx) * sl2);
-  }
-  xch[hsel * 128 + row] = sum;
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  const float e_self = exp2f((s_self - mx) * sl2);
-  const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float mxs = mx * sl2;
 #pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
     uint32_t rr[32];
@@ -178,22 +180,38 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
     tmem_ld_wait();
     const int lc = lc0 + c0;
     const int nvalid = p.n_tile_valid - lc;
-    if (ok && nvalid > 0) {
-      float* prow = p.C + (int64_t)m * p.ldc + nt * p.c_nt_off + lc;
+    if (nvalid > 0) {
       float v[32];
+      if (lc + 32 <= p.n_keys) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (lc + j < p.n_keys) ? exp2f((__uint_as_float(rr[j]) - mx) * sl2) * inv : 0.f;
-      if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(prow) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<float4*>(prow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 32; ++j) { v[j] = exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < nvalid) prow[j] = v[j];
+        for (int j = 0; j < 32; ++j) {
+          v[j] = (lc + j < p.n_keys) ? exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f;
+          sum += v[j];
+        }
+      }
+      if (ok) {
+        float* prow = p.C + (int64_t)m * p.ldc + nt * p.c_nt_off + lc;
+        if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(prow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(prow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nvalid) prow[j] = v[j];
+        }
       }
     }
   }
+  xch[hsel * 128 + row] = sum;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float e_self = exp2f(fmaf(s_self, sl2, -mxs));
+  const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
   if (hsel == 0 && ok) {
+    p.R_inv[(int64_t)m * 8 + nt] = inv;
     const float ps = e_self * inv;
     float* rrow = p.R + (int64_t)m * 256 + nt * 32;
 #pragma unroll
@@ -448,7 +466,7 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.M = M; p.N = N; p.K = K; p.act = act; p.precision = precision;
   p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = (N + TC_BN - 1) / TC_BN; p.k_chunks = (K + TC_BK - 1) / TC_BK;
   p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
-  p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.scale = 0.f; p.n_keys = 0;
+  p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.R_inv = nullptr; p.scale = 0.f; p.n_keys = 0; p.rowscale = nullptr;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
@@ -457,11 +475,12 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
 }
 
 // ---- attention on the tensor cores (two grouped launches of gemm_tc_kernel) ------------------------------------
-// scores + softmax:  P[m, h*208 + j] = softmax_j( scale * q_h(m) . k_lat_h(j)  (+ the point's own key) ),  R = p_self * v_p
+// scores + softmax numerators:  P[m, h*208 + j] = exp(scale*(q_h(m).k_lat_h(j) - max)),  Rinv[m,h] = 1/sum (incl. the point's own
+// key), R[m, 32h+d] = p_self * v_p,h[d]
 // `Kpacked`: 8 tiles (one per head) packed with zs_gemm_tc_pack from K_lat_h [208 (197 + zero rows), 32].
 extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpacked, int M, int n_keys, float scale,
-                                 float* P, float* R, int precision, void* stream) {
-  ZS_REQUIRE(qkv && Kpacked && P && R && M >= 0, "zs_attn_scores_tc: null pointer");
+                                 float* P, float* R, float* Rinv, int precision, void* stream) {
+  ZS_REQUIRE(qkv && Kpacked && P && R && Rinv && M >= 0, "zs_attn_scores_tc: null pointer");
   ZS_REQUIRE(n_keys > 0 && n_keys <= 208, "zs_attn_scores_tc: n_keys must be in [1, 208]");
   ZS_REQUIRE((ld_qkv & 3) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
              "zs_attn_scores_tc: qkv / R must be 16-byte aligned with ld % 4 == 0");
@@ -478,7 +497,7 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   p.M = M; p.N = 8 * 208; p.K = 32; p.act = ZS_ACT_NONE; p.precision = precision;
   p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = 8; p.k_chunks = 1;
   p.a_nt_off = 32; p.c_nt_off = 208; p.n_tile_valid = 208; p.mma_n = 208; p.w_tile_bytes = 208 * 128; p.epi_mode = 1;
-  p.qkv = qkv; p.ld_qkv = ld_qkv; p.R = R; p.scale = scale; p.n_keys = n_keys;
+  p.qkv = qkv; p.ld_qkv = ld_qkv; p.R = R; p.R_inv = Rinv; p.scale = scale; p.n_keys = n_keys;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
@@ -486,10 +505,11 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   return ZS_OK;
 }
 
-// O[m, 32h + d] = sum_j P[m, h*208 + j] * v_lat_h[j, d] + R[m, 32h + d]
+// O[m, 32h + d] = Rinv[m,h] * sum_j P[m, h*208 + j] * v_lat_h[j, d] + R[m, 32h + d]
 // `Vpacked`: 8 heads x 4 K-chunks, packed with zs_gemm_tc_pack from V_lat_h^T [32, 208].
-extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, float* O, int M, int precision, void* stream) {
-  ZS_REQUIRE(P && Vpacked && R && O && M >= 0, "zs_attn_pv_tc: null pointer");
+extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, const float* Rinv, float* O, int M, int precision,
+                             void* stream) {
+  ZS_REQUIRE(P && Vpacked && R && Rinv && O && M >= 0, "zs_attn_pv_tc: null pointer");
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(P) & 15) == 0, "zs_attn_pv_tc: P must be 16-byte aligned");
   ZS_REQUIRE(precision == 0 || precision == 1, "zs_attn_pv_tc: bad precision");
   if (M == 0) return ZS_OK;
@@ -504,6 +524,7 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   p.M = M; p.N = 256; p.K = 208; p.act = ZS_ACT_NONE; p.precision = precision;
   p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = 8; p.k_chunks = 4;
   p.a_nt_off = 208; p.c_nt_off = 32; p.n_tile_valid = 32; p.mma_n = 32; p.w_tile_bytes = 32 * 128; p.epi_mode = 0;
+  p.rowscale = Rinv;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);

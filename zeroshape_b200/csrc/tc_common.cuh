@@ -113,11 +113,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits; products hi*hi + hi*lo + lo*hi
 // reproduce the fp32 product to ~2^-16 relative.
+// (packed form: one cvt.rn.bf16x2.f32 per pair and pass, 6 instructions per pair instead of ~14)
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-  hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x (low 16 bits) = bf16(a), .y (high) = bf16(b)
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16);                // bf16 -> fp32 is a 16-bit shift
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 }  // namespace tc

@@ -89,7 +89,7 @@ class Implicit(nn.Module):
             nn.Linear(dims[l] + (dims[0] if l in self.skip_in else 0), dims[l + 1]) for l in range(len(dims) - 1)])
         self.engine = "auto"          # "auto" | "fused" | "tc" | "f32"
         self.precision = "bf16x3"     # tensor-core operand precision: "bf16x3" (parity) | "bf16" (fast)
-        self.attention = "f32"        # point attention: "tc" (tcgen05 grouped GEMMs + softmax epilogue) | "f32" (FFMA kernel)
+        self.attention = "tc"         # point attention: "tc" (tcgen05 grouped GEMMs + softmax epilogue) | "f32" (FFMA kernel)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         self.point_chunk = 1 << 18    # query points per pass of the per-layer / chained engines (bounds scratch memory)
         self._packed = None           # (version key, packed weight blob) for the fused engine
@@ -198,8 +198,8 @@ class Implicit(nn.Module):
                 for b in range(B):
                     if (l, b) not in packs:
                         packs[(l, b)] = ops.attn_pack_kv(k_lat[b], v_lat[b], self.num_heads)
-                    a[b * P:(b + 1) * P] = ops.attn_tc(qkv[b * P:(b + 1) * P], packs[(l, b)][0], packs[(l, b)][1], lat["L"],
-                                                       (C // self.num_heads) ** -0.5, self.precision)
+                    ops.attn_tc(qkv[b * P:(b + 1) * P], packs[(l, b)][0], packs[(l, b)][1], lat["L"],
+                                (C // self.num_heads) ** -0.5, self.precision, out=a[b * P:(b + 1) * P])
             else:
                 a = ops.point_attention(qkv.view(B, P, 3 * C), k_lat, v_lat, self.num_heads, attn=attn_out,
                                         attn_scale=1.0 / nb, attn_accumulate=(l > 0)).view(B * P, C)

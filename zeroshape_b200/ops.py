@@ -138,16 +138,26 @@ def attn_pack_kv(k_lat, v_lat, heads=8):
     return torch.cat([pack_generic(kp[h]) for h in range(heads)]), torch.cat([pack_generic(vp[h]) for h in range(heads)])
 
 
-def attn_tc(qkv, kpacked, vpacked, n_keys, scale, precision="bf16x3"):
+ATTN_SUBCHUNK = 8192      # rows per scores -> P.V round trip: keeps P (8192 x 1664 fp32 = 54 MB) resident in the 126 MB L2
+
+
+def attn_tc(qkv, kpacked, vpacked, n_keys, scale, precision="bf16x3", out=None):
     """qkv [M,768] (q|k|v of the query points) -> attention output [M,256] on the tensor cores (one image)."""
     assert qkv.dim() == 2 and qkv.shape[1] == 768 and qkv.stride(1) == 1 and qkv.is_cuda and qkv.dtype == torch.float32
     M = qkv.shape[0]
-    P = torch.empty(M, 8 * 208, device=qkv.device, dtype=torch.float32)
-    R = torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
-    O = torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
-    check(lib.zs_attn_scores_tc(_p(qkv), qkv.stride(0), _p(kpacked), M, n_keys, scale, _p(P), _p(R), PRECISIONS[precision],
-                                _stream()), "zs_attn_scores_tc")
-    check(lib.zs_attn_pv_tc(_p(P), _p(vpacked), _p(R), _p(O), M, PRECISIONS[precision], _stream()), "zs_attn_pv_tc")
+    dev = qkv.device
+    O = out if out is not None else torch.empty(M, 256, device=dev, dtype=torch.float32)
+    sub = min(M, ATTN_SUBCHUNK)
+    P = torch.empty(sub, 8 * 208, device=dev, dtype=torch.float32)
+    R = torch.empty(sub, 256, device=dev, dtype=torch.float32)
+    Rinv = torch.empty(sub, 8, device=dev, dtype=torch.float32)
+    prec = PRECISIONS[precision]
+    for s in range(0, M, sub):
+        m = min(sub, M - s)
+        q = qkv[s:s + m]
+        check(lib.zs_attn_scores_tc(_p(q), q.stride(0), _p(kpacked), m, n_keys, scale, _p(P), _p(R), _p(Rinv), prec, _stream()),
+              "zs_attn_scores_tc")
+        check(lib.zs_attn_pv_tc(_p(P), _p(vpacked), _p(R), _p(Rinv), _p(O[s:s + m]), m, prec, _stream()), "zs_attn_pv_tc")
     return O
 
 
