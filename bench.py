@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--shapes", type=int, default=1, help="shapes per GPU per step")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
-    ap.add_argument("--attention", default=None, choices=["tc", "f32"])
+    ap.add_argument("--attention", default=None, choices=["fused", "tc", "f32"])
     ap.add_argument("--cpu-slices", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -83,6 +83,12 @@ int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpacked, int M, 
 int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, const float* Rinv, float* O, int M, int precision,
                   void* stream);
 
+/* Same attention, flash-style in ONE kernel (scores, softmax numerators and P.V of a 128-point tile stay on the SM;
+ * csrc/chain_tc.cu chain_attn_kernel).  Kblob as Kpacked above; Vblob: 8 heads x 32 KB = 4 key-chunks x [hi 4 KB | lo 4 KB]
+ * (the first 4 KB of each hi / lo tile of Vpacked).  O [M,256]. */
+int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
+                      float scale, float* O, int precision, void* stream);
+
 /* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
  * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack
  * (N=256 rows, K padded to 64) and concatenated:

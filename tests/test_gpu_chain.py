@@ -53,11 +53,11 @@ def test_chain_occ_matches_oracle_mlp(cuda, P):
     with torch.no_grad():
         sdd = {k: v.double() for k, v in sd.items()}
         ref = _occupancy_mlp(pts.double(), _ln(x.double(), sdd, "norm"), sdd, "impl_mlp").squeeze(-1)
-    _, _, occ_blob, biases, w8, b8 = m._chain_blobs()
-    out = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8)
+    _, _, occ_blob, biases, w8, b8, _ = m._chain_blobs()
+    out = ops.chain_occ(x.to(cuda), pts.to(cuda), None, None, m.norm.eps, occ_blob, biases, w8, b8)
     from parity import parity_rel
     assert parity_rel(out, ref) < 1e-3
-    sig = ops.chain_occ(x.to(cuda), pts.to(cuda), m.norm.weight, m.norm.bias, m.norm.eps, occ_blob, biases, w8, b8, sigmoid=True)
+    sig = ops.chain_occ(x.to(cuda), pts.to(cuda), None, None, m.norm.eps, occ_blob, biases, w8, b8, sigmoid=True)
     assert (sig.cpu().double() - torch.sigmoid(ref)).abs().max().item() < 1e-5
 
 
@@ -131,4 +131,48 @@ def test_decoder_with_tensor_core_attention(cuda):
     from parity import parity_rel, normwise
     rel, nw = parity_rel(out, ref), normwise(out, ref)
     print(f"chain+tc-attn max abs {(out.cpu() - ref).abs().max().item():.3e} parity rel {rel:.3e} normwise {nw:.3e}")
+    assert rel < 1e-3 and nw < 1e-4
+
+
+@pytest.mark.parametrize("M", [128, 1000, 4224])
+def test_fused_attention_kernel_matches_reference_math(cuda, M):
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(M + 1)
+    L, C, H = 197, 256, 8
+    qkv = torch.randn(M, 3 * C, generator=g)
+    lat_qkv = torch.randn(1, L, 3 * C, generator=g)
+    q, k, v = [t.double().reshape(M, H, 32).permute(1, 0, 2) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])]
+    kl = lat_qkv[0, :, C:2 * C].double().reshape(L, H, 32).permute(1, 0, 2)
+    vl = lat_qkv[0, :, 2 * C:].double().reshape(L, H, 32).permute(1, 0, 2)
+    s = torch.cat([q @ kl.transpose(1, 2), (q * k).sum(-1, keepdim=True)], -1) * 32 ** -0.5
+    a = s.softmax(-1)
+    ref = (a[..., :L] @ vl + a[..., L:] * v).permute(1, 0, 2).reshape(M, C)
+    lat_dev = lat_qkv.to(cuda)
+    kp, vp = ops.attn_pack_kv(lat_dev[0, :, C:2 * C], lat_dev[0, :, 2 * C:], H)
+    out = ops.attn_fused(qkv.to(cuda), kp, ops.attn_pack_v_fused(vp, H), L, 32 ** -0.5)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err < 2e-5 * ref.abs().max().item(), err
+    fast = ops.attn_fused(qkv.to(cuda), kp, ops.attn_pack_v_fused(vp, H), L, 32 ** -0.5, precision="bf16")
+    assert (fast.cpu().double() - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
+
+
+def test_decoder_with_fused_attention(cuda):
+    _need_sm100()
+    from oracle.implicit import implicit_forward, implicit_init
+    from parity import parity_rel, normwise
+    from zeroshape_b200.model.shape.implicit import Implicit
+    sd = implicit_init(seed=14)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    m.engine, m.attention = "chain", "fused"
+    g = torch.Generator().manual_seed(4)
+    lat, pts = torch.randn(2, 197, 256, generator=g), torch.rand(2, 2000, 3, generator=g) * 3 - 1.5
+    with torch.no_grad():
+        ref, _ = implicit_forward(sd, lat, pts)
+    out, _ = m(lat.to(cuda), None, pts.to(cuda), need_attn=False)
+    rel, nw = parity_rel(out, ref), normwise(out, ref)
+    print(f"chain+fused-attn parity rel {rel:.3e} normwise {nw:.3e}")
     assert rel < 1e-3 and nw < 1e-4

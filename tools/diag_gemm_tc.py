@@ -111,19 +111,43 @@ try:
     from zeroshape_b200.model.shape.implicit import Implicit
     net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
                    pos_perlayer=False).to(dev).eval()
-    _, _, occ_blob, biases, w8, b8 = net._chain_blobs()
+    _, _, occ_blob, biases, w8, b8, _ = net._chain_blobs()
     pts = torch.rand(M, 3, device=dev)
     for prec in ("bf16x3", "bf16"):
         for _ in range(2):
-            ops.chain_occ(x0, pts, net.norm.weight, net.norm.bias, 1e-6, occ_blob, biases, w8, b8, precision=prec)
+            ops.chain_occ(x0, pts, None, None, 1e-6, occ_blob, biases, w8, b8, precision=prec)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.chain_occ(x0, pts, net.norm.weight, net.norm.bias, 1e-6, occ_blob, biases, w8, b8, precision=prec)
+            ops.chain_occ(x0, pts, None, None, 1e-6, occ_blob, biases, w8, b8, precision=prec)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         log(f"[time] chain_occ M={M} {prec}: {ms:.3f} ms  {2 * M * 724224 / ms / 1e9:.1f} TFLOP/s (algorithmic)  {M / ms / 1e3:.1f} Mpts/s")
 except Exception as ex:
     log("chain diag failed:", repr(ex))
+open("gpurun_out/diag_gemm_tc.txt", "w").write("\n".join(out_lines) + "\n")
+
+# ---- attention variants -----------------------------------------------------------------------------------
+try:
+    M = 148 * 128 * 8
+    L, C, H = 197, 256, 8
+    qkv = torch.randn(M, 3 * C, device=dev)
+    latq = torch.randn(1, L, 3 * C, device=dev)
+    kp, vp = ops.attn_pack_kv(latq[0, :, C:2 * C], latq[0, :, 2 * C:], H)
+    vf = ops.attn_pack_v_fused(vp, H)
+    def timeit(fn, n=5):
+        for _ in range(2): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for prec in ("bf16x3", "bf16"):
+        log(f"[time] attn_fused M={M} {prec}: {timeit(lambda: ops.attn_fused(qkv, kp, vf, L, 32 ** -0.5, prec)):.3f} ms")
+    log(f"[time] attn_tc (2 kernels) M={M} bf16x3: {timeit(lambda: ops.attn_tc(qkv, kp, vp, L, 32 ** -0.5)):.3f} ms")
+    log(f"[time] point_attention f32 M={M}: {timeit(lambda: ops.point_attention(qkv.view(1, M, 3 * C), latq[..., C:2 * C], latq[..., 2 * C:], H), 2):.3f} ms")
+except Exception as ex:
+    log("attention diag failed:", repr(ex))
 open("gpurun_out/diag_gemm_tc.txt", "w").write("\n".join(out_lines) + "\n")

@@ -190,6 +190,16 @@ __device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const floa
 // loader thread: fetch normalised x[:, 64kc .. 64kc+63] of its row into registers
 __device__ __forceinline__ void fetch_ln_chunk(const float* xrow, bool ok, int kc, float mean, float rstd,
                                                const float* __restrict__ g, const float* __restrict__ b, float4* buf) {
+  if (g == nullptr) {   // affine folded into the packed weights / bias by the host: only (x - mean) * rstd here
+    const float nm = -mean * rstd;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = fmaf(v.x, rstd, nm); v.y = fmaf(v.y, rstd, nm); v.z = fmaf(v.z, rstd, nm); v.w = fmaf(v.w, rstd, nm);
+      buf[c] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -473,6 +483,249 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p)
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ===============================================================================================================
+// Point-to-latent attention of one image (model/shape/implicit.py:38-57), flash-style: per 128-point tile and head h
+//   S = Q_h K_lat_h^T (tcgen05, N=208, TMEM half 0) -> softmax numerators (row max / sum also cover the point's own
+//   key) -> ring E as split-bf16 A chunks -> O_h = P V_lat_h (tcgen05, N=32, TMEM half 1) -> (O_h + e_self v_p,h)/sum.
+// The probabilities never leave the SM.  ChainParams reuse: x = qkv [M,768] (q|k|v, ldx), blob = K tiles (8 heads x
+// [hi 32K | lo 32K], 208 valid rows, 32 valid K columns), points -> V blob (8 heads x 32 KB: 4 key-chunks x
+// [hi 4K | lo 4K], 32 rows = head dims), out = O [M,256], b8 = softmax scale, apply_sigmoid = number of latent keys.
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  Bars B{smem_base + CT_OFF_BAR};
+  float* xch = reinterpret_cast<float*>(smem_gen + CT_OFF_BAR + 256);   // [2][128] exchange between column halves
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
+  const int n_tiles = (p.M + 127) / 128;
+  const int n_keys = p.apply_sigmoid;
+  const uint8_t* vblob = reinterpret_cast<const uint8_t*>(p.points);
+  constexpr uint32_t K_TILE_BYTES = 208 * 128;     // rows actually read by the N=208 MMA
+
+  if (warp < 4) {
+    // ---------------- loader: per head one chunk [q_h (32) | 0 (32)] ----------------
+    const int r = threadIdx.x;
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + r;
+      const bool ok = m < p.M;
+      const float* qrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
+      for (int h = 0; h < 8; ++h) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) buf[c] = ok ? __ldg(reinterpret_cast<const float4*>(qrow + h * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 8; c < 16; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+      }
+    }
+  } else if (warp == 13) {
+    // ---------------- W loader: per head K hi, K lo, V pack ----------------
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int h = 0; h < 8; ++h) {
+          for (int j = 0; j < 3; ++j) {
+            if (j == 1 && !split) continue;
+            const uint8_t* src = j < 2 ? p.blob + (size_t)h * 2 * CT_TILE_BYTES + (size_t)j * CT_TILE_BYTES
+                                       : vblob + (size_t)h * CT_TILE_BYTES;
+            const uint32_t bytes = j < 2 ? K_TILE_BYTES : (uint32_t)CT_TILE_BYTES;
+            mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
+            mbar_arrive_expect_tx(B.wfull(wr.idx), bytes);
+            bulk_g2s(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES, src, bytes, B.wfull(wr.idx));
+            wr.advance();
+          }
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS), lr(CT_LSLOTS), er(CT_ESLOTS);
+      uint32_t te_phase[2] = {0, 0};
+      const uint32_t idesc_s = umma_idesc_bf16(128, 208), idesc_o = umma_idesc_bf16(128, 32);
+      const uint32_t d_s = tmem_base, d_o = tmem_base + 256;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int h = 0; h < 8; ++h) {
+          // ---- S = Q_h K_h^T : K = 32 -> two K-steps of the chunk ----
+          mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
+          tc_fence_after();
+          mbar_wait(B.lfull(lr.idx), lr.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF;
+          const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+          mbar_wait(B.wfull(wr.idx), wr.phase);
+          tc_fence_after();
+          {
+            const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              umma_bf16(d_s, a_hi + 2 * k, w + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+              if (split) umma_bf16(d_s, a_lo + 2 * k, w + 2 * k, idesc_s, 1u);
+            }
+            umma_commit(B.wempty(wr.idx));
+            wr.advance();
+          }
+          if (split) {
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            tc_fence_after();
+            const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_bf16(d_s, a_hi + 2 * k, w + 2 * k, idesc_s, 1u);
+            umma_commit(B.wempty(wr.idx));
+            wr.advance();
+          }
+          umma_commit(B.lempty(lr.idx));
+          lr.advance();
+          umma_commit(B.tfull(0));
+          // ---- O_h = P V_h : 4 key chunks from ring E, V tiles from one W slot ----
+          mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1;
+          tc_fence_after();
+          mbar_wait(B.wfull(wr.idx), wr.phase);
+          tc_fence_after();
+          const uint32_t v_addr = smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES;
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(B.efull(er.idx), er.phase);
+            tc_fence_after();
+            const uint32_t e_addr = smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF;
+            const uint64_t e_hi = umma_desc_sw128(e_addr), e_lo = umma_desc_sw128(e_addr + CT_A_HALF);
+            const uint64_t v_hi = umma_desc_sw128(v_addr + c * 8192), v_lo = umma_desc_sw128(v_addr + c * 8192 + 4096);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_o, e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+              if (split) {
+                umma_bf16(d_o, e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
+                umma_bf16(d_o, e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
+              }
+            }
+            umma_commit(B.eempty(er.idx));
+            er.advance();
+          }
+          umma_commit(B.wempty(wr.idx));
+          wr.advance();
+          umma_commit(B.tfull(1));
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: softmax numerators -> ring E ; O normalisation -> global ----------------
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    Ring er(CT_ESLOTS);
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float sl2 = p.b8 * 1.4426950408889634f;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + row;
+      const bool ok = m < p.M;
+      const float* qrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
+      for (int h = 0; h < 8; ++h) {
+        float s_self = 0.f;
+#pragma unroll
+        for (int d = 0; d < 32; d += 4) {
+          const float4 qq = __ldg(reinterpret_cast<const float4*>(qrow + h * 32 + d));
+          const float4 kk = __ldg(reinterpret_cast<const float4*>(qrow + 256 + h * 32 + d));
+          s_self = fmaf(qq.x, kk.x, s_self); s_self = fmaf(qq.y, kk.y, s_self);
+          s_self = fmaf(qq.z, kk.z, s_self); s_self = fmaf(qq.w, kk.w, s_self);
+        }
+        mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+        tc_fence_after();
+        // pass 1: row max over the latent keys (this thread: columns c*64 + hsel*32 .. +32, c = 0..3)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
+          tmem_ld_wait();
+          const int c0 = c * 64 + hsel * 32;
+          if (c0 + 32 <= n_keys) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rr[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c0 + j < n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
+          }
+        }
+        xch[hsel * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(fmaxf(xch[row], xch[128 + row]), s_self);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mxs = mx * sl2;
+        // pass 2: e_j = exp(scale (s_j - max)) -> ring E (split bf16), running sum
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
+          tmem_ld_wait();
+          const int c0 = c * 64 + hsel * 32;
+          float v[32];
+          if (c0 + 32 <= n_keys) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = (c0 + j < n_keys) ? exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f; sum += v[j]; }
+          }
+          mbar_wait(B.eempty(er.idx), er.phase ^ 1);
+          uint8_t* slot = smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 hi, lo;
+            split_bf16x2(v[cc * 8 + 0], v[cc * 8 + 1], hi.x, lo.x);
+            split_bf16x2(v[cc * 8 + 2], v[cc * 8 + 3], hi.y, lo.y);
+            split_bf16x2(v[cc * 8 + 4], v[cc * 8 + 5], hi.z, lo.z);
+            split_bf16x2(v[cc * 8 + 6], v[cc * 8 + 7], hi.w, lo.w);
+            const uint32_t off = swizzle128_offset(row, hsel * 4 + cc);
+            *reinterpret_cast<uint4*>(slot + off) = hi;
+            if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(B.efull(er.idx));
+          er.advance();
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(0));
+        xch[hsel * 128 + row] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float e_self = exp2f(fmaf(s_self, sl2, -mxs));
+        const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // O_h: 32 accumulator columns, handled by the hsel == 0 thread of each row
+        mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
+        tc_fence_after();
+        if (hsel == 0) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + 256 + lane_off, rr);
+          tmem_ld_wait();
+          if (ok) {
+            const float ps = e_self * inv;
+            float* orow = p.out + (int64_t)m * 256 + h * 32;
+#pragma unroll
+            for (int d = 0; d < 32; d += 4) {
+              const float4 vv = __ldg(reinterpret_cast<const float4*>(qrow + 512 + h * 32 + d));
+              *reinterpret_cast<float4*>(orow + d) = make_float4(
+                  fmaf(__uint_as_float(rr[d + 0]), inv, ps * vv.x), fmaf(__uint_as_float(rr[d + 1]), inv, ps * vv.y),
+                  fmaf(__uint_as_float(rr[d + 2]), inv, ps * vv.z), fmaf(__uint_as_float(rr[d + 3]), inv, ps * vv.w));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(1));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static int chain_launch(void (*kern)(ChainParams), const ChainParams& p, cudaStream_t st, const char* name) {
   ZS_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   int tiles = (p.M + 127) / 128;
@@ -491,7 +744,7 @@ extern "C" size_t zs_chain_occ_blob_bytes(void) { return (size_t)48 * 2 * CT_TIL
 
 extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
                                 const void* blob, const float* b1, const float* b2, int precision, void* stream) {
-  ZS_REQUIRE(x && ln_w && ln_b && blob && b1 && b2 && M >= 0, "zs_chain_mlp_fwd: null pointer");
+  ZS_REQUIRE(x && blob && b1 && b2 && M >= 0 && ((ln_w == nullptr) == (ln_b == nullptr)), "zs_chain_mlp_fwd: null pointer");
   ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_mlp_fwd: x must be 16B aligned, ldx%4==0");
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (precision == 0 || precision == 1), "zs_chain_mlp_fwd: bad blob/precision");
   if (M == 0) return ZS_OK;
@@ -501,10 +754,26 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
 }
 
+extern "C" int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
+                                 float scale, float* O, int precision, void* stream) {
+  ZS_REQUIRE(qkv && Kblob && Vblob && O && M >= 0, "zs_chain_attn_fwd: null pointer");
+  ZS_REQUIRE(n_keys > 0 && n_keys <= 208, "zs_chain_attn_fwd: n_keys must be in [1, 208]");
+  ZS_REQUIRE(ld_qkv >= 768 && (ld_qkv & 3) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(O) & 15) == 0, "zs_chain_attn_fwd: qkv/O must be 16B aligned, ld % 4 == 0");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(Kblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vblob) & 15) == 0 &&
+             (precision == 0 || precision == 1), "zs_chain_attn_fwd: bad blob / precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = const_cast<float*>(qkv); p.ldx = ld_qkv; p.M = M; p.blob = reinterpret_cast<const uint8_t*>(Kblob);
+  p.points = reinterpret_cast<const float*>(Vblob); p.out = O; p.b8 = scale; p.apply_sigmoid = n_keys; p.precision = precision;
+  return chain_launch(chain_attn_kernel, p, as_stream(stream), "zs_chain_attn_fwd");
+}
+
 extern "C" int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
                                 float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
                                 float* out, int apply_sigmoid, int precision, void* stream) {
-  ZS_REQUIRE(x && points && ln_w && ln_b && blob && biases && w8 && out && M >= 0, "zs_chain_occ_fwd: null pointer");
+  ZS_REQUIRE(x && points && blob && biases && w8 && out && M >= 0 && ((ln_w == nullptr) == (ln_b == nullptr)),
+             "zs_chain_occ_fwd: null pointer");
   ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_occ_fwd: x must be 16B aligned, ldx%4==0");
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (precision == 0 || precision == 1), "zs_chain_occ_fwd: bad blob/precision");
   if (M == 0) return ZS_OK;

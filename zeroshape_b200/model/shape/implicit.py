@@ -158,25 +158,34 @@ class Implicit(nn.Module):
     def _chain_blobs(self):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if getattr(self, "_chain_cache", None) is None or self._chain_cache[0] != key:
-            mlp = []
+            # The LayerNorm affine is folded into the consumer GEMM (W.(g*xhat + b) = (W*g).xhat + W.b), so the loader
+            # warps only normalise: fc1' = fc1*gamma2, b1' = b1 + fc1.beta2; same for the `feat` columns of impl_mlp.
+            mlp, mlp_b1 = [], []
             for blk in self.blocks_attn:
-                w1, w2 = blk.mlp.fc1.weight.detach(), blk.mlp.fc2.weight.detach()
+                w1, w2 = blk.mlp.fc1.weight.detach().double(), blk.mlp.fc2.weight.detach()
+                g2, be2 = blk.norm2.weight.detach().double(), blk.norm2.bias.detach().double()
+                mlp_b1.append((blk.mlp.fc1.bias.detach().double() + w1 @ be2).float().contiguous())
+                w1 = (w1 * g2[None, :]).float()
                 mats = []
                 for g in range(4):
                     mats += [w1[256 * g:256 * (g + 1), :], w2[:, 256 * g:256 * (g + 1)]]
                 mlp.append(ops.pack_tiles(mats))
-            L = [lin.weight.detach() for lin in self.impl_mlp.layers]
-            s = 1.0 / SQRT2
-            mats = [torch.cat([L[0][:, 3:259], L[0][:, 0:3]], dim=1)]            # K order [feat | xyz]
+            L = [lin.weight.detach().double() for lin in self.impl_mlp.layers]
+            gn, bn = self.norm.weight.detach().double(), self.norm.bias.detach().double()
+            s = 1.0 / float(np.sqrt(2))
+            biases = [lin.bias.detach().double().clone() for lin in self.impl_mlp.layers[:8]]
+            biases[0] += L[0][:, 3:259] @ bn
+            mats = [torch.cat([L[0][:, 3:259] * gn[None, :], L[0][:, 0:3]], dim=1)]       # K order [feat | xyz]
             for l in range(1, 8):
-                if l in self.skip_in:                                             # cat([h, xyz, feat]) / sqrt(2)
-                    mats += [torch.cat([L[l][:, 259:515], L[l][:, 256:259]], dim=1) * s, L[l][:, 0:256] * s]
+                if l in self.skip_in:                                                      # cat([h, xyz, feat]) / sqrt(2)
+                    biases[l] += (L[l][:, 259:515] @ bn) * s
+                    mats += [torch.cat([L[l][:, 259:515] * gn[None, :], L[l][:, 256:259]], dim=1) * s, L[l][:, 0:256] * s]
                 else:
                     mats.append(L[l])
-            occ = ops.pack_tiles(mats)
-            biases = torch.stack([lin.bias.detach() for lin in self.impl_mlp.layers[:8]]).contiguous()
+            occ = ops.pack_tiles([m.float() for m in mats])
+            biases = torch.stack(biases).float().contiguous()
             w8 = self.impl_mlp.layers[8].weight.detach().reshape(-1).contiguous()
-            self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()))
+            self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()), mlp_b1)
         return self._chain_cache
 
     def _points_chain(self, lat, pts, attn_out=None, tc=False, sigmoid=False):
@@ -186,12 +195,22 @@ class Implicit(nn.Module):
         nb = len(self.blocks_attn)
         chain = tc and self.engine != "tc" and self._chain_ok()
         if chain:
-            _, mlp_blobs, occ_blob, occ_biases, w8, b8 = self._chain_blobs()
+            _, mlp_blobs, occ_blob, occ_biases, w8, b8, mlp_b1 = self._chain_blobs()
         x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
             k_lat, v_lat = lat["kv"][l]
             qkv = self._lin(self._ln(x, blk.norm1), blk.attn.qkv, tc)
-            if chain and attn_out is None and self.attention == "tc":
+            if chain and attn_out is None and self.attention == "fused":
+                # flash-style tensor-core attention: scores, softmax and P.V of a tile never leave the SM
+                packs = lat.setdefault("kv_fused", {})
+                a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
+                for b in range(B):
+                    if (l, b) not in packs:
+                        kp, vp = ops.attn_pack_kv(k_lat[b], v_lat[b], self.num_heads)
+                        packs[(l, b)] = (kp, ops.attn_pack_v_fused(vp, self.num_heads))
+                    ops.attn_fused(qkv[b * P:(b + 1) * P], packs[(l, b)][0], packs[(l, b)][1], lat["L"],
+                                   (C // self.num_heads) ** -0.5, self.precision, out=a[b * P:(b + 1) * P])
+            elif chain and attn_out is None and self.attention == "tc":
                 # tensor-core attention (two grouped tcgen05 launches per image; K/V operand images cached per image)
                 packs = lat.setdefault("kv_tc", {})
                 a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
@@ -206,14 +225,13 @@ class Implicit(nn.Module):
             del qkv
             x = self._lin(a, blk.attn.proj, tc, res=x)
             if chain:
-                ops.chain_mlp(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, mlp_blobs[l], blk.mlp.fc1.bias,
-                              blk.mlp.fc2.bias, self.precision)
+                ops.chain_mlp(x, None, None, blk.norm2.eps, mlp_blobs[l], mlp_b1[l], blk.mlp.fc2.bias, self.precision)
                 continue
             h = self._lin(self._ln(x, blk.norm2), blk.mlp.fc1, tc, act=ops.ACT_GELU)
             x = self._lin(h, blk.mlp.fc2, tc, res=x)
             del h
         if chain:
-            out = ops.chain_occ(x, pts.reshape(B * P, 3), self.norm.weight, self.norm.bias, self.norm.eps, occ_blob,
+            out = ops.chain_occ(x, pts.reshape(B * P, 3), None, None, self.norm.eps, occ_blob,
                                 occ_biases, w8, b8, sigmoid=sigmoid, precision=self.precision)
             return out.reshape(B, P)
         feat = self._ln(x, self.norm)

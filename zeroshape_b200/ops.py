@@ -138,7 +138,25 @@ def attn_pack_kv(k_lat, v_lat, heads=8):
     return torch.cat([pack_generic(kp[h]) for h in range(heads)]), torch.cat([pack_generic(vp[h]) for h in range(heads)])
 
 
-ATTN_SUBCHUNK = 8192      # rows per scores -> P.V round trip: keeps P (8192 x 1664 fp32 = 54 MB) resident in the 126 MB L2
+def attn_pack_v_fused(vpacked, heads=8):
+    """Vpacked (8 heads x 4 chunks x [hi 32K | lo 32K], 32 valid rows) -> compact blob for zs_chain_attn_fwd:
+    8 heads x 4 chunks x [hi 4K | lo 4K] (one 32 KB weight-ring slot per head)."""
+    v = vpacked.view(heads, 4, 2, 32768)[:, :, :, :4096]
+    return v.contiguous().view(-1)
+
+
+def attn_fused(qkv, kpacked, vfused, n_keys, scale, precision="bf16x3", out=None):
+    """qkv [M,768] -> attention output [M,256]: scores, softmax and P.V in one tcgen05 kernel (one image)."""
+    assert qkv.dim() == 2 and qkv.shape[1] == 768 and qkv.stride(1) == 1 and qkv.is_cuda and qkv.dtype == torch.float32
+    M = qkv.shape[0]
+    O = out if out is not None else torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
+    assert O.stride(0) == 256 and O.stride(1) == 1
+    check(lib.zs_chain_attn_fwd(_p(qkv), qkv.stride(0), M, _p(kpacked), _p(vfused), n_keys, scale, _p(O),
+                                PRECISIONS[precision], _stream()), "zs_chain_attn_fwd")
+    return O
+
+
+ATTN_SUBCHUNK = 1 << 18   # rows per scores -> P.V round trip of the two-kernel variant (attn_tc)
 
 
 def attn_tc(qkv, kpacked, vpacked, n_keys, scale, precision="bf16x3", out=None):
