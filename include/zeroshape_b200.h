@@ -102,6 +102,9 @@ size_t zs_chain_mlp_blob_bytes(void);
 size_t zs_chain_occ_blob_bytes(void);
 int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
                      const void* blob, const float* b1, const float* b2, int precision, void* stream);
+/* debug: zs_chain_mlp_fwd (LayerNorm affine folded) that also records per-role (clock64 << 8 | tag) events of CTA 0 */
+int zs_chain_mlp_trace(float* x, int ldx, int M, float ln_eps, const void* blob, const float* b1, const float* b2,
+                       int precision, unsigned long long* trace, void* stream);
 int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
                      float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
                      float* out, int apply_sigmoid, int precision, void* stream);

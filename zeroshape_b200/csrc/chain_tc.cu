@@ -41,6 +41,7 @@ struct ChainParams {
   float* out;                    // OCC: [M]
   int apply_sigmoid;
   int precision;
+  unsigned long long* trace;     // debug: per-role (tag, clock64) events of CTA 0 (nullptr in production)
 };
 
 struct Bars {
@@ -62,14 +63,19 @@ struct Ring {   // index/phase walker of an n-slot mbarrier ring
   __device__ void advance() { if (++idx == n) { idx = 0; phase ^= 1; } }
 };
 
+constexpr int CT_TRACE_EVENTS = 512;   // per role
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int role, int& n, int tag) {
+  if (tr != nullptr && blockIdx.x == 0 && n < CT_TRACE_EVENTS) tr[role * CT_TRACE_EVENTS + n++] = ((unsigned long long)clock64() << 8) | (unsigned)tag;
+}
+
 __device__ __forceinline__ float fast_softplus100(float x) {
   // torch Softplus(beta=100, threshold=20) = x if 100x > 20 else log1p(exp(100x))/100
   // Accurate to ~1e-7 relative with ~20 instructions: log1p(e^t) = max(t,0) + log1p(e^-|t|); log1p(u), u in (0,1], via
   // 2*atanh(u/(2+u)) (odd series, z <= 1/3) -- avoids the cancellation of log(1+u) for small u.
   const float bx = 100.0f * x;
   if (bx > 20.0f) return x;
-  const float u = exp2f(-fabsf(bx) * 1.4426950408889634f);
-  const float z = __fdividef(u, 2.0f + u);
+  const float u = fast_ex2(-fabsf(bx) * 1.4426950408889634f);
+  const float z = u * fast_rcp(2.0f + u);
   const float z2 = z * z;
   const float l = 2.0f * z * (1.0f + z2 * (0.33333334f + z2 * (0.2f + z2 * (0.14285715f + z2 * (0.11111111f + z2 * (0.09090909f + z2 * 0.07692308f))))));
   return (fmaxf(bx, 0.0f) + l) * 0.01f;
@@ -81,13 +87,13 @@ __device__ __forceinline__ float fast_softplus100(float x) {
 __device__ __forceinline__ float fast_gelu_erf(float x) {
   const float z = x * 0.70710678118654752440f;
   const float az = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, az, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-az * az * 1.4426950408889634f);
+  const float e = fast_ex2(-az * az * 1.4426950408889634f);
   const float erf_abs = fmaf(-poly, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, z));
 }
@@ -111,10 +117,12 @@ __device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen
 
 // MMA warp: consume one A chunk (hi at a_addr, lo at a_addr + 16K) against the next weight tile pair
 __device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Ring& wr, uint32_t a_addr, uint32_t d_tmem,
-                                          bool first, bool split, uint32_t a_empty_bar) {
+                                          bool first, bool split, uint32_t a_empty_bar, unsigned long long* tr = nullptr,
+                                          int* tn = nullptr) {
   const uint32_t idesc = umma_idesc_bf16(128, 256);
   const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
   mbar_wait(B.wfull(wr.idx), wr.phase);
+  if (tr) trace_ev(tr, 0, *tn, 3);
   tc_fence_after();
   {
     const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
@@ -126,8 +134,10 @@ __device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Rin
     umma_commit(B.wempty(wr.idx));
     wr.advance();
   }
+  if (tr) trace_ev(tr, 0, *tn, 4);
   if (split) {
     mbar_wait(B.wfull(wr.idx), wr.phase);
+    if (tr) trace_ev(tr, 0, *tn, 5);
     tc_fence_after();
     const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
 #pragma unroll
@@ -136,6 +146,7 @@ __device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Rin
     wr.advance();
   }
   umma_commit(a_empty_bar);
+  if (tr) trace_ev(tr, 0, *tn, 6);
 }
 
 // W loader warp (one lane): stream `pairs` (hi,lo) tile pairs of the blob through the W ring
@@ -254,20 +265,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
     const int r = threadIdx.x;
     Ring lr(CT_LSLOTS);
     float4 buf[16];
+    int tn = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m = t * 128 + r;
       const bool ok = m < p.M;
       const float* xrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
       float mean, rstd;
+      if (r == 0) trace_ev(p.trace, 1, tn, 14);
       row_ln_stats(xrow, ok, p.ln_eps, mean, rstd);
       fetch_ln_chunk(xrow, ok, 0, mean, rstd, p.ln_w, p.ln_b, buf);
+      if (r == 0) trace_ev(p.trace, 1, tn, 15);
       for (int i = 0; i < 16; ++i) {
+        if (r == 0) trace_ev(p.trace, 1, tn, 10);
         mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        if (r == 0) trace_ev(p.trace, 1, tn, 11);
         store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
         fence_proxy_async_smem();
         mbar_arrive(B.lfull(lr.idx));
+        if (r == 0) trace_ev(p.trace, 1, tn, 12);
         lr.advance();
         if (i + 1 < 16) fetch_ln_chunk(xrow, ok, (i + 1) & 3, mean, rstd, p.ln_w, p.ln_b, buf);
+        if (r == 0) trace_ev(p.trace, 1, tn, 13);
       }
     }
   } else if (warp == 13) {
@@ -280,23 +298,31 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
     if (lane == 0) {
       Ring wr(CT_WSLOTS), lr(CT_LSLOTS), er(CT_ESLOTS);
       uint32_t te_phase[2] = {0, 0};
+      int tn = 0;
       const uint32_t d0 = tmem_base, d1 = tmem_base + 256;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int g = 0; g < 4; ++g) {
+          trace_ev(p.trace, 0, tn, 7);
           mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
           tc_fence_after();
           for (int kc = 0; kc < 4; ++kc) {
+            trace_ev(p.trace, 0, tn, 1);
             mbar_wait(B.lfull(lr.idx), lr.phase);
+            trace_ev(p.trace, 0, tn, 2);
             tc_fence_after();
-            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, d0, kc == 0, split, B.lempty(lr.idx));
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, d0, kc == 0, split, B.lempty(lr.idx),
+                      p.trace, &tn);
             lr.advance();
           }
           umma_commit(B.tfull(0));
           if (g == 0) { mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1; tc_fence_after(); }
           for (int kc = 0; kc < 4; ++kc) {
+            trace_ev(p.trace, 0, tn, 8);
             mbar_wait(B.efull(er.idx), er.phase);
+            trace_ev(p.trace, 0, tn, 9);
             tc_fence_after();
-            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF, d1, g == 0 && kc == 0, split, B.eempty(er.idx));
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF, d1, g == 0 && kc == 0, split, B.eempty(er.idx),
+                      p.trace, &tn);
             er.advance();
           }
         }
@@ -310,20 +336,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
     Ring er(CT_ESLOTS);
     uint32_t tf_phase[2] = {0, 0};
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    int tn = 0;
+    const bool tr0 = (warp == 4 && lane == 0);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m = t * 128 + row;
       for (int g = 0; g < 4; ++g) {
+        if (tr0) trace_ev(p.trace, 2, tn, 20);
         mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 21);
         tc_fence_after();
         for (int c = 0; c < 4; ++c) {
           uint32_t rr[32];
           tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
           tmem_ld_wait();
+          if (tr0) trace_ev(p.trace, 2, tn, 22);
           mbar_wait(B.eempty(er.idx), er.phase ^ 1);
+          if (tr0) trace_ev(p.trace, 2, tn, 23);
           epi_to_ring<ZS_ACT_GELU>(smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF, row, hsel, rr,
                                    p.bias + g * 256 + c * 64 + hsel * 32, split);
           fence_proxy_async_smem();
           mbar_arrive(B.efull(er.idx));
+          if (tr0) trace_ev(p.trace, 2, tn, 24);
           er.advance();
         }
         tc_fence_before();
@@ -668,10 +701,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
           float v[32];
           if (c0 + 32 <= n_keys) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
+            for (int j = 0; j < 32; ++j) { v[j] = fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = (c0 + j < n_keys) ? exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f; sum += v[j]; }
+            for (int j = 0; j < 32; ++j) { v[j] = (c0 + j < n_keys) ? fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f; sum += v[j]; }
           }
           mbar_wait(B.eempty(er.idx), er.phase ^ 1);
           uint8_t* slot = smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF;
@@ -694,7 +727,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
         mbar_arrive(B.tempty(0));
         xch[hsel * 128 + row] = sum;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float e_self = exp2f(fmaf(s_self, sl2, -mxs));
+        const float e_self = fast_ex2(fmaf(s_self, sl2, -mxs));
         const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // O_h: 32 accumulator columns, handled by the hsel == 0 thread of each row
@@ -752,6 +785,16 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   p.x = x; p.ldx = ldx; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
   return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
+}
+
+// debug variant of zs_chain_mlp_fwd: also records (clock64 << 8 | tag) events of CTA 0 into `trace` [3][512] uint64
+extern "C" int zs_chain_mlp_trace(float* x, int ldx, int M, float ln_eps, const void* blob, const float* b1, const float* b2,
+                                  int precision, unsigned long long* trace, void* stream) {
+  ZS_REQUIRE(x && blob && b1 && b2 && trace && M > 0, "zs_chain_mlp_trace: null pointer");
+  ChainParams p{};
+  p.x = x; p.ldx = ldx; p.M = M; p.ln_w = nullptr; p.ln_b = nullptr; p.ln_eps = ln_eps;
+  p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision; p.trace = trace;
+  return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_trace");
 }
 
 extern "C" int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,

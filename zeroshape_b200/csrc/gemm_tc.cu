@@ -184,11 +184,11 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
       float v[32];
       if (lc + 32 <= p.n_keys) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
+        for (int j = 0; j < 32; ++j) { v[j] = fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          v[j] = (lc + j < p.n_keys) ? exp2f(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f;
+          v[j] = (lc + j < p.n_keys) ? fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f;
           sum += v[j];
         }
       }
@@ -207,7 +207,7 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
   }
   xch[hsel * 128 + row] = sum;
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  const float e_self = exp2f(fmaf(s_self, sl2, -mxs));
+  const float e_self = fast_ex2(fmaf(s_self, sl2, -mxs));
   const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (hsel == 0 && ok) {

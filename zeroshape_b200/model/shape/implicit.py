@@ -89,7 +89,7 @@ class Implicit(nn.Module):
             nn.Linear(dims[l] + (dims[0] if l in self.skip_in else 0), dims[l + 1]) for l in range(len(dims) - 1)])
         self.engine = "auto"          # "auto" | "fused" | "tc" | "f32"
         self.precision = "bf16x3"     # tensor-core operand precision: "bf16x3" (parity) | "bf16" (fast)
-        self.attention = "tc"         # point attention: "tc" (tcgen05 grouped GEMMs + softmax epilogue) | "f32" (FFMA kernel)
+        self.attention = "fused"      # point attention: "fused" (one flash-style tcgen05 kernel) | "tc" (two grouped tcgen05 launches) | "f32" (FFMA kernel)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         self.point_chunk = 1 << 18    # query points per pass of the per-layer / chained engines (bounds scratch memory)
         self._packed = None           # (version key, packed weight blob) for the fused engine
