@@ -98,6 +98,45 @@ __device__ __forceinline__ float fast_gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, z));
 }
 
+// The same two activations on PAIRS (FFMA2 / FMUL2 / FADD2): the polynomial parts cost half the issue slots; only
+// |.|, MUFU, copysign / max / select stay per element.  ~10 (GELU) and ~14 (Softplus) instructions per element.
+__device__ __forceinline__ float2 fast_gelu_erf2(float2 x) {
+  const float2 z = mul2(x, bc2(0.70710678118654752440f));
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = fma2(bc2(0.3275911f), az, bc2(1.0f));
+  const float2 t = make_float2(fast_rcp(den.x), fast_rcp(den.y));
+  float2 np = fma2(bc2(-1.061405429f), t, bc2(1.453152027f));   // the NEGATED polynomial (exact sign symmetry of fma)
+  np = fma2(np, t, bc2(-1.421413741f));
+  np = fma2(np, t, bc2(0.284496736f));
+  np = fma2(np, t, bc2(-0.254829592f));
+  np = mul2(np, t);
+  const float2 ea = mul2(mul2(az, az), bc2(-1.4426950408889634f));
+  const float2 e = make_float2(fast_ex2(ea.x), fast_ex2(ea.y));
+  const float2 erf_abs = fma2(np, e, bc2(1.0f));
+  const float2 er = make_float2(copysignf(erf_abs.x, z.x), copysignf(erf_abs.y, z.y));
+  const float2 hx = mul2(x, bc2(0.5f));
+  return fma2(hx, er, hx);
+}
+
+__device__ __forceinline__ float2 fast_softplus100_2(float2 x) {
+  const float2 bx = mul2(x, bc2(100.0f));
+  const float2 nab = make_float2(-fabsf(bx.x), -fabsf(bx.y));
+  const float2 ua = mul2(nab, bc2(1.4426950408889634f));
+  const float2 u = make_float2(fast_ex2(ua.x), fast_ex2(ua.y));
+  const float2 den = add2(u, bc2(2.0f));
+  const float2 z = mul2(u, make_float2(fast_rcp(den.x), fast_rcp(den.y)));
+  const float2 z2 = mul2(z, z);
+  float2 poly = fma2(z2, bc2(0.07692308f), bc2(0.09090909f));
+  poly = fma2(z2, poly, bc2(0.11111111f));
+  poly = fma2(z2, poly, bc2(0.14285715f));
+  poly = fma2(z2, poly, bc2(0.2f));
+  poly = fma2(z2, poly, bc2(0.33333334f));
+  poly = fma2(z2, poly, bc2(1.0f));
+  const float2 l = mul2(mul2(z, bc2(2.0f)), poly);
+  const float2 o = mul2(add2(make_float2(fmaxf(bx.x, 0.0f), fmaxf(bx.y, 0.0f)), l), bc2(0.01f));
+  return make_float2(bx.x > 20.0f ? x.x : o.x, bx.y > 20.0f ? x.y : o.y);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // common prologue: barriers + TMEM
 __device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen, uint32_t smem_base, int warp) {
@@ -162,26 +201,6 @@ __device__ __forceinline__ void w_stream(const Bars& B, uint32_t smem_base, Ring
   }
 }
 
-// loader thread: LayerNorm statistics of its row (two sweeps over L2-resident data)
-__device__ __forceinline__ void row_ln_stats(const float* xrow, bool ok, float eps, float& mean, float& rstd) {
-  float s = 0.f;
-  if (ok) {
-#pragma unroll 8
-    for (int c = 0; c < 64; ++c) { float4 v = __ldg(reinterpret_cast<const float4*>(xrow) + c); s += (v.x + v.y) + (v.z + v.w); }
-  }
-  mean = s * (1.0f / 256.0f);
-  float q = 0.f;
-  if (ok) {
-#pragma unroll 8
-    for (int c = 0; c < 64; ++c) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(xrow) + c);
-      float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
-      q += (a * a + b * b) + (cc * cc + d * d);
-    }
-  }
-  rstd = rsqrtf(q * (1.0f / 256.0f) + eps);
-}
-
 // loader thread: write 64 values (already in registers as 16 float4) as a swizzled (hi,lo) chunk row
 __device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const float4* buf, bool split) {
 #pragma unroll
@@ -198,27 +217,72 @@ __device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const floa
   }
 }
 
-// loader thread: fetch normalised x[:, 64kc .. 64kc+63] of its row into registers
-__device__ __forceinline__ void fetch_ln_chunk(const float* xrow, bool ok, int kc, float mean, float rstd,
-                                               const float* __restrict__ g, const float* __restrict__ b, float4* buf) {
-  if (g == nullptr) {   // affine folded into the packed weights / bias by the host: only (x - mean) * rstd here
-    const float nm = -mean * rstd;
+// ---- coalesced loader (4 warps; warp w owns tile rows 32w .. 32w+31) ------------------------------------------
+// A thread-per-row loader reads 16 B out of every 1 KB row per instruction (32 sectors per request, L1 thrashing):
+// measured 44k cycles per tile for the LayerNorm statistics alone.  Here a warp walks its rows with the lanes along
+// the columns, so every request is one or two fully used 256..1024-byte segments.
+// LayerNorm statistics of the warp's 32 rows (two-pass variance on register-held data); lane L receives
+// (sc, sh) = (rstd, -mean * rstd) of row m0 + L, or (0, 0) past M so that padded rows normalise to zero.
+__device__ __forceinline__ void warp_ln_stats(const float* __restrict__ x, int ldx, int m0, int M, float eps, int lane,
+                                              float& sc, float& sh) {
+  sc = 0.f; sh = 0.f;
+#pragma unroll 1
+  for (int i0 = 0; i0 < 32; i0 += 4) {
+    float4 a[4], b[4];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v.x = fmaf(v.x, rstd, nm); v.y = fmaf(v.y, rstd, nm); v.z = fmaf(v.z, rstd, nm); v.w = fmaf(v.w, rstd, nm);
-      buf[c] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + i0 + u;
+      const float4* p4 = reinterpret_cast<const float4*>(x + (int64_t)(m < M ? m : 0) * ldx);
+      a[u] = __ldg(p4 + lane);
+      b[u] = __ldg(p4 + 32 + lane);
     }
-    return;
-  }
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xrow + kc * 64) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + kc * 64) + c);
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + kc * 64) + c);
-    v.x = (v.x - mean) * rstd * gg.x + bb.x; v.y = (v.y - mean) * rstd * gg.y + bb.y;
-    v.z = (v.z - mean) * rstd * gg.z + bb.z; v.w = (v.w - mean) * rstd * gg.w + bb.w;
-    buf[c] = ok ? v : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const float s = ((a[u].x + a[u].y) + (a[u].z + a[u].w)) + ((b[u].x + b[u].y) + (b[u].z + b[u].w));
+      const float mean = warp_sum(s) * (1.0f / 256.0f);
+      const float d0 = a[u].x - mean, d1 = a[u].y - mean, d2 = a[u].z - mean, d3 = a[u].w - mean;
+      const float d4 = b[u].x - mean, d5 = b[u].y - mean, d6 = b[u].z - mean, d7 = b[u].w - mean;
+      const float q = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + eps);
+      if (lane == i0 + u && m0 + i0 + u < M) { sc = rstd; sh = -mean * rstd; }
+    }
+  }
+}
+
+// 64 columns [col0, col0+64) of the warp's 32 rows: instruction j covers rows 2j, 2j+1 (16 lanes x float4 each)
+__device__ __forceinline__ void fetch_chunk_co(const float* __restrict__ x, int ldx, int m0, int M, int col0, int lane, float4* buf) {
+  const int sub = lane >> 4, q = lane & 15;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int m = m0 + 2 * j + sub;
+    buf[j] = m < M ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)m * ldx + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// normalise (v * sc[row] + sh[row], optional affine g/b of this lane's 4 columns), split, store into the swizzled chunk
+__device__ __forceinline__ void store_chunk_co(uint8_t* slot, int w, int lane, const float4* buf, bool normalise, float sc, float sh,
+                                               const float* __restrict__ g, const float* __restrict__ b, bool split) {
+  const int sub = lane >> 4, q = lane & 15;
+  float4 gg = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g != nullptr) { gg = __ldg(reinterpret_cast<const float4*>(g) + q); bb = __ldg(reinterpret_cast<const float4*>(b) + q); }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int rl = 2 * j + sub;
+    float2 v0 = make_float2(buf[j].x, buf[j].y), v1 = make_float2(buf[j].z, buf[j].w);
+    if (normalise) {
+      const float s = __shfl_sync(0xffffffffu, sc, rl), h = __shfl_sync(0xffffffffu, sh, rl);
+      v0 = fma2(v0, bc2(s), bc2(h)); v1 = fma2(v1, bc2(s), bc2(h));
+      if (g != nullptr) {
+        v0 = fma2(v0, make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+        v1 = fma2(v1, make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+      }
+    }
+    uint2 hi, lo;
+    split_bf16x2(v0.x, v0.y, hi.x, lo.x);
+    split_bf16x2(v1.x, v1.y, hi.y, lo.y);
+    const uint32_t off = swizzle128_offset(32 * w + rl, q >> 1) + ((q & 1) << 3);
+    *reinterpret_cast<uint2*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
   }
 }
 
@@ -228,20 +292,20 @@ __device__ __forceinline__ void epi_to_ring(uint8_t* slot, int row, int hsel, co
                                             bool split) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    float v[8];
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + 4));
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    float2 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = __uint_as_float(rr[c * 8 + j]) + bb[j];
-      v[j] = ACT == ZS_ACT_GELU ? fast_gelu_erf(t) : fast_softplus100(t);
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = add2(make_float2(__uint_as_float(rr[c * 8 + 2 * j]), __uint_as_float(rr[c * 8 + 2 * j + 1])), bb[j]);
+      v[j] = ACT == ZS_ACT_GELU ? fast_gelu_erf2(t) : fast_softplus100_2(t);
     }
     uint4 hi, lo;
-    split_bf16x2(v[0], v[1], hi.x, lo.x);
-    split_bf16x2(v[2], v[3], hi.y, lo.y);
-    split_bf16x2(v[4], v[5], hi.z, lo.z);
-    split_bf16x2(v[6], v[7], hi.w, lo.w);
+    split_bf16x2(v[0].x, v[0].y, hi.x, lo.x);
+    split_bf16x2(v[1].x, v[1].y, hi.y, lo.y);
+    split_bf16x2(v[2].x, v[2].y, hi.z, lo.z);
+    split_bf16x2(v[3].x, v[3].y, hi.w, lo.w);
     const uint32_t off = swizzle128_offset(row, hsel * 4 + c);
     *reinterpret_cast<uint4*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
@@ -267,24 +331,24 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
     float4 buf[16];
     int tn = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m = t * 128 + r;
-      const bool ok = m < p.M;
-      const float* xrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
-      float mean, rstd;
+      const int m0 = t * 128 + warp * 32;
+      float sc, sh;
       if (r == 0) trace_ev(p.trace, 1, tn, 14);
-      row_ln_stats(xrow, ok, p.ln_eps, mean, rstd);
-      fetch_ln_chunk(xrow, ok, 0, mean, rstd, p.ln_w, p.ln_b, buf);
+      warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk_co(p.x, p.ldx, m0, p.M, 0, lane, buf);
       if (r == 0) trace_ev(p.trace, 1, tn, 15);
       for (int i = 0; i < 16; ++i) {
+        const int kc = i & 3;
         if (r == 0) trace_ev(p.trace, 1, tn, 10);
         mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
         if (r == 0) trace_ev(p.trace, 1, tn, 11);
-        store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+        store_chunk_co(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh,
+                       p.ln_w ? p.ln_w + kc * 64 : nullptr, p.ln_b ? p.ln_b + kc * 64 : nullptr, split);
         fence_proxy_async_smem();
         mbar_arrive(B.lfull(lr.idx));
         if (r == 0) trace_ev(p.trace, 1, tn, 12);
         lr.advance();
-        if (i + 1 < 16) fetch_ln_chunk(xrow, ok, (i + 1) & 3, mean, rstd, p.ln_w, p.ln_b, buf);
+        if (i + 1 < 16) fetch_chunk_co(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
         if (r == 0) trace_ev(p.trace, 1, tn, 13);
       }
     }
@@ -364,22 +428,33 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
       }
       mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
       tc_fence_after();
+      // x += fc2 + b2, transposed through smem (ring E is idle here: every fc2 MMA of the tile has completed) so that
+      // global memory sees whole 256-byte row segments instead of 16 bytes per row per request.
+      float* tr_buf = reinterpret_cast<float*>(smem_gen + CT_OFF_E);   // [128][68] fp32 (padded rows: conflict-free both ways)
+      const int sub = lane >> 4, q4 = lane & 15;
       for (int c = 0; c < 4; ++c) {
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + 256 + lane_off + c * 64 + hsel * 32, rr);
         tmem_ld_wait();
-        if (m < p.M) {
-          float* xr = p.x + (int64_t)m * p.ldx + c * 64 + hsel * 32;
-          const float* b2 = p.bias2 + c * 64 + hsel * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 xv = *reinterpret_cast<const float4*>(xr + 4 * j);
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(b2) + j);
-            xv.x += __uint_as_float(rr[4 * j + 0]) + bv.x; xv.y += __uint_as_float(rr[4 * j + 1]) + bv.y;
-            xv.z += __uint_as_float(rr[4 * j + 2]) + bv.z; xv.w += __uint_as_float(rr[4 * j + 3]) + bv.w;
-            *reinterpret_cast<float4*>(xr + 4 * j) = xv;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tr_buf + row * 68 + hsel * 32 + 4 * j) =
+              make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + c * 64) + q4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 16 + e * 2 + sub;
+          const int mm = t * 128 + rl;
+          if (mm < p.M) {
+            const float4 a = *reinterpret_cast<const float4*>(tr_buf + rl * 68 + 4 * q4);
+            float4* xp = reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + c * 64) + q4;
+            float4 xv = *xp;
+            xv.x += a.x + bv.x; xv.y += a.y + bv.y; xv.z += a.z + bv.z; xv.w += a.w + bv.w;
+            *xp = xv;
           }
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       tc_fence_before();
       mbar_arrive(B.tempty(1));
@@ -409,25 +484,31 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p)
     const int r = threadIdx.x;
     Ring lr(CT_LSLOTS);
     float4 buf[16];
+    (void)r;
+    const int sub = lane >> 4, q = lane & 15;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m = t * 128 + r;
-      const bool ok = m < p.M;
-      const float* xrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
-      float mean, rstd;
-      row_ln_stats(xrow, ok, p.ln_eps, mean, rstd);
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (ok) { px = __ldg(p.points + (int64_t)m * 3); py = __ldg(p.points + (int64_t)m * 3 + 1); pz = __ldg(p.points + (int64_t)m * 3 + 2); }
+      const int m0 = t * 128 + warp * 32;
+      float sc, sh;
+      warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
       for (int rep = 0; rep < 4; ++rep) {
         for (int kc = 0; kc < 5; ++kc) {
           if (kc < 4) {
-            fetch_ln_chunk(xrow, ok, kc, mean, rstd, p.ln_w, p.ln_b, buf);
+            fetch_chunk_co(p.x, p.ldx, m0, p.M, kc * 64, lane, buf);
           } else {
+            // the xyz chunk: columns 0..2 = the query point, the rest zero (lanes q == 0 own columns 0..3 of their rows)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-            buf[0] = make_float4(px, py, pz, 0.f);
+            for (int j = 0; j < 16; ++j) {
+              const int m = m0 + 2 * j + sub;
+              buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (q == 0 && m < p.M) {
+                const float* pp = p.points + (int64_t)m * 3;
+                buf[j] = make_float4(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2), 0.f);
+              }
+            }
           }
           mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
-          store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+          store_chunk_co(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, kc < 4, sc, sh,
+                         (kc < 4 && p.ln_w) ? p.ln_w + kc * 64 : nullptr, (kc < 4 && p.ln_b) ? p.ln_b + kc * 64 : nullptr, split);
           fence_proxy_async_smem();
           mbar_arrive(B.lfull(lr.idx));
           lr.advance();
@@ -492,8 +573,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p)
             er.advance();
           } else {
             const float* w8 = p.bias2 + c * 64 + hsel * 32;
+            float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dot = fmaf(fast_softplus100(__uint_as_float(rr[j]) + __ldg(bl + j)), __ldg(w8 + j), dot);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bl) + j), w4 = __ldg(reinterpret_cast<const float4*>(w8) + j);
+              const float2 s0 = fast_softplus100_2(add2(make_float2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), make_float2(b4.x, b4.y)));
+              const float2 s1 = fast_softplus100_2(add2(make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), make_float2(b4.z, b4.w)));
+              dot2 = fma2(s0, make_float2(w4.x, w4.y), dot2);
+              dot2 = fma2(s1, make_float2(w4.z, w4.w), dot2);
+            }
+            dot += dot2.x + dot2.y;
           }
         }
         tc_fence_before();

@@ -122,6 +122,41 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, new on sm_100): two IEEE-rounded fp32 results per issue
+// slot, bit-identical to the scalar fmaf / * / + they replace.  The epilogues of the chained kernels are bound by
+// instruction issue, so everything polynomial runs on pairs. -------------------------------------------------------
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long r) {
+  float2 a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+  return a;
+}
+__device__ __forceinline__ float2 bc2(float c) { return make_float2(c, c); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+  return upk2(d);
+}
+
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits; products hi*hi + hi*lo + lo*hi
 // reproduce the fp32 product to ~2^-16 relative.
@@ -129,9 +164,9 @@ __device__ __forceinline__ float fast_rcp(float x) {
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x (low 16 bits) = bf16(a), .y (high) = bf16(b)
   hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float ra = a - __uint_as_float(hi << 16);                // bf16 -> fp32 is a 16-bit shift
-  const float rb = b - __uint_as_float(hi & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  // bf16 -> fp32 is a 16-bit shift; the two residuals are one FADD2
+  const float2 r = sub2(make_float2(a, b), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
