@@ -84,10 +84,16 @@ int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, const flo
                   void* stream);
 
 /* Same attention, flash-style in ONE kernel (scores, softmax numerators and P.V of a 128-point tile stay on the SM;
- * csrc/chain_tc.cu chain_attn_kernel).  Kblob as Kpacked above; Vblob: 8 heads x 32 KB = 4 key-chunks x [hi 4 KB | lo 4 KB]
- * (the first 4 KB of each hi / lo tile of Vpacked).  O [M,256]. */
+ * csrc/chain_tc.cu chain_attn_kernel).  The 8 heads are processed as 4 pairs (2p, 2p+1):
+ *   Kblob: 4 pair tiles from zs_gemm_tc_pack(K_lat[:, 64p:64p+64] zero-padded to 256 rows) = 4 x [hi 32 KB | lo 32 KB]
+ *          (the two heads' 32 dims side by side, keys along the rows);
+ *   Vblob: 8 heads x 32 KB = 4 key-chunks x [hi 4 KB | lo 4 KB] (the first 4 KB of each hi / lo tile of Vpacked above).
+ * n_keys <= 208.  O [M,256]. */
 int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
                       float scale, float* O, int precision, void* stream);
+/* debug: while buf (device, [3][512] uint64) is non-NULL the chained kernels record role-level clock64 events of
+ * CTA 0 (MMA thread, loader thread 0, epilogue warp 4 lane 0) into it; see tools/trace_chain.py.  Not thread-safe. */
+int zs_debug_chain_trace(unsigned long long* buf);
 
 /* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
  * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack
@@ -102,9 +108,6 @@ size_t zs_chain_mlp_blob_bytes(void);
 size_t zs_chain_occ_blob_bytes(void);
 int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
                      const void* blob, const float* b1, const float* b2, int precision, void* stream);
-/* debug: zs_chain_mlp_fwd (LayerNorm affine folded) that also records per-role (clock64 << 8 | tag) events of CTA 0 */
-int zs_chain_mlp_trace(float* x, int ldx, int M, float ln_eps, const void* blob, const float* b1, const float* b2,
-                       int precision, unsigned long long* trace, void* stream);
 int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
                      float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
                      float* out, int apply_sigmoid, int precision, void* stream);

@@ -149,11 +149,11 @@ def test_fused_attention_kernel_matches_reference_math(cuda, M):
     a = s.softmax(-1)
     ref = (a[..., :L] @ vl + a[..., L:] * v).permute(1, 0, 2).reshape(M, C)
     lat_dev = lat_qkv.to(cuda)
-    kp, vp = ops.attn_pack_kv(lat_dev[0, :, C:2 * C], lat_dev[0, :, 2 * C:], H)
-    out = ops.attn_fused(qkv.to(cuda), kp, ops.attn_pack_v_fused(vp, H), L, 32 ** -0.5)
+    kb, vb = ops.attn_pack_fused(lat_dev[0, :, C:2 * C], lat_dev[0, :, 2 * C:], H)
+    out = ops.attn_fused(qkv.to(cuda), kb, vb, L, 32 ** -0.5)
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 2e-5 * ref.abs().max().item(), err
-    fast = ops.attn_fused(qkv.to(cuda), kp, ops.attn_pack_v_fused(vp, H), L, 32 ** -0.5, precision="bf16")
+    fast = ops.attn_fused(qkv.to(cuda), kb, vb, L, 32 ** -0.5, precision="bf16")
     assert (fast.cpu().double() - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
 
 

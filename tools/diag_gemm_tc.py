@@ -135,7 +135,7 @@ try:
     qkv = torch.randn(M, 3 * C, device=dev)
     latq = torch.randn(1, L, 3 * C, device=dev)
     kp, vp = ops.attn_pack_kv(latq[0, :, C:2 * C], latq[0, :, 2 * C:], H)
-    vf = ops.attn_pack_v_fused(vp, H)
+    kb, vf = ops.attn_pack_fused(latq[0, :, C:2 * C], latq[0, :, 2 * C:], H)
     def timeit(fn, n=5):
         for _ in range(2): fn()
         torch.cuda.synchronize()
@@ -145,7 +145,7 @@ try:
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     for prec in ("bf16x3", "bf16"):
-        log(f"[time] attn_fused M={M} {prec}: {timeit(lambda: ops.attn_fused(qkv, kp, vf, L, 32 ** -0.5, prec)):.3f} ms")
+        log(f"[time] attn_fused M={M} {prec}: {timeit(lambda: ops.attn_fused(qkv, kb, vf, L, 32 ** -0.5, prec)):.3f} ms")
     log(f"[time] attn_tc (2 kernels) M={M} bf16x3: {timeit(lambda: ops.attn_tc(qkv, kp, vp, L, 32 ** -0.5)):.3f} ms")
     log(f"[time] point_attention f32 M={M}: {timeit(lambda: ops.point_attention(qkv.view(1, M, 3 * C), latq[..., C:2 * C], latq[..., 2 * C:], H), 2):.3f} ms")
 except Exception as ex:

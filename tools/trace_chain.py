@@ -1,6 +1,7 @@
-"""Role-level timeline of chain_mlp_kernel (CTA 0): clock64 events of the MMA thread, loader row 0 and epilogue warp 4.
+"""Role-level timelines of the chained tcgen05 kernels (CTA 0): clock64 events of the MMA thread, loader thread 0 and
+epilogue warp 4 lane 0, recorded through zs_debug_chain_trace.
 
-Writes gpurun_out/trace_chain_mlp_<prec>.txt (events sorted by time, cycles relative to the first event) and a
+Writes gpurun_out/trace_<kernel>_<prec>.txt (events sorted by time, cycles relative to the first event) and a
 per-role summary of where the cycles go.  Debug tool -- not part of the product path.
 """
 import os
@@ -12,14 +13,55 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zeroshape_b200 import ops  # noqa: E402
 from zeroshape_b200._native import check, lib  # noqa: E402
 
-TAGS = {
+TAGS_MLP = {
     1: "mma: wait lfull", 2: "mma: lfull ok", 3: "mma: wfull(hi) ok", 4: "mma: hi issued", 5: "mma: wfull(lo) ok",
     6: "mma: chunk issued", 7: "mma: wait tempty", 8: "mma: wait efull", 9: "mma: efull ok",
     10: "ld : wait lempty", 11: "ld : lempty ok", 12: "ld : stored+arrived", 13: "ld : next fetched", 14: "ld : tile start",
     15: "ld : stats+first fetch done",
     20: "epi: wait tfull", 21: "epi: tfull ok", 22: "epi: tmem ld done", 23: "epi: eempty ok", 24: "epi: stored+arrived",
 }
+TAGS_ATTN = {
+    1: "mma: pair start (wait lfull)", 2: "mma: S issued", 3: "mma: PV chunk issued",
+    10: "ld : fetched, wait lempty", 11: "ld : lempty ok", 12: "ld : stored+arrived",
+    20: "epi: wait sfull", 21: "epi: sfull ok", 22: "epi: pass1 done", 23: "epi: chunk stored", 24: "epi: wait ofull",
+    25: "epi: ofull ok", 26: "epi: out stored",
+}
 NE = 512
+
+
+def run_traced(name, tags, fn):
+    dev = torch.device("cuda:0")
+    tr = torch.zeros(3 * NE, dtype=torch.int64, device=dev)
+    for _ in range(2):  # second call = warm
+        tr.zero_()
+        check(lib.zs_debug_chain_trace(tr.data_ptr()), "trace on")
+        try:
+            fn()
+            torch.cuda.synchronize()
+        finally:
+            check(lib.zs_debug_chain_trace(None), "trace off")
+    ev = []
+    for role in range(3):
+        for v in tr[role * NE:(role + 1) * NE].tolist():
+            if v:
+                ev.append(((v >> 8) & ((1 << 56) - 1), role, v & 0xff))
+    ev.sort()
+    t0 = ev[0][0]
+    lines = [f"{t - t0:9d}  r{role}  {tags.get(tag, tag)}" for t, role, tag in ev]
+    summ = {}   # per role: time between consecutive events, attributed to the LATER event's tag
+    for role in range(3):
+        es = [(t, tag) for t, r, tag in ev if r == role]
+        for (ta, _), (tb, tagb) in zip(es, es[1:]):
+            k = tags.get(tagb, str(tagb))
+            c, n = summ.get(k, (0, 0))
+            summ[k] = (c + tb - ta, n + 1)
+    out = [f"{name}: cycles until each event since the previous event of the same role"]
+    for k in sorted(summ):
+        c, n = summ[k]
+        out.append(f"  {k:32s} total {c:9d}  n {n:4d}  avg {c / max(n, 1):9.1f}")
+    out.append(f"  traced span {ev[-1][0] - t0} cycles")
+    open(f"gpurun_out/trace_{name}.txt", "w").write("\n".join(out + [""] + lines) + "\n")
+    print("\n".join(out))
 
 
 def main():
@@ -36,38 +78,17 @@ def main():
     blob = ops.pack_tiles(mats)
     x0 = torch.randn(M, 256, device=dev)
     os.makedirs("gpurun_out", exist_ok=True)
-    for prec in ("bf16x3", "bf16"):
+    which = sys.argv[1:] or ["mlp", "attn"]
+    if "mlp" in which:
         x = x0.clone()
-        tr = torch.zeros(3 * NE, dtype=torch.int64, device=dev)
-        for _ in range(2):  # second call = warm
-            tr.zero_()
-            check(lib.zs_chain_mlp_trace(x.data_ptr(), 256, M, 1e-6, blob.data_ptr(), b1.data_ptr(), b2.data_ptr(),
-                                         ops.PRECISIONS[prec], tr.data_ptr(), None), "trace")
-            torch.cuda.synchronize()
-        ev = []
-        for role in range(3):
-            for v in tr[role * NE:(role + 1) * NE].tolist():
-                if v:
-                    ev.append(((v >> 8) & ((1 << 56) - 1), role, v & 0xff))
-        ev.sort()
-        t0 = ev[0][0]
-        lines = [f"{t - t0:9d}  r{role}  {TAGS.get(tag, tag)}" for t, role, tag in ev]
-        # per-role: time between consecutive events, attributed to the LATER event's tag
-        summ = {}
-        for role in range(3):
-            es = [(t, tag) for t, r, tag in ev if r == role]
-            for (ta, _), (tb, tagb) in zip(es, es[1:]):
-                k = TAGS.get(tagb, str(tagb))
-                c, n = summ.get(k, (0, 0))
-                summ[k] = (c + tb - ta, n + 1)
-        out = [f"chain_mlp trace, precision {prec}, M={M}; cycles until each event since the previous event of the same role"]
-        for k in sorted(summ):
-            c, n = summ[k]
-            out.append(f"  {k:32s} total {c:9d}  n {n:4d}  avg {c / max(n, 1):9.1f}")
-        span = ev[-1][0] - t0
-        out.append(f"  traced span {span} cycles")
-        open(f"gpurun_out/trace_chain_mlp_{prec}.txt", "w").write("\n".join(out + [""] + lines) + "\n")
-        print("\n".join(out))
+        run_traced("chain_mlp_bf16x3", TAGS_MLP, lambda: ops.chain_mlp(x, None, None, 1e-6, blob, b1, b2, "bf16x3"))
+    if "attn" in which:
+        L, C, H = 197, 256, 8
+        lat = torch.randn(L, 2 * C, generator=g).to(dev)
+        kb, vb = ops.attn_pack_fused(lat[:, :C], lat[:, C:], H)
+        qkv = torch.randn(M, 3 * C, generator=g).to(dev)
+        out = torch.empty(M, C, device=dev)
+        run_traced("chain_attn_bf16x3", TAGS_ATTN, lambda: ops.attn_fused(qkv, kb, vb, L, 32 ** -0.5, "bf16x3", out=out))
 
 
 if __name__ == "__main__":

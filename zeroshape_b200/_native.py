@@ -39,7 +39,7 @@ SIGNATURES = {
     "zs_gemm_tc_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_attn_scores_tc": (c_int, [P, c_int, P, c_int, c_int, c_float, P, P, P, c_int, P]),
     "zs_attn_pv_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
-    "zs_chain_mlp_trace": (c_int, [P, c_int, c_int, c_float, P, P, P, c_int, P, P]),
+    "zs_debug_chain_trace": (c_int, [P]),
     "zs_chain_attn_fwd": (c_int, [P, c_int, c_int, P, P, c_int, c_float, P, c_int, P]),
     "zs_chain_mlp_blob_bytes": (c_size_t, []),
     "zs_chain_occ_blob_bytes": (c_size_t, []),

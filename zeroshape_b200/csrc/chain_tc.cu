@@ -27,7 +27,8 @@ constexpr int CT_OFF_W = 0;
 constexpr int CT_OFF_L = CT_OFF_W + CT_WSLOTS * CT_TILE_BYTES;          // 96 KB
 constexpr int CT_OFF_E = CT_OFF_L + CT_LSLOTS * 2 * CT_A_HALF;          // +64 KB
 constexpr int CT_OFF_BAR = CT_OFF_E + CT_ESLOTS * 2 * CT_A_HALF;        // +64 KB = 224 KB
-constexpr int CT_SMEM = CT_OFF_BAR + 256 + 1024 /*row scratch*/ + 1024 /*align slack*/;
+constexpr int CT_SMEM_USED = CT_OFF_BAR + 256 + 2048;   // barriers + 2 KB of per-kernel scratch (row partials / self scores)
+constexpr int CT_SMEM = 227 * 1024;                     // the whole opt-in window: 768 B of slack for a base that is not 1024-aligned
 
 struct ChainParams {
   float* x; int ldx;             // [M, 256] residual stream (MLP: in/out; OCC: in)
@@ -315,7 +316,7 @@ __device__ __forceinline__ void epi_to_ring(uint8_t* slot, int row, int hsel, co
 // ===============================================================================================================
 // x <- x + fc2(GELU(fc1(LN(x))))      blob order: for g in 0..3: fc1[g] (4 pairs), fc2[:, g] (4 pairs)
 __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   Bars B{smem_base + CT_OFF_BAR};
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
 // A chunks of ring L: 4 x LN(x) then 1 x [xyz, 0...]  (K order = [feat | xyz]; weights permuted to match at pack time)
 // blob order: l0: 5 pairs (feat 4, xyz 1); l1: 4; l2: 5 (inputs) + 4 (h); l3: 4; l4: 5+4; l5: 4; l6: 5+4; l7: 4   = 48 pairs
 __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   Bars B{smem_base + CT_OFF_BAR};
@@ -606,57 +607,155 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p)
 }
 
 // ===============================================================================================================
-// Point-to-latent attention of one image (model/shape/implicit.py:38-57), flash-style: per 128-point tile and head h
-//   S = Q_h K_lat_h^T (tcgen05, N=208, TMEM half 0) -> softmax numerators (row max / sum also cover the point's own
-//   key) -> ring E as split-bf16 A chunks -> O_h = P V_lat_h (tcgen05, N=32, TMEM half 1) -> (O_h + e_self v_p,h)/sum.
-// The probabilities never leave the SM.  ChainParams reuse: x = qkv [M,768] (q|k|v, ldx), blob = K tiles (8 heads x
-// [hi 32K | lo 32K], 208 valid rows, 32 valid K columns), points -> V blob (8 heads x 32 KB: 4 key-chunks x
-// [hi 4K | lo 4K], 32 rows = head dims), out = O [M,256], b8 = softmax scale, apply_sigmoid = number of latent keys.
+// Point-to-latent attention of one image (model/shape/implicit.py:38-57), flash-style.  Per 128-point tile the 8 heads
+// are processed as 4 PAIRS (2p, 2p+1); the two heads of a pair are owned by two independent groups of 4 epilogue
+// warps (one thread = one query row of one head, so the softmax needs no cross-thread exchange):
+//   loader   : q[:, 64p:64p+64] -> ring L as one split-bf16 A chunk (head 2p = K-steps 0,1; head 2p+1 = K-steps 2,3),
+//              the points' own scores q_h.k_h -> smem;
+//   MMA      : S_g = Q_h K_lat_h^T (N=208, own TMEM buffer per group) ; O_g = P_h V_lat_h (N=32) chunk by chunk;
+//   group g  : row max (pass 1 over TMEM) -> e_j = exp(scale (s_j - max)) -> its ring-E slot (split bf16) -> row sum;
+//              (O_g + e_self v_p,h) / sum -> transposed in smem -> coalesced store.
+// The probabilities never leave the SM.  Weight ring (4 x 32 KB) per pair: K pair tile hi, lo ([208 keys x 64] : the
+// two heads' 32 dims side by side), V_2p, V_2p+1 (each 4 key-chunks x [hi 4K | lo 4K], rows = head dims).
+// ChainParams reuse: x = qkv [M,768] (q|k|v, ldx), blob = K pair tiles (4 x [hi 32K | lo 32K]), points -> V blob
+// (8 heads x 32 KB), out = O [M,256], b8 = softmax scale, apply_sigmoid = number of latent keys (<= 208).
+constexpr int AT_WSLOTS = 4;
+constexpr int AT_OFF_L = AT_WSLOTS * CT_TILE_BYTES;          // 128 KB: the pair's q chunk (hi 16K | lo 16K)
+constexpr int AT_OFF_E = AT_OFF_L + 2 * CT_A_HALF;           // 160 KB: one 32 KB slot per group
+constexpr int AT_OFF_BAR = AT_OFF_E + 2 * 2 * CT_A_HALF;     // 224 KB
+constexpr int AT_OFF_SELF = AT_OFF_BAR + 256;                // [2 pair parities][2 heads][128 rows] fp32 = 2 KB
+static_assert(AT_OFF_BAR == CT_OFF_BAR && AT_OFF_SELF + 2048 <= CT_SMEM_USED, "attention smem layout");
+
+struct ABars {
+  uint32_t base;
+  __device__ uint32_t wfull(int i) const { return base + 8u * i; }
+  __device__ uint32_t wempty(int i) const { return base + 32u + 8u * i; }
+  __device__ uint32_t lfull() const { return base + 64u; }
+  __device__ uint32_t lempty() const { return base + 72u; }
+  __device__ uint32_t efull(int g) const { return base + 80u + 8u * g; }
+  __device__ uint32_t eempty(int g) const { return base + 96u + 8u * g; }
+  __device__ uint32_t sfull(int g) const { return base + 112u + 8u * g; }
+  __device__ uint32_t sempty(int g) const { return base + 128u + 8u * g; }
+  __device__ uint32_t ofull(int g) const { return base + 144u + 8u * g; }
+  __device__ uint32_t oempty(int g) const { return base + 160u + 8u * g; }
+  __device__ uint32_t tmem_slot() const { return base + 176u; }
+};
+
+// e = exp2(s * sl2 - mxs) of 2*NP scores (keys k0 ...), masked past n_keys; accumulates the row sum; writes the split-bf16
+// values as NP/4 16-byte chunks of the row (16-byte chunk index c16_0 ...) of a swizzled A chunk
+template <int NP>
+__device__ __forceinline__ void attn_exp_block(const uint32_t* rr, int k0, int n_keys, float sl2, float mxs, float2& sum2,
+                                               uint8_t* slot, int row, int c16_0, bool split) {
+  const bool full = k0 + 2 * NP <= n_keys;
+#pragma unroll
+  for (int cc = 0; cc < NP / 4; ++cc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = cc * 8 + 2 * j;
+      const float2 a = fma2(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), bc2(sl2), bc2(-mxs));
+      float2 v = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+      if (!full) { if (k0 + i >= n_keys) v.x = 0.f; if (k0 + i + 1 >= n_keys) v.y = 0.f; }
+      sum2 = add2(sum2, v);
+      split_bf16x2(v.x, v.y, hi[j], lo[j]);
+    }
+    const uint32_t off = swizzle128_offset(row, c16_0 + cc);
+    *reinterpret_cast<uint4*>(slot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ float attn_max_block(const uint32_t* rr, int k0, int n_keys, float mx) {
+  if (k0 + N <= n_keys) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) mx = fmaxf(mx, __uint_as_float(rr[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) if (k0 + j < n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
+  }
+  return mx;
+}
+
 __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  Bars B{smem_base + CT_OFF_BAR};
-  float* xch = reinterpret_cast<float*>(smem_gen + CT_OFF_BAR + 256);   // [2][128] exchange between column halves
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();   // dynamic smem base less aligned than budgeted
+  ABars B{smem_base + AT_OFF_BAR};
+  float* sself = reinterpret_cast<float*>(smem_gen + AT_OFF_SELF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = p.precision == 0;
-  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
   const int n_tiles = (p.M + 127) / 128;
   const int n_keys = p.apply_sigmoid;
   const uint8_t* vblob = reinterpret_cast<const uint8_t*>(p.points);
   constexpr uint32_t K_TILE_BYTES = 208 * 128;     // rows actually read by the N=208 MMA
 
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AT_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
+    mbar_init(B.lfull(), 128); mbar_init(B.lempty(), 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(B.efull(g), 128); mbar_init(B.eempty(g), 1);
+      mbar_init(B.sfull(g), 1); mbar_init(B.sempty(g), 128);
+      mbar_init(B.ofull(g), 1); mbar_init(B.oempty(g), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(B.tmem_slot(), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
+  // TMEM columns: S of group 0 [0,208), O of group 0 [208,240), S of group 1 [256,464), O of group 1 [464,496)
+
   if (warp < 4) {
-    // ---------------- loader: per head one chunk [q_h (32) | 0 (32)] ----------------
-    const int r = threadIdx.x;
-    Ring lr(CT_LSLOTS);
+    // ---------------- loader: per pair the q chunk (coalesced) and the points' own scores ----------------
+    const int sub = lane >> 4, q = lane & 15;
+    uint32_t lph = 0;
     float4 buf[16];
+    int tn = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m = t * 128 + r;
-      const bool ok = m < p.M;
-      const float* qrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
-      for (int h = 0; h < 8; ++h) {
+      const int m0 = t * 128 + warp * 32;
+      for (int pr = 0; pr < 4; ++pr) {
+        fetch_chunk_co(p.x, p.ldx, m0, p.M, pr * 64, lane, buf);
+        float dd[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) buf[c] = ok ? __ldg(reinterpret_cast<const float4*>(qrow + h * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 16; ++j) {
+          const int m = m0 + 2 * j + sub;
+          float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < p.M) k4 = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)m * p.ldx + 256 + pr * 64) + q);
+          float d = fmaf(buf[j].x, k4.x, fmaf(buf[j].y, k4.y, fmaf(buf[j].z, k4.z, buf[j].w * k4.w)));
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          dd[j] = d;
+        }
+        if (threadIdx.x == 0) trace_ev(p.trace, 1, tn, 10);
+        mbar_wait(B.lempty(), lph ^ 1);
+        if (threadIdx.x == 0) trace_ev(p.trace, 1, tn, 11);
+        // (the previous user of this sself parity, pair pr-2, is finished: S(pr-1) was issued after both groups released it)
+        if ((q & 7) == 0) {
+          float* ss = sself + (pr & 1) * 256 + (q >> 3) * 128 + warp * 32 + sub;
 #pragma unroll
-        for (int c = 8; c < 16; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
-        store_chunk_row(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, r, buf, split);
+          for (int j = 0; j < 16; ++j) ss[2 * j] = dd[j];
+        }
+        store_chunk_co(smem_gen + AT_OFF_L, warp, lane, buf, false, 0.f, 0.f, nullptr, nullptr, split);
         fence_proxy_async_smem();
-        mbar_arrive(B.lfull(lr.idx));
-        lr.advance();
+        mbar_arrive(B.lfull());
+        if (threadIdx.x == 0) trace_ev(p.trace, 1, tn, 12);
+        lph ^= 1;
       }
     }
   } else if (warp == 13) {
-    // ---------------- W loader: per head K hi, K lo, V pack ----------------
+    // ---------------- W loader: per pair K hi, K lo, V_2p, V_2p+1 ----------------
     if (lane == 0) {
-      Ring wr(CT_WSLOTS);
+      Ring wr(AT_WSLOTS);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int h = 0; h < 8; ++h) {
-          for (int j = 0; j < 3; ++j) {
+        for (int pr = 0; pr < 4; ++pr) {
+          for (int j = 0; j < 4; ++j) {
             if (j == 1 && !split) continue;
-            const uint8_t* src = j < 2 ? p.blob + (size_t)h * 2 * CT_TILE_BYTES + (size_t)j * CT_TILE_BYTES
-                                       : vblob + (size_t)h * CT_TILE_BYTES;
+            const uint8_t* src = j < 2 ? p.blob + (size_t)pr * 2 * CT_TILE_BYTES + (size_t)j * CT_TILE_BYTES
+                                       : vblob + (size_t)(2 * pr + (j - 2)) * CT_TILE_BYTES;
             const uint32_t bytes = j < 2 ? K_TILE_BYTES : (uint32_t)CT_TILE_BYTES;
             mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
             mbar_arrive_expect_tx(B.wfull(wr.idx), bytes);
@@ -669,27 +768,33 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
   } else if (warp == 12) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      Ring wr(CT_WSLOTS), lr(CT_LSLOTS), er(CT_ESLOTS);
-      uint32_t te_phase[2] = {0, 0};
+      Ring wr(AT_WSLOTS);
+      uint32_t lph = 0, se_ph[2] = {0, 0}, oe_ph[2] = {0, 0}, ef_ph[2] = {0, 0};
       const uint32_t idesc_s = umma_idesc_bf16(128, 208), idesc_o = umma_idesc_bf16(128, 32);
-      const uint32_t d_s = tmem_base, d_o = tmem_base + 256;
+      const uint32_t d_s[2] = {tmem_base, tmem_base + 256}, d_o[2] = {tmem_base + 208, tmem_base + 464};
+      const uint32_t a_addr = smem_base + AT_OFF_L;
+      const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+      int tn = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int h = 0; h < 8; ++h) {
-          // ---- S = Q_h K_h^T : K = 32 -> two K-steps of the chunk ----
-          mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
+        for (int pr = 0; pr < 4; ++pr) {
+          // ---- S_g = Q_h K_h^T : head g of the pair = K-steps 2g, 2g+1 of the q chunk and of the K pair tile ----
+          trace_ev(p.trace, 0, tn, 1);
+          mbar_wait(B.lfull(), lph); lph ^= 1;
           tc_fence_after();
-          mbar_wait(B.lfull(lr.idx), lr.phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF;
-          const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
           mbar_wait(B.wfull(wr.idx), wr.phase);
           tc_fence_after();
           {
             const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(B.sempty(g), se_ph[g] ^ 1); se_ph[g] ^= 1;
+              tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              umma_bf16(d_s, a_hi + 2 * k, w + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-              if (split) umma_bf16(d_s, a_lo + 2 * k, w + 2 * k, idesc_s, 1u);
+              for (int k = 0; k < 2; ++k) {
+                const int kk = 2 * g + k;
+                umma_bf16(d_s[g], a_hi + 2 * kk, w + 2 * kk, idesc_s, k > 0 ? 1u : 0u);
+                if (split) umma_bf16(d_s[g], a_lo + 2 * kk, w + 2 * kk, idesc_s, 1u);
+              }
+              if (!split) umma_commit(B.sfull(g));
             }
             umma_commit(B.wempty(wr.idx));
             wr.advance();
@@ -698,148 +803,152 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
             mbar_wait(B.wfull(wr.idx), wr.phase);
             tc_fence_after();
             const uint64_t w = umma_desc_sw128(smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES);
+            for (int g = 0; g < 2; ++g) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) umma_bf16(d_s, a_hi + 2 * k, w + 2 * k, idesc_s, 1u);
+              for (int k = 0; k < 2; ++k) umma_bf16(d_s[g], a_hi + 2 * (2 * g + k), w + 2 * (2 * g + k), idesc_s, 1u);
+              umma_commit(B.sfull(g));
+            }
             umma_commit(B.wempty(wr.idx));
             wr.advance();
           }
-          umma_commit(B.lempty(lr.idx));
-          lr.advance();
-          umma_commit(B.tfull(0));
-          // ---- O_h = P V_h : 4 key chunks from ring E, V tiles from one W slot ----
-          mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1;
-          tc_fence_after();
-          mbar_wait(B.wfull(wr.idx), wr.phase);
-          tc_fence_after();
-          const uint32_t v_addr = smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES;
-          for (int c = 0; c < 4; ++c) {
-            mbar_wait(B.efull(er.idx), er.phase);
-            tc_fence_after();
-            const uint32_t e_addr = smem_base + CT_OFF_E + er.idx * 2 * CT_A_HALF;
-            const uint64_t e_hi = umma_desc_sw128(e_addr), e_lo = umma_desc_sw128(e_addr + CT_A_HALF);
-            const uint64_t v_hi = umma_desc_sw128(v_addr + c * 8192), v_lo = umma_desc_sw128(v_addr + c * 8192 + 4096);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_o, e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
-              if (split) {
-                umma_bf16(d_o, e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
-                umma_bf16(d_o, e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
-              }
-            }
-            umma_commit(B.eempty(er.idx));
-            er.advance();
+          umma_commit(B.lempty());
+          trace_ev(p.trace, 0, tn, 2);
+          // ---- O_g = P_h V_h : key chunks from the groups' ring-E slots, the two heads interleaved ----
+          uint32_t v_addr[2]; int v_slot[2];
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            v_slot[g] = wr.idx; v_addr[g] = smem_base + CT_OFF_W + wr.idx * CT_TILE_BYTES;
+            wr.advance();
+            mbar_wait(B.oempty(g), oe_ph[g] ^ 1); oe_ph[g] ^= 1;
           }
-          umma_commit(B.wempty(wr.idx));
-          wr.advance();
-          umma_commit(B.tfull(1));
+          tc_fence_after();
+          for (int c = 0; c < 4; ++c) {
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(B.efull(g), ef_ph[g]); ef_ph[g] ^= 1;
+              tc_fence_after();
+              const uint32_t e_addr = smem_base + AT_OFF_E + g * 2 * CT_A_HALF;
+              const uint64_t e_hi = umma_desc_sw128(e_addr), e_lo = umma_desc_sw128(e_addr + CT_A_HALF);
+              const uint64_t v_hi = umma_desc_sw128(v_addr[g] + c * 8192), v_lo = umma_desc_sw128(v_addr[g] + c * 8192 + 4096);
+              const int nk = c == 3 ? 1 : 4;        // keys 192..207 are one K-step; 208.. do not exist
+              for (int k = 0; k < nk; ++k) {
+                umma_bf16(d_o[g], e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+                if (split) {
+                  umma_bf16(d_o[g], e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
+                  umma_bf16(d_o[g], e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
+                }
+              }
+              umma_commit(B.eempty(g));
+              if (c == 3) umma_commit(B.ofull(g));
+              trace_ev(p.trace, 0, tn, 3);
+            }
+          }
+          umma_commit(B.wempty(v_slot[0]));
+          umma_commit(B.wempty(v_slot[1]));
         }
       }
     }
   } else {
-    // ---------------- epilogue: softmax numerators -> ring E ; O normalisation -> global ----------------
-    const int e = warp - 4, q = e & 3, hsel = e >> 2;
-    const int row = q * 32 + lane;
-    Ring er(CT_ESLOTS);
-    uint32_t tf_phase[2] = {0, 0};
-    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    // ---------------- epilogue: group g = one head of the pair; one thread = one query row ----------------
+    const int e = warp - 4, wq = e & 3, g = e >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t s_tm = tmem_base + lane_off + (g ? 256u : 0u), o_tm = tmem_base + lane_off + (g ? 464u : 208u);
+    uint8_t* eslot = smem_gen + AT_OFF_E + g * 2 * CT_A_HALF;
+    uint8_t* wscr = eslot + wq * 4096;            // this warp's own 32 rows of the slot's hi half: [32][32] fp32 transpose scratch
+    uint32_t sf_ph = 0, of_ph = 0, ee_ph = 0;
     const float sl2 = p.b8 * 1.4426950408889634f;
+    const bool tr0 = (warp == 4 && lane == 0);
+    int tn = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m = t * 128 + row;
-      const bool ok = m < p.M;
-      const float* qrow = p.x + (int64_t)(ok ? m : 0) * p.ldx;
-      for (int h = 0; h < 8; ++h) {
-        float s_self = 0.f;
-#pragma unroll
-        for (int d = 0; d < 32; d += 4) {
-          const float4 qq = __ldg(reinterpret_cast<const float4*>(qrow + h * 32 + d));
-          const float4 kk = __ldg(reinterpret_cast<const float4*>(qrow + 256 + h * 32 + d));
-          s_self = fmaf(qq.x, kk.x, s_self); s_self = fmaf(qq.y, kk.y, s_self);
-          s_self = fmaf(qq.z, kk.z, s_self); s_self = fmaf(qq.w, kk.w, s_self);
-        }
-        mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+      for (int pr = 0; pr < 4; ++pr) {
+        const int h = 2 * pr + g;
+        if (tr0) trace_ev(p.trace, 2, tn, 20);
+        mbar_wait(B.sfull(g), sf_ph); sf_ph ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 21);
         tc_fence_after();
-        // pass 1: row max over the latent keys (this thread: columns c*64 + hsel*32 .. +32, c = 0..3)
-        float mx = -INFINITY;
+        const float s_self = sself[(pr & 1) * 256 + g * 128 + row];
+        // pass 1: row max over the latent keys and the point's own key
+        float mx = s_self;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int b = 0; b < 6; ++b) {
           uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
+          tmem_ld_32x32(s_tm + b * 32, rr);
           tmem_ld_wait();
-          const int c0 = c * 64 + hsel * 32;
-          if (c0 + 32 <= n_keys) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rr[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (c0 + j < n_keys) mx = fmaxf(mx, __uint_as_float(rr[j]));
-          }
+          mx = attn_max_block<32>(rr, b * 32, n_keys, mx);
         }
-        xch[hsel * 128 + row] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(fmaxf(xch[row], xch[128 + row]), s_self);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        {
+          uint32_t rr[16];
+          tmem_ld_32x16(s_tm + 192, rr);
+          tmem_ld_wait();
+          mx = attn_max_block<16>(rr, 192, n_keys, mx);
+        }
         const float mxs = mx * sl2;
-        // pass 2: e_j = exp(scale (s_j - max)) -> ring E (split bf16), running sum
-        float sum = 0.f;
+        if (tr0) trace_ev(p.trace, 2, tn, 22);
+        // pass 2: e_j -> this group's ring-E slot, chunk by chunk (64 keys; the last chunk has 16)
+        float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + lane_off + c * 64 + hsel * 32, rr);
-          tmem_ld_wait();
-          const int c0 = c * 64 + hsel * 32;
-          float v[32];
-          if (c0 + 32 <= n_keys) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)); sum += v[j]; }
+          if (c < 3) {
+            uint32_t rr[32];
+            tmem_ld_32x32(s_tm + c * 64, rr);
+            tmem_ld_wait();
+            mbar_wait(B.eempty(g), ee_ph ^ 1);
+            attn_exp_block<16>(rr, c * 64, n_keys, sl2, mxs, sum2, eslot, row, 0, split);
+            tmem_ld_32x32(s_tm + c * 64 + 32, rr);
+            tmem_ld_wait();
+            attn_exp_block<16>(rr, c * 64 + 32, n_keys, sl2, mxs, sum2, eslot, row, 4, split);
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = (c0 + j < n_keys) ? fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs)) : 0.f; sum += v[j]; }
+            uint32_t rr[16];
+            tmem_ld_32x16(s_tm + 192, rr);
+            tmem_ld_wait();
+            mbar_wait(B.eempty(g), ee_ph ^ 1);
+            attn_exp_block<8>(rr, 192, n_keys, sl2, mxs, sum2, eslot, row, 0, split);
           }
-          mbar_wait(B.eempty(er.idx), er.phase ^ 1);
-          uint8_t* slot = smem_gen + CT_OFF_E + er.idx * 2 * CT_A_HALF;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 hi, lo;
-            split_bf16x2(v[cc * 8 + 0], v[cc * 8 + 1], hi.x, lo.x);
-            split_bf16x2(v[cc * 8 + 2], v[cc * 8 + 3], hi.y, lo.y);
-            split_bf16x2(v[cc * 8 + 4], v[cc * 8 + 5], hi.z, lo.z);
-            split_bf16x2(v[cc * 8 + 6], v[cc * 8 + 7], hi.w, lo.w);
-            const uint32_t off = swizzle128_offset(row, hsel * 4 + cc);
-            *reinterpret_cast<uint4*>(slot + off) = hi;
-            if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
-          }
+          ee_ph ^= 1;
           fence_proxy_async_smem();
-          mbar_arrive(B.efull(er.idx));
-          er.advance();
+          mbar_arrive(B.efull(g));
+          if (tr0) trace_ev(p.trace, 2, tn, 23);
         }
         tc_fence_before();
-        mbar_arrive(B.tempty(0));
-        xch[hsel * 128 + row] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(B.sempty(g));
         const float e_self = fast_ex2(fmaf(s_self, sl2, -mxs));
-        const float inv = 1.0f / (xch[row] + xch[128 + row] + e_self);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        // O_h: 32 accumulator columns, handled by the hsel == 0 thread of each row
-        mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
+        const float inv = 1.0f / ((sum2.x + sum2.y) + e_self);
+        const float ps = e_self * inv;
+        // O_h: 32 accumulator columns of this row -> normalise -> transpose inside the warp -> coalesced store
+        if (tr0) trace_ev(p.trace, 2, tn, 24);
+        mbar_wait(B.ofull(g), of_ph); of_ph ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 25);
         tc_fence_after();
-        if (hsel == 0) {
+        {
           uint32_t rr[32];
-          tmem_ld_32x32(tmem_base + 256 + lane_off, rr);
+          tmem_ld_32x32(o_tm, rr);
           tmem_ld_wait();
-          if (ok) {
-            const float ps = e_self * inv;
-            float* orow = p.out + (int64_t)m * 256 + h * 32;
+          tc_fence_before();
+          mbar_arrive(B.oempty(g));
 #pragma unroll
-            for (int d = 0; d < 32; d += 4) {
-              const float4 vv = __ldg(reinterpret_cast<const float4*>(qrow + 512 + h * 32 + d));
-              *reinterpret_cast<float4*>(orow + d) = make_float4(
-                  fmaf(__uint_as_float(rr[d + 0]), inv, ps * vv.x), fmaf(__uint_as_float(rr[d + 1]), inv, ps * vv.y),
-                  fmaf(__uint_as_float(rr[d + 2]), inv, ps * vv.z), fmaf(__uint_as_float(rr[d + 3]), inv, ps * vv.w));
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(rr[4 * j]) * inv, __uint_as_float(rr[4 * j + 1]) * inv,
+                            __uint_as_float(rr[4 * j + 2]) * inv, __uint_as_float(rr[4 * j + 3]) * inv);
+        }
+        __syncwarp();
+        {
+          const int q8 = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
+            const float psr = __shfl_sync(0xffffffffu, ps, rl);
+            const int mm = t * 128 + wq * 32 + rl;
+            const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+            if (mm < p.M) {
+              const float4 vv = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)mm * p.ldx + 512 + h * 32) + q8);
+              *(reinterpret_cast<float4*>(p.out + (int64_t)mm * 256 + h * 32) + q8) =
+                  make_float4(fmaf(psr, vv.x, a.x), fmaf(psr, vv.y, a.y), fmaf(psr, vv.z, a.z), fmaf(psr, vv.w, a.w));
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(B.tempty(1));
+        __syncwarp();
+        if (tr0) trace_ev(p.trace, 2, tn, 26);
       }
     }
   }
@@ -848,7 +957,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-static int chain_launch(void (*kern)(ChainParams), const ChainParams& p, cudaStream_t st, const char* name) {
+static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
+
+static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name) {
+  p.trace = g_chain_trace;
   ZS_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   int tiles = (p.M + 127) / 128;
   int grid = tiles < sm_count() ? tiles : sm_count();
@@ -876,15 +988,9 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
 }
 
-// debug variant of zs_chain_mlp_fwd: also records (clock64 << 8 | tag) events of CTA 0 into `trace` [3][512] uint64
-extern "C" int zs_chain_mlp_trace(float* x, int ldx, int M, float ln_eps, const void* blob, const float* b1, const float* b2,
-                                  int precision, unsigned long long* trace, void* stream) {
-  ZS_REQUIRE(x && blob && b1 && b2 && trace && M > 0, "zs_chain_mlp_trace: null pointer");
-  ChainParams p{};
-  p.x = x; p.ldx = ldx; p.M = M; p.ln_w = nullptr; p.ln_b = nullptr; p.ln_eps = ln_eps;
-  p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision; p.trace = trace;
-  return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_trace");
-}
+// debug: while `buf` (device, [3][512] uint64) is non-null every chained kernel records (clock64 << 8 | tag) events of the
+// MMA thread, loader thread 0 and epilogue warp 4 lane 0 of CTA 0 into it (tools/trace_chain.py).  Not thread-safe.
+extern "C" int zs_debug_chain_trace(unsigned long long* buf) { g_chain_trace = buf; return ZS_OK; }
 
 extern "C" int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
                                  float scale, float* O, int precision, void* stream) {

@@ -206,8 +206,7 @@ class Implicit(nn.Module):
                 a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
                 for b in range(B):
                     if (l, b) not in packs:
-                        kp, vp = ops.attn_pack_kv(k_lat[b], v_lat[b], self.num_heads)
-                        packs[(l, b)] = (kp, ops.attn_pack_v_fused(vp, self.num_heads))
+                        packs[(l, b)] = ops.attn_pack_fused(k_lat[b], v_lat[b], self.num_heads)
                     ops.attn_fused(qkv[b * P:(b + 1) * P], packs[(l, b)][0], packs[(l, b)][1], lat["L"],
                                    (C // self.num_heads) ** -0.5, self.precision, out=a[b * P:(b + 1) * P])
             elif chain and attn_out is None and self.attention == "tc":

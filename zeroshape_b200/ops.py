@@ -138,20 +138,30 @@ def attn_pack_kv(k_lat, v_lat, heads=8):
     return torch.cat([pack_generic(kp[h]) for h in range(heads)]), torch.cat([pack_generic(vp[h]) for h in range(heads)])
 
 
-def attn_pack_v_fused(vpacked, heads=8):
-    """Vpacked (8 heads x 4 chunks x [hi 32K | lo 32K], 32 valid rows) -> compact blob for zs_chain_attn_fwd:
-    8 heads x 4 chunks x [hi 4K | lo 4K] (one 32 KB weight-ring slot per head)."""
-    v = vpacked.view(heads, 4, 2, 32768)[:, :, :, :4096]
-    return v.contiguous().view(-1)
+def attn_pack_fused(k_lat, v_lat, heads=8):
+    """Per-image latent keys/values [L, C] -> (Kblob, Vblob) of zs_chain_attn_fwd.
+    Kblob: 4 head-pair tiles (keys along the rows, the two heads' 32 dims side by side), Vblob: 8 heads x 32 KB."""
+    L, C = k_lat.shape
+    hd = C // heads
+    assert hd == 32 and heads == 8 and L <= 208
+    kp = torch.zeros(256, C, device=k_lat.device, dtype=torch.float32)
+    kp[:L] = k_lat
+    kblob = torch.cat([pack_generic(kp[:, 64 * p:64 * p + 64]) for p in range(heads // 2)])
+    vp = torch.zeros(heads, hd, 208, device=v_lat.device, dtype=torch.float32)
+    vp[:, :, :L] = v_lat.reshape(L, heads, hd).permute(1, 2, 0)
+    vpacked = torch.cat([pack_generic(vp[h]) for h in range(heads)])
+    vblob = vpacked.view(heads, 4, 2, 32768)[:, :, :, :4096].contiguous().view(-1)
+    return kblob, vblob
 
 
-def attn_fused(qkv, kpacked, vfused, n_keys, scale, precision="bf16x3", out=None):
+def attn_fused(qkv, kblob, vblob, n_keys, scale, precision="bf16x3", out=None):
     """qkv [M,768] -> attention output [M,256]: scores, softmax and P.V in one tcgen05 kernel (one image)."""
     assert qkv.dim() == 2 and qkv.shape[1] == 768 and qkv.stride(1) == 1 and qkv.is_cuda and qkv.dtype == torch.float32
     M = qkv.shape[0]
     O = out if out is not None else torch.empty(M, 256, device=qkv.device, dtype=torch.float32)
     assert O.stride(0) == 256 and O.stride(1) == 1
-    check(lib.zs_chain_attn_fwd(_p(qkv), qkv.stride(0), M, _p(kpacked), _p(vfused), n_keys, scale, _p(O),
+    assert kblob.numel() == 4 * 65536 and vblob.numel() == 8 * 32768
+    check(lib.zs_chain_attn_fwd(_p(qkv), qkv.stride(0), M, _p(kblob), _p(vblob), n_keys, scale, _p(O),
                                 PRECISIONS[precision], _stream()), "zs_chain_attn_fwd")
     return O
 
