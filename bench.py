@@ -187,7 +187,11 @@ def run_ours(args, rank, world, dev):
         sampler = ClockSampler(dev.index)
         sampler.start()
         l0 = lib.zs_launch_count()
+        if args.profile_region:       # `ncu --profile-from-start off`: only the timed steps are captured
+            torch.cuda.profiler.start()
         ms = timed(lambda: hot_path(rgb_dev, mask_dev, True), args.steps)
+        if args.profile_region:
+            torch.cuda.profiler.stop()
         launches = lib.zs_launch_count() - l0
         clocks = sampler.stop()
         torch.cuda.synchronize()
@@ -196,9 +200,12 @@ def run_ours(args, rank, world, dev):
         def e2e_step():
             out_host.copy_(hot_path(rgb_host.to(dev, non_blocking=True), mask_host.to(dev, non_blocking=True), False),
                            non_blocking=True)
-        for _ in range(2):
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
+        if args.no_e2e:
+            ms_e2e = float("nan")
+        else:
+            for _ in range(2):
+                e2e_step()
+            ms_e2e = timed(e2e_step, args.steps)
 
     shapes_total = args.shapes * world * args.steps
     pts = n ** 3
@@ -320,6 +327,8 @@ def main():
     ap.add_argument("--attention", default=None, choices=["fused", "tc", "f32"])
     ap.add_argument("--cpu-slices", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

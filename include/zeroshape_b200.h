@@ -104,6 +104,11 @@ int zs_debug_chain_trace(unsigned long long* buf);
  *        l in {2,4,6}: [W_l[:,259:515] | W_l[:,256:259]]/sqrt2 then W_l[:,0:256]/sqrt2.
  * zs_chain_mlp_fwd:  x <- x + fc2(GELU(fc1(LayerNorm(x))))           (model/shape/implicit.py:94-108, timm Mlp)
  * zs_chain_occ_fwd:  out = MLPBlocks([xyz, LayerNorm(x)]) (+sigmoid)  (model/shape/implicit.py:275,168-184) */
+/* zs_chain_lin_fwd:  out[M, 256*n_tiles] = LN?(x)[M,256] W^T + bias (+ res)   (qkv / proj of ImplFuncAttention,
+ * model/shape/implicit.py:30,74; do_ln = the block's norm1 statistics computed in-kernel, affine folded into W / bias).
+ * `blob` = zs_gemm_tc_pack image of W[256*n_tiles, 256].  `res`/`out` may alias (in-place residual update). */
+int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float ln_eps, const void* blob, int n_tiles,
+                     const float* bias, const float* res, int ldres, float* out, int ldo, int precision, void* stream);
 size_t zs_chain_mlp_blob_bytes(void);
 size_t zs_chain_occ_blob_bytes(void);
 int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
@@ -120,6 +125,13 @@ int zs_conv2d_nhwc_f32(const float* x, int B, int H, int W, int Cin,
                        const float* w, const float* bias, const float* res, int res_mode,
                        float* y, int Cout, int KH, int KW, int stride, int pad_top, int pad_left,
                        int OH, int OW, int act, int pre_relu, void* stream);
+
+/* The same convolution on the tensor cores: gemm_tc_kernel with an im2col-on-the-fly A producer (the K-chunks of an
+ * output pixel are 256-byte runs of one input pixel when Cin % 64 == 0).  `Wpacked` = zs_gemm_tc_pack of the OHWI filter
+ * viewed as W[Cout, KH*KW*Cin].  Needs Cin % 4 == 0 (every conv of the path except the two RGB/XYZ stems). */
+int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, const void* Wpacked, const float* bias,
+                      const float* res, int res_mode, float* y, int Cout, int KH, int KW, int stride,
+                      int pad_top, int pad_left, int OH, int OW, int act, int pre_relu, int precision, void* stream);
 
 /* LayerNorm over the last dim (eps given).  Replaces nn.LayerNorm in timm Block / implicit.py:89,95,225 */
 int zs_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
@@ -170,6 +182,12 @@ int zs_point_attention_f32(const float* qkv_p, const float* k_lat, const float* 
 /* Dense query grid of utils/eval_3D.py:10-20 for x-slices [x0,x1): out [x1-x0, n, n, 3], n = N+1,
  * coordinates = linspace(rmin,rmax,n) exactly as torch.linspace computes them. */
 int zs_dense_grid_f32(float* out, int n, float rmin, float rmax, int x0, int x1, void* stream);
+
+/* debug: effective SM clock in MHz at this point of the stream (one-thread spin kernel, ~10 us). */
+int zs_debug_clock_mhz(float* out, void* stream);
+
+/* LinearProj3D (model/shape/implicit.py:128-131): out[M,C] = points[M,3] W[C,3]^T + bias.  Output-bandwidth bound. */
+int zs_point_proj_f32(const float* points, int64_t M, const float* W, const float* bias, float* out, int C, void* stream);
 
 /* concat-and-divide used by MLPBlocks skip layers (implicit.py:179-180): y[r,:] = [a[r,:Ca], b[r,:Cb]] / s */
 int zs_concat2_f32(const float* a, int lda, int Ca, const float* b, int ldb, int Cb, float s, float* y, int ldy,

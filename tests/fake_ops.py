@@ -32,7 +32,7 @@ def gemm(a, w, bias=None, res=None, res_mode=0, act=0, out=None):
     return y.contiguous()
 
 
-def linear(x, w, bias=None, act=0, res=None, res_mode=0):
+def linear(x, w, bias=None, act=0, res=None, res_mode=0, tc=None):
     return _epi(F.linear(x, w), bias, res, res_mode, act).contiguous()
 
 

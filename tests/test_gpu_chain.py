@@ -36,6 +36,33 @@ def test_chain_mlp_matches_fp64(cuda, M):
         assert err < tol * ref.abs().max().item(), (prec, err)
 
 
+@pytest.mark.parametrize("M", [1, 128, 1000, 40000])
+def test_chain_lin_matches_fp64(cuda, M):
+    """LN + qkv (3 n-tiles) and proj + in-place residual (1 n-tile) of zs_chain_lin_fwd; zs_point_proj_f32."""
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(M + 5)
+    x = torch.randn(M, 256, generator=g) * 1.5 + 0.3
+    w, b = torch.randn(768, 256, generator=g) / 16, torch.randn(768, generator=g) * 0.1
+    ref = F.linear(F.layer_norm(x.double(), (256,), None, None, 1e-6), w.double(), b.double())
+    blob = ops.pack_generic(w.to(cuda))
+    for prec, tol in (("bf16x3", 3e-5), ("bf16", 3e-2)):
+        out = ops.chain_lin(x.to(cuda), blob, b.to(cuda), 3, do_ln=True, ln_eps=1e-6, precision=prec)
+        assert (out.cpu().double() - ref).abs().max().item() < tol * ref.abs().max().item(), prec
+    # proj: no LN, residual read and written in place, row-strided input view
+    wp, bp = torch.randn(256, 256, generator=g) / 16, torch.randn(256, generator=g) * 0.1
+    a = torch.randn(M, 300, generator=g)
+    ref2 = x.double() + F.linear(a[:, 8:264].double(), wp.double(), bp.double())
+    xc = x.clone().to(cuda)
+    ops.chain_lin(a.to(cuda)[:, 8:264], ops.pack_generic(wp.to(cuda)), bp.to(cuda), 1, res=xc, out=xc)
+    assert (xc.cpu().double() - ref2).abs().max().item() < 3e-5 * ref2.abs().max().item()
+    # LinearProj3D
+    pts = torch.rand(M, 3, generator=g) * 3 - 1.5
+    w3, b3 = torch.randn(256, 3, generator=g), torch.randn(256, generator=g)
+    out = ops.point_proj(pts.to(cuda), w3.to(cuda), b3.to(cuda))
+    assert (out.cpu().double() - F.linear(pts.double(), w3.double(), b3.double())).abs().max().item() < 2e-6
+
+
 @pytest.mark.parametrize("P", [1, 130, 5000])
 def test_chain_occ_matches_oracle_mlp(cuda, P):
     _need_sm100()
@@ -53,7 +80,7 @@ def test_chain_occ_matches_oracle_mlp(cuda, P):
     with torch.no_grad():
         sdd = {k: v.double() for k, v in sd.items()}
         ref = _occupancy_mlp(pts.double(), _ln(x.double(), sdd, "norm"), sdd, "impl_mlp").squeeze(-1)
-    _, _, occ_blob, biases, w8, b8, _ = m._chain_blobs()
+    _, _, occ_blob, biases, w8, b8, _, _ = m._chain_blobs()
     out = ops.chain_occ(x.to(cuda), pts.to(cuda), None, None, m.norm.eps, occ_blob, biases, w8, b8)
     from parity import parity_rel
     assert parity_rel(out, ref) < 1e-3

@@ -98,3 +98,47 @@ def test_decoder_tc_engine_meets_parity_bar(cuda, precision, tol):
     band = (occ_ref - 0.5).abs() > 2.5e-4
     assert torch.equal((occ > 0.5)[band], (occ_ref > 0.5)[band])
     assert band.float().mean() > 0.99
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,pad", [
+    (1, 14, 14, 64, 256, 3, 1, (1, 1, 1, 1)),      # chunk == one filter tap
+    (2, 28, 28, 128, 128, 3, 2, (0, 1, 0, 1)),     # timm SAME padding of a stride-2 3x3 (asymmetric)
+    (1, 56, 56, 256, 64, 1, 1, (0, 0, 0, 0)),      # 1x1, Cout < one N tile
+    (2, 7, 7, 768, 768, 3, 1, (1, 1, 1, 1)),       # intrinsics head: M = 98 < 128, K = 6912
+    (1, 30, 30, 32, 1, 1, 1, (0, 0, 0, 0)),        # DPT head last layer: K = 32 (generic tap decode), Cout = 1
+    (1, 20, 20, 96, 40, 3, 1, (1, 1, 1, 1)),       # Cin % 64 != 0: chunks straddle taps
+    (1, 1, 1, 2048, 2048, 1, 1, (0, 0, 0, 0)),     # CoordEncRes global token (a [B,C] vector as a 1x1 image)
+])
+def test_conv2d_tc_matches_fp64_conv(cuda, B, H, W, Cin, Cout, k, stride, pad):
+    """zs_conv2d_nhwc_tc (tcgen05 implicit GEMM, im2col in the A producer) vs an fp64 convolution."""
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout + k)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, k, k, Cin, generator=g) / (k * k * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    pt, pb, pl, pr = pad
+    xp = F.pad(x.permute(0, 3, 1, 2).double(), (pl, pr, pt, pb))
+    ref = F.conv2d(xp, w.permute(0, 3, 1, 2).double(), b.double(), stride=stride).permute(0, 2, 3, 1)
+    scale = ref.abs().max().item()
+    old = ops.ENCODER_ENGINE
+    try:
+        ops.ENCODER_ENGINE = "tc"
+        xd, wd, bd = x.to(cuda), w.to(cuda).contiguous(), b.to(cuda)
+        out = ops.conv2d_nhwc(xd, wd, bd, stride, pad)
+        assert out.shape == ref.shape
+        assert (out.cpu().double() - ref).abs().max().item() < 2e-5 * scale
+        # ReLU on load + residual + activation epilogue (ResidualConvUnit_custom / Bottleneck_Conv forms)
+        r = torch.randn(ref.shape, generator=g)
+        xpr = F.pad(F.relu(x).permute(0, 3, 1, 2).double(), (pl, pr, pt, pb))
+        ref2 = F.conv2d(xpr, w.permute(0, 3, 1, 2).double(), b.double(), stride=stride).permute(0, 2, 3, 1)
+        out = ops.conv2d_nhwc(xd, wd, bd, stride, pad, pre_relu=True, res=r.to(cuda))
+        assert (out.cpu().double() - (ref2 + r.double())).abs().max().item() < 3e-5 * max(scale, 1.0)
+        out = ops.conv2d_nhwc(xd, wd, bd, stride, pad, act=ops.ACT_RELU, res=r.to(cuda), res_mode=ops.RES_BEFORE_ACT)
+        assert (out.cpu().double() - F.relu(ref + r.double())).abs().max().item() < 3e-5 * max(scale, 1.0)
+        # and it agrees with the FFMA kernel it replaces
+        ops.ENCODER_ENGINE = "f32"
+        out32 = ops.conv2d_nhwc(xd, wd, bd, stride, pad)
+        assert (out32.cpu().double() - ref).abs().max().item() < 2e-5 * scale
+    finally:
+        ops.ENCODER_ENGINE = old

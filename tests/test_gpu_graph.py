@@ -85,11 +85,19 @@ def test_graph_forward_matches_oracle_batch(cuda):
     with torch.no_grad():
         ref = BB.graph_shape_encode(sd, rgb, mask)
     var = EasyDict(idx=torch.arange(2), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), pose_gt=False)
-    var, loss = graph.forward(make_opt(cuda), var, training=False, get_loss=True)
-    assert _rel(var.depth_pred, ref["depth_pred"]) < 1e-4
-    assert _rel(var.seen_points, ref["seen_points"]) < 1e-4
-    assert _rel(var.latent_depth, ref["latent_depth"]) < 1e-4
-    assert torch.equal(var.validity_mask.cpu(), ref["validity_mask"])
+    from zeroshape_b200 import ops
+    # bit-faithful FFMA encoder: fp32-grade agreement; tensor-core (bf16x3) encoder: the north-star 1e-3 bar
+    for engine, tol in (("f32", 1e-4), ("auto", 1e-3)):
+        ops.ENCODER_ENGINE = engine
+        try:
+            var = EasyDict(idx=torch.arange(2), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), pose_gt=False)
+            var, loss = graph.forward(make_opt(cuda), var, training=False, get_loss=True)
+        finally:
+            ops.ENCODER_ENGINE = "auto"
+        errs = (_rel(var.depth_pred, ref["depth_pred"]), _rel(var.seen_points, ref["seen_points"]), _rel(var.latent_depth, ref["latent_depth"]))
+        print("encoder engine", engine, "depth / seen_points / latent rel err", errs)
+        assert max(errs) < tol, (engine, errs)
+        assert torch.equal(var.validity_mask.cpu(), ref["validity_mask"])
     # image -> occupancy grid, default (tensor-core) engine: identical thresholded voxels outside the band
     n = 17
     occ = graph.impl_network.grid_occupancy(var.latent_depth, n, -1.5, 1.5).cpu()
@@ -113,6 +121,6 @@ def test_depth_graph_and_guards(cuda):
     var = dg.forward(opt, var, training=False, get_loss=False)
     with torch.no_grad():
         d_ref, _ = BB.dpt_depth_forward(sd, rgb, "dpt_depth.")
-    assert _rel(var.depth_pred, d_ref) < 1e-4 and var.intr_pred.shape == (1, 3, 3)
+    assert _rel(var.depth_pred, d_ref) < 1e-3 and var.intr_pred.shape == (1, 3, 3)
     with pytest.raises(NotImplementedError):
         dg.forward(opt, var, training=True)

@@ -1,0 +1,59 @@
+"""Per-op device times (CUDA events, warm) and SM-clock probes of one decoder pass on a real B200.
+    python tools/diag_decoder.py [points]      -> gpurun_out/diag_decoder.txt
+Not a test.  Shows (a) where a pass of `points` query points spends its time, (b) the effective SM clock right after
+every kernel (power-cap droop), (c) old (layernorm + gemm_tc) vs fused (chain_lin) qkv / proj."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from zeroshape_b200 import ops  # noqa: E402
+from zeroshape_b200.model.shape.implicit import Implicit  # noqa: E402
+
+dev = torch.device("cuda:0")
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 15 * 129 * 129
+lines = []
+
+
+def log(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True)
+    lines.append(s)
+
+
+torch.manual_seed(0)
+net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+               pos_perlayer=False).to(dev).eval()
+lat_in = torch.randn(1, 197, 256, device=dev)
+pts = (torch.rand(1, P, 3, device=dev) * 3 - 1.5).contiguous()
+FLOP = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
+        "chain_occ": 2 * 724224, "gemm_tc": 0, "point_proj": 2 * 768}
+with torch.no_grad():
+    lat = net.prepare_latents(lat_in)
+    for fused in (True, False, True):
+        net.lin_fused = fused
+        for _ in range(3):
+            net._points_chain(lat, pts, tc=True, sigmoid=True)
+        torch.cuda.synchronize()
+        reps = 5
+        with ops.OpTimer(clock_probe=False) as t:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                net._points_chain(lat, pts, tc=True, sigmoid=True)
+            e1.record()
+        summ = t.summary()
+        total = e0.elapsed_time(e1) / reps
+        log(f"\n== lin_fused={fused}: {P} points, pass {total:.3f} ms ({P / total / 1e3:.1f} Mpts/s; x{2146689 / P:.2f} = {total * 2146689 / P:.1f} ms per 129^3 shape)")
+        for k, (c, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+            per = ms / c
+            tf = FLOP.get(k, 0) * P / per / 1e9 if per > 0 else 0
+            log(f"   {k:18s} x{c // reps}  {per * 1e3:8.1f} us/launch  {ms / reps:7.3f} ms/pass  {100 * ms / reps / total:5.1f}%   {tf:7.1f} TFLOP/s algorithmic ({3 * tf:.0f} executed bf16x3)")
+        with ops.OpTimer(clock_probe=True) as t:
+            for _ in range(3):
+                net._points_chain(lat, pts, tc=True, sigmoid=True)
+        tr = t.clock_trace()
+        log("   SM MHz after each kernel (3rd pass):", ", ".join(f"{n}:{v:.0f}" for n, v in tr[-len(tr) // 3:]))
+os.makedirs("gpurun_out", exist_ok=True)
+open("gpurun_out/diag_decoder.txt", "w").write("\n".join(lines) + "\n")

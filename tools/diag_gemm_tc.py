@@ -111,7 +111,7 @@ try:
     from zeroshape_b200.model.shape.implicit import Implicit
     net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
                    pos_perlayer=False).to(dev).eval()
-    _, _, occ_blob, biases, w8, b8, _ = net._chain_blobs()
+    _, _, occ_blob, biases, w8, b8, _, _ = net._chain_blobs()
     pts = torch.rand(M, 3, device=dev)
     for prec in ("bf16x3", "bf16"):
         for _ in range(2):

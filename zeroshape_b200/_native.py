@@ -41,12 +41,17 @@ SIGNATURES = {
     "zs_attn_pv_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "zs_debug_chain_trace": (c_int, [P]),
     "zs_chain_attn_fwd": (c_int, [P, c_int, c_int, P, P, c_int, c_float, P, c_int, P]),
+    "zs_debug_clock_mhz": (c_int, [P, P]),
+    "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
+    "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),
     "zs_chain_mlp_blob_bytes": (c_size_t, []),
     "zs_chain_occ_blob_bytes": (c_size_t, []),
     "zs_chain_mlp_fwd": (c_int, [P, c_int, c_int, P, P, c_float, P, P, P, c_int, P]),
     "zs_chain_occ_fwd": (c_int, [P, c_int, P, c_int, P, P, c_float, P, P, P, c_float, P, c_int, c_int, P]),
     "zs_conv2d_nhwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_conv2d_nhwc_tc": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_layernorm_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_float, P]),
     "zs_groupnorm_nhwc_f32": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "zs_channel_affine_f32": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P]),

@@ -43,6 +43,8 @@ struct ChainParams {
   int apply_sigmoid;
   int precision;
   unsigned long long* trace;     // debug: per-role (tag, clock64) events of CTA 0 (nullptr in production)
+  // chain_lin_kernel: out[M, 256*n_tiles] = LN?(x) W^T + bias (+ res)
+  const float* res; int ldres; int ldo; int n_tiles; int do_ln;
 };
 
 struct Bars {
@@ -459,6 +461,121 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
       }
       tc_fence_before();
       mbar_arrive(B.tempty(1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ===============================================================================================================
+// out[M, 256*NT] = LN?(x)[M,256] . W[256*NT, 256]^T + bias (+ res)      (qkv and proj of ImplFuncAttention,
+// model/shape/implicit.py:30,74 with norm1 of ImplFuncBlock :105 folded in: the LayerNorm statistics are computed by
+// the loader warps, its affine is folded into W / bias at pack time).
+// Same dataflow as chain_mlp_kernel without the second GEMM: coalesced LN loader -> ring L, weights through the TMA
+// ring (blob = zs_gemm_tc_pack image of W: [n_tile][k_chunk][hi | lo]), accumulators ping-pong between the TMEM halves,
+// and the epilogue transposes each 32x32 accumulator block inside its warp (4 KB of the idle ring E per warp) so that
+// bias / residual / store run on whole 128-byte row segments.
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_lin_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  Bars B{smem_base + CT_OFF_BAR};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
+  const int n_tiles = (p.M + 127) / 128;
+  const int NT = p.n_tiles;
+
+  if (warp < 4) {
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 32;
+      float sc = 1.f, sh = 0.f;
+      if (p.do_ln) warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk_co(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      const int n_chunks = 4 * NT;
+      for (int i = 0; i < n_chunks; ++i) {
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk_co(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, p.do_ln != 0, sc, sh, nullptr, nullptr, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (i + 1 < n_chunks) fetch_chunk_co(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream(B, smem_base, wr, p.blob, 4 * NT, split);
+    }
+  } else if (warp == 12) {
+    if (lane == 0) {
+      Ring wr(CT_WSLOTS), lr(CT_LSLOTS);
+      uint32_t te_phase[2] = {0, 0};
+      int acc = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int nt = 0; nt < NT; ++nt) {
+          mbar_wait(B.tempty(acc), te_phase[acc] ^ 1); te_phase[acc] ^= 1;
+          tc_fence_after();
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, tmem_base + acc * 256, kc == 0, split,
+                      B.lempty(lr.idx));
+            lr.advance();
+          }
+          umma_commit(B.tfull(acc));
+          acc ^= 1;
+        }
+      }
+    }
+  } else {
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* wscr = smem_gen + CT_OFF_E + e * 4096;       // this warp's [32 rows][32 cols] fp32 transpose scratch
+    const int sub = lane >> 3, q8 = lane & 7;
+    uint32_t tf_phase[2] = {0, 0};
+    int acc = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int nt = 0; nt < NT; ++nt) {
+        mbar_wait(B.tfull(acc), tf_phase[acc]); tf_phase[acc] ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = c * 64 + hsel * 32;
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + acc * 256 + lane_off + col0, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          __syncwarp();
+          const int n0 = nt * 256 + col0 + 4 * q8;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + sub;
+            const int mm = t * 128 + q * 32 + rl;
+            const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+            if (mm < p.M) {
+              float4 v = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
+              if (p.res) {
+                const float4 r4 = *reinterpret_cast<const float4*>(p.res + (int64_t)mm * p.ldres + n0);
+                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+              }
+              *reinterpret_cast<float4*>(p.out + (int64_t)mm * p.ldo + n0) = v;
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(acc));
+        acc ^= 1;
+      }
     }
   }
   tc_fence_before();
@@ -986,6 +1103,24 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   p.x = x; p.ldx = ldx; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
   return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
+}
+
+extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float ln_eps, const void* blob, int n_tiles,
+                                const float* bias, const float* res, int ldres, float* out, int ldo, int precision, void* stream) {
+  ZS_REQUIRE(x && blob && out && M >= 0, "zs_chain_lin_fwd: null pointer");
+  ZS_REQUIRE(n_tiles >= 1 && n_tiles <= 16, "zs_chain_lin_fwd: n_tiles must be in [1, 16]");
+  ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_lin_fwd: x must be 16B aligned, ldx%%4==0");
+  ZS_REQUIRE(ldo >= 256 * n_tiles && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "zs_chain_lin_fwd: out must be 16B aligned, ldo%%4==0");
+  ZS_REQUIRE(res == nullptr || ((ldres & 3) == 0 && ldres >= 256 * n_tiles && (reinterpret_cast<uintptr_t>(res) & 15) == 0),
+             "zs_chain_lin_fwd: res must be 16B aligned, ldres%%4==0");
+  ZS_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "zs_chain_lin_fwd: bias must be 16B aligned");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(blob) & 15) == 0 && (precision == 0 || precision == 1), "zs_chain_lin_fwd: bad blob/precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.do_ln = do_ln;
+  p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = bias; p.res = res; p.ldres = ldres; p.out = out; p.ldo = ldo;
+  p.n_tiles = n_tiles; p.precision = precision;
+  return chain_launch(chain_lin_kernel, p, as_stream(stream), "zs_chain_lin_fwd");
 }
 
 // debug: while `buf` (device, [3][512] uint64) is non-null every chained kernel records (clock64 << 8 | tag) events of the

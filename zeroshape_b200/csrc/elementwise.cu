@@ -350,3 +350,69 @@ extern "C" int zs_dense_grid_f32(float* out, int n, float rmin, float rmax, int 
   ZS_CUDA_CHECK_LAUNCH("zs_dense_grid_f32");
   return ZS_OK;
 }
+
+// out[m, c] = W[c,0]*p[m,0] + W[c,1]*p[m,1] + W[c,2]*p[m,2] + b[c]    (LinearProj3D, model/shape/implicit.py:128-131)
+// A K=3 "GEMM" is pure output bandwidth: one float4 of one row per thread, the thread's 4 weight rows in registers.
+namespace zs {
+__global__ void point_proj_kernel(const float* __restrict__ pts, int64_t M, const float* __restrict__ W, const float* __restrict__ b,
+                                  float* __restrict__ out, int C) {
+  const int c4 = C >> 2;                                   // float4 groups per row
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // a multiple of c4 (host guarantees) -> fixed column group per thread
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg = (int)(i0 % c4);
+  float w[4][3], bb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cg * 4 + j;
+    w[j][0] = __ldg(W + c * 3); w[j][1] = __ldg(W + c * 3 + 1); w[j][2] = __ldg(W + c * 3 + 2);
+    bb[j] = b ? __ldg(b + c) : 0.f;
+  }
+  const int64_t total = M * c4;
+  for (int64_t i = i0; i < total; i += stride) {
+    const int64_t m = i / c4;
+    const float x = __ldg(pts + m * 3), y = __ldg(pts + m * 3 + 1), z = __ldg(pts + m * 3 + 2);
+    float4 v;
+    // same association as the FFMA GEMM it replaces: ((b? no) k = 0,1,2 accumulated in order, bias added last
+    v.x = fmaf(w[0][2], z, fmaf(w[0][1], y, w[0][0] * x)) + bb[0];
+    v.y = fmaf(w[1][2], z, fmaf(w[1][1], y, w[1][0] * x)) + bb[1];
+    v.z = fmaf(w[2][2], z, fmaf(w[2][1], y, w[2][0] * x)) + bb[2];
+    v.w = fmaf(w[3][2], z, fmaf(w[3][1], y, w[3][0] * x)) + bb[3];
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+}  // namespace zs
+
+extern "C" int zs_point_proj_f32(const float* points, int64_t M, const float* W, const float* bias, float* out, int C, void* stream) {
+  ZS_REQUIRE(points && W && out && M >= 0, "zs_point_proj_f32: null pointer");
+  ZS_REQUIRE(C > 0 && (C & 3) == 0 && 256 % (C >> 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "zs_point_proj_f32: C/4 must divide 256 and out must be 16-byte aligned");
+  if (M == 0) return ZS_OK;
+  int64_t total = M * (C >> 2);
+  int64_t blocks = (total + 255) / 256;
+  int maxb = zs::sm_count() * 16;
+  int grid = (int)(blocks < maxb ? blocks : maxb);
+  zs::point_proj_kernel<<<grid, 256, 0, zs::as_stream(stream)>>>(points, M, W, bias, out, C);
+  ZS_CUDA_CHECK_LAUNCH("zs_point_proj_f32");
+  return ZS_OK;
+}
+
+// ---- debug: effective SM clock right now (cycles of clock64 per globaltimer microsecond over a ~20k-cycle spin) ----
+// Used by tools/diag_decoder.py and bench.py to see power-cap clock droop between the tensor-heavy kernels.
+namespace zs {
+__global__ void clock_probe_kernel(float* out) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  long long c1 = c0;
+  while (c1 - c0 < 20000) c1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  *out = t1 > t0 ? (float)((double)(c1 - c0) * 1e3 / (double)(t1 - t0)) : 0.f;   // MHz
+}
+}  // namespace zs
+
+extern "C" int zs_debug_clock_mhz(float* out, void* stream) {
+  ZS_REQUIRE(out, "zs_debug_clock_mhz: null pointer");
+  zs::clock_probe_kernel<<<1, 1, 0, zs::as_stream(stream)>>>(out);
+  ZS_CUDA_CHECK_LAUNCH("zs_debug_clock_mhz");
+  return ZS_OK;
+}

@@ -46,6 +46,8 @@ struct TcParams {
   int epi_mode;                // 0: bias / activation / residual;  1: attention softmax (tc_epilogue_softmax)
   const float* qkv; int ld_qkv; float* R; float* R_inv; float scale; int n_keys;
   const float* rowscale;       // optional [M, n_tiles]: accumulator row scale applied before bias/residual (P.V normalisation)
+  // implicit-GEMM convolution (AMODE 1): A row m = output pixel (b, oh, ow) of an NHWC image, K index = (kh, kw, ci)
+  int cB, cH, cW, cCin, cKH, cKW, cStride, cPadT, cPadL, cOH, cOW, cPreRelu;
 };
 
 template <int ACT>
@@ -222,6 +224,8 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
   }
 }
 
+// AMODE 0: A is a dense row-major fp32 matrix;  AMODE 1: A rows are gathered from an NHWC image (im2col on the fly)
+template <int AMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 1024-aligned operand tiles
@@ -265,11 +269,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // All 64 fp32 of a K-chunk are fetched into registers BEFORE waiting for the smem slot (also across
     // tile boundaries), so the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
     float4 buf[16];
+    int cb = 0, cih0 = 0, ciw0 = 0;          // AMODE 1: this thread's output pixel of the tile being fetched
+    bool crow_ok = false;
     auto fetch = [&](int t, int kc) {
       const int m = (t / p.n_tiles) * TC_BM + r;
+      const int k0 = kc * TC_BK;
+      if (AMODE == 1) {
+        if (kc == 0) {
+          crow_ok = m < p.M;
+          const int ow = m % p.cOW, tt = m / p.cOW;
+          cb = tt / p.cOH;
+          cih0 = (tt % p.cOH) * p.cStride - p.cPadT;
+          ciw0 = ow * p.cStride - p.cPadL;
+        }
+        if ((p.cCin & 63) == 0) {
+          // the whole 64-wide K-chunk lies inside one filter tap: 256 contiguous bytes of one input pixel (or zeros)
+          const int tap = k0 / p.cCin, ci0 = k0 - tap * p.cCin;
+          const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
+          const int ih = cih0 + kh, iw = ciw0 + kw;
+          const bool ok = crow_ok && k0 < p.K && (unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW;
+          const float4* src = reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cH + (ok ? ih : 0)) * p.cW + (ok ? iw : 0)) * p.cCin + ci0);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) buf[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          // generic (Cin % 4 == 0): decode the tap of every float4
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int k = k0 + c * 4;
+            const int tap = k / p.cCin, ci = k - tap * p.cCin;
+            const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
+            const int ih = cih0 + kh, iw = ciw0 + kw;
+            const bool ok = crow_ok && k < p.K && (unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW;
+            buf[c] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cH + ih) * p.cW + iw) * p.cCin + ci))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (p.cPreRelu) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            buf[c] = make_float4(fmaxf(buf[c].x, 0.f), fmaxf(buf[c].y, 0.f), fmaxf(buf[c].z, 0.f), fmaxf(buf[c].w, 0.f));
+        }
+        return;
+      }
       const bool row_ok = m < p.M;
       const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda + (t % p.n_tiles) * p.a_nt_off;
-      const int k0 = kc * TC_BK;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int k = k0 + c * 4;
@@ -457,10 +500,10 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
-  TcParams p;
+  TcParams p{};
   p.A = A; p.lda = lda; p.Wp = reinterpret_cast<const uint8_t*>(Wpacked); p.bias = bias;
   p.res = res; p.ldres = ldres; p.res_mode = res_mode; p.C = C; p.ldc = ldc;
   p.M = M; p.N = N; p.K = K; p.act = act; p.precision = precision;
@@ -469,8 +512,41 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.R_inv = nullptr; p.scale = 0.f; p.n_keys = 0; p.rowscale = nullptr;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_f32");
+  return ZS_OK;
+}
+
+// ---- implicit-GEMM convolution on the tensor cores (NHWC fp32 activations, OHWI filters packed as W[Cout, KH*KW*Cin]) ----
+extern "C" int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, const void* Wpacked, const float* bias,
+                                 const float* res, int res_mode, float* y, int Cout, int KH, int KW, int stride,
+                                 int pad_top, int pad_left, int OH, int OW, int act, int pre_relu, int precision, void* stream) {
+  ZS_REQUIRE(x && Wpacked && y, "zs_conv2d_nhwc_tc: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_tc: bad shape");
+  ZS_REQUIRE((Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_conv2d_nhwc_tc: needs Cin %% 4 == 0 and a 16-byte aligned image");
+  ZS_REQUIRE(res_mode == ZS_RES_NONE || res != nullptr, "zs_conv2d_nhwc_tc: residual requested but res==NULL");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_conv2d_nhwc_tc: precision must be 0 (bf16x3) or 1 (bf16)");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wpacked) & 15) == 0, "zs_conv2d_nhwc_tc: packed weights must be 16-byte aligned");
+  const int64_t M64 = (int64_t)B * OH * OW;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_tc: too many output pixels");
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  TcParams p{};
+  p.A = x; p.lda = 0; p.Wp = reinterpret_cast<const uint8_t*>(Wpacked); p.bias = bias;
+  p.res = res; p.ldres = Cout; p.res_mode = res_mode; p.C = y; p.ldc = Cout;
+  p.M = (int)M64; p.N = Cout; p.K = KH * KW * Cin; p.act = act; p.precision = precision;
+  p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.n_tiles = (p.N + TC_BN - 1) / TC_BN; p.k_chunks = (p.K + TC_BK - 1) / TC_BK;
+  p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
+  p.cOH = OH; p.cOW = OW; p.cPreRelu = pre_relu;
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_tc");
   return ZS_OK;
 }
 
@@ -488,7 +564,7 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -500,7 +576,7 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   p.qkv = qkv; p.ld_qkv = ld_qkv; p.R = R; p.R_inv = Rinv; p.scale = scale; p.n_keys = n_keys;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_attn_scores_tc");
   return ZS_OK;
 }
@@ -515,7 +591,7 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -527,7 +603,7 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   p.rowscale = Rinv;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_attn_pv_tc");
   return ZS_OK;
 }

@@ -90,6 +90,7 @@ class Implicit(nn.Module):
         self.engine = "auto"          # "auto" | "fused" | "tc" | "f32"
         self.precision = "bf16x3"     # tensor-core operand precision: "bf16x3" (parity) | "bf16" (fast)
         self.attention = "fused"      # point attention: "fused" (one flash-style tcgen05 kernel) | "tc" (two grouped tcgen05 launches) | "f32" (FFMA kernel)
+        self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         self.point_chunk = 1 << 18    # query points per pass of the per-layer / chained engines (bounds scratch memory)
         self._packed = None           # (version key, packed weight blob) for the fused engine
@@ -124,20 +125,21 @@ class Implicit(nn.Module):
     def prepare_latents(self, latent_depth):
         """Per-image latent-side work -> dict with K/V views of both blocks ([B,L,C], row stride 3C)."""
         C = self.n_channels
-        lat = ops.linear(latent_depth.float().contiguous(), self.latent_proj.weight, self.latent_proj.bias)
+        tc = self._use_tc()          # engine "f32" keeps the latent side on the bit-faithful FFMA kernels too
+        lat = ops.linear(latent_depth.float().contiguous(), self.latent_proj.weight, self.latent_proj.bias, tc=tc)
         kv = []
         nb = len(self.blocks_attn)
         for l, blk in enumerate(self.blocks_attn):
             if self.pos_perlayer or l == 0:
                 lat = ops.axpby(lat, 1.0, self.pos_embed.expand_as(lat).contiguous(), 1.0)
-            qkv = ops.linear(self._ln(lat, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias)
+            qkv = ops.linear(self._ln(lat, blk.norm1), blk.attn.qkv.weight, blk.attn.qkv.bias, tc=tc)
             kv.append((qkv[..., C:2 * C], qkv[..., 2 * C:]))
             if l == nb - 1:
                 break
             att = ops.mha(qkv, self.num_heads)
-            lat = ops.linear(att, blk.attn.proj.weight, blk.attn.proj.bias, res=lat)
-            h = ops.linear(self._ln(lat, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
-            lat = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=lat)
+            lat = ops.linear(att, blk.attn.proj.weight, blk.attn.proj.bias, res=lat, tc=tc)
+            h = ops.linear(self._ln(lat, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, tc=tc)
+            lat = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=lat, tc=tc)
         return {"kv": kv, "B": latent_depth.shape[0], "L": latent_depth.shape[1]}
 
     # -- per-layer engines: chain of kernels over a chunk of points --------------------------------
@@ -161,6 +163,13 @@ class Implicit(nn.Module):
             # The LayerNorm affine is folded into the consumer GEMM (W.(g*xhat + b) = (W*g).xhat + W.b), so the loader
             # warps only normalise: fc1' = fc1*gamma2, b1' = b1 + fc1.beta2; same for the `feat` columns of impl_mlp.
             mlp, mlp_b1 = [], []
+            lin_blobs = []    # per block: (qkv blob with norm1 folded, qkv bias', proj blob)
+            for blk in self.blocks_attn:
+                wq = blk.attn.qkv.weight.detach().double()
+                g1, be1 = blk.norm1.weight.detach().double(), blk.norm1.bias.detach().double()
+                lin_blobs.append((ops.pack_generic((wq * g1[None, :]).float()),
+                            (blk.attn.qkv.bias.detach().double() + wq @ be1).float().contiguous(),
+                            ops.pack_generic(blk.attn.proj.weight.detach().float())))
             for blk in self.blocks_attn:
                 w1, w2 = blk.mlp.fc1.weight.detach().double(), blk.mlp.fc2.weight.detach()
                 g2, be2 = blk.norm2.weight.detach().double(), blk.norm2.bias.detach().double()
@@ -185,7 +194,7 @@ class Implicit(nn.Module):
             occ = ops.pack_tiles([m.float() for m in mats])
             biases = torch.stack(biases).float().contiguous()
             w8 = self.impl_mlp.layers[8].weight.detach().reshape(-1).contiguous()
-            self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()), mlp_b1)
+            self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()), mlp_b1, lin_blobs)
         return self._chain_cache
 
     def _points_chain(self, lat, pts, attn_out=None, tc=False, sigmoid=False):
@@ -195,11 +204,16 @@ class Implicit(nn.Module):
         nb = len(self.blocks_attn)
         chain = tc and self.engine != "tc" and self._chain_ok()
         if chain:
-            _, mlp_blobs, occ_blob, occ_biases, w8, b8, mlp_b1 = self._chain_blobs()
-        x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
+            _, mlp_blobs, occ_blob, occ_biases, w8, b8, mlp_b1, lin_blobs = self._chain_blobs()
+            x = ops.point_proj(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)
+        else:
+            x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
             k_lat, v_lat = lat["kv"][l]
-            qkv = self._lin(self._ln(x, blk.norm1), blk.attn.qkv, tc)
+            if chain and self.lin_fused:    # LayerNorm statistics + qkv GEMM in one launch (norm1 affine folded into the packed weights)
+                qkv = ops.chain_lin(x, lin_blobs[l][0], lin_blobs[l][1], 3, do_ln=True, ln_eps=blk.norm1.eps, precision=self.precision)
+            else:
+                qkv = self._lin(self._ln(x, blk.norm1), blk.attn.qkv, tc)
             if chain and attn_out is None and self.attention == "fused":
                 # flash-style tensor-core attention: scores, softmax and P.V of a tile never leave the SM
                 packs = lat.setdefault("kv_fused", {})
@@ -222,10 +236,14 @@ class Implicit(nn.Module):
                 a = ops.point_attention(qkv.view(B, P, 3 * C), k_lat, v_lat, self.num_heads, attn=attn_out,
                                         attn_scale=1.0 / nb, attn_accumulate=(l > 0)).view(B * P, C)
             del qkv
-            x = self._lin(a, blk.attn.proj, tc, res=x)
             if chain:
+                if self.lin_fused:
+                    ops.chain_lin(a, lin_blobs[l][2], blk.attn.proj.bias, 1, res=x, out=x, precision=self.precision)   # x += proj(a)
+                else:
+                    x = self._lin(a, blk.attn.proj, tc, res=x)
                 ops.chain_mlp(x, None, None, blk.norm2.eps, mlp_blobs[l], mlp_b1[l], blk.mlp.fc2.bias, self.precision)
                 continue
+            x = self._lin(a, blk.attn.proj, tc, res=x)
             h = self._lin(self._ln(x, blk.norm2), blk.mlp.fc1, tc, act=ops.ACT_GELU)
             x = self._lin(h, blk.mlp.fc2, tc, res=x)
             del h

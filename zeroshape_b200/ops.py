@@ -198,6 +198,32 @@ def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
     return x
 
 
+def point_proj(points, w, bias):
+    """points [M,3] -> [M,C] = points @ w[C,3]^T + bias (LinearProj3D), one output-bandwidth-bound launch."""
+    _chk(points, "points"); _chk(w, "w"); _chk(bias, "bias")
+    assert points.dim() == 2 and points.shape[1] == 3 and w.shape[1] == 3
+    out = torch.empty(points.shape[0], w.shape[0], device=points.device, dtype=torch.float32)
+    check(lib.zs_point_proj_f32(_p(points), points.shape[0], _p(w), _p(bias), _p(out), w.shape[0], _stream()), "zs_point_proj_f32")
+    return out
+
+
+def chain_lin(x, blob, bias, n_tiles, do_ln=False, ln_eps=1e-6, res=None, out=None, precision="bf16x3"):
+    """out[M, 256*n_tiles] = LN?(x)[M,256] W^T + bias (+ res) on the chained tcgen05 kernel; `out` may alias `res`."""
+    assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+    assert blob.numel() == lib.zs_gemm_tc_packed_bytes(256 * n_tiles, 256)
+    _chk(bias, "bias")
+    M = x.shape[0]
+    if out is None:
+        out = torch.empty(M, 256 * n_tiles, device=x.device, dtype=torch.float32)
+    assert out.shape == (M, 256 * n_tiles) and out.stride(1) == 1
+    if res is not None:
+        assert res.shape == out.shape and res.stride(1) == 1 and res.dtype == torch.float32
+    check(lib.zs_chain_lin_fwd(_p(x), x.stride(0), M, int(do_ln), ln_eps, _p(blob), n_tiles, _p(bias), _p(res),
+                               res.stride(0) if res is not None else 0, _p(out), out.stride(0), PRECISIONS[precision], _stream()),
+          "zs_chain_lin_fwd")
+    return out
+
+
 def chain_occ(x, points, ln_w, ln_b, ln_eps, blob, biases, w8, b8, sigmoid=False, precision="bf16x3"):
     """logits[M] = MLPBlocks([points, LayerNorm(x)]) on the chained tcgen05 kernel."""
     assert x.dim() == 2 and x.shape[1] == 256 and x.stride(1) == 1 and points.shape == (x.shape[0], 3)
@@ -209,12 +235,41 @@ def chain_occ(x, points, ln_w, ln_b, ln_eps, blob, biases, w8, b8, sigmoid=False
     return out
 
 
-def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE):
-    """F.linear on the last dim of a contiguous tensor."""
+# Dense layers of the encoder side run on the tcgen05 kernel when the device has it ("auto"); "f32" forces the
+# bit-faithful FFMA kernels (parity pinning), "tc" requires the tensor-core path.
+ENCODER_ENGINE = "auto"
+ENCODER_PRECISION = "bf16x3"
+
+
+def _encoder_tc():
+    if ENCODER_ENGINE == "f32":
+        return False
+    ok = device_cc() == 100
+    if ENCODER_ENGINE == "tc" and not ok:
+        raise RuntimeError("ENCODER_ENGINE='tc' needs an sm_100 device")
+    return ok
+
+
+def _packed_of(w):
+    """tcgen05 operand image of a weight matrix / OHWI filter, cached on the tensor object per version."""
+    pw = getattr(w, "_zs_packed", None)
+    if pw is None:
+        w2 = w.detach()
+        w2 = w2.reshape(w2.shape[0], -1) if w2.dim() != 2 else w2
+        pw = PackedWeight(w2)                # re-packs itself when the (shared) version counter moves
+        w._zs_packed = pw
+    return pw
+
+
+def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE, tc=None):
+    """F.linear on the last dim of a contiguous tensor (`tc`: None = ENCODER_ENGINE policy, False = force FFMA)."""
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     r2 = res.reshape(-1, w.shape[0]) if res is not None else None
-    y = gemm(x2, w, bias, r2, res_mode, act)
+    if w.shape[0] >= 64 and w.shape[1] % 4 == 0 and w.shape[1] >= 64 and (tc if tc is not None else _encoder_tc()):
+        y = gemm_tc(x2, _packed_of(w), bias, r2, res_mode, act, precision=ENCODER_PRECISION)
+    else:
+        y = gemm(x2, w, bias, r2, res_mode, act)
     return y.reshape(*shp[:-1], w.shape[0])
 
 
@@ -233,6 +288,11 @@ def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=N
         res_mode = RES_NONE
     elif res_mode == RES_NONE:
         res_mode = RES_AFTER_ACT
+    if Cin % 4 == 0 and KH * KW * Cin >= 32 and _encoder_tc():
+        check(lib.zs_conv2d_nhwc_tc(_p(x), B, H, W, Cin, _p(_packed_of(w).get()), _p(bias), _p(res), res_mode, _p(y), Cout,
+                                    KH, KW, stride, pt, pl, OH, OW, act, int(pre_relu), PRECISIONS[ENCODER_PRECISION],
+                                    _stream()), "zs_conv2d_nhwc_tc")
+        return y
     check(lib.zs_conv2d_nhwc_f32(_p(x), B, H, W, Cin, _p(w), _p(bias), _p(res), res_mode, _p(y), Cout, KH, KW,
                                  stride, pt, pl, OH, OW, act, int(pre_relu), _stream()), "zs_conv2d_nhwc_f32")
     return y
@@ -453,3 +513,66 @@ def mesh_sample(verts, faces, num, vscale=1.0, voffset=0.0, seed=0):
     check(lib.zs_mesh_sample(_p(verts) if F else None, _p(faces) if F else None, verts.shape[0], F, vscale, voffset,
                              num, seed, _p(ws), _p(pts), _stream()), "zs_mesh_sample")
     return pts
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Per-op device timing (bench.py's per-kernel roofline table, tools/diag_decoder.py).  Not used on the product path.
+class OpTimer:
+    """Context manager: wraps the module-level op wrappers with CUDA event pairs on the current stream.
+
+        with ops.OpTimer() as t:  ...run the hot path...
+        t.summary() -> {op name: (launch groups, total ms)}   (synchronises)
+    """
+    NAMES = ("point_proj", "chain_lin", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_occ", "gemm_tc", "gemm",
+             "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "mha", "bilinear_nhwc", "dense_grid", "axpby", "marching_cubes",
+             "mesh_sample", "unproject_normalize", "concat2", "maxpool3x3s2_nhwc", "avgpool_nhwc", "chamfer_nn")
+
+    def __init__(self, clock_probe=False):
+        self.events = []
+        self.saved = {}
+        self.clock_probe = clock_probe
+        self.clocks = []
+
+    def _probe(self, name):
+        if self.clock_probe:
+            buf = torch.empty(1, device="cuda", dtype=torch.float32)
+            check(lib.zs_debug_clock_mhz(_p(buf), _stream()), "zs_debug_clock_mhz")
+            self.clocks.append((name, buf))
+
+    def __enter__(self):
+        g = globals()
+        for name in self.NAMES:
+            fn = g.get(name)
+            if fn is None:
+                continue
+            self.saved[name] = fn
+
+            def wrapped(*a, __fn=fn, __name=name, **k):
+                key = __name
+                if __name == "chain_lin":
+                    key = "chain_lin[qkv]" if (a[3] if len(a) > 3 else k.get("n_tiles")) == 3 else "chain_lin[proj]"
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = __fn(*a, **k)
+                e1.record()
+                self.events.append((key, e0, e1))
+                self._probe(key)
+                return r
+            g[name] = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        globals().update(self.saved)
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for key, e0, e1 in self.events:
+            c, ms = out.get(key, (0, 0.0))
+            out[key] = (c + 1, ms + e0.elapsed_time(e1))
+        return out
+
+    def clock_trace(self):
+        torch.cuda.synchronize()
+        return [(n, float(b.item())) for n, b in self.clocks]
