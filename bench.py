@@ -212,10 +212,29 @@ def run_ours(args, rank, world, dev):
     peaks = _peaks()
     dec_avg = sum(dec_ms) / len(dec_ms)
     achieved = pts * FLOP_PER_POINT / (dec_avg * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_tab = None, {}
     tp = os.path.join(ROOT, "profiles", "decoder_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(engine)
+        traffic_tab = json.load(open(tp))
+        if traffic_tab.get(engine) is not None:
+            traffic = traffic_tab[engine] * pts          # DRAM bytes of the whole launch group of one shape (ncu, per point x points)
+    # per-kernel table: one extra (untimed) shape with every op wrapper bracketed by CUDA events
+    kernels = []
+    with torch.no_grad():
+        with ops.OpTimer() as ot:
+            hot_path(rgb_dev[:1], mask_dev[:1], False)
+        summ = ot.summary()
+    per_point_flop = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
+                      "chain_occ": 2 * 724224, "point_proj": 2 * 768}
+    per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_occ": 1, "point_proj": 1}
+    tot_ms = sum(v[1] for v in summ.values())
+    for k, (cnt, ms_k) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+        row = {"op": k, "launches": cnt, "ms_per_shape": ms_k, "share": ms_k / tot_ms}
+        if k in per_point_flop:
+            tf = per_point_flop[k] * per_shape_launches[k] * pts / (ms_k * 1e-3) / 1e12
+            row.update({"algorithmic_tflops": tf, "frac_of_peak": tf / peaks["bf16_tflops"],
+                        "dram_bytes_per_point": traffic_tab.get("bytes_per_point", {}).get(k)})
+        kernels.append(row)
     line = {
         "metric": METRIC, "value": shapes_total / (ms * 1e-3), "unit": "shapes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -232,7 +251,11 @@ def run_ours(args, rank, world, dev):
         "roofline": {"bound": "tensor", "kernel": "implicit decoder grid pass (%s engine)" % engine,
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                      "traffic": traffic, "peak_source": peaks["source"], "avg_launch_ms": dec_avg,
-                     "algorithmic_flop_per_launch": pts * FLOP_PER_POINT},
+                     "algorithmic_flop_per_launch": pts * FLOP_PER_POINT,
+                     "note": "launch = the decoder launch group of one shape (9 x [point_proj, 2 x (LN+qkv, attention, proj, MLP), occupancy MLP]); "
+                             "bf16x3 executes 3x the algorithmic MMA work, so frac <= 1/3 in parity mode; `kernels` = every op of one "
+                             "shape timed live with CUDA events (encoder ops included), `traffic` = ncu DRAM bytes of the group",
+                     "kernels": kernels},
         "e2e": {"value": shapes_total / (ms_e2e * 1e-3), "unit": "shapes/s",
                 "h2d_bytes_per_step": (rgb_host.numel() + mask_host.numel()) * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": int(launches), "clocks": clocks,

@@ -12,7 +12,9 @@ from zeroshape_b200 import ops  # noqa: E402
 from zeroshape_b200.model.shape.implicit import Implicit  # noqa: E402
 
 dev = torch.device("cuda:0")
-P = int(sys.argv[1]) if len(sys.argv) > 1 else 15 * 129 * 129
+ONCE = "--once" in sys.argv          # ncu mode: 2 warm passes + 1 pass, nothing else
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+P = int(_args[0]) if _args else 15 * 129 * 129
 lines = []
 
 
@@ -31,6 +33,11 @@ FLOP = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused"
         "chain_occ": 2 * 724224, "gemm_tc": 0, "point_proj": 2 * 768}
 with torch.no_grad():
     lat = net.prepare_latents(lat_in)
+    if ONCE:
+        for _ in range(3):
+            net._points_chain(lat, pts, tc=True, sigmoid=True)
+        torch.cuda.synchronize()
+        sys.exit(0)
     for fused in (True, False, True):
         net.lin_fused = fused
         for _ in range(3):

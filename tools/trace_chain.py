@@ -82,6 +82,18 @@ def main():
     if "mlp" in which:
         x = x0.clone()
         run_traced("chain_mlp_bf16x3", TAGS_MLP, lambda: ops.chain_mlp(x, None, None, 1e-6, blob, b1, b2, "bf16x3"))
+    if "lin" in which:
+        wq = (torch.randn(768, 256, generator=g) / 16).to(dev)
+        bq = torch.zeros(768, device=dev)
+        qblob = ops.pack_generic(wq)
+        out = torch.empty(M, 768, device=dev)
+        tags = dict(TAGS_MLP)
+        tags[24] = "epi: 64-col group stored"
+        run_traced("chain_lin_qkv_bf16x3", tags, lambda: ops.chain_lin(x0, qblob, bq, 3, do_ln=True, out=out))
+        wp = (torch.randn(256, 256, generator=g) / 16).to(dev)
+        pblob = ops.pack_generic(wp)
+        xr = x0.clone()
+        run_traced("chain_lin_proj_bf16x3", tags, lambda: ops.chain_lin(x0, pblob, bq[:256], 1, res=xr, out=xr))
     if "attn" in which:
         L, C, H = 197, 256, 8
         lat = torch.randn(L, 2 * C, generator=g).to(dev)

@@ -142,15 +142,16 @@ __device__ __forceinline__ float2 fast_softplus100_2(float2 x) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // common prologue: barriers + TMEM
-__device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen, uint32_t smem_base, int warp) {
+__device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen, uint32_t smem_base, int warp, int mma_warp = 12,
+                                                int loader_threads = 128) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < CT_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
-    for (int i = 0; i < CT_LSLOTS; ++i) { mbar_init(B.lfull(i), 128); mbar_init(B.lempty(i), 1); }
+    for (int i = 0; i < CT_LSLOTS; ++i) { mbar_init(B.lfull(i), loader_threads); mbar_init(B.lempty(i), 1); }
     for (int i = 0; i < CT_ESLOTS; ++i) { mbar_init(B.efull(i), 256); mbar_init(B.eempty(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(B.tfull(i), 1); mbar_init(B.tempty(i), 256); }
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc(B.tmem_slot(), 512);
+  if (warp == mma_warp) tmem_alloc(B.tmem_slot(), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,7 +188,7 @@ __device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Rin
     umma_commit(B.wempty(wr.idx));
     wr.advance();
   }
-  umma_commit(a_empty_bar);
+  if (a_empty_bar != 0u) umma_commit(a_empty_bar);
   if (tr) trace_ev(tr, 0, *tn, 6);
 }
 
@@ -226,29 +227,66 @@ __device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const floa
 // the columns, so every request is one or two fully used 256..1024-byte segments.
 // LayerNorm statistics of the warp's 32 rows (two-pass variance on register-held data); lane L receives
 // (sc, sh) = (rstd, -mean * rstd) of row m0 + L, or (0, 0) past M so that padded rows normalise to zero.
+__device__ __forceinline__ void ln_load4(const float* __restrict__ x, int ldx, int m0, int M, int lane, float4* aa, float4* bb) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int m = m0 + u;
+    const float4* p4 = reinterpret_cast<const float4*>(x + (int64_t)(m < M ? m : 0) * ldx);
+    aa[u] = __ldg(p4 + lane);
+    bb[u] = __ldg(p4 + 32 + lane);
+  }
+}
+__device__ __forceinline__ void ln_reduce4(const float4* a, const float4* b, int m0, int i0, int M, float eps, int lane, float& sc, float& sh) {
+  float mean[4], q[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) mean[u] = ((a[u].x + a[u].y) + (a[u].z + a[u].w)) + ((b[u].x + b[u].y) + (b[u].z + b[u].w));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) mean[u] += __shfl_xor_sync(0xffffffffu, mean[u], o);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    mean[u] *= (1.0f / 256.0f);
+    const float d0 = a[u].x - mean[u], d1 = a[u].y - mean[u], d2 = a[u].z - mean[u], d3 = a[u].w - mean[u];
+    const float d4 = b[u].x - mean[u], d5 = b[u].y - mean[u], d6 = b[u].z - mean[u], d7 = b[u].w - mean[u];
+    q[u] = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float rstd = rsqrtf(q[u] * (1.0f / 256.0f) + eps);
+    if (lane == i0 + u && m0 + i0 + u < M) { sc = rstd; sh = -mean[u] * rstd; }
+  }
+}
 __device__ __forceinline__ void warp_ln_stats(const float* __restrict__ x, int ldx, int m0, int M, float eps, int lane,
                                               float& sc, float& sh) {
   sc = 0.f; sh = 0.f;
+  // 4 rows per step in two register sets: the next step's 8 loads are in flight while the current rows are reduced
+  // (rolled loop: a fully unrolled version measured slower, the role code must stay small for the instruction cache)
+  float4 a0[4], b0[4], a1[4], b1[4];
+  ln_load4(x, ldx, m0, M, lane, a0, b0);
 #pragma unroll 1
-  for (int i0 = 0; i0 < 32; i0 += 4) {
-    float4 a[4], b[4];
+  for (int i0 = 0; i0 < 32; i0 += 8) {
+    ln_load4(x, ldx, m0 + i0 + 4, M, lane, a1, b1);
+    ln_reduce4(a0, b0, m0, i0, M, eps, lane, sc, sh);
+    if (i0 + 8 < 32) ln_load4(x, ldx, m0 + i0 + 8, M, lane, a0, b0);
+    ln_reduce4(a1, b1, m0, i0 + 4, M, eps, lane, sc, sh);
+  }
+}
+
+// L2 prefetch of 256 fp32 columns [col0, col0+256) of the warp's 32 rows m0..m0+31 (8 x 128-byte lines per row, one line per
+// lane per instruction).  The loaders issue it one tile ahead: with a single 32 KB chunk in flight per SM the HBM stream
+// is latency-bound (Little: 6.4 TB/s x ~1.5 us needs ~65 KB in flight per SM); afterwards every demand load is an L2 hit.
+__device__ __forceinline__ void prefetch_rows_l2(const float* __restrict__ x, int ldx, int m0, int M, int col0, int lane) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int m = m0 + i0 + u;
-      const float4* p4 = reinterpret_cast<const float4*>(x + (int64_t)(m < M ? m : 0) * ldx);
-      a[u] = __ldg(p4 + lane);
-      b[u] = __ldg(p4 + 32 + lane);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float s = ((a[u].x + a[u].y) + (a[u].z + a[u].w)) + ((b[u].x + b[u].y) + (b[u].z + b[u].w));
-      const float mean = warp_sum(s) * (1.0f / 256.0f);
-      const float d0 = a[u].x - mean, d1 = a[u].y - mean, d2 = a[u].z - mean, d3 = a[u].w - mean;
-      const float d4 = b[u].x - mean, d5 = b[u].y - mean, d6 = b[u].z - mean, d7 = b[u].w - mean;
-      const float q = ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + eps);
-      if (lane == i0 + u && m0 + i0 + u < M) { sc = rstd; sh = -mean * rstd; }
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + 4 * i + (lane >> 3);
+    if (m < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (int64_t)m * ldx + col0 + (lane & 7) * 32));
   }
 }
 
@@ -337,6 +375,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
       const int m0 = t * 128 + warp * 32;
       float sc, sh;
       if (r == 0) trace_ev(p.trace, 1, tn, 14);
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
       warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
       fetch_chunk_co(p.x, p.ldx, m0, p.M, 0, lane, buf);
       if (r == 0) trace_ev(p.trace, 1, tn, 15);
@@ -445,17 +484,22 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
               make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + c * 64) + q4);
+        // all 8 residual loads first (they alias the stores below, so the compiler would otherwise serialise
+        // load -> store -> load: 8 dependent L2 round trips per column group)
+        float4 xin[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = t * 128 + i * 16 + e * 2 + sub;
+          xin[i] = *(reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + c * 64) + q4);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 16 + e * 2 + sub;
           const int mm = t * 128 + rl;
-          if (mm < p.M) {
-            const float4 a = *reinterpret_cast<const float4*>(tr_buf + rl * 68 + 4 * q4);
-            float4* xp = reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + c * 64) + q4;
-            float4 xv = *xp;
-            xv.x += a.x + bv.x; xv.y += a.y + bv.y; xv.z += a.z + bv.z; xv.w += a.w + bv.w;
-            *xp = xv;
-          }
+          const float4 a = *reinterpret_cast<const float4*>(tr_buf + rl * 68 + 4 * q4);
+          float4 xv = xin[i];
+          xv.x += a.x + bv.x; xv.y += a.y + bv.y; xv.z += a.z + bv.z; xv.w += a.w + bv.w;
+          if (mm < p.M) *(reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + c * 64) + q4) = xv;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -468,6 +512,53 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// 16-row variants of the coalesced loader helpers (warp w owns tile rows 16w .. 16w+15): with 8 loader warps a chunk
+// conversion is split over two warps per scheduler (one warp converting a chunk alone is latency-bound at ~0.3 IPC)
+__device__ __forceinline__ void prefetch_rows16_l2(const float* __restrict__ x, int ldx, int m0, int M, int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + 4 * i + (lane >> 3);
+    if (m < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (int64_t)m * ldx + col0 + (lane & 7) * 32));
+  }
+}
+__device__ __forceinline__ void warp_ln_stats16(const float* __restrict__ x, int ldx, int m0, int M, float eps, int lane,
+                                                float& sc, float& sh) {
+  sc = 0.f; sh = 0.f;
+  float4 a0[4], b0[4];          // one register set: the 96-register budget of a 576-thread CTA has no room for two
+#pragma unroll 1
+  for (int i0 = 0; i0 < 16; i0 += 4) {
+    ln_load4(x, ldx, m0 + i0, M, lane, a0, b0);
+    ln_reduce4(a0, b0, m0, i0, M, eps, lane, sc, sh);
+  }
+}
+__device__ __forceinline__ void fetch_chunk16(const float* __restrict__ x, int ldx, int m0, int M, int col0, int lane, float4* buf) {
+  const int sub = lane >> 4, q = lane & 15;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int m = m0 + 2 * j + sub;
+    buf[j] = m < M ? __ldg(reinterpret_cast<const float4*>(x + (int64_t)m * ldx + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void store_chunk16(uint8_t* slot, int w, int lane, const float4* buf, bool normalise, float sc, float sh, bool split) {
+  const int sub = lane >> 4, q = lane & 15;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rl = 2 * j + sub;
+    float2 v0 = make_float2(buf[j].x, buf[j].y), v1 = make_float2(buf[j].z, buf[j].w);
+    if (normalise) {
+      const float s = __shfl_sync(0xffffffffu, sc, rl), h = __shfl_sync(0xffffffffu, sh, rl);
+      v0 = fma2(v0, bc2(s), bc2(h)); v1 = fma2(v1, bc2(s), bc2(h));
+    }
+    uint2 hi, lo;
+    split_bf16x2(v0.x, v0.y, hi.x, lo.x);
+    split_bf16x2(v1.x, v1.y, hi.y, lo.y);
+    const uint32_t off = swizzle128_offset(16 * w + rl, q >> 1) + ((q & 1) << 3);
+    *reinterpret_cast<uint2*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+
+
 // ===============================================================================================================
 // out[M, 256*NT] = LN?(x)[M,256] . W[256*NT, 256]^T + bias (+ res)      (qkv and proj of ImplFuncAttention,
 // model/shape/implicit.py:30,74 with norm1 of ImplFuncBlock :105 folded in: the LayerNorm statistics are computed by
@@ -476,54 +567,71 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp_kernel(ChainParams p)
 // ring (blob = zs_gemm_tc_pack image of W: [n_tile][k_chunk][hi | lo]), accumulators ping-pong between the TMEM halves,
 // and the epilogue transposes each 32x32 accumulator block inside its warp (4 KB of the idle ring E per warp) so that
 // bias / residual / store run on whole 128-byte row segments.
-__global__ void __launch_bounds__(CT_THREADS, 1) chain_lin_kernel(ChainParams p) {
+constexpr int LN_THREADS = 576;   // chain_lin_kernel warps: 0-7 loaders (16 rows each), 8-15 epilogue, 16 MMA, 17 W loader
+__global__ void __launch_bounds__(LN_THREADS, 1) chain_lin_kernel(ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   Bars B{smem_base + CT_OFF_BAR};
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = p.precision == 0;
-  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp);
+  const uint32_t tmem_base = chain_setup(B, smem_gen, smem_base, warp, 16, 256);
   const int n_tiles = (p.M + 127) / 128;
   const int NT = p.n_tiles;
 
-  if (warp < 4) {
+  if (warp < 8) {
     Ring lr(CT_LSLOTS);
-    float4 buf[16];
+    float4 buf[8];
+    int tn = 0;
+    const bool tr0 = threadIdx.x == 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int m0 = t * 128 + warp * 32;
+      const int m0 = t * 128 + warp * 16;
       float sc = 1.f, sh = 0.f;
-      if (p.do_ln) warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
-      fetch_chunk_co(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      if (tr0) trace_ev(p.trace, 1, tn, 14);
+      if (t + (int)gridDim.x < n_tiles) {
+        prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+        if (p.res)
+          for (int nt = 0; nt < NT; ++nt) prefetch_rows16_l2(p.res, p.ldres, m0 + (int)gridDim.x * 128, p.M, nt * 256, lane);
+      }
+      if (p.do_ln) warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      if (tr0) trace_ev(p.trace, 1, tn, 15);
       const int n_chunks = 4 * NT;
       for (int i = 0; i < n_chunks; ++i) {
+        if (tr0) trace_ev(p.trace, 1, tn, 10);
         mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
-        store_chunk_co(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, p.do_ln != 0, sc, sh, nullptr, nullptr, split);
+        if (tr0) trace_ev(p.trace, 1, tn, 11);
+        store_chunk16(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, p.do_ln != 0, sc, sh, split);
         fence_proxy_async_smem();
         mbar_arrive(B.lfull(lr.idx));
+        if (tr0) trace_ev(p.trace, 1, tn, 12);
         lr.advance();
-        if (i + 1 < n_chunks) fetch_chunk_co(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+        if (i + 1 < n_chunks) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+        if (tr0) trace_ev(p.trace, 1, tn, 13);
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 17) {
     if (lane == 0) {
       Ring wr(CT_WSLOTS);
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream(B, smem_base, wr, p.blob, 4 * NT, split);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     if (lane == 0) {
       Ring wr(CT_WSLOTS), lr(CT_LSLOTS);
       uint32_t te_phase[2] = {0, 0};
-      int acc = 0;
+      int acc = 0, tn = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int nt = 0; nt < NT; ++nt) {
+          trace_ev(p.trace, 0, tn, 7);
           mbar_wait(B.tempty(acc), te_phase[acc] ^ 1); te_phase[acc] ^= 1;
           tc_fence_after();
           for (int kc = 0; kc < 4; ++kc) {
+            trace_ev(p.trace, 0, tn, 1);
             mbar_wait(B.lfull(lr.idx), lr.phase);
+            trace_ev(p.trace, 0, tn, 2);
             tc_fence_after();
             mma_chunk(B, smem_base, wr, smem_base + CT_OFF_L + lr.idx * 2 * CT_A_HALF, tmem_base + acc * 256, kc == 0, split,
-                      B.lempty(lr.idx));
+                      B.lempty(lr.idx), p.trace, &tn);
             lr.advance();
           }
           umma_commit(B.tfull(acc));
@@ -532,15 +640,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_lin_kernel(ChainParams p)
       }
     }
   } else {
-    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int e = warp - 8, q = e & 3, hsel = e >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint8_t* wscr = smem_gen + CT_OFF_E + e * 4096;       // this warp's [32 rows][32 cols] fp32 transpose scratch
     const int sub = lane >> 3, q8 = lane & 7;
     uint32_t tf_phase[2] = {0, 0};
-    int acc = 0;
+    int acc = 0, tn = 0;
+    const bool tr0 = (warp == 8 && lane == 0);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       for (int nt = 0; nt < NT; ++nt) {
+        if (tr0) trace_ev(p.trace, 2, tn, 20);
         mbar_wait(B.tfull(acc), tf_phase[acc]); tf_phase[acc] ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 21);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -556,21 +667,29 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_lin_kernel(ChainParams p)
           const int n0 = nt * 256 + col0 + 4 * q8;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+          // residual loads batched 4 at a time: `res` may alias `out` (in-place update), which would otherwise serialise
+          // load -> store -> load; 8 at a time spills at the 96-register budget of a 576-thread CTA
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + sub;
-            const int mm = t * 128 + q * 32 + rl;
-            const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
-            if (mm < p.M) {
-              float4 v = make_float4(a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w);
-              if (p.res) {
-                const float4 r4 = *reinterpret_cast<const float4*>(p.res + (int64_t)mm * p.ldres + n0);
-                v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-              }
-              *reinterpret_cast<float4*>(p.out + (int64_t)mm * p.ldo + n0) = v;
+          for (int hb = 0; hb < 2; ++hb) {
+            float4 rin[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int mm = t * 128 + q * 32 + 4 * (4 * hb + i) + sub;
+              rin[i] = p.res ? *reinterpret_cast<const float4*>(p.res + (int64_t)(mm < p.M ? mm : 0) * p.ldres + n0)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 4 * (4 * hb + i) + sub;
+              const int mm = t * 128 + q * 32 + rl;
+              const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+              if (mm < p.M)
+                *reinterpret_cast<float4*>(p.out + (int64_t)mm * p.ldo + n0) =
+                    make_float4(a.x + bv.x + rin[i].x, a.y + bv.y + rin[i].y, a.z + bv.z + rin[i].z, a.w + bv.w + rin[i].w);
             }
           }
           __syncwarp();
+          if (tr0) trace_ev(p.trace, 2, tn, 24);
         }
         tc_fence_before();
         mbar_arrive(B.tempty(acc));
@@ -580,7 +699,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_lin_kernel(ChainParams p)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ===============================================================================================================
@@ -607,6 +726,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ_kernel(ChainParams p)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m0 = t * 128 + warp * 32;
       float sc, sh;
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
       warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
       for (int rep = 0; rep < 4; ++rep) {
         for (int kc = 0; kc < 5; ++kc) {
@@ -749,8 +869,9 @@ struct ABars {
   __device__ uint32_t wempty(int i) const { return base + 32u + 8u * i; }
   __device__ uint32_t lfull() const { return base + 64u; }
   __device__ uint32_t lempty() const { return base + 72u; }
-  __device__ uint32_t efull(int g) const { return base + 80u + 8u * g; }
-  __device__ uint32_t eempty(int g) const { return base + 96u + 8u * g; }
+  // ring-E slot of group g is handed over in two 32-key halves (K-steps {0,1} and {2,3}): h = 0, 1
+  __device__ uint32_t efull(int g, int h) const { return base + (h ? 184u : 80u) + 8u * g; }
+  __device__ uint32_t eempty(int g, int h) const { return base + (h ? 200u : 96u) + 8u * g; }
   __device__ uint32_t sfull(int g) const { return base + 112u + 8u * g; }
   __device__ uint32_t sempty(int g) const { return base + 128u + 8u * g; }
   __device__ uint32_t ofull(int g) const { return base + 144u + 8u * g; }
@@ -812,7 +933,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
     for (int i = 0; i < AT_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
     mbar_init(B.lfull(), 128); mbar_init(B.lempty(), 1);
     for (int g = 0; g < 2; ++g) {
-      mbar_init(B.efull(g), 128); mbar_init(B.eempty(g), 1);
+      for (int h = 0; h < 2; ++h) { mbar_init(B.efull(g, h), 128); mbar_init(B.eempty(g, h), 1); }
       mbar_init(B.sfull(g), 1); mbar_init(B.sempty(g), 128);
       mbar_init(B.ofull(g), 1); mbar_init(B.oempty(g), 128);
     }
@@ -834,6 +955,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m0 = t * 128 + warp * 32;
       for (int pr = 0; pr < 4; ++pr) {
+        {
+          // pull the NEXT pair's q / k / v column blocks (2 x 128-byte lines each) of this warp's 32 rows into L2, one
+          // pair (~10k cycles) ahead of their use by this loader (q, k) and by the epilogue (the points' own values v)
+          const int tn2 = pr == 3 ? t + (int)gridDim.x : t, pn = (pr + 1) & 3;
+          const int mrow = tn2 * 128 + warp * 32 + lane;
+          if (tn2 < n_tiles && mrow < p.M) {
+            const float* rowp = p.x + (int64_t)mrow * p.ldx + pn * 64;
+#pragma unroll
+            for (int l = 0; l < 6; ++l)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + (l >> 1) * 256 + (l & 1) * 32));
+          }
+        }
         fetch_chunk_co(p.x, p.ldx, m0, p.M, pr * 64, lane, buf);
         float dd[16];
 #pragma unroll
@@ -886,7 +1019,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       Ring wr(AT_WSLOTS);
-      uint32_t lph = 0, se_ph[2] = {0, 0}, oe_ph[2] = {0, 0}, ef_ph[2] = {0, 0};
+      uint32_t lph = 0, se_ph[2] = {0, 0}, oe_ph[2] = {0, 0}, ef_ph[2][2] = {{0, 0}, {0, 0}};
       const uint32_t idesc_s = umma_idesc_bf16(128, 208), idesc_o = umma_idesc_bf16(128, 32);
       const uint32_t d_s[2] = {tmem_base, tmem_base + 256}, d_o[2] = {tmem_base + 208, tmem_base + 464};
       const uint32_t a_addr = smem_base + AT_OFF_L;
@@ -940,23 +1073,26 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
           }
           tc_fence_after();
           for (int c = 0; c < 4; ++c) {
-            for (int g = 0; g < 2; ++g) {
-              mbar_wait(B.efull(g), ef_ph[g]); ef_ph[g] ^= 1;
-              tc_fence_after();
-              const uint32_t e_addr = smem_base + AT_OFF_E + g * 2 * CT_A_HALF;
-              const uint64_t e_hi = umma_desc_sw128(e_addr), e_lo = umma_desc_sw128(e_addr + CT_A_HALF);
-              const uint64_t v_hi = umma_desc_sw128(v_addr[g] + c * 8192), v_lo = umma_desc_sw128(v_addr[g] + c * 8192 + 4096);
-              const int nk = c == 3 ? 1 : 4;        // keys 192..207 are one K-step; 208.. do not exist
-              for (int k = 0; k < nk; ++k) {
-                umma_bf16(d_o[g], e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
-                if (split) {
-                  umma_bf16(d_o[g], e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
-                  umma_bf16(d_o[g], e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
+            const int nh = c == 3 ? 1 : 2;        // keys 192..207 are one K-step (half 0 only); 208.. do not exist
+            for (int hh = 0; hh < nh; ++hh) {
+              for (int g = 0; g < 2; ++g) {
+                mbar_wait(B.efull(g, hh), ef_ph[g][hh]); ef_ph[g][hh] ^= 1;
+                tc_fence_after();
+                const uint32_t e_addr = smem_base + AT_OFF_E + g * 2 * CT_A_HALF;
+                const uint64_t e_hi = umma_desc_sw128(e_addr), e_lo = umma_desc_sw128(e_addr + CT_A_HALF);
+                const uint64_t v_hi = umma_desc_sw128(v_addr[g] + c * 8192), v_lo = umma_desc_sw128(v_addr[g] + c * 8192 + 4096);
+                const int k0 = 2 * hh, k1 = c == 3 ? 1 : 2 * hh + 2;
+                for (int k = k0; k < k1; ++k) {
+                  umma_bf16(d_o[g], e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+                  if (split) {
+                    umma_bf16(d_o[g], e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
+                    umma_bf16(d_o[g], e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
+                  }
                 }
+                umma_commit(B.eempty(g, hh));
+                if (c == 3) umma_commit(B.ofull(g));
+                trace_ev(p.trace, 0, tn, 3);
               }
-              umma_commit(B.eempty(g));
-              if (c == 3) umma_commit(B.ofull(g));
-              trace_ev(p.trace, 0, tn, 3);
             }
           }
           umma_commit(B.wempty(v_slot[0]));
@@ -972,7 +1108,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
     const uint32_t s_tm = tmem_base + lane_off + (g ? 256u : 0u), o_tm = tmem_base + lane_off + (g ? 464u : 208u);
     uint8_t* eslot = smem_gen + AT_OFF_E + g * 2 * CT_A_HALF;
     uint8_t* wscr = eslot + wq * 4096;            // this warp's own 32 rows of the slot's hi half: [32][32] fp32 transpose scratch
-    uint32_t sf_ph = 0, of_ph = 0, ee_ph = 0;
+    uint32_t sf_ph = 0, of_ph = 0, ee_ph[2] = {0, 0};
     const float sl2 = p.b8 * 1.4426950408889634f;
     const bool tr0 = (warp == 4 && lane == 0);
     int tn = 0;
@@ -1009,21 +1145,25 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
             uint32_t rr[32];
             tmem_ld_32x32(s_tm + c * 64, rr);
             tmem_ld_wait();
-            mbar_wait(B.eempty(g), ee_ph ^ 1);
+            mbar_wait(B.eempty(g, 0), ee_ph[0] ^ 1); ee_ph[0] ^= 1;
             attn_exp_block<16>(rr, c * 64, n_keys, sl2, mxs, sum2, eslot, row, 0, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.efull(g, 0));
             tmem_ld_32x32(s_tm + c * 64 + 32, rr);
             tmem_ld_wait();
+            mbar_wait(B.eempty(g, 1), ee_ph[1] ^ 1); ee_ph[1] ^= 1;
             attn_exp_block<16>(rr, c * 64 + 32, n_keys, sl2, mxs, sum2, eslot, row, 4, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.efull(g, 1));
           } else {
             uint32_t rr[16];
             tmem_ld_32x16(s_tm + 192, rr);
             tmem_ld_wait();
-            mbar_wait(B.eempty(g), ee_ph ^ 1);
+            mbar_wait(B.eempty(g, 0), ee_ph[0] ^ 1); ee_ph[0] ^= 1;
             attn_exp_block<8>(rr, 192, n_keys, sl2, mxs, sum2, eslot, row, 0, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.efull(g, 0));
           }
-          ee_ph ^= 1;
-          fence_proxy_async_smem();
-          mbar_arrive(B.efull(g));
           if (tr0) trace_ev(p.trace, 2, tn, 23);
         }
         tc_fence_before();
@@ -1031,6 +1171,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
         const float e_self = fast_ex2(fmaf(s_self, sl2, -mxs));
         const float inv = 1.0f / ((sum2.x + sum2.y) + e_self);
         const float ps = e_self * inv;
+        // the points' own values v_p,h of the 8 (row, 4-column) pieces this lane stores below: issued together (L2 hits, the
+        // loader prefetched them a pair ago) so their latency overlaps the wait for O instead of serialising 8 round trips
+        const int q8 = lane & 7;
+        float4 vself[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = t * 128 + wq * 32 + 4 * i + (lane >> 3);
+          vself[i] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + 512 + h * 32) + q8);
+        }
         // O_h: 32 accumulator columns of this row -> normalise -> transpose inside the warp -> coalesced store
         if (tr0) trace_ev(p.trace, 2, tn, 24);
         mbar_wait(B.ofull(g), of_ph); of_ph ^= 1;
@@ -1049,20 +1198,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
                             __uint_as_float(rr[4 * j + 2]) * inv, __uint_as_float(rr[4 * j + 3]) * inv);
         }
         __syncwarp();
-        {
-          const int q8 = lane & 7;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + (lane >> 3);
-            const float psr = __shfl_sync(0xffffffffu, ps, rl);
-            const int mm = t * 128 + wq * 32 + rl;
-            const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
-            if (mm < p.M) {
-              const float4 vv = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)mm * p.ldx + 512 + h * 32) + q8);
-              *(reinterpret_cast<float4*>(p.out + (int64_t)mm * 256 + h * 32) + q8) =
-                  make_float4(fmaf(psr, vv.x, a.x), fmaf(psr, vv.y, a.y), fmaf(psr, vv.z, a.z), fmaf(psr, vv.w, a.w));
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + (lane >> 3);
+          const float psr = __shfl_sync(0xffffffffu, ps, rl);
+          const int mm = t * 128 + wq * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+          const float4 vv = vself[i];
+          if (mm < p.M)
+            *(reinterpret_cast<float4*>(p.out + (int64_t)mm * 256 + h * 32) + q8) =
+                make_float4(fmaf(psr, vv.x, a.x), fmaf(psr, vv.y, a.y), fmaf(psr, vv.z, a.z), fmaf(psr, vv.w, a.w));
         }
         __syncwarp();
         if (tr0) trace_ev(p.trace, 2, tn, 26);
@@ -1076,12 +1221,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
 
 static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
 
-static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name) {
+static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name, int threads = CT_THREADS) {
   p.trace = g_chain_trace;
   ZS_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
   int tiles = (p.M + 127) / 128;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, CT_THREADS, CT_SMEM, st>>>(p);
+  kern<<<grid, threads, CT_SMEM, st>>>(p);
   ZS_CUDA_CHECK_LAUNCH(name);
   return ZS_OK;
 }
@@ -1120,7 +1265,7 @@ extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float
   p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.do_ln = do_ln;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = bias; p.res = res; p.ldres = ldres; p.out = out; p.ldo = ldo;
   p.n_tiles = n_tiles; p.precision = precision;
-  return chain_launch(chain_lin_kernel, p, as_stream(stream), "zs_chain_lin_fwd");
+  return chain_launch(chain_lin_kernel, p, as_stream(stream), "zs_chain_lin_fwd", LN_THREADS);
 }
 
 // debug: while `buf` (device, [3][512] uint64) is non-null every chained kernel records (clock64 << 8 | tag) events of the
