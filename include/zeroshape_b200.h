@@ -183,6 +183,39 @@ int zs_point_attention_f32(const float* qkv_p, const float* k_lat, const float* 
  * coordinates = linspace(rmin,rmax,n) exactly as torch.linspace computes them. */
 int zs_dense_grid_f32(float* out, int n, float rmin, float rmax, int x0, int x1, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step of the implicit decoder (decoder slice): fp32 backward kernels.
+ * Replace torch autograd over model/shape/implicit.py for the call at model/compute_graph/graph_shape.py:185,
+ * utils/loss.py:18-28 (shape_loss) and torch.optim.AdamW (model/shape_engine.py:132, 276).
+ * ---------------------------------------------------------------------------------------------- */
+/* loss = mean_i w_i * BCEWithLogits(logits_i, sdf_i < 0), w_i = impt_weight where |sdf_i| < impt_thres else 1.
+ * `ws` = one double of scratch; `loss` = one float on the device. */
+int zs_bce_logits_fwd(const float* logits, const float* sdf, int64_t n, float impt_thres, float impt_weight,
+                      double* ws, float* loss, void* stream);
+/* dlogits_i = grad_scale * w_i * (sigmoid(logits_i) - y_i) / n */
+int zs_bce_logits_bwd(const float* logits, const float* sdf, int64_t n, float impt_thres, float impt_weight,
+                      float grad_scale, float* dlogits, void* stream);
+/* dx = dy * act'(z) for the pre-activation z (ZS_ACT_GELU exact-erf, ZS_ACT_SOFTPLUS100, ZS_ACT_RELU, ZS_ACT_NONE) */
+int zs_act_bwd_f32(const float* dy, const float* z, float* dx, int64_t n, int act, void* stream);
+/* out[n] (+)= sum_m A[m,n]  (bias gradients) */
+int zs_colsum_f32(const float* A, int lda, int64_t M, int N, float* out, int accumulate, void* stream);
+/* C[N,K] (+)= A[M,N]^T B[M,K]  (weight gradients dW = dY^T X) */
+int zs_gemm_tn_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                   int accumulate, void* stream);
+/* LayerNorm backward over 256 columns; dgamma/dbeta (optional, both or neither) are ACCUMULATED into. */
+int zs_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, float eps, float* dx, float* dgamma,
+                         float* dbeta, int64_t rows, int cols, void* stream);
+/* Backward of zs_point_attention_f32 (head dim 32): O = forward output, dO its gradient; writes dqkv_p [B,P,3C] (all of it)
+ * and the latent-side gradients dk_lat / dv_lat [B,L,C] (row stride ld_dlat). */
+int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, const float* O,
+                               const float* dO, float* dqkv_p, float* dk_lat, float* dv_lat, int ld_dlat, int B, int P,
+                               int L, int heads, int hd, float scale, void* stream);
+/* Backward of zs_mha_f32: dqkv [B,T,3C] from qkv and dO [B,T,C]. */
+int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* stream);
+/* torch.optim.AdamW step (decoupled weight decay, bias correction) on one flat tensor; `step` counts from 1. */
+int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* debug: effective SM clock in MHz at this point of the stream (one-thread spin kernel, ~10 us). */
 int zs_debug_clock_mhz(float* out, void* stream);
 

@@ -87,8 +87,9 @@ def test_grid_occupancy_matches_reference_slice_loop(cuda):
     assert torch.equal(ops.dense_grid(129, -1.5, 1.5, 0, 2, cuda).cpu(), E.dense_grid(129, -1.5, 1.5)[0, :2])
 
 
-def test_inference_only_guard(cuda):
+def test_query_point_gradients_are_refused(cuda):
+    """The training path differentiates w.r.t. parameters and latents; gradients w.r.t. the query points do not exist."""
     m = _module(implicit_init(0), cuda, "f32")
-    lat = torch.randn(1, 197, 256, device=cuda, requires_grad=True)
+    lat = torch.randn(1, 197, 256, device=cuda)
     with pytest.raises(NotImplementedError):
-        m(lat, None, torch.rand(1, 8, 3, device=cuda))
+        m(lat, None, torch.rand(1, 8, 3, device=cuda, requires_grad=True))

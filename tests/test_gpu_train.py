@@ -1,0 +1,172 @@
+"""GPU: training step of the implicit decoder (decoder slice).
+
+The hand-written backward (csrc/train.cu through zeroshape_b200/model/shape/implicit_train.py) is compared with torch
+autograd over the ORACLE restatement of the reference's Implicit.forward (oracle/implicit.py, pinned bit-equal to the
+reference module) on the same seeded weights / latents / points: every parameter gradient, the latent gradient, the BCE
+shape loss of utils/loss.py:18-28, and one AdamW step against torch.optim.AdamW."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.implicit import implicit_forward, implicit_init
+
+pytestmark = pytest.mark.gpu
+
+
+def _module(sd, cuda, drop_path=0.0):
+    from zeroshape_b200.model.shape.implicit import Implicit
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False, drop_path=drop_path)
+    m.load_state_dict(sd)
+    return m.to(cuda)
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _ref_shape_loss(logits, sdf, thres, weight):
+    y = (sdf < 0).float()
+    loss = F.binary_cross_entropy_with_logits(logits, y, reduction="none")
+    w = torch.ones_like(loss)
+    w[sdf.abs() < thres] = weight
+    return (loss * w).mean()
+
+
+@pytest.mark.parametrize("B,P", [(1, 130), (3, 700)])
+def test_decoder_gradients_match_oracle_autograd(cuda, B, P):
+    from zeroshape_b200.utils.loss import Loss
+    sd = implicit_init(seed=21)
+    g = torch.Generator().manual_seed(B * 100 + P)
+    lat = torch.randn(B, 197, 256, generator=g)
+    pts = torch.rand(B, P, 3, generator=g) * 2 - 1
+    sdf = (pts.norm(dim=-1) - 0.6) * (torch.rand(B, P, generator=g) * 0.1 + 0.95)
+    sdf[0, :5] = torch.tensor([0.004, -0.003, 0.009, -0.0099, 0.0])        # inside the importance band |sdf| < 0.01
+    thres, weight = 0.01, 3.0
+    # oracle: autograd over the functional restatement of the reference module
+    sd_ref = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in sd.items()}
+    lat_ref = lat.clone().requires_grad_(True)
+    logits_ref, _ = implicit_forward(sd_ref, lat_ref, pts)
+    loss_ref = _ref_shape_loss(logits_ref, sdf, thres, weight)
+    loss_ref.backward()
+    # ours
+    m = _module(sd, cuda).train()                 # drop_path = 0: deterministic
+    lat_d = lat.to(cuda).requires_grad_(True)
+    logits, attn = m(lat_d, None, pts.to(cuda))
+    assert attn is None and logits.requires_grad
+    lossfn = Loss({"training": {"shape_loss": {"impt_thres": thres, "impt_weight": weight}}})
+    loss = lossfn.shape_loss(logits, sdf.to(cuda))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 2e-6 * max(1.0, abs(loss_ref.item()))
+    assert (logits.detach().cpu() - logits_ref.detach()).abs().max().item() < 5e-5
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        if name == "pos_embed":
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        r = _rel(p.grad, sd_ref[name].grad)
+        if r > worst[1]:
+            worst = (name, r)
+        assert r < 2e-4, (name, r)
+    assert _rel(lat_d.grad, lat_ref.grad) < 2e-4
+    print("worst parameter-gradient relative error:", worst, " latent grad:", _rel(lat_d.grad, lat_ref.grad))
+
+
+def test_training_kernels_against_torch(cuda):
+    """Each backward kernel on its own (shapes that exercise tails and strides)."""
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    # dW = dY^T X, bias column sums
+    dy, x = torch.randn(1000, 70, generator=g), torch.randn(1000, 259, generator=g)
+    dw = ops.gemm_tn(dy.to(cuda), x.to(cuda))
+    assert _rel(dw, dy.double().T @ x.double()) < 1e-5
+    acc = torch.ones(70, 259, device=cuda)
+    ops.gemm_tn(dy.to(cuda), x.to(cuda), out=acc, accumulate=True)
+    assert _rel(acc, dy.double().T @ x.double() + 1) < 1e-5
+    assert _rel(ops.colsum(dy.to(cuda)), dy.double().sum(0)) < 1e-5
+    # activations
+    z = torch.randn(5000, generator=g) * 0.05
+    dyv = torch.randn(5000, generator=g)
+    for act, fn in ((ops.ACT_GELU, lambda t: F.gelu(t)), (ops.ACT_SOFTPLUS100, lambda t: F.softplus(t, beta=100)), (ops.ACT_RELU, F.relu)):
+        for scale in (1.0, 40.0):
+            zz = (z * scale).double().requires_grad_(True)
+            fn(zz).backward(dyv.double())
+            got = ops.act_bwd(dyv.to(cuda), (z * scale).to(cuda), act)
+            assert (got.cpu().double() - zz.grad).abs().max().item() < 2e-5, (act, scale)
+    # LayerNorm
+    x = (torch.randn(333, 256, generator=g) * 1.7 + 0.4)
+    gam, bet = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    dyl = torch.randn(333, 256, generator=g)
+    xr, gr, br = x.double().requires_grad_(True), gam.double().requires_grad_(True), bet.double().requires_grad_(True)
+    F.layer_norm(xr, (256,), gr, br, 1e-6).backward(dyl.double())
+    dg, db = torch.zeros(256, device=cuda), torch.zeros(256, device=cuda)
+    dx = ops.layernorm_bwd(dyl.to(cuda), x.to(cuda), gam.to(cuda), 1e-6, dg, db)
+    assert _rel(dx, xr.grad) < 1e-5 and _rel(dg, gr.grad) < 1e-5 and _rel(db, br.grad) < 1e-5
+    # token self-attention
+    qkv = torch.randn(2, 197, 768, generator=g) * 0.7
+    do = torch.randn(2, 197, 256, generator=g)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = qr.reshape(2, 197, 3, 8, 32).permute(2, 0, 3, 1, 4)
+    o = ((q @ k.transpose(-2, -1)) * 32 ** -0.5).softmax(-1) @ v
+    o.transpose(1, 2).reshape(2, 197, 256).backward(do.double())
+    assert _rel(ops.mha_bwd(qkv.to(cuda), do.to(cuda), 8), qr.grad) < 2e-5
+    # AdamW against torch.optim.AdamW (3 steps)
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    w0 = torch.randn(1000, generator=g)
+    pa, pb = torch.nn.Parameter(w0.clone().to(cuda)), torch.nn.Parameter(w0.clone())
+    oa = FusedAdamW([pa], lr=3e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    ob = torch.optim.AdamW([pb], lr=3e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    for i in range(3):
+        gr_ = torch.randn(1000, generator=g)
+        pa.grad, pb.grad = gr_.to(cuda), gr_.clone()
+        v0 = pa._version
+        oa.step(); ob.step()
+        assert pa._version > v0
+    assert (pa.detach().cpu() - pb.detach()).abs().max().item() < 1e-6
+
+
+def test_graph_training_step_reduces_the_shape_loss(cuda):
+    """Graph.forward(training=True) with a synthetic GT batch, frozen encoders: losses as in
+    graph_shape.py:194-202, backward into impl_network, FusedAdamW steps -> the BCE loss goes down."""
+    from zeroshape_b200.model.compute_graph.graph_shape import Graph
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    from zeroshape_b200.utils.util import EasyDict
+    from test_gpu_graph import make_opt, synthetic_image_and_mask
+    opt = make_opt(cuda)
+    opt.loss_weight = EasyDict(depth=None, intr=1, shape=1)
+    opt.training = EasyDict(shape_loss=EasyDict(impt_thres=0.01, impt_weight=1))
+    torch.manual_seed(0)
+    graph = Graph(opt).to(cuda)
+    B, N = 2, 1024
+    rgb, mask = synthetic_image_and_mask(B, 7)
+    g = torch.Generator().manual_seed(8)
+    depth = (1.5 + 0.3 * torch.rand(B, 1, 224, 224, generator=g)) * mask
+    intr = torch.tensor([[1.3875 * 224, 0, 112], [0, 1.3875 * 224, 112], [0, 0, 1.0]]).repeat(B, 1, 1)
+    pose = torch.cat([torch.eye(3), torch.tensor([[0.0], [0.0], [1.6]])], dim=1).repeat(B, 1, 1)
+    gt_pts = torch.rand(B, N, 3, generator=g) - 0.5
+    gt_sdf = gt_pts.norm(dim=-1) - 0.3 - 0.003
+
+    def batch():
+        return EasyDict(idx=torch.arange(B), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), depth_input_map=depth.to(cuda),
+                        intr=intr.to(cuda), pose_gt=pose.to(cuda), gt_sample_points=gt_pts.to(cuda), gt_sample_sdf=gt_sdf.to(cuda))
+    graph.train()
+    with pytest.raises(NotImplementedError):        # encoders not frozen: refuse instead of silently not training them
+        graph.forward(opt, batch(), training=True)
+    for mod in (graph.dpt_depth, graph.intr_head, graph.intr_proj, graph.coord_encoder):
+        for p in mod.parameters():
+            p.requires_grad_(False)
+        mod.eval()                                   # eval-mode BatchNorm (the inference kernels fold running statistics)
+    optim = FusedAdamW(graph.impl_network.parameters(), lr=3e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    losses = []
+    for it in range(6):
+        var, loss = graph.forward(opt, batch(), training=True)
+        assert var.pred_sample_occ.shape == (B, N) and var.gt_surf_points.shape == (B, 100, 3) and "intr" in loss
+        optim.zero_grad()
+        loss.shape.backward()
+        optim.step()
+        losses.append(loss.shape.item())
+    print("shape loss per step:", [round(v, 4) for v in losses])
+    assert 0.5 * (losses[-1] + losses[-2]) < losses[0] and all(np.isfinite(losses))   # DropPath(0.1) is active: compare a 2-step mean

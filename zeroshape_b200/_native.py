@@ -42,6 +42,15 @@ SIGNATURES = {
     "zs_debug_chain_trace": (c_int, [P]),
     "zs_chain_attn_fwd": (c_int, [P, c_int, c_int, P, P, c_int, c_float, P, c_int, P]),
     "zs_debug_clock_mhz": (c_int, [P, P]),
+    "zs_bce_logits_fwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
+    "zs_bce_logits_bwd": (c_int, [P, P, c_int64, c_float, c_float, c_float, P, P]),
+    "zs_act_bwd_f32": (c_int, [P, P, P, c_int64, c_int, P]),
+    "zs_colsum_f32": (c_int, [P, c_int, c_int64, c_int, P, c_int, P]),
+    "zs_gemm_tn_f32": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, c_int, c_int, c_int, P]),
+    "zs_layernorm_bwd_f32": (c_int, [P, P, P, c_float, P, P, P, c_int64, c_int, P]),
+    "zs_point_attention_bwd_f32": (c_int, [P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_mha_bwd_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_adamw_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
     "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),
     "zs_chain_mlp_blob_bytes": (c_size_t, []),

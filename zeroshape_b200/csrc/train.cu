@@ -1,0 +1,501 @@
+// Backward / training kernels of the implicit decoder (first slice: the decoder's
+// training step -- Implicit.forward on the GT sample points, BCE shape loss, backward, AdamW).
+//   reference: model/compute_graph/graph_shape.py:185 (pred_sample_occ), utils/loss.py:18-28 (shape_loss),
+//              model/shape_engine.py:248-277 (loss.backward(); optim.step()), torch autograd for every layer of
+//              model/shape/implicit.py.
+// All kernels are fp32 (gradient parity against torch autograd on the oracle); no tensor-core path yet.
+#include "common.cuh"
+
+namespace zs {
+
+static inline int grid_for_n(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)sm_count() * 32;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---- BCE-with-logits shape loss (utils/loss.py:18-28) ---------------------------------------------------------
+// loss = mean_i w_i * bce(x_i, y_i), y = (sdf < 0), w = impt_weight where |sdf| < impt_thres else 1
+// bce(x, y) = max(x, 0) - x*y + log1p(exp(-|x|))  (torch's stable form);  dloss/dx_i = w_i (sigmoid(x_i) - y_i) / n
+__global__ void bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ sdf, int64_t n, float thres, float weight,
+                               double* __restrict__ acc) {
+  double local = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xi = x[i], s = sdf[i];
+    const float y = s < 0.f ? 1.f : 0.f;
+    const float w = fabsf(s) < thres ? weight : 1.f;
+    local += (double)(w * (fmaxf(xi, 0.f) - xi * y + log1pf(expf(-fabsf(xi)))));
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(acc, red[0]);
+}
+__global__ void bce_finish_kernel(const double* acc, int64_t n, float* loss) { *loss = (float)(*acc / (double)n); }
+__global__ void bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ sdf, int64_t n, float thres, float weight,
+                               float gscale, float* __restrict__ dx) {
+  const float inv_n = gscale / (float)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xi = x[i], s = sdf[i];
+    const float y = s < 0.f ? 1.f : 0.f;
+    const float w = fabsf(s) < thres ? weight : 1.f;
+    dx[i] = w * (1.0f / (1.0f + expf(-xi)) - y) * inv_n;
+  }
+}
+
+// ---- activation backward: dx = dy * act'(z), z = pre-activation -------------------------------------------------
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, float* __restrict__ dx, int64_t n, int act) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float zi = z[i];
+    float d;
+    if (act == ZS_ACT_GELU) {              // d/dz [0.5 z (1 + erf(z/sqrt2))] = 0.5 (1 + erf(z/sqrt2)) + z exp(-z^2/2) / sqrt(2 pi)
+      d = 0.5f * (1.0f + erff(zi * 0.70710678118654752440f)) + zi * expf(-0.5f * zi * zi) * 0.39894228040143267794f;
+    } else if (act == ZS_ACT_SOFTPLUS100) {  // softplus(beta=100, threshold=20): sigmoid(100 z), 1 past the threshold
+      const float bz = 100.0f * zi;
+      d = bz > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-bz));
+    } else if (act == ZS_ACT_RELU) {
+      d = zi > 0.f ? 1.f : 0.f;
+    } else {
+      d = 1.f;
+    }
+    dx[i] = dy[i] * d;
+  }
+}
+
+// ---- column sums (bias gradients): out[n] (+)= sum_m A[m, n] ----------------------------------------------------
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, int64_t M, int N, float* __restrict__ out) {
+  // block = 32 x 8: 32 consecutive columns, 8 row lanes; grid.x over column groups, grid.y over row slabs (atomics combine slabs)
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (n < N)
+    for (int64_t m = blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8) acc += A[m * lda + n];
+  __shared__ float red[8][33];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+
+// ---- C[N,K] += A[M,N]^T B[M,K]  (weight gradients: dW = dY^T X) --------------------------------------------------
+// 64x64 output tile per CTA, 256 threads x (4x4) outputs, M split over grid.z and combined with atomics.
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                      float* __restrict__ C, int ldc, int64_t M, int N, int K, int64_t m_per_split) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int64_t mb = blockIdx.z * m_per_split, me = (mb + m_per_split < M) ? mb + m_per_split : M;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // outputs n = n0 + ty*4 + i, k = k0 + tx*4 + j
+  float acc[4][4] = {};
+  for (int64_t m0 = mb; m0 < me; m0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      const int64_t m = m0 + r;
+      As[r][c] = (m < me && n0 + c < N) ? A[m * lda + n0 + c] : 0.f;
+      Bs[r][c] = (m < me && k0 + c < K) ? B[m * ldb + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[r][ty * 4 + i]; b[i] = Bs[r][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty * 4 + i, k = k0 + tx * 4 + j;
+      if (n < N && k < K) atomicAdd(C + (int64_t)n * ldc + k, acc[i][j]);
+    }
+}
+
+// ---- LayerNorm backward (C == 256): warp per row --------------------------------------------------------------
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma;  dgamma += dy * xhat, dbeta += dy
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gam[8], dg[8], db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gam[i] = gamma ? gamma[lane + 32 * i] : 1.f; dg[i] = 0.f; db[i] = 0.f; }
+  for (int64_t r = blockIdx.x * 8 + warp; r < rows; r += (int64_t)gridDim.x * 8) {
+    float xv[8], dv[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xv[i] = x[r * 256 + lane + 32 * i]; dv[i] = dy[r * 256 + lane + 32 * i]; s += xv[i]; }
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xv[i] *= rstd;                      // xhat
+      const float g = dv[i] * gam[i];
+      s1 += g; s2 += g * xv[i];
+      dg[i] += dv[i] * xv[i]; db[i] += dv[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / 256.0f);
+    s2 = warp_sum(s2) * (1.0f / 256.0f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dx[r * 256 + lane + 32 * i] = rstd * (dv[i] * gam[i] - s1 - xv[i] * s2);
+  }
+  if (dgamma == nullptr) return;
+  __shared__ float rg[8][256], rb[8][256];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { rg[warp][lane + 32 * i] = dg[i]; rb[warp][lane + 32 * i] = db[i]; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { a += rg[w][c]; b += rb[w][c]; }
+  atomicAdd(dgamma + c, a);
+  atomicAdd(dbeta + c, b);
+}
+
+// ---- point -> (latents + self) attention backward (head dim 32) --------------------------------------------------
+// One CTA per (head, image): walks the image's P query points in tiles of 128 (thread = point) and keeps the latent-side
+// gradients dK_lat_h, dV_lat_h [L,32] of its (image, head) in shared memory for the whole walk -> no atomics, deterministic.
+// Per tile and block of 32 keys the threads publish ds[p][j] and p[p][j]; the CTA then reduces dK += ds^T Q, dV += p^T dO.
+template <int HD>
+__global__ void __launch_bounds__(128) point_attention_bwd_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ k_lat, const float* __restrict__ v_lat, int ld_lat,
+    const float* __restrict__ O, const float* __restrict__ dO, float* __restrict__ dqkv, float* __restrict__ dk_lat,
+    float* __restrict__ dv_lat, int ld_dlat, int P, int L, int heads, float scale) {
+  extern __shared__ float sm[];
+  float* Ks = sm;                   // [L][HD]
+  float* Vs = Ks + L * HD;          // [L][HD]
+  float* dKs = Vs + L * HD;         // [L][HD]
+  float* dVs = dKs + L * HD;        // [L][HD]
+  float* Qs = dVs + L * HD;         // [128][HD+1]
+  float* Gs = Qs + 128 * (HD + 1);  // [128][HD+1]  (dO)
+  float* dsT = Gs + 128 * (HD + 1); // [32][129]
+  float* pT = dsT + 32 * 129;       // [32][129]
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int C = heads * HD;
+  for (int i = t; i < L * HD; i += 128) {
+    const int j = i / HD, d = i % HD;
+    Ks[i] = k_lat[((int64_t)b * L + j) * ld_lat + h * HD + d];
+    Vs[i] = v_lat[((int64_t)b * L + j) * ld_lat + h * HD + d];
+    dKs[i] = 0.f; dVs[i] = 0.f;
+  }
+  __syncthreads();
+  for (int p0 = 0; p0 < P; p0 += 128) {
+    const int p = p0 + t;
+    const bool live = p < P;
+    const int64_t row = (int64_t)b * P + (live ? p : 0);
+    float q[HD], g[HD], dq[HD];
+    float D = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+      q[d] = live ? qkv[row * 3 * C + h * HD + d] : 0.f;
+      g[d] = live ? dO[row * C + h * HD + d] : 0.f;
+      D = fmaf(g[d], live ? O[row * C + h * HD + d] : 0.f, D);
+      dq[d] = 0.f;
+      Qs[t * (HD + 1) + d] = q[d];
+      Gs[t * (HD + 1) + d] = g[d];
+    }
+    // pass 1: softmax statistics over the latent keys and the point's own key
+    float s_self = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) s_self = fmaf(q[d], live ? qkv[row * 3 * C + C + h * HD + d] : 0.f, s_self);
+    s_self *= scale;
+    float mx = s_self;
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+      mx = fmaxf(mx, s * scale);
+    }
+    float sum = expf(s_self - mx);
+    for (int j = 0; j < L; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
+      sum += expf(s * scale - mx);
+    }
+    const float inv = 1.0f / sum;
+    // the point's own key / value
+    if (live) {
+      const float ps = expf(s_self - mx) * inv;
+      float dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dp = fmaf(g[d], qkv[row * 3 * C + 2 * C + h * HD + d], dp);
+      const float ds = ps * (dp - D) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        const float ks = qkv[row * 3 * C + C + h * HD + d];
+        dq[d] = fmaf(ds, ks, dq[d]);
+        dqkv[row * 3 * C + C + h * HD + d] = ds * q[d];
+        dqkv[row * 3 * C + 2 * C + h * HD + d] = ps * g[d];
+      }
+    }
+    // pass 2: latent keys in blocks of 32
+    for (int jb = 0; jb < L; jb += 32) {
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = jb + jj;
+        float dsv = 0.f, pv = 0.f;
+        if (j < L && live) {
+          float s = 0.f, dp = 0.f;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) { s = fmaf(q[d], Ks[j * HD + d], s); dp = fmaf(g[d], Vs[j * HD + d], dp); }
+          pv = expf(s * scale - mx) * inv;
+          dsv = pv * (dp - D) * scale;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) dq[d] = fmaf(dsv, Ks[j * HD + d], dq[d]);
+        }
+        dsT[jj * 129 + t] = dsv;
+        pT[jj * 129 + t] = pv;
+      }
+      __syncthreads();
+      {
+        // thread -> key jj = t / 4, dims d0 = (t % 4) * 8 .. +8
+        const int jj = t >> 2, d0 = (t & 3) * (HD / 4);
+        const int j = jb + jj;
+        if (j < L) {
+          float ak[HD / 4] = {}, av[HD / 4] = {};
+          for (int pp = 0; pp < 128; ++pp) {
+            const float dsv = dsT[jj * 129 + pp], pv = pT[jj * 129 + pp];
+#pragma unroll
+            for (int i = 0; i < HD / 4; ++i) {
+              ak[i] = fmaf(dsv, Qs[pp * (HD + 1) + d0 + i], ak[i]);
+              av[i] = fmaf(pv, Gs[pp * (HD + 1) + d0 + i], av[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < HD / 4; ++i) { dKs[j * HD + d0 + i] += ak[i]; dVs[j * HD + d0 + i] += av[i]; }
+        }
+      }
+      __syncthreads();
+    }
+    if (live) {
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dqkv[row * 3 * C + h * HD + d] = dq[d];
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < L * HD; i += 128) {
+    const int j = i / HD, d = i % HD;
+    dk_lat[((int64_t)b * L + j) * ld_dlat + h * HD + d] = dKs[i];
+    dv_lat[((int64_t)b * L + j) * ld_dlat + h * HD + d] = dVs[i];
+  }
+}
+
+// ---- token self-attention backward (latent branch; timm Attention core) -----------------------------------------
+// One CTA per (image, head); one warp per query row; dK / dV accumulated in shared memory.
+__global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                      float* __restrict__ dqkv, int T, int heads, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int ld = hd + 1;
+  float* Qs = sm;                       // [T][hd+1]
+  float* Ks = Qs + (size_t)T * ld;
+  float* Vs = Ks + (size_t)T * ld;
+  float* Gs = Vs + (size_t)T * ld;      // dO
+  float* dKs = Gs + (size_t)T * ld;
+  float* dVs = dKs + (size_t)T * ld;
+  const int nwarps = blockDim.x >> 5;
+  float* Ps = dVs + (size_t)T * ld;     // [nwarps][T]   p_j
+  float* Ds = Ps + (size_t)nwarps * T;  // [nwarps][T]   ds_j
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int C = heads * hd;
+  const float* base = qkv + (int64_t)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    Qs[t * ld + d] = base[(int64_t)t * 3 * C + h * hd + d];
+    Ks[t * ld + d] = base[(int64_t)t * 3 * C + C + h * hd + d];
+    Vs[t * ld + d] = base[(int64_t)t * 3 * C + 2 * C + h * hd + d];
+    Gs[t * ld + d] = dO[((int64_t)b * T + t) * C + h * hd + d];
+    dKs[t * ld + d] = 0.f; dVs[t * ld + d] = 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* P = Ps + warp * T;
+  float* Dv = Ds + warp * T;
+  for (int i = warp; i < T; i += nwarps) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(Qs[i * ld + d], Ks[j * ld + d], s);
+      s *= scale;
+      P[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { const float e = expf(P[j] - mx); P[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    float Dp = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      float dp = 0.f;
+      for (int d = 0; d < hd; ++d) dp = fmaf(Gs[i * ld + d], Vs[j * ld + d], dp);
+      const float p = P[j] * inv;
+      P[j] = p;
+      Dv[j] = dp;
+      Dp = fmaf(p, dp, Dp);
+    }
+    Dp = warp_sum(Dp);
+    for (int j = lane; j < T; j += 32) Dv[j] = P[j] * (Dv[j] - Dp) * scale;
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float acc = 0.f;
+      const float qi = Qs[i * ld + d], gi = Gs[i * ld + d];
+      for (int j = 0; j < T; ++j) {
+        acc = fmaf(Dv[j], Ks[j * ld + d], acc);
+        atomicAdd(&dKs[j * ld + d], Dv[j] * qi);
+        atomicAdd(&dVs[j * ld + d], P[j] * gi);
+      }
+      dqkv[((int64_t)b * T + i) * 3 * C + h * hd + d] = acc;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
+    const int t = i / hd, d = i % hd;
+    dqkv[((int64_t)b * T + t) * 3 * C + C + h * hd + d] = dKs[t * ld + d];
+    dqkv[((int64_t)b * T + t) * 3 * C + 2 * C + h * hd + d] = dVs[t * ld + d];
+  }
+}
+
+// ---- AdamW (torch.optim.AdamW semantics, model/shape_engine.py:132) ---------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i] * (1.0f - lr * wd);
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" int zs_bce_logits_fwd(const float* logits, const float* sdf, int64_t n, float impt_thres, float impt_weight,
+                                 double* ws, float* loss, void* stream) {
+  ZS_REQUIRE(logits && sdf && ws && loss && n > 0, "zs_bce_logits_fwd: bad args");
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaMemsetAsync(ws, 0, sizeof(double), st));
+  bce_fwd_kernel<<<grid_for_n(n), 256, 0, st>>>(logits, sdf, n, impt_thres, impt_weight, ws);
+  ZS_CUDA_CHECK_LAUNCH("zs_bce_logits_fwd");
+  bce_finish_kernel<<<1, 1, 0, st>>>(ws, n, loss);
+  ZS_CUDA_CHECK_LAUNCH("zs_bce_logits_fwd(finish)");
+  return ZS_OK;
+}
+
+extern "C" int zs_bce_logits_bwd(const float* logits, const float* sdf, int64_t n, float impt_thres, float impt_weight,
+                                 float grad_scale, float* dlogits, void* stream) {
+  ZS_REQUIRE(logits && sdf && dlogits && n > 0, "zs_bce_logits_bwd: bad args");
+  bce_bwd_kernel<<<grid_for_n(n), 256, 0, as_stream(stream)>>>(logits, sdf, n, impt_thres, impt_weight, grad_scale, dlogits);
+  ZS_CUDA_CHECK_LAUNCH("zs_bce_logits_bwd");
+  return ZS_OK;
+}
+
+extern "C" int zs_act_bwd_f32(const float* dy, const float* z, float* dx, int64_t n, int act, void* stream) {
+  ZS_REQUIRE(dy && z && dx && n >= 0, "zs_act_bwd_f32: bad args");
+  if (n == 0) return ZS_OK;
+  act_bwd_kernel<<<grid_for_n(n), 256, 0, as_stream(stream)>>>(dy, z, dx, n, act);
+  ZS_CUDA_CHECK_LAUNCH("zs_act_bwd_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_colsum_f32(const float* A, int lda, int64_t M, int N, float* out, int accumulate, void* stream) {
+  ZS_REQUIRE(A && out && M >= 0 && N > 0 && lda >= N, "zs_colsum_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) ZS_CUDA_CALL(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  if (M == 0) return ZS_OK;
+  int64_t slabs = (M + 8 * 64 - 1) / (8 * 64);
+  if (slabs > 256) slabs = 256;
+  dim3 grid((N + 31) / 32, (unsigned)(slabs > 0 ? slabs : 1));
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, M, N, out);
+  ZS_CUDA_CHECK_LAUNCH("zs_colsum_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_gemm_tn_f32(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                              int accumulate, void* stream) {
+  ZS_REQUIRE(A && B && C && M >= 0 && N > 0 && K > 0 && lda >= N && ldb >= K && ldc >= K, "zs_gemm_tn_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) ZS_CUDA_CALL(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * K, N, st));
+  if (M == 0) return ZS_OK;
+  const int tiles = ((N + 63) / 64) * ((K + 63) / 64);
+  int64_t splits = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  const int64_t max_splits = (M + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int64_t mps = ((M + splits - 1) / splits + 15) / 16 * 16;
+  splits = (M + mps - 1) / mps;
+  dim3 grid((N + 63) / 64, (K + 63) / 64, (unsigned)splits);
+  gemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, mps);
+  ZS_CUDA_CHECK_LAUNCH("zs_gemm_tn_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, float eps, float* dx, float* dgamma,
+                                    float* dbeta, int64_t rows, int cols, void* stream) {
+  ZS_REQUIRE(dy && x && dx && rows >= 0, "zs_layernorm_bwd_f32: null pointer");
+  ZS_REQUIRE(cols == 256, "zs_layernorm_bwd_f32: only 256 columns (the decoder width) are supported");
+  ZS_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "zs_layernorm_bwd_f32: dgamma and dbeta go together");
+  if (rows == 0) return ZS_OK;
+  int64_t g = (rows + 7) / 8;
+  const int cap = sm_count() * 8;
+  layernorm_bwd_kernel<<<(int)(g < cap ? g : cap), 256, 0, as_stream(stream)>>>(dy, x, gamma, eps, dx, dgamma, dbeta, rows);
+  ZS_CUDA_CHECK_LAUNCH("zs_layernorm_bwd_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, const float* O,
+                                          const float* dO, float* dqkv_p, float* dk_lat, float* dv_lat, int ld_dlat, int B, int P,
+                                          int L, int heads, int hd, float scale, void* stream) {
+  ZS_REQUIRE(qkv_p && k_lat && v_lat && O && dO && dqkv_p && dk_lat && dv_lat, "zs_point_attention_bwd_f32: null pointer");
+  ZS_REQUIRE(hd == 32 && B > 0 && P > 0 && L > 0 && heads > 0, "zs_point_attention_bwd_f32: head dim must be 32");
+  const size_t smem = sizeof(float) * ((size_t)4 * L * 32 + 2 * 128 * 33 + 2 * 32 * 129);
+  ZS_REQUIRE(smem <= 200 * 1024, "zs_point_attention_bwd_f32: too many latent tokens for shared memory");
+  ZS_CUDA_CALL(cudaFuncSetAttribute(point_attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  point_attention_bwd_kernel<32><<<dim3(heads, B), 128, smem, as_stream(stream)>>>(qkv_p, k_lat, v_lat, ld_lat, O, dO, dqkv_p, dk_lat,
+                                                                                  dv_lat, ld_dlat, P, L, heads, scale);
+  ZS_CUDA_CHECK_LAUNCH("zs_point_attention_bwd_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale,
+                              void* stream) {
+  ZS_REQUIRE(qkv && dO && dqkv && B > 0 && T > 0 && heads > 0 && hd > 0, "zs_mha_bwd_f32: bad args");
+  const int nwarps = 8;
+  const size_t smem = sizeof(float) * ((size_t)6 * T * (hd + 1) + (size_t)2 * nwarps * T);
+  ZS_REQUIRE(smem <= 200 * 1024, "zs_mha_bwd_f32: sequence too long for shared memory");
+  ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mha_bwd_kernel<<<B * heads, nwarps * 32, smem, as_stream(stream)>>>(qkv, dO, dqkv, T, heads, hd, scale);
+  ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, int step, void* stream) {
+  ZS_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "zs_adamw_f32: bad args");
+  if (n == 0) return ZS_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_for_n(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                           bc1, bc2);
+  ZS_CUDA_CHECK_LAUNCH("zs_adamw_f32");
+  return ZS_OK;
+}

@@ -6,9 +6,13 @@ math runs in libzeroshape_b200.so.
     forward fills var.{latent_semantic, depth_pred, intr_pred, validity_mask, seen_points, latent_depth, pose}
     (reference: model/compute_graph/graph_shape.py:115-192)
 
-Inference only in this revision (SURVEY.md section 8 row a13 -- training forward/backward -- is "next"):
-`training=True` / `get_loss=True` with a GT batch raises NotImplementedError instead of silently
-running a different code path.
+Training, decoder slice: with a GT batch (`gt_sample_points`, `gt_sample_sdf`,
+`depth_input_map`, `intr`, `pose_gt`) the forward also fills seen_points_gt / gt_points_cam / gt_surf_points /
+pred_sample_occ (graph_shape.py:155-185) and `compute_loss` returns the shape (BCE) and intrinsics losses
+(utils/loss.py:18-41).  Gradients exist for the implicit decoder (impl_network) only: the encoders run on the
+inference kernels, so their parameters must be frozen (requires_grad False) in train mode -- otherwise the
+forward raises instead of silently training a different model.  The MiDaS depth loss (model/depth/midas_loss.py)
+belongs to the depth-engine row and raises.
 """
 import torch
 import torch.nn as nn
@@ -19,6 +23,7 @@ from ...utils.util import EasyDict as edict
 from ..depth.dpt_depth import DPTDepthModel
 from ..shape.implicit import Implicit
 from ..shape.seen_coord_enc import CoordEncRes
+from ...utils.loss import Loss
 
 
 class Graph(nn.Module):
@@ -52,7 +57,7 @@ class Graph(nn.Module):
                                      n_layers_mlp=opt.arch.impl.mlp_layers, num_heads=opt.arch.num_heads,
                                      posenc_3D=opt.arch.impl.posenc_3D, mlp_ratio=opt.arch.impl.mlp_ratio,
                                      skip_in=opt.arch.impl.skip_in, pos_perlayer=opt.arch.impl.posenc_perlayer)
-        self.loss_fns = None    # utils/loss.py (BCE / MiDaS) belongs to the training path
+        self.loss_fns = Loss(opt)
 
     def load_pretrained_depth(self, opt):
         """graph_shape.py:69-87 (checkpoint bootstrap of the depth sub-network)."""
@@ -72,9 +77,14 @@ class Graph(nn.Module):
         return ops.intr_param2mtx(intr_params.float().contiguous(), opt.H, opt.W)
 
     def forward(self, opt, var, training=False, get_loss=True):
-        if training or ("gt_sample_points" in var and "gt_sample_sdf" in var):
-            raise NotImplementedError("zeroshape_b200 Graph: the training branch (GT points, losses, backward; "
-                                      "graph_shape.py:155-202) is not implemented in this revision")
+        if training and torch.is_grad_enabled():
+            enc = [n for m_name in ("dpt_depth", "intr_head", "intr_proj", "coord_encoder")
+                   for n, p in getattr(self, m_name).named_parameters() if p.requires_grad]
+            if enc:
+                raise NotImplementedError(
+                    "zeroshape_b200 Graph: backward exists for impl_network only in this revision; freeze the encoders "
+                    f"(requires_grad_(False) on dpt_depth / intr_head / intr_proj / coord_encoder) -- {len(enc)} encoder "
+                    "parameters still require grad")
         batch_size = len(var.idx)
         with torch.no_grad():
             var.latent_semantic = None
@@ -97,9 +107,32 @@ class Graph(nn.Module):
             coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
             var.latent_depth = self.coord_encoder.forward_nhwc(coord)
             var.pose = var.pose_gt if "pose_gt" in var else False
+            if "gt_sample_points" in var and "gt_sample_sdf" in var:
+                # graph_shape.py:157-182: normalising factors from the GT seen surface, GT points -> camera frame -> normalised
+                gt_pts, self.gt_mean, self.gt_scale = ops.unproject_normalize(var.depth_input_map.float(), mask, var.intr.float())
+                var.seen_points_gt = gt_pts
+                R_gt, T_gt = var.pose_gt[:, :, :3].float(), var.pose_gt[:, :, 3:].float()
+                cam = (R_gt @ var.gt_sample_points.float().permute(0, 2, 1) + T_gt).permute(0, 2, 1)   # [B,N,3] (tiny; host glue)
+                var.gt_points_cam = ((cam - self.gt_mean.unsqueeze(1)) / self.gt_scale.view(-1, 1, 1)).contiguous()
+                idx = torch.topk(var.gt_sample_sdf.abs(), k=min(100, var.gt_sample_sdf.shape[1]), dim=1, largest=False)[1]
+                var.gt_surf_points = torch.gather(var.gt_points_cam, 1, idx.unsqueeze(-1).repeat(1, 1, 3))
+        if "gt_sample_points" in var and "gt_sample_sdf" in var:
+            # graph_shape.py:185 -- differentiable when the decoder is in train mode (implicit_train.ImplicitTrainFn)
+            var.pred_sample_occ, _ = self.impl_network(var.latent_depth, None, var.gt_points_cam, need_attn=False)
         if get_loss:
-            return var, edict()
+            return var, self.compute_loss(opt, var, training)
         return var
 
     def compute_loss(self, opt, var, training=False):
-        raise NotImplementedError("losses belong to the training path (not in this revision)")
+        """graph_shape.py:194-202."""
+        loss = edict()
+        lw = opt.get("loss_weight", None) if isinstance(opt, dict) else getattr(opt, "loss_weight", None)
+        if lw is None:
+            return loss
+        if lw.get("depth") is not None:
+            loss.depth = self.loss_fns.depth_loss(var.depth_pred, var.depth_input_map, var.mask_input_map)
+        if lw.get("intr") is not None and training:
+            loss.intr = self.loss_fns.intr_loss(var.seen_points, var.seen_points_gt, var.validity_mask)
+        if lw.get("shape") is not None and training:
+            loss.shape = self.loss_fns.shape_loss(var.pred_sample_occ, var.gt_sample_sdf)
+        return loss

@@ -13,8 +13,9 @@ B200-first restructuring (results identical to the reference's):
     the chain of plain-fp32 kernels (`engine="f32"`, the bit-faithful path used for parity pinning);
   * `grid_occupancy` generates the (N+1)^3 query points on the fly (no [B,N,N,N,3] tensor).
 
-Inference only in this revision: calling it with autograd enabled on inputs that require grad
-raises NotImplementedError (training path = SURVEY.md section 8 row a13, scheduled next).
+Training (decoder slice): when autograd is enabled and a decoder parameter or the
+latents require grad, `forward` routes through `implicit_train.ImplicitTrainFn` -- fp32 forward with saved
+activations and the hand-written backward kernels of csrc/train.cu -- so `loss.backward()` fills `param.grad`.
 """
 import math
 from functools import partial
@@ -114,13 +115,15 @@ class Implicit(nn.Module):
     def _ln(x, m):
         return ops.layernorm(x, m.weight, m.bias, m.eps)
 
-    def _check_inference(self, *tensors):
-        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-            raise NotImplementedError(
-                "zeroshape_b200.Implicit: backward is not implemented in this revision (inference only); "
-                "wrap the call in torch.no_grad()")
-        if self.training and self.drop_path > 0 and torch.is_grad_enabled():
-            raise NotImplementedError("train-mode DropPath requires the training path (not in this revision)")
+    def _wants_grad(self, latent_depth, points_3D):
+        if not torch.is_grad_enabled():
+            return False
+        if points_3D.requires_grad:
+            raise NotImplementedError("zeroshape_b200.Implicit: gradients w.r.t. the query points are not implemented "
+                                      "(the reference never asks for them: graph_shape.py:160-185 builds them under no_grad)")
+        # eval-mode calls with parameters that merely *could* take gradients (the nn.Module default) stay on the inference
+        # kernels, like every demo / evaluation call of the reference under torch.no_grad()
+        return latent_depth.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))
 
     def prepare_latents(self, latent_depth):
         """Per-image latent-side work -> dict with K/V views of both blocks ([B,L,C], row stride 3C)."""
@@ -340,8 +343,13 @@ class Implicit(nn.Module):
 
     # -- public API --------------------------------------------------------------------------------
     def forward(self, latent_depth, latent_semantic, points_3D, need_attn=True):
-        self._check_inference(latent_depth, points_3D)
         assert latent_semantic is None
+        if self._wants_grad(latent_depth, points_3D):
+            # training call (graph_shape.py:185): differentiable logits; the attention map the reference also returns there
+            # is never used by the training loop (graph_shape.py:185, shape_engine.py:248-277) and is not produced
+            from .implicit_train import ImplicitTrainFn
+            params = [p for p in self.parameters()]
+            return ImplicitTrainFn.apply(self, latent_depth, points_3D, *params), None
         with torch.no_grad():
             pts = points_3D.float().contiguous()
             B, P, _ = pts.shape

@@ -576,3 +576,97 @@ class OpTimer:
     def clock_trace(self):
         torch.cuda.synchronize()
         return [(n, float(b.item())) for n, b in self.clocks]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Training-step kernels (csrc/train.cu): fp32 backward of the implicit decoder, BCE shape loss, AdamW.
+def gemm_tn(a, b, out=None, accumulate=False):
+    """out[N,K] (+)= a[M,N]^T @ b[M,K]  (weight gradient dW = dY^T X); 2-D row-strided inputs."""
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0] and a.stride(1) == 1 and b.stride(1) == 1
+    M, N = a.shape
+    K = b.shape[1]
+    if out is None:
+        out = torch.empty(N, K, device=a.device, dtype=torch.float32)
+        accumulate = False
+    assert out.shape == (N, K) and out.stride(1) == 1
+    check(lib.zs_gemm_tn_f32(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, int(accumulate), _stream()),
+          "zs_gemm_tn_f32")
+    return out
+
+
+def colsum(a, out=None, accumulate=False):
+    """out[N] (+)= a[M,N].sum(0)  (bias gradient)."""
+    assert a.dim() == 2 and a.stride(1) == 1
+    M, N = a.shape
+    if out is None:
+        out = torch.empty(N, device=a.device, dtype=torch.float32)
+        accumulate = False
+    check(lib.zs_colsum_f32(_p(a), a.stride(0), M, N, _p(out), int(accumulate), _stream()), "zs_colsum_f32")
+    return out
+
+
+def act_bwd(dy, z, act):
+    _chk(dy, "dy"); _chk(z, "z")
+    dx = torch.empty_like(dy)
+    check(lib.zs_act_bwd_f32(_p(dy), _p(z), _p(dx), dy.numel(), act, _stream()), "zs_act_bwd_f32")
+    return dx
+
+
+def layernorm_bwd(dy, x, gamma, eps, dgamma=None, dbeta=None):
+    """dx of LayerNorm over the last dim (256); dgamma / dbeta are accumulated into when given."""
+    _chk(dy, "dy"); _chk(x, "x"); _chk(gamma, "gamma"); _chk(dgamma, "dgamma"); _chk(dbeta, "dbeta")
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    check(lib.zs_layernorm_bwd_f32(_p(dy), _p(x), _p(gamma), eps, _p(dx), _p(dgamma), _p(dbeta), x.numel() // C, C, _stream()),
+          "zs_layernorm_bwd_f32")
+    return dx
+
+
+def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
+    """Backward of `point_attention`: -> dqkv_p [B,P,3C], dk_lat [B,L,C], dv_lat [B,L,C]."""
+    _chk(qkv_p, "qkv_p"); _chk(out, "out"); _chk(dout, "dout")
+    B, Pn, C3 = qkv_p.shape
+    C = C3 // 3
+    L = k_lat.shape[1]
+    assert k_lat.stride(2) == 1 and v_lat.stride(2) == 1 and k_lat.stride(1) == v_lat.stride(1)
+    assert k_lat.stride(0) == L * k_lat.stride(1) and v_lat.stride(0) == L * v_lat.stride(1)
+    dqkv = torch.empty_like(qkv_p)
+    dk = torch.empty(B, L, C, device=qkv_p.device, dtype=torch.float32)
+    dv = torch.empty(B, L, C, device=qkv_p.device, dtype=torch.float32)
+    check(lib.zs_point_attention_bwd_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(out), _p(dout), _p(dqkv), _p(dk), _p(dv),
+                                         C, B, Pn, L, heads, C // heads, (C // heads) ** -0.5, _stream()), "zs_point_attention_bwd_f32")
+    return dqkv, dk, dv
+
+
+def mha_bwd(qkv, dout, heads):
+    _chk(qkv, "qkv"); _chk(dout, "dout")
+    B, T, C3 = qkv.shape
+    C = C3 // 3
+    dqkv = torch.empty_like(qkv)
+    check(lib.zs_mha_bwd_f32(_p(qkv), _p(dout), _p(dqkv), B, T, heads, C // heads, (C // heads) ** -0.5, _stream()), "zs_mha_bwd_f32")
+    return dqkv
+
+
+def bce_logits_loss(logits, sdf, impt_thres, impt_weight):
+    """utils/loss.py:18-28 -> scalar device tensor (mean of the weighted BCE-with-logits against sdf < 0)."""
+    _chk(logits, "logits"); _chk(sdf, "sdf")
+    assert logits.shape == sdf.shape
+    ws = torch.empty(1, device=logits.device, dtype=torch.float64)
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(lib.zs_bce_logits_fwd(_p(logits), _p(sdf), logits.numel(), impt_thres, impt_weight, _p(ws), _p(loss), _stream()),
+          "zs_bce_logits_fwd")
+    return loss
+
+
+def bce_logits_loss_bwd(logits, sdf, impt_thres, impt_weight, grad_scale=1.0):
+    d = torch.empty_like(logits)
+    check(lib.zs_bce_logits_bwd(_p(logits), _p(sdf), logits.numel(), impt_thres, impt_weight, grad_scale, _p(d), _stream()),
+          "zs_bce_logits_bwd")
+    return d
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk(t, n)
+    check(lib.zs_adamw_f32(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                           _stream()), "zs_adamw_f32")
