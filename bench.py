@@ -264,6 +264,54 @@ def run_ours(args, rank, world, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+def run_train_decoder(args, rank, world, dev):
+    """BASELINE.json config 3, decoder slice only (the encoder backward does not exist yet): one step = Implicit forward on
+    B x 4096 GT sample points + BCE shape loss + backward + fused AdamW, latents given (as if the encoders were frozen)."""
+    import torch
+    from zeroshape_b200._native import lib
+    from zeroshape_b200.model.shape.implicit import Implicit
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    from zeroshape_b200.utils.loss import Loss
+    B, N = args.train_batch, 4096
+    torch.manual_seed(0)
+    net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                   pos_perlayer=False).to(dev).train()
+    optim = FusedAdamW(net.parameters(), lr=3e-5, betas=(0.9, 0.95), weight_decay=0.05)
+    lossfn = Loss({"training": {"shape_loss": {"impt_thres": 0.01, "impt_weight": 1.0}}})
+    g = torch.Generator().manual_seed(1)
+    lat_h = torch.randn(B, 197, 256, generator=g).pin_memory()
+    pts_h = (torch.rand(B, N, 3, generator=g) - 0.5).pin_memory()
+    sdf_h = (pts_h.norm(dim=-1) - 0.3 - 0.003).pin_memory()
+
+    def step():
+        lat, pts, sdf = lat_h.to(dev, non_blocking=True), pts_h.to(dev, non_blocking=True), sdf_h.to(dev, non_blocking=True)
+        logits, _ = net(lat, None, pts)
+        loss = lossfn.shape_loss(logits, sdf)
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        return loss
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.zs_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step()
+    last = float(loss.item())
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    flop = 3 * FLOP_PER_POINT * B * N          # fwd + dgrad + wgrad of the per-point work
+    return {"metric": "decoder training step (Implicit fwd + BCE + bwd + AdamW), query points/s", "value": B * N / (ms * 1e-3),
+            "unit": "points/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"row a13 decoder slice: {B} images x {N} GT sample points, latents given, fp32 kernels (csrc/train.cu)",
+                       "train_batch": B, "points_per_image": N},
+            "approx_tflops": flop / (ms * 1e-3) / 1e12, "last_loss": last, "gpu_launches": int(lib.zs_launch_count() - l0)}
+
+
 def cpu_reference_shapes_per_s(vox_res, slices, threads=None):
     """The reference algorithm on host cores (oracle restatement: same op sequence as the reference's
     PyTorch-CPU path): full encoder forward once, Implicit over `slices` x-slices of the (vox_res+1)^3
@@ -329,7 +377,7 @@ def run_reference(args, rank, world):
         vals.append(v)
     v = statistics.median(vals)
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": "shapes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": args.shapes * 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "reference algorithm on host CPU cores (oracle port; reference cannot be imported: "
                                    "timm/mcubes/trimesh absent)", "vox_res": args.vox_res},
@@ -337,14 +385,26 @@ def run_reference(args, rank, world):
             "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def _emit(line, real_stdout):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Exactly ONE line on stdout (the JSON): anything a library prints there (e.g. NCCL's version banner when NCCL_DEBUG is
+    # set) is diverted to stderr for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vox-res", type=int, default=128)
-    ap.add_argument("--shapes", type=int, default=1, help="shapes per GPU per step")
+    ap.add_argument("--shapes", type=int, default=8, help="shapes per GPU per step (SURVEY.md section 8d: B = 8 images in flight)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train-decoder"],
+                    help="train-decoder: time the decoder training step (row a13 slice) instead of the headline metric")
+    ap.add_argument("--train-batch", type=int, default=32, help="images per training step (options/shape.yaml batch 28-32)")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--attention", default=None, choices=["fused", "tc", "f32"])
@@ -360,7 +420,7 @@ def main():
     if args.impl == "reference":
         line = run_reference(args, rank, world)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            _emit(line, real_stdout)
         return
 
     import torch
@@ -372,12 +432,17 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    if args.mode == "train-decoder":
+        line = run_train_decoder(args, rank, world, dev)
+        if rank == 0:
+            _emit(line, real_stdout)
+        return
     line = run_ours(args, rank, world, dev)
     if rank == 0:
         if not args.no_cpu_baseline:
             v, info = cpu_reference_shapes_per_s(args.vox_res, args.cpu_slices)
             line["cpu_baseline"] = {"value": v, "unit": "shapes/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
-        print(json.dumps(line), flush=True)
+        _emit(line, real_stdout)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
