@@ -216,6 +216,23 @@ int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T,
 int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* Training of the seen-surface encoder (CoordEncRes: torchvision ResNet-50 + Bottleneck_Conv heads with batch-statistics
+ * BatchNorm, model/shape/seen_coord_enc.py:141-194; the `optim.fix_dpt` configuration of options/shape.yaml).
+ * zs_conv2d_nhwc_dgrad_f32: dx [B,H,W,Cin] from dy [B,OH,OW,Cout]; `w_dgrad` = the OHWI filter re-laid as [Cin][KH][KW][Cout].
+ * zs_conv2d_nhwc_wgrad_f32: dw [Cout,KH,KW,Cin] (+)= sum over output pixels of dy x im2col(x). */
+int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, int Cin, const float* w_dgrad, float* dx, int Cout,
+                             int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, void* stream);
+int zs_conv2d_nhwc_wgrad_f32(const float* x, int B, int H, int W, int Cin, const float* dy, float* dw, int Cout, int KH,
+                             int KW, int stride, int pad_top, int pad_left, int OH, int OW, int accumulate, void* stream);
+/* per-channel batch statistics of x [M,C]: mean, biased variance, rstd = 1/sqrt(var + eps); `ws` = 2*C doubles */
+int zs_bn_stats_f32(const float* x, int64_t M, int C, float eps, double* ws, float* mean, float* var, float* rstd, void* stream);
+/* BatchNorm (batch statistics) backward: dx, and dgamma / dbeta ACCUMULATED into; `ws` = 2*C doubles */
+int zs_bn_bwd_f32(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int64_t M,
+                  int C, double* ws, float* dx, float* dgamma, float* dbeta, void* stream);
+int zs_maxpool3x3s2_bwd_nhwc_f32(const float* x, const float* dy, float* dx, int B, int H, int W, int C, int pad_top,
+                                 int pad_left, int OH, int OW, void* stream);
+int zs_avgpool_bwd_nhwc_f32(const float* dy, float* dx, int B, int HW, int C, void* stream);
+
 /* debug: effective SM clock in MHz at this point of the stream (one-thread spin kernel, ~10 us). */
 int zs_debug_clock_mhz(float* out, void* stream);
 

@@ -45,7 +45,7 @@ def gemm_tc(a, pw, bias=None, res=None, res_mode=0, act=0, out=None, precision="
     return gemm(a, pw.src, bias, res, res_mode, act, out)
 
 
-def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, res=None, res_mode=0, pre_relu=False):
+def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, res=None, res_mode=0, pre_relu=False, tc=None):
     xn = x.permute(0, 3, 1, 2)
     if pre_relu:
         xn = F.relu(xn)

@@ -50,6 +50,13 @@ SIGNATURES = {
     "zs_layernorm_bwd_f32": (c_int, [P, P, P, c_float, P, P, P, c_int64, c_int, P]),
     "zs_point_attention_bwd_f32": (c_int, [P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "zs_mha_bwd_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_conv2d_nhwc_dgrad_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_conv2d_nhwc_wgrad_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, P]),
+    "zs_bn_stats_f32": (c_int, [P, c_int64, c_int, c_float, P, P, P, P, P]),
+    "zs_bn_bwd_f32": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P, P]),
+    "zs_maxpool3x3s2_bwd_nhwc_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_avgpool_bwd_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
     "zs_adamw_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
     "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),

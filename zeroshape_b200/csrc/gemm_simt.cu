@@ -300,3 +300,119 @@ extern "C" int zs_conv2d_nhwc_f32(const float* x, int B, int H, int W, int Cin,
           (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0), pre_relu != 0};
   return launch_gemm(a, w, K, M, Cout, K, ep, as_stream(stream), "zs_conv2d_nhwc_f32");
 }
+
+// =====================================================================================================================
+// Convolution backward (training of the seen-surface encoder): both gradients are
+// implicit GEMMs over the same NHWC tensors.
+//   dgrad: dX[b,ih,iw,ci] = sum_{kh,kw,co} dY[b,oh,ow,co] w[co,kh,kw,ci],  oh = (ih + pad_top - kh) / stride (exact, in range)
+//          = gemm_f32_kernel with rows = INPUT pixels, K = (kh,kw,co) gathered from dY, weights re-laid as Wd[ci][(kh,kw,co)]
+//   wgrad: dW[co,(kh,kw,ci)] = sum_m dY[m,co] * im2col(x)[m,(kh,kw,ci)]     (A^T B with B gathered by ConvA)
+namespace zs {
+
+struct DgradA {
+  const float* dy;
+  int B, H, W, Cout, KH, KW, stride, pad_top, pad_left, OH, OW;
+  int M, K;
+  struct Row { int b, ih, iw; bool ok; };
+  __device__ __forceinline__ Row row(int m) const {
+    Row r;
+    r.ok = m < M;
+    r.iw = m % W;
+    int t = m / W;
+    r.ih = t % H;
+    r.b = t / H;
+    return r;
+  }
+  __device__ __forceinline__ float4 load4(const Row& r, int k) const {   // Cout % 4 == 0: a float4 never straddles a tap
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!r.ok || k >= K) return v;
+    const int co = k % Cout;
+    const int t = k / Cout;
+    const int kw = t % KW, kh = t / KW;
+    const int a = r.ih + pad_top - kh, bb = r.iw + pad_left - kw;
+    if (a < 0 || bb < 0) return v;
+    const int oh = a / stride, ow = bb / stride;
+    if (oh * stride != a || ow * stride != bb || oh >= OH || ow >= OW) return v;
+    return __ldg(reinterpret_cast<const float4*>(dy + (((int64_t)r.b * OH + oh) * OW + ow) * Cout + co));
+  }
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ dY, ConvA xa, float* __restrict__ dW, int M, int N,
+                                                         int K, int m_per_split) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int mb = blockIdx.z * m_per_split, me = min(M, mb + m_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int m0 = mb; m0 < me; m0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      const int m = m0 + r;
+      As[r][c] = (m < me && n0 + c < N) ? dY[(int64_t)m * N + n0 + c] : 0.f;
+      float bv = 0.f;
+      if (m < me && k0 + c < K) { ConvA::Row rw = xa.row(m); bv = xa.elem(rw, k0 + c); }
+      Bs[r][c] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[r][ty * 4 + i]; b[i] = Bs[r][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty * 4 + i, k = k0 + tx * 4 + j;
+      if (n < N && k < K) atomicAdd(dW + (int64_t)n * K + k, acc[i][j]);
+    }
+}
+
+}  // namespace zs
+
+extern "C" int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, int Cin, const float* w_dgrad, float* dx, int Cout,
+                                        int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, void* stream) {
+  using namespace zs;
+  ZS_REQUIRE(dy && w_dgrad && dx, "zs_conv2d_nhwc_dgrad_f32: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (Cout & 3) == 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_dgrad_f32: bad shape (Cout %% 4 == 0 required)");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "zs_conv2d_nhwc_dgrad_f32: dy must be 16-byte aligned");
+  const int64_t M64 = (int64_t)B * H * W;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_dgrad_f32: too many pixels");
+  const int M = (int)M64, K = KH * KW * Cout;
+  DgradA a{dy, B, H, W, Cout, KH, KW, stride, pad_top, pad_left, OH, OW, M, K};
+  Epilogue ep{nullptr, nullptr, Cin, ZS_RES_NONE, dx, Cin, ZS_ACT_NONE};
+  return launch_gemm(a, w_dgrad, K, M, Cin, K, ep, as_stream(stream), "zs_conv2d_nhwc_dgrad_f32");
+}
+
+extern "C" int zs_conv2d_nhwc_wgrad_f32(const float* x, int B, int H, int W, int Cin, const float* dy, float* dw, int Cout, int KH,
+                                        int KW, int stride, int pad_top, int pad_left, int OH, int OW, int accumulate, void* stream) {
+  using namespace zs;
+  ZS_REQUIRE(x && dy && dw, "zs_conv2d_nhwc_wgrad_f32: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_wgrad_f32: bad shape");
+  const int64_t M64 = (int64_t)B * OH * OW;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_wgrad_f32: too many pixels");
+  const int M = (int)M64, K = KH * KW * Cin;
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) ZS_CUDA_CALL(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * K, st));
+  ConvA a{x, B, H, W, Cin, KH, KW, stride, pad_top, pad_left, OH, OW, M, K, false, false};
+  const int tiles = ((Cout + 63) / 64) * ((K + 63) / 64);
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  const int max_splits = (M + 127) / 128;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int mps = ((M + splits - 1) / splits + 15) / 16 * 16;
+  splits = (M + mps - 1) / mps;
+  dim3 grid((Cout + 63) / 64, (K + 63) / 64, splits);
+  conv_wgrad_kernel<<<grid, 256, 0, st>>>(dy, a, dw, M, Cout, K, mps);
+  ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_wgrad_f32");
+  return ZS_OK;
+}

@@ -371,6 +371,105 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
   }
 }
 
+// ---- BatchNorm in training mode (torchvision ResNet-50 / Bottleneck_Conv of CoordEncRes, seen_coord_enc.py:145-178) ----
+// statistics over the rows of x [M, C] (NHWC: M = B*H*W): double accumulators, atomics across row slabs
+__global__ void bn_stats_kernel(const float* __restrict__ x, int64_t M, int C, double* __restrict__ acc) {   // acc[0:C] sum, [C:2C] sumsq
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, q = 0.0;
+  if (c < C)
+    for (int64_t m = blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8) { const double v = x[m * C + c]; s += v; q += v * v; }
+  __shared__ double rs[8][33], rq[8][33];
+  rs[threadIdx.y][threadIdx.x] = s; rq[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += rs[i][threadIdx.x]; b += rq[i][threadIdx.x]; }
+    atomicAdd(acc + c, a);
+    atomicAdd(acc + C + c, b);
+  }
+}
+__global__ void bn_stats_finish_kernel(const double* __restrict__ acc, int64_t M, int C, float eps, float* __restrict__ mean,
+                                       float* __restrict__ var, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = acc[c] / (double)M;
+  double v = acc[C + c] / (double)M - mu * mu;
+  if (v < 0.0) v = 0.0;
+  mean[c] = (float)mu; var[c] = (float)v; rstd[c] = (float)(1.0 / sqrt(v + (double)eps));
+}
+// dgamma[c] = sum_m dy * xhat, dbeta[c] = sum_m dy
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, int64_t M, int C, double* __restrict__ acc) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const float mu = mean[c], rs = rstd[c];
+    for (int64_t m = blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8) {
+      const float d = dy[m * C + c];
+      s += (double)d; q += (double)(d * ((x[m * C + c] - mu) * rs));
+    }
+  }
+  __shared__ double rs_[8][33], rq_[8][33];
+  rs_[threadIdx.y][threadIdx.x] = s; rq_[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += rs_[i][threadIdx.x]; b += rq_[i][threadIdx.x]; }
+    atomicAdd(acc + c, a);          // dbeta
+    atomicAdd(acc + C + c, b);      // dgamma
+  }
+}
+// dx = gamma * rstd * (dy - dbeta / M - xhat * dgamma / M);  also converts the double accumulators to the fp32 gradients
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma, const double* __restrict__ acc,
+                                    int64_t M, int C, float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int64_t n = M * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float db = (float)(acc[c] / (double)M), dg = (float)(acc[C + c] / (double)M);
+    const float xh = (x[i] - mean[c]) * rstd[c];
+    dx[i] = gamma[c] * rstd[c] * (dy[i] - db - xh * dg);
+    if (i < C) { dbeta[i] += (float)acc[i]; dgamma[i] += (float)acc[C + i]; }
+  }
+}
+
+// ---- 3x3 stride-2 max-pool backward (NHWC): the gradient goes to the first maximum in scan order, like PyTorch ----
+__global__ void maxpool3x3s2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H,
+                                        int W, int C, int pad_top, int pad_left, int OH, int OW) {
+  const int64_t n = (int64_t)B * OH * OW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int b = (int)(t / OH);
+    float best = -INFINITY;
+    int64_t arg = -1;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = oh * 2 - pad_top + kh, iw = ow * 2 - pad_left + kw;
+        if ((unsigned)ih >= (unsigned)H || (unsigned)iw >= (unsigned)W) continue;
+        const int64_t j = (((int64_t)b * H + ih) * W + iw) * C + c;
+        const float v = x[j];
+        if (v > best || arg < 0) { if (v > best || arg < 0) { best = v; arg = j; } }
+      }
+    if (arg >= 0) atomicAdd(dx + arg, dy[i]);
+  }
+}
+
+// dx[b, hw, c] = dy[b, c] / HW   (global average pool backward)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int HW, int C) {
+  const int64_t n = (int64_t)B * HW * C;
+  const float inv = 1.0f / (float)HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    dx[i] = dy[(int64_t)b * C + c] * inv;
+  }
+}
+
 // ---- AdamW (torch.optim.AdamW semantics, model/shape_engine.py:132) ---------------------------------------------
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
@@ -497,5 +596,50 @@ extern "C" int zs_adamw_f32(float* param, const float* grad, float* exp_avg, flo
   adamw_kernel<<<grid_for_n(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                            bc1, bc2);
   ZS_CUDA_CHECK_LAUNCH("zs_adamw_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_bn_stats_f32(const float* x, int64_t M, int C, float eps, double* ws, float* mean, float* var, float* rstd,
+                               void* stream) {
+  ZS_REQUIRE(x && ws && mean && var && rstd && M > 0 && C > 0, "zs_bn_stats_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+  int64_t slabs = (M + 8 * 32 - 1) / (8 * 32);
+  if (slabs > 512) slabs = 512;
+  bn_stats_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, st>>>(x, M, C, ws);
+  ZS_CUDA_CHECK_LAUNCH("zs_bn_stats_f32");
+  bn_stats_finish_kernel<<<(C + 255) / 256, 256, 0, st>>>(ws, M, C, eps, mean, var, rstd);
+  ZS_CUDA_CHECK_LAUNCH("zs_bn_stats_f32(finish)");
+  return ZS_OK;
+}
+
+extern "C" int zs_bn_bwd_f32(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int64_t M,
+                             int C, double* ws, float* dx, float* dgamma, float* dbeta, void* stream) {
+  ZS_REQUIRE(dy && x && mean && rstd && gamma && ws && dx && dgamma && dbeta && M > 0 && C > 0, "zs_bn_bwd_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, st));
+  int64_t slabs = (M + 8 * 32 - 1) / (8 * 32);
+  if (slabs > 512) slabs = 512;
+  bn_bwd_reduce_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, st>>>(dy, x, mean, rstd, M, C, ws);
+  ZS_CUDA_CHECK_LAUNCH("zs_bn_bwd_f32(reduce)");
+  bn_bwd_apply_kernel<<<grid_for_n(M * C), 256, 0, st>>>(dy, x, mean, rstd, gamma, ws, M, C, dx, dgamma, dbeta);
+  ZS_CUDA_CHECK_LAUNCH("zs_bn_bwd_f32(apply)");
+  return ZS_OK;
+}
+
+extern "C" int zs_maxpool3x3s2_bwd_nhwc_f32(const float* x, const float* dy, float* dx, int B, int H, int W, int C, int pad_top,
+                                            int pad_left, int OH, int OW, void* stream) {
+  ZS_REQUIRE(x && dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_maxpool3x3s2_bwd_nhwc_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st));
+  maxpool3x3s2_bwd_kernel<<<grid_for_n((int64_t)B * OH * OW * C), 256, 0, st>>>(x, dy, dx, B, H, W, C, pad_top, pad_left, OH, OW);
+  ZS_CUDA_CHECK_LAUNCH("zs_maxpool3x3s2_bwd_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_avgpool_bwd_nhwc_f32(const float* dy, float* dx, int B, int HW, int C, void* stream) {
+  ZS_REQUIRE(dy && dx && B > 0 && HW > 0 && C > 0, "zs_avgpool_bwd_nhwc_f32: bad args");
+  avgpool_bwd_kernel<<<grid_for_n((int64_t)B * HW * C), 256, 0, as_stream(stream)>>>(dy, dx, B, HW, C);
+  ZS_CUDA_CHECK_LAUNCH("zs_avgpool_bwd_nhwc_f32");
   return ZS_OK;
 }

@@ -9,9 +9,9 @@ math runs in libzeroshape_b200.so.
 Training, decoder slice: with a GT batch (`gt_sample_points`, `gt_sample_sdf`,
 `depth_input_map`, `intr`, `pose_gt`) the forward also fills seen_points_gt / gt_points_cam / gt_surf_points /
 pred_sample_occ (graph_shape.py:155-185) and `compute_loss` returns the shape (BCE) and intrinsics losses
-(utils/loss.py:18-41).  Gradients exist for the implicit decoder (impl_network) only: the encoders run on the
-inference kernels, so their parameters must be frozen (requires_grad False) in train mode -- otherwise the
-forward raises instead of silently training a different model.  The MiDaS depth loss (model/depth/midas_loss.py)
+(utils/loss.py:18-41).  Gradients exist for the seen-surface encoder (coord_encoder) and the implicit decoder (impl_network), i.e. the
+`optim.fix_dpt` configuration; the depth estimator (dpt_depth / intr_head / intr_proj) runs on the inference kernels, so
+its parameters must be frozen in train mode -- otherwise the forward raises instead of silently training a different model.  The MiDaS depth loss (model/depth/midas_loss.py)
 belongs to the depth-engine row and raises.
 """
 import torch
@@ -78,13 +78,13 @@ class Graph(nn.Module):
 
     def forward(self, opt, var, training=False, get_loss=True):
         if training and torch.is_grad_enabled():
-            enc = [n for m_name in ("dpt_depth", "intr_head", "intr_proj", "coord_encoder")
+            enc = [n for m_name in ("dpt_depth", "intr_head", "intr_proj")
                    for n, p in getattr(self, m_name).named_parameters() if p.requires_grad]
             if enc:
                 raise NotImplementedError(
-                    "zeroshape_b200 Graph: backward exists for impl_network only in this revision; freeze the encoders "
-                    f"(requires_grad_(False) on dpt_depth / intr_head / intr_proj / coord_encoder) -- {len(enc)} encoder "
-                    "parameters still require grad")
+                    "zeroshape_b200 Graph: backward exists for coord_encoder and impl_network (the optim.fix_dpt configuration); "
+                    f"the depth estimator has none in this revision -- {len(enc)} parameters of dpt_depth / intr_head / intr_proj "
+                    "still require grad (construct the Graph with opt.optim.fix_dpt = True)")
         batch_size = len(var.idx)
         with torch.no_grad():
             var.latent_semantic = None
@@ -105,7 +105,8 @@ class Graph(nn.Module):
             var.seen_points, self.last_mean, self.last_scale = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
             # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
             coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
-            var.latent_depth = self.coord_encoder.forward_nhwc(coord)
+            if not self.coord_encoder.training:
+                var.latent_depth = self.coord_encoder.forward_nhwc(coord)
             var.pose = var.pose_gt if "pose_gt" in var else False
             if "gt_sample_points" in var and "gt_sample_sdf" in var:
                 # graph_shape.py:157-182: normalising factors from the GT seen surface, GT points -> camera frame -> normalised
@@ -116,6 +117,9 @@ class Graph(nn.Module):
                 var.gt_points_cam = ((cam - self.gt_mean.unsqueeze(1)) / self.gt_scale.view(-1, 1, 1)).contiguous()
                 idx = torch.topk(var.gt_sample_sdf.abs(), k=min(100, var.gt_sample_sdf.shape[1]), dim=1, largest=False)[1]
                 var.gt_surf_points = torch.gather(var.gt_points_cam, 1, idx.unsqueeze(-1).repeat(1, 1, 3))
+        if self.coord_encoder.training:
+            # train mode: batch-statistics BatchNorm, differentiable w.r.t. the encoder parameters (seen_coord_enc_train.py)
+            var.latent_depth = self.coord_encoder.forward_nhwc(coord)
         if "gt_sample_points" in var and "gt_sample_sdf" in var:
             # graph_shape.py:185 -- differentiable when the decoder is in train mode (implicit_train.ImplicitTrainFn)
             var.pred_sample_occ, _ = self.impl_network(var.latent_depth, None, var.gt_points_cam, need_attn=False)

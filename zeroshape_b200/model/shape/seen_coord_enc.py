@@ -7,7 +7,8 @@ options/shape.yaml:26 `arch.depth.encoder: resnet`), every layer in the CUDA lib
 state_dict keys = torchvision's (`encoder.conv1/bn1/layerN.M.{conv,bn}K/downsample.{0,1}`) plus
 `encoder.fc.{0,1}` Bottleneck_Conv(2048), `encoder.fc.2` Linear and `depth_feat_proj.{0,1,2}`.
 Eval-mode BatchNorm is folded into the (OHWI) filters once per weight version; conv+BN+ReLU and
-conv+BN+add+ReLU are single launches.  The transformer variant (CoordEncAtt) is not the shipped
+conv+BN+add+ReLU are single launches.  In train mode the forward uses batch statistics and is differentiable
+(seen_coord_enc_train.py: the `optim.fix_dpt` training configuration).  The transformer variant (CoordEncAtt) is not the shipped
 configuration and is not mirrored.
 """
 import torch
@@ -70,7 +71,13 @@ class CoordEncRes(nn.Module):
     def forward_nhwc(self, coord_nhwc):
         """coord_nhwc [B,H,W,3] (already multiplied by the mask) -> [B,197,latent]."""
         if self.training:
-            raise NotImplementedError("CoordEncRes: batch-statistics BatchNorm (training) is not in this revision")
+            # batch-statistics BatchNorm + saved activations + hand-written backward (seen_coord_enc_train.py)
+            from .seen_coord_enc_train import CoordEncTrainFn, train_forward
+            params = list(self.parameters())
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                return CoordEncTrainFn.apply(self, coord_nhwc, *params)
+            with torch.no_grad():
+                return train_forward(self, coord_nhwc.float().contiguous())[0]
         self._cache.refresh()
         enc = self.encoder
         B = coord_nhwc.shape[0]
@@ -101,4 +108,7 @@ class CoordEncRes(nn.Module):
         assert coord_obj.dim() == 4 and mask_obj.dim() == 4
         with torch.no_grad():
             x = ops.nchw_to_nhwc((coord_obj * mask_obj.float()).float().contiguous())
+        if self.training:
+            return self.forward_nhwc(x)
+        with torch.no_grad():
             return self.forward_nhwc(x)

@@ -274,8 +274,8 @@ def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE, tc=None):
 
 
 def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=None, res_mode=RES_NONE,
-                pre_relu=False):
-    """x [B,H,W,Cin]; w [Cout,KH,KW,Cin]; pad = (top, bottom, left, right)."""
+                pre_relu=False, tc=None):
+    """x [B,H,W,Cin]; w [Cout,KH,KW,Cin]; pad = (top, bottom, left, right).  `tc`: None = ENCODER_ENGINE policy, False = FFMA."""
     _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias"); _chk(res, "res")
     B, H, W, Cin = x.shape
     Cout, KH, KW, Cin2 = w.shape
@@ -288,7 +288,7 @@ def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=N
         res_mode = RES_NONE
     elif res_mode == RES_NONE:
         res_mode = RES_AFTER_ACT
-    if Cin % 4 == 0 and KH * KW * Cin >= 32 and _encoder_tc():
+    if Cin % 4 == 0 and KH * KW * Cin >= 32 and (tc if tc is not None else _encoder_tc()):
         check(lib.zs_conv2d_nhwc_tc(_p(x), B, H, W, Cin, _p(_packed_of(w).get()), _p(bias), _p(res), res_mode, _p(y), Cout,
                                     KH, KW, stride, pt, pl, OH, OW, act, int(pre_relu), PRECISIONS[ENCODER_PRECISION],
                                     _stream()), "zs_conv2d_nhwc_tc")
@@ -670,3 +670,69 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
         _chk(t, n)
     check(lib.zs_adamw_f32(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, weight_decay, step,
                            _stream()), "zs_adamw_f32")
+
+
+def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad):
+    """dx [B,H,W,Cin] of conv2d_nhwc given dy [B,OH,OW,Cout]; w_ohwi [Cout,KH,KW,Cin]; pad = (top, bottom, left, right)."""
+    _chk(dy, "dy"); _chk(w_ohwi, "w")
+    B, H, W, Cin = in_shape
+    Cout, KH, KW, _ = w_ohwi.shape
+    OH, OW = dy.shape[1], dy.shape[2]
+    wd = w_ohwi.permute(3, 1, 2, 0).contiguous().view(Cin, KH * KW * Cout)       # weights only: [ci][(kh,kw,co)]
+    dx = torch.empty(B, H, W, Cin, device=dy.device, dtype=torch.float32)
+    check(lib.zs_conv2d_nhwc_dgrad_f32(_p(dy), B, H, W, Cin, _p(wd), _p(dx), Cout, KH, KW, stride, pad[0], pad[2], OH, OW, _stream()),
+          "zs_conv2d_nhwc_dgrad_f32")
+    return dx
+
+
+def conv2d_nhwc_wgrad(x, dy, kh, kw, stride, pad, out=None, accumulate=False):
+    """dw [Cout,KH,KW,Cin] (+)= wgrad of conv2d_nhwc."""
+    _chk(x, "x"); _chk(dy, "dy")
+    B, H, W, Cin = x.shape
+    OH, OW, Cout = dy.shape[1], dy.shape[2], dy.shape[3]
+    if out is None:
+        out = torch.empty(Cout, kh, kw, Cin, device=x.device, dtype=torch.float32)
+        accumulate = False
+    _chk(out, "out")
+    check(lib.zs_conv2d_nhwc_wgrad_f32(_p(x), B, H, W, Cin, _p(dy), _p(out), Cout, kh, kw, stride, pad[0], pad[2], OH, OW,
+                                       int(accumulate), _stream()), "zs_conv2d_nhwc_wgrad_f32")
+    return out
+
+
+def bn_stats(x2d, eps):
+    """Per-channel batch statistics of x [M,C] -> mean, biased var, rstd."""
+    _chk(x2d, "x")
+    M, C = x2d.shape
+    ws = torch.empty(2 * C, device=x2d.device, dtype=torch.float64)
+    mean, var, rstd = (torch.empty(C, device=x2d.device, dtype=torch.float32) for _ in range(3))
+    check(lib.zs_bn_stats_f32(_p(x2d), M, C, eps, _p(ws), _p(mean), _p(var), _p(rstd), _stream()), "zs_bn_stats_f32")
+    return mean, var, rstd
+
+
+def bn_bwd(dy2d, x2d, mean, rstd, gamma, dgamma, dbeta):
+    """BatchNorm (batch statistics) backward; dgamma / dbeta are accumulated into."""
+    for t, n in ((dy2d, "dy"), (x2d, "x"), (mean, "mean"), (rstd, "rstd"), (gamma, "gamma"), (dgamma, "dgamma"), (dbeta, "dbeta")):
+        _chk(t, n)
+    M, C = x2d.shape
+    ws = torch.empty(2 * C, device=x2d.device, dtype=torch.float64)
+    dx = torch.empty_like(x2d)
+    check(lib.zs_bn_bwd_f32(_p(dy2d), _p(x2d), _p(mean), _p(rstd), _p(gamma), M, C, _p(ws), _p(dx), _p(dgamma), _p(dbeta), _stream()),
+          "zs_bn_bwd_f32")
+    return dx
+
+
+def maxpool3x3s2_bwd_nhwc(x, dy, pad_top, pad_left):
+    _chk(x, "x"); _chk(dy, "dy")
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    check(lib.zs_maxpool3x3s2_bwd_nhwc_f32(_p(x), _p(dy), _p(dx), B, H, W, C, pad_top, pad_left, dy.shape[1], dy.shape[2], _stream()),
+          "zs_maxpool3x3s2_bwd_nhwc_f32")
+    return dx
+
+
+def avgpool_bwd_nhwc(dy, H, W):
+    _chk(dy, "dy")
+    B, C = dy.shape
+    dx = torch.empty(B, H, W, C, device=dy.device, dtype=torch.float32)
+    check(lib.zs_avgpool_bwd_nhwc_f32(_p(dy), _p(dx), B, H * W, C, _stream()), "zs_avgpool_bwd_nhwc_f32")
+    return dx

@@ -2,7 +2,8 @@
 
   Bottleneck_Conv (utils/layers.py:76-100): conv -> BN -> ReLU -> conv -> BN -> +x -> ReLU, used by the
   intrinsics head (kernel 3, graph_shape.py:20-23) and CoordEncRes (kernel 1, seen_coord_enc.py:149-153).
-Parameter names (`linear1`, `bn1`, `linear2`, `bn2`) are the reference's.  Inference (eval-mode BN) only.
+Parameter names (`linear1`, `bn1`, `linear2`, `bn2`) are the reference's.  Eval mode folds BN into the filters; train mode
+uses batch statistics (forward value here, gradients via model/shape/seen_coord_enc_train.py).
 """
 import torch
 import torch.nn as nn
@@ -22,9 +23,15 @@ class Bottleneck_Conv(nn.Module):
 
     def run_nhwc(self, x, cache, tag):
         """x [B,H,W,C] NHWC (a [B,C] vector is a 1x1 image) -> same shape.  BN folded via `cache`."""
-        if self.training:
-            raise NotImplementedError("Bottleneck_Conv: batch-statistics BatchNorm (training) is not in this revision")
         squeeze = x.dim() == 2
+        if self.training:
+            # train mode = batch statistics + running-stat update, exactly what nn.BatchNorm2d does even when the parameters
+            # are frozen (the reference leaves intr_head in train mode under optim.fix_dpt, graph_shape.py:35-38).
+            # Forward value only here; the differentiable use goes through seen_coord_enc_train.CoordEncTrainFn.
+            from ..model.shape.seen_coord_enc_train import _bneck_conv_fwd
+            with torch.no_grad():
+                y = _bneck_conv_fwd([], x.view(x.shape[0], 1, 1, x.shape[1]) if squeeze else x, self)
+            return y.view(y.shape[0], -1) if squeeze else y
         if squeeze:
             x = x.view(x.shape[0], 1, 1, x.shape[1])
         p = self.kernel_size // 2
