@@ -233,6 +233,20 @@ int zs_maxpool3x3s2_bwd_nhwc_f32(const float* x, const float* dy, float* dx, int
                                  int pad_left, int OH, int OW, void* stream);
 int zs_avgpool_bwd_nhwc_f32(const float* dy, float* dx, int B, int HW, int C, void* stream);
 
+/* Backward kernels of the depth estimator's layers (DPT-hybrid: timm ResNetV2 GroupNorm, ViT LayerNorm over 768 columns,
+ * align_corners bilinear upsampling of model/depth/blocks.py:321-342) and of the geometry glue (utils/camera.py:52-108). */
+int zs_coldot_f32(const float* A, int lda, const float* B2, int ldb, int64_t M, int N, float* out, int accumulate, void* stream);
+int zs_layernorm_bwd_generic_f32(const float* dy, const float* x, const float* gamma, float eps, float* dx, float* xhat,
+                                 int64_t rows, int cols, void* stream);
+int zs_groupnorm_bwd_nhwc_f32(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                              int B, int HW, int C, int groups, float eps, void* stream);
+int zs_bilinear_bwd_nhwc_f32(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW, int align_corners, void* stream);
+/* ddepth [B,H,W] and dKinv [B,3,3] (gradient w.r.t. the INVERSE intrinsics) from dseen [B,HW,3]; seen_points / scale are the
+ * forward outputs of zs_unproject_normalize_f32. */
+int zs_unproject_normalize_bwd_f32(const float* depth, const float* mask, const float* K, const float* seen_points,
+                                   const float* scale, const float* dseen, float* ddepth, float* dKinv, int B, int H, int W,
+                                   void* stream);
+
 /* debug: effective SM clock in MHz at this point of the stream (one-thread spin kernel, ~10 us). */
 int zs_debug_clock_mhz(float* out, void* stream);
 

@@ -164,7 +164,12 @@ def dpt_depth_forward(sd, image, pre="", get_feat=True):
 
 
 # ---- Bottleneck_Conv / torchvision ResNet-50 / CoordEncRes ------------------------------------------
+BN_TRAINING = False   # tests of the training path flip this: nn.BatchNorm2d in train mode normalises with batch statistics
+
+
 def _bn(x, sd, pre):
+    if BN_TRAINING:
+        return F.batch_norm(x, None, None, sd[pre + ".weight"], sd[pre + ".bias"], True, 0.0, BN_EPS)
     return F.batch_norm(x, sd[pre + ".running_mean"], sd[pre + ".running_var"], sd[pre + ".weight"], sd[pre + ".bias"],
                         False, 0.0, BN_EPS)
 

@@ -57,6 +57,11 @@ SIGNATURES = {
     "zs_bn_bwd_f32": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P, P]),
     "zs_maxpool3x3s2_bwd_nhwc_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_avgpool_bwd_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "zs_coldot_f32": (c_int, [P, c_int, P, c_int, c_int64, c_int, P, c_int, P]),
+    "zs_layernorm_bwd_generic_f32": (c_int, [P, P, P, c_float, P, P, c_int64, c_int, P]),
+    "zs_groupnorm_bwd_nhwc_f32": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_bilinear_bwd_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_unproject_normalize_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "zs_adamw_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
     "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),

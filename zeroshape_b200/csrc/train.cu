@@ -59,6 +59,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
       d = bz > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-bz));
     } else if (act == ZS_ACT_RELU) {
       d = zi > 0.f ? 1.f : 0.f;
+    } else if (act == ZS_ACT_CLAMP01) {      // clamp(relu(z), 0, 1): passes gradient strictly inside (0, 1)
+      d = (zi > 0.f && zi < 1.f) ? 1.f : 0.f;
     } else {
       d = 1.f;
     }
@@ -67,12 +69,15 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 }
 
 // ---- column sums (bias gradients): out[n] (+)= sum_m A[m, n] ----------------------------------------------------
-__global__ void colsum_kernel(const float* __restrict__ A, int lda, int64_t M, int N, float* __restrict__ out) {
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B2, int ldb, int64_t M, int N,
+                              float* __restrict__ out) {
   // block = 32 x 8: 32 consecutive columns, 8 row lanes; grid.x over column groups, grid.y over row slabs (atomics combine slabs)
+  // B2 != nullptr: column-wise dot products sum_m A[m,n] * B2[m,n]
   const int n = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (n < N)
-    for (int64_t m = blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8) acc += A[m * lda + n];
+    for (int64_t m = blockIdx.y * 8 + threadIdx.y; m < M; m += (int64_t)gridDim.y * 8)
+      acc += B2 ? A[m * lda + n] * B2[m * ldb + n] : A[m * lda + n];
   __shared__ float red[8][33];
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
@@ -295,41 +300,47 @@ __global__ void __launch_bounds__(128) point_attention_bwd_kernel(
   }
 }
 
-// ---- token self-attention backward (latent branch; timm Attention core) -----------------------------------------
-// One CTA per (image, head); one warp per query row; dK / dV accumulated in shared memory.
+// ---- token self-attention backward (latent branch of the decoder, ViT blocks of the depth encoder; timm Attention) ----
+// One CTA per (image, head); one warp per query row; K, V and the dK / dV accumulators live in shared memory (the 197 x 64
+// ViT-B heads need 4 x 51 KB), q_i / dO_i of the row in a per-warp buffer.
 __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                                                       float* __restrict__ dqkv, int T, int heads, int hd, float scale) {
   extern __shared__ float sm[];
   const int ld = hd + 1;
-  float* Qs = sm;                       // [T][hd+1]
-  float* Ks = Qs + (size_t)T * ld;
+  float* Ks = sm;                       // [T][hd+1]
   float* Vs = Ks + (size_t)T * ld;
-  float* Gs = Vs + (size_t)T * ld;      // dO
-  float* dKs = Gs + (size_t)T * ld;
+  float* dKs = Vs + (size_t)T * ld;
   float* dVs = dKs + (size_t)T * ld;
   const int nwarps = blockDim.x >> 5;
   float* Ps = dVs + (size_t)T * ld;     // [nwarps][T]   p_j
   float* Ds = Ps + (size_t)nwarps * T;  // [nwarps][T]   ds_j
+  float* Qw = Ds + (size_t)nwarps * T;  // [nwarps][hd]
+  float* Gw = Qw + (size_t)nwarps * hd; // [nwarps][hd]
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
   const int C = heads * hd;
   const float* base = qkv + (int64_t)b * T * 3 * C;
   for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
     const int t = i / hd, d = i % hd;
-    Qs[t * ld + d] = base[(int64_t)t * 3 * C + h * hd + d];
     Ks[t * ld + d] = base[(int64_t)t * 3 * C + C + h * hd + d];
     Vs[t * ld + d] = base[(int64_t)t * 3 * C + 2 * C + h * hd + d];
-    Gs[t * ld + d] = dO[((int64_t)b * T + t) * C + h * hd + d];
     dKs[t * ld + d] = 0.f; dVs[t * ld + d] = 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* P = Ps + warp * T;
   float* Dv = Ds + warp * T;
+  float* Q = Qw + warp * hd;
+  float* G = Gw + warp * hd;
   for (int i = warp; i < T; i += nwarps) {
+    for (int d = lane; d < hd; d += 32) {
+      Q[d] = base[(int64_t)i * 3 * C + h * hd + d];
+      G[d] = dO[((int64_t)b * T + i) * C + h * hd + d];
+    }
+    __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < T; j += 32) {
       float s = 0.f;
-      for (int d = 0; d < hd; ++d) s = fmaf(Qs[i * ld + d], Ks[j * ld + d], s);
+      for (int d = 0; d < hd; ++d) s = fmaf(Q[d], Ks[j * ld + d], s);
       s *= scale;
       P[j] = s;
       mx = fmaxf(mx, s);
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
     float Dp = 0.f;
     for (int j = lane; j < T; j += 32) {
       float dp = 0.f;
-      for (int d = 0; d < hd; ++d) dp = fmaf(Gs[i * ld + d], Vs[j * ld + d], dp);
+      for (int d = 0; d < hd; ++d) dp = fmaf(G[d], Vs[j * ld + d], dp);
       const float p = P[j] * inv;
       P[j] = p;
       Dv[j] = dp;
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
     __syncwarp();
     for (int d = lane; d < hd; d += 32) {
       float acc = 0.f;
-      const float qi = Qs[i * ld + d], gi = Gs[i * ld + d];
+      const float qi = Q[d], gi = G[d];
       for (int j = 0; j < T; ++j) {
         acc = fmaf(Dv[j], Ks[j * ld + d], acc);
         atomicAdd(&dKs[j * ld + d], Dv[j] * qi);
@@ -470,6 +481,220 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dy, float* __restri
   }
 }
 
+// ---- LayerNorm backward, any C (multiple of 4): dx only (dgamma = coldot(dy, xhat), dbeta = colsum(dy)) -----------
+__global__ void __launch_bounds__(256) layernorm_bwd_generic_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                    const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                                    float* __restrict__ xhat, int64_t rows, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t r = blockIdx.x * 8 + warp; r < rows; r += (int64_t)gridDim.x * 8) {
+    const float* xr = x + r * C;
+    const float* dr = dy + r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float g = dr[c] * (gamma ? gamma[c] : 1.f);
+      s1 += g; s2 += g * (xr[c] - mean) * rstd;
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mean) * rstd;
+      dx[r * C + c] = rstd * (dr[c] * (gamma ? gamma[c] : 1.f) - s1 - xh * s2);
+      if (xhat) xhat[r * C + c] = xh;
+    }
+  }
+}
+
+// ---- GroupNorm backward (NHWC; timm GroupNormAct of the ResNetV2 backbone): one CTA per (image, group) -----------
+__global__ void __launch_bounds__(512) groupnorm_bwd_nhwc_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 const float* __restrict__ gamma, float* __restrict__ dx,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C,
+                                                                 int groups, float eps) {
+  const int b = blockIdx.x / groups, gi = blockIdx.x % groups;
+  const int cg = C / groups;
+  const int64_t base = (int64_t)b * HW * C + gi * cg;
+  const int64_t n = (int64_t)HW * cg;
+  __shared__ float sh[34];
+  __shared__ float accg[64], accb[64];      // cg <= 64
+  auto bsum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+  };
+  if (threadIdx.x < 64) { accg[threadIdx.x] = 0.f; accb[threadIdx.x] = 0.f; }
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[base + (i / cg) * C + (i % cg)];
+  const float mean = bsum(s) / (float)n;
+  float v = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float d = x[base + (i / cg) * C + (i % cg)] - mean; v += d * d; }
+  const float rstd = rsqrtf(bsum(v) / (float)n + eps);
+  float s1 = 0.f, s2 = 0.f, lg = 0.f, lb = 0.f;      // blockDim % cg == 0: a thread always sees the same channel
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (int)(i % cg);
+    const int64_t off = base + (i / cg) * C + c;
+    const float xh = (x[off] - mean) * rstd, d = dy[off];
+    const float g = d * gamma[gi * cg + c];
+    s1 += g; s2 += g * xh;
+    lg += d * xh; lb += d;
+  }
+  atomicAdd(&accg[threadIdx.x % cg], lg);
+  atomicAdd(&accb[threadIdx.x % cg], lb);
+  s1 = bsum(s1) / (float)n;
+  s2 = bsum(s2) / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (int)(i % cg);
+    const int64_t off = base + (i / cg) * C + c;
+    const float xh = (x[off] - mean) * rstd;
+    dx[off] = rstd * (dy[off] * gamma[gi * cg + c] - s1 - xh * s2);
+  }
+  __syncthreads();
+  if (threadIdx.x < cg) { atomicAdd(dgamma + gi * cg + threadIdx.x, accg[threadIdx.x]); atomicAdd(dbeta + gi * cg + threadIdx.x, accb[threadIdx.x]); }
+}
+
+// ---- bilinear resize backward (NHWC): scatter with atomics ------------------------------------------------------
+__device__ __forceinline__ void bilinear_src_t(int dst, int in, int out, int align, int& i0, int& i1, float& l1) {
+  float src;
+  if (align) {
+    const float sc = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    src = sc * dst;
+  } else {
+    const float sc = (float)in / (float)out;
+    src = sc * (dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+  }
+  i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  l1 = src - (float)i0;
+}
+__global__ void bilinear_bwd_nhwc_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C, int OH, int OW,
+                                         int align) {
+  const int64_t total = (int64_t)B * OH * OW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int b = (int)(t / OH);
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_src_t(oh, H, OH, align, h0, h1, lh);
+    bilinear_src_t(ow, W, OW, align, w0, w1, lw);
+    float* xb = dx + (int64_t)b * H * W * C + c;
+    const float g = dy[i], hh0 = 1.f - lh, ww0 = 1.f - lw;
+    atomicAdd(xb + ((int64_t)h0 * W + w0) * C, g * hh0 * ww0);
+    atomicAdd(xb + ((int64_t)h0 * W + w1) * C, g * hh0 * lw);
+    atomicAdd(xb + ((int64_t)h1 * W + w0) * C, g * lh * ww0);
+    atomicAdd(xb + ((int64_t)h1 * W + w1) * C, g * lh * lw);
+  }
+}
+
+// ---- unproject + normalise backward (utils/camera.py:52-108, graph_shape.py:132-141) ------------------------------
+// out_i = (X_i - m) / s for valid pixels, X_i = d_i * r_i, r_i = Kinv (u, v, 1)^T, m = mean_valid X, s = max_valid |X - m|.
+// Given g_i = dL/dout_i:  dL/dX_i = g_i / s + [i == j] * ds * n_j + dm / N,   ds = -sum_i g_i . out_i / s,  n_j = out_j,
+// dm = -sum_i g_i / s - ds * n_j (j = the pixel that attains the maximum);  dL/dd_i = dL/dX_i . r_i,
+// dL/dKinv = sum_i d_i * (dL/dX_i) (u, v, 1).   One CTA (1024 threads) per image.
+__global__ void __launch_bounds__(1024) unproject_normalize_bwd_kernel(const float* __restrict__ depth, const float* __restrict__ mask,
+                                                                       const float* __restrict__ K, const float* __restrict__ out,
+                                                                       const float* __restrict__ scale, const float* __restrict__ g,
+                                                                       float* __restrict__ ddepth, float* __restrict__ dKinv, int H, int W) {
+  __shared__ float sh[33];
+  __shared__ float kinv[9];
+  __shared__ int sj;
+  const int b = blockIdx.x, HW = H * W;
+  if (threadIdx.x == 0) {
+    const float* k = K + b * 9;
+    const float a = k[0], bb = k[1], c = k[2], d = k[3], e = k[4], f = k[5], gg = k[6], h = k[7], i = k[8];
+    const float A = e * i - f * h, Bc = -(d * i - f * gg), Cc = d * h - e * gg;
+    const float r = 1.0f / (a * A + bb * Bc + c * Cc);
+    kinv[0] = A * r;  kinv[1] = -(bb * i - c * h) * r; kinv[2] = (bb * f - c * e) * r;
+    kinv[3] = Bc * r; kinv[4] = (a * i - c * gg) * r;  kinv[5] = -(a * f - c * d) * r;
+    kinv[6] = Cc * r; kinv[7] = -(a * h - bb * gg) * r; kinv[8] = (a * e - bb * d) * r;
+    sj = 0x7fffffff;
+  }
+  __syncthreads();
+  auto bred = [&](float v, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+      t = is_max ? warp_max(t) : warp_sum(t);
+      if (threadIdx.x == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+  };
+  const float* dp = depth + (int64_t)b * HW;
+  const float* mp = mask + (int64_t)b * HW;
+  const float* op = out + (int64_t)b * HW * 3;
+  const float* gp = g + (int64_t)b * HW * 3;
+  const float s = scale[b];
+  float gx = 0.f, gy = 0.f, gz = 0.f, go = 0.f, cnt = 0.f, nmax = -INFINITY;
+  for (int idx = threadIdx.x; idx < HW; idx += blockDim.x) {
+    if (mp[idx] > 0.5f) {
+      const float ox = op[idx * 3], oy = op[idx * 3 + 1], oz = op[idx * 3 + 2];
+      const float a0 = gp[idx * 3], a1 = gp[idx * 3 + 1], a2 = gp[idx * 3 + 2];
+      gx += a0; gy += a1; gz += a2; go += a0 * ox + a1 * oy + a2 * oz; cnt += 1.f;
+      nmax = fmaxf(nmax, ox * ox + oy * oy + oz * oz);
+    }
+  }
+  gx = bred(gx, false); gy = bred(gy, false); gz = bred(gz, false); go = bred(go, false); cnt = bred(cnt, false);
+  nmax = bred(nmax, true);
+  for (int idx = threadIdx.x; idx < HW; idx += blockDim.x) {     // first pixel attaining the maximum norm
+    if (mp[idx] > 0.5f) {
+      const float ox = op[idx * 3], oy = op[idx * 3 + 1], oz = op[idx * 3 + 2];
+      if (ox * ox + oy * oy + oz * oz == nmax) atomicMin(&sj, idx);
+    }
+  }
+  __syncthreads();
+  const int j = sj;
+  const float ds = -go / s;
+  float njx = 0.f, njy = 0.f, njz = 0.f;
+  if (j < HW) {
+    njx = op[j * 3]; njy = op[j * 3 + 1]; njz = op[j * 3 + 2];
+    const float nn = sqrtf(njx * njx + njy * njy + njz * njz);
+    if (nn > 0.f) { njx /= nn; njy /= nn; njz /= nn; }
+  }
+  const float dmx = (-gx / s - ds * njx) / cnt, dmy = (-gy / s - ds * njy) / cnt, dmz = (-gz / s - ds * njz) / cnt;
+  float m[9] = {};
+  for (int idx = threadIdx.x; idx < HW; idx += blockDim.x) {
+    float dd = 0.f;
+    if (mp[idx] > 0.5f) {
+      float dxv = gp[idx * 3] / s + dmx, dyv = gp[idx * 3 + 1] / s + dmy, dzv = gp[idx * 3 + 2] / s + dmz;
+      if (idx == j) { dxv += ds * njx; dyv += ds * njy; dzv += ds * njz; }
+      const float px = (float)(idx % W), py = (float)(idx / W);
+      const float rx = kinv[0] * px + kinv[1] * py + kinv[2], ry = kinv[3] * px + kinv[4] * py + kinv[5],
+                  rz = kinv[6] * px + kinv[7] * py + kinv[8];
+      dd = dxv * rx + dyv * ry + dzv * rz;
+      const float dz = dp[idx];
+      m[0] += dz * dxv * px; m[1] += dz * dxv * py; m[2] += dz * dxv;
+      m[3] += dz * dyv * px; m[4] += dz * dyv * py; m[5] += dz * dyv;
+      m[6] += dz * dzv * px; m[7] += dz * dzv * py; m[8] += dz * dzv;
+    }
+    ddepth[(int64_t)b * HW + idx] = dd;
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const float t = bred(m[q], false);
+    if (threadIdx.x == 0) dKinv[b * 9 + q] = t;
+  }
+}
+
 // ---- AdamW (torch.optim.AdamW semantics, model/shape_engine.py:132) ---------------------------------------------
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
@@ -524,8 +749,22 @@ extern "C" int zs_colsum_f32(const float* A, int lda, int64_t M, int N, float* o
   int64_t slabs = (M + 8 * 64 - 1) / (8 * 64);
   if (slabs > 256) slabs = 256;
   dim3 grid((N + 31) / 32, (unsigned)(slabs > 0 ? slabs : 1));
-  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, M, N, out);
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, nullptr, 0, M, N, out);
   ZS_CUDA_CHECK_LAUNCH("zs_colsum_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_coldot_f32(const float* A, int lda, const float* B2, int ldb, int64_t M, int N, float* out, int accumulate,
+                             void* stream) {
+  ZS_REQUIRE(A && B2 && out && M >= 0 && N > 0 && lda >= N && ldb >= N, "zs_coldot_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  if (!accumulate) ZS_CUDA_CALL(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+  if (M == 0) return ZS_OK;
+  int64_t slabs = (M + 8 * 64 - 1) / (8 * 64);
+  if (slabs > 256) slabs = 256;
+  dim3 grid((N + 31) / 32, (unsigned)(slabs > 0 ? slabs : 1));
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, B2, ldb, M, N, out);
+  ZS_CUDA_CHECK_LAUNCH("zs_coldot_f32");
   return ZS_OK;
 }
 
@@ -579,8 +818,8 @@ extern "C" int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, in
                               void* stream) {
   ZS_REQUIRE(qkv && dO && dqkv && B > 0 && T > 0 && heads > 0 && hd > 0, "zs_mha_bwd_f32: bad args");
   const int nwarps = 8;
-  const size_t smem = sizeof(float) * ((size_t)6 * T * (hd + 1) + (size_t)2 * nwarps * T);
-  ZS_REQUIRE(smem <= 200 * 1024, "zs_mha_bwd_f32: sequence too long for shared memory");
+  const size_t smem = sizeof(float) * ((size_t)4 * T * (hd + 1) + (size_t)2 * nwarps * T + (size_t)2 * nwarps * hd);
+  ZS_REQUIRE(smem <= 227 * 1024, "zs_mha_bwd_f32: sequence too long for shared memory");
   ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mha_bwd_kernel<<<B * heads, nwarps * 32, smem, as_stream(stream)>>>(qkv, dO, dqkv, T, heads, hd, scale);
   ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_f32");
@@ -641,5 +880,46 @@ extern "C" int zs_avgpool_bwd_nhwc_f32(const float* dy, float* dx, int B, int HW
   ZS_REQUIRE(dy && dx && B > 0 && HW > 0 && C > 0, "zs_avgpool_bwd_nhwc_f32: bad args");
   avgpool_bwd_kernel<<<grid_for_n((int64_t)B * HW * C), 256, 0, as_stream(stream)>>>(dy, dx, B, HW, C);
   ZS_CUDA_CHECK_LAUNCH("zs_avgpool_bwd_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_layernorm_bwd_generic_f32(const float* dy, const float* x, const float* gamma, float eps, float* dx, float* xhat,
+                                            int64_t rows, int cols, void* stream) {
+  ZS_REQUIRE(dy && x && dx && rows >= 0 && cols > 0, "zs_layernorm_bwd_generic_f32: bad args");
+  if (rows == 0) return ZS_OK;
+  int64_t g = (rows + 7) / 8;
+  const int cap = sm_count() * 8;
+  layernorm_bwd_generic_kernel<<<(int)(g < cap ? g : cap), 256, 0, as_stream(stream)>>>(dy, x, gamma, eps, dx, xhat, rows, cols);
+  ZS_CUDA_CHECK_LAUNCH("zs_layernorm_bwd_generic_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_groupnorm_bwd_nhwc_f32(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                                         int B, int HW, int C, int groups, float eps, void* stream) {
+  ZS_REQUIRE(dy && x && gamma && dx && dgamma && dbeta && B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0 && C / groups <= 64 &&
+                 512 % (C / groups) == 0,
+             "zs_groupnorm_bwd_nhwc_f32: bad args (channels per group must divide 512 and be at most 64)");
+  groupnorm_bwd_nhwc_kernel<<<B * groups, 512, 0, as_stream(stream)>>>(dy, x, gamma, dx, dgamma, dbeta, HW, C, groups, eps);
+  ZS_CUDA_CHECK_LAUNCH("zs_groupnorm_bwd_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_bilinear_bwd_nhwc_f32(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW, int align_corners,
+                                        void* stream) {
+  ZS_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_bilinear_bwd_nhwc_f32: bad args");
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st));
+  bilinear_bwd_nhwc_kernel<<<grid_for_n((int64_t)B * OH * OW * C), 256, 0, st>>>(dy, dx, B, H, W, C, OH, OW, align_corners);
+  ZS_CUDA_CHECK_LAUNCH("zs_bilinear_bwd_nhwc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_unproject_normalize_bwd_f32(const float* depth, const float* mask, const float* K, const float* seen_points,
+                                              const float* scale, const float* dseen, float* ddepth, float* dKinv, int B, int H, int W,
+                                              void* stream) {
+  ZS_REQUIRE(depth && mask && K && seen_points && scale && dseen && ddepth && dKinv && B > 0 && H > 0 && W > 0,
+             "zs_unproject_normalize_bwd_f32: bad args");
+  unproject_normalize_bwd_kernel<<<B, 1024, 0, as_stream(stream)>>>(depth, mask, K, seen_points, scale, dseen, ddepth, dKinv, H, W);
+  ZS_CUDA_CHECK_LAUNCH("zs_unproject_normalize_bwd_f32");
   return ZS_OK;
 }

@@ -9,9 +9,9 @@ math runs in libzeroshape_b200.so.
 Training, decoder slice: with a GT batch (`gt_sample_points`, `gt_sample_sdf`,
 `depth_input_map`, `intr`, `pose_gt`) the forward also fills seen_points_gt / gt_points_cam / gt_surf_points /
 pred_sample_occ (graph_shape.py:155-185) and `compute_loss` returns the shape (BCE) and intrinsics losses
-(utils/loss.py:18-41).  Gradients exist for the seen-surface encoder (coord_encoder) and the implicit decoder (impl_network), i.e. the
-`optim.fix_dpt` configuration; the depth estimator (dpt_depth / intr_head / intr_proj) runs on the inference kernels, so
-its parameters must be frozen in train mode -- otherwise the forward raises instead of silently training a different model.  The MiDaS depth loss (model/depth/midas_loss.py)
+(utils/loss.py:18-41).  Gradients exist for every module: with `optim.fix_dpt` the depth estimator runs on the inference kernels and only
+coord_encoder + impl_network train; otherwise the whole encoder side runs on one tape (model/depth/dpt_train.py) and the
+shape loss reaches dpt_depth / intr_head / intr_proj through the unprojected, normalised seen surface.  The MiDaS depth loss (model/depth/midas_loss.py)
 belongs to the depth-engine row and raises.
 """
 import torch
@@ -77,36 +77,43 @@ class Graph(nn.Module):
         return ops.intr_param2mtx(intr_params.float().contiguous(), opt.H, opt.W)
 
     def forward(self, opt, var, training=False, get_loss=True):
-        if training and torch.is_grad_enabled():
-            enc = [n for m_name in ("dpt_depth", "intr_head", "intr_proj")
-                   for n, p in getattr(self, m_name).named_parameters() if p.requires_grad]
-            if enc:
-                raise NotImplementedError(
-                    "zeroshape_b200 Graph: backward exists for coord_encoder and impl_network (the optim.fix_dpt configuration); "
-                    f"the depth estimator has none in this revision -- {len(enc)} parameters of dpt_depth / intr_head / intr_proj "
-                    "still require grad (construct the Graph with opt.optim.fix_dpt = True)")
         batch_size = len(var.idx)
-        with torch.no_grad():
+        depth_params = [p for m in (self.dpt_depth, self.intr_head, self.intr_proj) for p in m.parameters()]
+        full_train = training and torch.is_grad_enabled() and any(p.requires_grad for p in depth_params)
+        if full_train:
+            # default options/shape.yaml (fix_dpt: false): the shape loss reaches the depth estimator through the seen surface.
+            # One tape from the image to latent_depth (model/depth/dpt_train.py), hand-written backward for every layer.
+            if not self.coord_encoder.training:
+                raise NotImplementedError("zeroshape_b200 Graph: training the depth estimator with the seen-surface encoder in "
+                                          "eval mode is not supported (call graph.train())")
+            from ..depth.dpt_train import EncoderTrainFn
+            enc_params = depth_params + list(self.coord_encoder.parameters())
             var.latent_semantic = None
-            var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
-            feat = self.dpt_depth.last_feat_nhwc                                   # layer_4 [B,7,7,768] NHWC
-            cache = self.dpt_depth._cache                                          # intr head shares the pack cache policy
-            if not hasattr(self, "_intr_cache"):
-                from ...packing import PackCache
-                self._intr_cache = PackCache(self.intr_head)
-            self._intr_cache.refresh()
-            f = self.intr_head[0].run_nhwc(feat, self._intr_cache, "h0")
-            f = self.intr_head[1].run_nhwc(f, self._intr_cache, "h1")
-            intr_params = ops.linear(ops.avgpool_nhwc(f), self.intr_proj.weight, self.intr_proj.bias)
-            var.intr_pred = self.intr_param2mtx(opt, intr_params)
             mask = var.mask_input_map.float().contiguous()
             var.validity_mask = (mask > 0.5).float().view(batch_size, -1)
-            # unproject + masked mean / max-norm + normalise + zero background: one launch, no host sync
-            var.seen_points, self.last_mean, self.last_scale = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
-            # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
-            coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
-            if not self.coord_encoder.training:
-                var.latent_depth = self.coord_encoder.forward_nhwc(coord)
+            var.depth_pred, var.intr_pred, var.seen_points, var.latent_depth = EncoderTrainFn.apply(
+                self, opt, var.rgb_input_map, mask, *enc_params)
+        with torch.no_grad():
+            if not full_train:
+                var.latent_semantic = None
+                var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
+                feat = self.dpt_depth.last_feat_nhwc                                   # layer_4 [B,7,7,768] NHWC
+                if not hasattr(self, "_intr_cache"):
+                    from ...packing import PackCache
+                    self._intr_cache = PackCache(self.intr_head)
+                self._intr_cache.refresh()
+                f = self.intr_head[0].run_nhwc(feat, self._intr_cache, "h0")
+                f = self.intr_head[1].run_nhwc(f, self._intr_cache, "h1")
+                intr_params = ops.linear(ops.avgpool_nhwc(f), self.intr_proj.weight, self.intr_proj.bias)
+                var.intr_pred = self.intr_param2mtx(opt, intr_params)
+                mask = var.mask_input_map.float().contiguous()
+                var.validity_mask = (mask > 0.5).float().view(batch_size, -1)
+                # unproject + masked mean / max-norm + normalise + zero background: one launch, no host sync
+                var.seen_points, self.last_mean, self.last_scale = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
+                # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
+                coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
+                if not self.coord_encoder.training:
+                    var.latent_depth = self.coord_encoder.forward_nhwc(coord)
             var.pose = var.pose_gt if "pose_gt" in var else False
             if "gt_sample_points" in var and "gt_sample_sdf" in var:
                 # graph_shape.py:157-182: normalising factors from the GT seen surface, GT points -> camera frame -> normalised
@@ -117,7 +124,7 @@ class Graph(nn.Module):
                 var.gt_points_cam = ((cam - self.gt_mean.unsqueeze(1)) / self.gt_scale.view(-1, 1, 1)).contiguous()
                 idx = torch.topk(var.gt_sample_sdf.abs(), k=min(100, var.gt_sample_sdf.shape[1]), dim=1, largest=False)[1]
                 var.gt_surf_points = torch.gather(var.gt_points_cam, 1, idx.unsqueeze(-1).repeat(1, 1, 3))
-        if self.coord_encoder.training:
+        if self.coord_encoder.training and not full_train:
             # train mode: batch-statistics BatchNorm, differentiable w.r.t. the encoder parameters (seen_coord_enc_train.py)
             var.latent_depth = self.coord_encoder.forward_nhwc(coord)
         if "gt_sample_points" in var and "gt_sample_sdf" in var:

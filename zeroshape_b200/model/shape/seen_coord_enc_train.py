@@ -116,8 +116,8 @@ def train_forward(mod, coord_nhwc):
     return out, T
 
 
-def train_backward(mod, T, dout):
-    """dout [B,197,latent] -> _Grads over the encoder parameters (no gradient w.r.t. the input coordinates is produced)."""
+def train_backward(mod, T, dout, need_dcoord=False):
+    """dout [B,197,latent] -> _Grads over the encoder parameters (and, on request, the gradient w.r.t. the input coordinates)."""
     enc = mod.encoder
     G = _Grads()
     B = dout.shape[0]
@@ -161,8 +161,8 @@ def train_backward(mod, T, dout):
         if li == 4 and down:
             dx = ops.axpby(dx, 1.0, dfeat3_local, 1.0)
     dx = ops.maxpool3x3s2_bwd_nhwc(T["pool_in"], dx, 1, 1)
-    _unit_bwd(U.pop(), dx, G, need_dx=False)
-    return G
+    dcoord, _ = _unit_bwd(U.pop(), dx, G, need_dx=need_dcoord)
+    return (G, dcoord) if need_dcoord else G
 
 
 class CoordEncTrainFn(torch.autograd.Function):

@@ -736,3 +736,61 @@ def avgpool_bwd_nhwc(dy, H, W):
     dx = torch.empty(B, H, W, C, device=dy.device, dtype=torch.float32)
     check(lib.zs_avgpool_bwd_nhwc_f32(_p(dy), _p(dx), B, H * W, C, _stream()), "zs_avgpool_bwd_nhwc_f32")
     return dx
+
+
+def coldot(a, b, out=None, accumulate=False):
+    """out[N] (+)= sum_m a[m,n] * b[m,n]."""
+    assert a.shape == b.shape and a.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, N = a.shape
+    if out is None:
+        out = torch.empty(N, device=a.device, dtype=torch.float32)
+        accumulate = False
+    check(lib.zs_coldot_f32(_p(a), a.stride(0), _p(b), b.stride(0), M, N, _p(out), int(accumulate), _stream()), "zs_coldot_f32")
+    return out
+
+
+def layernorm_bwd_generic(dy, x, gamma, eps, dgamma=None, dbeta=None):
+    """LayerNorm backward over the last dim of any width; dgamma / dbeta accumulated into when given."""
+    _chk(dy, "dy"); _chk(x, "x"); _chk(gamma, "gamma")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    xhat = torch.empty_like(x) if dgamma is not None else None
+    check(lib.zs_layernorm_bwd_generic_f32(_p(dy), _p(x), _p(gamma), eps, _p(dx), _p(xhat), rows, C, _stream()),
+          "zs_layernorm_bwd_generic_f32")
+    if dgamma is not None:
+        coldot(dy.view(rows, C), xhat.view(rows, C), out=dgamma, accumulate=True)
+        colsum(dy.view(rows, C), out=dbeta, accumulate=True)
+    return dx
+
+
+def groupnorm_bwd_nhwc(dy, x, gamma, groups, eps, dgamma, dbeta):
+    for t, n in ((dy, "dy"), (x, "x"), (gamma, "gamma"), (dgamma, "dgamma"), (dbeta, "dbeta")):
+        _chk(t, n)
+    B, H, W, C = x.shape
+    dx = torch.empty_like(x)
+    check(lib.zs_groupnorm_bwd_nhwc_f32(_p(dy), _p(x), _p(gamma), _p(dx), _p(dgamma), _p(dbeta), B, H * W, C, groups, eps, _stream()),
+          "zs_groupnorm_bwd_nhwc_f32")
+    return dx
+
+
+def bilinear_bwd_nhwc(dy, H, W, align_corners):
+    _chk(dy, "dy")
+    B, OH, OW, C = dy.shape
+    dx = torch.empty(B, H, W, C, device=dy.device, dtype=torch.float32)
+    check(lib.zs_bilinear_bwd_nhwc_f32(_p(dy), _p(dx), B, H, W, C, OH, OW, int(align_corners), _stream()), "zs_bilinear_bwd_nhwc_f32")
+    return dx
+
+
+def unproject_normalize_bwd(depth, mask, K, seen_points, scale, dseen):
+    """-> ddepth [B,1,H,W], dKinv [B,3,3] (gradient w.r.t. inverse(K))."""
+    depth = depth.contiguous(); mask = mask.contiguous().float(); K = K.contiguous(); dseen = dseen.contiguous()
+    for t, n in ((depth, "depth"), (mask, "mask"), (K, "K"), (seen_points, "seen_points"), (scale, "scale"), (dseen, "dseen")):
+        _chk(t, n)
+    B = depth.shape[0]
+    H, W = depth.shape[-2:]
+    dd = torch.empty(B, 1, H, W, device=depth.device, dtype=torch.float32)
+    dk = torch.empty(B, 3, 3, device=depth.device, dtype=torch.float32)
+    check(lib.zs_unproject_normalize_bwd_f32(_p(depth), _p(mask), _p(K), _p(seen_points), _p(scale), _p(dseen), _p(dd), _p(dk), B, H, W,
+                                             _stream()), "zs_unproject_normalize_bwd_f32")
+    return dd, dk
