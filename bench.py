@@ -312,6 +312,67 @@ def run_train_decoder(args, rank, world, dev):
             "approx_tflops": flop / (ms * 1e-3) / 1e12, "last_loss": last, "gpu_launches": int(lib.zs_launch_count() - l0)}
 
 
+def run_train(args, rank, world, dev):
+    """BASELINE.json config 3: one train_iteration of options/shape.yaml (fix_dpt false, shape loss only) = Graph.forward(training=True)
+    on B synthetic images + 4096 GT sample points each, BCE loss, backward through decoder / seen-surface encoder / geometry glue /
+    intrinsics head / DPT-hybrid depth estimator, AdamW(0.9, 0.95) step.  fp32 kernels (csrc/train.cu, csrc/gemm_simt.cu).
+    tokens := B x (197 ViT tokens + 197 latent tokens + 4096 query points) per step."""
+    import torch
+    from zeroshape_b200._native import lib
+    from zeroshape_b200.model.compute_graph.graph_shape import Graph
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    from zeroshape_b200.utils.util import EasyDict
+    B, N = args.train_batch, 4096
+    opt = make_opt(dev, 128)
+    opt.loss_weight = EasyDict(depth=None, intr=None, shape=1)
+    opt.training = EasyDict(shape_loss=EasyDict(impt_thres=0.01, impt_weight=1))
+    torch.manual_seed(0)
+    graph = Graph(opt).to(dev).train()
+    with torch.no_grad():
+        graph.intr_proj.weight.normal_(0, 0.02)        # the reference's zero init would cut the intrinsics path out of the step
+    trainable = [p for p in graph.parameters() if p.requires_grad]
+    optim = FusedAdamW(trainable, lr=3e-5, betas=(0.9, 0.95), weight_decay=0.05)
+    rgb_h, mask_h = synthetic_images(B, 2000 + rank)
+    g = torch.Generator().manual_seed(3)
+    depth_h = (1.5 + 0.3 * torch.rand(B, 1, 224, 224, generator=g)) * mask_h
+    intr_h = torch.tensor([[1.3875 * 224, 0, 112], [0, 1.3875 * 224, 112], [0, 0, 1.0]]).repeat(B, 1, 1)
+    pose_h = torch.cat([torch.eye(3), torch.tensor([[0.0], [0.0], [1.6]])], dim=1).repeat(B, 1, 1)
+    pts_h = torch.rand(B, N, 3, generator=g) - 0.5
+    sdf_h = pts_h.norm(dim=-1) - 0.3 - 0.003
+    host = [t.pin_memory() for t in (rgb_h, mask_h, depth_h, intr_h, pose_h, pts_h, sdf_h)]
+
+    def step():
+        rgb, mask, depth, intr, pose, pts, sdf = (t.to(dev, non_blocking=True) for t in host)
+        var = EasyDict(idx=torch.arange(B), rgb_input_map=rgb, mask_input_map=mask, depth_input_map=depth, intr=intr, pose_gt=pose,
+                       gt_sample_points=pts, gt_sample_sdf=sdf)
+        var, loss = graph.forward(opt, var, training=True)
+        optim.zero_grad()
+        loss.shape.backward()
+        optim.step()
+        return loss.shape
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    l0 = lib.zs_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step()
+    last = float(loss.item())
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    tokens = B * (197 + 197 + N)
+    return {"metric": "train step tokens/s (options/shape.yaml, fwd+loss+bwd+AdamW)", "value": tokens / (ms * 1e-3), "unit": "tokens/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
+            "dtype": "f32", "data": "synthetic", "images_per_s": B / (ms * 1e-3),
+            "config": {"workload": f"BASELINE config 3: train_iteration, batch {B} synthetic images x {N} GT points, fix_dpt false, shape loss only; "
+                                   "tokens = B x (197 + 197 + 4096)", "train_batch": B},
+            "trainable_parameters": int(sum(p.numel() for p in trainable)), "last_loss": last,
+            "gpu_launches": int(lib.zs_launch_count() - l0),
+            "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
 def cpu_reference_shapes_per_s(vox_res, slices, threads=None):
     """The reference algorithm on host cores (oracle restatement: same op sequence as the reference's
     PyTorch-CPU path): full encoder forward once, Implicit over `slices` x-slices of the (vox_res+1)^3
@@ -402,8 +463,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vox-res", type=int, default=128)
     ap.add_argument("--shapes", type=int, default=8, help="shapes per GPU per step (SURVEY.md section 8d: B = 8 images in flight)")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train-decoder"],
-                    help="train-decoder: time the decoder training step (row a13 slice) instead of the headline metric")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "train-decoder"],
+                    help="train: BASELINE config 3 (full train_iteration, fwd + loss + bwd + AdamW); train-decoder: decoder slice only")
     ap.add_argument("--train-batch", type=int, default=32, help="images per training step (options/shape.yaml batch 28-32)")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
@@ -432,8 +493,8 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    if args.mode == "train-decoder":
-        line = run_train_decoder(args, rank, world, dev)
+    if args.mode in ("train", "train-decoder"):
+        line = (run_train if args.mode == "train" else run_train_decoder)(args, rank, world, dev)
         if rank == 0:
             _emit(line, real_stdout)
         return
