@@ -312,6 +312,71 @@ def run_train_decoder(args, rank, world, dev):
             "approx_tflops": flop / (ms * 1e-3) / 1e12, "last_loss": last, "gpu_launches": int(lib.zs_launch_count() - l0)}
 
 
+def run_eval(args, rank, world, dev):
+    """BASELINE.json config 5: evaluate.py on a synthetic set -- per shape (batch 1, as model/shape_engine.py:380-386 requires):
+    full forward, 129^3 grid, marching cubes, 10k-point sample, Chamfer + F-score (utils/eval_3D.py:104-138; --brute-force adds the
+    6912-rotation search of :140-207); shapes are sharded over the ranks like the reference's DistributedSampler and the per-shape
+    metrics are all_gathered at the end (shape_engine.py:413-429)."""
+    import torch
+    import torch.distributed as dist
+    from zeroshape_b200._native import lib
+    from zeroshape_b200.model.compute_graph.graph_shape import Graph
+    from zeroshape_b200.parallel import gather_metrics
+    from zeroshape_b200.utils import eval_3D
+    from zeroshape_b200.utils.util import EasyDict
+    opt = make_opt(dev, args.vox_res)
+    opt.eval.brute_force = bool(args.brute_force)
+    torch.manual_seed(0)
+    graph = Graph(opt).to(dev).eval()
+    net = graph.impl_network
+    with torch.no_grad():
+        rgb0, mask0 = synthetic_images(1, 999)
+        var = graph.forward(opt, EasyDict(idx=torch.arange(1), rgb_input_map=rgb0.to(dev), mask_input_map=mask0.to(dev), pose_gt=False),
+                            training=False, get_loss=False)
+        lg, _ = net(var.latent_depth, None, torch.rand(1, 8192, 3, device=dev) * 3 - 1.5, need_attn=False)
+        net.impl_mlp.layers[-1].bias -= lg.median()          # non-empty iso-surface for the random-init field (SURVEY.md 8d)
+    n_local = args.eval_shapes // world
+    pose = torch.cat([torch.eye(3), torch.zeros(3, 1)], dim=1).unsqueeze(0).to(dev)
+
+    def one(seed):
+        rgb, mask = synthetic_images(1, seed)
+        g = torch.Generator().manual_seed(seed)
+        d = torch.randn(10000, 3, generator=g)
+        gt = (d / d.norm(dim=1, keepdim=True)) * (0.3 + 0.4 * torch.rand(3, generator=g))       # points on a seed-dependent ellipsoid
+        var = EasyDict(idx=torch.arange(1), rgb_input_map=rgb.to(dev, non_blocking=True), mask_input_map=mask.to(dev, non_blocking=True),
+                       pose_gt=pose, dpc=EasyDict(points=gt.unsqueeze(0).to(dev, non_blocking=True)), category_label=torch.tensor([seed % 15]))
+        var = graph.forward(opt, var, training=False, get_loss=False)
+        eval_3D.eval_metrics(opt, var, net)
+        return torch.cat([var.cd_acc.view(1, 1), var.cd_comp.view(1, 1), var.f_score.view(1, -1)], dim=1)
+    with torch.no_grad():
+        for s in range(3):
+            one(10_000 + s)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = lib.zs_launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        rows = [one(rank * n_local + i) for i in range(n_local)]
+        allm = gather_metrics(torch.cat(rows, dim=0))
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    total = n_local * world
+    return {"metric": "evaluate.py shapes/s (forward + 129^3 grid + mesh + 10k sample + Chamfer/F-score%s)" % (", brute-force pose search" if args.brute_force else ""),
+            "value": total / (ms * 1e-3), "unit": "shapes/s", "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "dtype": "bf16x3->f32acc", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: {total} synthetic shapes, eval batch 1, vox_res {args.vox_res}, sharded over {world} GPU(s), "
+                                   "metric all_gather at the end", "brute_force": bool(args.brute_force)},
+            "mean_cd": float((allm[:, 0].mean() + allm[:, 1].mean()).item() / 2), "gathered_rows": int(allm.shape[0]),
+            "gpu_launches": int(lib.zs_launch_count() - l0)}
+
+
 def run_train(args, rank, world, dev):
     """BASELINE.json config 3: one train_iteration of options/shape.yaml (fix_dpt false, shape loss only) = Graph.forward(training=True)
     on B synthetic images + 4096 GT sample points each, BCE loss, backward through decoder / seen-surface encoder / geometry glue /
@@ -463,8 +528,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vox-res", type=int, default=128)
     ap.add_argument("--shapes", type=int, default=8, help="shapes per GPU per step (SURVEY.md section 8d: B = 8 images in flight)")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train", "train-decoder"],
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "train-decoder", "eval"],
                     help="train: BASELINE config 3 (full train_iteration, fwd + loss + bwd + AdamW); train-decoder: decoder slice only")
+    ap.add_argument("--eval-shapes", type=int, default=256, help="mode eval: size of the synthetic evaluation set (all ranks together)")
+    ap.add_argument("--brute-force", action="store_true", help="mode eval: the 6912-rotation pose search of evaluate.py (README protocol)")
     ap.add_argument("--train-batch", type=int, default=32, help="images per training step (options/shape.yaml batch 28-32)")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
@@ -493,8 +560,8 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    if args.mode in ("train", "train-decoder"):
-        line = (run_train if args.mode == "train" else run_train_decoder)(args, rank, world, dev)
+    if args.mode in ("train", "train-decoder", "eval"):
+        line = {"train": run_train, "train-decoder": run_train_decoder, "eval": run_eval}[args.mode](args, rank, world, dev)
         if rank == 0:
             _emit(line, real_stdout)
         return

@@ -93,7 +93,10 @@ class Implicit(nn.Module):
         self.attention = "fused"      # point attention: "fused" (one flash-style tcgen05 kernel) | "tc" (two grouped tcgen05 launches) | "f32" (FFMA kernel)
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
-        self.point_chunk = 1 << 18    # query points per pass of the per-layer / chained engines (bounds scratch memory)
+        # query points per pass of the per-layer / chained engines (bounds scratch memory: ~5 KB per point).  One pass over a whole
+        # 129^3 grid (2.15 M points, 11 GB) instead of 9 slice-aligned passes: persistent kernels lose the partial last wave and the
+        # pipeline fill/drain once per LAUNCH (1950 tiles = 13.2 waves per pass cost 14; a single pass of 16771 tiles = 113.3 costs 114)
+        self.point_chunk = 1 << 22
         self._packed = None           # (version key, packed weight blob) for the fused engine
         self.initialize_weights()
 
