@@ -250,6 +250,9 @@ int zs_unproject_normalize_bwd_f32(const float* depth, const float* mask, const 
 /* debug: effective SM clock in MHz at this point of the stream (one-thread spin kernel, ~10 us). */
 int zs_debug_clock_mhz(float* out, void* stream);
 
+/* out[A,N] = mean over the middle axis of x[A,M,N] (Z-mean of the attention maps, utils/eval_3D.py:47-52). */
+int zs_mean_axis1_f32(const float* x, float* out, int64_t A, int M, int N, void* stream);
+
 /* LinearProj3D (model/shape/implicit.py:128-131): out[M,C] = points[M,3] W[C,3]^T + bias.  Output-bandwidth bound. */
 int zs_point_proj_f32(const float* points, int64_t M, const float* W, const float* bias, float* out, int C, void* stream);
 

@@ -175,3 +175,33 @@ def test_eval_metrics_default_end_to_end(cuda):
     assert abs(np.sqrt(d1).mean() - acc.item()) < 0.15 * acc.item()
     assert abs(np.sqrt(d2).mean() - comp.item()) < 0.15 * comp.item()
     assert var.f_score.shape == (1, 6) and var.cd_acc.shape == (1,)
+
+
+def test_attention_movie_matches_oracle_zmean(cuda):
+    """compute_level_grid(vis_attn=True) (utils/eval_3D.py:47-80): the Z-averaged, head/layer-averaged attention of the columns
+    the movie shows equals the oracle's attention maps reduced the reference's way; frames have the reference's count/shape."""
+    from oracle.implicit import implicit_forward, implicit_init
+    from oracle import eval3d as E
+    from zeroshape_b200.model.shape.implicit import Implicit
+    from zeroshape_b200.utils import eval_3D
+    from zeroshape_b200.utils.util import EasyDict
+    sd = implicit_init(seed=31)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6], pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    n = 17
+    g = torch.Generator().manual_seed(32)
+    lat = torch.randn(1, 197, 256, generator=g)
+    pts = E.dense_grid(n, -1.5, 1.5)                                    # [1,n,n,n,3]
+    with torch.no_grad():
+        _, attn = implicit_forward(sd, lat, pts.view(1, -1, 3))
+    ref = attn.view(1, n, n, n, 197).mean(dim=3)
+    ref = (ref[..., :1] + ref[..., 1:])[:, ::8][:, :, ::8]              # [1,3,3,196]
+    got, idx = eval_3D.attention_maps_zmean(m, lat.to(cuda), pts.to(cuda))
+    assert idx.tolist() == [0, 8, 16]
+    assert (got.cpu() - ref).abs().max().item() < 2e-6
+    opt = EasyDict(H=224, W=224, arch=dict(win_size=16))
+    img = torch.rand(1, 3, 224, 224, generator=g)
+    occ, frames = eval_3D.compute_level_grid(opt, m, lat.to(cuda), None, pts.to(cuda), img.to(cuda), vis_attn=True)
+    assert occ.shape == (1, n, n, n) and len(frames) == 1 and len(frames[0]) == 9
+    assert frames[0][0].shape == (224, 224, 3) and 0.0 <= frames[0][0].min() and frames[0][0].max() <= 1.0

@@ -416,3 +416,28 @@ extern "C" int zs_debug_clock_mhz(float* out, void* stream) {
   ZS_CUDA_CHECK_LAUNCH("zs_debug_clock_mhz");
   return ZS_OK;
 }
+
+// ---- out[a, n] = mean_m x[a, m, n]  (Z-mean of the attention maps for the attention movie, utils/eval_3D.py:47-52) ----
+namespace zs {
+__global__ void mean_axis1_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t A, int M, int N) {
+  const int64_t total = A * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = i / N;
+    const int n = (int)(i % N);
+    const float* p = x + a * (int64_t)M * N + n;
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += p[(int64_t)m * N];
+    out[i] = s / (float)M;
+  }
+}
+}  // namespace zs
+
+extern "C" int zs_mean_axis1_f32(const float* x, float* out, int64_t A, int M, int N, void* stream) {
+  ZS_REQUIRE(x && out && A >= 0 && M > 0 && N > 0, "zs_mean_axis1_f32: bad args");
+  if (A == 0) return ZS_OK;
+  int64_t blocks = (A * N + 255) / 256;
+  int maxb = zs::sm_count() * 16;
+  zs::mean_axis1_kernel<<<(int)(blocks < maxb ? blocks : maxb), 256, 0, zs::as_stream(stream)>>>(x, out, A, M, N);
+  ZS_CUDA_CHECK_LAUNCH("zs_mean_axis1_f32");
+  return ZS_OK;
+}

@@ -794,3 +794,12 @@ def unproject_normalize_bwd(depth, mask, K, seen_points, scale, dseen):
     check(lib.zs_unproject_normalize_bwd_f32(_p(depth), _p(mask), _p(K), _p(seen_points), _p(scale), _p(dseen), _p(dd), _p(dk), B, H, W,
                                              _stream()), "zs_unproject_normalize_bwd_f32")
     return dd, dk
+
+
+def mean_axis1(x):
+    """x [A,M,N] -> [A,N] mean over the middle axis."""
+    _chk(x, "x")
+    A, M, N = x.shape
+    out = torch.empty(A, N, device=x.device, dtype=torch.float32)
+    check(lib.zs_mean_axis1_f32(_p(x), _p(out), A, M, N, _stream()), "zs_mean_axis1_f32")
+    return out

@@ -93,20 +93,66 @@ def _grid_from_points(points_3D):
 def compute_level_grid(opt, impl_network, latent_depth, latent_semantic, points_3D, images, vis_attn=False):
     """-> (occ [B,n,n,n] = sigmoid(logit), None).  One latent-side pass per image + one fused grid
     pass instead of the reference's n sequential slices."""
-    if vis_attn:
-        raise NotImplementedError("attention movie (utils/eval_3D.py:47-80) is out of scope (SURVEY.md 8f rank 2)")
     latent_depth = latent_depth.to(torch.float32)
     B, n = points_3D.shape[0], points_3D.shape[1]
     assert n == points_3D.shape[2] == points_3D.shape[3] and points_3D.shape[4] == 3
+    frames = attention_movie(opt, impl_network, latent_depth, points_3D, images) if vis_attn else None
     if hasattr(impl_network, "grid_occupancy"):
         check_n, rmin, rmax = _grid_from_points(points_3D)
         ref = ops.dense_grid(n, rmin, rmax, 0, n, points_3D.device)
         if torch.equal(ref, points_3D[0]):
-            return impl_network.grid_occupancy(latent_depth, n, rmin, rmax, 0, n, sigmoid=True), None
+            return impl_network.grid_occupancy(latent_depth, n, rmin, rmax, 0, n, sigmoid=True), frames
     # arbitrary point sets / foreign networks: slice loop like the reference
     pts = points_3D.view(B, n, n * n, 3)
     occ = torch.stack([impl_network(latent_depth, latent_semantic, pts[:, i])[0] for i in range(n)], dim=1)
-    return torch.sigmoid(occ.view(B, n, n, n)), None
+    return torch.sigmoid(occ.view(B, n, n, n)), frames
+
+
+def attention_maps_zmean(impl_network, latent_depth, points_3D, step=8):
+    """Head- and layer-averaged attention of the query columns the movie shows, averaged along Z (utils/eval_3D.py:47-56):
+    -> [B, K, K, feat_res**2] for the K = len(range(0, n, step)) x K columns (x, y) at multiples of `step`, global token folded in.
+    The reference keeps the attention map of EVERY grid point (1.7 GB per sample at 129^3) and then looks at 289 columns only;
+    here only those columns are evaluated (37 k of 2.1 M points)."""
+    B, n = points_3D.shape[0], points_3D.shape[1]
+    idx = torch.arange(0, n, step, device=points_3D.device)
+    K = idx.numel()
+    sel = points_3D.index_select(1, idx).index_select(2, idx).reshape(B, K * K * n, 3).float().contiguous()
+    _, attn = impl_network(latent_depth, None, sel, need_attn=True)             # [B, K*K*n, L]
+    L = attn.shape[-1]
+    zmean = ops.mean_axis1(attn.reshape(B * K * K, n, L).contiguous()).view(B, K, K, L)
+    return (zmean[..., :1] + zmean[..., 1:]).contiguous(), idx
+
+
+def attention_movie(opt, impl_network, latent_depth, points_3D, images, step=8):
+    """The frame lists of compute_level_grid(vis_attn=True) (utils/eval_3D.py:57-80): per sample a serpentine walk over the
+    (x, y) columns at multiples of 8, each frame = the image with the Z-averaged attention heat map."""
+    import numpy as np
+    B, n = points_3D.shape[0], points_3D.shape[1]
+    feat_res = opt.H // opt.arch.win_size
+    att, idx = attention_maps_zmean(impl_network, latent_depth, points_3D, step)      # [B,K,K,feat_res^2]
+    K = idx.numel()
+    maps = ops.bilinear_nhwc(att.view(B * K * K, feat_res, feat_res, 1).contiguous(), opt.H, opt.W, False).view(B, K, K, opt.H, opt.W)
+    maps = (maps / maps.amax(dim=(-1, -2), keepdim=True)).cpu().numpy()
+    out = []
+    for b in range(B):
+        image = images[b].permute(1, 2, 0).cpu().numpy()
+        seq = []
+        for row in range(0, n, step):
+            cols = range(0, n // step * step + 1, step) if row % (2 * step) == 0 else range(n // step * step, -1, -step)
+            for col in cols:
+                seq.append(show_att_on_image(image, maps[b, col // step, row // step]))
+        out.append(seq)
+    return out
+
+
+def show_att_on_image(img, mask):
+    """utils/util_vis.py:267-292: JET heat map of the attention added onto the image, renormalised (visualisation, host code)."""
+    import numpy as np
+    import cv2
+    assert np.max(img) <= 1 and np.max(mask) <= 1
+    heat = cv2.cvtColor(cv2.applyColorMap(np.uint8(255 * mask), cv2.COLORMAP_JET), cv2.COLOR_BGR2RGB)
+    merged = np.float32(heat) / 255 + np.float32(img)
+    return merged / np.max(merged)
 
 
 @torch.no_grad()
