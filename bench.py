@@ -272,6 +272,8 @@ def run_train_decoder(args, rank, world, dev):
     from zeroshape_b200.model.shape.implicit import Implicit
     from zeroshape_b200.model.shape.implicit_train import FusedAdamW
     from zeroshape_b200.utils.loss import Loss
+    from zeroshape_b200 import ops
+    ops.TRAIN_ENGINE, ops.TRAIN_PRECISION = args.train_engine, args.train_precision
     B, N = args.train_batch, 4096
     torch.manual_seed(0)
     net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
@@ -306,7 +308,7 @@ def run_train_decoder(args, rank, world, dev):
     flop = 3 * FLOP_PER_POINT * B * N          # fwd + dgrad + wgrad of the per-point work
     return {"metric": "decoder training step (Implicit fwd + BCE + bwd + AdamW), query points/s", "value": B * N / (ms * 1e-3),
             "unit": "points/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "dtype": ("f32" if args.train_engine == "f32" else ("bf16 (fp32 accumulate, fp32 master weights)" if args.train_precision == "bf16" else "bf16x3->f32acc")), "data": "synthetic",
             "config": {"workload": f"row a13 decoder slice: {B} images x {N} GT sample points, latents given, fp32 kernels (csrc/train.cu)",
                        "train_batch": B, "points_per_image": N},
             "approx_tflops": flop / (ms * 1e-3) / 1e12, "last_loss": last, "gpu_launches": int(lib.zs_launch_count() - l0)}
@@ -380,13 +382,16 @@ def run_eval(args, rank, world, dev):
 def run_train(args, rank, world, dev):
     """BASELINE.json config 3: one train_iteration of options/shape.yaml (fix_dpt false, shape loss only) = Graph.forward(training=True)
     on B synthetic images + 4096 GT sample points each, BCE loss, backward through decoder / seen-surface encoder / geometry glue /
-    intrinsics head / DPT-hybrid depth estimator, AdamW(0.9, 0.95) step.  fp32 kernels (csrc/train.cu, csrc/gemm_simt.cu).
+    intrinsics head / DPT-hybrid depth estimator, AdamW(0.9, 0.95) step.  GEMM-shaped work (forward, dgrad, wgrad of every linear / conv) on the tcgen05 kernels
+    (csrc/gemm_tc.cu, csrc/gemm_tn_tc.cu; --train-engine f32 = the FFMA kernels), everything else csrc/train.cu.
     tokens := B x (197 ViT tokens + 197 latent tokens + 4096 query points) per step."""
     import torch
     from zeroshape_b200._native import lib
     from zeroshape_b200.model.compute_graph.graph_shape import Graph
     from zeroshape_b200.model.shape.implicit_train import FusedAdamW
     from zeroshape_b200.utils.util import EasyDict
+    from zeroshape_b200 import ops
+    ops.TRAIN_ENGINE, ops.TRAIN_PRECISION = args.train_engine, args.train_precision
     B, N = args.train_batch, 4096
     opt = make_opt(dev, 128)
     opt.loss_weight = EasyDict(depth=None, intr=None, shape=1)
@@ -419,6 +424,8 @@ def run_train(args, rank, world, dev):
         step()
     torch.cuda.synchronize()
     l0 = lib.zs_launch_count()
+    if args.profile_region:
+        torch.cuda.profiler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -426,13 +433,16 @@ def run_train(args, rank, world, dev):
     last = float(loss.item())
     t1.record()
     torch.cuda.synchronize()
+    if args.profile_region:
+        torch.cuda.profiler.stop()
     ms = t0.elapsed_time(t1) / args.steps
     tokens = B * (197 + 197 + N)
     return {"metric": "train step tokens/s (options/shape.yaml, fwd+loss+bwd+AdamW)", "value": tokens / (ms * 1e-3), "unit": "tokens/s",
             "n_gpus": 1, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True,
-            "dtype": "f32", "data": "synthetic", "images_per_s": B / (ms * 1e-3),
+            "dtype": ("f32" if args.train_engine == "f32" else ("bf16 (fp32 accumulate, fp32 master weights)" if args.train_precision == "bf16" else "bf16x3->f32acc")), "data": "synthetic", "images_per_s": B / (ms * 1e-3),
             "config": {"workload": f"BASELINE config 3: train_iteration, batch {B} synthetic images x {N} GT points, fix_dpt false, shape loss only; "
-                                   "tokens = B x (197 + 197 + 4096)", "train_batch": B},
+                                   "tokens = B x (197 + 197 + 4096)", "train_batch": B, "train_engine": args.train_engine,
+                       "train_precision": args.train_precision},
             "trainable_parameters": int(sum(p.numel() for p in trainable)), "last_loss": last,
             "gpu_launches": int(lib.zs_launch_count() - l0),
             "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
@@ -533,6 +543,9 @@ def main():
     ap.add_argument("--eval-shapes", type=int, default=256, help="mode eval: size of the synthetic evaluation set (all ranks together)")
     ap.add_argument("--brute-force", action="store_true", help="mode eval: the 6912-rotation pose search of evaluate.py (README protocol)")
     ap.add_argument("--train-batch", type=int, default=32, help="images per training step (options/shape.yaml batch 28-32)")
+    ap.add_argument("--train-engine", default="tc", choices=["tc", "f32"], help="modes train / train-decoder: tcgen05 or FFMA GEMM kernels")
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "bf16x3"],
+                    help="tensor-core operand precision of the training GEMMs (BASELINE config 3 is bf16 mixed precision)")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--attention", default=None, choices=["fused", "tc", "f32"])

@@ -210,8 +210,11 @@ int zs_layernorm_bwd_f32(const float* dy, const float* x, const float* gamma, fl
 int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, const float* O,
                                const float* dO, float* dqkv_p, float* dk_lat, float* dv_lat, int ld_dlat, int B, int P,
                                int L, int heads, int hd, float scale, void* stream);
-/* Backward of zs_mha_f32: dqkv [B,T,3C] from qkv and dO [B,T,C]. */
-int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* stream);
+/* Backward of zs_mha_f32: dqkv [B,T,3C] from qkv and dO [B,T,C] (head dim <= 64).  Two passes without atomics: the
+ * probability and score-gradient rows go through `ws` (zs_mha_bwd_ws_bytes = 2 * B * heads * T * T floats, 16-byte aligned). */
+size_t zs_mha_bwd_ws_bytes(int B, int T, int heads);
+int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
+                   void* stream);
 /* torch.optim.AdamW step (decoupled weight decay, bias correction) on one flat tensor; `step` counts from 1. */
 int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, void* stream);
@@ -224,6 +227,24 @@ int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, int Cin, cons
                              int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, void* stream);
 int zs_conv2d_nhwc_wgrad_f32(const float* x, int B, int H, int W, int Cin, const float* dy, float* dw, int Cout, int KH,
                              int KW, int stride, int pad_top, int pad_left, int OH, int OW, int accumulate, void* stream);
+
+/* The three gradient GEMMs of the training step on the tensor cores (tcgen05, split-bf16 operands, fp32 TMEM accumulators;
+ * `precision` 0 = bf16x3, 1 = bf16 as in zs_gemm_tc_f32).  They replace what torch autograd runs for every nn.Linear /
+ * nn.Conv2d in `loss.backward()` of the reference (model/shape_engine.py:268-272):
+ *  - dX = dY W        : zs_gemm_tc_f32 with zs_gemm_tc_pack(W^T)  (no new entry point)
+ *  - zs_conv2d_nhwc_dgrad_tc: dx [B,H,W,Cin] from dy [B,OH,OW,Cout] (Cout % 4 == 0); `Wpacked` = zs_gemm_tc_pack of the
+ *    filter re-laid as Wd[Cin, KH*KW*Cout] (the operand of zs_conv2d_nhwc_dgrad_f32)
+ *  - zs_gemm_tn_tc          : C[N,K] (+)= A[M,N]^T B[M,K]  (dW = dY^T X), split over the rows, fp32 reductions into C
+ *  - zs_conv2d_nhwc_wgrad_tc: dw [Cout,KH,KW,Cin] (+)= dY^T im2col(x), the im2col gathered on the fly (Cin % 8 == 0)
+ * `layout` selects the shared-memory operand layout of the TN kernels: 0 = MN-major SWIZZLE_128B tiles (no transposition,
+ * the default), 1 = K-major tiles filled by transposing producers (cross-check), 2 = diagnostic. */
+int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int Cin, const void* Wpacked, float* dx, int Cout,
+                            int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, int precision, void* stream);
+int zs_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                  int accumulate, int precision, int layout, void* stream);
+int zs_conv2d_nhwc_wgrad_tc(const float* x, int B, int H, int W, int Cin, const float* dy, float* dw, int Cout, int KH,
+                            int KW, int stride, int pad_top, int pad_left, int OH, int OW, int accumulate, int precision,
+                            int layout, void* stream);
 /* per-channel batch statistics of x [M,C]: mean, biased variance, rstd = 1/sqrt(var + eps); `ws` = 2*C doubles */
 int zs_bn_stats_f32(const float* x, int64_t M, int C, float eps, double* ws, float* mean, float* var, float* rstd, void* stream);
 /* BatchNorm (batch statistics) backward: dx, and dgamma / dbeta ACCUMULATED into; `ws` = 2*C doubles */

@@ -14,6 +14,26 @@ from oracle.implicit import implicit_forward, implicit_init
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _f32_training_engine():
+    """Gradient parity is pinned on the plain-fp32 kernels; the tests parametrised with `engine` switch to the tcgen05
+    training kernels (ops.TRAIN_ENGINE = "tc") inside `_engine(...)`."""
+    from zeroshape_b200 import ops
+    saved = (ops.TRAIN_ENGINE, ops.TRAIN_PRECISION)
+    ops.TRAIN_ENGINE = "f32"
+    yield
+    ops.TRAIN_ENGINE, ops.TRAIN_PRECISION = saved
+
+
+def _engine(engine):
+    """engine: "f32" | "tc" (bf16x3) | "tc-bf16" (single-pass bf16, BASELINE config 3's mixed precision)."""
+    from zeroshape_b200 import ops
+    if engine != "f32" and ops.device_cc() != 100:
+        pytest.skip("tcgen05 kernels need sm_100")
+    ops.TRAIN_ENGINE = "f32" if engine == "f32" else "tc"
+    ops.TRAIN_PRECISION = "bf16" if engine == "tc-bf16" else "bf16x3"
+
+
 def _module(sd, cuda, drop_path=0.0):
     from zeroshape_b200.model.shape.implicit import Implicit
     m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
@@ -35,9 +55,12 @@ def _ref_shape_loss(logits, sdf, thres, weight):
     return (loss * w).mean()
 
 
+@pytest.mark.parametrize("engine", ["f32", "tc"])
 @pytest.mark.parametrize("B,P", [(1, 130), (3, 700)])
-def test_decoder_gradients_match_oracle_autograd(cuda, B, P):
+def test_decoder_gradients_match_oracle_autograd(cuda, B, P, engine):
     from zeroshape_b200.utils.loss import Loss
+    _engine(engine)
+    tol_loss, tol_logit, tol_grad = (2e-6, 5e-5, 2e-4) if engine == "f32" else (2e-5, 3e-4, 2e-3)
     sd = implicit_init(seed=21)
     g = torch.Generator().manual_seed(B * 100 + P)
     lat = torch.randn(B, 197, 256, generator=g)
@@ -59,8 +82,8 @@ def test_decoder_gradients_match_oracle_autograd(cuda, B, P):
     lossfn = Loss({"training": {"shape_loss": {"impt_thres": thres, "impt_weight": weight}}})
     loss = lossfn.shape_loss(logits, sdf.to(cuda))
     loss.backward()
-    assert abs(loss.item() - loss_ref.item()) < 2e-6 * max(1.0, abs(loss_ref.item()))
-    assert (logits.detach().cpu() - logits_ref.detach()).abs().max().item() < 5e-5
+    assert abs(loss.item() - loss_ref.item()) < tol_loss * max(1.0, abs(loss_ref.item()))
+    assert (logits.detach().cpu() - logits_ref.detach()).abs().max().item() < tol_logit
     worst = ("", 0.0)
     for name, p in m.named_parameters():
         if name == "pos_embed":
@@ -70,9 +93,9 @@ def test_decoder_gradients_match_oracle_autograd(cuda, B, P):
         r = _rel(p.grad, sd_ref[name].grad)
         if r > worst[1]:
             worst = (name, r)
-        assert r < 2e-4, (name, r)
-    assert _rel(lat_d.grad, lat_ref.grad) < 2e-4
-    print("worst parameter-gradient relative error:", worst, " latent grad:", _rel(lat_d.grad, lat_ref.grad))
+        assert r < tol_grad, (name, r)
+    assert _rel(lat_d.grad, lat_ref.grad) < tol_grad
+    print(f"[{engine}]", "worst parameter-gradient relative error:", worst, " latent grad:", _rel(lat_d.grad, lat_ref.grad))
 
 
 def test_training_kernels_against_torch(cuda):
@@ -128,10 +151,12 @@ def test_training_kernels_against_torch(cuda):
     assert (pa.detach().cpu() - pb.detach()).abs().max().item() < 1e-6
 
 
-def test_graph_training_step_reduces_the_shape_loss(cuda):
+@pytest.mark.parametrize("engine", ["f32", "tc-bf16"])
+def test_graph_training_step_reduces_the_shape_loss(cuda, engine):
     """Graph.forward(training=True) with a synthetic GT batch in the optim.fix_dpt configuration:
     losses as in graph_shape.py:194-202, backward into impl_network AND coord_encoder (batch-statistics BatchNorm),
-    FusedAdamW steps -> the BCE loss goes down."""
+    FusedAdamW steps -> the BCE loss goes down (also in the single-pass bf16 tensor-core mode)."""
+    _engine(engine)
     from zeroshape_b200.model.compute_graph.graph_shape import Graph
     from zeroshape_b200.model.shape.implicit_train import FusedAdamW
     from zeroshape_b200.utils.util import EasyDict
@@ -211,9 +236,12 @@ def _torch_coord_enc_res(latent=256):
     return Ref()
 
 
-def test_coord_encoder_training_matches_torch_autograd(cuda, engine="auto"):
+@pytest.mark.parametrize("train_engine", ["f32", "tc"])
+def test_coord_encoder_training_matches_torch_autograd(cuda, train_engine, engine="auto"):
     """CoordEncRes in train mode: batch-statistics BatchNorm forward, every parameter gradient, running-stat update."""
     from zeroshape_b200 import ops
+    _engine(train_engine)
+    slack = 3 if train_engine == "f32" else 8        # bf16x3 products carry ~2^-16, amplified like the fp32 rounding
     from zeroshape_b200.model.shape.seen_coord_enc import CoordEncRes
     from zeroshape_b200.utils.util import EasyDict
     opt = EasyDict(arch=dict(depth=dict(dsp=1), win_size=16, latent_dim=256))
@@ -245,17 +273,17 @@ def test_coord_encoder_training_matches_torch_autograd(cuda, engine="auto"):
         (out * wgt.to(cuda)).sum().backward()
     finally:
         ops.ENCODER_ENGINE = "auto"
-    tol_out, floor = 2e-4, 2e-3        # the training forward runs the plain-fp32 convolutions whatever ENCODER_ENGINE says
+    tol_out, floor = (2e-4, 2e-3) if train_engine == "f32" else (1e-3, 8e-3)
     assert _rel(out, out64) < tol_out, _rel(out, out64)
     refp, refp64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
     worst = ("", 0.0, 0.0)
     for name, p in mod.named_parameters():
         assert p.grad is not None, name
         r, r_torch = _rel(p.grad, refp64[name].grad), _rel(refp[name].grad, refp64[name].grad)
-        if r / max(3 * r_torch, floor) > worst[1] / max(3 * worst[2], floor):
+        if r / max(slack * r_torch, floor) > worst[1] / max(slack * worst[2], floor):
             worst = (name, r, r_torch)
-        assert r < max(3 * r_torch, floor), (name, r, r_torch)
-    print(f"[{engine}] latent rel err {_rel(out, out64):.2e}; tightest parameter gradient (name, ours vs fp64, torch-fp32 vs fp64): {worst}")
+        assert r < max(slack * r_torch, floor), (name, r, r_torch)
+    print(f"[{train_engine}] latent rel err {_rel(out, out64):.2e}; tightest parameter gradient (name, ours vs fp64, torch-fp32 vs fp64): {worst}")
     # BatchNorm bookkeeping (momentum 0.1, unbiased variance)
     refb, modb = dict(ref.named_buffers()), dict(mod.named_buffers())
     for name in ("encoder.bn1.running_mean", "encoder.layer3.5.bn3.running_var", "depth_feat_proj.1.bn2.running_var"):
@@ -280,12 +308,14 @@ def _graph_and_sd(cuda, seed, fix_dpt=False):
     return opt, graph.to(cuda), sd
 
 
-def test_dpt_backward_matches_oracle_autograd(cuda):
+@pytest.mark.parametrize("engine", ["f32", "tc"])
+def test_dpt_backward_matches_oracle_autograd(cuda, engine):
     """DPT-hybrid on the tape (model/depth/dpt_train.py) vs torch autograd over the oracle's dpt_depth_forward: every
     parameter gradient of the depth estimator for a loss on the depth map and the layer_4 feature."""
     from oracle import backbone as BB
     from zeroshape_b200.model.depth import dpt_train as DT
     from test_gpu_graph import synthetic_image_and_mask
+    _engine(engine)
     opt, graph, sd = _graph_and_sd(cuda, 51)
     B = 1                                           # the CPU autograd reference dominates the run time
     rgb, _ = synthetic_image_and_mask(B, 52)
@@ -297,7 +327,8 @@ def test_dpt_backward_matches_oracle_autograd(cuda):
     tp = DT.Tape()
     with torch.no_grad():
         depth_nhwc, l4 = DT.dpt_forward(tp, graph.dpt_depth, rgb.to(cuda))
-        assert _rel(depth_nhwc.view(B, 1, 224, 224), depth_ref) < 1e-4 and _rel(l4.permute(0, 3, 1, 2), feat_ref) < 1e-4
+        tol_fwd = 1e-4 if engine == "f32" else 1e-3
+        assert _rel(depth_nhwc.view(B, 1, 224, 224), depth_ref) < tol_fwd and _rel(l4.permute(0, 3, 1, 2), feat_ref) < tol_fwd
         tp.add(depth_nhwc, w_depth.to(cuda).view(B, 224, 224, 1))
         tp.add(l4, w_feat.to(cuda).permute(0, 2, 3, 1).contiguous())
         tp.backward()
@@ -313,10 +344,12 @@ def test_dpt_backward_matches_oracle_autograd(cuda):
         n += 1
         errs.append((r, name))
     errs.sort(reverse=True)
-    print(f"DPT backward: {n} parameter gradients; worst:", [(round(r, 5), nm) for r, nm in errs[:8]], "median", errs[len(errs) // 2])
+    print(f"[{engine}] DPT backward: {n} parameter gradients; worst:", [(round(r, 5), nm) for r, nm in errs[:8]], "median", errs[len(errs) // 2])
     # random-init weight-standardised GroupNorm stacks amplify fp32 rounding ~100x (the forward already differs by 1e-5..1e-4):
     # the bar is a small uniform error, not a structural one
-    assert errs[0][0] < 5e-2 and errs[len(errs) // 2][0] < 5e-3, errs[:5]
+    # (bf16x3 products carry ~2^-16 instead of 2^-24: the same amplification applies, hence the wider bar for "tc")
+    worst_bar, median_bar = (5e-2, 5e-3) if engine == "f32" else (0.5, 0.1)
+    assert errs[0][0] < worst_bar and errs[len(errs) // 2][0] < median_bar, errs[:5]
 
 
 def test_geometry_backward_matches_oracle_autograd(cuda):
@@ -354,7 +387,8 @@ def test_geometry_backward_matches_oracle_autograd(cuda):
         assert abs(dK[:, i, j].cpu() - K_leaf.grad[:, i, j]).max() < 2e-4 * K_leaf.grad[:, i, j].abs().max().clamp_min(1e-6), (i, j)
 
 
-def test_full_graph_training_step(cuda):
+@pytest.mark.parametrize("engine", ["f32", "tc"])
+def test_full_graph_training_step(cuda, engine):
     """options/shape.yaml default (fix_dpt: false): one tape from the image to latent_depth, gradients for EVERY trainable
     parameter of the Graph, loose agreement with torch autograd over the oracle (batch-statistics BatchNorm over 3 samples
     in the 1x1 global branch of CoordEncRes makes the chain ill-conditioned: see the CoordEncRes test), and the loss goes down."""
@@ -362,6 +396,7 @@ def test_full_graph_training_step(cuda):
     from zeroshape_b200.model.shape.implicit_train import FusedAdamW
     from zeroshape_b200.utils.util import EasyDict
     from test_gpu_graph import synthetic_image_and_mask
+    _engine(engine)
     opt, graph, sd = _graph_and_sd(cuda, 61)
     graph.train()
     graph.impl_network.drop_path = 0.0

@@ -49,7 +49,13 @@ SIGNATURES = {
     "zs_gemm_tn_f32": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, c_int, c_int, c_int, P]),
     "zs_layernorm_bwd_f32": (c_int, [P, P, P, c_float, P, P, P, c_int64, c_int, P]),
     "zs_point_attention_bwd_f32": (c_int, [P, P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P]),
-    "zs_mha_bwd_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P]),
+    "zs_mha_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "zs_mha_bwd_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "zs_conv2d_nhwc_dgrad_tc": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, P]),
+    "zs_gemm_tn_tc": (c_int, [P, c_int, P, c_int, P, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
+    "zs_conv2d_nhwc_wgrad_tc": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, P]),
     "zs_conv2d_nhwc_dgrad_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_conv2d_nhwc_wgrad_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                          c_int, P]),

@@ -224,7 +224,8 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
   }
 }
 
-// AMODE 0: A is a dense row-major fp32 matrix;  AMODE 1: A rows are gathered from an NHWC image (im2col on the fly)
+// AMODE 0: A is a dense row-major fp32 matrix;  AMODE 1: A rows are gathered from an NHWC image (im2col on the fly);
+// AMODE 2: A rows are gathered from the output gradient of a convolution (data gradient as an implicit GEMM)
 template <int AMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -308,6 +309,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             buf[c] = make_float4(fmaxf(buf[c].x, 0.f), fmaxf(buf[c].y, 0.f), fmaxf(buf[c].z, 0.f), fmaxf(buf[c].w, 0.f));
+        }
+        return;
+      }
+      if (AMODE == 2) {
+        // data gradient of a convolution: row m = INPUT pixel (b, ih, iw), K index = (kh, kw, co) gathered from
+        // dY [B, OH, OW, Cout] (p.cCin holds Cout): oh = (ih + pad_top - kh) / stride when exact and in range, else zero
+        if (kc == 0) {
+          crow_ok = m < p.M;
+          const int iw = m % p.cW, tt = m / p.cW;
+          cb = tt / p.cH;
+          cih0 = (tt % p.cH) + p.cPadT;
+          ciw0 = iw + p.cPadL;
+        }
+        auto src_of = [&](int k, bool& ok) -> const float4* {
+          const int tap = k / p.cCin, co = k - tap * p.cCin;
+          const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
+          const int a = cih0 - kh, bb = ciw0 - kw;
+          int oh = a, ow = bb;
+          ok = crow_ok && k < p.K && a >= 0 && bb >= 0;
+          if (p.cStride != 1) {
+            oh = a / p.cStride; ow = bb / p.cStride;
+            ok = ok && oh * p.cStride == a && ow * p.cStride == bb;
+          }
+          ok = ok && oh < p.cOH && ow < p.cOW;
+          return reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cOH + (ok ? oh : 0)) * p.cOW + (ok ? ow : 0)) * p.cCin + co);
+        };
+        if ((p.cCin & 63) == 0) {
+          bool ok;
+          const float4* src = src_of(k0, ok);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) buf[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            bool ok;
+            const float4* src = src_of(k0 + c * 4, ok);
+            buf[c] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         return;
       }
@@ -605,5 +644,40 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_attn_pv_tc");
+  return ZS_OK;
+}
+
+// ---- data gradient of an NHWC convolution on the tensor cores ------------------------------------------------------
+// dx[b,ih,iw,ci] = sum_{kh,kw,co} dy[b,oh,ow,co] w[co,kh,kw,ci]: gemm_tc_kernel<2> with rows = input pixels, the K index
+// (kh, kw, co) gathered from dy, and `Wpacked` = zs_gemm_tc_pack of the filter re-laid as Wd[Cin, KH*KW*Cout].
+// Replaces torch autograd's conv2d input gradient in the training step (formerly zs_conv2d_nhwc_dgrad_f32, FFMA).
+extern "C" int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int Cin, const void* Wpacked, float* dx, int Cout,
+                                       int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, int precision,
+                                       void* stream) {
+  ZS_REQUIRE(dy && Wpacked && dx, "zs_conv2d_nhwc_dgrad_tc: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (Cout & 3) == 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_dgrad_tc: bad shape (Cout %% 4 == 0 required)");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wpacked) & 15) == 0,
+             "zs_conv2d_nhwc_dgrad_tc: dy / packed weights must be 16-byte aligned");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_conv2d_nhwc_dgrad_tc: precision must be 0 (bf16x3) or 1 (bf16)");
+  const int64_t M64 = (int64_t)B * H * W;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_dgrad_tc: too many pixels");
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  TcParams p{};
+  p.A = dy; p.lda = 0; p.Wp = reinterpret_cast<const uint8_t*>(Wpacked); p.bias = nullptr;
+  p.res = nullptr; p.ldres = Cin; p.res_mode = ZS_RES_NONE; p.C = dx; p.ldc = Cin;
+  p.M = (int)M64; p.N = Cin; p.K = KH * KW * Cout; p.act = ZS_ACT_NONE; p.precision = precision;
+  p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.n_tiles = (p.N + TC_BN - 1) / TC_BN; p.k_chunks = (p.K + TC_BK - 1) / TC_BK;
+  p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  p.cB = B; p.cH = H; p.cW = W; p.cCin = Cout; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
+  p.cOH = OH; p.cOW = OW; p.cPreRelu = 0;
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_dgrad_tc");
   return ZS_OK;
 }

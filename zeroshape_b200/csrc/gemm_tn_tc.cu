@@ -1,0 +1,427 @@
+// tcgen05 "TN" GEMM for weight gradients:   C[N, Kc] (+)= A[M, N]^T * Bm[M, Kc]
+//
+//   A  = dY, fp32 row-major [M, N]                      (gradient of a layer's output, one row per sample / token / pixel)
+//   Bm = the layer's input, fp32: a dense row-major matrix [M, Kc] (nn.Linear, 1x1 convolutions) or the im2col view of an
+//        NHWC image (Kc = KH*KW*Cin, gathered on the fly -- the matrix is never materialised)
+//   C  = dW in the parameter's own [N, Kc] layout (OHWI filters for convolutions)
+// Replaces torch autograd's weight gradients of every nn.Linear / nn.Conv2d of the training step (reference
+// model/shape_engine.py:248-277 `loss.backward()`), formerly zs_gemm_tn_f32 / zs_conv2d_nhwc_wgrad_f32 (FFMA).
+//
+// The reduction runs over the ROWS of both operands, i.e. over the slow index of both fp32 matrices, so both UMMA operands
+// are "MN-major": element (n, m) of the A operand sits next to (n+1, m).  The shared-memory tiles use the canonical
+// MN-major SWIZZLE_128B layout (64 MN-elements = 128 B per K-row, 8 K-rows per 1024-byte atom, atoms tiled MN-first) so a
+// producer thread turns 8 consecutive fp32 of one row (two float4 loads, fully coalesced) into ONE 16-byte bf16 chunk per
+// precision pass -- no transposition in registers or shared memory.  Layout 1 keeps the K-major operand tiles of gemm_tc.cu
+// with transposing producers (scalar loads); it exists to cross-check the MN-major descriptors on the device.
+//
+// CTA = 416 threads: warps 0-7 producers (fp32 -> (hi, lo) bf16 tiles), warps 8-11 epilogue (TMEM -> red.global.add into C),
+// warp 12 MMA issuer.  Work item = (128 x 256 output tile, split of the row range); split-K partial sums are combined with
+// fp32 reductions in L2 (C is zeroed by the wrapper unless `accumulate`).  2 smem stages x 96 KB, 2 x 256 TMEM columns.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace zs {
+using namespace tc;
+
+constexpr int TN_BM = 128, TN_BN = 256, TN_BK = 64;     // output tile 128 (n) x 256 (k-columns); 64 rows reduced per chunk
+constexpr int TN_STAGES = 2;
+constexpr int TN_A_TILE = TN_BM * TN_BK * 2;            // 16 KB (one of hi / lo)
+constexpr int TN_B_TILE = TN_BN * TN_BK * 2;            // 32 KB
+constexpr int TN_STAGE_BYTES = 2 * TN_A_TILE + 2 * TN_B_TILE;
+constexpr int TN_PRODUCERS = 256;
+constexpr int TN_THREADS = 416;
+constexpr int TN_SMEM = TN_STAGES * TN_STAGE_BYTES + 1024 + 256;
+
+struct TnParams {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  int M, N, Kc;
+  int n_tiles, k_tiles, splits, chunks_per_split, total_chunks;
+  int precision;     // 0 = bf16x3, 1 = bf16
+  int layout;        // 0 = MN-major operand tiles, 1 = K-major tiles (transposing producers), 2 = MN-major, LBO/SBO swapped
+  // BMODE 1: Bm = im2col of an NHWC image; row m = output pixel (b, oh, ow), column = (kh, kw, ci)
+  int cB, cH, cW, cCin, cKH, cKW, cStride, cPadT, cPadL, cOH, cOW;
+};
+
+// MN-major SWIZZLE_128B operand descriptor: `lbo` = byte distance between 64-element atoms along M/N, `sbo` = byte distance
+// between groups of 8 K-rows (cute/atom/mma_traits_sm100.hpp: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+template <int BMODE>
+__global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + TN_STAGES * TN_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 64u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TN_STAGES * TN_STAGE_BYTES + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TN_STAGES; ++s) {
+      mbar_init(full_bar(s), TN_PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_work = p.n_tiles * p.k_tiles * p.splits;
+
+  if (warp < 8) {
+    // ================= producers =================
+    const int t = threadIdx.x;
+    int stage = 0; uint32_t phase = 0;
+    const bool vecA = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+    const bool vecB = BMODE == 1 ? true : (((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0));
+
+    // 8 consecutive columns of row m of A / Bm (zero outside the matrix)
+    auto load8A = [&](int m, int col, float4& x0, float4& x1) {
+      x0 = x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m >= p.M || col >= p.N) return;
+      const float* src = p.A + (int64_t)m * p.lda + col;
+      if (vecA && col + 8 <= p.N) {
+        x0 = __ldg(reinterpret_cast<const float4*>(src));
+        x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      } else {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (col + e < p.N) ? __ldg(src + e) : 0.f;
+        x0 = make_float4(v[0], v[1], v[2], v[3]); x1 = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    };
+    // BMODE 1 column decode (constant per work item for a thread in the MN-major layout)
+    int tap_kh = 0, tap_kw = 0, tap_ci = 0;
+    auto decode_col = [&](int col) {
+      const int tap = col / p.cCin;
+      tap_ci = col - tap * p.cCin;
+      tap_kh = tap / p.cKW;
+      tap_kw = tap - tap_kh * p.cKW;
+    };
+    auto load8B = [&](int m, int col, float4& x0, float4& x1) {
+      x0 = x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m >= p.M || col >= p.Kc) return;
+      if (BMODE == 1) {
+        // Cin % 8 == 0: the 8 columns lie inside one filter tap = 32 contiguous bytes of one input pixel
+        const int ow = m % p.cOW, tt = m / p.cOW;
+        const int oh = tt % p.cOH, b = tt / p.cOH;
+        const int ih = oh * p.cStride - p.cPadT + tap_kh, iw = ow * p.cStride - p.cPadL + tap_kw;
+        if ((unsigned)ih >= (unsigned)p.cH || (unsigned)iw >= (unsigned)p.cW) return;
+        const float4* src = reinterpret_cast<const float4*>(p.B + (((int64_t)b * p.cH + ih) * p.cW + iw) * p.cCin + tap_ci);
+        x0 = __ldg(src); x1 = __ldg(src + 1);
+        return;
+      }
+      const float* src = p.B + (int64_t)m * p.ldb + col;
+      if (vecB && col + 8 <= p.Kc) {
+        x0 = __ldg(reinterpret_cast<const float4*>(src));
+        x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      } else {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (col + e < p.Kc) ? __ldg(src + e) : 0.f;
+        x0 = make_float4(v[0], v[1], v[2], v[3]); x1 = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    };
+    auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float4& x0, const float4& x1) {
+      uint4 hi, lo;
+      split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+      split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+      split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+      split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+      *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+      if (split) *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+    };
+
+    if (p.layout != 1) {
+      // ---- MN-major tiles: thread = (row r of the chunk, 16-byte chunk c of that row) ----
+      // A: 64 rows x 16 chunks (128 n-columns): c = t & 15, rows (t >> 4) + 16 i, i < 4
+      // B: 64 rows x 32 chunks (256 k-columns): c = t & 31, rows (t >> 5) + 8 i,  i < 8
+      const int ca = t & 15, ra = t >> 4;
+      const int cb = t & 31, rb = t >> 5;
+      float4 abuf[4][2], bbuf[8][2];
+      auto fetch = [&](int w, int chunk) {
+        const int tile = w / p.splits;
+        const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+        const int m0 = chunk * TN_BK;
+        const int colA = nt * TN_BM + ca * 8, colB = kt * TN_BN + cb * 8;
+        if (BMODE == 1) decode_col(colB);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) load8A(m0 + ra + 16 * i, colA, abuf[i][0], abuf[i][1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) load8B(m0 + rb + 8 * i, colB, bbuf[i][0], bbuf[i][1]);
+      };
+      auto chunk_range = [&](int w, int& c0, int& c1) {
+        const int sp = w % p.splits;
+        c0 = sp * p.chunks_per_split;
+        c1 = min(p.total_chunks, c0 + p.chunks_per_split);
+      };
+      int w = blockIdx.x, c0 = 0, c1 = 0;
+      if (w < total_work) { chunk_range(w, c0, c1); fetch(w, c0); }
+      for (; w < total_work; w += gridDim.x) {
+        chunk_range(w, c0, c1);
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          uint8_t* a_hi = smem_gen + stage * TN_STAGE_BYTES;
+          uint8_t* a_lo = a_hi + TN_A_TILE;
+          uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
+          uint8_t* b_lo = b_hi + TN_B_TILE;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = ra + 16 * i;                      // K-row of the chunk
+            const uint32_t off = (uint32_t)(r >> 3) * (2u * 1024u) + (uint32_t)(ca >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                                 (uint32_t)(((ca & 7) ^ (r & 7)) << 4);
+            put(a_hi, a_lo, off, abuf[i][0], abuf[i][1]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rb + 8 * i;
+            const uint32_t off = (uint32_t)(r >> 3) * (4u * 1024u) + (uint32_t)(cb >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                                 (uint32_t)(((cb & 7) ^ (r & 7)) << 4);
+            put(b_hi, b_lo, off, bbuf[i][0], bbuf[i][1]);
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(stage));
+          if (c + 1 < c1) fetch(w, c + 1);
+          else if (w + (int)gridDim.x < total_work) { int n0, n1; chunk_range(w + gridDim.x, n0, n1); fetch(w + gridDim.x, n0); }
+          if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      // ---- K-major tiles (layout of gemm_tc.cu): thread = (column, group of 8 rows), scalar loads, transposed store ----
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = w / p.splits, sp = w % p.splits;
+        const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+        const int c0 = sp * p.chunks_per_split, c1 = min(p.total_chunks, c0 + p.chunks_per_split);
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          uint8_t* a_hi = smem_gen + stage * TN_STAGE_BYTES;
+          uint8_t* a_lo = a_hi + TN_A_TILE;
+          uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
+          uint8_t* b_lo = b_hi + TN_B_TILE;
+          const int m0 = c * TN_BK;
+          for (int u = t; u < TN_BM * 8; u += TN_PRODUCERS) {        // A: 128 columns x 8 row groups
+            const int n = u & (TN_BM - 1), j = u >> 7;
+            const int col = nt * TN_BM + n;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int m = m0 + j * 8 + e;
+              v[e] = (m < p.M && col < p.N) ? __ldg(p.A + (int64_t)m * p.lda + col) : 0.f;
+            }
+            put(a_hi, a_lo, swizzle128_offset(n, j), make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+          }
+          for (int u = t; u < TN_BN * 8; u += TN_PRODUCERS) {        // B: 256 columns x 8 row groups
+            const int n = u & (TN_BN - 1), j = u >> 8;
+            const int col = kt * TN_BN + n;
+            if (BMODE == 1) decode_col(col < p.Kc ? col : 0);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int m = m0 + j * 8 + e;
+              float x = 0.f;
+              if (m < p.M && col < p.Kc) {
+                if (BMODE == 1) {
+                  const int ow = m % p.cOW, tt = m / p.cOW;
+                  const int oh = tt % p.cOH, b = tt / p.cOH;
+                  const int ih = oh * p.cStride - p.cPadT + tap_kh, iw = ow * p.cStride - p.cPadL + tap_kw;
+                  if ((unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW)
+                    x = __ldg(p.B + (((int64_t)b * p.cH + ih) * p.cW + iw) * p.cCin + tap_ci);
+                } else {
+                  x = __ldg(p.B + (int64_t)m * p.ldb + col);
+                }
+              }
+              v[e] = x;
+            }
+            put(b_hi, b_lo, swizzle128_offset(n, j), make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar(stage));
+          if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const bool mn = p.layout != 1;
+      const uint32_t idesc = umma_idesc_bf16(TN_BM, TN_BN) | (mn ? ((1u << 15) | (1u << 16)) : 0u);
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int sp = w % p.splits;
+        const int c0 = sp * p.chunks_per_split, c1 = min(p.total_chunks, c0 + p.chunks_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN_BN;
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * TN_STAGE_BYTES;
+          const uint32_t sb = sa + 2 * TN_A_TILE;
+#pragma unroll
+          for (int k = 0; k < TN_BK / 16; ++k) {
+            uint64_t a_hi, a_lo, b_hi, b_lo;
+            if (mn) {
+              // one MMA consumes 16 K-rows = two 8-row groups: A groups are 2 KB apart (2 atoms of 64 n), B groups 4 KB
+              const uint32_t aoff = (uint32_t)k * 2u * 2048u, boff = (uint32_t)k * 2u * 4096u;
+              if (p.layout == 0) {
+                a_hi = umma_desc_mn_sw128(sa + aoff, 1024u, 2048u); a_lo = umma_desc_mn_sw128(sa + TN_A_TILE + aoff, 1024u, 2048u);
+                b_hi = umma_desc_mn_sw128(sb + boff, 1024u, 4096u); b_lo = umma_desc_mn_sw128(sb + TN_B_TILE + boff, 1024u, 4096u);
+              } else {
+                a_hi = umma_desc_mn_sw128(sa + aoff, 2048u, 1024u); a_lo = umma_desc_mn_sw128(sa + TN_A_TILE + aoff, 2048u, 1024u);
+                b_hi = umma_desc_mn_sw128(sb + boff, 4096u, 1024u); b_lo = umma_desc_mn_sw128(sb + TN_B_TILE + boff, 4096u, 1024u);
+              }
+            } else {
+              const uint64_t koff = (uint64_t)((k * 32) >> 4);
+              a_hi = umma_desc_sw128(sa) + koff; a_lo = umma_desc_sw128(sa + TN_A_TILE) + koff;
+              b_hi = umma_desc_sw128(sb) + koff; b_lo = umma_desc_sw128(sb + TN_B_TILE) + koff;
+            }
+            umma_bf16(d_tmem, a_hi, b_hi, idesc, (c != c0 || k != 0) ? 1u : 0u);
+            if (split) {
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (c == c1 - 1) umma_commit(tfull_bar(acc));
+          if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: warps 8-11, warp q owns TMEM lanes 32q .. 32q+31 (rows n of the tile) =================
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / p.splits;
+      const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+      const int n = nt * TN_BM + q * 32 + lane;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * TN_BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cc = 0; cc < TN_BN; cc += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + cc, rr);
+        tmem_ld_wait();
+        const int col0 = kt * TN_BN + cc;
+        if (n < p.N && col0 < p.Kc) {
+          float* crow = p.C + (int64_t)n * p.ldc + col0;
+          if (col0 + 32 <= p.Kc && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(crow + j, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]), __uint_as_float(rr[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Kc) red_add(crow + j, __uint_as_float(rr[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BMODE>
+static int launch_tn(TnParams& p, int accumulate, cudaStream_t st, const char* what) {
+  static thread_local bool configured = false;
+  if (!configured) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tn_tc_kernel<BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    configured = true;
+  }
+  p.n_tiles = (p.N + TN_BM - 1) / TN_BM;
+  p.k_tiles = (p.Kc + TN_BN - 1) / TN_BN;
+  p.total_chunks = (p.M + TN_BK - 1) / TN_BK;
+  const int tiles = p.n_tiles * p.k_tiles;
+  int splits = (sm_count() + tiles - 1) / tiles;           // about one work item per SM
+  if (splits > p.total_chunks) splits = p.total_chunks;
+  if (splits < 1) splits = 1;
+  p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
+  p.splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  if (!accumulate) {
+    if (p.ldc == p.Kc) ZS_CUDA_CALL(cudaMemsetAsync(p.C, 0, sizeof(float) * (size_t)p.N * p.Kc, st));
+    else ZS_CUDA_CALL(cudaMemset2DAsync(p.C, sizeof(float) * (size_t)p.ldc, 0, sizeof(float) * (size_t)p.Kc, (size_t)p.N, st));
+  }
+  const int work = tiles * p.splits;
+  const int grid = work < sm_count() ? work : sm_count();
+  gemm_tn_tc_kernel<BMODE><<<grid, TN_THREADS, TN_SMEM, st>>>(p);
+  ZS_CUDA_CHECK_LAUNCH(what);
+  return ZS_OK;
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" int zs_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                             int accumulate, int precision, int layout, void* stream) {
+  ZS_REQUIRE(A && B && C, "zs_gemm_tn_tc: null pointer");
+  ZS_REQUIRE(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && lda >= N && ldb >= K && ldc >= K, "zs_gemm_tn_tc: bad shape");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_gemm_tn_tc: precision must be 0 (bf16x3) or 1 (bf16)");
+  ZS_REQUIRE(layout >= 0 && layout <= 2, "zs_gemm_tn_tc: layout must be 0 (MN-major), 1 (K-major) or 2");
+  TnParams p{};
+  p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
+  p.M = (int)M; p.N = N; p.Kc = K; p.precision = precision; p.layout = layout;
+  return launch_tn<0>(p, accumulate, as_stream(stream), "zs_gemm_tn_tc");
+}
+
+extern "C" int zs_conv2d_nhwc_wgrad_tc(const float* x, int B, int H, int W, int Cin, const float* dy, float* dw, int Cout, int KH,
+                                       int KW, int stride, int pad_top, int pad_left, int OH, int OW, int accumulate,
+                                       int precision, int layout, void* stream) {
+  ZS_REQUIRE(x && dy && dw, "zs_conv2d_nhwc_wgrad_tc: null pointer");
+  ZS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+             "zs_conv2d_nhwc_wgrad_tc: bad shape");
+  ZS_REQUIRE((Cin & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+             "zs_conv2d_nhwc_wgrad_tc: needs Cin %% 8 == 0 and a 16-byte aligned image");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_conv2d_nhwc_wgrad_tc: precision must be 0 (bf16x3) or 1 (bf16)");
+  ZS_REQUIRE(layout >= 0 && layout <= 2, "zs_conv2d_nhwc_wgrad_tc: layout must be 0, 1 or 2");
+  const int64_t M64 = (int64_t)B * OH * OW;
+  ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_wgrad_tc: too many output pixels");
+  TnParams p{};
+  p.A = dy; p.lda = Cout; p.B = x; p.ldb = 0; p.C = dw; p.ldc = KH * KW * Cin;
+  p.M = (int)M64; p.N = Cout; p.Kc = KH * KW * Cin; p.precision = precision; p.layout = layout;
+  p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
+  p.cOH = OH; p.cOW = OW;
+  return launch_tn<1>(p, accumulate, as_stream(stream), "zs_conv2d_nhwc_wgrad_tc");
+}

@@ -301,29 +301,30 @@ __global__ void __launch_bounds__(128) point_attention_bwd_kernel(
 }
 
 // ---- token self-attention backward (latent branch of the decoder, ViT blocks of the depth encoder; timm Attention) ----
-// One CTA per (image, head); one warp per query row; K, V and the dK / dV accumulators live in shared memory (the 197 x 64
-// ViT-B heads need 4 x 51 KB), q_i / dO_i of the row in a per-warp buffer.
-__global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
-                                                      float* __restrict__ dqkv, int T, int heads, int hd, float scale) {
-  extern __shared__ float sm[];
-  const int ld = hd + 1;
-  float* Ks = sm;                       // [T][hd+1]
+// Two passes, no atomics.  Pass 1 (rows): one CTA per (image, head, row slab), K and V in shared memory, one warp per query
+// row i: p_i = softmax(scale q_i K^T), dp_ij = dO_i . v_j, ds_ij = p_ij (dp_ij - sum_j p_ij dp_ij) scale, dq_i = ds_i K;
+// the probability and ds rows go to a [B*heads, T, T] workspace.  Pass 2 (columns): dV = P^T dO, dK = dS^T Q, one CTA per
+// (image, head, 32 key columns) with Q / dO of the head and the column block of P / dS in shared memory.
+constexpr int MHA_BWD_WARPS = 16;
+__global__ void __launch_bounds__(MHA_BWD_WARPS * 32) mha_bwd_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                                          float* __restrict__ dqkv, float* __restrict__ Pg,
+                                                                          float* __restrict__ Sg, int T, int heads, int hd, float scale,
+                                                                          int rows_per_cta) {
+  extern __shared__ __align__(16) float sm[];
+  const int ld = hd + 4;                // float4 rows; lanes 68 floats apart hit distinct bank quads
+  float* Ks = sm;                       // [T][ld]
   float* Vs = Ks + (size_t)T * ld;
-  float* dKs = Vs + (size_t)T * ld;
-  float* dVs = dKs + (size_t)T * ld;
-  const int nwarps = blockDim.x >> 5;
-  float* Ps = dVs + (size_t)T * ld;     // [nwarps][T]   p_j
-  float* Ds = Ps + (size_t)nwarps * T;  // [nwarps][T]   ds_j
-  float* Qw = Ds + (size_t)nwarps * T;  // [nwarps][hd]
-  float* Gw = Qw + (size_t)nwarps * hd; // [nwarps][hd]
+  float* Ps = Vs + (size_t)T * ld;      // [warps][T]   p_j
+  float* Ds = Ps + (size_t)MHA_BWD_WARPS * T;   // [warps][T]   dp_j, then ds_j
+  float* Qw = Ds + (size_t)MHA_BWD_WARPS * T;   // [warps][hd]
+  float* Gw = Qw + (size_t)MHA_BWD_WARPS * hd;  // [warps][hd]
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
   const int C = heads * hd;
   const float* base = qkv + (int64_t)b * T * 3 * C;
-  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
-    const int t = i / hd, d = i % hd;
-    Ks[t * ld + d] = base[(int64_t)t * 3 * C + C + h * hd + d];
-    Vs[t * ld + d] = base[(int64_t)t * 3 * C + 2 * C + h * hd + d];
-    dKs[t * ld + d] = 0.f; dVs[t * ld + d] = 0.f;
+  for (int i = threadIdx.x; i < T * (hd >> 2); i += blockDim.x) {
+    const int t = i / (hd >> 2), d = (i % (hd >> 2)) * 4;
+    *reinterpret_cast<float4*>(Ks + t * ld + d) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t * 3 * C + C + h * hd + d));
+    *reinterpret_cast<float4*>(Vs + t * ld + d) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t * 3 * C + 2 * C + h * hd + d));
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,7 +332,10 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
   float* Dv = Ds + warp * T;
   float* Q = Qw + warp * hd;
   float* G = Gw + warp * hd;
-  for (int i = warp; i < T; i += nwarps) {
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(T, r0 + rows_per_cta);
+  float* Pout = Pg + (int64_t)bh * T * T;
+  float* Sout = Sg + (int64_t)bh * T * T;
+  for (int i = r0 + warp; i < r1; i += MHA_BWD_WARPS) {
     for (int d = lane; d < hd; d += 32) {
       Q[d] = base[(int64_t)i * 3 * C + h * hd + d];
       G[d] = dO[((int64_t)b * T + i) * C + h * hd + d];
@@ -339,10 +343,16 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
     __syncwarp();
     float mx = -INFINITY;
     for (int j = lane; j < T; j += 32) {
-      float s = 0.f;
-      for (int d = 0; d < hd; ++d) s = fmaf(Q[d], Ks[j * ld + d], s);
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < hd; d += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(Q + d), g = *reinterpret_cast<const float4*>(G + d);
+        const float4 k = *reinterpret_cast<const float4*>(Ks + j * ld + d), v = *reinterpret_cast<const float4*>(Vs + j * ld + d);
+        s = fmaf(q.x, k.x, s); s = fmaf(q.y, k.y, s); s = fmaf(q.z, k.z, s); s = fmaf(q.w, k.w, s);
+        dp = fmaf(g.x, v.x, dp); dp = fmaf(g.y, v.y, dp); dp = fmaf(g.z, v.z, dp); dp = fmaf(g.w, v.w, dp);
+      }
       s *= scale;
       P[j] = s;
+      Dv[j] = dp;
       mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
@@ -352,33 +362,75 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const float* __restrict__ 
     const float inv = 1.0f / sum;
     float Dp = 0.f;
     for (int j = lane; j < T; j += 32) {
-      float dp = 0.f;
-      for (int d = 0; d < hd; ++d) dp = fmaf(G[d], Vs[j * ld + d], dp);
       const float p = P[j] * inv;
       P[j] = p;
-      Dv[j] = dp;
-      Dp = fmaf(p, dp, Dp);
+      Dp = fmaf(p, Dv[j], Dp);
     }
     Dp = warp_sum(Dp);
-    for (int j = lane; j < T; j += 32) Dv[j] = P[j] * (Dv[j] - Dp) * scale;
+    for (int j = lane; j < T; j += 32) {
+      const float ds = P[j] * (Dv[j] - Dp) * scale;
+      Dv[j] = ds;
+      Pout[(int64_t)i * T + j] = P[j];
+      Sout[(int64_t)i * T + j] = ds;
+    }
     __syncwarp();
     for (int d = lane; d < hd; d += 32) {
       float acc = 0.f;
-      const float qi = Q[d], gi = G[d];
-      for (int j = 0; j < T; ++j) {
-        acc = fmaf(Dv[j], Ks[j * ld + d], acc);
-        atomicAdd(&dKs[j * ld + d], Dv[j] * qi);
-        atomicAdd(&dVs[j * ld + d], P[j] * gi);
-      }
+      for (int j = 0; j < T; ++j) acc = fmaf(Dv[j], Ks[j * ld + d], acc);
       dqkv[((int64_t)b * T + i) * 3 * C + h * hd + d] = acc;
     }
     __syncwarp();
   }
+}
+
+__global__ void __launch_bounds__(256) mha_bwd_cols_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
+                                                           float* __restrict__ dqkv, const float* __restrict__ Pg,
+                                                           const float* __restrict__ Sg, int T, int heads, int hd) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                        // [T][hd]
+  float* Gs = Qs + (size_t)T * hd;       // [T][hd]
+  float* Pc = Gs + (size_t)T * hd;       // [T][32]  column block of P
+  float* Sc = Pc + (size_t)T * 32;       // [T][32]  column block of dS
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int C = heads * hd;
+  const int j0 = blockIdx.y * 32;
+  const float* base = qkv + (int64_t)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * (hd >> 2); i += blockDim.x) {
+    const int t = i / (hd >> 2), d = (i % (hd >> 2)) * 4;
+    *reinterpret_cast<float4*>(Qs + t * hd + d) = __ldg(reinterpret_cast<const float4*>(base + (int64_t)t * 3 * C + h * hd + d));
+    *reinterpret_cast<float4*>(Gs + t * hd + d) = __ldg(reinterpret_cast<const float4*>(dO + ((int64_t)b * T + t) * C + h * hd + d));
+  }
+  const float* Pin = Pg + (int64_t)bh * T * T;
+  const float* Sin = Sg + (int64_t)bh * T * T;
+  for (int i = threadIdx.x; i < T * 32; i += blockDim.x) {
+    const int t = i >> 5, c = i & 31;
+    const bool ok = j0 + c < T;
+    Pc[i] = ok ? Pin[(int64_t)t * T + j0 + c] : 0.f;
+    Sc[i] = ok ? Sin[(int64_t)t * T + j0 + c] : 0.f;
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * hd; i += blockDim.x) {
-    const int t = i / hd, d = i % hd;
-    dqkv[((int64_t)b * T + t) * 3 * C + C + h * hd + d] = dKs[t * ld + d];
-    dqkv[((int64_t)b * T + t) * 3 * C + 2 * C + h * hd + d] = dVs[t * ld + d];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool two = hd > 32;              // hd <= 64: lane owns d = lane and lane + 32
+  float av[4][2] = {}, ak[4][2] = {};
+  for (int i = 0; i < T; ++i) {
+    const float4 pv = *reinterpret_cast<const float4*>(Pc + i * 32 + warp * 4);
+    const float4 sv = *reinterpret_cast<const float4*>(Sc + i * 32 + warp * 4);
+    const float g0 = lane < hd ? Gs[i * hd + lane] : 0.f, q0 = lane < hd ? Qs[i * hd + lane] : 0.f;
+    const float g1 = two ? Gs[i * hd + lane + 32] : 0.f, q1 = two ? Qs[i * hd + lane + 32] : 0.f;
+    const float pp[4] = {pv.x, pv.y, pv.z, pv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      av[c][0] = fmaf(pp[c], g0, av[c][0]); av[c][1] = fmaf(pp[c], g1, av[c][1]);
+      ak[c][0] = fmaf(ss[c], q0, ak[c][0]); ak[c][1] = fmaf(ss[c], q1, ak[c][1]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int j = j0 + warp * 4 + c;
+    if (j >= T) continue;
+    float* row = dqkv + ((int64_t)b * T + j) * 3 * C + h * hd;
+    if (lane < hd) { row[C + lane] = ak[c][0]; row[2 * C + lane] = av[c][0]; }
+    if (two) { row[C + lane + 32] = ak[c][1]; row[2 * C + lane + 32] = av[c][1]; }
   }
 }
 
@@ -814,15 +866,34 @@ extern "C" int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat
   return ZS_OK;
 }
 
-extern "C" int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale,
+extern "C" size_t zs_mha_bwd_ws_bytes(int B, int T, int heads) {
+  if (B <= 0 || T <= 0 || heads <= 0) return 0;
+  return sizeof(float) * 2 * (size_t)B * heads * T * T;
+}
+
+extern "C" int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
                               void* stream) {
-  ZS_REQUIRE(qkv && dO && dqkv && B > 0 && T > 0 && heads > 0 && hd > 0, "zs_mha_bwd_f32: bad args");
-  const int nwarps = 8;
-  const size_t smem = sizeof(float) * ((size_t)4 * T * (hd + 1) + (size_t)2 * nwarps * T + (size_t)2 * nwarps * hd);
-  ZS_REQUIRE(smem <= 227 * 1024, "zs_mha_bwd_f32: sequence too long for shared memory");
-  ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mha_bwd_kernel<<<B * heads, nwarps * 32, smem, as_stream(stream)>>>(qkv, dO, dqkv, T, heads, hd, scale);
-  ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_f32");
+  ZS_REQUIRE(qkv && dO && dqkv && ws && B > 0 && T > 0 && heads > 0 && hd > 0, "zs_mha_bwd_f32: bad args");
+  ZS_REQUIRE((hd & 3) == 0 && hd <= 64, "zs_mha_bwd_f32: head dim must be a multiple of 4, at most 64");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dO) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "zs_mha_bwd_f32: qkv / dO / ws must be 16-byte aligned");
+  float* Pg = reinterpret_cast<float*>(ws);
+  float* Sg = Pg + (size_t)B * heads * T * T;
+  const size_t smem1 = sizeof(float) * ((size_t)2 * T * (hd + 4) + (size_t)2 * MHA_BWD_WARPS * T + (size_t)2 * MHA_BWD_WARPS * hd);
+  const size_t smem2 = sizeof(float) * ((size_t)2 * T * hd + (size_t)2 * T * 32);
+  ZS_REQUIRE(smem1 <= 227 * 1024 && smem2 <= 227 * 1024, "zs_mha_bwd_f32: sequence too long for shared memory");
+  ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  int slabs = (2 * sm_count() + B * heads - 1) / (B * heads);        // enough CTAs for two waves at small batch
+  if (slabs < 2) slabs = 2;
+  int rows_per_cta = (T + slabs - 1) / slabs;
+  if (rows_per_cta < MHA_BWD_WARPS) rows_per_cta = MHA_BWD_WARPS;
+  slabs = (T + rows_per_cta - 1) / rows_per_cta;
+  cudaStream_t st = as_stream(stream);
+  mha_bwd_rows_kernel<<<dim3(B * heads, slabs), MHA_BWD_WARPS * 32, smem1, st>>>(qkv, dO, dqkv, Pg, Sg, T, heads, hd, scale, rows_per_cta);
+  ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_f32(rows)");
+  mha_bwd_cols_kernel<<<dim3(B * heads, (T + 31) / 32), 256, smem2, st>>>(qkv, dO, dqkv, Pg, Sg, T, heads, hd);
+  ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_f32(cols)");
   return ZS_OK;
 }
 

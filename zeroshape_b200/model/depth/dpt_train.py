@@ -82,10 +82,11 @@ def _same_pad(i, k, s):
 
 # ---- tape ops ------------------------------------------------------------------------------------------------------
 def conv(tp, x, W, bias_param=None, stride=1, pad=(0, 0, 0, 0), need_dx=True):
-    """x NHWC, W = _W holding an OHWI filter -> y (plain-fp32 convolution)."""
+    """x NHWC, W = _W holding an OHWI filter -> y (engine / precision per ops.TRAIN_ENGINE / ops.TRAIN_PRECISION)."""
     w = W.val
     Cout, KH, KW, Cin = w.shape
-    y = ops.conv2d_nhwc(x, w, bias_param.detach().float() if bias_param is not None else None, stride, pad, tc=False)
+    y = ops.conv2d_nhwc(x, w, bias_param.detach().float() if bias_param is not None else None, stride, pad, tc=ops.train_tc(),
+                        precision=ops.TRAIN_PRECISION)
 
     def bwd():
         dy = tp.pop(y)
@@ -96,7 +97,7 @@ def conv(tp, x, W, bias_param=None, stride=1, pad=(0, 0, 0, 0), need_dx=True):
         if KH == 1 and KW == 1 and stride == 1 and pad == (0, 0, 0, 0):
             W.push(tp, ops.gemm_tn(dy.view(-1, Cout), x.view(-1, Cin)))
             if need_dx:
-                tp.add(x, ops.gemm(dy.view(-1, Cout), w.view(Cout, Cin).t().clone(memory_format=torch.contiguous_format)).view(x.shape))
+                tp.add(x, ops.train_dgrad(dy.view(-1, Cout), w.view(Cout, Cin)).view(x.shape))
         else:
             W.push(tp, ops.conv2d_nhwc_wgrad(x, dy, KH, KW, stride, pad))
             if need_dx:
@@ -191,7 +192,7 @@ def linear(tp, x, lin):
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     w = lin.weight.detach().float()
-    y = ops.gemm(x2, w, lin.bias.detach().float() if lin.bias is not None else None).view(*shp[:-1], w.shape[0])
+    y = ops.train_linear(x2, w, lin.bias.detach().float() if lin.bias is not None else None).view(*shp[:-1], w.shape[0])
 
     def bwd():
         dy = tp.pop(y)
@@ -201,7 +202,7 @@ def linear(tp, x, lin):
         tp.padd(lin.weight, ops.gemm_tn(d2, x2))
         if lin.bias is not None:
             tp.padd(lin.bias, ops.colsum(d2))
-        tp.add(x, ops.gemm(d2, w.t().clone(memory_format=torch.contiguous_format)).view(shp))
+        tp.add(x, ops.train_dgrad(d2, w).view(shp))
     tp.record(bwd)
     return y
 

@@ -24,7 +24,7 @@ SQRT2 = float(np.sqrt(2))
 
 
 def _lin_fwd(x2d, lin, act=ops.ACT_NONE, res=None):
-    return ops.gemm(x2d, lin.weight, lin.bias, res=res, act=act)
+    return ops.train_linear(x2d, lin.weight, lin.bias, res=res, act=act)
 
 
 class _Grads:
@@ -49,9 +49,8 @@ def _lin_bwd(dy, x2d, lin, grads, need_dx=True):
         ops.colsum(dy, out=grads.buf(lin.bias), accumulate=True)
     if not need_dx:
         return None
-    # [K, N]: dX = dY @ W = gemm(dY, (W^T)); a weights-only transpose (tiny).  clone() normalises the strides of [K, 1]
-    wt = lin.weight.detach().t().clone(memory_format=torch.contiguous_format)
-    return ops.gemm(dy, wt)
+    # dX = dY @ W = gemm(dY, (W^T)): a weights-only transpose (+ tensor-core packing), then the forward GEMM kernel
+    return ops.train_dgrad(dy, lin.weight)
 
 
 def _ln_bwd(dy, x, norm, grads):

@@ -21,9 +21,9 @@ def _ohwi(conv):
 def _unit_fwd(tape, x, conv, bn, stride=1, pad=0, relu=True, res=None, update_stats=True):
     """x NHWC -> act(BN_batchstats(conv(x)) + res)."""
     w = _ohwi(conv)
-    # plain-fp32 convolution: batch-statistics BatchNorm over few samples (the 1x1 global branch) amplifies forward rounding
-    # in the gradients, and the backward kernels are fp32 as well
-    z = ops.conv2d_nhwc(x, w, None, stride, (pad, pad, pad, pad), tc=False)
+    # ops.TRAIN_ENGINE picks the tcgen05 implicit GEMM (ops.TRAIN_PRECISION) or the plain-fp32 convolution; note that
+    # batch-statistics BatchNorm over few samples (the 1x1 global branch) amplifies forward rounding in the gradients
+    z = ops.conv2d_nhwc(x, w, None, stride, (pad, pad, pad, pad), tc=ops.train_tc(), precision=ops.TRAIN_PRECISION)
     C = z.shape[-1]
     mean, var, rstd = ops.bn_stats(z.view(-1, C), bn.eps)
     gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
@@ -57,7 +57,7 @@ def _unit_bwd(e, dy, G, need_dx=True):
     gw = G.buf(conv.weight)                                # OIHW, the parameter's own layout
     if KH == 1 and KW == 1 and e["stride"] == 1 and e["pad"] == 0:
         ops.gemm_tn(dz.view(-1, Cout), x.view(-1, Cin), out=gw.view(Cout, Cin), accumulate=True)
-        dx = ops.gemm(dz.view(-1, Cout), w.view(Cout, Cin).t().clone(memory_format=torch.contiguous_format)).view(x.shape) if need_dx else None
+        dx = ops.train_dgrad(dz.view(-1, Cout), w.view(Cout, Cin)).view(x.shape) if need_dx else None
     else:
         p = e["pad"]
         dw = ops.conv2d_nhwc_wgrad(x, dz, KH, KW, e["stride"], (p, p, p, p))          # OHWI
@@ -105,13 +105,13 @@ def train_forward(mod, coord_nhwc):
     g = _bneck_conv_fwd(Ug, g, enc.fc[0])
     g = _bneck_conv_fwd(Ug, g, enc.fc[1])
     T["g_in"] = g.view(B, -1)
-    gl = ops.gemm(T["g_in"], enc.fc[2].weight, enc.fc[2].bias)                      # [B, latent]
+    gl = ops.train_linear(T["g_in"], enc.fc[2].weight, enc.fc[2].bias)                      # [B, latent]
     Ul = T["local"] = []
     y = _bneck_conv_fwd(Ul, feats[3], mod.depth_feat_proj[0])
     y = _bneck_conv_fwd(Ul, y, mod.depth_feat_proj[1])
     T["l_in"] = y
     pc = mod.depth_feat_proj[2]
-    yl = ops.gemm(y.view(-1, y.shape[-1]), pc.weight.detach().view(pc.weight.shape[0], -1), pc.bias)   # 1x1 conv with bias
+    yl = ops.train_linear(y.view(-1, y.shape[-1]), pc.weight.detach().view(pc.weight.shape[0], -1), pc.bias)   # 1x1 conv with bias
     out = torch.cat([gl.view(B, 1, -1), yl.view(B, -1, yl.shape[-1])], dim=1).contiguous()
     return out, T
 
@@ -131,14 +131,14 @@ def train_backward(mod, T, dout, need_dcoord=False):
     w2 = pc.weight.detach().view(pc.weight.shape[0], -1)
     ops.gemm_tn(dyl, y.view(-1, Cl), out=G.buf(pc.weight).view(w2.shape), accumulate=True)
     ops.colsum(dyl, out=G.buf(pc.bias), accumulate=True)
-    d = ops.gemm(dyl, w2.t().clone(memory_format=torch.contiguous_format)).view(y.shape)
+    d = ops.train_dgrad(dyl, w2).view(y.shape)
     d = _bneck_conv_bwd(T["local"], d, G)
     dfeat3_local = _bneck_conv_bwd(T["local"], d, G)
     # global branch: Linear <- 2 x Bottleneck_Conv(2048) <- average pool <- layer4 output
     fc = enc.fc[2]
     ops.gemm_tn(dgl, T["g_in"], out=G.buf(fc.weight), accumulate=True)
     ops.colsum(dgl, out=G.buf(fc.bias), accumulate=True)
-    d = ops.gemm(dgl, fc.weight.detach().t().clone(memory_format=torch.contiguous_format)).view(B, 1, 1, -1)
+    d = ops.train_dgrad(dgl, fc.weight).view(B, 1, 1, -1)
     d = _bneck_conv_bwd(T["global"], d, G)
     d = _bneck_conv_bwd(T["global"], d, G)
     _, H4, W4, C4 = T["feat4_shape"]

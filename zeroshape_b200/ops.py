@@ -274,7 +274,7 @@ def linear(x, w, bias=None, act=ACT_NONE, res=None, res_mode=RES_NONE, tc=None):
 
 
 def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=None, res_mode=RES_NONE,
-                pre_relu=False, tc=None):
+                pre_relu=False, tc=None, precision=None):
     """x [B,H,W,Cin]; w [Cout,KH,KW,Cin]; pad = (top, bottom, left, right).  `tc`: None = ENCODER_ENGINE policy, False = FFMA."""
     _chk(x, "x"); _chk(w, "w"); _chk(bias, "bias"); _chk(res, "res")
     B, H, W, Cin = x.shape
@@ -290,7 +290,7 @@ def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=ACT_NONE, res=N
         res_mode = RES_AFTER_ACT
     if Cin % 4 == 0 and KH * KW * Cin >= 32 and (tc if tc is not None else _encoder_tc()):
         check(lib.zs_conv2d_nhwc_tc(_p(x), B, H, W, Cin, _p(_packed_of(w).get()), _p(bias), _p(res), res_mode, _p(y), Cout,
-                                    KH, KW, stride, pt, pl, OH, OW, act, int(pre_relu), PRECISIONS[ENCODER_PRECISION],
+                                    KH, KW, stride, pt, pl, OH, OW, act, int(pre_relu), PRECISIONS[precision or ENCODER_PRECISION],
                                     _stream()), "zs_conv2d_nhwc_tc")
         return y
     check(lib.zs_conv2d_nhwc_f32(_p(x), B, H, W, Cin, _p(w), _p(bias), _p(res), res_mode, _p(y), Cout, KH, KW,
@@ -579,8 +579,45 @@ class OpTimer:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Training-step kernels (csrc/train.cu): fp32 backward of the implicit decoder, BCE shape loss, AdamW.
-def gemm_tn(a, b, out=None, accumulate=False):
+# Training-step kernels (csrc/train.cu, csrc/gemm_tn_tc.cu): backward of every layer, BCE shape loss, AdamW.
+#
+# The GEMM-shaped work of the step (forward, data gradients, weight gradients of every nn.Linear / nn.Conv2d) runs on the
+# tcgen05 kernels when TRAIN_ENGINE allows it: "auto" = tensor cores on an sm_100 device, "tc" = require them, "f32" = the
+# FFMA kernels (bit-faithful gradients for parity pinning).  TRAIN_PRECISION: "bf16x3" (fp32-grade, split operands) or
+# "bf16" (single pass with fp32 accumulation -- the mixed-precision mode of BASELINE config 3; master weights, activations and
+# gradients stay fp32 in memory).
+TRAIN_ENGINE = "auto"
+TRAIN_PRECISION = "bf16x3"
+TN_LAYOUT = 0          # operand layout of the TN (weight-gradient) kernel: 0 = MN-major tiles, 1 = K-major transposing producers
+
+
+def train_tc():
+    if TRAIN_ENGINE == "f32":
+        return False
+    ok = device_cc() == 100
+    if TRAIN_ENGINE == "tc" and not ok:
+        raise RuntimeError("TRAIN_ENGINE='tc' needs an sm_100 device")
+    return ok
+
+
+def train_linear(x2, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE):
+    """Forward of nn.Linear inside a training step: x2 [M,K] @ w[N,K]^T (+ bias ...)."""
+    N, K = w.shape
+    if train_tc() and N >= 64 and K >= 64:
+        return gemm_tc(x2, PackedWeight(w.detach()), bias, res, res_mode, act, precision=TRAIN_PRECISION)
+    return gemm(x2, w, bias, res, res_mode, act)
+
+
+def train_dgrad(dy, w):
+    """dX[M,K] = dY[M,N] @ w[N,K]  (data gradient of nn.Linear / a 1x1 convolution); weights-only transpose + pack."""
+    N, K = w.shape
+    wt = w.detach().t().contiguous()
+    if train_tc() and N >= 64 and K >= 64:
+        return gemm_tc(dy, PackedWeight(wt), precision=TRAIN_PRECISION)
+    return gemm(dy, wt)
+
+
+def gemm_tn(a, b, out=None, accumulate=False, tc=None):
     """out[N,K] (+)= a[M,N]^T @ b[M,K]  (weight gradient dW = dY^T X); 2-D row-strided inputs."""
     assert a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0] and a.stride(1) == 1 and b.stride(1) == 1
     M, N = a.shape
@@ -589,6 +626,10 @@ def gemm_tn(a, b, out=None, accumulate=False):
         out = torch.empty(N, K, device=a.device, dtype=torch.float32)
         accumulate = False
     assert out.shape == (N, K) and out.stride(1) == 1
+    if (tc if tc is not None else train_tc()) and N >= 32 and K >= 64 and M >= 128:
+        check(lib.zs_gemm_tn_tc(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, int(accumulate),
+                                PRECISIONS[TRAIN_PRECISION], TN_LAYOUT, _stream()), "zs_gemm_tn_tc")
+        return out
     check(lib.zs_gemm_tn_f32(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, int(accumulate), _stream()),
           "zs_gemm_tn_f32")
     return out
@@ -643,7 +684,9 @@ def mha_bwd(qkv, dout, heads):
     B, T, C3 = qkv.shape
     C = C3 // 3
     dqkv = torch.empty_like(qkv)
-    check(lib.zs_mha_bwd_f32(_p(qkv), _p(dout), _p(dqkv), B, T, heads, C // heads, (C // heads) ** -0.5, _stream()), "zs_mha_bwd_f32")
+    ws = torch.empty(lib.zs_mha_bwd_ws_bytes(B, T, heads), device=qkv.device, dtype=torch.uint8)
+    check(lib.zs_mha_bwd_f32(_p(qkv), _p(dout), _p(dqkv), B, T, heads, C // heads, (C // heads) ** -0.5, _p(ws), _stream()),
+          "zs_mha_bwd_f32")
     return dqkv
 
 
@@ -672,7 +715,7 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
                            _stream()), "zs_adamw_f32")
 
 
-def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad):
+def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad, tc=None):
     """dx [B,H,W,Cin] of conv2d_nhwc given dy [B,OH,OW,Cout]; w_ohwi [Cout,KH,KW,Cin]; pad = (top, bottom, left, right)."""
     _chk(dy, "dy"); _chk(w_ohwi, "w")
     B, H, W, Cin = in_shape
@@ -680,12 +723,16 @@ def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad):
     OH, OW = dy.shape[1], dy.shape[2]
     wd = w_ohwi.permute(3, 1, 2, 0).contiguous().view(Cin, KH * KW * Cout)       # weights only: [ci][(kh,kw,co)]
     dx = torch.empty(B, H, W, Cin, device=dy.device, dtype=torch.float32)
+    if (tc if tc is not None else train_tc()) and Cout % 4 == 0 and Cin >= 32 and KH * KW * Cout >= 64:
+        check(lib.zs_conv2d_nhwc_dgrad_tc(_p(dy), B, H, W, Cin, _p(PackedWeight(wd).get()), _p(dx), Cout, KH, KW, stride, pad[0], pad[2],
+                                          OH, OW, PRECISIONS[TRAIN_PRECISION], _stream()), "zs_conv2d_nhwc_dgrad_tc")
+        return dx
     check(lib.zs_conv2d_nhwc_dgrad_f32(_p(dy), B, H, W, Cin, _p(wd), _p(dx), Cout, KH, KW, stride, pad[0], pad[2], OH, OW, _stream()),
           "zs_conv2d_nhwc_dgrad_f32")
     return dx
 
 
-def conv2d_nhwc_wgrad(x, dy, kh, kw, stride, pad, out=None, accumulate=False):
+def conv2d_nhwc_wgrad(x, dy, kh, kw, stride, pad, out=None, accumulate=False, tc=None):
     """dw [Cout,KH,KW,Cin] (+)= wgrad of conv2d_nhwc."""
     _chk(x, "x"); _chk(dy, "dy")
     B, H, W, Cin = x.shape
@@ -694,6 +741,10 @@ def conv2d_nhwc_wgrad(x, dy, kh, kw, stride, pad, out=None, accumulate=False):
         out = torch.empty(Cout, kh, kw, Cin, device=x.device, dtype=torch.float32)
         accumulate = False
     _chk(out, "out")
+    if (tc if tc is not None else train_tc()) and Cin % 8 == 0 and Cout >= 32:
+        check(lib.zs_conv2d_nhwc_wgrad_tc(_p(x), B, H, W, Cin, _p(dy), _p(out), Cout, kh, kw, stride, pad[0], pad[2], OH, OW,
+                                          int(accumulate), PRECISIONS[TRAIN_PRECISION], TN_LAYOUT, _stream()), "zs_conv2d_nhwc_wgrad_tc")
+        return out
     check(lib.zs_conv2d_nhwc_wgrad_f32(_p(x), B, H, W, Cin, _p(dy), _p(out), Cout, kh, kw, stride, pad[0], pad[2], OH, OW,
                                        int(accumulate), _stream()), "zs_conv2d_nhwc_wgrad_f32")
     return out
