@@ -205,3 +205,63 @@ def test_attention_movie_matches_oracle_zmean(cuda):
     occ, frames = eval_3D.compute_level_grid(opt, m, lat.to(cuda), None, pts.to(cuda), img.to(cuda), vis_attn=True)
     assert occ.shape == (1, n, n, n) and len(frames) == 1 and len(frames[0]) == 9
     assert frames[0][0].shape == (224, 224, 3) and 0.0 <= frames[0][0].min() and frames[0][0].max() <= 1.0
+
+
+@pytest.mark.parametrize("sets,n,nq", [(1, 10000, 10000), (3, 700, 1300), (2, 33, 5), (1, 16384, 257), (4, 1, 40)])
+def test_nn_bvh_is_bit_identical_to_the_dense_chamfer(cuda, sets, n, nq):
+    """csrc/nn_bvh.cu (box hierarchy) vs csrc/chamfer.cu (every pair) vs the C restatement of the reference kernel:
+    squared distances bit-equal, indices equal (lowest index on ties: duplicated target points are planted)."""
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(sets * 1000 + n)
+    # a surface-like cloud (points on a noisy ellipsoid) plus exact duplicates, queries from a rotated copy + far outliers
+    t = torch.randn(sets, n, 3, generator=g)
+    t = t / t.norm(dim=-1, keepdim=True) * torch.tensor([0.5, 0.3, 0.4]) + 0.01 * torch.randn(sets, n, 3, generator=g)
+    if n > 40:
+        t[:, 7] = t[:, 31]
+        t[:, n - 1] = t[:, 2]
+    q = torch.randn(sets, nq, 3, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True) * torch.tensor([0.3, 0.5, 0.4])
+    q[:, : max(1, nq // 50)] *= 6.0
+    if n > 40:
+        q[:, -1] = t[:, 31]                       # an exact hit on a duplicated target: distance 0, index 7
+    td, qd = t.to(cuda).contiguous(), q.to(cuda).contiguous()
+    bvh = ops.NNBvh(td)
+    order = ops.NNBvh(qd[:1].contiguous()).morton_order()
+    for q_order in (None, order):
+        d, i = bvh.query(qd, q_order=q_order)
+        d_ref, _, i_ref, _ = ops.chamfer_nn(qd, td)
+        assert torch.equal(d, d_ref) and torch.equal(i, i_ref)
+    r1, _, j1, _ = E.chamfer_nn(q.numpy(), t.numpy())
+    assert np.array_equal(d.cpu().numpy(), r1) and np.array_equal(i.cpu().numpy(), j1)
+    assert sorted(order.cpu().tolist()) == list(range(nq))
+    # shared target / shared query forms used by the pose search
+    d_s, i_s = ops.NNBvh(td[:1].contiguous()).query(qd)
+    d_sr, _, i_sr, _ = ops.chamfer_nn(qd, td[:1].expand(sets, -1, -1).contiguous())
+    assert torch.equal(d_s, d_sr) and torch.equal(i_s, i_sr)
+    d_q, i_q = bvh.query(qd[:1].contiguous(), batch=sets)
+    d_qr, _, i_qr, _ = ops.chamfer_nn(qd[:1].expand(sets, -1, -1).contiguous(), td)
+    assert torch.equal(d_q, d_qr) and torch.equal(i_q, i_qr)
+
+
+def test_pose_search_bvh_equals_dense(cuda):
+    """utils/eval_3D.brute_force_search: the box-hierarchy path selects the same rotation and returns the same metrics as the
+    dense 10k x 10k Chamfer path (the reference's algorithm) on a reduced rotation table."""
+    from zeroshape_b200.utils import eval_3D as ours
+    from zeroshape_b200.utils import camera
+    g = torch.Generator().manual_seed(12)
+    gt = torch.randn(3000, 3, generator=g)
+    gt = gt / gt.norm(dim=-1, keepdim=True) * torch.tensor([0.5, 0.25, 0.35])
+    Rz = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    pred = (gt[torch.randperm(3000, generator=g)[:2500]] + 0.004 * torch.randn(2500, 3, generator=g)) @ Rz.T
+    real = camera.get_rotation_sphere
+    camera_small = lambda azim_sample, elev_sample, roll_sample, scales, device: real(8, 6, 4, scales, device)
+    saved = ours.get_rotation_sphere
+    ours.get_rotation_sphere = camera_small
+    try:
+        a = ours.brute_force_search(pred, gt, device=cuda, method="bvh", batch_size=50)
+        b = ours.brute_force_search(pred, gt, device=cuda, method="dense", batch_size=24)
+    finally:
+        ours.get_rotation_sphere = saved
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert torch.isfinite(a[0]) and torch.isfinite(a[1]) and a[2].shape == (6,)

@@ -82,6 +82,7 @@ def test_gemm_tn_tc(tc_ops, cuda, precision, M, N, K):
     dict(B=2, H=14, W=14, Cin=256, Cout=96, k=1, s=2, pad=(0, 0, 0, 0)),
     dict(B=1, H=30, W=30, Cin=32, Cout=32, k=3, s=1, pad=(1, 1, 1, 1)),
     dict(B=2, H=23, W=23, Cin=64, Cout=64, k=3, s=2, pad=(0, 1, 0, 1)),          # timm "SAME" padding of an odd map
+    dict(B=2, H=32, W=30, Cin=3, Cout=64, k=7, s=2, pad=(3, 3, 3, 3)),           # XYZ stem: FFMA forward / wgrad, warp-per-pixel dgrad
 ])
 def test_conv_gradients_tc(tc_ops, cuda, precision, cfg):
     ops = tc_ops

@@ -375,6 +375,45 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict
     }
 }
 
+// Data gradient for a stem convolution (Cin <= 4, e.g. the 7x7 / stride-2 XYZ stem of the seen-surface encoder): as a GEMM it
+// has N = Cin = 3 useful columns of a 128-wide tile.  Here one warp owns one input pixel: lanes run over the output channels of
+// every filter tap that reaches the pixel (coalesced dy rows, L1-resident weights), a shuffle reduction finishes the Cin sums.
+__global__ void __launch_bounds__(256) conv_dgrad_smallcin_kernel(const float* __restrict__ dy, const float* __restrict__ wd,
+                                                                  float* __restrict__ dx, int B, int H, int W, int Cin, int Cout, int KH,
+                                                                  int KW, int stride, int pad_top, int pad_left, int OH, int OW) {
+  const int64_t pix = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= (int64_t)B * H * W) return;
+  const int iw = (int)(pix % W);
+  const int64_t t = pix / W;
+  const int ih = (int)(t % H), b = (int)(t / H);
+  const int K = KH * KW * Cout;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < KH; ++kh) {
+    const int a = ih + pad_top - kh;
+    if (a < 0) break;                                   // a only decreases with kh
+    const int oh = a / stride;
+    if (oh * stride != a || oh >= OH) continue;
+    for (int kw = 0; kw < KW; ++kw) {
+      const int c = iw + pad_left - kw;
+      if (c < 0) break;
+      const int ow = c / stride;
+      if (ow * stride != c || ow >= OW) continue;
+      const float* g = dy + (((int64_t)b * OH + oh) * OW + ow) * Cout;
+      const float* wk = wd + (kh * KW + kw) * Cout;
+      for (int co = lane; co < Cout; co += 32) {
+        const float gv = __ldg(g + co);
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci < Cin) acc[ci] = fmaf(gv, __ldg(wk + (int64_t)ci * K + co), acc[ci]);
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) acc[ci] = warp_sum(acc[ci]);
+  if (lane < Cin) dx[pix * Cin + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+}
+
 }  // namespace zs
 
 extern "C" int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, int Cin, const float* w_dgrad, float* dx, int Cout,
@@ -387,6 +426,12 @@ extern "C" int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, in
   const int64_t M64 = (int64_t)B * H * W;
   ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_dgrad_f32: too many pixels");
   const int M = (int)M64, K = KH * KW * Cout;
+  if (Cin <= 4) {
+    conv_dgrad_smallcin_kernel<<<(unsigned)((M64 + 7) / 8), 256, 0, as_stream(stream)>>>(dy, w_dgrad, dx, B, H, W, Cin, Cout, KH, KW, stride,
+                                                                                       pad_top, pad_left, OH, OW);
+    ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_dgrad_f32(small Cin)");
+    return ZS_OK;
+  }
   DgradA a{dy, B, H, W, Cout, KH, KW, stride, pad_top, pad_left, OH, OW, M, K};
   Epilogue ep{nullptr, nullptr, Cin, ZS_RES_NONE, dx, Cin, ZS_ACT_NONE};
   return launch_gemm(a, w_dgrad, K, M, Cin, K, ep, as_stream(stream), "zs_conv2d_nhwc_dgrad_f32");

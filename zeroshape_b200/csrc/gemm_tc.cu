@@ -7,12 +7,12 @@
 //               -> ~2^-16 relative error per product (parity mode, meets the 1e-3 bar with margin)
 //   1 "bf16"  : D += Ah*Wh only (fast mode, ~1e-2 relative on the decoder logits -- not parity)
 //
-// CTA = 448 threads, persistent over 128x256 output tiles, warp-specialised:
-//   warps 0-3   A producers : fp32 rows -> (hi,lo) bf16 -> 128B-swizzled K-major smem tiles (generic proxy
-//                              stores + fence.proxy.async), one row per thread
-//   warps 4-11  epilogue    : tcgen05.ld accumulator rows -> bias / activation / residual -> fp32 global
-//   warp  12    MMA issuer  : one elected lane issues tcgen05.mma (M=128,N=256,K=16), commits to mbarriers
-//   warp  13    W loader    : cp.async.bulk (TMA 1-D) of pre-swizzled weight tiles, complete_tx on mbarriers
+// CTA = 576 threads, persistent over 128x256 output tiles, warp-specialised:
+//   warps 0-7   A producers : fp32 rows -> (hi,lo) bf16 -> 128B-swizzled K-major smem tiles (generic proxy
+//                              stores + fence.proxy.async), coalesced: thread = (row, 16-byte chunk)
+//   warps 8-15  epilogue    : tcgen05.ld accumulator rows -> bias / activation / residual -> fp32 global
+//   warp  16    MMA issuer  : one elected lane issues tcgen05.mma (M=128,N=256,K=16), commits to mbarriers
+//   warp  17    W loader    : cp.async.bulk (TMA 1-D) of pre-swizzled weight tiles, complete_tx on mbarriers
 // smem: 2 stages x (A_hi 16K + A_lo 16K + W_hi 32K + W_lo 32K) = 192 KB; TMEM: 2 x 256 fp32 columns
 // (accumulator double buffer: the epilogue of tile i overlaps the MMAs of tile i+1).
 #include "common.cuh"
@@ -26,7 +26,9 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_TILE = TC_BM * TC_BK * 2;   // 16 KB (one of hi/lo)
 constexpr int TC_B_TILE = TC_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_TILE + 2 * TC_B_TILE;  // 96 KB
-constexpr int TC_THREADS = 448;   // warps 0-3 A producers, 4-11 epilogue, 12 MMA issuer, 13 W loader
+constexpr int TC_PROD_WARPS = 8;                                     // warps 0-7 A producers, 8-15 epilogue, 16 MMA issuer, 17 W loader
+constexpr int TC_MMA_WARP = TC_PROD_WARPS + 8, TC_W_WARP = TC_PROD_WARPS + 9;
+constexpr int TC_THREADS = (TC_PROD_WARPS + 10) * 32;
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*softmax exchange*/;
 
 struct TcParams {
@@ -65,6 +67,7 @@ template <int ACT>
 __device__ __forceinline__ void tc_epilogue_half(const TcParams& p, uint32_t taddr, int m, int nt, int hsel) {
 #pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
+    if (hsel * 128 + c0 >= p.mma_n) break;                // warp-uniform: nothing was accumulated beyond the MMA width
     uint32_t rr[32];
     tmem_ld_32x32(taddr + c0, rr);
     tmem_ld_wait();
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), 128 + 1);   // 128 A-producer threads + 1 expect_tx arrival of the W loader
+      mbar_init(full_bar(s), TC_PROD_WARPS * 32 + 1);   // A-producer threads + 1 expect_tx arrival of the W loader
       mbar_init(empty_bar(s), 1);        // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -262,106 +265,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp < 4) {
+  if (warp < TC_PROD_WARPS) {
     // ================= A producers =================
-    const int r = threadIdx.x;  // row inside the tile
+    // thread = (16-byte bf16 chunk c of the 64-wide K-chunk, rows rb + 32 i): a warp reads four 256-byte row segments per
+    // instruction pair (coalesced) and writes whole 128-byte swizzled smem rows (conflict-free).  Eight warps, because one
+    // warp per scheduler converting a chunk is latency-bound (profiles/r1_gemm_tc_v0.md, the chained kernels' lesson).
+    const int c = threadIdx.x & 7, rb = threadIdx.x >> 3;
     int stage = 0; uint32_t phase = 0;
     const bool vec_ok = ((p.lda & 3) == 0) && ((p.a_nt_off & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-    // All 64 fp32 of a K-chunk are fetched into registers BEFORE waiting for the smem slot (also across
-    // tile boundaries), so the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
-    float4 buf[16];
-    int cb = 0, cih0 = 0, ciw0 = 0;          // AMODE 1: this thread's output pixel of the tile being fetched
-    bool crow_ok = false;
+    // The 8 fp32 of each unit are fetched into registers BEFORE waiting for the smem slot (also across tile boundaries), so
+    // the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
+    float4 buf[4][2];
+    int cb[4] = {0, 0, 0, 0}, cih0[4] = {0, 0, 0, 0}, ciw0[4] = {0, 0, 0, 0};   // conv modes: pixel of each of the thread's rows
+    bool crow_ok[4] = {false, false, false, false};
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch = [&](int t, int kc) {
-      const int m = (t / p.n_tiles) * TC_BM + r;
-      const int k0 = kc * TC_BK;
-      if (AMODE == 1) {
-        if (kc == 0) {
-          crow_ok = m < p.M;
-          const int ow = m % p.cOW, tt = m / p.cOW;
-          cb = tt / p.cOH;
-          cih0 = (tt % p.cOH) * p.cStride - p.cPadT;
-          ciw0 = ow * p.cStride - p.cPadL;
-        }
-        if ((p.cCin & 63) == 0) {
-          // the whole 64-wide K-chunk lies inside one filter tap: 256 contiguous bytes of one input pixel (or zeros)
-          const int tap = k0 / p.cCin, ci0 = k0 - tap * p.cCin;
-          const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
-          const int ih = cih0 + kh, iw = ciw0 + kw;
-          const bool ok = crow_ok && k0 < p.K && (unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW;
-          const float4* src = reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cH + (ok ? ih : 0)) * p.cW + (ok ? iw : 0)) * p.cCin + ci0);
+      const int m_base = (t / p.n_tiles) * TC_BM + rb;
+      const int k = kc * TC_BK + c * 8;
+      if (AMODE != 0 && kc == 0) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) buf[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          // generic (Cin % 4 == 0): decode the tap of every float4
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int k = k0 + c * 4;
-            const int tap = k / p.cCin, ci = k - tap * p.cCin;
-            const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
-            const int ih = cih0 + kh, iw = ciw0 + kw;
-            const bool ok = crow_ok && k < p.K && (unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW;
-            buf[c] = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cH + ih) * p.cW + iw) * p.cCin + ci))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {
+          const int m = m_base + 32 * i;
+          crow_ok[i] = m < p.M;
+          if (AMODE == 1) {
+            const int ow = m % p.cOW, tt = m / p.cOW;
+            cb[i] = tt / p.cOH;
+            cih0[i] = (tt % p.cOH) * p.cStride - p.cPadT;
+            ciw0[i] = ow * p.cStride - p.cPadL;
+          } else {
+            const int iw = m % p.cW, tt = m / p.cW;
+            cb[i] = tt / p.cH;
+            cih0[i] = (tt % p.cH) + p.cPadT;
+            ciw0[i] = iw + p.cPadL;
           }
         }
-        if (p.cPreRelu) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            buf[c] = make_float4(fmaxf(buf[c].x, 0.f), fmaxf(buf[c].y, 0.f), fmaxf(buf[c].z, 0.f), fmaxf(buf[c].w, 0.f));
-        }
-        return;
       }
-      if (AMODE == 2) {
-        // data gradient of a convolution: row m = INPUT pixel (b, ih, iw), K index = (kh, kw, co) gathered from
-        // dY [B, OH, OW, Cout] (p.cCin holds Cout): oh = (ih + pad_top - kh) / stride when exact and in range, else zero
-        if (kc == 0) {
-          crow_ok = m < p.M;
-          const int iw = m % p.cW, tt = m / p.cW;
-          cb = tt / p.cH;
-          cih0 = (tt % p.cH) + p.cPadT;
-          ciw0 = iw + p.cPadL;
+      if (AMODE == 1 || AMODE == 2) {
+        // K index = (kh, kw, channel); the two float4 of a unit share a filter tap when the channel count is a multiple of 8
+        int kh[2], kw[2], ch[2];
+        bool kok[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kk = k + 4 * h;
+          if (h == 1 && (p.cCin & 7) == 0) { kh[1] = kh[0]; kw[1] = kw[0]; ch[1] = ch[0] + 4; kok[1] = kok[0]; continue; }
+          const int tap = kk / p.cCin;
+          ch[h] = kk - tap * p.cCin;
+          kh[h] = tap / p.cKW;
+          kw[h] = tap - kh[h] * p.cKW;
+          kok[h] = kk < p.K;
         }
-        auto src_of = [&](int k, bool& ok) -> const float4* {
-          const int tap = k / p.cCin, co = k - tap * p.cCin;
-          const int kh = tap / p.cKW, kw = tap - kh * p.cKW;
-          const int a = cih0 - kh, bb = ciw0 - kw;
-          int oh = a, ow = bb;
-          ok = crow_ok && k < p.K && a >= 0 && bb >= 0;
-          if (p.cStride != 1) {
-            oh = a / p.cStride; ow = bb / p.cStride;
-            ok = ok && oh * p.cStride == a && ow * p.cStride == bb;
-          }
-          ok = ok && oh < p.cOH && ow < p.cOW;
-          return reinterpret_cast<const float4*>(p.A + (((int64_t)cb * p.cOH + (ok ? oh : 0)) * p.cOW + (ok ? ow : 0)) * p.cCin + co);
-        };
-        if ((p.cCin & 63) == 0) {
-          bool ok;
-          const float4* src = src_of(k0, ok);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) buf[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            bool ok;
-            const float4* src = src_of(k0 + c * 4, ok);
-            buf[c] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int h = 0; h < 2; ++h) {
+            float4 v = zero4;
+            if (AMODE == 1) {
+              const int ih = cih0[i] + kh[h], iw = ciw0[i] + kw[h];
+              if (crow_ok[i] && kok[h] && (unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW)
+                v = __ldg(reinterpret_cast<const float4*>(p.A + (((int64_t)cb[i] * p.cH + ih) * p.cW + iw) * p.cCin + ch[h]));
+              if (p.cPreRelu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            } else {
+              // data gradient: rows are INPUT pixels, the gather runs over dY [B, OH, OW, Cout] (p.cCin holds Cout):
+              // oh = (ih + pad_top - kh) / stride when exact and in range, else zero
+              const int a = cih0[i] - kh[h], bb = ciw0[i] - kw[h];
+              int oh = a, ow = bb;
+              bool ok = crow_ok[i] && kok[h] && a >= 0 && bb >= 0;
+              if (p.cStride != 1) {
+                oh = a / p.cStride; ow = bb / p.cStride;
+                ok = ok && oh * p.cStride == a && ow * p.cStride == bb;
+              }
+              ok = ok && oh < p.cOH && ow < p.cOW;
+              if (ok) v = __ldg(reinterpret_cast<const float4*>(p.A + (((int64_t)cb[i] * p.cOH + oh) * p.cOW + ow) * p.cCin + ch[h]));
+            }
+            buf[i][h] = v;
           }
         }
         return;
       }
-      const bool row_ok = m < p.M;
-      const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda + (t % p.n_tiles) * p.a_nt_off;
+      const int a_off = (t % p.n_tiles) * p.a_nt_off;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int k = k0 + c * 4;
-        if (row_ok && vec_ok && k + 4 <= p.K) {
-          buf[c] = __ldg(reinterpret_cast<const float4*>(arow + k));
-        } else {
-          float tt[4];
+      for (int i = 0; i < 4; ++i) {
+        const int m = m_base + 32 * i;
+        const bool row_ok = m < p.M;
+        const float* arow = p.A + (int64_t)(row_ok ? m : 0) * p.lda + a_off;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) tt[e] = (row_ok && k + e < p.K) ? __ldg(arow + k + e) : 0.f;
-          buf[c] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+        for (int h = 0; h < 2; ++h) {
+          const int kk = k + 4 * h;
+          if (row_ok && vec_ok && kk + 4 <= p.K) {
+            buf[i][h] = __ldg(reinterpret_cast<const float4*>(arow + kk));
+          } else {
+            float tt[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tt[e] = (row_ok && kk + e < p.K) ? __ldg(arow + kk + e) : 0.f;
+            buf[i][h] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+          }
         }
       }
     };
@@ -372,14 +369,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         uint8_t* a_hi = smem_gen + stage * TC_STAGE_BYTES;
         uint8_t* a_lo = a_hi + TC_A_TILE;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {   // 8 chunks of 8 elements (16 B of bf16)
-          const float4 x0 = buf[2 * c], x1 = buf[2 * c + 1];
+        for (int i = 0; i < 4; ++i) {
+          const float4 x0 = buf[i][0], x1 = buf[i][1];
           uint4 hi, lo;
           split_bf16x2(x0.x, x0.y, hi.x, lo.x);
           split_bf16x2(x0.z, x0.w, hi.y, lo.y);
           split_bf16x2(x1.x, x1.y, hi.z, lo.z);
           split_bf16x2(x1.z, x1.w, hi.w, lo.w);
-          const uint32_t off = swizzle128_offset(r, c);
+          const uint32_t off = swizzle128_offset(rb + 32 * i, c);
           *reinterpret_cast<uint4*>(a_hi + off) = hi;
           if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
         }
@@ -390,7 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == TC_W_WARP) {
     // ================= W loader =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -408,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == TC_MMA_WARP) {
     // ================= MMA issuer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -444,7 +441,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     // ================= epilogue: 8 warps; warp e -> TMEM lane quarter e&3, column half e>>2 =================
     // (two warps per SM sub-partition and a compile-time activation: a single warp per scheduler running a
     //  jump-table per element was latency-bound at ~0.2 IPC -- profiles/r1_gemm_tc_v0.md)
-    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int e = warp - TC_PROD_WARPS, q = e & 3, hsel = e >> 2;
     float* xch = reinterpret_cast<float*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 256);   // [2][128] softmax exchange
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -473,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -509,6 +506,16 @@ __global__ void gemm_tc_pack_kernel(const float* __restrict__ W, int ldw, int N,
 }  // namespace zs
 
 using namespace zs;
+
+// A layer narrower than one 256-column tile runs its MMAs at N = round_up(N, 16) and copies only those weight rows (the
+// first mma_n rows of a packed K-major tile are contiguous): less tensor work, 1/8 .. 1/2 of the weight traffic from L2.
+static void tc_narrow(zs::TcParams& p) {
+  if (p.n_tiles != 1 || p.N >= zs::TC_BN) return;
+  const int n16 = (p.N + 15) / 16 * 16;
+  p.mma_n = n16 < 16 ? 16 : n16;
+  p.n_tile_valid = p.N;
+  p.w_tile_bytes = (uint32_t)p.mma_n * 128u;
+}
 
 extern "C" size_t zs_gemm_tc_packed_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
@@ -548,6 +555,7 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.M = M; p.N = N; p.K = K; p.act = act; p.precision = precision;
   p.m_tiles = (M + TC_BM - 1) / TC_BM; p.n_tiles = (N + TC_BN - 1) / TC_BN; p.k_chunks = (K + TC_BK - 1) / TC_BK;
   p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  tc_narrow(p);
   p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.R_inv = nullptr; p.scale = 0.f; p.n_keys = 0; p.rowscale = nullptr;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
@@ -580,6 +588,7 @@ extern "C" int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, c
   p.M = (int)M64; p.N = Cout; p.K = KH * KW * Cin; p.act = act; p.precision = precision;
   p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.n_tiles = (p.N + TC_BN - 1) / TC_BN; p.k_chunks = (p.K + TC_BK - 1) / TC_BK;
   p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  tc_narrow(p);
   p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
   p.cOH = OH; p.cOW = OW; p.cPreRelu = pre_relu;
   int tiles = p.m_tiles * p.n_tiles;
@@ -673,6 +682,7 @@ extern "C" int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int
   p.M = (int)M64; p.N = Cin; p.K = KH * KW * Cout; p.act = ZS_ACT_NONE; p.precision = precision;
   p.m_tiles = (p.M + TC_BM - 1) / TC_BM; p.n_tiles = (p.N + TC_BN - 1) / TC_BN; p.k_chunks = (p.K + TC_BK - 1) / TC_BK;
   p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
+  tc_narrow(p);
   p.cB = B; p.cH = H; p.cW = W; p.cCin = Cout; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
   p.cOH = OH; p.cOW = OW; p.cPreRelu = 0;
   int tiles = p.m_tiles * p.n_tiles;

@@ -14,8 +14,8 @@
 // precision pass -- no transposition in registers or shared memory.  Layout 1 keeps the K-major operand tiles of gemm_tc.cu
 // with transposing producers (scalar loads); it exists to cross-check the MN-major descriptors on the device.
 //
-// CTA = 416 threads: warps 0-7 producers (fp32 -> (hi, lo) bf16 tiles), warps 8-11 epilogue (TMEM -> red.global.add into C),
-// warp 12 MMA issuer.  Work item = (128 x 256 output tile, split of the row range); split-K partial sums are combined with
+// CTA = 672 threads: warps 0-15 producers (fp32 -> (hi, lo) bf16 tiles), warps 16-19 epilogue (TMEM -> red.global.add into
+// C), warp 20 MMA issuer.  Work item = (128 x 256 output tile, split of the row range); split-K partial sums are combined with
 // fp32 reductions in L2 (C is zeroed by the wrapper unless `accumulate`).  2 smem stages x 96 KB, 2 x 256 TMEM columns.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -28,8 +28,10 @@ constexpr int TN_STAGES = 2;
 constexpr int TN_A_TILE = TN_BM * TN_BK * 2;            // 16 KB (one of hi / lo)
 constexpr int TN_B_TILE = TN_BN * TN_BK * 2;            // 32 KB
 constexpr int TN_STAGE_BYTES = 2 * TN_A_TILE + 2 * TN_B_TILE;
-constexpr int TN_PRODUCERS = 256;
-constexpr int TN_THREADS = 416;
+constexpr int TN_PROD_WARPS = 16;                       // latency-bound fp32 loads: 4 producer warps per scheduler
+constexpr int TN_PRODUCERS = TN_PROD_WARPS * 32;
+constexpr int TN_EPI_WARP0 = TN_PROD_WARPS, TN_MMA_WARP = TN_PROD_WARPS + 4;
+constexpr int TN_THREADS = (TN_PROD_WARPS + 5) * 32;
 constexpr int TN_SMEM = TN_STAGES * TN_STAGE_BYTES + 1024 + 256;
 
 struct TnParams {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == TN_MMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
 
   const int total_work = p.n_tiles * p.k_tiles * p.splits;
 
-  if (warp < 8) {
+  if (warp < TN_PROD_WARPS) {
     // ================= producers =================
     const int t = threadIdx.x;
     int stage = 0; uint32_t phase = 0;
@@ -164,11 +166,13 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
 
     if (p.layout != 1) {
       // ---- MN-major tiles: thread = (row r of the chunk, 16-byte chunk c of that row) ----
-      // A: 64 rows x 16 chunks (128 n-columns): c = t & 15, rows (t >> 4) + 16 i, i < 4
-      // B: 64 rows x 32 chunks (256 k-columns): c = t & 31, rows (t >> 5) + 8 i,  i < 8
+      // A: 64 rows x 16 chunks (128 n-columns): c = t & 15, rows (t >> 4) + 32 i, i < 2
+      // B: 64 rows x 32 chunks (256 k-columns): c = t & 31, rows (t >> 5) + 16 i, i < 4
       const int ca = t & 15, ra = t >> 4;
       const int cb = t & 31, rb = t >> 5;
-      float4 abuf[4][2], bbuf[8][2];
+      constexpr int NA = TN_BK * 16 / TN_PRODUCERS, NB = TN_BK * 32 / TN_PRODUCERS;      // units per thread: 2, 4
+      constexpr int SA = TN_PRODUCERS / 16, SB = TN_PRODUCERS / 32;                      // row strides: 32, 16
+      float4 abuf[NA][2], bbuf[NB][2];
       auto fetch = [&](int w, int chunk) {
         const int tile = w / p.splits;
         const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
@@ -176,9 +180,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
         const int colA = nt * TN_BM + ca * 8, colB = kt * TN_BN + cb * 8;
         if (BMODE == 1) decode_col(colB);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) load8A(m0 + ra + 16 * i, colA, abuf[i][0], abuf[i][1]);
+        for (int i = 0; i < NA; ++i) load8A(m0 + ra + SA * i, colA, abuf[i][0], abuf[i][1]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) load8B(m0 + rb + 8 * i, colB, bbuf[i][0], bbuf[i][1]);
+        for (int i = 0; i < NB; ++i) load8B(m0 + rb + SB * i, colB, bbuf[i][0], bbuf[i][1]);
       };
       auto chunk_range = [&](int w, int& c0, int& c1) {
         const int sp = w % p.splits;
@@ -196,15 +200,15 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
           uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
           uint8_t* b_lo = b_hi + TN_B_TILE;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = ra + 16 * i;                      // K-row of the chunk
+          for (int i = 0; i < NA; ++i) {
+            const int r = ra + SA * i;                      // K-row of the chunk
             const uint32_t off = (uint32_t)(r >> 3) * (2u * 1024u) + (uint32_t)(ca >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
                                  (uint32_t)(((ca & 7) ^ (r & 7)) << 4);
             put(a_hi, a_lo, off, abuf[i][0], abuf[i][1]);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rb + 8 * i;
+          for (int i = 0; i < NB; ++i) {
+            const int r = rb + SB * i;
             const uint32_t off = (uint32_t)(r >> 3) * (4u * 1024u) + (uint32_t)(cb >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
                                  (uint32_t)(((cb & 7) ^ (r & 7)) << 4);
             put(b_hi, b_lo, off, bbuf[i][0], bbuf[i][1]);
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
         }
       }
     }
-  } else if (warp == 12) {
+  } else if (warp == TN_MMA_WARP) {
     // ================= MMA issuer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
       }
     }
   } else {
-    // ================= epilogue: warps 8-11, warp q owns TMEM lanes 32q .. 32q+31 (rows n of the tile) =================
+    // ================= epilogue: warps 16-19, warp q owns TMEM lanes 32q .. 32q+31 (rows n of the tile) =================
     const int q = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == TN_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -374,8 +378,8 @@ static int launch_tn(TnParams& p, int accumulate, cudaStream_t st, const char* w
   p.k_tiles = (p.Kc + TN_BN - 1) / TN_BN;
   p.total_chunks = (p.M + TN_BK - 1) / TN_BK;
   const int tiles = p.n_tiles * p.k_tiles;
-  int splits = (sm_count() + tiles - 1) / tiles;           // about one work item per SM
-  if (splits > p.total_chunks) splits = p.total_chunks;
+  int splits = sm_count() / tiles;                         // at most one work item per SM: a second item on a few CTAs
+  if (splits > p.total_chunks) splits = p.total_chunks;    // would double the kernel's duration (one wave, no tail)
   if (splits < 1) splits = 1;
   p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
   p.splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;

@@ -173,33 +173,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 }
 
 // ---- point -> (latents + self) attention backward (head dim 32) --------------------------------------------------
-// One CTA per (head, image): walks the image's P query points in tiles of 128 (thread = point) and keeps the latent-side
+// One CTA per (head, image): walks the image's P query points in tiles of 256 (thread = point) and keeps the latent-side
 // gradients dK_lat_h, dV_lat_h [L,32] of its (image, head) in shared memory for the whole walk -> no atomics, deterministic.
-// Per tile and block of 32 keys the threads publish ds[p][j] and p[p][j]; the CTA then reduces dK += ds^T Q, dV += p^T dO.
+// Per tile and block of 16 keys the threads publish ds[p][j] and p[p][j]; the CTA then reduces dK += ds^T Q, dV += p^T dO.
+constexpr int PAB_NT = 256, PAB_KB = 16;     // threads (= points per tile) and latent keys per reduction block
 template <int HD>
-__global__ void __launch_bounds__(128) point_attention_bwd_kernel(
+__global__ void __launch_bounds__(PAB_NT) point_attention_bwd_kernel(
     const float* __restrict__ qkv, const float* __restrict__ k_lat, const float* __restrict__ v_lat, int ld_lat,
     const float* __restrict__ O, const float* __restrict__ dO, float* __restrict__ dqkv, float* __restrict__ dk_lat,
     float* __restrict__ dv_lat, int ld_dlat, int P, int L, int heads, float scale) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* Ks = sm;                   // [L][HD]
   float* Vs = Ks + L * HD;          // [L][HD]
   float* dKs = Vs + L * HD;         // [L][HD]
   float* dVs = dKs + L * HD;        // [L][HD]
-  float* Qs = dVs + L * HD;         // [128][HD+1]
-  float* Gs = Qs + 128 * (HD + 1);  // [128][HD+1]  (dO)
-  float* dsT = Gs + 128 * (HD + 1); // [32][129]
-  float* pT = dsT + 32 * 129;       // [32][129]
+  float* Qs = dVs + L * HD;         // [NT][HD+1]
+  float* Gs = Qs + PAB_NT * (HD + 1);  // [NT][HD+1]  (dO)
+  float* dsT = Gs + PAB_NT * (HD + 1); // [KB][NT+1]
+  float* pT = dsT + PAB_KB * (PAB_NT + 1);       // [KB][NT+1]
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
   const int C = heads * HD;
-  for (int i = t; i < L * HD; i += 128) {
+  for (int i = t; i < L * HD; i += PAB_NT) {
     const int j = i / HD, d = i % HD;
     Ks[i] = k_lat[((int64_t)b * L + j) * ld_lat + h * HD + d];
     Vs[i] = v_lat[((int64_t)b * L + j) * ld_lat + h * HD + d];
     dKs[i] = 0.f; dVs[i] = 0.f;
   }
   __syncthreads();
-  for (int p0 = 0; p0 < P; p0 += 128) {
+  for (int p0 = 0; p0 < P; p0 += PAB_NT) {
     const int p = p0 + t;
     const bool live = p < P;
     const int64_t row = (int64_t)b * P + (live ? p : 0);
@@ -219,19 +220,19 @@ __global__ void __launch_bounds__(128) point_attention_bwd_kernel(
 #pragma unroll
     for (int d = 0; d < HD; ++d) s_self = fmaf(q[d], live ? qkv[row * 3 * C + C + h * HD + d] : 0.f, s_self);
     s_self *= scale;
-    float mx = s_self;
+    // one online-softmax sweep over the latent keys (running max + rescaled sum); K rows are read as broadcast float4
+    float mx = s_self, sum = 1.0f;
     for (int j = 0; j < L; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD);
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
-      mx = fmaxf(mx, s * scale);
-    }
-    float sum = expf(s_self - mx);
-    for (int j = 0; j < L; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], Ks[j * HD + d], s);
-      sum += expf(s * scale - mx);
+      for (int d4 = 0; d4 < HD / 4; ++d4) {
+        const float4 k = kr[d4];
+        s = fmaf(q[4 * d4], k.x, s); s = fmaf(q[4 * d4 + 1], k.y, s); s = fmaf(q[4 * d4 + 2], k.z, s); s = fmaf(q[4 * d4 + 3], k.w, s);
+      }
+      s *= scale;
+      if (s > mx) { sum *= expf(mx - s); mx = s; }
+      sum += expf(s - mx);
     }
     const float inv = 1.0f / sum;
     // the point's own key / value
@@ -250,39 +251,51 @@ __global__ void __launch_bounds__(128) point_attention_bwd_kernel(
       }
     }
     // pass 2: latent keys in blocks of 32
-    for (int jb = 0; jb < L; jb += 32) {
-      for (int jj = 0; jj < 32; ++jj) {
+    for (int jb = 0; jb < L; jb += PAB_KB) {
+      for (int jj = 0; jj < PAB_KB; ++jj) {
         const int j = jb + jj;
         float dsv = 0.f, pv = 0.f;
         if (j < L && live) {
           float s = 0.f, dp = 0.f;
+          const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD);
+          const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD);
+          float4 kk[HD / 4];
 #pragma unroll
-          for (int d = 0; d < HD; ++d) { s = fmaf(q[d], Ks[j * HD + d], s); dp = fmaf(g[d], Vs[j * HD + d], dp); }
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 k = kr[d4], v = vr[d4];
+            kk[d4] = k;
+            s = fmaf(q[4 * d4], k.x, s); s = fmaf(q[4 * d4 + 1], k.y, s); s = fmaf(q[4 * d4 + 2], k.z, s); s = fmaf(q[4 * d4 + 3], k.w, s);
+            dp = fmaf(g[4 * d4], v.x, dp); dp = fmaf(g[4 * d4 + 1], v.y, dp); dp = fmaf(g[4 * d4 + 2], v.z, dp); dp = fmaf(g[4 * d4 + 3], v.w, dp);
+          }
           pv = expf(s * scale - mx) * inv;
           dsv = pv * (dp - D) * scale;
 #pragma unroll
-          for (int d = 0; d < HD; ++d) dq[d] = fmaf(dsv, Ks[j * HD + d], dq[d]);
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            dq[4 * d4] = fmaf(dsv, kk[d4].x, dq[4 * d4]); dq[4 * d4 + 1] = fmaf(dsv, kk[d4].y, dq[4 * d4 + 1]);
+            dq[4 * d4 + 2] = fmaf(dsv, kk[d4].z, dq[4 * d4 + 2]); dq[4 * d4 + 3] = fmaf(dsv, kk[d4].w, dq[4 * d4 + 3]);
+          }
         }
-        dsT[jj * 129 + t] = dsv;
-        pT[jj * 129 + t] = pv;
+        dsT[jj * (PAB_NT + 1) + t] = dsv;
+        pT[jj * (PAB_NT + 1) + t] = pv;
       }
       __syncthreads();
       {
-        // thread -> key jj = t / 4, dims d0 = (t % 4) * 8 .. +8
-        const int jj = t >> 2, d0 = (t & 3) * (HD / 4);
+        // thread -> key jj = t / TPK, dims d0 = (t % TPK) * DPT .. + DPT
+        constexpr int TPK = PAB_NT / PAB_KB, DPT = HD / TPK;
+        const int jj = t / TPK, d0 = (t % TPK) * DPT;
         const int j = jb + jj;
         if (j < L) {
-          float ak[HD / 4] = {}, av[HD / 4] = {};
-          for (int pp = 0; pp < 128; ++pp) {
-            const float dsv = dsT[jj * 129 + pp], pv = pT[jj * 129 + pp];
+          float ak[DPT] = {}, av[DPT] = {};
+          for (int pp = 0; pp < PAB_NT; ++pp) {
+            const float dsv = dsT[jj * (PAB_NT + 1) + pp], pv = pT[jj * (PAB_NT + 1) + pp];
 #pragma unroll
-            for (int i = 0; i < HD / 4; ++i) {
+            for (int i = 0; i < DPT; ++i) {
               ak[i] = fmaf(dsv, Qs[pp * (HD + 1) + d0 + i], ak[i]);
               av[i] = fmaf(pv, Gs[pp * (HD + 1) + d0 + i], av[i]);
             }
           }
 #pragma unroll
-          for (int i = 0; i < HD / 4; ++i) { dKs[j * HD + d0 + i] += ak[i]; dVs[j * HD + d0 + i] += av[i]; }
+          for (int i = 0; i < DPT; ++i) { dKs[j * HD + d0 + i] += ak[i]; dVs[j * HD + d0 + i] += av[i]; }
         }
       }
       __syncthreads();
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(128) point_attention_bwd_kernel(
     }
     __syncthreads();
   }
-  for (int i = t; i < L * HD; i += 128) {
+  for (int i = t; i < L * HD; i += PAB_NT) {
     const int j = i / HD, d = i % HD;
     dk_lat[((int64_t)b * L + j) * ld_dlat + h * HD + d] = dKs[i];
     dv_lat[((int64_t)b * L + j) * ld_dlat + h * HD + d] = dVs[i];
@@ -857,10 +870,10 @@ extern "C" int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat
                                           int L, int heads, int hd, float scale, void* stream) {
   ZS_REQUIRE(qkv_p && k_lat && v_lat && O && dO && dqkv_p && dk_lat && dv_lat, "zs_point_attention_bwd_f32: null pointer");
   ZS_REQUIRE(hd == 32 && B > 0 && P > 0 && L > 0 && heads > 0, "zs_point_attention_bwd_f32: head dim must be 32");
-  const size_t smem = sizeof(float) * ((size_t)4 * L * 32 + 2 * 128 * 33 + 2 * 32 * 129);
-  ZS_REQUIRE(smem <= 200 * 1024, "zs_point_attention_bwd_f32: too many latent tokens for shared memory");
+  const size_t smem = sizeof(float) * ((size_t)4 * L * 32 + 2 * PAB_NT * 33 + 2 * PAB_KB * (PAB_NT + 1));
+  ZS_REQUIRE(smem <= 227 * 1024, "zs_point_attention_bwd_f32: too many latent tokens for shared memory");
   ZS_CUDA_CALL(cudaFuncSetAttribute(point_attention_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  point_attention_bwd_kernel<32><<<dim3(heads, B), 128, smem, as_stream(stream)>>>(qkv_p, k_lat, v_lat, ld_lat, O, dO, dqkv_p, dk_lat,
+  point_attention_bwd_kernel<32><<<dim3(heads, B), PAB_NT, smem, as_stream(stream)>>>(qkv_p, k_lat, v_lat, ld_lat, O, dO, dqkv_p, dk_lat,
                                                                                   dv_lat, ld_dlat, P, L, heads, scale);
   ZS_CUDA_CHECK_LAUNCH("zs_point_attention_bwd_f32");
   return ZS_OK;

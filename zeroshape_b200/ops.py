@@ -474,6 +474,38 @@ def chamfer_nn_bwd(xyz1, xyz2, g1, g2, i1, i2):
     return gx1, gx2
 
 
+class NNBvh:
+    """Flat box hierarchy over `sets` point clouds [sets, n, 3] (zs_nn_bvh_build): exact NN queries at ~1/20 of the
+    brute-force pair evaluations, same distances / tie-breaking as `chamfer_nn`."""
+
+    def __init__(self, pts):
+        _chk(pts, "pts")
+        assert pts.dim() == 3 and pts.shape[2] == 3
+        self.sets, self.n = pts.shape[0], pts.shape[1]
+        self.blob = torch.empty(lib.zs_nn_bvh_bytes(self.sets, self.n), device=pts.device, dtype=torch.uint8)
+        check(lib.zs_nn_bvh_build(_p(pts), self.sets, self.n, _p(self.blob), _stream()), "zs_nn_bvh_build")
+
+    def morton_order(self, s=0):
+        """Original indices of set `s` in Morton order (int32 [n]): a cache-friendly processing order for queries made of
+        the same points under any rigid / similarity transform."""
+        npad = (self.n + 31) // 32 * 32
+        per_set = self.blob.numel() // self.sets
+        pts = self.blob[s * per_set: s * per_set + npad * 16].view(torch.int32).view(npad, 4)
+        return pts[:self.n, 3].contiguous()
+
+    def query(self, q, batch=None, q_order=None):
+        """q [sets_q, nq, 3] (sets_q = 1: shared by the batch) -> dist [batch, nq] (squared), idx [batch, nq] int32."""
+        _chk(q, "q")
+        sets_q, nq = q.shape[0], q.shape[1]
+        batch = batch or max(self.sets, sets_q)
+        dist = torch.empty(batch, nq, device=q.device, dtype=torch.float32)
+        idx = torch.empty(batch, nq, device=q.device, dtype=torch.int32)
+        _chk(q_order, "q_order", torch.int32)
+        check(lib.zs_nn_bvh_query(_p(self.blob), self.sets, self.n, _p(q), sets_q, nq, batch, _p(q_order), _p(dist), _p(idx),
+                                  _stream()), "zs_nn_bvh_query")
+        return dist, idx
+
+
 def chamfer_stats(sq1, sq2, thresholds, squared=True):
     _chk(sq1, "sq1"); _chk(sq2, "sq2")
     b, n = sq1.shape
@@ -611,7 +643,7 @@ def train_linear(x2, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE):
 def train_dgrad(dy, w):
     """dX[M,K] = dY[M,N] @ w[N,K]  (data gradient of nn.Linear / a 1x1 convolution); weights-only transpose + pack."""
     N, K = w.shape
-    wt = w.detach().t().contiguous()
+    wt = w.detach().t().clone(memory_format=torch.contiguous_format)      # clone() normalises the strides of a [K, 1] transpose
     if train_tc() and N >= 64 and K >= 64:
         return gemm_tc(dy, PackedWeight(wt), precision=TRAIN_PRECISION)
     return gemm(dy, wt)

@@ -241,16 +241,31 @@ def eval_metrics_default(opt, var, impl_network, vis_only=False):
 
 
 @torch.no_grad()
-def brute_force_search(pc_pred, pc_gt, f_thresholds=[0.005, 0.01, 0.02, 0.05, 0.1, 0.2], device="cuda", batch_size=24):
-    """6912-rotation pose search (utils/eval_3D.py:140-170); running argmin kept on the device."""
+def brute_force_search(pc_pred, pc_gt, f_thresholds=[0.005, 0.01, 0.02, 0.05, 0.1, 0.2], device="cuda", batch_size=None, method="bvh"):
+    """6912-rotation pose search (utils/eval_3D.py:140-170); running argmin kept on the device.
+
+    method "bvh" (default): nearest neighbours through flat box hierarchies (csrc/nn_bvh.cu) -- one over the normalised GT
+    cloud, built once, queried by every rotated prediction; one per rotated prediction (a CTA each), queried by the GT points.
+    Distances are bit-identical to the dense Chamfer kernel's, so the selected rotation and the metrics are those of
+    method "dense" (the reference's 288 batched 10k x 10k Chamfer calls, ops.chamfer_nn), at ~1/20 of the pair evaluations."""
     pc_pred = pc_pred.to(device).unsqueeze(0).float()
-    pc_gt = normalize_pc(pc_gt.to(device).unsqueeze(0).float().contiguous())
+    pc_gt = normalize_pc(pc_gt.to(device).unsqueeze(0).float().contiguous()).contiguous()
     rotations = get_rotation_sphere(azim_sample=24, elev_sample=24, roll_sample=12, scales=[1.0], device=device)
+    if batch_size is None:
+        batch_size = 288 if method == "bvh" else 24
+    if method == "bvh":
+        gt_bvh = ops.NNBvh(pc_gt)
+        gt_order = gt_bvh.morton_order()
+        pred_order = ops.NNBvh(pc_pred.contiguous()).morton_order()      # a Morton order survives every rotation of the cloud
     best = None
     for i in range(0, len(rotations), batch_size):
         R = rotations[i:i + batch_size]
         rot = normalize_pc((R @ pc_pred.permute(0, 2, 1)).permute(0, 2, 1)).contiguous()
-        d1, d2, _, _ = ops.chamfer_nn(rot, pc_gt.expand(R.shape[0], -1, -1).contiguous())
+        if method == "bvh":
+            d1, _ = gt_bvh.query(rot, q_order=pred_order)
+            d2, _ = ops.NNBvh(rot).query(pc_gt, batch=R.shape[0], q_order=gt_order)
+        else:
+            d1, d2, _, _ = ops.chamfer_nn(rot, pc_gt.expand(R.shape[0], -1, -1).contiguous())
         acc, comp, p, r = ops.chamfer_stats(d1, d2, f_thresholds)
         cd = (acc + comp) / 2
         j = int(torch.argmin(cd))            # first minimum == the reference's strict-< scan order
