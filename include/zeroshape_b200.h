@@ -218,6 +218,10 @@ int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T,
 /* torch.optim.AdamW step (decoupled weight decay, bias correction) on one flat tensor; `step` counts from 1. */
 int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, void* stream);
+/* The same step for every parameter tensor of the optimizer in one launch.  `table` (device memory) = n_tensors rows of five
+ * 64-bit words {param, grad, exp_avg, exp_avg_sq (device addresses), numel}; identical arithmetic to zs_adamw_f32. */
+int zs_adamw_multi_f32(const void* table, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       int step, void* stream);
 
 /* Training of the seen-surface encoder (CoordEncRes: torchvision ResNet-50 + Bottleneck_Conv heads with batch-statistics
  * BatchNorm, model/shape/seen_coord_enc.py:141-194; the `optim.fix_dpt` configuration of options/shape.yaml).
@@ -236,8 +240,8 @@ int zs_conv2d_nhwc_wgrad_f32(const float* x, int B, int H, int W, int Cin, const
  *    filter re-laid as Wd[Cin, KH*KW*Cout] (the operand of zs_conv2d_nhwc_dgrad_f32)
  *  - zs_gemm_tn_tc          : C[N,K] (+)= A[M,N]^T B[M,K]  (dW = dY^T X), split over the rows, fp32 reductions into C
  *  - zs_conv2d_nhwc_wgrad_tc: dw [Cout,KH,KW,Cin] (+)= dY^T im2col(x), the im2col gathered on the fly (Cin % 8 == 0)
- * `layout` selects the shared-memory operand layout of the TN kernels: 0 = MN-major SWIZZLE_128B tiles (no transposition,
- * the default), 1 = K-major tiles filled by transposing producers (cross-check), 2 = diagnostic. */
+ * `layout` names the shared-memory operand layout of the TN kernels and must be 0: MN-major SWIZZLE_128B tiles (the reduction
+ * runs over the rows of both fp32 matrices, so no transposition is needed anywhere). */
 int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int Cin, const void* Wpacked, float* dx, int Cout,
                             int KH, int KW, int stride, int pad_top, int pad_left, int OH, int OW, int precision, void* stream);
 int zs_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,

@@ -69,6 +69,7 @@ SIGNATURES = {
     "zs_bilinear_bwd_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_unproject_normalize_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "zs_adamw_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "zs_adamw_multi_f32": (c_int, [P, c_int, c_float, c_float, c_float, c_float, c_float, c_int, P]),
     "zs_mean_axis1_f32": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
     "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),

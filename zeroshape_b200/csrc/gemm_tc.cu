@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(full_bar(s), TC_PROD_WARPS * 32 + 1);   // A-producer threads + 1 expect_tx arrival of the W loader
+      mbar_init(full_bar(s), TC_PROD_WARPS + 1);        // one arrival per A-producer warp + 1 expect_tx arrival of the W loader
       mbar_init(empty_bar(s), 1);        // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -273,13 +273,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     const int c = threadIdx.x & 7, rb = threadIdx.x >> 3;
     int stage = 0; uint32_t phase = 0;
     const bool vec_ok = ((p.lda & 3) == 0) && ((p.a_nt_off & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-    // The 8 fp32 of each unit are fetched into registers BEFORE waiting for the smem slot (also across tile boundaries), so
-    // the global/L2 latency of the next chunk overlaps the MMAs that still own the slot.
-    float4 buf[4][2];
+    // The 8 fp32 of each unit are fetched into registers one K-chunk ahead of their conversion (also across tile boundaries),
+    // so the global / L2 latency of the next chunk overlaps the MMAs that still own the smem slot.  (A second register buffer
+    // -- two chunks of look-ahead -- was measured on B200: the conv modes spill at the 96-register cap of an 18-warp CTA and
+    // every GEMM class of the training step got 5-25 % slower; profiles/r1_train_launches.md.)
+    float4 buf0[4][2];
     int cb[4] = {0, 0, 0, 0}, cih0[4] = {0, 0, 0, 0}, ciw0[4] = {0, 0, 0, 0};   // conv modes: pixel of each of the thread's rows
     bool crow_ok[4] = {false, false, false, false};
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](int t, int kc) {
+    auto fetch = [&](float4 (&buf)[4][2], int t, int kc) {
       const int m_base = (t / p.n_tiles) * TC_BM + rb;
       const int k = kc * TC_BK + c * 8;
       if (AMODE != 0 && kc == 0) {
@@ -362,30 +364,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
         }
       }
     };
-    if (blockIdx.x < total_tiles) fetch(blockIdx.x, 0);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        uint8_t* a_hi = smem_gen + stage * TC_STAGE_BYTES;
-        uint8_t* a_lo = a_hi + TC_A_TILE;
+    auto consume = [&](float4 (&buf)[4][2]) {
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      uint8_t* a_hi = smem_gen + stage * TC_STAGE_BYTES;
+      uint8_t* a_lo = a_hi + TC_A_TILE;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x0 = buf[i][0], x1 = buf[i][1];
-          uint4 hi, lo;
-          split_bf16x2(x0.x, x0.y, hi.x, lo.x);
-          split_bf16x2(x0.z, x0.w, hi.y, lo.y);
-          split_bf16x2(x1.x, x1.y, hi.z, lo.z);
-          split_bf16x2(x1.z, x1.w, hi.w, lo.w);
-          const uint32_t off = swizzle128_offset(rb + 32 * i, c);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar(stage));
-        if (kc + 1 < p.k_chunks) fetch(t, kc + 1);
-        else if (t + (int)gridDim.x < total_tiles) fetch(t + gridDim.x, 0);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < 4; ++i) {
+        const float4 x0 = buf[i][0], x1 = buf[i][1];
+        uint4 hi, lo;
+        split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+        split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+        split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+        split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+        const uint32_t off = swizzle128_offset(rb + 32 * i, c);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp (its 32 stores are fenced and ordered)
+      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    };
+    // fetch iterator (runs one (tile, chunk) item ahead of the consume iterator, in the same order)
+    int ft = blockIdx.x, fkc = 0;
+    auto fetch_next = [&](float4 (&buf)[4][2]) {
+      if (ft >= total_tiles) return;
+      fetch(buf, ft, fkc);
+      if (++fkc == p.k_chunks) { fkc = 0; ft += gridDim.x; }
+    };
+    fetch_next(buf0);
+    int64_t items = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) items += p.k_chunks;
+    for (int64_t it = 0; it < items; ++it) {
+      consume(buf0);
+      fetch_next(buf0);
     }
   } else if (warp == TC_W_WARP) {
     // ================= W loader =================

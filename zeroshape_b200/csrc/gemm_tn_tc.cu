@@ -11,12 +11,14 @@
 // are "MN-major": element (n, m) of the A operand sits next to (n+1, m).  The shared-memory tiles use the canonical
 // MN-major SWIZZLE_128B layout (64 MN-elements = 128 B per K-row, 8 K-rows per 1024-byte atom, atoms tiled MN-first) so a
 // producer thread turns 8 consecutive fp32 of one row (two float4 loads, fully coalesced) into ONE 16-byte bf16 chunk per
-// precision pass -- no transposition in registers or shared memory.  Layout 1 keeps the K-major operand tiles of gemm_tc.cu
-// with transposing producers (scalar loads); it exists to cross-check the MN-major descriptors on the device.
+// precision pass -- no transposition in registers or shared memory.  (Round-1 bring-up cross-checked these descriptors on B200
+// against a K-major variant with transposing producers: both exact on integer operands; the transposing variant was dropped.)
 //
 // CTA = 672 threads: warps 0-15 producers (fp32 -> (hi, lo) bf16 tiles), warps 16-19 epilogue (TMEM -> red.global.add into
 // C), warp 20 MMA issuer.  Work item = (128 x 256 output tile, split of the row range); split-K partial sums are combined with
-// fp32 reductions in L2 (C is zeroed by the wrapper unless `accumulate`).  2 smem stages x 96 KB, 2 x 256 TMEM columns.
+// fp32 reductions in L2 (C is zeroed by the wrapper unless `accumulate`).  2 smem stages x 96 KB (64 reduced rows each), the
+// producers fetch one stage ahead of their conversion (4 x 48 KB stages with two stages of look-ahead measured 20 % slower);
+// 2 x 256 TMEM columns.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -41,7 +43,7 @@ struct TnParams {
   int M, N, Kc;
   int n_tiles, k_tiles, splits, chunks_per_split, total_chunks;
   int precision;     // 0 = bf16x3, 1 = bf16
-  int layout;        // 0 = MN-major operand tiles, 1 = K-major tiles (transposing producers), 2 = MN-major, LBO/SBO swapped
+  int layout;        // 0 = MN-major operand tiles (the only layout; validated on B200 against K-major transposing producers)
   // BMODE 1: Bm = im2col of an NHWC image; row m = output pixel (b, oh, ow), column = (kh, kw, ci)
   int cB, cH, cW, cCin, cKH, cKW, cStride, cPadT, cPadL, cOH, cOW;
 };
@@ -72,18 +74,19 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + TN_STAGES * TN_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto tfull_bar = [&](int a) { return bar_base + 32u + 8u * a; };
-  auto tempty_bar = [&](int a) { return bar_base + 48u + 8u * a; };
-  const uint32_t tmem_slot = bar_base + 64u;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TN_STAGES * TN_STAGE_BYTES + 64);
+  auto empty_bar = [&](int s) { return bar_base + 8u * TN_STAGES + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 16u * TN_STAGES + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 16u * TN_STAGES + 16u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 16u * TN_STAGES + 32u;
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + TN_STAGES * TN_STAGE_BYTES + 16 * TN_STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = p.precision == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TN_STAGES; ++s) {
-      mbar_init(full_bar(s), TN_PRODUCERS);
+      mbar_init(full_bar(s), TN_PROD_WARPS);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -99,13 +102,27 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int total_work = p.n_tiles * p.k_tiles * p.splits;
+  auto chunk_range = [&](int w, int& c0, int& c1) {
+    const int sp = w % p.splits;
+    c0 = sp * p.chunks_per_split;
+    c1 = min(p.total_chunks, c0 + p.chunks_per_split);
+  };
 
   if (warp < TN_PROD_WARPS) {
     // ================= producers =================
+    // thread = (row r of the chunk, 16-byte bf16 chunk c of that row) of the MN-major tiles:
+    //   A: 64 rows x 16 chunks (128 n-columns): c = t & 15, rows (t >> 4) + 32 i, i < 2
+    //   B: 64 rows x 32 chunks (256 k-columns): c = t & 31, rows (t >> 5) + 16 i, i < 4
+    // A warp reads whole 512-byte / 1-KB row segments and writes whole 128-byte swizzled smem rows (conflict-free).
     const int t = threadIdx.x;
     int stage = 0; uint32_t phase = 0;
     const bool vecA = ((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
     const bool vecB = BMODE == 1 ? true : (((p.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0));
+    const int ca = t & 15, ra = t >> 4;
+    const int cb = t & 31, rb = t >> 5;
+    constexpr int NA = TN_BK * 16 / TN_PRODUCERS, NB = TN_BK * 32 / TN_PRODUCERS;      // units per thread: 2, 4
+    constexpr int SA = TN_PRODUCERS / 16, SB = TN_PRODUCERS / 32;                      // row strides: 32, 16
+    struct Buf { float4 a[NA][2], b[NB][2]; };
 
     // 8 consecutive columns of row m of A / Bm (zero outside the matrix)
     auto load8A = [&](int m, int col, float4& x0, float4& x1) {
@@ -122,19 +139,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
         x0 = make_float4(v[0], v[1], v[2], v[3]); x1 = make_float4(v[4], v[5], v[6], v[7]);
       }
     };
-    // BMODE 1 column decode (constant per work item for a thread in the MN-major layout)
+    // BMODE 1: the thread's 8 columns lie inside one filter tap (Cin % 8 == 0) = 32 contiguous bytes of one input pixel
     int tap_kh = 0, tap_kw = 0, tap_ci = 0;
-    auto decode_col = [&](int col) {
-      const int tap = col / p.cCin;
-      tap_ci = col - tap * p.cCin;
-      tap_kh = tap / p.cKW;
-      tap_kw = tap - tap_kh * p.cKW;
-    };
     auto load8B = [&](int m, int col, float4& x0, float4& x1) {
       x0 = x1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m >= p.M || col >= p.Kc) return;
       if (BMODE == 1) {
-        // Cin % 8 == 0: the 8 columns lie inside one filter tap = 32 contiguous bytes of one input pixel
         const int ow = m % p.cOW, tt = m / p.cOW;
         const int oh = tt % p.cOH, b = tt / p.cOH;
         const int ih = oh * p.cStride - p.cPadT + tap_kh, iw = ow * p.cStride - p.cPadL + tap_kw;
@@ -163,127 +173,73 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
       *reinterpret_cast<uint4*>(hi_tile + off) = hi;
       if (split) *reinterpret_cast<uint4*>(lo_tile + off) = lo;
     };
-
-    if (p.layout != 1) {
-      // ---- MN-major tiles: thread = (row r of the chunk, 16-byte chunk c of that row) ----
-      // A: 64 rows x 16 chunks (128 n-columns): c = t & 15, rows (t >> 4) + 32 i, i < 2
-      // B: 64 rows x 32 chunks (256 k-columns): c = t & 31, rows (t >> 5) + 16 i, i < 4
-      const int ca = t & 15, ra = t >> 4;
-      const int cb = t & 31, rb = t >> 5;
-      constexpr int NA = TN_BK * 16 / TN_PRODUCERS, NB = TN_BK * 32 / TN_PRODUCERS;      // units per thread: 2, 4
-      constexpr int SA = TN_PRODUCERS / 16, SB = TN_PRODUCERS / 32;                      // row strides: 32, 16
-      float4 abuf[NA][2], bbuf[NB][2];
-      auto fetch = [&](int w, int chunk) {
-        const int tile = w / p.splits;
-        const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
-        const int m0 = chunk * TN_BK;
-        const int colA = nt * TN_BM + ca * 8, colB = kt * TN_BN + cb * 8;
-        if (BMODE == 1) decode_col(colB);
-#pragma unroll
-        for (int i = 0; i < NA; ++i) load8A(m0 + ra + SA * i, colA, abuf[i][0], abuf[i][1]);
-#pragma unroll
-        for (int i = 0; i < NB; ++i) load8B(m0 + rb + SB * i, colB, bbuf[i][0], bbuf[i][1]);
-      };
-      auto chunk_range = [&](int w, int& c0, int& c1) {
-        const int sp = w % p.splits;
-        c0 = sp * p.chunks_per_split;
-        c1 = min(p.total_chunks, c0 + p.chunks_per_split);
-      };
-      int w = blockIdx.x, c0 = 0, c1 = 0;
-      if (w < total_work) { chunk_range(w, c0, c1); fetch(w, c0); }
-      for (; w < total_work; w += gridDim.x) {
-        chunk_range(w, c0, c1);
-        for (int c = c0; c < c1; ++c) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          uint8_t* a_hi = smem_gen + stage * TN_STAGE_BYTES;
-          uint8_t* a_lo = a_hi + TN_A_TILE;
-          uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
-          uint8_t* b_lo = b_hi + TN_B_TILE;
-#pragma unroll
-          for (int i = 0; i < NA; ++i) {
-            const int r = ra + SA * i;                      // K-row of the chunk
-            const uint32_t off = (uint32_t)(r >> 3) * (2u * 1024u) + (uint32_t)(ca >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                                 (uint32_t)(((ca & 7) ^ (r & 7)) << 4);
-            put(a_hi, a_lo, off, abuf[i][0], abuf[i][1]);
-          }
-#pragma unroll
-          for (int i = 0; i < NB; ++i) {
-            const int r = rb + SB * i;
-            const uint32_t off = (uint32_t)(r >> 3) * (4u * 1024u) + (uint32_t)(cb >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                                 (uint32_t)(((cb & 7) ^ (r & 7)) << 4);
-            put(b_hi, b_lo, off, bbuf[i][0], bbuf[i][1]);
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar(stage));
-          if (c + 1 < c1) fetch(w, c + 1);
-          else if (w + (int)gridDim.x < total_work) { int n0, n1; chunk_range(w + gridDim.x, n0, n1); fetch(w + gridDim.x, n0); }
-          if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
-        }
+    // fetch iterator over (work item, chunk): runs one chunk ahead of the conversion, so a chunk's L2 / DRAM round trip
+    // overlaps the MMAs that still own the smem slot
+    int fw = blockIdx.x, fc = 0, fc1 = 0;
+    if (fw < total_work) chunk_range(fw, fc, fc1);
+    auto fetch_next = [&](Buf& buf) {
+      if (fw >= total_work) return;
+      const int tile = fw / p.splits;
+      const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+      const int m0 = fc * TN_BK;
+      const int colA = nt * TN_BM + ca * 8, colB = kt * TN_BN + cb * 8;
+      if (BMODE == 1) {
+        const int tap = colB / p.cCin;
+        tap_ci = colB - tap * p.cCin;
+        tap_kh = tap / p.cKW;
+        tap_kw = tap - tap_kh * p.cKW;
       }
-    } else {
-      // ---- K-major tiles (layout of gemm_tc.cu): thread = (column, group of 8 rows), scalar loads, transposed store ----
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = w / p.splits, sp = w % p.splits;
-        const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
-        const int c0 = sp * p.chunks_per_split, c1 = min(p.total_chunks, c0 + p.chunks_per_split);
-        for (int c = c0; c < c1; ++c) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          uint8_t* a_hi = smem_gen + stage * TN_STAGE_BYTES;
-          uint8_t* a_lo = a_hi + TN_A_TILE;
-          uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
-          uint8_t* b_lo = b_hi + TN_B_TILE;
-          const int m0 = c * TN_BK;
-          for (int u = t; u < TN_BM * 8; u += TN_PRODUCERS) {        // A: 128 columns x 8 row groups
-            const int n = u & (TN_BM - 1), j = u >> 7;
-            const int col = nt * TN_BM + n;
-            float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int m = m0 + j * 8 + e;
-              v[e] = (m < p.M && col < p.N) ? __ldg(p.A + (int64_t)m * p.lda + col) : 0.f;
-            }
-            put(a_hi, a_lo, swizzle128_offset(n, j), make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
-          }
-          for (int u = t; u < TN_BN * 8; u += TN_PRODUCERS) {        // B: 256 columns x 8 row groups
-            const int n = u & (TN_BN - 1), j = u >> 8;
-            const int col = kt * TN_BN + n;
-            if (BMODE == 1) decode_col(col < p.Kc ? col : 0);
-            float v[8];
+      for (int i = 0; i < NA; ++i) load8A(m0 + ra + SA * i, colA, buf.a[i][0], buf.a[i][1]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int m = m0 + j * 8 + e;
-              float x = 0.f;
-              if (m < p.M && col < p.Kc) {
-                if (BMODE == 1) {
-                  const int ow = m % p.cOW, tt = m / p.cOW;
-                  const int oh = tt % p.cOH, b = tt / p.cOH;
-                  const int ih = oh * p.cStride - p.cPadT + tap_kh, iw = ow * p.cStride - p.cPadL + tap_kw;
-                  if ((unsigned)ih < (unsigned)p.cH && (unsigned)iw < (unsigned)p.cW)
-                    x = __ldg(p.B + (((int64_t)b * p.cH + ih) * p.cW + iw) * p.cCin + tap_ci);
-                } else {
-                  x = __ldg(p.B + (int64_t)m * p.ldb + col);
-                }
-              }
-              v[e] = x;
-            }
-            put(b_hi, b_lo, swizzle128_offset(n, j), make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
-          }
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar(stage));
-          if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
-        }
+      for (int i = 0; i < NB; ++i) load8B(m0 + rb + SB * i, colB, buf.b[i][0], buf.b[i][1]);
+      if (++fc == fc1) {
+        fw += gridDim.x;
+        if (fw < total_work) chunk_range(fw, fc, fc1);
       }
+    };
+    auto consume = [&](const Buf& buf) {
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      uint8_t* a_hi = smem_gen + stage * TN_STAGE_BYTES;
+      uint8_t* a_lo = a_hi + TN_A_TILE;
+      uint8_t* b_hi = a_hi + 2 * TN_A_TILE;
+      uint8_t* b_lo = b_hi + TN_B_TILE;
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        const int r = ra + SA * i;                      // K-row of the chunk
+        const uint32_t off = (uint32_t)(r >> 3) * (2u * 1024u) + (uint32_t)(ca >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                             (uint32_t)(((ca & 7) ^ (r & 7)) << 4);
+        put(a_hi, a_lo, off, buf.a[i][0], buf.a[i][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int r = rb + SB * i;
+        const uint32_t off = (uint32_t)(r >> 3) * (4u * 1024u) + (uint32_t)(cb >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                             (uint32_t)(((cb & 7) ^ (r & 7)) << 4);
+        put(b_hi, b_lo, off, buf.b[i][0], buf.b[i][1]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));      // one arrival per producer warp (its 32 stores are fenced and ordered)
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1; }
+    };
+    Buf buf0;
+    fetch_next(buf0);
+    int64_t items = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) { int c0, c1; chunk_range(w, c0, c1); items += c1 - c0; }
+    for (int64_t it = 0; it < items; ++it) {
+      consume(buf0);
+      fetch_next(buf0);
     }
   } else if (warp == TN_MMA_WARP) {
     // ================= MMA issuer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const bool mn = p.layout != 1;
-      const uint32_t idesc = umma_idesc_bf16(TN_BM, TN_BN) | (mn ? ((1u << 15) | (1u << 16)) : 0u);
+      const uint32_t idesc = umma_idesc_bf16(TN_BM, TN_BN) | (1u << 15) | (1u << 16);     // A and B MN-major
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int sp = w % p.splits;
-        const int c0 = sp * p.chunks_per_split, c1 = min(p.total_chunks, c0 + p.chunks_per_split);
+        int c0, c1;
+        chunk_range(w, c0, c1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TN_BN;
@@ -294,22 +250,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
           const uint32_t sb = sa + 2 * TN_A_TILE;
 #pragma unroll
           for (int k = 0; k < TN_BK / 16; ++k) {
-            uint64_t a_hi, a_lo, b_hi, b_lo;
-            if (mn) {
-              // one MMA consumes 16 K-rows = two 8-row groups: A groups are 2 KB apart (2 atoms of 64 n), B groups 4 KB
-              const uint32_t aoff = (uint32_t)k * 2u * 2048u, boff = (uint32_t)k * 2u * 4096u;
-              if (p.layout == 0) {
-                a_hi = umma_desc_mn_sw128(sa + aoff, 1024u, 2048u); a_lo = umma_desc_mn_sw128(sa + TN_A_TILE + aoff, 1024u, 2048u);
-                b_hi = umma_desc_mn_sw128(sb + boff, 1024u, 4096u); b_lo = umma_desc_mn_sw128(sb + TN_B_TILE + boff, 1024u, 4096u);
-              } else {
-                a_hi = umma_desc_mn_sw128(sa + aoff, 2048u, 1024u); a_lo = umma_desc_mn_sw128(sa + TN_A_TILE + aoff, 2048u, 1024u);
-                b_hi = umma_desc_mn_sw128(sb + boff, 4096u, 1024u); b_lo = umma_desc_mn_sw128(sb + TN_B_TILE + boff, 4096u, 1024u);
-              }
-            } else {
-              const uint64_t koff = (uint64_t)((k * 32) >> 4);
-              a_hi = umma_desc_sw128(sa) + koff; a_lo = umma_desc_sw128(sa + TN_A_TILE) + koff;
-              b_hi = umma_desc_sw128(sb) + koff; b_lo = umma_desc_sw128(sb + TN_B_TILE) + koff;
-            }
+            // one MMA consumes 16 K-rows = two 8-row groups: A groups are 2 KB apart (2 atoms of 64 n), B groups 4 KB
+            const uint32_t aoff = (uint32_t)k * 2u * 2048u, boff = (uint32_t)k * 2u * 4096u;
+            const uint64_t a_hi = umma_desc_mn_sw128(sa + aoff, 1024u, 2048u), a_lo = umma_desc_mn_sw128(sa + TN_A_TILE + aoff, 1024u, 2048u);
+            const uint64_t b_hi = umma_desc_mn_sw128(sb + boff, 1024u, 4096u), b_lo = umma_desc_mn_sw128(sb + TN_B_TILE + boff, 1024u, 4096u);
             umma_bf16(d_tmem, a_hi, b_hi, idesc, (c != c0 || k != 0) ? 1u : 0u);
             if (split) {
               umma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
@@ -403,7 +347,7 @@ extern "C" int zs_gemm_tn_tc(const float* A, int lda, const float* B, int ldb, f
   ZS_REQUIRE(A && B && C, "zs_gemm_tn_tc: null pointer");
   ZS_REQUIRE(M > 0 && M < (1LL << 31) && N > 0 && K > 0 && lda >= N && ldb >= K && ldc >= K, "zs_gemm_tn_tc: bad shape");
   ZS_REQUIRE(precision == 0 || precision == 1, "zs_gemm_tn_tc: precision must be 0 (bf16x3) or 1 (bf16)");
-  ZS_REQUIRE(layout >= 0 && layout <= 2, "zs_gemm_tn_tc: layout must be 0 (MN-major), 1 (K-major) or 2");
+  ZS_REQUIRE(layout == 0, "zs_gemm_tn_tc: layout must be 0 (MN-major operand tiles)");
   TnParams p{};
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.M = (int)M; p.N = N; p.Kc = K; p.precision = precision; p.layout = layout;
@@ -419,7 +363,7 @@ extern "C" int zs_conv2d_nhwc_wgrad_tc(const float* x, int B, int H, int W, int 
   ZS_REQUIRE((Cin & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0,
              "zs_conv2d_nhwc_wgrad_tc: needs Cin %% 8 == 0 and a 16-byte aligned image");
   ZS_REQUIRE(precision == 0 || precision == 1, "zs_conv2d_nhwc_wgrad_tc: precision must be 0 (bf16x3) or 1 (bf16)");
-  ZS_REQUIRE(layout >= 0 && layout <= 2, "zs_conv2d_nhwc_wgrad_tc: layout must be 0, 1 or 2");
+  ZS_REQUIRE(layout == 0, "zs_conv2d_nhwc_wgrad_tc: layout must be 0 (MN-major operand tiles)");
   const int64_t M64 = (int64_t)B * OH * OW;
   ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_wgrad_tc: too many output pixels");
   TnParams p{};

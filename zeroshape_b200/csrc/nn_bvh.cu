@@ -6,11 +6,13 @@
 // bit-identical), lowest index on ties -- at ~1/20 of the pair evaluations:
 //   build : one CTA per point set.  Points are sorted along a 30-bit Morton curve of the set's bounding cube
 //           (cub::BlockRadixSort in shared memory) and cut into clusters of 32 consecutive points, each with its
-//           tight axis-aligned box.  A surface cloud of 10,000 points gives 313 compact patches.
+//           tight axis-aligned box; 16 consecutive clusters share a super-box.  A surface cloud of 10,000 points gives
+//           313 compact patches under 20 super-boxes.
 //   query : one thread per query point, the target set's boxes in shared memory (every thread of the CTA scans the same
-//           list: broadcast reads, no divergence).  Pass 1 finds the box with the smallest lower bound and scans its 32
-//           points; pass 2 visits every other box whose (conservatively rounded) lower bound does not exceed the best
-//           distance so far.  Exact: a skipped box cannot hold a closer -- or an equally close, lower-index -- point.
+//           super-box list: broadcast reads, no divergence).  Pass 1 descends to the box with the smallest lower bound
+//           and scans its 32 points; pass 2 opens every super-box, and inside it every box, whose (conservatively
+//           rounded) lower bound does not exceed the best distance so far.  Exact: a skipped box cannot hold a closer --
+//           or an equally close, lower-index -- point.
 // Distances are evaluated on the caller's own fp32 coordinates (no re-centring / rotation inside), so they are the very
 // numbers the brute-force kernel produces.
 #include <cub/block/block_radix_sort.cuh>
@@ -19,7 +21,7 @@
 namespace zs {
 
 constexpr int BVH_THREADS = 1024, BVH_ITEMS = 16, BVH_MAX_N = BVH_THREADS * BVH_ITEMS;   // 16,384 points per set
-constexpr int BVH_CLUSTER = 32;
+constexpr int BVH_CLUSTER = 32, BVH_SUPER = 16;      // points per box, boxes per super-box (= one warp of the build kernel)
 
 __device__ __forceinline__ float sqdist_ref_bvh(float tx, float ty, float tz, float qx, float qy, float qz) {
   // == sqdist_ref of chamfer.cu: what nvcc emits for the reference expression x2*x2+y2*y2+z2*z2 (chamfer3D.cu:32)
@@ -28,10 +30,12 @@ __device__ __forceinline__ float sqdist_ref_bvh(float tx, float ty, float tz, fl
 }
 
 __host__ __device__ inline int bvh_padded(int n) { return (n + BVH_CLUSTER - 1) / BVH_CLUSTER * BVH_CLUSTER; }
-// per set: float4 points[NP] (x, y, z, original index as int bits; padding = +inf), then float boxes[NC][8] (min xyz, -, max xyz, -)
+__host__ __device__ inline int bvh_supers(int n) { return (bvh_padded(n) / BVH_CLUSTER + BVH_SUPER - 1) / BVH_SUPER; }
+// per set: float4 points[NP] (x, y, z, original index as int bits; padding = +inf), float boxes[NC][8] (min xyz, -, max xyz, -),
+// float superboxes[NS][8]
 __host__ __device__ inline size_t bvh_set_bytes(int n) {
   const size_t np = (size_t)bvh_padded(n);
-  return np * 16 + (np / BVH_CLUSTER) * 32;
+  return np * 16 + (np / BVH_CLUSTER) * 32 + (size_t)bvh_supers(n) * 32;
 }
 
 __device__ __forceinline__ unsigned spread10(unsigned v) {     // 10 bits -> every third bit
@@ -129,6 +133,20 @@ __global__ void __launch_bounds__(BVH_THREADS) nn_bvh_build_kernel(const float* 
     b[0] = cmn[0]; b[1] = cmn[1]; b[2] = cmn[2]; b[3] = 0.f;
     b[4] = cmx[0]; b[5] = cmx[1]; b[6] = cmx[2]; b[7] = 0.f;
   }
+  // a warp holds 16 consecutive clusters = one super-box (empty clusters contribute +inf / -inf)
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 1; o >>= 1) {
+      cmn[a] = fminf(cmn[a], __shfl_xor_sync(0xffffffffu, cmn[a], o));
+      cmx[a] = fmaxf(cmx[a], __shfl_xor_sync(0xffffffffu, cmx[a], o));
+    }
+  }
+  if (lane == 0 && warp < bvh_supers(n)) {
+    float* b = boxes + (size_t)(NP / BVH_CLUSTER) * 8 + (size_t)warp * 8;
+    b[0] = cmn[0]; b[1] = cmn[1]; b[2] = cmn[2]; b[3] = 0.f;
+    b[4] = cmx[0]; b[5] = cmx[1]; b[6] = cmx[2]; b[7] = 0.f;
+  }
 }
 
 constexpr int BVQ_THREADS = 256;
@@ -137,13 +155,13 @@ __global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_kernel(const uint8_t
                                                                    const float* __restrict__ q, int sets_q, int nq,
                                                                    const int32_t* __restrict__ q_order, float* __restrict__ dist,
                                                                    int32_t* __restrict__ idx) {
-  extern __shared__ __align__(16) float sbox[];          // [NC][8]
+  extern __shared__ __align__(16) float sbox[];          // [NC + NS][8]: boxes, then super-boxes
   const int b = blockIdx.y;
-  const int NP = bvh_padded(n), NC = NP / BVH_CLUSTER;
+  const int NP = bvh_padded(n), NC = NP / BVH_CLUSTER, NS = bvh_supers(n);
   const uint8_t* base = bvh + (size_t)(sets_t == 1 ? 0 : b) * bvh_set_bytes(n);
   const float4* pts = reinterpret_cast<const float4*>(base);
   const float4* gbox = reinterpret_cast<const float4*>(base + (size_t)NP * 16);
-  for (int i = threadIdx.x; i < NC * 2; i += BVQ_THREADS) reinterpret_cast<float4*>(sbox)[i] = gbox[i];
+  for (int i = threadIdx.x; i < (NC + NS) * 2; i += BVQ_THREADS) reinterpret_cast<float4*>(sbox)[i] = gbox[i];
   __syncthreads();
   const int slot = blockIdx.x * BVQ_THREADS + threadIdx.x;
   if (slot >= nq) return;
@@ -170,16 +188,28 @@ __global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_kernel(const uint8_t
       if (d < best || (d == best && ti < besti)) { best = d; besti = ti; }     // lowest original index on ties
     }
   };
-  int first = 0;
+  // pass 1: closest super-box -> its closest box -> a first candidate
+  int s_first = 0, first = 0;
   float lb_first = INFINITY;
-  for (int c = 0; c < NC; ++c) {
+  for (int s = 0; s < NS; ++s) {
+    const float lb = lower(NC + s);
+    if (lb < lb_first) { lb_first = lb; s_first = s; }
+  }
+  lb_first = INFINITY;
+  first = s_first * BVH_SUPER;
+  for (int c = s_first * BVH_SUPER; c < min(NC, (s_first + 1) * BVH_SUPER); ++c) {
     const float lb = lower(c);
     if (lb < lb_first) { lb_first = lb; first = c; }
   }
   visit(first);
-  for (int c = 0; c < NC; ++c) {
-    if (c == first) continue;
-    if (lower(c) <= best) visit(c);
+  // pass 2: everything that can still hold a point at most as far
+  for (int s = 0; s < NS; ++s) {
+    if (!(lower(NC + s) <= best)) continue;
+    const int c1 = min(NC, (s + 1) * BVH_SUPER);
+    for (int c = s * BVH_SUPER; c < c1; ++c) {
+      if (c == first) continue;
+      if (lower(c) <= best) visit(c);
+    }
   }
   dist[(int64_t)b * nq + qi] = best;
   idx[(int64_t)b * nq + qi] = besti;
@@ -215,7 +245,7 @@ extern "C" int zs_nn_bvh_query(const void* bvh, int sets_t, int n, const float* 
   ZS_REQUIRE((sets_t == 1 || sets_t == batch) && (sets_q == 1 || sets_q == batch),
              "zs_nn_bvh_query: target / query set counts must be 1 (shared) or the batch size");
   ZS_REQUIRE(n <= BVH_MAX_N && batch <= 65535, "zs_nn_bvh_query: too many points per set or too large a batch");
-  const int smem = bvh_padded(n) / BVH_CLUSTER * 32;
+  const int smem = (bvh_padded(n) / BVH_CLUSTER + bvh_supers(n)) * 32;
   dim3 grid((nq + BVQ_THREADS - 1) / BVQ_THREADS, batch);
   nn_bvh_query_kernel<<<grid, BVQ_THREADS, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(bvh), sets_t, n, q, sets_q, nq,
                                                                      q_order, dist, idx);

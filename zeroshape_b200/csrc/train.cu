@@ -774,9 +774,42 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// all parameter tensors of the optimizer in ONE launch: `table` holds, per tensor, {param, grad, exp_avg, exp_avg_sq, numel}
+// as five 64-bit words; blockIdx.y = tensor, the CTAs of a row stride over its elements
+__global__ void adamw_multi_kernel(const unsigned long long* __restrict__ table, float lr, float b1, float b2, float eps, float wd,
+                                   float bc1, float bc2_sqrt) {
+  const unsigned long long* e = table + (size_t)blockIdx.y * 5;
+  float* __restrict__ p = reinterpret_cast<float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  float* __restrict__ m = reinterpret_cast<float*>(e[2]);
+  float* __restrict__ v = reinterpret_cast<float*>(e[3]);
+  const int64_t n = (int64_t)e[4];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i] * (1.0f - lr * wd);
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
 }  // namespace zs
 
 using namespace zs;
+
+extern "C" int zs_adamw_multi_f32(const void* table, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  int step, void* stream) {
+  ZS_REQUIRE(table && n_tensors >= 0 && n_tensors <= 65535 && step >= 1, "zs_adamw_multi_f32: bad args");
+  if (n_tensors == 0) return ZS_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_multi_kernel<<<dim3(48, n_tensors), 256, 0, as_stream(stream)>>>(reinterpret_cast<const unsigned long long*>(table), lr, beta1,
+                                                                         beta2, eps, weight_decay, bc1, bc2);
+  ZS_CUDA_CHECK_LAUNCH("zs_adamw_multi_f32");
+  return ZS_OK;
+}
 
 extern "C" int zs_bce_logits_fwd(const float* logits, const float* sdf, int64_t n, float impt_thres, float impt_weight,
                                  double* ws, float* loss, void* stream) {

@@ -258,11 +258,12 @@ class FusedAdamW:
     @torch.no_grad()
     def step(self):
         self.steps += 1
-        for p in self.params:
-            if p.grad is None:
-                continue
-            m, v = self.state[id(p)]
-            ops.adamw_step(p.detach(), p.grad.contiguous(), m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.steps)
+        live = [p for p in self.params if p.grad is not None]
+        grads = [p.grad.contiguous() for p in live]               # kept alive until the launch is enqueued
+        ops.adamw_step_multi([p.detach() for p in live], grads, [self.state[id(p)][0] for p in live],
+                             [self.state[id(p)][1] for p in live], self.lr, self.betas[0], self.betas[1], self.eps,
+                             self.weight_decay, self.steps)
+        for p in live:
             # the kernel wrote through the raw pointer: bump the version counter so that the packed-weight caches
             # (keyed on data_ptr / _version) re-pack, exactly as after a torch optimizer step
             torch.autograd.graph.increment_version(p)

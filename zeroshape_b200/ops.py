@@ -620,7 +620,7 @@ class OpTimer:
 # gradients stay fp32 in memory).
 TRAIN_ENGINE = "auto"
 TRAIN_PRECISION = "bf16x3"
-TN_LAYOUT = 0          # operand layout of the TN (weight-gradient) kernel: 0 = MN-major tiles, 1 = K-major transposing producers
+TN_LAYOUT = 0          # operand layout of the TN (weight-gradient) kernel: MN-major tiles
 
 
 def train_tc():
@@ -745,6 +745,19 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_d
         _chk(t, n)
     check(lib.zs_adamw_f32(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, weight_decay, step,
                            _stream()), "zs_adamw_f32")
+
+
+def adamw_step_multi(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps, weight_decay, step):
+    """AdamW for a whole parameter list in one launch (zs_adamw_multi_f32); every tensor fp32 contiguous on one device."""
+    rows = []
+    for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
+        for t, n in ((p, "param"), (g, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+            _chk(t, n)
+        rows.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()))
+    if not rows:
+        return
+    table = torch.tensor(rows, dtype=torch.int64).to(params[0].device, non_blocking=False)
+    check(lib.zs_adamw_multi_f32(_p(table), len(rows), lr, beta1, beta2, eps, weight_decay, step, _stream()), "zs_adamw_multi_f32")
 
 
 def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad, tc=None):
