@@ -229,7 +229,9 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
 
 // AMODE 0: A is a dense row-major fp32 matrix;  AMODE 1: A rows are gathered from an NHWC image (im2col on the fly);
 // AMODE 2: A rows are gathered from the output gradient of a convolution (data gradient as an implicit GEMM)
-template <int AMODE>
+// SPLIT: compile-time copy of `precision == 0` for the A producers (single-pass bf16 skips the hi/lo residual arithmetic: the
+// producers are bound by instruction issue, profiles/r1_ncu_train_gemm.md)
+template <int AMODE, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 1024-aligned operand tiles
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool split = p.precision == 0;
+  constexpr bool split = SPLIT;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -371,14 +373,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 x0 = buf[i][0], x1 = buf[i][1];
-        uint4 hi, lo;
-        split_bf16x2(x0.x, x0.y, hi.x, lo.x);
-        split_bf16x2(x0.z, x0.w, hi.y, lo.y);
-        split_bf16x2(x1.x, x1.y, hi.z, lo.z);
-        split_bf16x2(x1.z, x1.w, hi.w, lo.w);
         const uint32_t off = swizzle128_offset(rb + 32 * i, c);
-        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-        if (split) *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        if (SPLIT) {
+          uint4 hi, lo;
+          split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+          split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+          split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+          split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+          *reinterpret_cast<uint4*>(a_hi + off) = hi;
+          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+        } else {
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(pack_bf16x2(x0.x, x0.y), pack_bf16x2(x0.z, x0.w), pack_bf16x2(x1.x, x1.y),
+                                                             pack_bf16x2(x1.z, x1.w));
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -558,7 +565,8 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -571,7 +579,8 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.R_inv = nullptr; p.scale = 0.f; p.n_keys = 0; p.rowscale = nullptr;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  if (p.precision == 0) gemm_tc_kernel<0, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  else gemm_tc_kernel<0, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_f32");
   return ZS_OK;
 }
@@ -591,7 +600,8 @@ extern "C" int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, c
   ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_tc: too many output pixels");
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -605,7 +615,8 @@ extern "C" int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, c
   p.cOH = OH; p.cOW = OW; p.cPreRelu = pre_relu;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  if (p.precision == 0) gemm_tc_kernel<1, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  else gemm_tc_kernel<1, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_tc");
   return ZS_OK;
 }
@@ -624,7 +635,8 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -636,7 +648,8 @@ extern "C" int zs_attn_scores_tc(const float* qkv, int ld_qkv, const void* Kpack
   p.qkv = qkv; p.ld_qkv = ld_qkv; p.R = R; p.R_inv = Rinv; p.scale = scale; p.n_keys = n_keys;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  if (p.precision == 0) gemm_tc_kernel<0, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  else gemm_tc_kernel<0, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_attn_scores_tc");
   return ZS_OK;
 }
@@ -651,7 +664,8 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   if (M == 0) return ZS_OK;
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -663,7 +677,8 @@ extern "C" int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R
   p.rowscale = Rinv;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  if (p.precision == 0) gemm_tc_kernel<0, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  else gemm_tc_kernel<0, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_attn_pv_tc");
   return ZS_OK;
 }
@@ -685,7 +700,8 @@ extern "C" int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int
   ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_dgrad_tc: too many pixels");
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   TcParams p{};
@@ -699,7 +715,8 @@ extern "C" int zs_conv2d_nhwc_dgrad_tc(const float* dy, int B, int H, int W, int
   p.cOH = OH; p.cOW = OW; p.cPreRelu = 0;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  if (p.precision == 0) gemm_tc_kernel<2, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
+  else gemm_tc_kernel<2, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
   ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_dgrad_tc");
   return ZS_OK;
 }

@@ -34,7 +34,7 @@ constexpr int TN_PROD_WARPS = 16;                       // latency-bound fp32 lo
 constexpr int TN_PRODUCERS = TN_PROD_WARPS * 32;
 constexpr int TN_EPI_WARP0 = TN_PROD_WARPS, TN_MMA_WARP = TN_PROD_WARPS + 4;
 constexpr int TN_THREADS = (TN_PROD_WARPS + 5) * 32;
-constexpr int TN_SMEM = TN_STAGES * TN_STAGE_BYTES + 1024 + 256;
+constexpr int TN_SMEM = TN_STAGES * TN_STAGE_BYTES + 1024 + 256 + 2 * TN_BK * 16;     // + align slack, barriers, 2 row tables
 
 struct TnParams {
   const float* A; int lda;
@@ -67,7 +67,9 @@ __device__ __forceinline__ void red_add(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
-template <int BMODE>
+// SPLIT: compile-time copy of `precision == 0` (single-pass bf16 skips the hi/lo residual arithmetic in the producers, which are
+// bound by instruction issue: profiles/r1_ncu_train_gemm.md)
+template <int BMODE, bool SPLIT>
 __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
       reinterpret_cast<volatile uint32_t*>(smem_gen + TN_STAGES * TN_STAGE_BYTES + 16 * TN_STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool split = p.precision == 0;
+  constexpr bool split = SPLIT;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TN_STAGES; ++s) {
@@ -139,20 +141,24 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
         x0 = make_float4(v[0], v[1], v[2], v[3]); x1 = make_float4(v[4], v[5], v[6], v[7]);
       }
     };
-    // BMODE 1: the thread's 8 columns lie inside one filter tap (Cin % 8 == 0) = 32 contiguous bytes of one input pixel
+    // BMODE 1: the thread's 8 columns lie inside one filter tap (Cin % 8 == 0) = 32 contiguous bytes of one input pixel.  The
+    // output pixel of each of the chunk's 64 rows is decoded ONCE per chunk into a shared table {first pixel of the image, ih0, iw0}
+    // (the per-unit div / mod chains were 1/3 of the producers' instructions and kept the XU pipe 22 % busy).
+    int4* row_tab = reinterpret_cast<int4*>(smem_gen + TN_STAGES * TN_STAGE_BYTES + 256);
+    int fetches = 0;
     int tap_kh = 0, tap_kw = 0, tap_ci = 0;
-    auto load8B = [&](int m, int col, float4& x0, float4& x1) {
+    auto load8B = [&](int r, int m, int col, float4& x0, float4& x1) {
       x0 = x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m >= p.M || col >= p.Kc) return;
       if (BMODE == 1) {
-        const int ow = m % p.cOW, tt = m / p.cOW;
-        const int oh = tt % p.cOH, b = tt / p.cOH;
-        const int ih = oh * p.cStride - p.cPadT + tap_kh, iw = ow * p.cStride - p.cPadL + tap_kw;
+        const int4 e = row_tab[(fetches & 1) * TN_BK + r];
+        if (e.x < 0 || col >= p.Kc) return;
+        const int ih = e.y + tap_kh, iw = e.z + tap_kw;
         if ((unsigned)ih >= (unsigned)p.cH || (unsigned)iw >= (unsigned)p.cW) return;
-        const float4* src = reinterpret_cast<const float4*>(p.B + (((int64_t)b * p.cH + ih) * p.cW + iw) * p.cCin + tap_ci);
+        const float4* src = reinterpret_cast<const float4*>(p.B + ((int64_t)e.x + ih * p.cW + iw) * p.cCin + tap_ci);
         x0 = __ldg(src); x1 = __ldg(src + 1);
         return;
       }
+      if (m >= p.M || col >= p.Kc) return;
       const float* src = p.B + (int64_t)m * p.ldb + col;
       if (vecB && col + 8 <= p.Kc) {
         x0 = __ldg(reinterpret_cast<const float4*>(src));
@@ -165,13 +171,18 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
       }
     };
     auto put = [&](uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float4& x0, const float4& x1) {
-      uint4 hi, lo;
-      split_bf16x2(x0.x, x0.y, hi.x, lo.x);
-      split_bf16x2(x0.z, x0.w, hi.y, lo.y);
-      split_bf16x2(x1.x, x1.y, hi.z, lo.z);
-      split_bf16x2(x1.z, x1.w, hi.w, lo.w);
-      *reinterpret_cast<uint4*>(hi_tile + off) = hi;
-      if (split) *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+      if (SPLIT) {
+        uint4 hi, lo;
+        split_bf16x2(x0.x, x0.y, hi.x, lo.x);
+        split_bf16x2(x0.z, x0.w, hi.y, lo.y);
+        split_bf16x2(x1.x, x1.y, hi.z, lo.z);
+        split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+        *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+        *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+      } else {
+        *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(pack_bf16x2(x0.x, x0.y), pack_bf16x2(x0.z, x0.w), pack_bf16x2(x1.x, x1.y),
+                                                              pack_bf16x2(x1.z, x1.w));
+      }
     };
     // fetch iterator over (work item, chunk): runs one chunk ahead of the conversion, so a chunk's L2 / DRAM round trip
     // overlaps the MMAs that still own the smem slot
@@ -188,11 +199,25 @@ __global__ void __launch_bounds__(TN_THREADS, 1) gemm_tn_tc_kernel(TnParams p) {
         tap_ci = colB - tap * p.cCin;
         tap_kh = tap / p.cKW;
         tap_kw = tap - tap_kh * p.cKW;
+        if (t < TN_BK) {
+          const int m = m0 + t;
+          int4 e = make_int4(-1, 0, 0, 0);
+          if (m < p.M) {
+            const int ow = m % p.cOW, tt = m / p.cOW;
+            const int oh = tt % p.cOH, b = tt / p.cOH;
+            e = make_int4(b * p.cH * p.cW, oh * p.cStride - p.cPadT, ow * p.cStride - p.cPadL, 0);
+          }
+          row_tab[(fetches & 1) * TN_BK + t] = e;
+        }
+        // producers only (named barrier 1); the table of the fetch before last is free again: every producer passed the
+        // barrier of the last fetch after its final read of it
+        asm volatile("bar.sync 1, %0;" ::"n"(TN_PRODUCERS) : "memory");
       }
 #pragma unroll
       for (int i = 0; i < NA; ++i) load8A(m0 + ra + SA * i, colA, buf.a[i][0], buf.a[i][1]);
 #pragma unroll
-      for (int i = 0; i < NB; ++i) load8B(m0 + rb + SB * i, colB, buf.b[i][0], buf.b[i][1]);
+      for (int i = 0; i < NB; ++i) load8B(rb + SB * i, m0 + rb + SB * i, colB, buf.b[i][0], buf.b[i][1]);
+      ++fetches;
       if (++fc == fc1) {
         fw += gridDim.x;
         if (fw < total_work) chunk_range(fw, fc, fc1);
@@ -315,7 +340,8 @@ template <int BMODE>
 static int launch_tn(TnParams& p, int accumulate, cudaStream_t st, const char* what) {
   static thread_local bool configured = false;
   if (!configured) {
-    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tn_tc_kernel<BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tn_tc_kernel<BMODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(gemm_tn_tc_kernel<BMODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
     configured = true;
   }
   p.n_tiles = (p.N + TN_BM - 1) / TN_BM;
@@ -333,7 +359,8 @@ static int launch_tn(TnParams& p, int accumulate, cudaStream_t st, const char* w
   }
   const int work = tiles * p.splits;
   const int grid = work < sm_count() ? work : sm_count();
-  gemm_tn_tc_kernel<BMODE><<<grid, TN_THREADS, TN_SMEM, st>>>(p);
+  if (p.precision == 0) gemm_tn_tc_kernel<BMODE, true><<<grid, TN_THREADS, TN_SMEM, st>>>(p);
+  else gemm_tn_tc_kernel<BMODE, false><<<grid, TN_THREADS, TN_SMEM, st>>>(p);
   ZS_CUDA_CHECK_LAUNCH(what);
   return ZS_OK;
 }

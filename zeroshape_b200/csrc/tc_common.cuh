@@ -165,6 +165,12 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
   return upk2(d);
 }
 
+// two fp32 -> packed bf16x2 (round to nearest even), .x in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------
 // x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits; products hi*hi + hi*lo + lo*hi
 // reproduce the fp32 product to ~2^-16 relative.
