@@ -215,6 +215,14 @@ int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat, const flo
 size_t zs_mha_bwd_ws_bytes(int B, int T, int heads);
 int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
                    void* stream);
+/* MiDaS scale-and-shift-invariant depth loss (model/depth/midas_loss.py:145-185 as configured by utils/loss.py:14-16,30-34:
+ * SSI-MAE on median / mean-absolute-deviation aligned maps + alpha x gradient matching over 4 scales of the least-squares aligned
+ * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
+ * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
+ * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
+size_t zs_midas_ws_bytes(int B, int H, int W);
+int zs_midas_loss_f32(const float* pred, const float* gt, const float* mask, int B, int H, int W, float alpha,
+                      int inverse_depth, float grad_scale, void* ws, float* loss, float* dpred, void* stream);
 /* torch.optim.AdamW step (decoupled weight decay, bias correction) on one flat tensor; `step` counts from 1. */
 int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, void* stream);

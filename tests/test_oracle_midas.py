@@ -1,0 +1,33 @@
+"""CPU: the oracle restatement of the reference's MiDaS depth loss (oracle/midas.py) and its closed-form gradient against
+golden vectors produced by the REAL reference module + torch autograd (tests/golden/midas.npz, make_golden_midas.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.midas import midas_loss, midas_loss_grad
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "midas.npz"))
+
+
+@pytest.mark.parametrize("name", ["small", "odd", "empty_image"])
+@pytest.mark.parametrize("alpha", [0.1, 0.0])
+def test_midas_oracle_matches_reference(name, alpha):
+    pred, gt, mask = (torch.from_numpy(G[f"{name}_{k}"]) for k in ("pred", "gt", "mask"))
+    tag = f"{name}_a{int(alpha * 10)}"
+    loss = midas_loss(pred, gt, mask, alpha=alpha)
+    assert abs(float(loss) - float(G[f"{tag}_loss"])) < 2e-6 * max(1.0, abs(float(G[f"{tag}_loss"])))
+    grad = midas_loss_grad(pred, gt, mask, alpha=alpha)
+    ref = torch.from_numpy(G[f"{tag}_grad"]).double()
+    assert (grad - ref).abs().max().item() < 1e-5 * ref.abs().max().item() + 1e-9, (grad - ref).abs().max().item()
+
+
+def test_midas_oracle_gradient_matches_autograd_of_itself():
+    g = torch.Generator().manual_seed(5)
+    pred = (0.3 + 0.5 * torch.rand(2, 1, 18, 22, generator=g)).double().requires_grad_(True)
+    gt = (1.0 + torch.rand(2, 1, 18, 22, generator=g)).double()
+    mask = (torch.rand(2, 1, 18, 22, generator=g) < 0.7).float()
+    midas_loss(pred, gt * mask, mask).backward()
+    an = midas_loss_grad(pred.detach().float(), (gt * mask).float(), mask)
+    assert (an - pred.grad).abs().max().item() < 1e-5 * pred.grad.abs().max().item()

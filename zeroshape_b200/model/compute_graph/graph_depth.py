@@ -1,6 +1,8 @@
 """Host-side mirror of the reference's depth-only compute graph (model/compute_graph/graph_depth.py:61-97):
 DPT depth + intrinsics head -> var.depth_pred, var.intr_pred, var.seen_points_pred.  BASELINE config (1).
-Inference only in this revision."""
+`forward(training=True)` runs the same graph on the tape of model/depth/dpt_train.py and returns the reference's losses
+(graph_depth.py:99-105: MiDaS depth loss on depth_pred, masked squared distance of the normalised seen surfaces), both
+differentiable into every parameter of the depth estimator and the intrinsics head (`train.py options/depth.yaml`)."""
 import torch
 import torch.nn as nn
 
@@ -25,11 +27,13 @@ class Graph(nn.Module):
             nn.init.zeros_(self.intr_proj.weight)
             nn.init.zeros_(self.intr_proj.bias)
             self._intr_cache = PackCache(self.intr_head)
+        from ...utils.loss import Loss
+        self.loss_fns = Loss(opt)
 
     def forward(self, opt, var, training=False, get_loss=True):
-        if training:
-            raise NotImplementedError("training path is not implemented in this revision")
         B = len(var.idx)
+        if training:
+            return self._forward_train(opt, var, get_loss)
         with torch.no_grad():
             var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
             if self.with_intr:
@@ -41,3 +45,25 @@ class Graph(nn.Module):
                 mask = var.mask_input_map.float().contiguous()
                 var.seen_points_pred, _, _ = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
         return (var, edict()) if get_loss else var
+
+    def _forward_train(self, opt, var, get_loss):
+        """graph_depth.py:61-105 in train mode: batch-statistics BatchNorm in the intrinsics head, losses with gradients."""
+        from ..depth.dpt_train import DepthGraphTrainFn
+        B = len(var.idx)
+        mask = var.mask_input_map.float().contiguous()
+        params = [p for p in self.parameters()]
+        if self.with_intr:
+            var.depth_pred, var.intr_pred, var.seen_points_pred = DepthGraphTrainFn.apply(self, opt, var.rgb_input_map, mask, True, *params)
+            with torch.no_grad():
+                var.seen_points_gt, _, _ = ops.unproject_normalize(var.depth_input_map.float(), mask, var.intr.float())
+                var.validity_mask = (var.mask_input_map > 0.5).float().view(B, -1)
+        else:
+            var.depth_pred = DepthGraphTrainFn.apply(self, opt, var.rgb_input_map, mask, False, *params)
+        if not get_loss:
+            return var
+        loss = edict()
+        if opt.loss_weight.depth is not None:
+            loss.depth = self.loss_fns.depth_loss(var.depth_pred, var.depth_input_map, var.mask_input_map)
+        if opt.loss_weight.intr is not None:
+            loss.intr = self.loss_fns.intr_loss(var.seen_points_pred, var.seen_points_gt, var.validity_mask)
+        return var, loss

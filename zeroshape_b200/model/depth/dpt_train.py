@@ -361,13 +361,17 @@ def _resize_pos(pe, gh, gw):
 
 
 # ---- the whole encoder side --------------------------------------------------------------------------------------------
-def encoder_forward(graph, opt, rgb, mask):
-    """-> (tape, outputs dict).  Mirrors Graph.forward up to latent_depth in train mode (graph_shape.py:115-150)."""
+def encoder_forward(graph, opt, rgb, mask, with_intr=True, with_coord=True):
+    """-> (tape, outputs dict).  Mirrors Graph.forward up to latent_depth in train mode (graph_shape.py:115-150); with
+    `with_coord=False` it is the depth-only graph (graph_depth.py:61-86: depth, intrinsics, normalised seen surface), with
+    `with_intr=False` the depth estimator alone."""
     tp = Tape()
     B = rgb.shape[0]
     H, W = opt.H, opt.W
     depth_nhwc, l4 = dpt_forward(tp, graph.dpt_depth, rgb)
     depth = depth_nhwc.view(B, 1, H, W)
+    if not with_intr:
+        return tp, {"depth": depth, "depth_nhwc": depth_nhwc, "K": None, "seen": None, "mean": None, "scale": None, "latent": None}
     # intrinsics head: 2 x Bottleneck_Conv(768, k=3) with batch-statistics BatchNorm -> avg pool -> Linear(768, 3) -> K
     U = []
     f = cet._bneck_conv_fwd(U, l4, graph.intr_head[0])
@@ -413,8 +417,10 @@ def encoder_forward(graph, opt, rgb, mask):
                           dK[:, 0, 2] * (W / 2.0) * dt[:, 1], dK[:, 1, 2] * (H / 2.0) * dt[:, 2]], dim=1)
         tp.add(params, dp)
     tp.record(bwd_geom)
+    out = {"depth": depth, "depth_nhwc": depth_nhwc, "K": K, "seen": seen, "mean": mean, "scale": scale, "latent": None}
+    if not with_coord:
+        return tp, out
     coord = ops.axpby(seen.view(B, H, W, 3), 1.0 / (1.0 + 1.e-6))
-    out = {"depth": depth, "K": K, "seen": seen, "mean": mean, "scale": scale}
     enc = graph.coord_encoder
     if enc.training:
         latent, T = cet.train_forward(enc, coord)
@@ -452,11 +458,40 @@ class EncoderTrainFn(torch.autograd.Function):
         with torch.no_grad():
             if dlatent is not None:
                 tp.add(out["latent"], dlatent)
-            if dseen is not None and bool((dseen != 0).any()):
-                tp.add(out["seen"], dseen)
-            if ddepth is not None and bool((ddepth != 0).any()):
-                raise NotImplementedError("a loss on depth_pred itself (MiDaS, loss_weight.depth) is not implemented")
+            _seed_depth_and_seen(tp, out, ddepth, dseen)
             tp.backward()
         grads = tuple(tp.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.params)
         ctx.tp = None
         return (None, None, None, None) + grads
+
+
+def _seed_depth_and_seen(tp, out, ddepth, dseen):
+    """Gradients arriving at depth_pred (MiDaS depth loss) and at the normalised seen surface (intrinsics loss)."""
+    if dseen is not None and out["seen"] is not None and bool((dseen != 0).any()):
+        tp.add(out["seen"], dseen)
+    if ddepth is not None and bool((ddepth != 0).any()):
+        tp.add(out["depth_nhwc"], ddepth.contiguous().view(out["depth_nhwc"].shape))      # [B,1,H,W] and [B,H,W,1] share the memory order
+
+
+class DepthGraphTrainFn(torch.autograd.Function):
+    """depth[, K, seen_points] = DepthGraphTrainFn.apply(graph, opt, rgb, mask, with_intr, *parameters): the depth-only compute
+    graph (model/compute_graph/graph_depth.py:61-86) on the tape, for `train.py options/depth.yaml`."""
+
+    @staticmethod
+    def forward(ctx, graph, opt, rgb, mask, with_intr, *params):
+        with torch.no_grad():
+            tp, out = encoder_forward(graph, opt, rgb, mask, with_intr=with_intr, with_coord=False)
+        ctx.tp, ctx.out, ctx.params, ctx.with_intr = tp, out, params, with_intr
+        if not with_intr:
+            return out["depth"]
+        return out["depth"], out["K"], out["seen"]
+
+    @staticmethod
+    def backward(ctx, ddepth, dK=None, dseen=None):
+        tp, out = ctx.tp, ctx.out
+        with torch.no_grad():
+            _seed_depth_and_seen(tp, out, ddepth, dseen)
+            tp.backward()
+        grads = tuple(tp.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        ctx.tp = None
+        return (None, None, None, None, None) + grads

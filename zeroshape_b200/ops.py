@@ -740,6 +740,21 @@ def bce_logits_loss_bwd(logits, sdf, impt_thres, impt_weight, grad_scale=1.0):
     return d
 
 
+def midas_loss(pred, gt, mask, alpha=0.1, inverse_depth=True, need_grad=True, grad_scale=1.0):
+    """model/depth/midas_loss.py MidasLoss (image-based reduction, no mask shrinking) -> (loss scalar tensor, d loss / d pred or None).
+    pred, gt, mask [B,1,H,W]."""
+    pred, gt, mask = pred.contiguous(), gt.contiguous(), mask.float().contiguous()
+    _chk(pred, "pred"); _chk(gt, "gt"); _chk(mask, "mask")
+    assert pred.dim() == 4 and pred.shape[1] == 1 and pred.shape == gt.shape == mask.shape
+    B, _, H, W = pred.shape
+    ws = torch.empty((lib.zs_midas_ws_bytes(B, H, W) + 7) // 8, device=pred.device, dtype=torch.float64)
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if need_grad else None
+    check(lib.zs_midas_loss_f32(_p(pred), _p(gt), _p(mask), B, H, W, float(alpha), int(bool(inverse_depth)), float(grad_scale),
+                                _p(ws), _p(loss), _p(dpred), _stream()), "zs_midas_loss_f32")
+    return loss, dpred
+
+
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
     for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _chk(t, n)
