@@ -75,7 +75,7 @@ def test_depth_graph_training_step(cuda):
         return EasyDict(idx=torch.arange(B), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), depth_input_map=depth_gt.to(cuda),
                         intr=intr.to(cuda))
     trainable = [p for p in graph.parameters() if p.requires_grad]
-    optim = FusedAdamW(trainable, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05)
+    optim = FusedAdamW(trainable, lr=3e-6, betas=(0.9, 0.95), weight_decay=0.05)      # random init: a larger step kills the output ReLU
     totals = []
     for it in range(4):
         var, loss = graph.forward(opt, batch(), training=True)
