@@ -220,6 +220,9 @@ int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T,
  * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
  * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
  * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
+/* MidasLoss.erode_mask (midas_loss.py:158-167, `training.depth_loss.mask_shrink`): out = 1 where a whole pool x pool block of the raw
+ * mask [B,1,H,W] equals 1 (1 - mask -> max_pool2d -> nearest upsampling -> == 0), else 0. */
+int zs_mask_erode_f32(const float* mask, float* out, int B, int H, int W, int pool, void* stream);
 size_t zs_midas_ws_bytes(int B, int H, int W);
 int zs_midas_loss_f32(const float* pred, const float* gt, const float* mask, int B, int H, int W, float alpha,
                       int inverse_depth, float grad_scale, void* ws, float* loss, float* dpred, void* stream);

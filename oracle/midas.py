@@ -51,6 +51,15 @@ def _scale_shift(p, t, m):
     return (a11 * b0 - a01 * b1) / (det + 1e-6), (-a01 * b0 + a00 * b1) / (det + 1e-6), (a00, a01, a11, b0, b1, det)
 
 
+def erode_mask(mask, pool=4):
+    """MidasLoss.erode_mask (midas_loss.py:158-167): valid only where a whole pool x pool block of the raw mask is valid."""
+    m = 1 - mask.float()
+    h, w = m.shape[2], m.shape[3]
+    m = torch.nn.functional.max_pool2d(m, kernel_size=pool)
+    m = torch.nn.functional.interpolate(m, (h, w), mode="nearest")
+    return (m == 0).float()
+
+
 def midas_loss(pred, gt, mask, alpha=0.1, inverse_depth=True, scales=4):
     """pred, gt, mask [B,1,H,W] -> scalar (fp32 torch tensor).  mask_raw > 0.5 is the valid set (mask_shrink False)."""
     B = pred.shape[0]

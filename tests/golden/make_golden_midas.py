@@ -38,6 +38,18 @@ def main():
             store[f"{tag}_loss"] = loss.detach().numpy()
             store[f"{tag}_grad"] = p.grad.numpy()
         store[f"{name}_pred"], store[f"{name}_gt"], store[f"{name}_mask"] = pred.numpy(), gt.numpy(), mask.numpy()
+    # mask shrinking (training.depth_loss.mask_shrink): a blocky mask so that some 4x4 blocks survive the erosion
+    g = torch.Generator().manual_seed(99)
+    pred = 0.2 + 0.6 * torch.rand(2, 1, 24, 28, generator=g)
+    gt = 0.8 + 1.4 * torch.rand(2, 1, 24, 28, generator=g)
+    mask = torch.nn.functional.interpolate((torch.rand(2, 1, 6, 7, generator=g) < 0.7).float(), (24, 28), mode="nearest")
+    mask[:, :, 5, 9] = 0
+    fn = MidasLoss(alpha=0.1, inverse_depth=True, shrink_mask=True)
+    p = pred.clone().requires_grad_(True)
+    loss = fn(p, gt * mask, mask)
+    loss.backward()
+    store.update(shrink_pred=pred.numpy(), shrink_gt=(gt * mask).numpy(), shrink_mask=mask.numpy(), shrink_loss=loss.detach().numpy(),
+                 shrink_grad=p.grad.numpy(), shrink_eroded=fn.erode_mask(mask).float().numpy())
     np.savez_compressed(os.path.join(HERE, "midas.npz"), **store)
     print("wrote", os.path.join(HERE, "midas.npz"), {k: v.shape for k, v in store.items() if k.endswith("loss")})
 

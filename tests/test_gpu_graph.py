@@ -122,8 +122,6 @@ def test_depth_graph_and_guards(cuda):
     with torch.no_grad():
         d_ref, _ = BB.dpt_depth_forward(sd, rgb, "dpt_depth.")
     assert _rel(var.depth_pred, d_ref) < 1e-3 and var.intr_pred.shape == (1, 3, 3)
-    # the training path exists (tests/test_gpu_midas.py); what is guarded is the mask-shrinking variant of the MiDaS loss
-    opt.training = EasyDict(depth_loss=EasyDict(grad_reg=0.1, depth_inv=True, mask_shrink=True))
-    shrink = DepthGraph(opt).loss_fns
-    with pytest.raises(NotImplementedError):
-        shrink.depth_loss(var.depth_pred, var.depth_pred, var.mask_input_map)
+    # the training path of this graph is covered by tests/test_gpu_midas.py; eval mode never needs ground truth
+    var2, loss = dg.forward(opt, EasyDict(idx=torch.arange(1), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda)), training=False)
+    assert len(loss) == 0 and torch.equal(var2.depth_pred, var.depth_pred)

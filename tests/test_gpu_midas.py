@@ -26,6 +26,20 @@ def test_midas_kernel_matches_reference_golden(cuda, name, alpha):
     assert err < 2e-5 * ref_grad.abs().max().item() + 1e-9, err
 
 
+def test_midas_mask_shrink_matches_reference_golden(cuda):
+    from zeroshape_b200 import ops
+    from zeroshape_b200.utils.loss import Loss
+    pred, gt, mask = (torch.from_numpy(G[f"shrink_{k}"]).to(cuda) for k in ("pred", "gt", "mask"))
+    assert np.array_equal(ops.erode_mask(mask).cpu().numpy(), G["shrink_eroded"])
+    lossfn = Loss({"training": {"depth_loss": {"grad_reg": 0.1, "depth_inv": True, "mask_shrink": True}}})
+    p = pred.clone().requires_grad_(True)
+    loss = lossfn.depth_loss(p, gt, mask)
+    loss.backward()
+    assert abs(loss.item() - float(G["shrink_loss"])) < 5e-6 * abs(float(G["shrink_loss"]))
+    ref = torch.from_numpy(G["shrink_grad"]).double()
+    assert (p.grad.cpu().double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
 def test_midas_kernel_matches_oracle_at_full_size(cuda):
     from zeroshape_b200 import ops
     from zeroshape_b200.utils.loss import Loss

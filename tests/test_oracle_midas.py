@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.midas import midas_loss, midas_loss_grad
+from oracle.midas import erode_mask, midas_loss, midas_loss_grad
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "midas.npz"))
 
@@ -31,3 +31,12 @@ def test_midas_oracle_gradient_matches_autograd_of_itself():
     midas_loss(pred, gt * mask, mask).backward()
     an = midas_loss_grad(pred.detach().float(), (gt * mask).float(), mask)
     assert (an - pred.grad).abs().max().item() < 1e-5 * pred.grad.abs().max().item()
+
+
+def test_midas_oracle_mask_shrink():
+    pred, gt, mask = (torch.from_numpy(G[f"shrink_{k}"]) for k in ("pred", "gt", "mask"))
+    er = erode_mask(mask)
+    assert np.array_equal(er.numpy(), G["shrink_eroded"]) and 0 < er.sum() < mask.sum()
+    assert abs(float(midas_loss(pred, gt, er)) - float(G["shrink_loss"])) < 2e-6 * abs(float(G["shrink_loss"]))
+    ref = torch.from_numpy(G["shrink_grad"]).double()
+    assert (midas_loss_grad(pred, gt, er) - ref).abs().max().item() < 1e-5 * ref.abs().max().item()

@@ -272,9 +272,35 @@ __global__ void midas_finish_kernel(const double* __restrict__ stats, int B, flo
   *loss = (float)(ssi / N + (alpha > 0.f ? (double)alpha * reg : 0.0));
 }
 
+// MidasLoss.erode_mask (midas_loss.py:158-167): valid where a whole pool x pool block of the raw mask is 1
+// (1 - mask -> max_pool2d(pool) -> nearest upsampling back to H x W -> == 0)
+__global__ void mask_erode_kernel(const float* __restrict__ mask, float* __restrict__ out, int B, int H, int W, int pool) {
+  const int Hp = H / pool, Wp = W / pool;
+  const float sh = (float)Hp / (float)H, sw = (float)Wp / (float)W;
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((int64_t)W * H));
+    const int py = min((int)floorf(y * sh), Hp - 1), px = min((int)floorf(x * sw), Wp - 1);
+    float mx = -INFINITY;
+    for (int dy = 0; dy < pool; ++dy)
+      for (int dx = 0; dx < pool; ++dx) mx = fmaxf(mx, 1.0f - mask[((int64_t)b * H + py * pool + dy) * W + px * pool + dx]);
+    out[i] = mx == 0.0f ? 1.0f : 0.0f;
+  }
+}
+
 }  // namespace zs
 
 using namespace zs;
+
+extern "C" int zs_mask_erode_f32(const float* mask, float* out, int B, int H, int W, int pool, void* stream) {
+  ZS_REQUIRE(mask && out && B > 0 && pool > 0 && H >= pool && W >= pool, "zs_mask_erode_f32: bad args");
+  const int64_t total = (int64_t)B * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 4096) grid = 4096;
+  mask_erode_kernel<<<grid, 256, 0, as_stream(stream)>>>(mask, out, B, H, W, pool);
+  ZS_CUDA_CHECK_LAUNCH("zs_mask_erode_f32");
+  return ZS_OK;
+}
 
 extern "C" size_t zs_midas_ws_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;

@@ -740,6 +740,16 @@ def bce_logits_loss_bwd(logits, sdf, impt_thres, impt_weight, grad_scale=1.0):
     return d
 
 
+def erode_mask(mask, pool=4):
+    """MidasLoss.erode_mask: [B,1,H,W] raw mask -> 1.0 where a whole pool x pool block is valid."""
+    mask = mask.float().contiguous()
+    _chk(mask, "mask")
+    B, _, H, W = mask.shape
+    out = torch.empty_like(mask)
+    check(lib.zs_mask_erode_f32(_p(mask), _p(out), B, H, W, pool, _stream()), "zs_mask_erode_f32")
+    return out
+
+
 def midas_loss(pred, gt, mask, alpha=0.1, inverse_depth=True, need_grad=True, grad_scale=1.0):
     """model/depth/midas_loss.py MidasLoss (image-based reduction, no mask shrinking) -> (loss scalar tensor, d loss / d pred or None).
     pred, gt, mask [B,1,H,W]."""

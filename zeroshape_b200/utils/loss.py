@@ -84,5 +84,5 @@ class Loss(nn.Module):
         assert pred_depth.dim() == gt_depth.dim() == mask.dim() == 4
         assert pred_depth.shape[1] == gt_depth.shape[1] == mask.shape[1] == 1
         if self.depth_mask_shrink:
-            raise NotImplementedError("training.depth_loss.mask_shrink (MidasLoss.erode_mask) is not implemented; options/depth.yaml uses false")
+            mask = ops.erode_mask(mask.detach(), 4)               # MidasLoss.erode_mask (midas_loss.py:158-167)
         return _DepthLossFn.apply(pred_depth, gt_depth, mask, self.depth_alpha, self.depth_inv)
