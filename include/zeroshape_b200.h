@@ -220,6 +220,12 @@ int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T,
  * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
  * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
  * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
+/* DepthMetric.compute_metrics (utils/eval_depth.py:41-110): per image, least-squares scale / shift of the predicted disparity
+ * (1 / (pred + 1e-6), or pred itself when disparity_input) to 1 / gt over mask > 0.5, aligned depth = 1 / max(aligned disparity,
+ * 1 / depth_cap) (depth_cap <= 0: no cap), then metrics [B, T + 3] = {fraction with max(d/g, g/d) > thresholds[k]} (thresholds: T <= 8
+ * floats in device memory), RMSE, L1, absolute relative error; depth_out [B,1,H,W] = the aligned depth map (also outside the mask). */
+int zs_depth_metrics_f32(const float* pred, const float* gt, const float* mask, int B, int H, int W, const float* thresholds,
+                         int T, float depth_cap, int disparity_input, float* metrics, float* depth_out, void* stream);
 /* MidasLoss.erode_mask (midas_loss.py:158-167, `training.depth_loss.mask_shrink`): out = 1 where a whole pool x pool block of the raw
  * mask [B,1,H,W] equals 1 (1 - mask -> max_pool2d -> nearest upsampling -> == 0), else 0. */
 int zs_mask_erode_f32(const float* mask, float* out, int B, int H, int W, int pool, void* stream);

@@ -150,3 +150,33 @@ def midas_loss_grad(pred, gt, mask, alpha=0.1, inverse_depth=True, scales=4):
             gb = gb + alpha * (gp * (-(p * p)) if inverse_depth else gp)
         g[b, 0] = gb
     return g
+
+
+def depth_metrics(prediction, target, mask, thresholds=(1.25, 1.25 ** 2, 1.25 ** 3), depth_cap=None, prediction_type="depth"):
+    """Restatement of DepthMetric.compute_metrics (utils/eval_depth.py:41-110) -> ({key: [B]}, aligned depth [B,1,H,W])."""
+    p, t = prediction.float().squeeze(1), target.float().squeeze(1)
+    m = (mask.float().squeeze(1) > 0.5)
+    mf = m.float()
+    pd = torch.where(m, 1.0 / (p + 1.e-6) if prediction_type == "depth" else p, torch.zeros_like(p))
+    td = torch.where(m, 1.0 / t, torch.zeros_like(t))
+    a00, a01, a11 = (mf * pd * pd).sum((1, 2)), (mf * pd).sum((1, 2)), mf.sum((1, 2))
+    b0, b1 = (mf * pd * td).sum((1, 2)), (mf * td).sum((1, 2))
+    det = a00 * a11 - a01 * a01
+    ok = det > 0
+    safe = torch.where(ok, det, torch.ones_like(det))
+    x0 = torch.where(ok, (a11 * b0 - a01 * b1) / safe, torch.zeros_like(det))
+    x1 = torch.where(ok, (-a01 * b0 + a00 * b1) / safe, torch.zeros_like(det))
+    al = x0.view(-1, 1, 1) * pd + x1.view(-1, 1, 1)
+    if depth_cap is not None:
+        al = torch.clamp(al, min=1.0 / depth_cap)
+    d = 1.0 / al
+    out = {}
+    n = mf.sum((1, 2))
+    ratio = torch.where(m, torch.max(d / t, t / d), torch.zeros_like(d))
+    for th in thresholds:
+        out["d>{}".format(th)] = ((ratio > th).float() * mf).sum((1, 2)) / n
+    diff = torch.where(m, d - t, torch.zeros_like(d))
+    out["rmse"] = torch.sqrt((diff ** 2).sum((1, 2)) / n)
+    out["l1_err"] = diff.abs().sum((1, 2)) / n
+    out["abs_rel"] = torch.where(m, diff.abs() / t, torch.zeros_like(d)).sum((1, 2)) / n
+    return out, d.unsqueeze(1)

@@ -50,6 +50,16 @@ def main():
     loss.backward()
     store.update(shrink_pred=pred.numpy(), shrink_gt=(gt * mask).numpy(), shrink_mask=mask.numpy(), shrink_loss=loss.detach().numpy(),
                  shrink_grad=p.grad.numpy(), shrink_eroded=fn.erode_mask(mask).float().numpy())
+    # DepthMetric (utils/eval_depth.py) on the "odd" case (depth in [0.2, 0.8], gt > 0 inside the mask), with and without a depth cap
+    from utils.eval_depth import DepthMetric
+    name, pred, gt, mask = cases()[1]
+    gt = torch.where(mask > 0.5, gt, torch.ones_like(gt))          # the reference divides by target inside the mask only
+    for tag, cap in (("dm", None), ("dmcap", 1.6)):
+        dm = DepthMetric(thresholds=[1.02, 1.05, 1.1, 1.2], depth_cap=cap)
+        metrics, depth = dm.compute_metrics(pred, gt, mask)
+        store[f"{tag}_metrics"] = np.stack([metrics[k].numpy() for k in dm.metric_keys], axis=1)
+        store[f"{tag}_depth"] = depth.numpy()
+    store["dm_gt"] = gt.numpy()
     np.savez_compressed(os.path.join(HERE, "midas.npz"), **store)
     print("wrote", os.path.join(HERE, "midas.npz"), {k: v.shape for k, v in store.items() if k.endswith("loss")})
 

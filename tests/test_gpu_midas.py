@@ -64,6 +64,30 @@ def test_midas_kernel_matches_oracle_at_full_size(cuda):
     assert torch.allclose(p.grad, grad * 3.0, rtol=1e-6, atol=1e-12) and abs(out.item() - loss.item()) < 1e-7
 
 
+@pytest.mark.parametrize("tag,cap", [("dm", None), ("dmcap", 1.6)])
+def test_depth_metric_matches_reference_golden(cuda, tag, cap):
+    """utils.eval_depth.DepthMetric (one launch) vs the real reference class (golden) and, at full size, vs the oracle restatement."""
+    from oracle.midas import depth_metrics
+    from zeroshape_b200.utils.eval_depth import DepthMetric
+    pred, mask, gt = (torch.from_numpy(G[k]).to(cuda) for k in ("odd_pred", "odd_mask", "dm_gt"))
+    dm = DepthMetric(thresholds=[1.02, 1.05, 1.1, 1.2], depth_cap=cap)
+    assert dm.metric_keys == ["d>1.02", "d>1.05", "d>1.1", "d>1.2", "rmse", "l1_err", "abs_rel"]
+    metrics, depth = dm.compute_metrics(pred, gt, mask)
+    got = np.stack([metrics[k].cpu().numpy() for k in dm.metric_keys], axis=1)
+    np.testing.assert_allclose(got, G[f"{tag}_metrics"], rtol=3e-5, atol=1e-7)
+    np.testing.assert_allclose(depth.cpu().numpy(), G[f"{tag}_depth"], rtol=3e-5)
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 3, 224, 224
+    p2 = 0.2 + 0.6 * torch.rand(B, 1, H, W, generator=g)
+    g2 = 0.9 + 1.2 * torch.rand(B, 1, H, W, generator=g)
+    m2 = (torch.rand(B, 1, H, W, generator=g) < 0.45).float()
+    ref, dref = depth_metrics(p2, g2, m2, thresholds=[1.02, 1.05, 1.1, 1.2], depth_cap=cap)
+    out, dout = dm.compute_metrics(p2.to(cuda), g2.to(cuda), m2.to(cuda))
+    for k in dm.metric_keys:
+        np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=5e-5, atol=1e-7)
+    np.testing.assert_allclose(dout.cpu().numpy(), dref.numpy(), rtol=5e-5)
+
+
 def test_depth_graph_training_step(cuda):
     """graph_depth.Graph.forward(training=True) with options/depth.yaml's loss weights (depth 1, intr 10): the losses equal the
     oracle's on the graph's own outputs, every parameter that takes part gets a finite gradient, AdamW steps lower the loss."""

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.midas import erode_mask, midas_loss, midas_loss_grad
+from oracle.midas import depth_metrics, erode_mask, midas_loss, midas_loss_grad
 
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "midas.npz"))
 
@@ -40,3 +40,12 @@ def test_midas_oracle_mask_shrink():
     assert abs(float(midas_loss(pred, gt, er)) - float(G["shrink_loss"])) < 2e-6 * abs(float(G["shrink_loss"]))
     ref = torch.from_numpy(G["shrink_grad"]).double()
     assert (midas_loss_grad(pred, gt, er) - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("tag,cap", [("dm", None), ("dmcap", 1.6)])
+def test_depth_metric_oracle_matches_reference(tag, cap):
+    pred, mask, gt = torch.from_numpy(G["odd_pred"]), torch.from_numpy(G["odd_mask"]), torch.from_numpy(G["dm_gt"])
+    metrics, depth = depth_metrics(pred, gt, mask, thresholds=[1.02, 1.05, 1.1, 1.2], depth_cap=cap)
+    got = np.stack([v.numpy() for v in metrics.values()], axis=1)
+    np.testing.assert_allclose(got, G[f"{tag}_metrics"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(depth.numpy(), G[f"{tag}_depth"], rtol=2e-5)

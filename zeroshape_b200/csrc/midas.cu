@@ -288,9 +288,73 @@ __global__ void mask_erode_kernel(const float* __restrict__ mask, float* __restr
   }
 }
 
+// ---- DepthMetric.compute_metrics (utils/eval_depth.py:41-110): least-squares alignment of the predicted disparity to the ground
+// truth disparity per image, aligned depth map, then d > threshold fractions, RMSE, L1 and absolute relative error over the mask.
+// One CTA per image: five sums -> scale / shift -> one sweep that writes the aligned depth and accumulates the metrics.
+constexpr int DM_MAX_T = 8;
+__global__ void __launch_bounds__(MD_THREADS) depth_metric_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                  const float* __restrict__ mask, int H, int W, const float* __restrict__ thr,
+                                                                  int T, float depth_cap, int disparity_input,
+                                                                  float* __restrict__ metrics, float* __restrict__ depth_out) {
+  __shared__ double red[MD_THREADS / 32];
+  const int b = blockIdx.x, HW = H * W;
+  const float* P = pred + (size_t)b * HW;
+  const float* G = gt + (size_t)b * HW;
+  const float* Mk = mask + (size_t)b * HW;
+  double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+  for (int i = threadIdx.x; i < HW; i += MD_THREADS) {
+    if (Mk[i] > 0.5f) {
+      const float p = disparity_input ? P[i] : 1.0f / (P[i] + 1.e-6f);
+      const float t = 1.0f / G[i];
+      a00 += (double)p * p; a01 += p; a11 += 1.0; b0 += (double)p * t; b1 += t;
+    }
+  }
+  a00 = block_sum(a00, red); a01 = block_sum(a01, red); a11 = block_sum(a11, red); b0 = block_sum(b0, red); b1 = block_sum(b1, red);
+  const double det = a00 * a11 - a01 * a01;
+  float x0 = 0.f, x1 = 0.f;
+  if (det > 0.0) { x0 = (float)((a11 * b0 - a01 * b1) / det); x1 = (float)((-a01 * b0 + a00 * b1) / det); }
+  const float dcap = depth_cap > 0.f ? 1.0f / depth_cap : 0.f;
+  double cnt[DM_MAX_T] = {}, se = 0, l1 = 0, rel = 0;
+  for (int i = threadIdx.x; i < HW; i += MD_THREADS) {
+    const bool v = Mk[i] > 0.5f;
+    const float p = v ? (disparity_input ? P[i] : 1.0f / (P[i] + 1.e-6f)) : 0.f;
+    float al = x0 * p + x1;
+    if (depth_cap > 0.f && al < dcap) al = dcap;
+    const float d = 1.0f / al;
+    depth_out[(size_t)b * HW + i] = d;
+    if (v) {
+      const float g = G[i];
+      const float ratio = fmaxf(d / g, g / d);
+      for (int k = 0; k < T; ++k) cnt[k] += ratio > thr[k] ? 1.0 : 0.0;
+      const float df = d - g;
+      se += (double)(df * df); l1 += (double)fabsf(df); rel += (double)(fabsf(df) / g);
+    }
+  }
+  for (int k = 0; k < T; ++k) cnt[k] = block_sum(cnt[k], red);
+  se = block_sum(se, red); l1 = block_sum(l1, red); rel = block_sum(rel, red);
+  if (threadIdx.x == 0) {
+    float* m = metrics + (size_t)b * (T + 3);
+    const float n = (float)a11;
+    for (int k = 0; k < T; ++k) m[k] = (float)cnt[k] / n;
+    m[T] = sqrtf((float)se / n);
+    m[T + 1] = (float)l1 / n;
+    m[T + 2] = (float)rel / n;
+  }
+}
+
 }  // namespace zs
 
 using namespace zs;
+
+extern "C" int zs_depth_metrics_f32(const float* pred, const float* gt, const float* mask, int B, int H, int W, const float* thresholds,
+                                    int T, float depth_cap, int disparity_input, float* metrics, float* depth_out, void* stream) {
+  ZS_REQUIRE(pred && gt && mask && metrics && depth_out && B > 0 && H > 0 && W > 0, "zs_depth_metrics_f32: bad args");
+  ZS_REQUIRE(T >= 0 && T <= DM_MAX_T && (T == 0 || thresholds), "zs_depth_metrics_f32: 0 <= T <= 8 thresholds (device array)");
+  depth_metric_kernel<<<B, MD_THREADS, 0, as_stream(stream)>>>(pred, gt, mask, H, W, thresholds, T, depth_cap, disparity_input, metrics,
+                                                              depth_out);
+  ZS_CUDA_CHECK_LAUNCH("zs_depth_metrics_f32");
+  return ZS_OK;
+}
 
 extern "C" int zs_mask_erode_f32(const float* mask, float* out, int B, int H, int W, int pool, void* stream) {
   ZS_REQUIRE(mask && out && B > 0 && pool > 0 && H >= pool && W >= pool, "zs_mask_erode_f32: bad args");
