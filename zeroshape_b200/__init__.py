@@ -24,6 +24,8 @@ def install_as_reference_modules():
         "model.compute_graph.graph_depth": "zeroshape_b200.model.compute_graph.graph_depth",
         "utils.eval_3D": "zeroshape_b200.utils.eval_3D",
         "utils.camera": "zeroshape_b200.utils.camera",
+        "utils.loss": "zeroshape_b200.utils.loss",
+        "utils.eval_depth": "zeroshape_b200.utils.eval_depth",
         "external.chamfer3D.dist_chamfer_3D": "zeroshape_b200.external.chamfer3D.dist_chamfer_3D",
     }
     for ref_name, ours in mapping.items():
