@@ -220,6 +220,11 @@ int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T,
  * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
  * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
  * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
+/* Front end of the transformer seen-surface encoder (CoordEmb.forward, model/shape/seen_coord_enc.py:49-72): per-pixel
+ * Linear(3 -> C) of the XYZ map coord [B,H,W,3], `invalid` token where mask [B,H,W] <= 0.5, ws x ws window partition, the fixed
+ * 2-D sin-cos embedding pos [ws*ws+1, C] local to each window and the cls row -> out [B*(H/ws)*(W/ws), ws*ws+1, C]. */
+int zs_coord_embed_windows_f32(const float* coord, const float* mask, const float* w, const float* bias, const float* invalid,
+                               const float* pos, const float* cls, float* out, int B, int H, int W, int C, int ws, void* stream);
 /* DepthMetric.compute_metrics (utils/eval_depth.py:41-110): per image, least-squares scale / shift of the predicted disparity
  * (1 / (pred + 1e-6), or pred itself when disparity_input) to 1 / gt over mask > 0.5, aligned depth = 1 / max(aligned disparity,
  * 1 / depth_cap) (depth_cap <= 0: no cap), then metrics [B, T + 3] = {fraction with max(d/g, g/d) > thresholds[k]} (thresholds: T <= 8

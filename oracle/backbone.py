@@ -283,3 +283,28 @@ def graph_shape_encode(sd, rgb, mask_map, H=224, W=224):
     latent = coord_enc_res(sd, dsp, mask_dsp)
     return dict(depth_pred=depth, intr_pred=K, seen_points=seen, latent_depth=latent,
                 validity_mask=(mask_map > 0.5).float().view(B, -1), intr_feat=feat)
+
+
+# ---- transformer seen-surface encoder (model/shape/seen_coord_enc.py:13-139; SURVEY.md section 8a row a7') ----------------
+def coord_emb_forward(sd, coord, mask, pre, heads, ws):
+    """CoordEmb.forward :49-78.  coord [B,H,W,3], mask bool [B,H,W] -> [B, (H/ws)*(W/ws), C]."""
+    emb = F.linear(coord, sd[pre + "pos_embed.weight"], sd[pre + "pos_embed.bias"])
+    emb = torch.where(mask.unsqueeze(-1), emb, sd[pre + "invalid_coord_token"].expand_as(emb))
+    B, H, W, C = emb.shape
+    emb = emb.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws * ws, C)
+    pos = sd[pre + "two_d_pos_embed"]
+    emb = emb + pos[:, 1:, :]
+    cls = (sd[pre + "cls_token"] + pos[:, :1, :]).expand(emb.shape[0], -1, -1)
+    emb = vit_block(sd, torch.cat((cls, emb), dim=1), pre + "blocks.0.", heads)
+    return emb[:, 0].view(B, (H // ws) * (W // ws), -1)
+
+
+def coord_enc_att_forward(sd, coord, mask, pre="coord_encoder.", heads=8, ws=8):
+    """CoordEncAtt.forward :119-139 (eval mode) -> [B, 1 + (H/ws)*(W/ws), C]."""
+    x = coord_emb_forward(sd, coord, mask, pre + "coord_embed.", heads, ws)
+    x = torch.cat((sd[pre + "cls_token"].expand(x.shape[0], -1, -1), x), dim=1)
+    n_blocks = 1 + max(int(k[len(pre + "blocks."):].split(".")[0]) for k in sd if k.startswith(pre + "blocks."))
+    for i in range(n_blocks):
+        x = vit_block(sd, x, f"{pre}blocks.{i}.", heads)
+    C = x.shape[-1]
+    return F.layer_norm(x, (C,), sd[pre + "norm.weight"], sd[pre + "norm.bias"], VIT_LN_EPS)

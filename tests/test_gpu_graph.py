@@ -125,3 +125,71 @@ def test_depth_graph_and_guards(cuda):
     # the training path of this graph is covered by tests/test_gpu_midas.py; eval mode never needs ground truth
     var2, loss = dg.forward(opt, EasyDict(idx=torch.arange(1), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda)), training=False)
     assert len(loss) == 0 and torch.equal(var2.depth_pred, var.depth_pred)
+
+
+def test_coord_enc_att_matches_reference_golden_and_oracle(cuda):
+    """Transformer seen-surface encoder (SURVEY.md section 8a row a7'): the mirror on the CUDA kernels vs the real reference
+    module's golden output, and vs the oracle at the deployed geometry (112 x 112 map, 12 blocks)."""
+    from test_oracle_coordatt import G as GC, golden_sd
+    from zeroshape_b200 import ops
+    from zeroshape_b200.model.shape.seen_coord_enc import CoordEncAtt
+    mod = CoordEncAtt(embed_dim=256, n_blocks=3, num_heads=8, win_size=8)
+    mod.load_state_dict(golden_sd(), strict=True)
+    mod = mod.to(cuda).eval()
+    ref = torch.from_numpy(GC["out"])
+    for engine, tol in (("f32", 2e-5), ("auto", 1e-3)):
+        ops.ENCODER_ENGINE = engine
+        try:
+            out = mod(torch.from_numpy(GC["coord"]).to(cuda), torch.from_numpy(GC["mask"]).to(cuda))
+        finally:
+            ops.ENCODER_ENGINE = "auto"
+        err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
+        print("CoordEncAtt engine", engine, "rel err vs the reference module", err)
+        assert out.shape == ref.shape and err < tol, (engine, err)
+    # deployed geometry: H/dsp = W/dsp = 112, win 8 -> 196 window tokens + cls, 12 blocks
+    big = CoordEncAtt(embed_dim=256, n_blocks=12, num_heads=8, win_size=8)
+    shapes = {k: tuple(v.shape) for k, v in big.state_dict().items()}
+    sd = seeded_state_dict(shapes, seed=77, implicit_prefix=None)
+    sd["coord_embed.two_d_pos_embed"] = big.state_dict()["coord_embed.two_d_pos_embed"].clone()
+    big.load_state_dict(sd, strict=True)
+    big = big.to(cuda).eval()
+    g = torch.Generator().manual_seed(78)
+    coord = torch.randn(2, 112, 112, 3, generator=g) * 0.4
+    yy, xx = torch.meshgrid(torch.arange(112), torch.arange(112), indexing="ij")
+    mask = (((yy - 56) ** 2 + (xx - 52) ** 2) < 40 ** 2).unsqueeze(0).repeat(2, 1, 1)
+    with torch.no_grad():
+        want = BB.coord_enc_att_forward({"coord_encoder." + k: v for k, v in sd.items()}, coord * mask.unsqueeze(-1), mask)
+    got = big((coord * mask.unsqueeze(-1)).to(cuda), mask.to(cuda))
+    assert got.shape == (2, 197, 256) and _rel(got, want) < 1e-3, _rel(got, want)
+
+
+def test_graph_with_transformer_encoder(cuda):
+    """graph_shape.Graph with `arch.depth.encoder != resnet` (dsp 2, windows of 16 // 2 = 8 pixels on the 112 x 112 resampled XYZ map):
+    latent_depth equals the oracle's interpolate_coordmap + CoordEncAtt on the graph's own seen surface (graph_shape.py:141-150)."""
+    import torch.nn.functional as F
+    from zeroshape_b200.model.compute_graph.graph_shape import Graph
+    from zeroshape_b200.utils.util import EasyDict
+    opt = make_opt(cuda)
+    opt.arch.depth.encoder = "transformer"
+    opt.arch.depth.n_blocks = 2
+    opt.arch.depth.dsp = 2
+    torch.manual_seed(5)
+    graph = Graph(opt).to(cuda).eval()
+    with torch.no_grad():
+        getattr(graph.dpt_depth.scratch.output_conv, "4").bias.fill_(0.5)      # depth inside (0, 1) for the random-init estimator
+    rgb, mask = synthetic_image_and_mask(2, 91, 116, 108, 70)
+    var = EasyDict(idx=torch.arange(2), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), pose_gt=False)
+    var = graph.forward(opt, var, training=False, get_loss=False)
+    assert var.latent_depth.shape == (2, 197, 256) and torch.isfinite(var.latent_depth).all()
+    seen = var.seen_points.cpu().view(2, 224, 224, 3).permute(0, 3, 1, 2)
+    m = (mask > 0.5).float()
+    cv = F.interpolate(seen * m, (112, 112), mode="bilinear", align_corners=False)
+    mk = F.interpolate(m, (112, 112), mode="bilinear", align_corners=False)
+    mb = (mk > 0.5).float()
+    coord = (cv / (mk + 1.e-6)) * mb
+    sd = {k: v.detach().cpu() for k, v in graph.state_dict().items() if k.startswith("coord_encoder.")}
+    with torch.no_grad():
+        want = BB.coord_enc_att_forward(sd, coord.permute(0, 2, 3, 1).contiguous(), mb.squeeze(1) > 0.5)
+    assert _rel(var.latent_depth, want) < 1e-3, _rel(var.latent_depth, want)
+    logits, _ = graph.impl_network(var.latent_depth, None, torch.rand(2, 50, 3, device=cuda) - 0.5, need_attn=False)
+    assert logits.shape == (2, 50) and torch.isfinite(logits).all()

@@ -69,6 +69,7 @@ SIGNATURES = {
     "zs_bilinear_bwd_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_unproject_normalize_bwd_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "zs_adamw_f32": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "zs_coord_embed_windows_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_depth_metrics_f32": (c_int, [P, P, P, c_int, c_int, c_int, P, c_int, c_float, c_int, P, P, P]),
     "zs_mask_erode_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "zs_midas_ws_bytes": (c_size_t, [c_int, c_int, c_int]),

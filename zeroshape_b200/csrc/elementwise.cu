@@ -396,6 +396,55 @@ extern "C" int zs_point_proj_f32(const float* points, int64_t M, const float* W,
   return ZS_OK;
 }
 
+// ---- CoordEmb front end (model/shape/seen_coord_enc.py:49-72): Linear(3 -> C) of every pixel of the XYZ map, the learned token
+// for invalid pixels, the window partition, the fixed 2-D sin-cos embedding local to each window and the per-window cls row --
+// seven tensor-sized torch ops (incl. two boolean scatters and a 6-D permute) as one output-bandwidth-bound launch.
+//   out[(b, wy, wx), 0, c]        = cls[c] + pos[0, c]
+//   out[(b, wy, wx), 1 + j, c]    = (mask ? w[c,:] . xyz + bias[c] : invalid[c]) + pos[1 + j, c],   j = dy * ws + dx
+namespace zs {
+__global__ void coord_embed_windows_kernel(const float* __restrict__ coord, const float* __restrict__ mask, const float* __restrict__ w,
+                                           const float* __restrict__ bias, const float* __restrict__ invalid,
+                                           const float* __restrict__ pos, const float* __restrict__ cls, float* __restrict__ out, int B,
+                                           int H, int W, int C, int ws) {
+  const int nwy = H / ws, nwx = W / ws, T = ws * ws + 1;
+  const int64_t total = (int64_t)B * nwy * nwx * T * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int tok = (int)(r % T);
+    const int64_t win = r / T;
+    float v;
+    if (tok == 0) {
+      v = cls[c];
+    } else {
+      const int j = tok - 1, dy = j / ws, dx = j - dy * ws;
+      const int wx = (int)(win % nwx), wy = (int)((win / nwx) % nwy), b = (int)(win / ((int64_t)nwx * nwy));
+      const int64_t pix = ((int64_t)b * H + wy * ws + dy) * W + wx * ws + dx;
+      if (mask[pix] > 0.5f) {
+        const float x = coord[pix * 3], y = coord[pix * 3 + 1], z = coord[pix * 3 + 2];
+        v = fmaf(z, w[c * 3 + 2], fmaf(y, w[c * 3 + 1], x * w[c * 3])) + bias[c];
+      } else {
+        v = invalid[c];
+      }
+    }
+    out[i] = v + pos[(int64_t)tok * C + c];
+  }
+}
+}  // namespace zs
+
+extern "C" int zs_coord_embed_windows_f32(const float* coord, const float* mask, const float* w, const float* bias, const float* invalid,
+                                          const float* pos, const float* cls, float* out, int B, int H, int W, int C, int ws,
+                                          void* stream) {
+  ZS_REQUIRE(coord && mask && w && bias && invalid && pos && cls && out, "zs_coord_embed_windows_f32: null pointer");
+  ZS_REQUIRE(B > 0 && C > 0 && ws > 0 && H >= ws && W >= ws && H % ws == 0 && W % ws == 0,
+             "zs_coord_embed_windows_f32: the map must tile into ws x ws windows");
+  const int64_t total = (int64_t)B * (H / ws) * (W / ws) * (ws * ws + 1) * C;
+  zs::coord_embed_windows_kernel<<<zs::grid_for(total), 256, 0, zs::as_stream(stream)>>>(coord, mask, w, bias, invalid, pos, cls, out, B, H, W,
+                                                                                        C, ws);
+  ZS_CUDA_CHECK_LAUNCH("zs_coord_embed_windows_f32");
+  return ZS_OK;
+}
+
 // ---- debug: effective SM clock right now (cycles of clock64 per globaltimer microsecond over a ~20k-cycle spin) ----
 // Used by tools/diag_decoder.py and bench.py to see power-cap clock droop between the tensor-heavy kernels.
 namespace zs {

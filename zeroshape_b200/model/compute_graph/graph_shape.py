@@ -22,7 +22,7 @@ from ...utils.layers import Bottleneck_Conv
 from ...utils.util import EasyDict as edict
 from ..depth.dpt_depth import DPTDepthModel
 from ..shape.implicit import Implicit
-from ..shape.seen_coord_enc import CoordEncRes
+from ..shape.seen_coord_enc import CoordEncAtt, CoordEncRes
 from ...utils.loss import Loss
 
 
@@ -45,9 +45,9 @@ class Graph(nn.Module):
         if opt.arch.depth.encoder == "resnet":
             opt.arch.depth.dsp = 1                              # graph_shape.py:41-43
             self.coord_encoder = CoordEncRes(opt)
-        else:
-            raise NotImplementedError("transformer seen-surface encoder (CoordEncAtt) is not the shipped "
-                                      "configuration (options/shape.yaml:26); SURVEY.md section 8f rank 4")
+        else:                                                   # graph_shape.py:44-46 (inference only here)
+            self.coord_encoder = CoordEncAtt(embed_dim=opt.arch.latent_dim, n_blocks=opt.arch.depth.n_blocks,
+                                             num_heads=opt.arch.num_heads, win_size=opt.arch.win_size // opt.arch.depth.dsp)
         if opt.arch.rgb.encoder:
             raise NotImplementedError("RGB branch is 'not used in final model' (graph_shape.py:48)")
         self.rgb_encoder = None
@@ -83,6 +83,8 @@ class Graph(nn.Module):
         if full_train:
             # default options/shape.yaml (fix_dpt: false): the shape loss reaches the depth estimator through the seen surface.
             # One tape from the image to latent_depth (model/depth/dpt_train.py), hand-written backward for every layer.
+            if isinstance(self.coord_encoder, CoordEncAtt):
+                raise NotImplementedError("zeroshape_b200 Graph: the transformer seen-surface encoder (CoordEncAtt) is inference-only")
             if not self.coord_encoder.training:
                 raise NotImplementedError("zeroshape_b200 Graph: training the depth estimator with the seen-surface encoder in "
                                           "eval mode is not supported (call graph.train())")
@@ -110,10 +112,19 @@ class Graph(nn.Module):
                 var.validity_mask = (mask > 0.5).float().view(batch_size, -1)
                 # unproject + masked mean / max-norm + normalise + zero background: one launch, no host sync
                 var.seen_points, self.last_mean, self.last_scale = ops.unproject_normalize(var.depth_pred, mask, var.intr_pred)
-                # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
-                coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
-                if not self.coord_encoder.training:
-                    var.latent_depth = self.coord_encoder.forward_nhwc(coord)
+                if isinstance(self.coord_encoder, CoordEncAtt):
+                    # graph_shape.py:141-150: mask-aware resampling of the XYZ map to H/dsp x W/dsp, NHWC + boolean mask
+                    from ...utils.util import interpolate_coordmap
+                    seen_map = var.seen_points.view(batch_size, opt.H, opt.W, 3).permute(0, 3, 1, 2).contiguous()
+                    seen_dsp, mask_dsp = interpolate_coordmap(seen_map, var.mask_input_map.float(),
+                                                              (opt.H // opt.arch.depth.dsp, opt.W // opt.arch.depth.dsp))
+                    var.latent_depth = self.coord_encoder(seen_dsp.permute(0, 2, 3, 1).contiguous(), mask_dsp.squeeze(1) > 0.5)
+                    coord = None
+                else:
+                    # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
+                    coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
+                    if not self.coord_encoder.training:
+                        var.latent_depth = self.coord_encoder.forward_nhwc(coord)
             var.pose = var.pose_gt if "pose_gt" in var else False
             if "gt_sample_points" in var and "gt_sample_sdf" in var:
                 # graph_shape.py:157-182: normalising factors from the GT seen surface, GT points -> camera frame -> normalised
@@ -124,7 +135,7 @@ class Graph(nn.Module):
                 var.gt_points_cam = ((cam - self.gt_mean.unsqueeze(1)) / self.gt_scale.view(-1, 1, 1)).contiguous()
                 idx = torch.topk(var.gt_sample_sdf.abs(), k=min(100, var.gt_sample_sdf.shape[1]), dim=1, largest=False)[1]
                 var.gt_surf_points = torch.gather(var.gt_points_cam, 1, idx.unsqueeze(-1).repeat(1, 1, 3))
-        if self.coord_encoder.training and not full_train:
+        if self.coord_encoder.training and not full_train and not isinstance(self.coord_encoder, CoordEncAtt):
             # train mode: batch-statistics BatchNorm, differentiable w.r.t. the encoder parameters (seen_coord_enc_train.py)
             var.latent_depth = self.coord_encoder.forward_nhwc(coord)
         if "gt_sample_points" in var and "gt_sample_sdf" in var:

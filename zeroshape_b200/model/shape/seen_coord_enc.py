@@ -8,8 +8,11 @@ state_dict keys = torchvision's (`encoder.conv1/bn1/layerN.M.{conv,bn}K/downsamp
 `encoder.fc.{0,1}` Bottleneck_Conv(2048), `encoder.fc.2` Linear and `depth_feat_proj.{0,1,2}`.
 Eval-mode BatchNorm is folded into the (OHWI) filters once per weight version; conv+BN+ReLU and
 conv+BN+add+ReLU are single launches.  In train mode the forward uses batch statistics and is differentiable
-(seen_coord_enc_train.py: the `optim.fix_dpt` training configuration).  The transformer variant (CoordEncAtt) is not the shipped
-configuration and is not mirrored.
+(seen_coord_enc_train.py: the `optim.fix_dpt` training configuration).
+
+The transformer variant `CoordEncAtt` (+ `CoordEmb`; model/shape/seen_coord_enc.py:13-139, `arch.depth.encoder != resnet`) is mirrored for
+inference: the window front end is one launch (zs_coord_embed_windows_f32), every Block runs on the LayerNorm / tcgen05 linear / attention
+kernels of the ViT path.  Its training backward is not implemented.
 """
 import torch
 import torch.nn as nn
@@ -112,3 +115,109 @@ class CoordEncRes(nn.Module):
             return self.forward_nhwc(x)
         with torch.no_grad():
             return self.forward_nhwc(x)
+
+
+# ---- transformer seen-surface encoder (SURVEY.md section 8a row a7') ---------------------------------------------------
+def _sincos_1d(dim, pos):
+    """utils/pos_embed.py:53-70."""
+    import numpy as np
+    omega = np.arange(dim // 2, dtype=np.float32)
+    omega /= dim / 2.
+    omega = 1. / 10000 ** omega
+    out = np.einsum("m,d->md", pos.reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def get_2d_sincos_pos_embed(embed_dim, grid_size, cls_token=False):
+    """utils/pos_embed.py:21-50 (MAE-style fixed embedding; w goes first in the meshgrid)."""
+    import numpy as np
+    gh = np.arange(grid_size, dtype=np.float32)
+    gw = np.arange(grid_size, dtype=np.float32)
+    grid = np.stack(np.meshgrid(gw, gh), axis=0).reshape([2, 1, grid_size, grid_size])
+    emb = np.concatenate([_sincos_1d(embed_dim // 2, grid[0]), _sincos_1d(embed_dim // 2, grid[1])], axis=1)
+    if cls_token:
+        emb = np.concatenate([np.zeros([1, embed_dim]), emb], axis=0)
+    return emb
+
+
+def _make_block(dim, mlp_ratio):
+    """Parameter container with timm Block's sub-module names (norm1, attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2)."""
+    blk = _Holder()
+    blk.norm1 = nn.LayerNorm(dim, eps=1e-6)
+    blk.attn = _Holder()
+    blk.attn.qkv = nn.Linear(dim, dim * 3)
+    blk.attn.proj = nn.Linear(dim, dim)
+    blk.norm2 = nn.LayerNorm(dim, eps=1e-6)
+    blk.mlp = _Holder()
+    blk.mlp.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
+    blk.mlp.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
+    return blk
+
+
+def _run_block(x, blk, heads):
+    """timm Block forward (eval: DropPath is the identity) on [N, T, C]."""
+    h = ops.layernorm(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+    a = ops.mha(ops.linear(h, blk.attn.qkv.weight, blk.attn.qkv.bias), heads)
+    x = ops.linear(a, blk.attn.proj.weight, blk.attn.proj.bias, res=x)
+    h = ops.layernorm(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+    h = ops.linear(h, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU)
+    return ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=x)
+
+
+class CoordEmb(nn.Module):
+    """model/shape/seen_coord_enc.py:13-78: every ws x ws window of the XYZ map -> one token (cls row of a single Block)."""
+
+    def __init__(self, embed_dim, win_size=8, num_heads=8):
+        super().__init__()
+        self.embed_dim, self.win_size, self.num_heads = embed_dim, win_size, num_heads
+        self.two_d_pos_embed = nn.Parameter(torch.zeros(1, win_size * win_size + 1, embed_dim), requires_grad=False)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Linear(3, embed_dim)
+        self.blocks = nn.ModuleList([_make_block(embed_dim, 2.0)])
+        self.invalid_coord_token = nn.Parameter(torch.zeros(embed_dim,))
+        nn.init.normal_(self.cls_token, std=.02)
+        self.two_d_pos_embed.data.copy_(torch.from_numpy(get_2d_sincos_pos_embed(embed_dim, win_size, cls_token=True)).float().unsqueeze(0))
+        nn.init.normal_(self.invalid_coord_token, std=.02)
+
+    def forward(self, coord_obj, mask_obj):
+        """coord_obj [B,H,W,3], mask_obj bool [B,H,W] -> [B, (H/ws)*(W/ws), C]."""
+        B, H, W, _ = coord_obj.shape
+        ws = self.win_size
+        emb = ops.coord_embed_windows(coord_obj.float().contiguous(), mask_obj.float().contiguous(), self.pos_embed.weight.detach(),
+                                      self.pos_embed.bias.detach(), self.invalid_coord_token.detach(),
+                                      self.two_d_pos_embed.detach().reshape(ws * ws + 1, -1).contiguous(),
+                                      self.cls_token.detach().reshape(-1).contiguous(), ws)
+        for blk in self.blocks:
+            emb = _run_block(emb, blk, self.num_heads)
+        return emb[:, 0].reshape(B, (H // ws) * (W // ws), -1)
+
+
+class CoordEncAtt(nn.Module):
+    """model/shape/seen_coord_enc.py:80-139: window tokens + a global cls token through n_blocks transformer blocks."""
+
+    def __init__(self, embed_dim=768, n_blocks=12, num_heads=12, win_size=8, mlp_ratio=4., drop_path=0.1):
+        super().__init__()
+        self.num_heads = num_heads
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.coord_embed = CoordEmb(embed_dim, win_size, num_heads)
+        self.blocks = nn.ModuleList([_make_block(embed_dim, mlp_ratio) for _ in range(n_blocks)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        nn.init.normal_(self.cls_token, std=.02)
+        for m in self.modules():                                 # seen_coord_enc.py:109-117
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    def forward(self, coord_obj, mask_obj):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("CoordEncAtt has no hand-written backward (the shipped configuration trains CoordEncRes)")
+        with torch.no_grad():
+            x = self.coord_embed(coord_obj, mask_obj)
+            x = torch.cat([self.cls_token.detach().expand(x.shape[0], -1, -1), x], dim=1).contiguous()
+            for blk in self.blocks:
+                x = _run_block(x, blk, self.num_heads)
+            return ops.layernorm(x, self.norm.weight, self.norm.bias, self.norm.eps)

@@ -401,6 +401,19 @@ def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_
     return out
 
 
+def coord_embed_windows(coord, mask, w, bias, invalid, pos, cls, ws):
+    """CoordEmb front end: coord [B,H,W,3], mask [B,H,W] (float 0/1) -> window tokens [B*(H/ws)*(W/ws), ws*ws+1, C]."""
+    for t, n in ((coord, "coord"), (mask, "mask"), (w, "w"), (bias, "bias"), (invalid, "invalid"), (pos, "pos"), (cls, "cls")):
+        _chk(t, n)
+    B, H, W, _ = coord.shape
+    C = w.shape[0]
+    assert coord.shape[3] == 3 and mask.shape == (B, H, W) and w.shape == (C, 3) and pos.numel() == (ws * ws + 1) * C
+    out = torch.empty(B * (H // ws) * (W // ws), ws * ws + 1, C, device=coord.device, dtype=torch.float32)
+    check(lib.zs_coord_embed_windows_f32(_p(coord), _p(mask), _p(w), _p(bias), _p(invalid), _p(pos), _p(cls), _p(out), B, H, W, C, ws,
+                                         _stream()), "zs_coord_embed_windows_f32")
+    return out
+
+
 def dense_grid(n, rmin, rmax, x0, x1, device):
     out = torch.empty(x1 - x0, n, n, 3, device=device, dtype=torch.float32)
     check(lib.zs_dense_grid_f32(_p(out), n, rmin, rmax, x0, x1, _stream()), "zs_dense_grid_f32")
