@@ -83,8 +83,6 @@ class Graph(nn.Module):
         if full_train:
             # default options/shape.yaml (fix_dpt: false): the shape loss reaches the depth estimator through the seen surface.
             # One tape from the image to latent_depth (model/depth/dpt_train.py), hand-written backward for every layer.
-            if isinstance(self.coord_encoder, CoordEncAtt):
-                raise NotImplementedError("zeroshape_b200 Graph: the transformer seen-surface encoder (CoordEncAtt) is inference-only")
             if not self.coord_encoder.training:
                 raise NotImplementedError("zeroshape_b200 Graph: training the depth estimator with the seen-surface encoder in "
                                           "eval mode is not supported (call graph.train())")
@@ -118,8 +116,9 @@ class Graph(nn.Module):
                     seen_map = var.seen_points.view(batch_size, opt.H, opt.W, 3).permute(0, 3, 1, 2).contiguous()
                     seen_dsp, mask_dsp = interpolate_coordmap(seen_map, var.mask_input_map.float(),
                                                               (opt.H // opt.arch.depth.dsp, opt.W // opt.arch.depth.dsp))
-                    var.latent_depth = self.coord_encoder(seen_dsp.permute(0, 2, 3, 1).contiguous(), mask_dsp.squeeze(1) > 0.5)
-                    coord = None
+                    coord, att_mask = seen_dsp.permute(0, 2, 3, 1).contiguous(), mask_dsp.squeeze(1) > 0.5
+                    if not self.coord_encoder.training:
+                        var.latent_depth = self.coord_encoder(coord, att_mask)
                 else:
                     # interpolate_coordmap at dsp=1 (utils/util.py:336-345) is the identity resample followed by / (1 + 1e-6)
                     coord = ops.axpby(var.seen_points.view(batch_size, opt.H, opt.W, 3), 1.0 / (1.0 + 1.e-6))
@@ -135,7 +134,10 @@ class Graph(nn.Module):
                 var.gt_points_cam = ((cam - self.gt_mean.unsqueeze(1)) / self.gt_scale.view(-1, 1, 1)).contiguous()
                 idx = torch.topk(var.gt_sample_sdf.abs(), k=min(100, var.gt_sample_sdf.shape[1]), dim=1, largest=False)[1]
                 var.gt_surf_points = torch.gather(var.gt_points_cam, 1, idx.unsqueeze(-1).repeat(1, 1, 3))
-        if self.coord_encoder.training and not full_train and not isinstance(self.coord_encoder, CoordEncAtt):
+        if self.coord_encoder.training and not full_train and isinstance(self.coord_encoder, CoordEncAtt):
+            # train mode, depth estimator frozen (optim.fix_dpt): DropPath + hand-written backward (seen_coord_att_train.py)
+            var.latent_depth = self.coord_encoder(coord, att_mask)
+        elif self.coord_encoder.training and not full_train:
             # train mode: batch-statistics BatchNorm, differentiable w.r.t. the encoder parameters (seen_coord_enc_train.py)
             var.latent_depth = self.coord_encoder.forward_nhwc(coord)
         if "gt_sample_points" in var and "gt_sample_sdf" in var:

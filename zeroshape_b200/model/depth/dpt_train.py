@@ -420,8 +420,15 @@ def encoder_forward(graph, opt, rgb, mask, with_intr=True, with_coord=True):
     out = {"depth": depth, "depth_nhwc": depth_nhwc, "K": K, "seen": seen, "mean": mean, "scale": scale, "latent": None}
     if not with_coord:
         return tp, out
-    coord = ops.axpby(seen.view(B, H, W, 3), 1.0 / (1.0 + 1.e-6))
     enc = graph.coord_encoder
+    if hasattr(enc, "coord_embed"):
+        # transformer seen-surface encoder: mask-aware resampling to H/dsp x W/dsp, window tokens, transformer blocks -- all on the tape
+        from ...model.shape import seen_coord_att_train as cat
+        dsp = opt.arch.depth.dsp
+        coord_map, mb = cat.resample_on_tape(tp, view(tp, seen, B, H, W, 3), mask.view(B, 1, H, W), H // dsp, W // dsp)
+        out["latent"] = cat.train_forward(tp, enc, coord_map, mb)
+        return tp, out
+    coord = ops.axpby(seen.view(B, H, W, 3), 1.0 / (1.0 + 1.e-6))
     if enc.training:
         latent, T = cet.train_forward(enc, coord)
 

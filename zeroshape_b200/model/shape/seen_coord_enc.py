@@ -12,7 +12,7 @@ conv+BN+add+ReLU are single launches.  In train mode the forward uses batch stat
 
 The transformer variant `CoordEncAtt` (+ `CoordEmb`; model/shape/seen_coord_enc.py:13-139, `arch.depth.encoder != resnet`) is mirrored for
 inference: the window front end is one launch (zs_coord_embed_windows_f32), every Block runs on the LayerNorm / tcgen05 linear / attention
-kernels of the ViT path.  Its training backward is not implemented.
+kernels of the ViT path; in train mode it runs on the tape of seen_coord_att_train.py (DropPath, hand-written backward).
 """
 import torch
 import torch.nn as nn
@@ -198,6 +198,7 @@ class CoordEncAtt(nn.Module):
     def __init__(self, embed_dim=768, n_blocks=12, num_heads=12, win_size=8, mlp_ratio=4., drop_path=0.1):
         super().__init__()
         self.num_heads = num_heads
+        self.drop_path = drop_path                               # timm DropPath of the main blocks (train mode only)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.coord_embed = CoordEmb(embed_dim, win_size, num_heads)
         self.blocks = nn.ModuleList([_make_block(embed_dim, mlp_ratio) for _ in range(n_blocks)])
@@ -214,7 +215,8 @@ class CoordEncAtt(nn.Module):
 
     def forward(self, coord_obj, mask_obj):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("CoordEncAtt has no hand-written backward (the shipped configuration trains CoordEncRes)")
+            from .seen_coord_att_train import CoordAttTrainFn      # DropPath + hand-written backward on the tape
+            return CoordAttTrainFn.apply(self, coord_obj, mask_obj.float(), *list(self.parameters()))
         with torch.no_grad():
             x = self.coord_embed(coord_obj, mask_obj)
             x = torch.cat([self.cls_token.detach().expand(x.shape[0], -1, -1), x], dim=1).contiguous()
