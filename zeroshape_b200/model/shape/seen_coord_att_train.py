@@ -89,7 +89,7 @@ def train_forward(tp, mod, coord, mask_f, need_dcoord=True):
     B, _, C = tok.shape
     x = torch.cat([mod.cls_token.detach().expand(B, -1, -1), tok], dim=1).contiguous()
 
-    def bwd_cat():
+    def bwd_cat(x=x):                      # bind now: `x` is re-assigned by the block loop below
         dx = tp.pop(x)
         if dx is None:
             return
