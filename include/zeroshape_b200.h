@@ -381,11 +381,13 @@ int zs_chamfer_nn_bwd(const float* xyz1, const float* xyz2, const float* graddis
  *   zs_nn_bvh_query: for b < batch: queries q[(sets_q == 1 ? 0 : b)] [nq, 3] against target set (sets_t == 1 ? 0 : b);
  *                    writes dist [batch, nq] (squared) and idx [batch, nq] (index into the ORIGINAL target order).
  *                    `q_order` (optional, [nq] int32): processing order of the queries (e.g. a Morton order, so that
- *                    neighbouring threads walk the same boxes); results are stored at the query's own index. */
+ *                    neighbouring threads walk the same boxes); results are stored at the query's own index.
+ *                    `variant` 0 = one thread per query, 1 = warp-cooperative (a warp answers its 32 queries one at a time with all
+ *                    lanes: no divergence); identical results. */
 size_t zs_nn_bvh_bytes(int sets, int n);
 int zs_nn_bvh_build(const float* pts, int sets, int n, void* bvh, void* stream);
 int zs_nn_bvh_query(const void* bvh, int sets_t, int n, const float* q, int sets_q, int nq, int batch,
-                    const int32_t* q_order, float* dist, int32_t* idx, void* stream);
+                    const int32_t* q_order, float* dist, int32_t* idx, int variant, void* stream);
 
 /* compute_fscore + means (utils/eval_3D.py:131-137,215-231) from squared distances: sqrt, mean, and
  * strict-< threshold fractions.  `squared`=1: inputs are squared distances (sqrt taken first, like

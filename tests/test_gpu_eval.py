@@ -227,20 +227,22 @@ def test_nn_bvh_is_bit_identical_to_the_dense_chamfer(cuda, sets, n, nq):
     td, qd = t.to(cuda).contiguous(), q.to(cuda).contiguous()
     bvh = ops.NNBvh(td)
     order = ops.NNBvh(qd[:1].contiguous()).morton_order()
-    for q_order in (None, order):
-        d, i = bvh.query(qd, q_order=q_order)
-        d_ref, _, i_ref, _ = ops.chamfer_nn(qd, td)
-        assert torch.equal(d, d_ref) and torch.equal(i, i_ref)
+    d_ref, _, i_ref, _ = ops.chamfer_nn(qd, td)
+    for variant in (0, 1):                    # one thread per query / warp-cooperative
+        for q_order in (None, order):
+            d, i = bvh.query(qd, q_order=q_order, variant=variant)
+            assert torch.equal(d, d_ref) and torch.equal(i, i_ref), (variant, q_order is None)
     r1, _, j1, _ = E.chamfer_nn(q.numpy(), t.numpy())
     assert np.array_equal(d.cpu().numpy(), r1) and np.array_equal(i.cpu().numpy(), j1)
     assert sorted(order.cpu().tolist()) == list(range(nq))
     # shared target / shared query forms used by the pose search
-    d_s, i_s = ops.NNBvh(td[:1].contiguous()).query(qd)
     d_sr, _, i_sr, _ = ops.chamfer_nn(qd, td[:1].expand(sets, -1, -1).contiguous())
-    assert torch.equal(d_s, d_sr) and torch.equal(i_s, i_sr)
-    d_q, i_q = bvh.query(qd[:1].contiguous(), batch=sets)
     d_qr, _, i_qr, _ = ops.chamfer_nn(qd[:1].expand(sets, -1, -1).contiguous(), td)
-    assert torch.equal(d_q, d_qr) and torch.equal(i_q, i_qr)
+    for variant in (0, 1):
+        d_s, i_s = ops.NNBvh(td[:1].contiguous()).query(qd, variant=variant)
+        assert torch.equal(d_s, d_sr) and torch.equal(i_s, i_sr)
+        d_q, i_q = bvh.query(qd[:1].contiguous(), batch=sets, variant=variant)
+        assert torch.equal(d_q, d_qr) and torch.equal(i_q, i_qr)
 
 
 def test_pose_search_bvh_equals_dense(cuda):

@@ -40,6 +40,8 @@ def main():
     gt_order = gt_bvh.morton_order()
     pred_order = ops.NNBvh(pred.contiguous()).morton_order()
     t_build, bvh = timed(lambda: ops.NNBvh(rot))
+    t_q1w, _ = timed(lambda: gt_bvh.query(rot, q_order=pred_order, variant=1))
+    t_q2w, _ = timed(lambda: bvh.query(gt, batch=R.shape[0], q_order=gt_order, variant=1))
     t_q1, (d1, _) = timed(lambda: gt_bvh.query(rot, q_order=pred_order))
     t_q1u, _ = timed(lambda: gt_bvh.query(rot))
     t_q2, (d2, _) = timed(lambda: bvh.query(gt, batch=R.shape[0], q_order=gt_order))
@@ -48,7 +50,13 @@ def main():
     print(f"one round of {R.shape[0]} rotations x {n} points (ms): rotate+normalise {t_rot:.3f} | build {t_build:.3f} | "
           f"query pred->gt {t_q1:.3f} (unordered {t_q1u:.3f}) | query gt->pred {t_q2:.3f} | stats {t_stats:.3f} "
           f"|| dense Chamfer of 24 rotations {t_dense:.3f} ms = {t_dense * R.shape[0] / 24:.1f} ms per {R.shape[0]}")
+    print(f"warp-cooperative queries: pred->gt {t_q1w:.3f} ms, gt->pred {t_q2w:.3f} ms")
     print(f"mean sqrt(d1) {d1.sqrt().mean().item():.4f}  mean sqrt(d2) {d2.sqrt().mean().item():.4f}")
+    for variant in (0, 1):
+        ops.BVH_QUERY_VARIANT = variant
+        t_v, _ = timed(lambda: eval_3D.brute_force_search(pred[0], gt[0], device=dev), reps=2)
+        print(f"brute_force_search, query variant {variant}: {t_v:.1f} ms per shape")
+    ops.BVH_QUERY_VARIANT = 0
     t_all, _ = timed(lambda: eval_3D.brute_force_search(pred[0], gt[0], device=dev), reps=2)
     print(f"brute_force_search (6912 rotations): {t_all:.1f} ms per shape")
 

@@ -114,7 +114,7 @@ SIGNATURES = {
     "zs_chamfer_nn_bwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P, P]),
     "zs_nn_bvh_bytes": (c_size_t, [c_int, c_int]),
     "zs_nn_bvh_build": (c_int, [P, c_int, c_int, P, P]),
-    "zs_nn_bvh_query": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, P, P, P, P]),
+    "zs_nn_bvh_query": (c_int, [P, c_int, c_int, P, c_int, c_int, c_int, P, P, P, c_int, P]),
     "zs_chamfer_stats": (c_int, [P, P, c_int, c_int, c_int, P, c_int, c_int, P, P, P, P, P]),
     "zs_mc_ws_bytes": (c_size_t, [c_int]),
     "zs_mc_count": (c_int, [P, c_int, c_float, P, P, P]),

@@ -215,6 +215,102 @@ __global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_kernel(const uint8_t
   idx[(int64_t)b * nq + qi] = besti;
 }
 
+// Warp-cooperative variant: a warp owns 32 consecutive query slots and answers them ONE AT A TIME with all 32 lanes -- lane = super-box
+// (<= 32 of them), then lane = box of an opened super-box (16), then lane = point of a visited cluster (32, one coalesced 512-byte read),
+// an arg-min butterfly per visited cluster.  Same visiting rule and tie rule, hence the same (distance, index) as the per-thread kernel,
+// but no divergence: the per-thread kernel ran with 16 of 32 lanes active (profiles/r1_ncu_nn_bvh.md).
+__global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_warp_kernel(const uint8_t* __restrict__ bvh, int sets_t, int n,
+                                                                        const float* __restrict__ q, int sets_q, int nq,
+                                                                        const int32_t* __restrict__ q_order, float* __restrict__ dist,
+                                                                        int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) float sbox[];          // [NC + NS][8]
+  const unsigned FULL = 0xffffffffu;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int NP = bvh_padded(n), NC = NP / BVH_CLUSTER, NS = bvh_supers(n);      // NS <= 32 (n <= 16384)
+  const uint8_t* base = bvh + (size_t)(sets_t == 1 ? 0 : b) * bvh_set_bytes(n);
+  const float4* pts = reinterpret_cast<const float4*>(base);
+  const float4* gbox = reinterpret_cast<const float4*>(base + (size_t)NP * 16);
+  for (int i = threadIdx.x; i < (NC + NS) * 2; i += BVQ_THREADS) reinterpret_cast<float4*>(sbox)[i] = gbox[i];
+  __syncthreads();
+  const int slot = blockIdx.x * BVQ_THREADS + threadIdx.x;
+  const bool live = slot < nq;
+  const int qi = live ? (q_order ? q_order[slot] : slot) : 0;
+  const float* qp = q + ((int64_t)(sets_q == 1 ? 0 : b) * nq + qi) * 3;
+  const float myx = live ? qp[0] : 0.f, myy = live ? qp[1] : 0.f, myz = live ? qp[2] : 0.f;
+  float my_best = INFINITY;
+  int my_besti = 0x7fffffff;
+  const unsigned live_mask = __ballot_sync(FULL, live);
+
+  for (int s = 0; s < 32; ++s) {
+    if (!((live_mask >> s) & 1u)) continue;                                   // warp-uniform
+    const float qx = __shfl_sync(FULL, myx, s), qy = __shfl_sync(FULL, myy, s), qz = __shfl_sync(FULL, myz, s);
+    auto lower = [&](int c) {
+      const float4 lo = reinterpret_cast<const float4*>(sbox)[2 * c], hi = reinterpret_cast<const float4*>(sbox)[2 * c + 1];
+      const float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.f),
+                  dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.f);
+      return (dx * dx + dy * dy + dz * dz) * 0.999999f;
+    };
+    float best = INFINITY;
+    int besti = 0x7fffffff;
+    auto visit = [&](int c) {                                                 // all lanes: one point each, then an arg-min butterfly
+      const float4 tp = __ldg(pts + (size_t)c * BVH_CLUSTER + lane);
+      float d = sqdist_ref_bvh(tp.x, tp.y, tp.z, qx, qy, qz);
+      int ti = __float_as_int(tp.w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float d2 = __shfl_xor_sync(FULL, d, o);
+        const int t2 = __shfl_xor_sync(FULL, ti, o);
+        if (d2 < d || (d2 == d && t2 < ti)) { d = d2; ti = t2; }
+      }
+      if (d < best || (d == best && ti < besti)) { best = d; besti = ti; }     // identical in every lane
+    };
+    // pass 1: closest super-box (lane = super-box), its closest box (lane = box), a first candidate
+    const float slb = lane < NS ? lower(NC + lane) : INFINITY;
+    float m = slb;
+    int ms = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(FULL, m, o);
+      const int s2 = __shfl_xor_sync(FULL, ms, o);
+      if (m2 < m || (m2 == m && s2 < ms)) { m = m2; ms = s2; }
+    }
+    const int s_first = ms < NS ? ms : 0;
+    {
+      const int c = s_first * BVH_SUPER + lane;
+      float bl = (lane < BVH_SUPER && c < NC) ? lower(c) : INFINITY;
+      int bc = c;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float b2 = __shfl_xor_sync(FULL, bl, o);
+        const int c2 = __shfl_xor_sync(FULL, bc, o);
+        if (b2 < bl || (b2 == bl && c2 < bc)) { bl = b2; bc = c2; }
+      }
+      const int first = (bc < NC && bc >= s_first * BVH_SUPER && bc < (s_first + 1) * BVH_SUPER) ? bc : s_first * BVH_SUPER;
+      visit(first);
+      // pass 2: every super-box / box that can still hold a point at most as far
+      for (int sb = 0; sb < NS; ++sb) {
+        const float lbs = __shfl_sync(FULL, slb, sb);
+        if (!(lbs <= best)) continue;                                         // warp-uniform
+        const int cc = sb * BVH_SUPER + lane;
+        const bool okc = lane < BVH_SUPER && cc < NC;
+        const float lbc = okc ? lower(cc) : INFINITY;
+        unsigned open = __ballot_sync(FULL, okc && lbc <= best && cc != first);
+        while (open) {
+          const int l = __ffs(open) - 1;
+          open &= open - 1;
+          const float lbl = __shfl_sync(FULL, lbc, l);
+          if (lbl <= best) visit(sb * BVH_SUPER + l);                         // `best` may have shrunk since the ballot
+        }
+      }
+    }
+    if (lane == s) { my_best = best; my_besti = besti; }
+  }
+  if (live) {
+    dist[(int64_t)b * nq + qi] = my_best;
+    idx[(int64_t)b * nq + qi] = my_besti;
+  }
+}
+
 }  // namespace zs
 
 using namespace zs;
@@ -240,15 +336,20 @@ extern "C" int zs_nn_bvh_build(const float* pts, int sets, int n, void* bvh, voi
 }
 
 extern "C" int zs_nn_bvh_query(const void* bvh, int sets_t, int n, const float* q, int sets_q, int nq, int batch,
-                               const int32_t* q_order, float* dist, int32_t* idx, void* stream) {
+                               const int32_t* q_order, float* dist, int32_t* idx, int variant, void* stream) {
   ZS_REQUIRE(bvh && q && dist && idx && n > 0 && nq > 0 && batch > 0, "zs_nn_bvh_query: bad args");
   ZS_REQUIRE((sets_t == 1 || sets_t == batch) && (sets_q == 1 || sets_q == batch),
              "zs_nn_bvh_query: target / query set counts must be 1 (shared) or the batch size");
   ZS_REQUIRE(n <= BVH_MAX_N && batch <= 65535, "zs_nn_bvh_query: too many points per set or too large a batch");
   const int smem = (bvh_padded(n) / BVH_CLUSTER + bvh_supers(n)) * 32;
   dim3 grid((nq + BVQ_THREADS - 1) / BVQ_THREADS, batch);
-  nn_bvh_query_kernel<<<grid, BVQ_THREADS, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(bvh), sets_t, n, q, sets_q, nq,
-                                                                     q_order, dist, idx);
+  ZS_REQUIRE(variant == 0 || variant == 1, "zs_nn_bvh_query: variant must be 0 (thread per query) or 1 (warp-cooperative)");
+  if (variant == 1)
+    nn_bvh_query_warp_kernel<<<grid, BVQ_THREADS, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(bvh), sets_t, n, q, sets_q,
+                                                                            nq, q_order, dist, idx);
+  else
+    nn_bvh_query_kernel<<<grid, BVQ_THREADS, smem, as_stream(stream)>>>(reinterpret_cast<const uint8_t*>(bvh), sets_t, n, q, sets_q, nq,
+                                                                       q_order, dist, idx);
   ZS_CUDA_CHECK_LAUNCH("zs_nn_bvh_query");
   return ZS_OK;
 }

@@ -487,6 +487,9 @@ def chamfer_nn_bwd(xyz1, xyz2, g1, g2, i1, i2):
     return gx1, gx2
 
 
+BVH_QUERY_VARIANT = 0      # zs_nn_bvh_query kernel: 0 = one thread per query, 1 = warp-cooperative (identical results)
+
+
 class NNBvh:
     """Flat box hierarchy over `sets` point clouds [sets, n, 3] (zs_nn_bvh_build): exact NN queries at ~1/20 of the
     brute-force pair evaluations, same distances / tie-breaking as `chamfer_nn`."""
@@ -506,7 +509,7 @@ class NNBvh:
         pts = self.blob[s * per_set: s * per_set + npad * 16].view(torch.int32).view(npad, 4)
         return pts[:self.n, 3].contiguous()
 
-    def query(self, q, batch=None, q_order=None):
+    def query(self, q, batch=None, q_order=None, variant=None):
         """q [sets_q, nq, 3] (sets_q = 1: shared by the batch) -> dist [batch, nq] (squared), idx [batch, nq] int32."""
         _chk(q, "q")
         sets_q, nq = q.shape[0], q.shape[1]
@@ -515,7 +518,7 @@ class NNBvh:
         idx = torch.empty(batch, nq, device=q.device, dtype=torch.int32)
         _chk(q_order, "q_order", torch.int32)
         check(lib.zs_nn_bvh_query(_p(self.blob), self.sets, self.n, _p(q), sets_q, nq, batch, _p(q_order), _p(dist), _p(idx),
-                                  _stream()), "zs_nn_bvh_query")
+                                  BVH_QUERY_VARIANT if variant is None else int(variant), _stream()), "zs_nn_bvh_query")
         return dist, idx
 
 
