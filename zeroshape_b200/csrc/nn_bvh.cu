@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_kernel(const uint8_t
 // Warp-cooperative variant: a warp owns 32 consecutive query slots and answers them ONE AT A TIME with all 32 lanes -- lane = super-box
 // (<= 32 of them), then lane = box of an opened super-box (16), then lane = point of a visited cluster (32, one coalesced 512-byte read),
 // an arg-min butterfly per visited cluster.  Same visiting rule and tie rule, hence the same (distance, index) as the per-thread kernel,
-// but no divergence: the per-thread kernel ran with 16 of 32 lanes active (profiles/r1_ncu_nn_bvh.md).
+// but no divergence: the per-thread kernel ran with 16 of 32 lanes active (profiles/r1_ncu_nn_bvh.md).  Measured on B200: 2.9x SLOWER
+// than the per-thread kernel (one dependent chain per warp instead of 16 independent ones) -- kept as a cross-check, not the default.
 __global__ void __launch_bounds__(BVQ_THREADS) nn_bvh_query_warp_kernel(const uint8_t* __restrict__ bvh, int sets_t, int n,
                                                                         const float* __restrict__ q, int sets_q, int nq,
                                                                         const int32_t* __restrict__ q_order, float* __restrict__ dist,
