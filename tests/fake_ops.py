@@ -76,7 +76,7 @@ def axpby(a, alpha=1.0, b=None, beta=1.0, act=0):
     y = a * alpha
     if b is not None:
         y = y + b * beta
-    return ACTS[act](y)
+    return ACTS[act](y).contiguous()
 
 
 def maxpool3x3s2_nhwc(x, pt, pl, OH, OW):
@@ -107,7 +107,7 @@ def mha(qkv, heads):
     C = C3 // 3
     hd = C // heads
     q, k, v = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
-    return (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C)
+    return (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C).contiguous()
 
 
 def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False):
@@ -170,4 +170,86 @@ def install(monkeypatch):
     for name in ("gemm", "linear", "PackedWeight", "gemm_tc", "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "channel_affine",
                  "axpby", "maxpool3x3s2_nhwc", "avgpool_nhwc", "bilinear_nhwc", "nchw_to_nhwc", "nhwc_to_nchw", "mha",
                  "point_attention", "dense_grid", "concat2", "intr_param2mtx", "unproject", "unproject_normalize", "device_cc"):
+        monkeypatch.setattr(ops, name, g[name])
+
+
+# ---- per-op stand-ins for the TRAINING kernels (tapes of model/shape/implicit_train.py, seen_coord_att_train.py, dpt_train.py):
+# forward ops as above, backward ops through torch autograd of the matching forward stand-in ------------------------------------
+def _via_autograd(fn, x, dy):
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        fn(xx).backward(dy)
+    return xx.grad
+
+
+def act_bwd(dy, z, act):
+    return _via_autograd(ACTS[act], z, dy)
+
+
+def layernorm_bwd(dy, x, gamma, eps, dgamma=None, dbeta=None):
+    gg, bb = gamma.detach().clone().requires_grad_(True), torch.zeros_like(gamma).requires_grad_(True)
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        F.layer_norm(xx, (x.shape[-1],), gg, bb, eps).backward(dy)
+    if dgamma is not None:
+        dgamma += gg.grad
+        dbeta += bb.grad
+    return xx.grad
+
+
+layernorm_bwd_generic = layernorm_bwd
+
+
+def mha_bwd(qkv, dout, heads):
+    return _via_autograd(lambda t: mha(t, heads), qkv, dout)
+
+
+def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
+    qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (qkv_p, k_lat, v_lat))
+    with torch.enable_grad():
+        point_attention(qq, kk, vv, heads).backward(dout)
+    return qq.grad, kk.grad, vv.grad
+
+
+def train_linear(x2, w, bias=None, res=None, res_mode=0, act=0):
+    return gemm(x2, w, bias, res, res_mode, act)
+
+
+def train_dgrad(dy, w):
+    return (dy @ w).contiguous()
+
+
+def gemm_tn(a, b, out=None, accumulate=False, tc=None):
+    r = a.T @ b
+    if out is not None:
+        out.copy_(out + r if accumulate else r)
+        return out
+    return r.contiguous()
+
+
+def colsum(a, out=None, accumulate=False):
+    r = a.sum(0)
+    if out is not None:
+        out.copy_(out + r if accumulate else r)
+        return out
+    return r
+
+
+def coord_embed_windows(coord, mask, w, bias, invalid, pos, cls, ws):
+    B, H, W, _ = coord.shape
+    C = w.shape[0]
+    emb = torch.where(mask.unsqueeze(-1) > 0.5, F.linear(coord, w, bias), invalid.expand(B, H, W, C))
+    emb = emb.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws * ws, C) + pos[1:].unsqueeze(0)
+    return torch.cat([(cls + pos[0]).view(1, 1, C).expand(emb.shape[0], -1, -1), emb], 1).contiguous()
+
+
+TRAIN_OPS = ("axpby", "act_bwd", "layernorm_bwd", "layernorm_bwd_generic", "mha", "mha_bwd", "point_attention", "point_attention_bwd",
+             "train_linear", "train_dgrad", "gemm_tn", "colsum", "coord_embed_windows", "layernorm", "gemm", "concat2")
+
+
+def install_train(monkeypatch):
+    """Replace the training-step wrappers of zeroshape_b200.ops by the CPU stand-ins above (host-logic tests of the tapes)."""
+    from zeroshape_b200 import ops
+    g = globals()
+    for name in TRAIN_OPS:
         monkeypatch.setattr(ops, name, g[name])

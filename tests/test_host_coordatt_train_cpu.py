@@ -3,73 +3,14 @@ gradient routing through the window selection / cls concatenation / front end) w
 torch autograd over the oracle restatement (pinned to the reference module).  The kernels themselves are checked on the GPU
 (tests/test_gpu_coordatt_train.py)."""
 import torch
-import torch.nn.functional as F
 
 import fake_ops
 from oracle import backbone as BB
 from oracle.graph_params import seeded_state_dict
 
 
-def _install(monkeypatch):
-    from zeroshape_b200 import ops
-    acts = fake_ops.ACTS
-
-    def axpby(a, alpha=1.0, b=None, beta=1.0, act=0):
-        return acts[act](alpha * a + (beta * b if b is not None else 0)).contiguous()
-
-    def via_autograd(fn, x, dy):
-        xx = x.detach().clone().requires_grad_(True)
-        with torch.enable_grad():
-            fn(xx).backward(dy)
-        return xx.grad
-
-    def ln_bwd(dy, x, gamma, eps, dgamma=None, dbeta=None):
-        gg, bb = gamma.detach().clone().requires_grad_(True), torch.zeros_like(gamma).requires_grad_(True)
-        xx = x.detach().clone().requires_grad_(True)
-        with torch.enable_grad():
-            F.layer_norm(xx, (x.shape[-1],), gg, bb, eps).backward(dy)
-        if dgamma is not None:
-            dgamma += gg.grad
-            dbeta += bb.grad
-        return xx.grad
-
-    def mha(qkv, heads):
-        B, T, C3 = qkv.shape
-        hd = C3 // 3 // heads
-        q, k, v = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
-        return (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C3 // 3).contiguous()
-
-    def coord_embed_windows(coord, mask, w, bias, invalid, pos, cls, ws):
-        B, H, W, _ = coord.shape
-        C = w.shape[0]
-        emb = torch.where(mask.unsqueeze(-1) > 0.5, F.linear(coord, w, bias), invalid.expand(B, H, W, C))
-        emb = emb.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws * ws, C) + pos[1:].unsqueeze(0)
-        return torch.cat([(cls + pos[0]).view(1, 1, C).expand(emb.shape[0], -1, -1), emb], 1).contiguous()
-
-    def gemm_tn(a, b, out=None, accumulate=False, tc=None):
-        r = a.T @ b
-        if out is not None:
-            out.copy_(out + r if accumulate else r)
-            return out
-        return r.contiguous()
-
-    def colsum(a, out=None, accumulate=False):
-        r = a.sum(0)
-        if out is not None:
-            out.copy_(out + r if accumulate else r)
-            return out
-        return r
-
-    for name, fn in dict(axpby=axpby, act_bwd=lambda dy, z, act: via_autograd(acts[act], z, dy), layernorm_bwd_generic=ln_bwd, mha=mha,
-                         mha_bwd=lambda qkv, dout, heads: via_autograd(lambda t: mha(t, heads), qkv, dout),
-                         coord_embed_windows=coord_embed_windows, layernorm=fake_ops.layernorm, gemm=fake_ops.gemm,
-                         train_linear=lambda x2, w, bias=None, res=None, res_mode=0, act=0: fake_ops.gemm(x2, w, bias, res, res_mode, act),
-                         train_dgrad=lambda dy, w: (dy @ w).contiguous(), gemm_tn=gemm_tn, colsum=colsum).items():
-        monkeypatch.setattr(ops, name, fn)
-
-
 def test_coord_att_tape_routes_every_gradient(monkeypatch):
-    _install(monkeypatch)
+    fake_ops.install_train(monkeypatch)
     from zeroshape_b200.model.depth import dpt_train as T
     from zeroshape_b200.model.shape import seen_coord_att_train as CAT
     from zeroshape_b200.model.shape.seen_coord_enc import CoordEncAtt

@@ -421,7 +421,7 @@ def dense_grid(n, rmin, rmax, x0, x1, device):
 
 
 def concat2(a, b, s=1.0):
-    """s * cat([a, b], -1) for 2-D row-strided inputs."""
+    """cat([a, b], -1) / s for 2-D row-strided inputs (the skip connections of MLPBlocks divide by sqrt(2), implicit.py:179-180)."""
     assert a.dim() == 2 and b.dim() == 2 and a.shape[0] == b.shape[0]
     rows = a.shape[0]
     y = torch.empty(rows, a.shape[1] + b.shape[1], device=a.device, dtype=torch.float32)
