@@ -45,7 +45,7 @@ def gemm_tc(a, pw, bias=None, res=None, res_mode=0, act=0, out=None, precision="
     return gemm(a, pw.src, bias, res, res_mode, act, out)
 
 
-def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, res=None, res_mode=0, pre_relu=False, tc=None):
+def conv2d_nhwc(x, w, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, res=None, res_mode=0, pre_relu=False, tc=None, precision=None):
     xn = x.permute(0, 3, 1, 2)
     if pre_relu:
         xn = F.relu(xn)
@@ -243,7 +243,46 @@ def coord_embed_windows(coord, mask, w, bias, invalid, pos, cls, ws):
     return torch.cat([(cls + pos[0]).view(1, 1, C).expand(emb.shape[0], -1, -1), emb], 1).contiguous()
 
 
-TRAIN_OPS = ("axpby", "act_bwd", "layernorm_bwd", "layernorm_bwd_generic", "mha", "mha_bwd", "point_attention", "point_attention_bwd",
+def train_tc():
+    return False
+
+
+def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad, tc=None):
+    x = torch.zeros(in_shape)
+    return _via_autograd(lambda t: conv2d_nhwc(t, w_ohwi, None, stride, pad), x, dy)
+
+
+def conv2d_nhwc_wgrad(x, dy, kh, kw, stride, pad, out=None, accumulate=False, tc=None):
+    w = torch.zeros(dy.shape[-1], kh, kw, x.shape[-1])
+    g = _via_autograd(lambda t: conv2d_nhwc(x, t, None, stride, pad), w, dy)
+    if out is not None:
+        out.copy_(out + g if accumulate else g)
+        return out
+    return g
+
+
+def groupnorm_bwd_nhwc(dy, x, gamma, groups, eps, dgamma, dbeta):
+    gg, bb = gamma.detach().clone().requires_grad_(True), torch.zeros_like(gamma).requires_grad_(True)
+    xx = x.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        groupnorm_nhwc(xx, gg, bb, groups, eps, False).backward(dy)
+    dgamma += gg.grad
+    dbeta += bb.grad
+    return xx.grad
+
+
+def maxpool3x3s2_bwd_nhwc(x, dy, pt, pl):
+    return _via_autograd(lambda t: maxpool3x3s2_nhwc(t, pt, pl, dy.shape[1], dy.shape[2]), x, dy)
+
+
+def bilinear_bwd_nhwc(dy, H, W, align):
+    x = torch.zeros(dy.shape[0], H, W, dy.shape[3])
+    return _via_autograd(lambda t: bilinear_nhwc(t, dy.shape[1], dy.shape[2], align), x, dy)
+
+
+TRAIN_OPS = ("train_tc", "conv2d_nhwc", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "groupnorm_nhwc", "groupnorm_bwd_nhwc", "maxpool3x3s2_nhwc",
+             "maxpool3x3s2_bwd_nhwc", "bilinear_nhwc", "bilinear_bwd_nhwc", "nchw_to_nhwc",
+             "axpby", "act_bwd", "layernorm_bwd", "layernorm_bwd_generic", "mha", "mha_bwd", "point_attention", "point_attention_bwd",
              "train_linear", "train_dgrad", "gemm_tn", "colsum", "coord_embed_windows", "layernorm", "gemm", "concat2")
 
 
