@@ -69,7 +69,7 @@ def channel_affine(x, scale, shift, act=0, res=None):
     y = x * scale + shift
     if res is not None:
         y = y + res
-    return ACTS[act](y)
+    return ACTS[act](y).contiguous()
 
 
 def axpby(a, alpha=1.0, b=None, beta=1.0, act=0):
@@ -280,7 +280,29 @@ def bilinear_bwd_nhwc(dy, H, W, align):
     return _via_autograd(lambda t: bilinear_nhwc(t, dy.shape[1], dy.shape[2], align), x, dy)
 
 
-TRAIN_OPS = ("train_tc", "conv2d_nhwc", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "groupnorm_nhwc", "groupnorm_bwd_nhwc", "maxpool3x3s2_nhwc",
+def bn_stats(x2d, eps):
+    mean = x2d.mean(0)
+    var = x2d.var(0, unbiased=False)
+    return mean, var, 1.0 / torch.sqrt(var + eps)
+
+
+def bn_bwd(dy2d, x2d, mean, rstd, gamma, dgamma, dbeta):
+    """Batch-statistics BatchNorm backward (the statistics depend on x)."""
+    xx, gg, bb = x2d.detach().clone().requires_grad_(True), gamma.detach().clone().requires_grad_(True), torch.zeros_like(gamma).requires_grad_(True)
+    with torch.enable_grad():
+        m, v = xx.mean(0), xx.var(0, unbiased=False)
+        eps = (1.0 / (rstd * rstd) - x2d.var(0, unbiased=False)).clamp_min(0).mean()      # recover eps from rstd (uniform over channels)
+        ((xx - m) / torch.sqrt(v + eps) * gg + bb).backward(dy2d)
+    dgamma += gg.grad
+    dbeta += bb.grad
+    return xx.grad
+
+
+def avgpool_bwd_nhwc(dy, H, W):
+    return (dy / (H * W)).view(dy.shape[0], 1, 1, dy.shape[1]).expand(-1, H, W, -1).contiguous()
+
+
+TRAIN_OPS = ("bn_stats", "bn_bwd", "avgpool_nhwc", "avgpool_bwd_nhwc", "channel_affine", "train_tc", "conv2d_nhwc", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "groupnorm_nhwc", "groupnorm_bwd_nhwc", "maxpool3x3s2_nhwc",
              "maxpool3x3s2_bwd_nhwc", "bilinear_nhwc", "bilinear_bwd_nhwc", "nchw_to_nhwc",
              "axpby", "act_bwd", "layernorm_bwd", "layernorm_bwd_generic", "mha", "mha_bwd", "point_attention", "point_attention_bwd",
              "train_linear", "train_dgrad", "gemm_tn", "colsum", "coord_embed_windows", "layernorm", "gemm", "concat2")
