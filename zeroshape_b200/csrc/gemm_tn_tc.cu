@@ -32,7 +32,7 @@ constexpr int TN_B_TILE = TN_BN * TN_BK * 2;            // 32 KB
 constexpr int TN_STAGE_BYTES = 2 * TN_A_TILE + 2 * TN_B_TILE;
 constexpr int TN_PROD_WARPS = 16;                       // latency-bound fp32 loads: 4 producer warps per scheduler
 constexpr int TN_PRODUCERS = TN_PROD_WARPS * 32;
-constexpr int TN_EPI_WARP0 = TN_PROD_WARPS, TN_MMA_WARP = TN_PROD_WARPS + 4;
+constexpr int TN_MMA_WARP = TN_PROD_WARPS + 4;         // epilogue warps = TN_PROD_WARPS .. +3 (TMEM lane quarter = warp & 3)
 constexpr int TN_THREADS = (TN_PROD_WARPS + 5) * 32;
 constexpr int TN_SMEM = TN_STAGES * TN_STAGE_BYTES + 1024 + 256 + 2 * TN_BK * 16;     // + align slack, barriers, 2 row tables
 
