@@ -13,6 +13,9 @@
 //                        the chain through scale / shift (five sums), the inverse-depth map and the SSI alignment -> d loss / d pred
 //   midas_finish_kernel: loss = sum_b ssi_b / (N + 1e-6) + alpha * sum_b reg_b
 // The formulas are those of oracle/midas.py::midas_loss_grad, which is pinned to the reference module's autograd.
+// Ties: when several valid pixels share the median value (e.g. predictions clamped to 0 or 1), the median's gradient goes to the LOWEST
+// pixel index among them; torch.nanmedian's choice among equal values is implementation-defined (CPU and CUDA differ), the loss value and
+// every other pixel's gradient are unaffected.
 #include "common.cuh"
 
 namespace zs {
