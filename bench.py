@@ -123,6 +123,8 @@ def run_ours(args, rank, world, dev):
     net.precision = args.precision
     if args.attention:
         net.attention = args.attention
+    if args.attn_flags is not None:
+        net.attn_flags = args.attn_flags
     rgb_host, mask_host = synthetic_images(args.shapes, 1000 + rank)
     rgb_host, mask_host = rgb_host.pin_memory(), mask_host.pin_memory()
     rgb_dev, mask_dev = rgb_host.to(dev), mask_host.to(dev)
@@ -133,7 +135,7 @@ def run_ours(args, rank, world, dev):
         lg, _ = net(var.latent_depth, None, probe, need_attn=False)
         net.impl_mlp.layers[-1].bias -= lg.median()
         assert torch.isfinite(var.latent_depth).all() and torch.isfinite(lg).all(), "synthetic model is degenerate"
-    engine = "fused" if net._use_fused() else (("tc" if net.engine == "tc" else "chain") if net._use_tc() else "f32")
+    engine = (("tc" if net.engine == "tc" else "chain") if net._use_tc() else "f32")
     out_host = torch.empty(args.shapes, 10000, 3).pin_memory()
     dec_events, enc_events = [], []
 
@@ -225,8 +227,9 @@ def run_ours(args, rank, world, dev):
             hot_path(rgb_dev[:1], mask_dev[:1], False)
         summ = ot.summary()
     per_point_flop = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
-                      "chain_occ": 2 * 724224, "point_proj": 2 * 768}
-    per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_occ": 1, "point_proj": 1}
+                      "chain_occ": 2 * 724224, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
+    per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_occ": 1, "point_proj": 1,
+                          "chain_qkvattn": 2}
     tot_ms = sum(v[1] for v in summ.values())
     for k, (cnt, ms_k) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
         row = {"op": k, "launches": cnt, "ms_per_shape": ms_k, "share": ms_k / tot_ms}
@@ -238,7 +241,7 @@ def run_ours(args, rank, world, dev):
     line = {
         "metric": METRIC, "value": shapes_total / (ms * 1e-3), "unit": "shapes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if engine == "f32" else ("bf16x3->f32acc" if args.precision == "bf16x3" else "bf16"),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if engine == "f32" else ("fp16x3->f32acc" if args.precision == "fp16x3" else "fp16"),
         "data": "synthetic",
         "config": {"workload": f"demo.py/evaluate.py hot path per shape: 224x224 RGB+mask -> DPT-hybrid depth + intrinsics -> unproject/"
                                f"normalise -> CoordEncRes latents -> implicit decoder over the ({args.vox_res}+1)^3 grid -> marching cubes "
@@ -547,8 +550,9 @@ def main():
     ap.add_argument("--train-precision", default="bf16", choices=["bf16", "bf16x3"],
                     help="tensor-core operand precision of the training GEMMs (BASELINE config 3 is bf16 mixed precision)")
     ap.add_argument("--engine", default="auto", choices=["auto", "chain", "fused", "tc", "f32"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
-    ap.add_argument("--attention", default=None, choices=["fused", "tc", "f32"])
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
+    ap.add_argument("--attention", default=None, choices=["qkv", "fused", "tc", "f32"])
+    ap.add_argument("--attn-flags", type=int, default=None, help="zs_chain_qkvattn_fwd pass policy (1 = k,v single-pass, 2, 4)")
     ap.add_argument("--cpu-slices", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu)")

@@ -67,6 +67,10 @@ int zs_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* b
  * precision 0 = "bf16x3" (Ah*Wh + Ah*Wl + Al*Wh, ~2^-16 relative: parity mode), 1 = "bf16" (single pass). */
 size_t zs_gemm_tc_packed_bytes(int N, int K);
 int zs_gemm_tc_pack(const float* W, int ldw, int N, int K, void* packed, void* stream);
+/* same image with the 16-bit operand format chosen: fmt 0 = bf16 (zs_gemm_tc_f32, convolutions, training GEMMs),
+ * fmt 1 = fp16 (every zs_chain_* kernel of the decoder: hi/lo fp16 carries 22 significand bits, 8x tighter than the
+ * bf16 split at the same MMA count -- profiles/r2_precision_study.md) */
+int zs_gemm_tc_pack_fmt(const float* W, int ldw, int N, int K, void* packed, int fmt, void* stream);
 int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, const float* bias,
                    const float* res, int ldres, int res_mode, float* C, int ldc,
                    int M, int N, int K, int act, int precision, void* stream);
@@ -84,13 +88,29 @@ int zs_attn_pv_tc(const float* P, const void* Vpacked, const float* R, const flo
                   void* stream);
 
 /* Same attention, flash-style in ONE kernel (scores, softmax numerators and P.V of a 128-point tile stay on the SM;
- * csrc/chain_tc.cu chain_attn_kernel).  The 8 heads are processed as 4 pairs (2p, 2p+1):
- *   Kblob: 4 pair tiles from zs_gemm_tc_pack(K_lat[:, 64p:64p+64] zero-padded to 256 rows) = 4 x [hi 32 KB | lo 32 KB]
+ * csrc/chain_tc.cu chain_attn_kernel).  Operand images of every zs_chain_* kernel are fp16 (zs_gemm_tc_pack_fmt, fmt 1);
+ * their `precision` 0 = "fp16x3" (Ah*Wh + Al*Wh + Ah*Wl, ~2^-22 relative: parity mode), 1 = "fp16" (single pass).
+ * The 8 heads are processed as 4 pairs (2p, 2p+1):
+ *   Kblob: 4 pair tiles from zs_gemm_tc_pack_fmt(K_lat[:, 64p:64p+64] zero-padded to 256 rows) = 4 x [hi 32 KB | lo 32 KB]
  *          (the two heads' 32 dims side by side, keys along the rows);
  *   Vblob: 8 heads x 32 KB = 4 key-chunks x [hi 4 KB | lo 4 KB] (the first 4 KB of each hi / lo tile of Vpacked above).
  * n_keys <= 208.  O [M,256]. */
 int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
                       float scale, float* O, int precision, void* stream);
+/* LayerNorm + qkv + the same attention in ONE kernel: norm1 of ImplFuncBlock and ImplFuncAttention up to the output
+ * projection (model/shape/implicit.py:105, 30-57; csrc/chain_tc.cu chain_qkvattn_kernel).  q, k, v of the query points,
+ * scores and probabilities stay on the SM: HBM sees x [M,256] (read) and O [M,256] (written).
+ *   Wblob   : zs_chain_qkvattn_blob_bytes() = 4 pairs x zs_gemm_tc_pack_fmt(Wp [256 rows, 256], fmt 1) where the rows of Wp
+ *             are [q rows of heads 2p, 2p+1 (64) | their k rows (64) | their v rows (64) | 64 zero rows] of
+ *             qkv.weight * norm1.weight (the LayerNorm affine folded in);
+ *   bias_qkv: [768] = qkv.bias + qkv.weight @ norm1.bias, original q | k | v order;
+ *   Kblob / Vblob / n_keys / scale: as zs_chain_attn_fwd.
+ *   flags   : per-GEMM pass policy on top of precision 0: 1 = k, v columns single-pass, 2 = scores without Qh*Kl,
+ *             4 = P*V without Ph*Vl (0 = every contraction three passes). */
+size_t zs_chain_qkvattn_blob_bytes(void);
+int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const void* Wblob, const float* bias_qkv,
+                         const void* Kblob, const void* Vblob, int n_keys, float scale, float* O, int ldo,
+                         int precision, int flags, void* stream);
 /* debug: while buf (device, [3][512] uint64) is non-NULL the chained kernels record role-level clock64 events of
  * CTA 0 (MMA thread, loader thread 0, epilogue warp 4 lane 0) into it; see tools/trace_chain.py.  Not thread-safe. */
 int zs_debug_chain_trace(unsigned long long* buf);
@@ -306,42 +326,6 @@ int zs_point_proj_f32(const float* points, int64_t M, const float* W, const floa
 /* concat-and-divide used by MLPBlocks skip layers (implicit.py:179-180): y[r,:] = [a[r,:Ca], b[r,:Cb]] / s */
 int zs_concat2_f32(const float* a, int lda, int Ca, const float* b, int ldb, int Cb, float s, float* y, int ldy,
                    int64_t rows, void* stream);
-
-/* Fused tcgen05 decoder (the hot kernel).  See DESIGN.md "K1".  `packed` is produced by
- * zs_implicit_pack; `kv` by zs_implicit_latent_kv_pack.  Points are either streamed (points != NULL,
- * [B,P,3]) or generated in-kernel from the dense grid description (points == NULL). */
-typedef struct {
-  const float* point_proj_w;  /* [256,3]   */
-  const float* point_proj_b;  /* [256]     */
-  const float* norm1_w[2];    /* [256]     */
-  const float* norm1_b[2];
-  const float* qkv_w[2];      /* [768,256] */
-  const float* qkv_b[2];
-  const float* proj_w[2];     /* [256,256] */
-  const float* proj_b[2];
-  const float* norm2_w[2];
-  const float* norm2_b[2];
-  const float* fc1_w[2];      /* [1024,256] */
-  const float* fc1_b[2];
-  const float* fc2_w[2];      /* [256,1024] */
-  const float* fc2_b[2];
-  const float* norm_w;        /* final LayerNorm */
-  const float* norm_b;
-  const float* mlp_w[9];      /* impl_mlp.layers.{0..8}: [256,259],[256,256],[256,515],... ,[1,256] */
-  const float* mlp_b[9];
-} ZsImplicitWeights;
-
-size_t zs_implicit_packed_bytes(void);
-int zs_implicit_pack(const ZsImplicitWeights* w_host, void* packed, void* stream);
-/* per-image latent K/V of both blocks -> tensor-core operand images. k,v: [B,L,256] fp32 per block. */
-size_t zs_implicit_kv_bytes(int B, int L);
-int zs_implicit_kv_pack(const float* k0, const float* v0, const float* k1, const float* v1,
-                        int B, int L, void* kv, void* stream);
-/* precision: 0 = bf16x3 split (parity mode, ~fp32 accuracy), 1 = single-pass bf16 (fast mode). */
-int zs_implicit_fused_fwd(const void* packed, const void* kv, int L,
-                          const float* points, int B, int64_t P,
-                          int grid_n, float rmin, float rmax, int x0, int x1,
-                          float* logits, int apply_sigmoid, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Geometry glue (utils/camera.py:52-108, model/compute_graph/graph_shape.py:89-144, utils/util.py:336-345)

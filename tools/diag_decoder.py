@@ -30,7 +30,7 @@ net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_ml
 lat_in = torch.randn(1, 197, 256, device=dev)
 pts = (torch.rand(1, P, 3, device=dev) * 3 - 1.5).contiguous()
 FLOP = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
-        "chain_occ": 2 * 724224, "gemm_tc": 0, "point_proj": 2 * 768}
+        "chain_occ": 2 * 724224, "gemm_tc": 0, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
 with torch.no_grad():
     lat = net.prepare_latents(lat_in)
     if ONCE:
@@ -38,8 +38,10 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    for fused in (True, False, True):
-        net.lin_fused = fused
+    variants = [("qkv", 0), ("qkv", 1), ("qkv", 7), ("fused", 0), ("qkv", 1)]
+    for attention, flags in variants:
+        fused = True
+        net.attention, net.attn_flags = attention, flags
         for _ in range(3):
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
@@ -52,11 +54,11 @@ with torch.no_grad():
             e1.record()
         summ = t.summary()
         total = e0.elapsed_time(e1) / reps
-        log(f"\n== lin_fused={fused}: {P} points, pass {total:.3f} ms ({P / total / 1e3:.1f} Mpts/s; x{2146689 / P:.2f} = {total * 2146689 / P:.1f} ms per 129^3 shape)")
+        log(f"\n== attention={attention} flags={flags}: {P} points, pass {total:.3f} ms ({P / total / 1e3:.1f} Mpts/s; x{2146689 / P:.2f} = {total * 2146689 / P:.1f} ms per 129^3 shape)")
         for k, (c, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
             per = ms / c
             tf = FLOP.get(k, 0) * P / per / 1e9 if per > 0 else 0
-            log(f"   {k:18s} x{c // reps}  {per * 1e3:8.1f} us/launch  {ms / reps:7.3f} ms/pass  {100 * ms / reps / total:5.1f}%   {tf:7.1f} TFLOP/s algorithmic ({3 * tf:.0f} executed bf16x3)")
+            log(f"   {k:18s} x{c // reps}  {per * 1e3:8.1f} us/launch  {ms / reps:7.3f} ms/pass  {100 * ms / reps / total:5.1f}%   {tf:7.1f} TFLOP/s algorithmic ({3 * tf:.0f} executed at 3 passes)")
         with ops.OpTimer(clock_probe=True) as t:
             for _ in range(3):
                 net._points_chain(lat, pts, tc=True, sigmoid=True)

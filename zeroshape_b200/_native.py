@@ -13,20 +13,6 @@ LIB_PATH = os.environ.get("ZEROSHAPE_B200_LIB", os.path.join(_HERE, "libzeroshap
 P = c_void_p  # device pointer
 
 
-class ZsImplicitWeights(ctypes.Structure):
-    _fields_ = [
-        ("point_proj_w", P), ("point_proj_b", P),
-        ("norm1_w", P * 2), ("norm1_b", P * 2),
-        ("qkv_w", P * 2), ("qkv_b", P * 2),
-        ("proj_w", P * 2), ("proj_b", P * 2),
-        ("norm2_w", P * 2), ("norm2_b", P * 2),
-        ("fc1_w", P * 2), ("fc1_b", P * 2),
-        ("fc2_w", P * 2), ("fc2_b", P * 2),
-        ("norm_w", P), ("norm_b", P),
-        ("mlp_w", P * 9), ("mlp_b", P * 9),
-    ]
-
-
 # name -> (restype, argtypes); must list every symbol of include/zeroshape_b200.h
 SIGNATURES = {
     "zs_last_error": (c_char_p, []),
@@ -36,6 +22,9 @@ SIGNATURES = {
     "zs_gemm_f32": (c_int, [P, c_int, P, c_int, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_gemm_tc_packed_bytes": (c_size_t, [c_int, c_int]),
     "zs_gemm_tc_pack": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "zs_gemm_tc_pack_fmt": (c_int, [P, c_int, c_int, c_int, P, c_int, P]),
+    "zs_chain_qkvattn_blob_bytes": (c_size_t, []),
+    "zs_chain_qkvattn_fwd": (c_int, [P, c_int, c_int, c_float, P, P, P, P, c_int, c_float, P, c_int, c_int, c_int, P]),
     "zs_gemm_tc_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_attn_scores_tc": (c_int, [P, c_int, P, c_int, c_int, c_float, P, P, P, c_int, P]),
     "zs_attn_pv_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
@@ -100,12 +89,6 @@ SIGNATURES = {
                                        c_float, P]),
     "zs_dense_grid_f32": (c_int, [P, c_int, c_float, c_float, c_int, c_int, P]),
     "zs_concat2_f32": (c_int, [P, c_int, c_int, P, c_int, c_int, c_float, P, c_int, c_int64, P]),
-    "zs_implicit_packed_bytes": (c_size_t, []),
-    "zs_implicit_pack": (c_int, [ctypes.POINTER(ZsImplicitWeights), P, P]),
-    "zs_implicit_kv_bytes": (c_size_t, [c_int, c_int]),
-    "zs_implicit_kv_pack": (c_int, [P, P, P, P, c_int, c_int, P, P]),
-    "zs_implicit_fused_fwd": (c_int, [P, P, c_int, P, c_int, c_int64, c_int, c_float, c_float, c_int, c_int,
-                                      P, c_int, c_int, P]),
     "zs_intr_param2mtx_f32": (c_int, [P, P, c_int, c_int, c_int, P]),
     "zs_unproject_ws_bytes": (c_size_t, [c_int]),
     "zs_unproject_normalize_f32": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P, P]),

@@ -45,6 +45,8 @@ struct ChainParams {
   unsigned long long* trace;     // debug: per-role (tag, clock64) events of CTA 0 (nullptr in production)
   // chain_lin_kernel: out[M, 256*n_tiles] = LN?(x) W^T + bias (+ res)
   const float* res; int ldres; int ldo; int n_tiles; int do_ln;
+  // chain_qkvattn_kernel: latent key / value operand images of the image, softmax scale, per-GEMM pass policy
+  const uint8_t* kblob; const uint8_t* vblob; int n_keys; float scale; int flags;
 };
 
 struct Bars {
@@ -162,7 +164,7 @@ __device__ __forceinline__ uint32_t chain_setup(const Bars& B, uint8_t* smem_gen
 __device__ __forceinline__ void mma_chunk(const Bars& B, uint32_t smem_base, Ring& wr, uint32_t a_addr, uint32_t d_tmem,
                                           bool first, bool split, uint32_t a_empty_bar, unsigned long long* tr = nullptr,
                                           int* tn = nullptr) {
-  const uint32_t idesc = umma_idesc_bf16(128, 256);
+  const uint32_t idesc = umma_idesc_f16(128, 256);
   const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
   mbar_wait(B.wfull(wr.idx), wr.phase);
   if (tr) trace_ev(tr, 0, *tn, 3);
@@ -211,10 +213,10 @@ __device__ __forceinline__ void store_chunk_row(uint8_t* slot, int r, const floa
   for (int c = 0; c < 8; ++c) {
     const float4 x0 = buf[2 * c], x1 = buf[2 * c + 1];
     uint4 hi, lo;
-    split_bf16x2(x0.x, x0.y, hi.x, lo.x);
-    split_bf16x2(x0.z, x0.w, hi.y, lo.y);
-    split_bf16x2(x1.x, x1.y, hi.z, lo.z);
-    split_bf16x2(x1.z, x1.w, hi.w, lo.w);
+    split_f16x2(x0.x, x0.y, hi.x, lo.x);
+    split_f16x2(x0.z, x0.w, hi.y, lo.y);
+    split_f16x2(x1.x, x1.y, hi.z, lo.z);
+    split_f16x2(x1.z, x1.w, hi.w, lo.w);
     const uint32_t off = swizzle128_offset(r, c);
     *reinterpret_cast<uint4*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
@@ -319,8 +321,8 @@ __device__ __forceinline__ void store_chunk_co(uint8_t* slot, int w, int lane, c
       }
     }
     uint2 hi, lo;
-    split_bf16x2(v0.x, v0.y, hi.x, lo.x);
-    split_bf16x2(v1.x, v1.y, hi.y, lo.y);
+    split_f16x2(v0.x, v0.y, hi.x, lo.x);
+    split_f16x2(v1.x, v1.y, hi.y, lo.y);
     const uint32_t off = swizzle128_offset(32 * w + rl, q >> 1) + ((q & 1) << 3);
     *reinterpret_cast<uint2*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
@@ -343,10 +345,10 @@ __device__ __forceinline__ void epi_to_ring(uint8_t* slot, int row, int hsel, co
       v[j] = ACT == ZS_ACT_GELU ? fast_gelu_erf2(t) : fast_softplus100_2(t);
     }
     uint4 hi, lo;
-    split_bf16x2(v[0].x, v[0].y, hi.x, lo.x);
-    split_bf16x2(v[1].x, v[1].y, hi.y, lo.y);
-    split_bf16x2(v[2].x, v[2].y, hi.z, lo.z);
-    split_bf16x2(v[3].x, v[3].y, hi.w, lo.w);
+    split_f16x2(v[0].x, v[0].y, hi.x, lo.x);
+    split_f16x2(v[1].x, v[1].y, hi.y, lo.y);
+    split_f16x2(v[2].x, v[2].y, hi.z, lo.z);
+    split_f16x2(v[3].x, v[3].y, hi.w, lo.w);
     const uint32_t off = swizzle128_offset(row, hsel * 4 + c);
     *reinterpret_cast<uint4*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint4*>(slot + CT_A_HALF + off) = lo;
@@ -550,8 +552,8 @@ __device__ __forceinline__ void store_chunk16(uint8_t* slot, int w, int lane, co
       v0 = fma2(v0, bc2(s), bc2(h)); v1 = fma2(v1, bc2(s), bc2(h));
     }
     uint2 hi, lo;
-    split_bf16x2(v0.x, v0.y, hi.x, lo.x);
-    split_bf16x2(v1.x, v1.y, hi.y, lo.y);
+    split_f16x2(v0.x, v0.y, hi.x, lo.x);
+    split_f16x2(v1.x, v1.y, hi.y, lo.y);
     const uint32_t off = swizzle128_offset(16 * w + rl, q >> 1) + ((q & 1) << 3);
     *reinterpret_cast<uint2*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
@@ -895,7 +897,7 @@ __device__ __forceinline__ void attn_exp_block(const uint32_t* rr, int k0, int n
       float2 v = make_float2(fast_ex2(a.x), fast_ex2(a.y));
       if (!full) { if (k0 + i >= n_keys) v.x = 0.f; if (k0 + i + 1 >= n_keys) v.y = 0.f; }
       sum2 = add2(sum2, v);
-      split_bf16x2(v.x, v.y, hi[j], lo[j]);
+      split_f16x2(v.x, v.y, hi[j], lo[j]);
     }
     const uint32_t off = swizzle128_offset(row, c16_0 + cc);
     *reinterpret_cast<uint4*>(slot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -1020,7 +1022,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
     if (lane == 0) {
       Ring wr(AT_WSLOTS);
       uint32_t lph = 0, se_ph[2] = {0, 0}, oe_ph[2] = {0, 0}, ef_ph[2][2] = {{0, 0}, {0, 0}};
-      const uint32_t idesc_s = umma_idesc_bf16(128, 208), idesc_o = umma_idesc_bf16(128, 32);
+      const uint32_t idesc_s = umma_idesc_f16(128, 208), idesc_o = umma_idesc_f16(128, 32);
       const uint32_t d_s[2] = {tmem_base, tmem_base + 256}, d_o[2] = {tmem_base + 208, tmem_base + 464};
       const uint32_t a_addr = smem_base + AT_OFF_L;
       const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
@@ -1219,6 +1221,415 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ===============================================================================================================
+// LayerNorm + qkv + point->latent attention of one image in ONE kernel: norm1 of ImplFuncBlock and ImplFuncAttention
+// up to (not including) the output projection (model/shape/implicit.py:105, 30-57).  q, k, v of the query points, the
+// scores and the probabilities never leave the SM; HBM sees x (read) and the attention output O (written).
+//
+// Per 128-point tile the 8 heads run as 4 pairs.  Work item of the pipeline = one pair ("unit"):
+//   loaders (8 warps) : LN(x) -> split fp16 -> ring L, 4 K-chunks per unit (the qkv GEMM of a pair has N = 192:
+//                       [q of heads 2p, 2p+1 | k | v], weight tile rows in that order, norm1 affine folded at pack time);
+//   MMA               : acc[128 x 192] = LN(x) Wp^T for the NEXT unit while the current unit's attention runs;
+//                       per head S = Q_h K_h^T (N = 208) -> one S buffer, O_h = P_h V_h (N = 32) -> two O buffers;
+//   softmax warps (8) : thread = (row, half).  epi-1: half g drains q_g | k_g | v_g of head 2p+g from the accumulator:
+//                       q_g + b -> fp16 split -> its K-steps of the Q chunk, the point's own score q.k and value v stay
+//                       in registers.  Per head both halves share the keys (half 0: K-steps {0,1} of every 64-key
+//                       chunk, half 1: K-steps {2,3}): row max and row sum are exchanged through smem (named barriers),
+//                       probabilities go to the P slot in 32-key halves (pfull/pempty per half), and the half that owns
+//                       the head finishes (O + e_self v_self) / sum -> transpose through the idle P slot -> global.
+// TMEM: qkv accumulator [0,192), S [192,400), O of even heads [400,432), of odd heads [432,464).
+// flags: 1 = k, v columns single-pass (Ah Wh only), 2 = scores without Qh Kl, 4 = P V without Ph Vl
+//        (profiles/r2_precision_study.md; precision 1 = everything single-pass).
+constexpr int QA_THREADS = 576;                                 // warps 0-7 loaders, 8-15 softmax, 16 MMA, 17 W loader
+constexpr int QA_WSLOTS = 3;
+constexpr int QA_OFF_W = 0;                                     // 3 x 32 KB weight / key / value tiles
+constexpr int QA_OFF_L = QA_OFF_W + QA_WSLOTS * CT_TILE_BYTES;  //  96 KB: 2 x (hi 16K | lo 16K) LN(x) chunks
+constexpr int QA_OFF_Q = QA_OFF_L + 2 * 2 * CT_A_HALF;          // 160 KB: the unit's q chunk (hi | lo)
+constexpr int QA_OFF_P = QA_OFF_Q + 2 * CT_A_HALF;              // 192 KB: probability slot (hi | lo)
+constexpr int QA_OFF_BAR = QA_OFF_P + 2 * CT_A_HALF;            // 224 KB
+constexpr int QA_OFF_X = QA_OFF_BAR + 256;                      // [2 (max, sum)][2 halves][128 rows] fp32 = 2 KB
+static_assert(QA_OFF_BAR == CT_OFF_BAR && QA_OFF_X + 2048 <= CT_SMEM_USED, "qkv-attention smem layout");
+constexpr uint32_t QA_QKV_TILE_BYTES = 192 * 128;               // rows of a packed 256-row tile actually read (N = 192)
+constexpr uint32_t QA_Q_TILE_BYTES = 64 * 128;                  // ... when only the q rows take the pass (N = 64)
+constexpr uint32_t QA_K_TILE_BYTES = 208 * 128;
+
+struct QBars {
+  uint32_t base;
+  __device__ uint32_t wfull(int i) const { return base + 8u * i; }
+  __device__ uint32_t wempty(int i) const { return base + 24u + 8u * i; }
+  __device__ uint32_t lfull(int i) const { return base + 48u + 8u * i; }
+  __device__ uint32_t lempty(int i) const { return base + 64u + 8u * i; }
+  __device__ uint32_t accfull() const { return base + 80u; }
+  __device__ uint32_t accempty() const { return base + 88u; }
+  __device__ uint32_t qfull() const { return base + 96u; }
+  __device__ uint32_t qempty() const { return base + 104u; }
+  __device__ uint32_t sfull() const { return base + 112u; }
+  __device__ uint32_t sempty() const { return base + 120u; }
+  __device__ uint32_t pfull(int h) const { return base + 128u + 8u * h; }
+  __device__ uint32_t pempty(int h) const { return base + 144u + 8u * h; }
+  __device__ uint32_t ofull(int i) const { return base + 160u + 8u * i; }
+  __device__ uint32_t oempty(int i) const { return base + 176u + 8u * i; }
+  __device__ uint32_t tmem_slot() const { return base + 192u; }
+};
+
+__global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();   // dynamic smem base less aligned than budgeted
+  QBars B{smem_base + QA_OFF_BAR};
+  float* xbuf = reinterpret_cast<float*>(smem_gen + QA_OFF_X);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const bool kv1 = split && (p.flags & 1), s2 = split && (p.flags & 2), pv2 = split && (p.flags & 4);
+  const int n_tiles = (p.M + 127) / 128;
+  const int n_keys = p.n_keys;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < QA_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.lfull(i), 256); mbar_init(B.lempty(i), 1); }
+    mbar_init(B.accfull(), 1); mbar_init(B.accempty(), 256);
+    mbar_init(B.qfull(), 256); mbar_init(B.qempty(), 1);
+    mbar_init(B.sfull(), 1); mbar_init(B.sempty(), 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(B.pfull(i), 128); mbar_init(B.pempty(i), 1);
+      mbar_init(B.ofull(i), 1); mbar_init(B.oempty(i), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc(B.tmem_slot(), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
+
+  if (warp < 8) {
+    // ---------------- loaders: LN(x) chunks, 4 units x 4 K-chunks per tile (as chain_lin_kernel) ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");      // the 8 softmax warps take the registers (v_self stays live)
+    Ring lr(2);
+    float4 buf[8];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 16;
+      float sc = 1.f, sh = 0.f;
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      for (int i = 0; i < 16; ++i) {
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk16(smem_gen + QA_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (i + 1 < 16) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+      }
+    }
+  } else if (warp == 17) {
+    // ---------------- W loader: tiles in exactly the order the MMA thread consumes them ----------------
+    if (lane == 0) {
+      Ring wr(QA_WSLOTS);
+      auto put = [&](const uint8_t* src, uint32_t bytes) {
+        mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
+        mbar_arrive_expect_tx(B.wfull(wr.idx), bytes);
+        bulk_g2s(smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES, src, bytes, B.wfull(wr.idx));
+        wr.advance();
+      };
+      auto qkv_chunk = [&](int pr, int kc) {
+        const uint8_t* src = p.blob + ((size_t)pr * 4 + kc) * 2 * CT_TILE_BYTES;
+        put(src, QA_QKV_TILE_BYTES);
+        if (split) put(src + CT_TILE_BYTES, kv1 ? QA_Q_TILE_BYTES : QA_QKV_TILE_BYTES);
+      };
+      bool first = true;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int pr = 0; pr < 4; ++pr) {
+          if (first) { for (int kc = 0; kc < 4; ++kc) qkv_chunk(0, kc); first = false; }
+          const bool has_next = pr < 3 || t + (int)gridDim.x < n_tiles;
+          const int pn = (pr + 1) & 3;
+          for (int g = 0; g < 2; ++g) {
+            put(p.kblob + (size_t)pr * 2 * CT_TILE_BYTES, QA_K_TILE_BYTES);
+            if (split && !s2) put(p.kblob + (size_t)pr * 2 * CT_TILE_BYTES + CT_TILE_BYTES, QA_K_TILE_BYTES);
+            if (has_next) { qkv_chunk(pn, 2 * g); qkv_chunk(pn, 2 * g + 1); }
+            put(p.vblob + (size_t)(2 * pr + g) * CT_TILE_BYTES, CT_TILE_BYTES);
+          }
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(QA_WSLOTS), lr(2);
+      uint32_t ph_accempty = 0, ph_qfull = 0, ph_sempty = 0, ph_pfull = 0, ph_oempty = 0;   // the last two: bit i = phase of barrier i
+      const uint32_t idesc_qkv = umma_idesc_f16(128, 192), idesc_q2 = kv1 ? umma_idesc_f16(128, 64) : idesc_qkv;
+      const uint32_t idesc_s = umma_idesc_f16(128, 208), idesc_o = umma_idesc_f16(128, 32);
+      const uint32_t d_acc = tmem_base, d_s = tmem_base + 192;
+      const uint64_t q_hi = umma_desc_sw128(smem_base + QA_OFF_Q), q_lo = umma_desc_sw128(smem_base + QA_OFF_Q + CT_A_HALF);
+      const uint64_t e_hi = umma_desc_sw128(smem_base + QA_OFF_P), e_lo = umma_desc_sw128(smem_base + QA_OFF_P + CT_A_HALF);
+      auto qkv_chunk = [&](int kc) {
+        mbar_wait(B.lfull(lr.idx), lr.phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + QA_OFF_L + lr.idx * 2 * CT_A_HALF;
+        const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+        mbar_wait(B.wfull(wr.idx), wr.phase);
+        tc_fence_after();
+        {
+          const uint64_t w = umma_desc_sw128(smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_acc, a_hi + 2 * k, w + 2 * k, idesc_qkv, (kc > 0 || k > 0) ? 1u : 0u);
+            if (split) umma_bf16(d_acc, a_lo + 2 * k, w + 2 * k, idesc_q2, 1u);
+          }
+          umma_commit(B.wempty(wr.idx));
+          wr.advance();
+        }
+        if (split) {
+          mbar_wait(B.wfull(wr.idx), wr.phase);
+          tc_fence_after();
+          const uint64_t w = umma_desc_sw128(smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_acc, a_hi + 2 * k, w + 2 * k, idesc_q2, 1u);
+          umma_commit(B.wempty(wr.idx));
+          wr.advance();
+        }
+        umma_commit(B.lempty(lr.idx));
+        lr.advance();
+      };
+      // the first unit's qkv GEMM; afterwards unit u+1's runs inside unit u
+      mbar_wait(B.accempty(), ph_accempty ^ 1); ph_accempty ^= 1;
+      tc_fence_after();
+      for (int kc = 0; kc < 4; ++kc) qkv_chunk(kc);
+      umma_commit(B.accfull());
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int pr = 0; pr < 4; ++pr) {
+          const bool has_next = pr < 3 || t + (int)gridDim.x < n_tiles;
+          mbar_wait(B.qfull(), ph_qfull); ph_qfull ^= 1;
+          tc_fence_after();
+          for (int g = 0; g < 2; ++g) {
+            // ---- S = Q_h K_h^T: head g of the pair = K-steps 2g, 2g+1 of the q chunk and of the K pair tile ----
+            mbar_wait(B.sempty(), ph_sempty ^ 1); ph_sempty ^= 1;
+            tc_fence_after();
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            tc_fence_after();
+            {
+              const uint64_t w = umma_desc_sw128(smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int kk = 2 * g + k;
+                umma_bf16(d_s, q_hi + 2 * kk, w + 2 * kk, idesc_s, k > 0 ? 1u : 0u);
+                if (split) umma_bf16(d_s, q_lo + 2 * kk, w + 2 * kk, idesc_s, 1u);
+              }
+              umma_commit(B.wempty(wr.idx));
+              wr.advance();
+            }
+            if (split && !s2) {
+              mbar_wait(B.wfull(wr.idx), wr.phase);
+              tc_fence_after();
+              const uint64_t w = umma_desc_sw128(smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) umma_bf16(d_s, q_hi + 2 * (2 * g + k), w + 2 * (2 * g + k), idesc_s, 1u);
+              umma_commit(B.wempty(wr.idx));
+              wr.advance();
+            }
+            umma_commit(B.sfull());
+            if (g == 1) umma_commit(B.qempty());
+            // ---- the next unit's qkv GEMM, two K-chunks per head: fills the tensor pipe while the softmax runs ----
+            if (has_next) {
+              if (g == 0) { mbar_wait(B.accempty(), ph_accempty ^ 1); ph_accempty ^= 1; tc_fence_after(); }
+              qkv_chunk(2 * g);
+              qkv_chunk(2 * g + 1);
+              if (g == 1) umma_commit(B.accfull());
+            }
+            // ---- O_h = P_h V_h: 32-key halves from the P slot ----
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            const int v_slot = wr.idx;
+            const uint32_t v_addr = smem_base + QA_OFF_W + wr.idx * CT_TILE_BYTES;
+            wr.advance();
+            mbar_wait(B.oempty(g), ((ph_oempty >> g) & 1u) ^ 1u); ph_oempty ^= 1u << g;
+            tc_fence_after();
+            const uint32_t d_o = tmem_base + 400u + 32u * g;
+            for (int c = 0; c < 4; ++c) {
+              const int nh = c == 3 ? 1 : 2;        // keys 192..207 are one K-step (half 0 only); 208.. do not exist
+              for (int hh = 0; hh < nh; ++hh) {
+                mbar_wait(B.pfull(hh), (ph_pfull >> hh) & 1u); ph_pfull ^= 1u << hh;
+                tc_fence_after();
+                const uint64_t v_hi = umma_desc_sw128(v_addr + c * 8192), v_lo = umma_desc_sw128(v_addr + c * 8192 + 4096);
+                const int k0 = 2 * hh, k1 = c == 3 ? 1 : 2 * hh + 2;
+                for (int k = k0; k < k1; ++k) {
+                  umma_bf16(d_o, e_hi + 2 * k, v_hi + 2 * k, idesc_o, (c > 0 || k > 0) ? 1u : 0u);
+                  if (split) {
+                    umma_bf16(d_o, e_lo + 2 * k, v_hi + 2 * k, idesc_o, 1u);
+                    if (!pv2) umma_bf16(d_o, e_hi + 2 * k, v_lo + 2 * k, idesc_o, 1u);
+                  }
+                }
+                umma_commit(B.pempty(hh));
+              }
+            }
+            umma_commit(B.ofull(g));
+            umma_commit(B.wempty(v_slot));
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax / epilogue warps: thread = (query row, half) ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    const int e = warp - 8, wq = e & 3, half = e >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t acc_tm = tmem_base + lane_off, s_tm = acc_tm + 192u, o_tm = acc_tm + 400u + 32u * half;
+    uint8_t* qslot = smem_gen + QA_OFF_Q;
+    uint8_t* pslot = smem_gen + QA_OFF_P;
+    uint8_t* wscr = pslot + wq * 4096;            // transpose scratch of the finishing half: the P slot is idle then (see below)
+    uint32_t ph_accfull = 0, ph_qempty = 0, ph_sfull = 0, ph_pempty = 0, ph_ofull = 0;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int q8 = lane & 7;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int pr = 0; pr < 4; ++pr) {
+        // ---- epi-1: this half's head of the pair out of the qkv accumulator ----
+        const int hm = 2 * pr + half;
+        float v[32];
+        float s_self;
+        mbar_wait(B.accfull(), ph_accfull); ph_accfull ^= 1;
+        tc_fence_after();
+        {
+          uint32_t rq[32], rk[32];
+          tmem_ld_32x32(acc_tm + 32u * half, rq);
+          tmem_ld_32x32(acc_tm + 64u + 32u * half, rk);
+          tmem_ld_wait();
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + hm * 32);
+          const float4* bk = reinterpret_cast<const float4*>(p.bias + 256 + hm * 32);
+          float2 d2 = make_float2(0.f, 0.f);
+          mbar_wait(B.qempty(), ph_qempty ^ 1); ph_qempty ^= 1;     // the previous unit's score MMAs have read the q chunk
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 b4 = __ldg(bq + 2 * c + j), k4 = __ldg(bk + 2 * c + j);
+              const int i = 8 * c + 4 * j;
+              const float2 qa = add2(make_float2(__uint_as_float(rq[i]), __uint_as_float(rq[i + 1])), make_float2(b4.x, b4.y));
+              const float2 qb = add2(make_float2(__uint_as_float(rq[i + 2]), __uint_as_float(rq[i + 3])), make_float2(b4.z, b4.w));
+              const float2 ka = add2(make_float2(__uint_as_float(rk[i]), __uint_as_float(rk[i + 1])), make_float2(k4.x, k4.y));
+              const float2 kb = add2(make_float2(__uint_as_float(rk[i + 2]), __uint_as_float(rk[i + 3])), make_float2(k4.z, k4.w));
+              d2 = fma2(qa, ka, d2);
+              d2 = fma2(qb, kb, d2);
+              split_f16x2(qa.x, qa.y, hi[2 * j], lo[2 * j]);
+              split_f16x2(qb.x, qb.y, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            const uint32_t off = swizzle128_offset(row, 4 * half + c);
+            *reinterpret_cast<uint4*>(qslot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (split) *reinterpret_cast<uint4*>(qslot + CT_A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          s_self = d2.x + d2.y;
+          fence_proxy_async_smem();
+          mbar_arrive(B.qfull());
+        }
+        {
+          uint32_t rv[32];
+          tmem_ld_32x32(acc_tm + 128u + 32u * half, rv);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(B.accempty());
+          const float4* bv = reinterpret_cast<const float4*>(p.bias + 512 + hm * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bv + j);
+            v[4 * j] = __uint_as_float(rv[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(rv[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(rv[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(rv[4 * j + 3]) + b4.w;
+          }
+        }
+        // ---- the two heads of the pair, one after the other (one S buffer); both halves share each head's keys ----
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          const int h = 2 * pr + hs;
+          const bool mine = hs == half;
+          mbar_wait(B.sfull(), ph_sfull); ph_sfull ^= 1;
+          tc_fence_after();
+          // pass 1: max over this half's keys (and the point's own key for the owner)
+          float mx = mine ? s_self : -3.0e38f;
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(s_tm + c * 64 + 32 * half, rr);
+            tmem_ld_wait();
+            mx = attn_max_block<32>(rr, c * 64 + 32 * half, n_keys, mx);
+          }
+          if (half == 0) {
+            uint32_t rr[16];
+            tmem_ld_32x16(s_tm + 192, rr);
+            tmem_ld_wait();
+            mx = attn_max_block<16>(rr, 192, n_keys, mx);
+          }
+          xbuf[half * 128 + row] = mx;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mx = fmaxf(mx, xbuf[(half ^ 1) * 128 + row]);
+          const float mxs = mx * sl2;
+          // pass 2: e_j -> the P slot, 32 keys per piece (half 0: 4 pieces, the last one 16 keys; half 1: 3 pieces)
+          float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(s_tm + c * 64 + 32 * half, rr);
+            tmem_ld_wait();
+            mbar_wait(B.pempty(half), ph_pempty ^ 1); ph_pempty ^= 1;
+            attn_exp_block<16>(rr, c * 64 + 32 * half, n_keys, sl2, mxs, sum2, pslot, row, 4 * half, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.pfull(half));
+          }
+          if (half == 0) {
+            uint32_t rr[16];
+            tmem_ld_32x16(s_tm + 192, rr);
+            tmem_ld_wait();
+            mbar_wait(B.pempty(0), ph_pempty ^ 1); ph_pempty ^= 1;
+            attn_exp_block<8>(rr, 192, n_keys, sl2, mxs, sum2, pslot, row, 0, split);
+            fence_proxy_async_smem();
+            mbar_arrive(B.pfull(0));
+          }
+          tc_fence_before();
+          mbar_arrive(B.sempty());
+          float sum = sum2.x + sum2.y, e_self = 0.f;
+          if (mine) { e_self = fast_ex2(fmaf(s_self, sl2, -mxs)); sum += e_self; }
+          xbuf[256 + half * 128 + row] = sum;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (mine) {
+            // this half owns head h: (O_h + e_self v_self) / sum.  The other half moves on to the next head, but writes the
+            // P slot only after named barrier 1 of that head, which this half joins after the stores below; every P V MMA of
+            // head h has completed (ofull): the slot is idle and serves as the transpose scratch.
+            const float inv = 1.0f / (sum + xbuf[256 + (half ^ 1) * 128 + row]);
+            mbar_wait(B.ofull(half), ph_ofull); ph_ofull ^= 1;
+            tc_fence_after();
+            {
+              uint32_t rr[32];
+              tmem_ld_32x32(o_tm, rr);
+              tmem_ld_wait();
+              tc_fence_before();
+              mbar_arrive(B.oempty(half));
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_float4(fmaf(e_self, v[4 * j], __uint_as_float(rr[4 * j])) * inv,
+                                fmaf(e_self, v[4 * j + 1], __uint_as_float(rr[4 * j + 1])) * inv,
+                                fmaf(e_self, v[4 * j + 2], __uint_as_float(rr[4 * j + 2])) * inv,
+                                fmaf(e_self, v[4 * j + 3], __uint_as_float(rr[4 * j + 3])) * inv);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = 4 * i + (lane >> 3);
+              const int mm = t * 128 + wq * 32 + rl;
+              const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+              if (mm < p.M) *(reinterpret_cast<float4*>(p.out + (int64_t)mm * p.ldo + h * 32) + q8) = a;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
 
 static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name, int threads = CT_THREADS) {
@@ -1300,4 +1711,25 @@ extern "C" int zs_chain_occ_fwd(const float* x, int ldx, const float* points, in
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = biases; p.bias2 = w8; p.b8 = b8; p.out = out;
   p.apply_sigmoid = apply_sigmoid; p.precision = precision;
   return chain_launch(chain_occ_kernel, p, as_stream(stream), "zs_chain_occ_fwd");
+}
+
+extern "C" size_t zs_chain_qkvattn_blob_bytes(void) { return (size_t)4 * 4 * 2 * CT_TILE_BYTES; }
+
+extern "C" int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const void* Wblob, const float* bias_qkv,
+                                    const void* Kblob, const void* Vblob, int n_keys, float scale, float* O, int ldo,
+                                    int precision, int flags, void* stream) {
+  ZS_REQUIRE(x && Wblob && bias_qkv && Kblob && Vblob && O && M >= 0, "zs_chain_qkvattn_fwd: null pointer");
+  ZS_REQUIRE(n_keys > 0 && n_keys <= 208, "zs_chain_qkvattn_fwd: n_keys must be in [1, 208]");
+  ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_qkvattn_fwd: x must be 16B aligned, ldx%%4==0");
+  ZS_REQUIRE(ldo >= 256 && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0, "zs_chain_qkvattn_fwd: O must be 16B aligned, ldo%%4==0");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(Kblob) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(Vblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias_qkv) & 15) == 0,
+             "zs_chain_qkvattn_fwd: blobs / bias must be 16-byte aligned");
+  ZS_REQUIRE((precision == 0 || precision == 1) && flags >= 0 && flags < 8, "zs_chain_qkvattn_fwd: bad precision / flags");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.blob = reinterpret_cast<const uint8_t*>(Wblob);
+  p.bias = bias_qkv; p.kblob = reinterpret_cast<const uint8_t*>(Kblob); p.vblob = reinterpret_cast<const uint8_t*>(Vblob);
+  p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = ldo; p.precision = precision; p.flags = flags;
+  return chain_launch(chain_qkvattn_kernel, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA_THREADS);
 }

@@ -496,8 +496,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 }
 
 // ---- weight packing: fp32 W[N,K] -> per (n_tile, k_chunk) [hi | lo] swizzled bf16 tiles --------------
+// fmt 0: bf16 (gemm_tc / encoder / training kernels), 1: fp16 (decoder chain kernels, csrc/chain_tc.cu)
 __global__ void gemm_tc_pack_kernel(const float* __restrict__ W, int ldw, int N, int K, uint8_t* __restrict__ out,
-                                    int n_tiles, int k_chunks) {
+                                    int n_tiles, int k_chunks, int fmt) {
   // one thread per (tile row, 16-byte chunk)
   int64_t total = (int64_t)n_tiles * k_chunks * TC_BN * 8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -511,10 +512,17 @@ __global__ void gemm_tc_pack_kernel(const float* __restrict__ W, int ldw, int N,
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = (n < N && k + e < K) ? W[(int64_t)n * ldw + k + e] : 0.f;
     uint4 hi, lo;
-    tc::split_bf16x2(v[0], v[1], hi.x, lo.x);
-    tc::split_bf16x2(v[2], v[3], hi.y, lo.y);
-    tc::split_bf16x2(v[4], v[5], hi.z, lo.z);
-    tc::split_bf16x2(v[6], v[7], hi.w, lo.w);
+    if (fmt == 1) {
+      tc::split_f16x2(v[0], v[1], hi.x, lo.x);
+      tc::split_f16x2(v[2], v[3], hi.y, lo.y);
+      tc::split_f16x2(v[4], v[5], hi.z, lo.z);
+      tc::split_f16x2(v[6], v[7], hi.w, lo.w);
+    } else {
+      tc::split_bf16x2(v[0], v[1], hi.x, lo.x);
+      tc::split_bf16x2(v[2], v[3], hi.y, lo.y);
+      tc::split_bf16x2(v[4], v[5], hi.z, lo.z);
+      tc::split_bf16x2(v[6], v[7], hi.w, lo.w);
+    }
     uint8_t* tile = out + ((size_t)nt * k_chunks + kc) * (2u * TC_B_TILE);
     uint32_t off = tc::swizzle128_offset(r, c);
     *reinterpret_cast<uint4*>(tile + off) = hi;
@@ -543,13 +551,17 @@ extern "C" size_t zs_gemm_tc_packed_bytes(int N, int K) {
 }
 
 extern "C" int zs_gemm_tc_pack(const float* W, int ldw, int N, int K, void* packed, void* stream) {
-  ZS_REQUIRE(W && packed && N > 0 && K > 0 && ldw >= K, "zs_gemm_tc_pack: bad args");
+  return zs_gemm_tc_pack_fmt(W, ldw, N, K, packed, 0, stream);
+}
+
+extern "C" int zs_gemm_tc_pack_fmt(const float* W, int ldw, int N, int K, void* packed, int fmt, void* stream) {
+  ZS_REQUIRE(W && packed && N > 0 && K > 0 && ldw >= K && (fmt == 0 || fmt == 1), "zs_gemm_tc_pack: bad args");
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "zs_gemm_tc_pack: packed buffer must be 16-byte aligned");
   int nt = (N + TC_BN - 1) / TC_BN, kc = (K + TC_BK - 1) / TC_BK;
   int64_t total = (int64_t)nt * kc * TC_BN * 8;
   int grid = (int)((total + 255) / 256);
   if (grid > 4096) grid = 4096;
-  gemm_tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, ldw, N, K, reinterpret_cast<uint8_t*>(packed), nt, kc);
+  gemm_tc_pack_kernel<<<grid, 256, 0, as_stream(stream)>>>(W, ldw, N, K, reinterpret_cast<uint8_t*>(packed), nt, kc, fmt);
   ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_pack");
   return ZS_OK;
 }

@@ -3,6 +3,7 @@
 // No CUTLASS dependency; bit layouts follow the PTX ISA (cross-checked against cute/arch/mma_sm100_desc.hpp).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace zs {
@@ -106,6 +107,10 @@ __device__ __forceinline__ uint32_t swizzle128_offset(uint32_t row, uint32_t chu
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// same with A = B = fp16 (format code 0): 11-bit significands, so the hi/lo split carries 22 bits (fp32-grade products)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -182,6 +187,23 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   const float2 r = sub2(make_float2(a, b), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));
   const __nv_bfloat162 l = __floats2bfloat162_rn(r.x, r.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ---- fp16 hi/lo split (decoder chain kernels) ----------------------------------------------------
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significand bits (lo is exact up to fp16's subnormal quantum
+// 2^-24); hi*hi + lo*hi + hi*lo reproduces the fp32 product to ~2^-22 relative, 8x tighter than the bf16 split
+// (profiles/r2_precision_study.md).  Conversions saturate at +-65504 instead of producing infinities; operands of the
+// decoder (LayerNorm outputs, GELU / Softplus activations, probabilities, LayerNorm-folded weights) are far inside.
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {   // .x (low 16 bits) = fp16(a), high = fp16(b)
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(a, b);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 r = sub2(make_float2(a, b), h);
+  lo = cvt_f16x2_sat(r.x, r.y);
 }
 
 }  // namespace tc

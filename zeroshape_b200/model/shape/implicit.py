@@ -9,8 +9,9 @@ B200-first restructuring (results identical to the reference's):
     latent side -- latent_proj, +pos_embed, block-0 self-attention/MLP over the 197 latents and the
     K/V of both blocks -- is computed ONCE per image (`prepare_latents`) instead of once per grid
     slice (utils/eval_3D.py:37-43 calls the whole module 129 times);
-  * the query-point side runs either through the fused tcgen05 kernel (`engine="fused"`) or through
-    the chain of plain-fp32 kernels (`engine="f32"`, the bit-faithful path used for parity pinning);
+  * the query-point side runs through the chained tcgen05 kernels of csrc/chain_tc.cu (`engine="auto"`: per block one
+    LayerNorm + qkv + attention kernel, proj + residual, the fused MLP; then the fused occupancy MLP) or through the chain
+    of plain-fp32 kernels (`engine="f32"`, the bit-faithful path used for parity pinning);
   * `grid_occupancy` generates the (N+1)^3 query points on the fly (no [B,N,N,N,3] tensor).
 
 Training (decoder slice): when autograd is enabled and a decoder parameter or the
@@ -25,7 +26,6 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ..._native import lib, check, ZsImplicitWeights
 
 SQRT2 = float(np.sqrt(2))
 
@@ -88,16 +88,18 @@ class Implicit(nn.Module):
         self.impl_mlp = _Holder()
         self.impl_mlp.layers = nn.ModuleList([
             nn.Linear(dims[l] + (dims[0] if l in self.skip_in else 0), dims[l + 1]) for l in range(len(dims) - 1)])
-        self.engine = "auto"          # "auto" | "fused" | "tc" | "f32"
-        self.precision = "bf16x3"     # tensor-core operand precision: "bf16x3" (parity) | "bf16" (fast)
-        self.attention = "fused"      # point attention: "fused" (one flash-style tcgen05 kernel) | "tc" (two grouped tcgen05 launches) | "f32" (FFMA kernel)
+        self.engine = "auto"          # "auto" / "chain" (chained tcgen05 kernels) | "tc" (per-layer tcgen05 GEMMs) | "f32" (FFMA, bit-faithful)
+        self.precision = "fp16x3"     # tensor-core operand precision of the chain kernels: "fp16x3" (parity) | "fp16" (one pass)
+        # point attention: "qkv" (LayerNorm + qkv + flash-style attention in ONE tcgen05 kernel, q/k/v never reach HBM) |
+        # "fused" (qkv by zs_chain_lin_fwd, then one flash-style attention kernel) | "tc" (two grouped launches) | "f32" (FFMA)
+        self.attention = "qkv"
+        self.attn_flags = 1           # zs_chain_qkvattn_fwd pass policy (profiles/r2_precision_study.md): 1 = k, v single-pass
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         # query points per pass of the per-layer / chained engines (bounds scratch memory: ~5 KB per point).  One pass over a whole
         # 129^3 grid (2.15 M points, 11 GB) instead of 9 slice-aligned passes: persistent kernels lose the partial last wave and the
         # pipeline fill/drain once per LAUNCH (1950 tiles = 13.2 waves per pass cost 14; a single pass of 16771 tiles = 113.3 costs 114)
         self.point_chunk = 1 << 22
-        self._packed = None           # (version key, packed weight blob) for the fused engine
         self.initialize_weights()
 
     # -- init (reference: implicit.py:235-249) ---------------------------------------------------
@@ -131,7 +133,9 @@ class Implicit(nn.Module):
     def prepare_latents(self, latent_depth):
         """Per-image latent-side work -> dict with K/V views of both blocks ([B,L,C], row stride 3C)."""
         C = self.n_channels
-        tc = self._use_tc()          # engine "f32" keeps the latent side on the bit-faithful FFMA kernels too
+        # the latent side is a per-image constant (0.02 % of the work): only the per-layer "tc" engine runs it on the tensor
+        # cores; the chained engine keeps it on the bit-faithful FFMA kernels so that K / V carry no split-precision error
+        tc = self._use_tc() and self.engine == "tc"
         lat = ops.linear(latent_depth.float().contiguous(), self.latent_proj.weight, self.latent_proj.bias, tc=tc)
         kv = []
         nb = len(self.blocks_attn)
@@ -173,9 +177,11 @@ class Implicit(nn.Module):
             for blk in self.blocks_attn:
                 wq = blk.attn.qkv.weight.detach().double()
                 g1, be1 = blk.norm1.weight.detach().double(), blk.norm1.bias.detach().double()
-                lin_blobs.append((ops.pack_generic((wq * g1[None, :]).float()),
+                wq_f = (wq * g1[None, :]).float()
+                lin_blobs.append((ops.pack_generic(wq_f),
                             (blk.attn.qkv.bias.detach().double() + wq @ be1).float().contiguous(),
-                            ops.pack_generic(blk.attn.proj.weight.detach().float())))
+                            ops.pack_generic(blk.attn.proj.weight.detach().float()),
+                            ops.qkvattn_pack(wq_f)))
             for blk in self.blocks_attn:
                 w1, w2 = blk.mlp.fc1.weight.detach().double(), blk.mlp.fc2.weight.detach()
                 g2, be2 = blk.norm2.weight.detach().double(), blk.norm2.bias.detach().double()
@@ -216,11 +222,24 @@ class Implicit(nn.Module):
             x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
             k_lat, v_lat = lat["kv"][l]
+            if chain and attn_out is None and self.attention == "qkv" and self.lin_fused:
+                # LayerNorm + qkv + attention of a tile in one kernel; then x += proj(a) and the MLP as below
+                packs = lat.setdefault("kv_fused", {})
+                a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
+                for b in range(B):
+                    if (l, b) not in packs:
+                        packs[(l, b)] = ops.attn_pack_fused(k_lat[b], v_lat[b], self.num_heads)
+                    ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
+                                      lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
+                                      flags=self.attn_flags, out=a[b * P:(b + 1) * P])
+                ops.chain_lin(a, lin_blobs[l][2], blk.attn.proj.bias, 1, res=x, out=x, precision=self.precision)   # x += proj(a)
+                ops.chain_mlp(x, None, None, blk.norm2.eps, mlp_blobs[l], mlp_b1[l], blk.mlp.fc2.bias, self.precision)
+                continue
             if chain and self.lin_fused:    # LayerNorm statistics + qkv GEMM in one launch (norm1 affine folded into the packed weights)
                 qkv = ops.chain_lin(x, lin_blobs[l][0], lin_blobs[l][1], 3, do_ln=True, ln_eps=blk.norm1.eps, precision=self.precision)
             else:
                 qkv = self._lin(self._ln(x, blk.norm1), blk.attn.qkv, tc)
-            if chain and attn_out is None and self.attention == "fused":
+            if chain and attn_out is None and self.attention in ("fused", "qkv"):
                 # flash-style tensor-core attention: scores, softmax and P.V of a tile never leave the SM
                 packs = lat.setdefault("kv_fused", {})
                 a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
@@ -267,8 +286,13 @@ class Implicit(nn.Module):
             h = self._lin(h, lin, tc, act=ops.ACT_SOFTPLUS100 if l < n_layers - 1 else ops.ACT_NONE)
         return h.reshape(B, P)
 
-    def _points_f32(self, lat, pts, attn_out=None):
-        return self._points_chain(lat, pts, attn_out, tc=self._use_tc())
+    def _points_f32(self, lat, pts, attn_out=None, sigmoid=False):
+        """Logits [B,P] of a chunk of points; with `sigmoid` the occupancy of compute_level_grid (eval_3D.py:46): fused into
+        the occupancy-MLP kernel's epilogue on the chained engine, one elementwise launch otherwise."""
+        tc = self._use_tc()
+        if sigmoid and not (tc and attn_out is None and self.engine != "tc" and self._chain_ok()):
+            return ops.axpby(self._points_chain(lat, pts, attn_out, tc=tc), 1.0, act=ops.ACT_SIGMOID)
+        return self._points_chain(lat, pts, attn_out, tc=tc, sigmoid=sigmoid)
 
     def _use_tc(self):
         if self.engine == "f32":
@@ -276,72 +300,6 @@ class Implicit(nn.Module):
         ok = ops.device_cc() == 100
         if self.engine == "tc" and not ok:
             raise RuntimeError("engine='tc' needs an sm_100 device")
-        return ok
-
-    # -- fused engine ------------------------------------------------------------------------------
-    def fused_available(self):
-        return lib.zs_implicit_packed_bytes() > 0 and self.n_channels == 256 and self.num_heads == 8 \
-            and len(self.blocks_attn) == 2 and len(self.impl_mlp.layers) == 9 and self.skip_in == [2, 4, 6] \
-            and not self.pos_perlayer
-
-    def _weights_struct(self):
-        w = ZsImplicitWeights()
-        keep = []
-
-        def ptr(t):
-            t = t.detach().float().contiguous()
-            keep.append(t)
-            return t.data_ptr()
-        w.point_proj_w, w.point_proj_b = ptr(self.point_proj.proj.weight), ptr(self.point_proj.proj.bias)
-        for l, blk in enumerate(self.blocks_attn):
-            w.norm1_w[l], w.norm1_b[l] = ptr(blk.norm1.weight), ptr(blk.norm1.bias)
-            w.qkv_w[l], w.qkv_b[l] = ptr(blk.attn.qkv.weight), ptr(blk.attn.qkv.bias)
-            w.proj_w[l], w.proj_b[l] = ptr(blk.attn.proj.weight), ptr(blk.attn.proj.bias)
-            w.norm2_w[l], w.norm2_b[l] = ptr(blk.norm2.weight), ptr(blk.norm2.bias)
-            w.fc1_w[l], w.fc1_b[l] = ptr(blk.mlp.fc1.weight), ptr(blk.mlp.fc1.bias)
-            w.fc2_w[l], w.fc2_b[l] = ptr(blk.mlp.fc2.weight), ptr(blk.mlp.fc2.bias)
-        w.norm_w, w.norm_b = ptr(self.norm.weight), ptr(self.norm.bias)
-        for l, lin in enumerate(self.impl_mlp.layers):
-            w.mlp_w[l], w.mlp_b[l] = ptr(lin.weight), ptr(lin.bias)
-        return w, keep
-
-    def _packed_weights(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._packed is None or self._packed[0] != key:
-            dev = self.latent_proj.weight.device
-            blob = torch.empty(lib.zs_implicit_packed_bytes(), device=dev, dtype=torch.uint8)
-            w, keep = self._weights_struct()
-            check(lib.zs_implicit_pack(w, blob.data_ptr(), torch.cuda.current_stream().cuda_stream), "zs_implicit_pack")
-            self._packed = (key, blob)
-        return self._packed[1]
-
-    def _kv_packed(self, lat):
-        if "kv_packed" not in lat:
-            (k0, v0), (k1, v1) = lat["kv"]
-            B, L = lat["B"], lat["L"]
-            buf = torch.empty(lib.zs_implicit_kv_bytes(B, L), device=k0.device, dtype=torch.uint8)
-            c = [t.contiguous() for t in (k0, v0, k1, v1)]
-            check(lib.zs_implicit_kv_pack(c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(), c[3].data_ptr(), B, L,
-                                          buf.data_ptr(), torch.cuda.current_stream().cuda_stream), "zs_implicit_kv_pack")
-            lat["kv_packed"] = buf
-        return lat["kv_packed"]
-
-    def _fused(self, lat, pts, B, P, grid=None, sigmoid=False):
-        out = torch.empty(B, P, device=self.latent_proj.weight.device, dtype=torch.float32)
-        n, rmin, rmax, x0, x1 = grid if grid is not None else (0, 0.0, 0.0, 0, 0)
-        prec = {"bf16x3": 0, "bf16": 1}[self.precision]
-        check(lib.zs_implicit_fused_fwd(self._packed_weights().data_ptr(), self._kv_packed(lat).data_ptr(), lat["L"],
-                                        None if pts is None else pts.data_ptr(), B, P, n, rmin, rmax, x0, x1,
-                                        out.data_ptr(), int(sigmoid), prec, torch.cuda.current_stream().cuda_stream),
-              "zs_implicit_fused_fwd")
-        return out
-
-    def _use_fused(self):
-        if self.engine in ("f32", "tc"):
-            return False
-        ok = self.fused_available()
-        if self.engine == "fused" and not ok:
-            raise RuntimeError("engine='fused' requested but the fused kernel does not support this configuration")
         return ok
 
     # -- public API --------------------------------------------------------------------------------
@@ -359,8 +317,6 @@ class Implicit(nn.Module):
             lat = self.prepare_latents(latent_depth)
             L = lat["L"]
             attn = torch.empty(B, P, L, device=pts.device, dtype=torch.float32) if need_attn else None
-            if self._use_fused() and not need_attn:
-                return self._fused(lat, pts, B, P), None
             logits = torch.empty(B, P, device=pts.device, dtype=torch.float32)
             for s in range(0, P, self.point_chunk):
                 e = min(P, s + self.point_chunk)
@@ -369,8 +325,6 @@ class Implicit(nn.Module):
                 logits[:, s:e] = self._points_f32(lat, pc, ac)
                 if need_attn:
                     attn[:, s:e] = ac
-            if self._use_fused():   # attention map from the f32 chain, logits from the hot kernel
-                logits = self._fused(lat, pts, B, P)
             return logits, attn
 
     @torch.no_grad()
@@ -380,14 +334,10 @@ class Implicit(nn.Module):
         x1 = n if x1 is None else x1
         lat = lat if lat is not None else self.prepare_latents(latent_depth)
         B = lat["B"]
-        if self._use_fused():
-            out = self._fused(lat, None, B, (x1 - x0) * n * n, grid=(n, float(rmin), float(rmax), x0, x1), sigmoid=sigmoid)
-            return out.view(B, x1 - x0, n, n)
         out = torch.empty(B, x1 - x0, n, n, device=latent_depth.device, dtype=torch.float32)
         slices = max(1, self.point_chunk // (n * n * max(B, 1)))
         for s in range(x0, x1, slices):
             e = min(x1, s + slices)
             pts = ops.dense_grid(n, rmin, rmax, s, e, latent_depth.device).view(1, -1, 3).expand(B, -1, -1).contiguous()
-            lg = self._points_f32(lat, pts)
-            out[:, s - x0:e - x0] = (ops.axpby(lg, 1.0, act=ops.ACT_SIGMOID) if sigmoid else lg).view(B, e - s, n, n)
+            out[:, s - x0:e - x0] = self._points_f32(lat, pts, sigmoid=sigmoid).view(B, e - s, n, n)
         return out

@@ -82,7 +82,11 @@ class PackedWeight:
         return self.blob
 
 
-PRECISIONS = {"bf16x3": 0, "bf16": 1}
+PRECISIONS = {"bf16x3": 0, "bf16": 1, "fp16x3": 0, "fp16": 1}     # zs_gemm_tc_f32 (bf16 images): parity / single-pass mode
+# decoder chain kernels (csrc/chain_tc.cu): fp16 operand images; "bf16x3" / "bf16" are accepted as the names of the
+# parity / single-pass modes for callers written against round 1
+CHAIN_PRECISIONS = {"fp16x3": 0, "fp16": 1, "bf16x3": 0, "bf16": 1}
+FMT_BF16, FMT_FP16 = 0, 1
 
 
 def gemm_tc(a, pw, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None, precision="bf16x3"):
@@ -106,23 +110,23 @@ def gemm_tc(a, pw, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=Non
     return out
 
 
-def pack_tiles(mats):
-    """Concatenate zs_gemm_tc_pack images of fp32 matrices [256, K] (K padded to 64) -> uint8 blob."""
+def pack_tiles(mats, fmt=FMT_FP16):
+    """Concatenate zs_gemm_tc_pack_fmt images of fp32 matrices [256, K] (K padded to 64) -> uint8 blob (chain kernels: fp16)."""
     blobs = []
     for w in mats:
         w = w.detach().float().contiguous()
         assert w.shape[0] == 256, w.shape
         b = torch.empty(lib.zs_gemm_tc_packed_bytes(256, w.shape[1]), device=w.device, dtype=torch.uint8)
-        check(lib.zs_gemm_tc_pack(_p(w), w.stride(0), 256, w.shape[1], _p(b), _stream()), "zs_gemm_tc_pack")
+        check(lib.zs_gemm_tc_pack_fmt(_p(w), w.stride(0), 256, w.shape[1], _p(b), fmt, _stream()), "zs_gemm_tc_pack_fmt")
         blobs.append(b)
     return torch.cat(blobs)
 
 
-def pack_generic(w):
-    """zs_gemm_tc_pack image of one fp32 matrix [N, K] (N tiles of 256 rows, K padded to 64)."""
+def pack_generic(w, fmt=FMT_FP16):
+    """zs_gemm_tc_pack_fmt image of one fp32 matrix [N, K] (N tiles of 256 rows, K padded to 64); chain kernels: fp16."""
     w = w.detach().float().contiguous()
     b = torch.empty(lib.zs_gemm_tc_packed_bytes(w.shape[0], w.shape[1]), device=w.device, dtype=torch.uint8)
-    check(lib.zs_gemm_tc_pack(_p(w), w.stride(0), w.shape[0], w.shape[1], _p(b), _stream()), "zs_gemm_tc_pack")
+    check(lib.zs_gemm_tc_pack_fmt(_p(w), w.stride(0), w.shape[0], w.shape[1], _p(b), fmt, _stream()), "zs_gemm_tc_pack_fmt")
     return b
 
 
@@ -135,7 +139,8 @@ def attn_pack_kv(k_lat, v_lat, heads=8):
     kp[:, :L] = k_lat.reshape(L, heads, hd).permute(1, 0, 2)
     vp = torch.zeros(heads, hd, 208, device=v_lat.device, dtype=torch.float32)
     vp[:, :, :L] = v_lat.reshape(L, heads, hd).permute(1, 2, 0)
-    return torch.cat([pack_generic(kp[h]) for h in range(heads)]), torch.cat([pack_generic(vp[h]) for h in range(heads)])
+    return (torch.cat([pack_generic(kp[h], FMT_BF16) for h in range(heads)]),
+            torch.cat([pack_generic(vp[h], FMT_BF16) for h in range(heads)]))
 
 
 def attn_pack_fused(k_lat, v_lat, heads=8):
@@ -162,7 +167,40 @@ def attn_fused(qkv, kblob, vblob, n_keys, scale, precision="bf16x3", out=None):
     assert O.stride(0) == 256 and O.stride(1) == 1
     assert kblob.numel() == 4 * 65536 and vblob.numel() == 8 * 32768
     check(lib.zs_chain_attn_fwd(_p(qkv), qkv.stride(0), M, _p(kblob), _p(vblob), n_keys, scale, _p(O),
-                                PRECISIONS[precision], _stream()), "zs_chain_attn_fwd")
+                                CHAIN_PRECISIONS[precision], _stream()), "zs_chain_attn_fwd")
+    return O
+
+
+QKVATTN_FLAGS = {"kv1": 1, "s2": 2, "pv2": 4}
+
+
+def qkvattn_pack(w_qkv_folded):
+    """qkv weight [768, 256] (norm1 affine already folded) -> Wblob of zs_chain_qkvattn_fwd: per head pair the rows
+    [q of heads 2p, 2p+1 | k | v | 64 zero rows] as one 256-row fp16 operand image."""
+    w = w_qkv_folded.detach().float()
+    assert w.shape == (768, 256)
+    blobs = []
+    for p in range(4):
+        wp = torch.zeros(256, 256, device=w.device, dtype=torch.float32)
+        for j in range(3):
+            wp[64 * j:64 * j + 64] = w[256 * j + 64 * p:256 * j + 64 * p + 64]
+        blobs.append(pack_generic(wp))
+    blob = torch.cat(blobs)
+    assert blob.numel() == lib.zs_chain_qkvattn_blob_bytes()
+    return blob
+
+
+def chain_qkvattn(x, wblob, bias_qkv, kblob, vblob, n_keys, scale, ln_eps=1e-6, precision="fp16x3", flags=0, out=None):
+    """x [M,256] -> attention output [M,256] of one image: LayerNorm + qkv + point->latent attention in one tcgen05 kernel."""
+    assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+    _chk(bias_qkv, "bias_qkv")
+    assert bias_qkv.numel() == 768 and kblob.numel() == 4 * 65536 and vblob.numel() == 8 * 32768
+    assert wblob.numel() == lib.zs_chain_qkvattn_blob_bytes()
+    M = x.shape[0]
+    O = out if out is not None else torch.empty(M, 256, device=x.device, dtype=torch.float32)
+    assert O.shape == (M, 256) and O.stride(1) == 1 and O.dtype == torch.float32
+    check(lib.zs_chain_qkvattn_fwd(_p(x), x.stride(0), M, ln_eps, _p(wblob), _p(bias_qkv), _p(kblob), _p(vblob), n_keys, scale,
+                                   _p(O), O.stride(0), CHAIN_PRECISIONS[precision], int(flags), _stream()), "zs_chain_qkvattn_fwd")
     return O
 
 
@@ -194,7 +232,7 @@ def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
     assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
     assert blob.numel() == lib.zs_chain_mlp_blob_bytes()
     check(lib.zs_chain_mlp_fwd(_p(x), x.stride(0), x.shape[0], _p(ln_w), _p(ln_b), ln_eps, _p(blob), _p(b1), _p(b2),
-                               PRECISIONS[precision], _stream()), "zs_chain_mlp_fwd")
+                               CHAIN_PRECISIONS[precision], _stream()), "zs_chain_mlp_fwd")
     return x
 
 
@@ -219,7 +257,7 @@ def chain_lin(x, blob, bias, n_tiles, do_ln=False, ln_eps=1e-6, res=None, out=No
     if res is not None:
         assert res.shape == out.shape and res.stride(1) == 1 and res.dtype == torch.float32
     check(lib.zs_chain_lin_fwd(_p(x), x.stride(0), M, int(do_ln), ln_eps, _p(blob), n_tiles, _p(bias), _p(res),
-                               res.stride(0) if res is not None else 0, _p(out), out.stride(0), PRECISIONS[precision], _stream()),
+                               res.stride(0) if res is not None else 0, _p(out), out.stride(0), CHAIN_PRECISIONS[precision], _stream()),
           "zs_chain_lin_fwd")
     return out
 
@@ -231,7 +269,7 @@ def chain_occ(x, points, ln_w, ln_b, ln_eps, blob, biases, w8, b8, sigmoid=False
     assert blob.numel() == lib.zs_chain_occ_blob_bytes()
     out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
     check(lib.zs_chain_occ_fwd(_p(x), x.stride(0), _p(points), x.shape[0], _p(ln_w), _p(ln_b), ln_eps, _p(blob), _p(biases),
-                               _p(w8), float(b8), _p(out), int(sigmoid), PRECISIONS[precision], _stream()), "zs_chain_occ_fwd")
+                               _p(w8), float(b8), _p(out), int(sigmoid), CHAIN_PRECISIONS[precision], _stream()), "zs_chain_occ_fwd")
     return out
 
 
@@ -571,7 +609,7 @@ class OpTimer:
         with ops.OpTimer() as t:  ...run the hot path...
         t.summary() -> {op name: (launch groups, total ms)}   (synchronises)
     """
-    NAMES = ("point_proj", "chain_lin", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_occ", "gemm_tc", "gemm",
+    NAMES = ("point_proj", "chain_lin", "chain_qkvattn", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_occ", "gemm_tc", "gemm",
              "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "mha", "bilinear_nhwc", "dense_grid", "axpby", "marching_cubes",
              "mesh_sample", "unproject_normalize", "concat2", "maxpool3x3s2_nhwc", "avgpool_nhwc", "chamfer_nn")
 
