@@ -106,7 +106,8 @@ int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, co
  *   bias_qkv: [768] = qkv.bias + qkv.weight @ norm1.bias, original q | k | v order;
  *   Kblob / Vblob / n_keys / scale: as zs_chain_attn_fwd.
  *   flags   : per-GEMM pass policy on top of precision 0: 1 = k, v columns single-pass, 2 = scores without Qh*Kl,
- *             4 = P*V without Ph*Vl (0 = every contraction three passes). */
+ *             4 = P*V without Ph*Vl (0 = every contraction three passes); 8 = keep the probabilities in tensor memory
+ *             (chain_qkvattn2_kernel: P overwrites the scores in place, P*V reads its A operand from TMEM). */
 size_t zs_chain_qkvattn_blob_bytes(void);
 int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const void* Wblob, const float* bias_qkv,
                          const void* Kblob, const void* Vblob, int n_keys, float scale, float* O, int ldo,

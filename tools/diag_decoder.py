@@ -38,7 +38,7 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    variants = [("qkv", 0), ("qkv", 1), ("qkv", 7), ("fused", 0), ("qkv", 1)]
+    variants = [("qkv", 8), ("qkv", 9), ("qkv", 15), ("qkv", 0), ("fused", 0), ("qkv", 8)]
     for attention, flags in variants:
         fused = True
         net.attention, net.attn_flags = attention, flags

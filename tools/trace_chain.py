@@ -26,6 +26,13 @@ TAGS_ATTN = {
     20: "epi: wait sfull", 21: "epi: sfull ok", 22: "epi: pass1 done", 23: "epi: chunk stored", 24: "epi: wait ofull",
     25: "epi: ofull ok", 26: "epi: out stored",
 }
+TAGS_QKVATTN = {
+    1: "mma: qkv chunk: wait lfull", 2: "mma: qkv chunk: lfull ok", 3: "mma: qkv chunk issued", 4: "mma: head start (wait K tile)",
+    5: "mma: S issued", 6: "mma: V tile ok (wait oempty, pfull)", 7: "mma: pfull ok", 8: "mma: PV issued",
+    10: "ld : wait lempty", 11: "ld : lempty ok", 12: "ld : stored+arrived", 14: "ld : tile start", 15: "ld : stats+first fetch done",
+    20: "epi: wait accfull", 21: "epi: accfull ok", 22: "epi: epi-1 done / wait sfull", 23: "epi: sfull ok", 24: "epi: max pass done",
+    25: "epi: bar1 passed", 26: "epi: exp pass done, pfull arrived", 27: "epi: bar2 passed", 28: "epi: ofull ok", 29: "epi: out stored",
+}
 NE = 512
 
 
@@ -79,6 +86,17 @@ def main():
     x0 = torch.randn(M, 256, device=dev)
     os.makedirs("gpurun_out", exist_ok=True)
     which = sys.argv[1:] or ["mlp", "attn"]
+    if "qkvattn" in which:
+        L, C, H = 197, 256, 8
+        lat = torch.randn(L, 2 * C, generator=g).to(dev)
+        kb, vb = ops.attn_pack_fused(lat[:, :C], lat[:, C:], H)
+        wq = (torch.randn(768, 256, generator=g) / 16).to(dev)
+        wb = ops.qkvattn_pack(wq)
+        bq = torch.zeros(768, device=dev)
+        out = torch.empty(M, C, device=dev)
+        for flags in (8, 9):
+            run_traced(f"chain_qkvattn_flags{flags}", TAGS_QKVATTN,
+                       lambda: ops.chain_qkvattn(x0, wb, bq, kb, vb, L, 32 ** -0.5, flags=flags, out=out))
     if "mlp" in which:
         x = x0.clone()
         run_traced("chain_mlp_bf16x3", TAGS_MLP, lambda: ops.chain_mlp(x, None, None, 1e-6, blob, b1, b2, "bf16x3"))

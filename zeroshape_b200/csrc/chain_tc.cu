@@ -1238,7 +1238,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_attn_kernel(ChainParams p
 //                       chunk, half 1: K-steps {2,3}): row max and row sum are exchanged through smem (named barriers),
 //                       probabilities go to the P slot in 32-key halves (pfull/pempty per half), and the half that owns
 //                       the head finishes (O + e_self v_self) / sum -> transpose through the idle P slot -> global.
-// TMEM: qkv accumulator [0,192), S [192,400), O of even heads [400,432), of odd heads [432,464).
+// TMEM (this kernel): qkv accumulator [0,192), S [192,400), O of even heads [400,432), of odd heads [432,464).
 // flags: 1 = k, v columns single-pass (Ah Wh only), 2 = scores without Qh Kl, 4 = P V without Ph Vl
 //        (profiles/r2_precision_study.md; precision 1 = everything single-pass).
 constexpr int QA_THREADS = 576;                                 // warps 0-7 loaders, 8-15 softmax, 16 MMA, 17 W loader
@@ -1630,6 +1630,429 @@ __global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn_kernel(ChainParam
   if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ===============================================================================================================
+// Same operation as chain_qkvattn_kernel with the probabilities kept in TENSOR MEMORY: the softmax threads overwrite
+// the fp32 scores of their 32-key blocks in place with the split-fp16 probabilities (32 score columns -> 16 packed hi
+// columns + 16 packed lo columns, tcgen05.st) and O_h = P_h V_h takes its A operand from TMEM (tcgen05.mma [d], [a], b).
+// One hand-over per head (pfull) replaces the seven P-slot round trips per head of the smem variant, P never crosses the
+// shared-memory port, and the freed 32 KB are a 4th weight-ring slot (the MMA thread was exposed to every tile-load
+// latency with 3).  S(h+1) overwrites the columns P(h) was read from: both are tcgen05.mma of the same issuing thread and
+// execute in order, and every softmax thread has finished its loads / stores of the buffer before pfull(h).
+// The attention output goes straight from registers to global memory (16 bytes per row and store; the rows' 128-byte
+// segments merge in L2).
+// Per head the W loader streams: K hi, K lo, [next unit's qkv weights: 2 K-chunks x (hi, lo)], V -- the order of use.
+constexpr int QB_WSLOTS = 4;
+constexpr int QB_OFF_W = 0;                                     // 4 x 32 KB
+constexpr int QB_OFF_L = QB_OFF_W + QB_WSLOTS * CT_TILE_BYTES;  // 128 KB: 2 x (hi 16K | lo 16K) LN(x) chunks
+constexpr int QB_OFF_Q = QB_OFF_L + 2 * 2 * CT_A_HALF;          // 192 KB: the unit's q chunk (hi | lo)
+static_assert(QB_OFF_Q + 2 * CT_A_HALF == QA_OFF_BAR, "qkv-attention (TMEM P) smem layout");
+
+struct QBars2 {
+  uint32_t base;
+  __device__ uint32_t wfull(int i) const { return base + 8u * i; }
+  __device__ uint32_t wempty(int i) const { return base + 32u + 8u * i; }
+  __device__ uint32_t lfull(int i) const { return base + 64u + 8u * i; }
+  __device__ uint32_t lempty(int i) const { return base + 80u + 8u * i; }
+  __device__ uint32_t accfull() const { return base + 96u; }
+  __device__ uint32_t accempty() const { return base + 104u; }
+  __device__ uint32_t qfull(int g) const { return base + 112u + 8u * g; }    // head g of the unit: written by half g
+  __device__ uint32_t qempty(int g) const { return base + 128u + 8u * g; }
+  __device__ uint32_t sfull() const { return base + 144u; }
+  __device__ uint32_t pfull() const { return base + 152u; }
+  __device__ uint32_t ofull() const { return base + 160u; }
+  __device__ uint32_t oempty() const { return base + 168u; }
+  __device__ uint32_t tmem_slot() const { return base + 176u; }
+};
+
+// e = exp2(s * sl2 - mxs) of NK scores (keys k0 ...), masked past n_keys; accumulates the row sum; the split-fp16 values go
+// back into the scores' own TMEM columns: NK/2 packed hi columns at taddr, NK/2 packed lo columns behind them
+template <int NK, bool MASKED>
+__device__ __forceinline__ void attn_exp_tmem(const uint32_t* rr, int k0, int n_keys, float sl2, float mxs, float2& sum2,
+                                              uint32_t taddr, bool split) {
+  uint32_t hi[NK / 2], lo[NK / 2];
+#pragma unroll
+  for (int j = 0; j < NK / 2; ++j) {
+    const int i = 2 * j;
+    const float2 a = fma2(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), bc2(sl2), bc2(-mxs));
+    float2 v = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+    if (MASKED) { if (k0 + i >= n_keys) v.x = 0.f; if (k0 + i + 1 >= n_keys) v.y = 0.f; }
+    sum2 = add2(sum2, v);
+    split_f16x2(v.x, v.y, hi[j], lo[j]);
+  }
+  if constexpr (NK == 32) {
+    tmem_st_32x16(taddr, hi);
+    if (split) tmem_st_32x16(taddr + 16, lo);
+  } else {
+    tmem_st_32x8(taddr, hi);
+    if (split) tmem_st_32x8(taddr + 8, lo);
+  }
+}
+
+__global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();   // dynamic smem base less aligned than budgeted
+  QBars2 B{smem_base + QA_OFF_BAR};
+  float* xbuf = reinterpret_cast<float*>(smem_gen + QA_OFF_X);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const bool kv1 = split && (p.flags & 1), s2 = split && (p.flags & 2), pv2 = split && (p.flags & 4);
+  const int n_tiles = (p.M + 127) / 128;
+  const int n_keys = p.n_keys;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < QB_WSLOTS; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(B.lfull(i), 256); mbar_init(B.lempty(i), 1); }
+    mbar_init(B.accfull(), 1); mbar_init(B.accempty(), 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(B.qfull(i), 128); mbar_init(B.qempty(i), 1); }
+    mbar_init(B.sfull(), 1); mbar_init(B.pfull(), 256);
+    mbar_init(B.ofull(), 1); mbar_init(B.oempty(), 128);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc(B.tmem_slot(), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
+
+  if (warp < 8) {
+    // ---------------- loaders: LN(x) chunks, 4 units x 4 K-chunks per tile ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    Ring lr(2);
+    float4 buf[8];
+    int tn = 0;
+    const bool tr0 = threadIdx.x == 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 16;
+      float sc = 1.f, sh = 0.f;
+      if (tr0) trace_ev(p.trace, 1, tn, 14);
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      if (tr0) trace_ev(p.trace, 1, tn, 15);
+      for (int i = 0; i < 16; ++i) {
+        if (tr0) trace_ev(p.trace, 1, tn, 10);
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        if (tr0) trace_ev(p.trace, 1, tn, 11);
+        store_chunk16(smem_gen + QB_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        if (tr0) trace_ev(p.trace, 1, tn, 12);
+        lr.advance();
+        if (i + 1 < 16) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+      }
+    }
+  } else if (warp == 17) {
+    // ---------------- W loader ----------------
+    if (lane == 0) {
+      Ring wr(QB_WSLOTS);
+      auto put = [&](const uint8_t* src, uint32_t bytes) {
+        mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
+        mbar_arrive_expect_tx(B.wfull(wr.idx), bytes);
+        bulk_g2s(smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES, src, bytes, B.wfull(wr.idx));
+        wr.advance();
+      };
+      auto qkv_chunk = [&](int pr, int kc) {
+        const uint8_t* src = p.blob + ((size_t)pr * 4 + kc) * 2 * CT_TILE_BYTES;
+        put(src, QA_QKV_TILE_BYTES);
+        if (split) put(src + CT_TILE_BYTES, kv1 ? QA_Q_TILE_BYTES : QA_QKV_TILE_BYTES);
+      };
+      bool first = true;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int pr = 0; pr < 4; ++pr) {
+          if (first) { for (int kc = 0; kc < 4; ++kc) qkv_chunk(0, kc); first = false; }
+          const bool has_next = pr < 3 || t + (int)gridDim.x < n_tiles;
+          const int pn = (pr + 1) & 3;
+          for (int g = 0; g < 2; ++g) {
+            put(p.kblob + (size_t)pr * 2 * CT_TILE_BYTES, QA_K_TILE_BYTES);
+            if (split && !s2) put(p.kblob + (size_t)pr * 2 * CT_TILE_BYTES + CT_TILE_BYTES, QA_K_TILE_BYTES);
+            if (has_next) { qkv_chunk(pn, 2 * g); qkv_chunk(pn, 2 * g + 1); }
+            put(p.vblob + (size_t)(2 * pr + g) * CT_TILE_BYTES, CT_TILE_BYTES);
+          }
+        }
+      }
+    }
+  } else if (warp == 16) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(QB_WSLOTS), lr(2);
+      uint32_t ph_accempty = 0, ph_qfull = 0, ph_pfull = 0, ph_oempty = 0;   // ph_qfull: bit g = phase of qfull(g)
+      const uint32_t idesc_qkv = umma_idesc_f16(128, 192), idesc_q2 = kv1 ? umma_idesc_f16(128, 64) : idesc_qkv;
+      const uint32_t idesc_s = umma_idesc_f16(128, 208), idesc_o = umma_idesc_f16(128, 32), idesc_o2 = umma_idesc_f16(128, 64);
+      const uint32_t d_acc = tmem_base, d_s = tmem_base + 192, d_o = tmem_base + 400;
+      const uint64_t q_hi = umma_desc_sw128(smem_base + QB_OFF_Q), q_lo = umma_desc_sw128(smem_base + QB_OFF_Q + CT_A_HALF);
+      int tn = 0;
+      auto qkv_chunk = [&](int kc) {
+        trace_ev(p.trace, 0, tn, 1);
+        mbar_wait(B.lfull(lr.idx), lr.phase);
+        trace_ev(p.trace, 0, tn, 2);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + QB_OFF_L + lr.idx * 2 * CT_A_HALF;
+        const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+        mbar_wait(B.wfull(wr.idx), wr.phase);
+        tc_fence_after();
+        {
+          const uint64_t w = umma_desc_sw128(smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d_acc, a_hi + 2 * k, w + 2 * k, idesc_qkv, (kc > 0 || k > 0) ? 1u : 0u);
+            if (split) umma_bf16(d_acc, a_lo + 2 * k, w + 2 * k, idesc_q2, 1u);
+          }
+          umma_commit(B.wempty(wr.idx));
+          wr.advance();
+        }
+        if (split) {
+          mbar_wait(B.wfull(wr.idx), wr.phase);
+          tc_fence_after();
+          const uint64_t w = umma_desc_sw128(smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_acc, a_hi + 2 * k, w + 2 * k, idesc_q2, 1u);
+          umma_commit(B.wempty(wr.idx));
+          wr.advance();
+        }
+        umma_commit(B.lempty(lr.idx));
+        lr.advance();
+        trace_ev(p.trace, 0, tn, 3);
+      };
+      mbar_wait(B.accempty(), ph_accempty ^ 1); ph_accempty ^= 1;
+      tc_fence_after();
+      for (int kc = 0; kc < 4; ++kc) qkv_chunk(kc);
+      umma_commit(B.accfull());
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int pr = 0; pr < 4; ++pr) {
+          const bool has_next = pr < 3 || t + (int)gridDim.x < n_tiles;
+          for (int g = 0; g < 2; ++g) {
+            // ---- S = Q_h K_h^T (overwrites the probabilities of the previous head: in-order tensor pipe) ----
+            trace_ev(p.trace, 0, tn, 4);
+            mbar_wait(B.qfull(g), (ph_qfull >> g) & 1u); ph_qfull ^= 1u << g;     // half g has written this head's q (epi-1)
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            tc_fence_after();
+            {
+              const uint64_t w = umma_desc_sw128(smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int kk = 2 * g + k;
+                umma_bf16(d_s, q_hi + 2 * kk, w + 2 * kk, idesc_s, k > 0 ? 1u : 0u);
+                if (split) umma_bf16(d_s, q_lo + 2 * kk, w + 2 * kk, idesc_s, 1u);
+              }
+              umma_commit(B.wempty(wr.idx));
+              wr.advance();
+            }
+            if (split && !s2) {
+              mbar_wait(B.wfull(wr.idx), wr.phase);
+              tc_fence_after();
+              const uint64_t w = umma_desc_sw128(smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) umma_bf16(d_s, q_hi + 2 * (2 * g + k), w + 2 * (2 * g + k), idesc_s, 1u);
+              umma_commit(B.wempty(wr.idx));
+              wr.advance();
+            }
+            umma_commit(B.sfull());
+            umma_commit(B.qempty(g));
+            trace_ev(p.trace, 0, tn, 5);
+            // ---- the next unit's qkv GEMM, two K-chunks per head, while the softmax of this head runs ----
+            if (has_next) {
+              if (g == 0) { mbar_wait(B.accempty(), ph_accempty ^ 1); ph_accempty ^= 1; tc_fence_after(); }
+              qkv_chunk(2 * g);
+              qkv_chunk(2 * g + 1);
+              if (g == 1) umma_commit(B.accfull());
+            }
+            // ---- O_h = P_h V_h: A = the probabilities in TMEM (in the score columns), B = the head's value tile ----
+            mbar_wait(B.wfull(wr.idx), wr.phase);
+            const int v_slot = wr.idx;
+            const uint32_t v_addr = smem_base + QB_OFF_W + wr.idx * CT_TILE_BYTES;
+            wr.advance();
+            trace_ev(p.trace, 0, tn, 6);
+            mbar_wait(B.oempty(), ph_oempty ^ 1); ph_oempty ^= 1;
+            mbar_wait(B.pfull(), ph_pfull); ph_pfull ^= 1;
+            trace_ev(p.trace, 0, tn, 7);
+            tc_fence_after();
+            // an MMA whose A operand comes from tensor memory costs ~64 cycles whatever its N (the 128 x 16 A block is
+            // fetched per instruction), so Ph Vh and Ph Vl are ONE instruction with N = 64: the value tile chunk is stored
+            // as [hi rows 0..31 | lo rows 32..63] = one 64-row operand tile, and the accumulator holds Ph Vh (+ Pl Vh) in
+            // columns [0,32) and Ph Vl in [32,64); the finishing threads add the two halves
+            const uint32_t idesc_hi = (split && !pv2) ? idesc_o2 : idesc_o;
+#pragma unroll 1
+            for (int j = 0; j < 13; ++j) {                 // K-step j = keys 16j .. 16j+15
+              const uint32_t a_hi = d_s + 32u * (j >> 1) + 8u * (j & 1);
+              const uint32_t a_lo = a_hi + (j == 12 ? 8u : 16u);
+              const uint64_t vv = umma_desc_sw128(v_addr + (j >> 2) * 8192) + 2 * (j & 3);
+              umma_ts(d_o, a_hi, vv, idesc_hi, j > 0 ? 1u : 0u);
+              if (split) umma_ts(d_o, a_lo, vv, idesc_o, 1u);
+            }
+            umma_commit(B.ofull());
+            umma_commit(B.wempty(v_slot));
+            trace_ev(p.trace, 0, tn, 8);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax / epilogue warps: thread = (query row, half) ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    int tn = 0;
+    const bool tr0 = (warp == 8 && lane == 0);
+    const int e = warp - 8, wq = e & 3, half = e >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t acc_tm = tmem_base + lane_off, s_tm = acc_tm + 192u, o_tm = acc_tm + 400u;
+    const bool o_two = split && !pv2;             // the accumulator carries Ph Vl in a second 32-column half
+    uint8_t* qslot = smem_gen + QB_OFF_Q;
+    uint32_t ph_accfull = 0, ph_qempty = 0, ph_sfull = 0, ph_ofull = 0;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int mrow = t * 128 + row;
+      for (int pr = 0; pr < 4; ++pr) {
+        // ---- epi-1: this half's head of the pair out of the qkv accumulator ----
+        const int hm = 2 * pr + half;
+        float v[32];
+        float s_self;
+        if (tr0) trace_ev(p.trace, 2, tn, 20);
+        mbar_wait(B.accfull(), ph_accfull); ph_accfull ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 21);
+        tc_fence_after();
+        {
+          uint32_t rq[32], rk[32];
+          tmem_ld_32x32(acc_tm + 32u * half, rq);
+          tmem_ld_32x32(acc_tm + 64u + 32u * half, rk);
+          tmem_ld_wait();
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + hm * 32);
+          const float4* bk = reinterpret_cast<const float4*>(p.bias + 256 + hm * 32);
+          float2 d2 = make_float2(0.f, 0.f);
+          mbar_wait(B.qempty(half), ph_qempty ^ 1); ph_qempty ^= 1;     // the previous unit's S MMA of this head slot has read its q
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 b4 = __ldg(bq + 2 * c + j), k4 = __ldg(bk + 2 * c + j);
+              const int i = 8 * c + 4 * j;
+              const float2 qa = add2(make_float2(__uint_as_float(rq[i]), __uint_as_float(rq[i + 1])), make_float2(b4.x, b4.y));
+              const float2 qb = add2(make_float2(__uint_as_float(rq[i + 2]), __uint_as_float(rq[i + 3])), make_float2(b4.z, b4.w));
+              const float2 ka = add2(make_float2(__uint_as_float(rk[i]), __uint_as_float(rk[i + 1])), make_float2(k4.x, k4.y));
+              const float2 kb = add2(make_float2(__uint_as_float(rk[i + 2]), __uint_as_float(rk[i + 3])), make_float2(k4.z, k4.w));
+              d2 = fma2(qa, ka, d2);
+              d2 = fma2(qb, kb, d2);
+              split_f16x2(qa.x, qa.y, hi[2 * j], lo[2 * j]);
+              split_f16x2(qb.x, qb.y, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            const uint32_t off = swizzle128_offset(row, 4 * half + c);
+            *reinterpret_cast<uint4*>(qslot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (split) *reinterpret_cast<uint4*>(qslot + CT_A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          s_self = d2.x + d2.y;
+          fence_proxy_async_smem();
+          mbar_arrive(B.qfull(half));
+        }
+        {
+          uint32_t rv[32];
+          tmem_ld_32x32(acc_tm + 128u + 32u * half, rv);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(B.accempty());
+          const float4* bv = reinterpret_cast<const float4*>(p.bias + 512 + hm * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bv + j);
+            v[4 * j] = __uint_as_float(rv[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(rv[4 * j + 1]) + b4.y;
+            v[4 * j + 2] = __uint_as_float(rv[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(rv[4 * j + 3]) + b4.w;
+          }
+        }
+        // ---- the two heads of the pair; both halves share each head's keys (half 0: 32-key blocks 0,2,4,6; half 1: 1,3,5) ----
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          const int h = 2 * pr + hs;
+          const bool mine = hs == half;
+          if (tr0) trace_ev(p.trace, 2, tn, 22);
+          mbar_wait(B.sfull(), ph_sfull); ph_sfull ^= 1;
+          if (tr0) trace_ev(p.trace, 2, tn, 23);
+          tc_fence_after();
+          float mx = mine ? s_self : -3.0e38f;
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(s_tm + c * 64 + 32 * half, rr);
+            tmem_ld_wait();
+            mx = attn_max_block<32>(rr, c * 64 + 32 * half, n_keys, mx);
+          }
+          if (half == 0) {
+            uint32_t rr[16];
+            tmem_ld_32x16(s_tm + 192, rr);
+            tmem_ld_wait();
+            mx = attn_max_block<16>(rr, 192, n_keys, mx);
+          }
+          xbuf[half * 128 + row] = mx;
+          if (tr0) trace_ev(p.trace, 2, tn, 24);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tr0) trace_ev(p.trace, 2, tn, 25);
+          mx = fmaxf(mx, xbuf[(half ^ 1) * 128 + row]);
+          const float mxs = mx * sl2;
+          float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t rr[32];
+            tmem_ld_32x32(s_tm + c * 64 + 32 * half, rr);
+            tmem_ld_wait();
+            const int k0 = c * 64 + 32 * half;     // a block is masked only when the key count ends inside it (CTA-uniform)
+            if (k0 + 32 <= n_keys) attn_exp_tmem<32, false>(rr, k0, n_keys, sl2, mxs, sum2, s_tm + k0, split);
+            else attn_exp_tmem<32, true>(rr, k0, n_keys, sl2, mxs, sum2, s_tm + k0, split);
+          }
+          if (half == 0) {
+            uint32_t rr[16];
+            tmem_ld_32x16(s_tm + 192, rr);
+            tmem_ld_wait();
+            attn_exp_tmem<16, true>(rr, 192, n_keys, sl2, mxs, sum2, s_tm + 192, split);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(B.pfull());
+          if (tr0) trace_ev(p.trace, 2, tn, 26);
+          float sum = sum2.x + sum2.y, e_self = 0.f;
+          if (mine) { e_self = fast_ex2(fmaf(s_self, sl2, -mxs)); sum += e_self; }
+          xbuf[256 + half * 128 + row] = sum;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (tr0) trace_ev(p.trace, 2, tn, 27);
+          if (mine) {
+            const float inv = 1.0f / (sum + xbuf[256 + (half ^ 1) * 128 + row]);
+            mbar_wait(B.ofull(), ph_ofull);
+            if (tr0) trace_ev(p.trace, 2, tn, 28);
+            tc_fence_after();
+            float4* dst = reinterpret_cast<float4*>(p.out + (int64_t)mrow * p.ldo + h * 32);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {            // 16 output columns at a time (register budget)
+              uint32_t rr[16], r2[16];
+              tmem_ld_32x16(o_tm + 16u * q, rr);
+              if (o_two) tmem_ld_32x16(o_tm + 32u + 16u * q, r2);
+              tmem_ld_wait();
+              if (q == 1) { tc_fence_before(); mbar_arrive(B.oempty()); }
+              if (mrow < p.M) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float o[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float a = __uint_as_float(rr[4 * j + i]);
+                    if (o_two) a += __uint_as_float(r2[4 * j + i]);
+                    o[i] = fmaf(e_self, v[16 * q + 4 * j + i], a) * inv;
+                  }
+                  dst[4 * q + j] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+              }
+            }
+            if (tr0) trace_ev(p.trace, 2, tn, 29);
+          }
+          ph_ofull ^= 1;      // one accumulator, one barrier: a phase per head, whichever half owns it
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
 
 static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name, int threads = CT_THREADS) {
@@ -1725,11 +2148,12 @@ extern "C" int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(Kblob) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(Vblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias_qkv) & 15) == 0,
              "zs_chain_qkvattn_fwd: blobs / bias must be 16-byte aligned");
-  ZS_REQUIRE((precision == 0 || precision == 1) && flags >= 0 && flags < 8, "zs_chain_qkvattn_fwd: bad precision / flags");
+  ZS_REQUIRE((precision == 0 || precision == 1) && flags >= 0 && flags < 16, "zs_chain_qkvattn_fwd: bad precision / flags");
   if (M == 0) return ZS_OK;
   ChainParams p{};
   p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.blob = reinterpret_cast<const uint8_t*>(Wblob);
   p.bias = bias_qkv; p.kblob = reinterpret_cast<const uint8_t*>(Kblob); p.vblob = reinterpret_cast<const uint8_t*>(Vblob);
   p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = ldo; p.precision = precision; p.flags = flags;
-  return chain_launch(chain_qkvattn_kernel, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA_THREADS);
+  // flags & 8: the variant that keeps the probabilities in tensor memory (chain_qkvattn2_kernel)
+  return chain_launch((flags & 8) ? chain_qkvattn2_kernel : chain_qkvattn_kernel, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA_THREADS);
 }

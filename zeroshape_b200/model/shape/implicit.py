@@ -93,7 +93,9 @@ class Implicit(nn.Module):
         # point attention: "qkv" (LayerNorm + qkv + flash-style attention in ONE tcgen05 kernel, q/k/v never reach HBM) |
         # "fused" (qkv by zs_chain_lin_fwd, then one flash-style attention kernel) | "tc" (two grouped launches) | "f32" (FFMA)
         self.attention = "qkv"
-        self.attn_flags = 1           # zs_chain_qkvattn_fwd pass policy (profiles/r2_precision_study.md): 1 = k, v single-pass
+        # zs_chain_qkvattn_fwd policy: 8 = probabilities in tensor memory (the faster kernel), every contraction three fp16
+        # passes; +1 = k, v single-pass (inside the 5e-4 parity budget of profiles/r2_precision_study.md, no measured speed-up)
+        self.attn_flags = 8
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         # query points per pass of the per-layer / chained engines (bounds scratch memory: ~5 KB per point).  One pass over a whole

@@ -171,7 +171,7 @@ def attn_fused(qkv, kblob, vblob, n_keys, scale, precision="bf16x3", out=None):
     return O
 
 
-QKVATTN_FLAGS = {"kv1": 1, "s2": 2, "pv2": 4}
+QKVATTN_FLAGS = {"kv1": 1, "s2": 2, "pv2": 4, "tmem_p": 8}
 
 
 def qkvattn_pack(w_qkv_folded):
