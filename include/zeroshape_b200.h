@@ -115,6 +115,10 @@ int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const voi
 /* debug: while buf (device, [3][512] uint64) is non-NULL the chained kernels record role-level clock64 events of
  * CTA 0 (MMA thread, loader thread 0, epilogue warp 4 lane 0) into it; see tools/trace_chain.py.  Not thread-safe. */
 int zs_debug_chain_trace(unsigned long long* buf);
+/* debug / A-B: zs_chain_mlp_fwd and zs_chain_occ_fwd run chain_mlp2 / chain_occ2 (activations of the next GEMM kept in tensor
+ * memory, 4 / 5 weight-ring slots) when v != 0 (default) and the round-1 kernels (shared-memory ring E, 3 slots) when v == 0.
+ * Identical arithmetic.  Process-wide, not thread-safe. */
+int zs_debug_chain_variant(int v);
 
 /* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
  * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack

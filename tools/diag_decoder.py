@@ -9,6 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zeroshape_b200 import ops  # noqa: E402
+from zeroshape_b200._native import lib  # noqa: E402
 from zeroshape_b200.model.shape.implicit import Implicit  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -38,10 +39,11 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    variants = [("qkv", 8), ("qkv", 9), ("qkv", 15), ("qkv", 0), ("fused", 0), ("qkv", 8)]
-    for attention, flags in variants:
+    variants = [("qkv", 8, 1), ("qkv", 8, 0), ("qkv", 9, 1), ("qkv", 0, 1), ("fused", 0, 0), ("qkv", 8, 1)]
+    for attention, flags, mlp_variant in variants:
         fused = True
         net.attention, net.attn_flags = attention, flags
+        lib.zs_debug_chain_variant(mlp_variant)
         for _ in range(3):
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
@@ -54,7 +56,7 @@ with torch.no_grad():
             e1.record()
         summ = t.summary()
         total = e0.elapsed_time(e1) / reps
-        log(f"\n== attention={attention} flags={flags}: {P} points, pass {total:.3f} ms ({P / total / 1e3:.1f} Mpts/s; x{2146689 / P:.2f} = {total * 2146689 / P:.1f} ms per 129^3 shape)")
+        log(f"\n== attention={attention} flags={flags} mlp/occ variant {mlp_variant}: {P} points, pass {total:.3f} ms ({P / total / 1e3:.1f} Mpts/s; x{2146689 / P:.2f} = {total * 2146689 / P:.1f} ms per 129^3 shape)")
         for k, (c, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
             per = ms / c
             tf = FLOP.get(k, 0) * P / per / 1e9 if per > 0 else 0

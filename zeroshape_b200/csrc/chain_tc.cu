@@ -2053,7 +2053,400 @@ __global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainPara
   if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ===============================================================================================================
+// Second generation of the two chained MLP kernels: the activations that feed the NEXT GEMM stay in TENSOR MEMORY.
+// The epilogue threads overwrite each 32-column block of the fp32 accumulator in place with the split-fp16 activation
+// (16 packed hi columns | 16 packed lo columns, tcgen05.st), and the next layer's MMAs take that block as their A operand
+// from TMEM (tcgen05.mma [d], [a], b) -- the construction validated in chain_qkvattn2_kernel.  Versus ring E:
+//   * the activations never cross the shared-memory port (the N = 256 MMAs read 12 KB of smem operands per 128 cycles
+//     = 96 of the port's 128 B/clk; ring-E chunks added 32 KB written + 48 KB read per 64-wide K-chunk);
+//   * the 64 KB of ring E become weight-ring slots (3 -> 4 for the MLP, 5 for the occupancy MLP): the weight stream is
+//     latency-bound (a slot is released only when the MMAs that read it have completed), so depth is throughput;
+//   * no eempty hand-back: the accumulator half is protected by the in-order tensor pipe and tempty.
+// A TS MMA costs >= 64 cycles whatever its N (the 128 x 16 A block is fetched per instruction); at N = 256 that is free.
+constexpr int M2_WSLOTS = 4, O2_WSLOTS = 5;
+constexpr int M2_OFF_L = M2_WSLOTS * CT_TILE_BYTES;            // 128 KB
+constexpr int M2_OFF_T = M2_OFF_L + CT_LSLOTS * 2 * CT_A_HALF; // 192 KB: 8 x 4 KB transpose scratch of the final epilogue
+constexpr int O2_OFF_L = O2_WSLOTS * CT_TILE_BYTES;            // 160 KB
+static_assert(M2_OFF_T + 8 * 4096 == CT_OFF_BAR && O2_OFF_L + CT_LSLOTS * 2 * CT_A_HALF == CT_OFF_BAR, "chain2 smem layout");
+
+struct Bars5 {   // up to 5 weight slots
+  uint32_t base;
+  __device__ uint32_t wfull(int i) const { return base + 8u * i; }
+  __device__ uint32_t wempty(int i) const { return base + 40u + 8u * i; }
+  __device__ uint32_t lfull(int i) const { return base + 80u + 8u * i; }
+  __device__ uint32_t lempty(int i) const { return base + 96u + 8u * i; }
+  // one barrier per 64-column activation chunk: a single barrier would let the epilogue run two phases ahead of the MMA
+  // thread (parity waits cannot tell phase k from k + 2); per chunk it is at most one, because the next layer's tfull needs
+  // the MMA thread to have consumed all four
+  __device__ uint32_t efull(int c) const { return base + 112u + 8u * c; }
+  __device__ uint32_t tfull(int i) const { return base + 144u + 8u * i; }
+  __device__ uint32_t tempty(int i) const { return base + 160u + 8u * i; }
+  __device__ uint32_t tmem_slot() const { return base + 176u; }
+};
+
+__device__ __forceinline__ uint32_t chain2_setup(const Bars5& B, uint8_t* smem_gen, uint32_t smem_base, int warp, int wslots) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < wslots; ++i) { mbar_init(B.wfull(i), 1); mbar_init(B.wempty(i), 1); }
+    for (int i = 0; i < CT_LSLOTS; ++i) { mbar_init(B.lfull(i), 128); mbar_init(B.lempty(i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(B.efull(i), 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(B.tfull(i), 1); mbar_init(B.tempty(i), 256); }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc(B.tmem_slot(), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
+}
+
+// MMA thread: one 64-wide K-chunk against the next weight tile pair; A from shared memory (a_addr) or, when `ts`,
+// from tensor memory (two 32-value blocks of [16 hi | 16 lo] columns: K-step kk at a_tmem + 32 (kk >> 1) + 8 (kk & 1))
+__device__ __forceinline__ void mma_chunk2(const Bars5& B, uint32_t smem_base, Ring& wr, bool ts, uint32_t a_addr, uint32_t a_tmem,
+                                           uint32_t d_tmem, bool first, bool split, uint32_t a_empty_bar) {
+  const uint32_t idesc = umma_idesc_f16(128, 256);
+  const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
+  mbar_wait(B.wfull(wr.idx), wr.phase);
+  tc_fence_after();
+  {
+    const uint64_t w = umma_desc_sw128(smem_base + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+      if (ts) {
+        const uint32_t at = a_tmem + 32u * (k >> 1) + 8u * (k & 1);
+        umma_ts(d_tmem, at, w + 2 * k, idesc, acc);
+        if (split) umma_ts(d_tmem, at + 16u, w + 2 * k, idesc, 1u);
+      } else {
+        umma_bf16(d_tmem, a_hi + 2 * k, w + 2 * k, idesc, acc);
+        if (split) umma_bf16(d_tmem, a_lo + 2 * k, w + 2 * k, idesc, 1u);
+      }
+    }
+    umma_commit(B.wempty(wr.idx));
+    wr.advance();
+  }
+  if (split) {
+    mbar_wait(B.wfull(wr.idx), wr.phase);
+    tc_fence_after();
+    const uint64_t w = umma_desc_sw128(smem_base + wr.idx * CT_TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ts) umma_ts(d_tmem, a_tmem + 32u * (k >> 1) + 8u * (k & 1), w + 2 * k, idesc, 1u);
+      else umma_bf16(d_tmem, a_hi + 2 * k, w + 2 * k, idesc, 1u);
+    }
+    umma_commit(B.wempty(wr.idx));
+    wr.advance();
+  }
+  if (a_empty_bar != 0u) umma_commit(a_empty_bar);
+}
+
+__device__ __forceinline__ void w_stream2(const Bars5& B, uint32_t smem_base, Ring& wr, const uint8_t* blob, int pairs, bool split) {
+  for (int i = 0; i < pairs; ++i) {
+    const uint8_t* src = blob + (size_t)i * 2 * CT_TILE_BYTES;
+    for (int h = 0; h < (split ? 2 : 1); ++h) {
+      mbar_wait(B.wempty(wr.idx), wr.phase ^ 1);
+      mbar_arrive_expect_tx(B.wfull(wr.idx), CT_TILE_BYTES);
+      bulk_g2s(smem_base + wr.idx * CT_TILE_BYTES, src + (size_t)h * CT_TILE_BYTES, CT_TILE_BYTES, B.wfull(wr.idx));
+      wr.advance();
+    }
+  }
+}
+
+// epilogue thread: 32 accumulator columns -> act(d + bias) -> split fp16 -> back into the same 32 TMEM columns [16 hi | 16 lo]
+template <int ACT>
+__device__ __forceinline__ void epi_to_tmem(uint32_t taddr, const uint32_t (&rr)[32], const float* __restrict__ bias, bool split) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8 + 4));
+    const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = add2(make_float2(__uint_as_float(rr[c * 8 + 2 * j]), __uint_as_float(rr[c * 8 + 2 * j + 1])), bb[j]);
+      const float2 v = ACT == ZS_ACT_GELU ? fast_gelu_erf2(t) : fast_softplus100_2(t);
+      split_f16x2(v.x, v.y, hi[4 * c + j], lo[4 * c + j]);
+    }
+  }
+  tmem_st_32x16(taddr, hi);
+  if (split) tmem_st_32x16(taddr + 16u, lo);
+}
+
+// x <- x + fc2(GELU(fc1(LN(x))))      blob order as chain_mlp_kernel
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp2_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();
+  Bars5 B{smem_base + CT_OFF_BAR};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain2_setup(B, smem_gen, smem_base, warp, M2_WSLOTS);
+  const int n_tiles = (p.M + 127) / 128;
+
+  if (warp < 4) {
+    // ---------------- loader: LN(x) chunks, 4 groups x 4 chunks per tile ----------------
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 32;
+      float sc, sh;
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      fetch_chunk_co(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      for (int i = 0; i < 16; ++i) {
+        const int kc = i & 3;
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk_co(smem_gen + M2_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh,
+                       p.ln_w ? p.ln_w + kc * 64 : nullptr, p.ln_b ? p.ln_b + kc * 64 : nullptr, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (i + 1 < 16) fetch_chunk_co(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(M2_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream2(B, smem_base, wr, p.blob, 32, split);
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(M2_WSLOTS), lr(CT_LSLOTS);
+      uint32_t te_phase[2] = {0, 0}, ef_phase = 0;
+      const uint32_t d0 = tmem_base, d1 = tmem_base + 256;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int g = 0; g < 4; ++g) {
+          mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
+          tc_fence_after();
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, false, smem_base + M2_OFF_L + lr.idx * 2 * CT_A_HALF, 0u, d0, kc == 0, split, B.lempty(lr.idx));
+            lr.advance();
+          }
+          umma_commit(B.tfull(0));
+          if (g == 0) { mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1; tc_fence_after(); }
+          for (int kc = 0; kc < 4; ++kc) {      // fc2: A = GELU(fc1) chunk kc, in place in d0's columns [64 kc, 64 kc + 64)
+            mbar_wait(B.efull(kc), ef_phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, true, 0u, d0 + 64u * kc, d1, g == 0 && kc == 0, split, 0u);
+          }
+          ef_phase ^= 1;
+        }
+        umma_commit(B.tfull(1));
+      }
+    }
+  } else {
+    // ---------------- epilogue: 8 warps; lane quarter q, column half hsel ----------------
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* wscr = smem_gen + M2_OFF_T + e * 4096;       // this warp's [32 rows][32 cols] fp32 transpose scratch
+    const int sub = lane >> 3, q8 = lane & 7;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int g = 0; g < 4; ++g) {
+        mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          const uint32_t ta = tmem_base + lane_off + c * 64 + hsel * 32;
+          tmem_ld_32x32(ta, rr);
+          tmem_ld_wait();
+          epi_to_tmem<ZS_ACT_GELU>(ta, rr, p.bias + g * 256 + c * 64 + hsel * 32, split);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(B.efull(c));
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(0));
+      }
+      mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
+      tc_fence_after();
+      // x += fc2 + b2: every 32 x 32 accumulator block is transposed inside its warp so that global memory sees whole
+      // 128-byte row segments (as chain_lin_kernel)
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + hsel * 32;
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + 256 + lane_off + col0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        __syncwarp();
+        const int n0 = col0 + 4 * q8;
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0));
+        float4 xin[8];                       // all residual loads first: they alias the stores below
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = t * 128 + q * 32 + 4 * i + sub;
+          xin[i] = *reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + n0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub;
+          const int mm = t * 128 + q * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+          if (mm < p.M)
+            *reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + n0) =
+                make_float4(xin[i].x + a.x + bv.x, xin[i].y + a.y + bv.y, xin[i].z + a.z + bv.z, xin[i].w + a.w + bv.w);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(B.tempty(1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// logit = MLPBlocks([xyz, LN(x)]); chunk / blob order as chain_occ_kernel
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_occ2_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();
+  Bars5 B{smem_base + CT_OFF_BAR};
+  float* row_scratch = reinterpret_cast<float*>(smem_gen + CT_OFF_BAR + 256);   // [128] partial dots
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const uint32_t tmem_base = chain2_setup(B, smem_gen, smem_base, warp, O2_WSLOTS);
+  const int n_tiles = (p.M + 127) / 128;
+
+  if (warp < 4) {
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    const int sub = lane >> 4, q = lane & 15;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 32;
+      float sc, sh;
+      if (t + (int)gridDim.x < n_tiles) prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      warp_ln_stats(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      for (int rep = 0; rep < 4; ++rep) {
+        for (int kc = 0; kc < 5; ++kc) {
+          if (kc < 4) {
+            fetch_chunk_co(p.x, p.ldx, m0, p.M, kc * 64, lane, buf);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = m0 + 2 * j + sub;
+              buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (q == 0 && m < p.M) {
+                const float* pp = p.points + (int64_t)m * 3;
+                buf[j] = make_float4(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2), 0.f);
+              }
+            }
+          }
+          mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+          store_chunk_co(smem_gen + O2_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, kc < 4, sc, sh,
+                         (kc < 4 && p.ln_w) ? p.ln_w + kc * 64 : nullptr, (kc < 4 && p.ln_b) ? p.ln_b + kc * 64 : nullptr, split);
+          fence_proxy_async_smem();
+          mbar_arrive(B.lfull(lr.idx));
+          lr.advance();
+        }
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(O2_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) w_stream2(B, smem_base, wr, p.blob, 48, split);
+    }
+  } else if (warp == 12) {
+    if (lane == 0) {
+      Ring wr(O2_WSLOTS), lr(CT_LSLOTS);
+      uint32_t te_phase[2] = {0, 0}, ef_phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int l = 0; l < 8; ++l) {
+          const int half = l & 1;
+          const uint32_t d = tmem_base + half * 256, dprev = tmem_base + (half ^ 1) * 256;
+          mbar_wait(B.tempty(half), te_phase[half] ^ 1); te_phase[half] ^= 1;
+          tc_fence_after();
+          const int nL = (l & 1) ? 0 : 5, nE = l == 0 ? 0 : 4;
+          for (int i = 0; i < nL; ++i) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, false, smem_base + O2_OFF_L + lr.idx * 2 * CT_A_HALF, 0u, d, i == 0, split, B.lempty(lr.idx));
+            lr.advance();
+          }
+          for (int i = 0; i < nE; ++i) {          // A = the previous layer's activations, in place in the other half
+            mbar_wait(B.efull(i), ef_phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, true, 0u, dprev + 64u * i, d, nL == 0 && i == 0, split, 0u);
+          }
+          if (nE) ef_phase ^= 1;
+          umma_commit(B.tfull(half));
+        }
+      }
+    }
+  } else {
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m = t * 128 + row;
+      for (int l = 0; l < 8; ++l) {
+        const int half = l & 1;
+        mbar_wait(B.tfull(half), tf_phase[half]); tf_phase[half] ^= 1;
+        tc_fence_after();
+        float dot = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          const uint32_t ta = tmem_base + half * 256 + lane_off + c * 64 + hsel * 32;
+          tmem_ld_32x32(ta, rr);
+          tmem_ld_wait();
+          const float* bl = p.bias + l * 256 + c * 64 + hsel * 32;
+          if (l < 7) {
+            epi_to_tmem<ZS_ACT_SOFTPLUS100>(ta, rr, bl, split);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(B.efull(c));
+          } else {
+            const float* w8 = p.bias2 + c * 64 + hsel * 32;
+            float2 dot2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bl) + j), w4 = __ldg(reinterpret_cast<const float4*>(w8) + j);
+              const float2 s0 = fast_softplus100_2(add2(make_float2(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1])), make_float2(b4.x, b4.y)));
+              const float2 s1 = fast_softplus100_2(add2(make_float2(__uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3])), make_float2(b4.z, b4.w)));
+              dot2 = fma2(s0, make_float2(w4.x, w4.y), dot2);
+              dot2 = fma2(s1, make_float2(w4.z, w4.w), dot2);
+            }
+            dot += dot2.x + dot2.y;
+          }
+        }
+        if (l == 7) {
+          // nothing reads this half any more: release it; the activations of layers < 7 stay until the next layer's MMAs
+          // have read them, which the in-order tensor pipe and the next tempty wait of that half guarantee
+          tc_fence_before();
+          mbar_arrive(B.tempty(half));
+          if (hsel == 1) row_scratch[row] = dot;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (hsel == 0 && m < p.M) {
+            float v = dot + row_scratch[row] + p.b8;
+            p.out[m] = p.apply_sigmoid ? 1.0f / (1.0f + __expf(-v)) : v;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        } else {
+          tc_fence_before();
+          mbar_arrive(B.tempty(half));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
+static int g_chain_variant = 1;   // zs_chain_mlp_fwd / zs_chain_occ_fwd: 1 = activations in tensor memory (chain_*2_kernel), 0 = ring E
 
 static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name, int threads = CT_THREADS) {
   p.trace = g_chain_trace;
@@ -2081,7 +2474,7 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   ChainParams p{};
   p.x = x; p.ldx = ldx; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
-  return chain_launch(chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
+  return chain_launch(g_chain_variant ? chain_mlp2_kernel : chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
 }
 
 extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float ln_eps, const void* blob, int n_tiles,
@@ -2105,6 +2498,8 @@ extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float
 // debug: while `buf` (device, [3][512] uint64) is non-null every chained kernel records (clock64 << 8 | tag) events of the
 // MMA thread, loader thread 0 and epilogue warp 4 lane 0 of CTA 0 into it (tools/trace_chain.py).  Not thread-safe.
 extern "C" int zs_debug_chain_trace(unsigned long long* buf) { g_chain_trace = buf; return ZS_OK; }
+// A/B switch of the two MLP kernels (tools/diag_decoder.py, tests): 1 (default) = TMEM-resident activations, 0 = smem ring E
+extern "C" int zs_debug_chain_variant(int v) { g_chain_variant = v != 0; return ZS_OK; }
 
 extern "C" int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
                                  float scale, float* O, int precision, void* stream) {
@@ -2133,7 +2528,7 @@ extern "C" int zs_chain_occ_fwd(const float* x, int ldx, const float* points, in
   p.x = const_cast<float*>(x); p.ldx = ldx; p.points = points; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = biases; p.bias2 = w8; p.b8 = b8; p.out = out;
   p.apply_sigmoid = apply_sigmoid; p.precision = precision;
-  return chain_launch(chain_occ_kernel, p, as_stream(stream), "zs_chain_occ_fwd");
+  return chain_launch(g_chain_variant ? chain_occ2_kernel : chain_occ_kernel, p, as_stream(stream), "zs_chain_occ_fwd");
 }
 
 extern "C" size_t zs_chain_qkvattn_blob_bytes(void) { return (size_t)4 * 4 * 2 * CT_TILE_BYTES; }
