@@ -163,6 +163,50 @@ def device_cc():
     return 0
 
 
+# ---- evaluation ops (marching cubes, surface sampling, Chamfer, statistics): the oracle's numpy / C restatements ----------------
+def marching_cubes(vol, iso):
+    from oracle import eval3d as E
+    v, f = E.marching_cubes(vol.detach().cpu().numpy(), float(iso))
+    return torch.from_numpy(v).float(), torch.from_numpy(f.astype("int32"))
+
+
+def mesh_sample(verts, faces, num, vscale=1.0, voffset=0.0, seed=0):
+    import numpy as np
+    from oracle import eval3d as E
+    if faces.shape[0] == 0:
+        return torch.zeros(num, 3)
+    v = verts.double().numpy() * vscale + voffset
+    return torch.from_numpy(E.sample_surface(v, faces.numpy().astype(np.int64), num, np.random.RandomState(seed))).float()
+
+
+def chamfer_nn(xyz1, xyz2):
+    from oracle import eval3d as E
+    d1, d2, i1, i2 = E.chamfer_nn(xyz1.numpy(), xyz2.numpy())
+    return torch.from_numpy(d1), torch.from_numpy(d2), torch.from_numpy(i1), torch.from_numpy(i2)
+
+
+def chamfer_stats(sq1, sq2, thresholds, squared=True):
+    d1, d2 = (sq1.sqrt(), sq2.sqrt()) if squared else (sq1, sq2)
+    th = torch.tensor(list(thresholds), dtype=torch.float32)
+    p = (d1.unsqueeze(-1) < th).float().mean(dim=1)
+    r = (d2.unsqueeze(-1) < th).float().mean(dim=1)
+    return d1.mean(dim=1), d2.mean(dim=1), p, r
+
+
+def mean_axis1(x):
+    return x.mean(dim=1)
+
+
+EVAL_OPS = ("marching_cubes", "mesh_sample", "chamfer_nn", "chamfer_stats", "mean_axis1")
+
+
+def install_eval(monkeypatch):
+    import zeroshape_b200.ops as ops
+    g = globals()
+    for name in EVAL_OPS:
+        monkeypatch.setattr(ops, name, g[name])
+
+
 def install(monkeypatch):
     """Patch zeroshape_b200.ops in place (pytest monkeypatch restores it)."""
     import zeroshape_b200.ops as ops

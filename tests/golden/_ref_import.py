@@ -296,7 +296,11 @@ def install_fake_timm_factory():
 def reference_opt(device="cpu"):
     """EasyDict with the fields graph_shape.Graph / Loss read (options/shape.yaml defaults)."""
     from utils.util import EasyDict as edict
-    return edict(dict(
+    return edict(reference_opt_dict(device))
+
+
+def reference_opt_dict(device="cpu"):
+    return (dict(
         device=device, H=224, W=224,
         pretrain=dict(depth=None),
         arch=dict(num_heads=8, latent_dim=256, win_size=16,

@@ -18,6 +18,12 @@ class Graph(nn.Module):
     def __init__(self, opt):
         super().__init__()
         self.dpt_depth = DPTDepthModel(backbone="vitb_rn50_384")
+        # graph_depth.py:16-19: options/depth.yaml:17 points at the omnidata DPT-hybrid checkpoint the depth estimator is
+        # fine-tuned from; without it training would silently start from a random initialisation
+        pretrained = getattr(getattr(opt.arch, "depth", None), "pretrained", None)
+        if pretrained is not None:
+            checkpoint = torch.load(pretrained, map_location="cpu")
+            self.dpt_depth.load_state_dict(checkpoint["model_state_dict"])
         self.with_intr = opt.loss_weight.intr is not None
         if self.with_intr:
             self.intr_feat_channels = 768

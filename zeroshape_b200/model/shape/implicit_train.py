@@ -242,28 +242,43 @@ class ImplicitTrainFn(torch.autograd.Function):
         return (None, dz if ctx.need_dz else None, None) + grads
 
 
-class FusedAdamW:
-    """torch.optim.AdamW semantics on the zs_adamw_f32 kernel (model/shape_engine.py:132: AdamW, betas (0.9, 0.95))."""
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics on the zs_adamw_multi_f32 kernel (model/shape_engine.py:75-136: AdamW, betas (0.9, 0.95),
+    four parameter groups with lr / lr_ft and zero weight decay for the no-decay sets).
+
+    A real `torch.optim.Optimizer`: `param_groups` (per-group lr / betas / eps / weight_decay, so CosineAnnealingLR and the
+    reference's group construction work), per-parameter `state` {step, exp_avg, exp_avg_sq} (a parameter whose gradient is
+    None in early steps gets its own bias correction), `state_dict` / `load_state_dict` (util.save_checkpoint serialises every
+    `optim*` attribute).  One launch per (group, step count) bucket."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
-        self.params = [p for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.state = {id(p): (torch.zeros_like(p), torch.zeros_like(p)) for p in self.params}
-        self.steps = 0
-
-    def zero_grad(self, set_to_none=True):
-        for p in self.params:
-            p.grad = None
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
-    def step(self):
-        self.steps += 1
-        live = [p for p in self.params if p.grad is not None]
-        grads = [p.grad.contiguous() for p in live]               # kept alive until the launch is enqueued
-        ops.adamw_step_multi([p.detach() for p in live], grads, [self.state[id(p)][0] for p in live],
-                             [self.state[id(p)][1] for p in live], self.lr, self.betas[0], self.betas[1], self.eps,
-                             self.weight_decay, self.steps)
-        for p in live:
-            # the kernel wrote through the raw pointer: bump the version counter so that the packed-weight caches
-            # (keyed on data_ptr / _version) re-pack, exactly as after a torch optimizer step
-            torch.autograd.graph.increment_version(p)
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            buckets = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] = int(st["step"]) + 1
+                buckets.setdefault(st["step"], []).append(p)
+            for step, ps in buckets.items():
+                grads = [p.grad.contiguous() for p in ps]             # kept alive until the launch is enqueued
+                ops.adamw_step_multi([p.detach() for p in ps], grads, [self.state[p]["exp_avg"] for p in ps],
+                                     [self.state[p]["exp_avg_sq"] for p in ps], float(group["lr"]), group["betas"][0],
+                                     group["betas"][1], group["eps"], group["weight_decay"], step)
+                for p in ps:
+                    # the kernel wrote through the raw pointer: bump the version counter so that the packed-weight caches
+                    # (keyed on data_ptr / _version) re-pack, exactly as after a torch optimizer step
+                    torch.autograd.graph.increment_version(p)
+        return loss

@@ -62,9 +62,29 @@ class CoordEncRes(nn.Module):
             raise NotImplementedError("win_size 32 variant is not the shipped configuration (options/shape.yaml:23)")
         latent = opt.arch.latent_dim
         self.encoder = _tv_resnet50()
+        # seen_coord_enc.py:148 starts the trunk from torchvision's ImageNet weights (`resnet50(pretrained=True)`, a download).
+        # No network here: the same state_dict is taken from a local file -- `opt.arch.depth.resnet50_weights` or the
+        # environment variable ZEROSHAPE_RESNET50_WEIGHTS (torchvision's resnet50-*.pth) -- loaded before `fc` is replaced,
+        # exactly like the reference.  Checkpoint-driven inference (demo.py / evaluate.py) overwrites every weight anyway.
+        import os
+        path = getattr(opt.arch.depth, "resnet50_weights", None) if hasattr(opt.arch, "depth") else None
+        path = path or os.environ.get("ZEROSHAPE_RESNET50_WEIGHTS")
+        self.imagenet_init = False
+        if path:
+            sd = torch.load(path, map_location="cpu")
+            sd = sd.get("state_dict", sd) if isinstance(sd, dict) else sd
+            missing, unexpected = self.encoder.load_state_dict({k: v for k, v in sd.items() if not k.startswith("fc.")}, strict=False)
+            if missing:
+                raise RuntimeError(f"CoordEncRes: {path} lacks ResNet-50 trunk tensors: {missing[:4]} ...")
+            self.imagenet_init = True
+        self._warned_init = False
         self.encoder.fc = nn.Sequential(Bottleneck_Conv(2048), Bottleneck_Conv(2048), nn.Linear(2048, latent))
         self.depth_feat_proj = nn.Sequential(Bottleneck_Conv(1024), Bottleneck_Conv(1024), nn.Conv2d(1024, latent, 1))
         self._cache = PackCache(self)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._loaded_checkpoint = True          # weights come from a checkpoint: the initialisation no longer matters
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _cbr(self, x, conv, bn, tag, act, stride=1, pad=0, res=None):
         w, b = self._cache.get(tag, lambda: fold_bn_ohwi(conv.weight, bn))
@@ -78,6 +98,13 @@ class CoordEncRes(nn.Module):
             from .seen_coord_enc_train import CoordEncTrainFn, train_forward
             params = list(self.parameters())
             if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                if not self.imagenet_init and not self._warned_init and not getattr(self, "_loaded_checkpoint", False):
+                    import warnings
+                    warnings.warn("CoordEncRes: training starts with a ResNet-50 trunk that was neither initialised from ImageNet "
+                                  "weights (the reference: torchvision resnet50(pretrained=True), seen_coord_enc.py:148) nor loaded "
+                                  "from a checkpoint -- set opt.arch.depth.resnet50_weights or ZEROSHAPE_RESNET50_WEIGHTS",
+                                  stacklevel=2)
+                    self._warned_init = True
                 return CoordEncTrainFn.apply(self, coord_nhwc, *params)
             with torch.no_grad():
                 return train_forward(self, coord_nhwc.float().contiguous())[0]

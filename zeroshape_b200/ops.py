@@ -60,17 +60,23 @@ def gemm(a, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None):
 
 
 class PackedWeight:
-    """fp32 W[N,K] packed for the tcgen05 GEMM (hi/lo bf16, UMMA swizzled tiles).  Re-packs itself when the
-    source tensor is modified in place (optimizer step / load_state_dict)."""
+    """fp32 W[N,K] packed for the tcgen05 GEMM (hi/lo bf16, UMMA swizzled tiles).  `w` may be a tensor or a zero-argument
+    callable returning the CURRENT weight (e.g. `lambda: param.detach()`): the blob is re-packed whenever the live tensor's
+    storage, version, shape or device changed (in-place optimizer steps, load_state_dict(assign=True), module.to(device),
+    EMA swaps that re-assign param.data)."""
 
     def __init__(self, w):
-        self.src = w
+        self._get = w if callable(w) else (lambda: w)
         self.key = None
         self.blob = None
 
+    @property
+    def src(self):
+        return self._get()
+
     def get(self):
-        w = self.src
-        key = (w.data_ptr(), w._version, tuple(w.shape))
+        w = self._get()
+        key = (w.data_ptr(), w._version, tuple(w.shape), w.device)
         if self.key != key:
             wd = w.detach()
             if wd.dtype != torch.float32 or wd.stride(-1) != 1 or not wd.is_cuda:
@@ -289,12 +295,17 @@ def _encoder_tc():
 
 
 def _packed_of(w):
-    """tcgen05 operand image of a weight matrix / OHWI filter, cached on the tensor object per version."""
+    """tcgen05 operand image of a weight matrix / OHWI filter, cached on the tensor object.  The cache reads the LIVE tensor
+    on every use (PackedWeight above), so re-assigning `param.data` after a first forward cannot leave a stale image."""
     pw = getattr(w, "_zs_packed", None)
     if pw is None:
-        w2 = w.detach()
-        w2 = w2.reshape(w2.shape[0], -1) if w2.dim() != 2 else w2
-        pw = PackedWeight(w2)                # re-packs itself when the (shared) version counter moves
+        import weakref
+        ref = weakref.ref(w)
+
+        def live():
+            t = ref().detach()
+            return t.reshape(t.shape[0], -1) if t.dim() != 2 else t
+        pw = PackedWeight(live)
         w._zs_packed = pw
     return pw
 

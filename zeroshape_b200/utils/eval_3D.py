@@ -8,8 +8,10 @@ Reference functions mirrored (file:line in the reference tree):
   brute_force_search     :140-170                    eval_metrics_BF       :172-207
   eval_metrics           :209-213                    compute_fscore        :215-231
   convert_to_explicit    :233-263                    chamfer_distance      :265-269
-Not mirrored: ICP (:271-284, off by default, options/shape.yaml:53) and the attention movie
-(:47-80, visualisation).
+  standardize_pc         :83-91                      ICP                   :271-284 (opt.eval.icp, off by default)
+The attention movie of compute_level_grid(vis_attn=True) (:47-80) is `attention_movie` below: only the 17 x 17 shown columns
+are evaluated.  Side effects on `var` follow the reference: eval_vox, mesh_pred, dpc_pred, dpc.points, attn_vis (vis_only),
+cd_acc, cd_comp, f_score.
 """
 import numpy as np
 import torch
@@ -156,6 +158,15 @@ def show_att_on_image(img, mask):
 
 
 @torch.no_grad()
+def standardize_pc(pc):
+    """Centre and scale to RMS radius 1/2 (utils/eval_3D.py:83-91; unused by the reference's own flows, kept for API parity)."""
+    assert pc.dim() == 3
+    z = pc - pc.mean(dim=1, keepdim=True)
+    rms = z.pow(2).sum(dim=2, keepdim=True).sum(dim=1, keepdim=True).div(pc.shape[1]).sqrt()
+    return z / (rms * 2)
+
+
+@torch.no_grad()
 def normalize_pc(pc):
     """Centre and scale by max(x-extent, y-extent) + 1e-7 (utils/eval_3D.py:93-102; z ignored)."""
     assert pc.dim() == 3
@@ -201,15 +212,39 @@ def chamfer_distance(opt, X1, X2):
     return d1.sqrt(), d2.sqrt(), i1, i2
 
 
-def _predict_clouds(opt, var, impl_network, seed=0):
+def ICP(opt, X1, X2, num_iter=50):
+    """Point-to-point ICP of X1 onto X2, [B,N,3] each (utils/eval_3D.py:271-284): nearest neighbours from the Chamfer kernel,
+    Kabsch rotation from a batched SVD.  Only run when opt.eval.icp is set (options/shape.yaml:53 default false)."""
+    assert len(X1) == len(X2)
+    for _ in range(num_iter):
+        _, _, idx, _ = chamfer_distance(opt, X1, X2)
+        corr = torch.gather(X2, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+        t1, t2 = X1.mean(dim=-2, keepdim=True), corr.mean(dim=-2, keepdim=True)
+        U, _, Vh = torch.linalg.svd((X1 - t1).transpose(1, 2) @ (corr - t2), full_matrices=False)
+        V = Vh.transpose(1, 2)
+        R = V @ U.transpose(1, 2)
+        R[R.det() < 0, 2] *= -1
+        X1 = (X1 - t1) @ R.transpose(1, 2) + t2
+    return X1
+
+
+def _predict_clouds(opt, var, impl_network, seed=0, vis_attn=False):
     points_n = opt.eval.vox_res + 1
     rmin, rmax = opt.eval.range
     B = len(var.idx)
-    if hasattr(impl_network, "grid_occupancy"):
+    if vis_attn:       # the reference passes vis_only as vis_attn (utils/eval_3D.py:108-111)
+        level_vox, frames = compute_level_grid(opt, impl_network, var.latent_depth, var.latent_semantic,
+                                               get_dense_3D_grid(opt, var), var.rgb_input_map, True)
+        if frames:
+            var.attn_vis = frames
+    elif hasattr(impl_network, "grid_occupancy"):
         level_vox = impl_network.grid_occupancy(var.latent_depth.float(), points_n, float(rmin), float(rmax))
     else:
         level_vox, _ = compute_level_grid(opt, impl_network, var.latent_depth, var.latent_semantic,
                                           get_dense_3D_grid(opt, var), var.rgb_input_map, False)
+    # utils/eval_3D.py:112: the query grid as [B, (N+1)^3, 3] (one 26 MB dense_grid launch at vox_res 128; the decoder pass
+    # itself regenerates its points per slab and never reads this tensor)
+    var.eval_vox = get_dense_3D_grid(opt, var).view(B, -1, 3)
     meshes, clouds = [], []
     for b in range(B):
         v, f = ops.marching_cubes(level_vox[b].contiguous(), 0.5)
@@ -227,11 +262,13 @@ def _predict_clouds(opt, var, impl_network, seed=0):
 
 @torch.no_grad()
 def eval_metrics_default(opt, var, impl_network, vis_only=False):
-    _predict_clouds(opt, var, impl_network)
+    _predict_clouds(opt, var, impl_network, vis_attn=vis_only)
     var.dpc_pred = normalize_pc(var.dpc_pred)
     var.dpc.points = normalize_pc(var.dpc.points)
     if vis_only:
         return
+    if opt.eval.get("icp", False) if hasattr(opt.eval, "get") else getattr(opt.eval, "icp", False):
+        var.dpc_pred = ICP(opt, var.dpc_pred, var.dpc.points)
     dist_acc, dist_comp, _, _ = chamfer_distance(opt, X1=var.dpc_pred, X2=var.dpc.points)
     var.f_score = compute_fscore(dist_acc, dist_comp, opt.eval.f_thresholds)
     assert dist_acc.shape[1] == opt.eval.num_points
@@ -278,7 +315,7 @@ def brute_force_search(pc_pred, pc_gt, f_thresholds=[0.005, 0.01, 0.02, 0.05, 0.
 
 @torch.no_grad()
 def eval_metrics_BF(opt, var, impl_network, vis_only=False):
-    _predict_clouds(opt, var, impl_network)
+    _predict_clouds(opt, var, impl_network, vis_attn=vis_only)
     if vis_only:
         return
     cd_acc, cd_comp, f_score = [], [], []
