@@ -60,3 +60,57 @@ def test_sharded_grid_equals_single_rank(tmp_path):
     for r in range(world):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert res["ok"] and res["shape"] == (1, 7, 7, 7)
+
+
+def _ddp_worker(rank, world, port, out):
+    """DistributedDataParallel over the decoder's custom autograd tape (CPU stand-ins for the kernels): DDP's gradient hooks
+    must see every parameter gradient the hand-written backward returns."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops
+        import zeroshape_b200.ops as ops
+        for name in fake_ops.TRAIN_OPS:
+            setattr(ops, name, getattr(fake_ops, name))
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        from zeroshape_b200.model.shape.implicit import Implicit
+        from oracle.implicit import implicit_init
+        net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8,
+                       skip_in=[2, 4, 6], pos_perlayer=False, drop_path=0.0)
+        net.load_state_dict(implicit_init(seed=31))
+        net.train()
+        ddp = DDP(net)
+        g = torch.Generator().manual_seed(9)
+        lat, pts = torch.randn(world, 197, 256, generator=g), torch.rand(world, 23, 3, generator=g) * 2 - 1
+        wgt = torch.randn(world, 23, generator=g)
+        logits, _ = ddp(lat[rank:rank + 1], None, pts[rank:rank + 1])
+        (logits * wgt[rank:rank + 1]).sum().backward()
+        if rank == 0:
+            torch.save({n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}, out)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_over_decoder_tape_gloo(tmp_path):
+    """world_size 2: DDP-averaged gradients == mean of the per-sample gradients of torch autograd over the oracle."""
+    import socket
+    from oracle.implicit import implicit_forward, implicit_init
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    sd = implicit_init(seed=31)
+    g = torch.Generator().manual_seed(9)
+    lat, pts = torch.randn(2, 197, 256, generator=g), torch.rand(2, 23, 3, generator=g) * 2 - 1
+    wgt = torch.randn(2, 23, generator=g)
+    ref = {k: v.clone().requires_grad_(k != "pos_embed") for k, v in sd.items()}
+    logits, _ = implicit_forward(ref, lat, pts)
+    ((logits * wgt).sum() / 2).backward()
+    assert len(got) == len(ref) - 1
+    for k, v in got.items():
+        assert ((v - ref[k].grad).norm() / ref[k].grad.norm().clamp_min(1e-30)).item() < 2e-4, k
