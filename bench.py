@@ -267,6 +267,134 @@ def run_ours(args, rank, world, dev):
 
 
 # ---------------------------------------------------------------------------------------------------
+def run_shard(args, rank, world, dev, graph=None, steps=None):
+    """BASELINE.json config 4: ONE batch of `--shapes` images at vox_res 128, the work of every shape sharded over
+    the ranks.  Per step: each rank encodes its share of the images -> all_gather of the latents [B,197,256] (1.6 MB) -> every
+    rank decodes its x-slab (+ one halo slice) of EVERY shape and runs marching cubes on its slab -> all_gather of the mesh parts
+    (sizes, then padded vertex / face buffers; zeroshape_b200/parallel.py) -> each rank samples the 10k-point clouds of its share.
+    Strong scaling: the batch is fixed, `value` = shapes / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from zeroshape_b200 import ops
+    from zeroshape_b200._native import lib
+    from zeroshape_b200.model.compute_graph.graph_shape import Graph
+    from zeroshape_b200.parallel import slab_meshes, gather_meshes, face_set
+    from zeroshape_b200.utils.util import EasyDict
+    n = args.vox_res + 1
+    rmin, rmax = -1.5, 1.5
+    B = args.shapes
+    steps = steps or args.steps
+    if B % world:
+        raise SystemExit(f"bench.py --mode shard: --shapes {B} must be a multiple of the number of ranks {world}")
+    share = B // world
+    opt = make_opt(dev, args.vox_res)
+    if graph is None:
+        torch.manual_seed(0)
+        graph = Graph(opt).to(dev).eval()
+        net = graph.impl_network
+        net.engine, net.precision = args.engine, args.precision
+        rgb0, mask0 = synthetic_images(1, 1000)
+        with torch.no_grad():
+            var = graph.forward(opt, EasyDict(idx=torch.arange(1), rgb_input_map=rgb0.to(dev), mask_input_map=mask0.to(dev), pose_gt=False),
+                                training=False, get_loss=False)
+            g = torch.Generator().manual_seed(5)
+            probe = (torch.rand(1, 8192, 3, generator=g) * 3 - 1.5).to(dev)
+            lg, _ = net(var.latent_depth, None, probe, need_attn=False)
+            net.impl_mlp.layers[-1].bias -= lg.median()
+    net = graph.impl_network
+    rgb_all, mask_all = synthetic_images(B, 1000)            # the same batch on every rank; a rank uploads only its share
+    rgb_h = rgb_all[rank * share:(rank + 1) * share].contiguous().pin_memory()
+    mask_h = mask_all[rank * share:(rank + 1) * share].contiguous().pin_memory()
+    out_h = torch.empty(share, 10000, 3).pin_memory()
+    coll_events = []
+
+    def step(record=True):
+        rgb, mask = rgb_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        var = EasyDict(idx=torch.arange(share), rgb_input_map=rgb, mask_input_map=mask, pose_gt=False)
+        var = graph.forward(opt, var, training=False, get_loss=False)
+        lat_local = var.latent_depth.contiguous()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        if world > 1:
+            parts = [torch.empty_like(lat_local) for _ in range(world)]
+            dist.all_gather(parts, lat_local)
+            latents = torch.cat(parts, dim=0)
+        else:
+            latents = lat_local
+        ev[1].record()
+        local = slab_meshes(net, latents, n, rmin, rmax, rank, world)
+        ev[2].record()
+        meshes = gather_meshes(local)
+        ev[3].record()
+        if record:
+            coll_events.append(ev)
+        clouds = [ops.mesh_sample(v, f, 10000, (rmax - rmin) / n, rmin, seed=rank * share + i)
+                  for i, (v, f) in enumerate(meshes[rank * share:(rank + 1) * share])]
+        out_h.copy_(torch.stack(clouds), non_blocking=True)
+        return meshes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            meshes = step(False)
+        # correctness of the sharded path on this hardware: shape 0's gathered mesh == the unsharded mesh, as a set of faces
+        mesh_equal = None
+        if world > 1:
+            var = graph.forward(opt, EasyDict(idx=torch.arange(share), rgb_input_map=rgb_h.to(dev), mask_input_map=mask_h.to(dev),
+                                              pose_gt=False), training=False, get_loss=False)
+            lat0 = [torch.empty_like(var.latent_depth) for _ in range(world)]
+            dist.all_gather(lat0, var.latent_depth.contiguous())
+            if rank == 0:
+                full = slab_meshes(net, lat0[0][:1], n, rmin, rmax, 0, 1)[0]
+                mesh_equal = bool(face_set(*meshes[0]) == face_set(*full) and meshes[0][1].shape[0] == full[1].shape[0])
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        l0 = lib.zs_launch_count()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            meshes = step(True)
+        t1.record()
+        barrier()
+        launches = lib.zs_launch_count() - l0
+        clocks = sampler.stop()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        coll = torch.tensor([sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e in coll_events) / max(1, len(coll_events))], device=dev)
+        dec = torch.tensor([sum(e[1].elapsed_time(e[2]) for e in coll_events) / max(1, len(coll_events))], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(coll, op=dist.ReduceOp.MAX)
+            dist.all_reduce(dec, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    faces = int(sum(f.shape[0] for _, f in meshes))
+    verts = int(sum(v.shape[0] for v, _ in meshes))
+    return {
+        "metric": METRIC, "value": B * steps / (ms * 1e-3), "unit": "shapes/s", "n_gpus": world, "steps": steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "fp16x3->f32acc", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 4 (demo.py, vox_res {args.vox_res}, batch {B}): every shape's ({args.vox_res}+1)^3 query grid "
+                               f"split into {world} x-slab(s) with a one-slice halo, per-slab marching cubes, all_gather of the mesh parts; "
+                               f"one image encoded per rank share, latents all_gathered; random-init weights",
+                   "vox_res": args.vox_res, "shapes_per_batch": B, "parallelism": f"x-slab x{world} (strong scaling)",
+                   "l2_policy": "per-step working set re-written each step (no cached outputs)"},
+        "latency_ms_per_batch": ms / steps, "collective_ms": coll.item(), "slab_decode_mc_ms": dec.item(),
+        "collectives_per_step": 0 if world == 1 else 5,
+        "mesh_equal_to_unsharded": mesh_equal, "mesh_faces_per_batch": faces, "mesh_vertices_per_batch": verts,
+        "limiter": "per-rank: encoder share + redundant latent-side prep of all shapes + slab decode; collective = waiting for the "
+                   "slowest rank plus two host syncs for the mesh sizes (wire time of ~30 MB over NVLink is < 0.1 ms)",
+        "e2e": {"value": B * steps / (ms * 1e-3), "unit": "shapes/s", "h2d_bytes_per_step": (rgb_h.numel() + mask_h.numel()) * 4 * world,
+                "d2h_bytes_per_step": out_h.numel() * 4 * world,
+                "note": "the timed step IS end to end: pinned host images -> device, point clouds -> pinned host, inside the timed region"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
 def run_train_decoder(args, rank, world, dev):
     """BASELINE.json config 3, decoder slice only (the encoder backward does not exist yet): one step = Implicit forward on
     B x 4096 GT sample points + BCE shape loss + backward + fused AdamW, latents given (as if the encoders were frozen)."""
@@ -541,7 +669,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vox-res", type=int, default=128)
     ap.add_argument("--shapes", type=int, default=8, help="shapes per GPU per step (SURVEY.md section 8d: B = 8 images in flight)")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train", "train-decoder", "eval"],
+    ap.add_argument("--mode", default="infer", choices=["infer", "shard", "train", "train-decoder", "eval"],
                     help="train: BASELINE config 3 (full train_iteration, fwd + loss + bwd + AdamW); train-decoder: decoder slice only")
     ap.add_argument("--eval-shapes", type=int, default=256, help="mode eval: size of the synthetic evaluation set (all ranks together)")
     ap.add_argument("--brute-force", action="store_true", help="mode eval: the 6912-rotation pose search of evaluate.py (README protocol)")
@@ -557,6 +685,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-region", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
+    ap.add_argument("--no-shard", action="store_true", help="default mode: skip the extra slab-sharded (config 4) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -577,12 +706,24 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    if args.mode in ("train", "train-decoder", "eval"):
-        line = {"train": run_train, "train-decoder": run_train_decoder, "eval": run_eval}[args.mode](args, rank, world, dev)
+    if args.mode in ("train", "train-decoder", "eval", "shard"):
+        line = {"train": run_train, "train-decoder": run_train_decoder, "eval": run_eval, "shard": run_shard}[args.mode](args, rank, world, dev)
         if rank == 0:
             _emit(line, real_stdout)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
         return
     line = run_ours(args, rank, world, dev)
+    if not args.no_shard and args.shapes % world == 0:
+        # the north-star partitioning (BASELINE config 4) measured in the same run, on the same ranks: slab-sharded grid, per-slab
+        # marching cubes, NCCL all_gather of the mesh parts (`--mode shard` runs it alone, with the full step count)
+        shard = run_shard(args, rank, world, dev, steps=min(args.steps, 3))
+        line["shard_config4"] = {k: shard[k] for k in ("value", "unit", "scaling", "steps", "latency_ms_per_batch", "collective_ms",
+                                                       "slab_decode_mc_ms", "collectives_per_step", "mesh_equal_to_unsharded",
+                                                       "mesh_faces_per_batch", "limiter", "gpu_launches")}
+        line["shard_config4"]["workload"] = shard["config"]["workload"]
     if rank == 0:
         if not args.no_cpu_baseline:
             v, info = cpu_reference_shapes_per_s(args.vox_res, args.cpu_slices)

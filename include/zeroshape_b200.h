@@ -397,6 +397,15 @@ int zs_mc_count(const float* vol, int n, float iso, void* ws, int32_t* counts, v
 /* Pass 2: emit (after the caller read counts and allocated).  verts [V,3] fp32 in array-index units,
  * faces [F,3] int32.  Deterministic ordering (by edge id / cell id). */
 int zs_mc_emit(const float* vol, int n, float iso, void* ws, float* verts, int32_t* faces, void* stream);
+/* The same two passes on an x-SLAB vol [nx, n, n] of the (n)^3 grid (multi-GPU partitioning of SURVEY.md 8e A: the slab of
+ * slices [x0, x1) plus the one-slice halo x1): cells whose low corner lies in local slices 0 .. nx-2, so every cell of the grid
+ * is owned by exactly one slab; vertex x coordinates are emitted in GLOBAL index units (local slice + x_offset).  The y/z-edge
+ * vertices of the halo slice are emitted by both neighbours (bit-identical coordinates): seam vertices are duplicated, faces
+ * are not.  nx == n, x_offset == 0 reproduces zs_mc_count / zs_mc_emit. */
+size_t zs_mc_slab_ws_bytes(int nx, int n);
+int zs_mc_slab_count(const float* vol, int nx, int n, float iso, void* ws, int32_t* counts, void* stream);
+int zs_mc_slab_emit(const float* vol, int nx, int n, float iso, void* ws, float* verts, int32_t* faces, int x_offset,
+                    void* stream);
 /* Area-weighted surface sampling with an explicit counter-based RNG seed (replaces trimesh.sample).
  * ws: zs_mesh_sample_ws_bytes(F). points [S,3]; vertices are scaled v*vscale+voffset first
  * (eval_3D.py:252-255). */

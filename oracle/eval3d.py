@@ -55,23 +55,24 @@ for _e, (_a, _b) in enumerate(EDGES):
 
 
 def marching_cubes(vol, iso):
-    """vol [n,n,n] float -> (vertices float64 [V,3] in index units, faces int64 [F,3]).
+    """vol [nx,ny,nz] float (the reference passes cubes, utils/eval_3D.py:250; x-slabs are used by the multi-GPU tests)
+    -> (vertices float64 [V,3] in index units, faces int64 [F,3]).
     Ordering: vertices by (grid point linear index, axis x<y<z); faces by (cell linear index,
     table order) -- the same deterministic order the CUDA kernel uses, so outputs compare exactly."""
     vol = np.asarray(vol)
-    n = vol.shape[0]
-    assert vol.shape == (n, n, n)
+    assert vol.ndim == 3
+    nx, ny, nz = vol.shape
     inside = vol <= iso
     f64 = vol.astype(np.float64)
-    flags = np.zeros((n, n, n), dtype=np.int64)
+    flags = np.zeros((nx, ny, nz), dtype=np.int64)
     flags[:-1, :, :] |= (inside[:-1] != inside[1:]).astype(np.int64) * 1
     flags[:, :-1, :] |= (inside[:, :-1] != inside[:, 1:]).astype(np.int64) * 2
     flags[:, :, :-1] |= (inside[:, :, :-1] != inside[:, :, 1:]).astype(np.int64) * 4
     cnt = ((flags & 1) + ((flags >> 1) & 1) + ((flags >> 2) & 1)).reshape(-1)
-    vbase = np.concatenate([[0], np.cumsum(cnt)[:-1]]).reshape(n, n, n)
+    vbase = np.concatenate([[0], np.cumsum(cnt)[:-1]]).reshape(nx, ny, nz)
     # vertices
     verts = np.zeros((int(cnt.sum()), 3), dtype=np.float64)
-    ii, jj, kk = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
     for axis in range(3):
         sel = ((flags >> axis) & 1).astype(bool)
         rank = np.zeros_like(flags)

@@ -164,10 +164,24 @@ def device_cc():
 
 
 # ---- evaluation ops (marching cubes, surface sampling, Chamfer, statistics): the oracle's numpy / C restatements ----------------
-def marching_cubes(vol, iso):
+def marching_cubes(vol, iso, x_offset=0):
     from oracle import eval3d as E
     v, f = E.marching_cubes(vol.detach().cpu().numpy(), float(iso))
+    v = v.copy()
+    v[:, 0] += x_offset
     return torch.from_numpy(v).float(), torch.from_numpy(f.astype("int32"))
+
+
+def marching_cubes_count(vol, iso):
+    v, f = marching_cubes(vol, iso)
+    return (v, f), torch.tensor([v.shape[0], f.shape[0]], dtype=torch.int32)
+
+
+def marching_cubes_emit(vol, iso, ws, V, F, x_offset=0):
+    v, f = ws
+    v = v.clone()
+    v[:, 0] += x_offset
+    return v, f
 
 
 def mesh_sample(verts, faces, num, vscale=1.0, voffset=0.0, seed=0):
@@ -197,7 +211,7 @@ def mean_axis1(x):
     return x.mean(dim=1)
 
 
-EVAL_OPS = ("marching_cubes", "mesh_sample", "chamfer_nn", "chamfer_stats", "mean_axis1")
+EVAL_OPS = ("marching_cubes", "marching_cubes_count", "marching_cubes_emit", "mesh_sample", "chamfer_nn", "chamfer_stats", "mean_axis1")
 
 
 def install_eval(monkeypatch):

@@ -267,3 +267,36 @@ def test_pose_search_bvh_equals_dense(cuda):
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert torch.isfinite(a[0]) and torch.isfinite(a[1]) and a[2].shape == (6,)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_meshes_union_equals_full_mesh(cuda, world):
+    """SURVEY.md 8e A / BASELINE config 4 on the real kernels: the x-slab (+ one halo slice) decode and per-slab marching cubes
+    of every simulated rank, merged the way `parallel.gather_meshes` merges them, give the single-rank mesh as a set of faces."""
+    from oracle.implicit import implicit_init
+    from zeroshape_b200.model.shape.implicit import Implicit
+    from zeroshape_b200.parallel import slab_meshes, face_set, all_slab_bounds
+    from zeroshape_b200 import ops
+    net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                   pos_perlayer=False)
+    net.load_state_dict(implicit_init(seed=17))
+    net = net.to(cuda).eval()
+    lat = torch.randn(2, 197, 256, generator=torch.Generator().manual_seed(18)).to(cuda)
+    n = 33
+    full = slab_meshes(net, lat, n, -1.5, 1.5, 0, 1)
+    parts = [slab_meshes(net, lat, n, -1.5, 1.5, r, world) for r in range(world)]
+    for b in range(2):
+        v = torch.cat([parts[r][b][0] for r in range(world)])
+        base, fs = 0, []
+        for r in range(world):
+            fs.append(parts[r][b][1] + base)
+            base += parts[r][b][0].shape[0]
+        f = torch.cat(fs)
+        assert f.shape[0] == full[b][1].shape[0] and f.shape[0] > 500
+        assert face_set(v, f) == face_set(*full[b])
+        # seam vertices are the only duplicates
+        assert v.shape[0] >= full[b][0].shape[0] and v.shape[0] - full[b][0].shape[0] < 0.2 * full[b][0].shape[0] * world / 2
+    # the cubic entry point still equals the slab entry point with nx == n
+    occ = net.grid_occupancy(lat[:1], n, -1.5, 1.5)[0].contiguous()
+    v0, f0 = ops.marching_cubes(occ, 0.5)
+    assert torch.equal(f0, full[0][1]) and torch.equal(v0, full[0][0])

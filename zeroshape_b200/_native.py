@@ -103,6 +103,9 @@ SIGNATURES = {
     "zs_mc_ws_bytes": (c_size_t, [c_int]),
     "zs_mc_count": (c_int, [P, c_int, c_float, P, P, P]),
     "zs_mc_emit": (c_int, [P, c_int, c_float, P, P, P, P]),
+    "zs_mc_slab_ws_bytes": (c_size_t, [c_int, c_int]),
+    "zs_mc_slab_count": (c_int, [P, c_int, c_int, c_float, P, P, P]),
+    "zs_mc_slab_emit": (c_int, [P, c_int, c_int, c_float, P, P, P, c_int, P]),
     "zs_mesh_sample_ws_bytes": (c_size_t, [c_int]),
     "zs_mesh_sample": (c_int, [P, P, c_int, c_int, c_float, c_float, c_int, c_uint64, P, P, P]),
 }

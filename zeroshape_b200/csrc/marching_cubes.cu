@@ -100,8 +100,8 @@ struct McWs {
   uint8_t* cases;   // [n^3] cube case index of the cell at this low corner (0 if none)
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static McWs carve(void* ws, int n) {
-  size_t n3 = (size_t)n * n * n, nb = (n3 + 1023) / 1024;
+static McWs carve(void* ws, int nx, int n) {
+  size_t n3 = (size_t)nx * n * n, nb = (n3 + 1023) / 1024;
   uint8_t* p = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
   McWs w;
   w.vcnt = reinterpret_cast<int32_t*>(p); p += align_up(n3 * 4, 256);
@@ -113,15 +113,17 @@ static McWs carve(void* ws, int n) {
   return w;
 }
 
-__global__ void mc_classify_kernel(const float* __restrict__ vol, int n, float iso, McWs w) {
-  int64_t n3 = (int64_t)n * n * n;
+// vol is [nx, n, n] (an x-slab of the (n)^3 grid, or the whole grid when nx == n): cells whose low corner lies in slices
+// 0 .. nx-2, one vertex per crossed edge owned by its low corner
+__global__ void mc_classify_kernel(const float* __restrict__ vol, int nx, int n, float iso, McWs w) {
+  int64_t n3 = (int64_t)nx * n * n;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n3; idx += (int64_t)gridDim.x * blockDim.x) {
     int k = (int)(idx % n);
     int64_t t = idx / n;
     int j = (int)(t % n), i = (int)(t / n);
     auto in = [&](int di, int dj, int dk) { return vol[idx + ((int64_t)di * n + dj) * n + dk] <= iso; };
     bool c0 = in(0, 0, 0);
-    bool hx = i + 1 < n, hy = j + 1 < n, hz = k + 1 < n;
+    bool hx = i + 1 < nx, hy = j + 1 < n, hz = k + 1 < n;
     bool cx = hx ? in(1, 0, 0) : c0, cy = hy ? in(0, 1, 0) : c0, cz = hz ? in(0, 0, 1) : c0;
     int flags = (hx && cx != c0 ? 1 : 0) | (hy && cy != c0 ? 2 : 0) | (hz && cz != c0 ? 4 : 0);
     int cs = 0;
@@ -137,9 +139,9 @@ __global__ void mc_classify_kernel(const float* __restrict__ vol, int n, float i
   }
 }
 
-__global__ void mc_emit_kernel(const float* __restrict__ vol, int n, float iso, McWs w, float* __restrict__ verts,
-                               int32_t* __restrict__ faces) {
-  int64_t n3 = (int64_t)n * n * n;
+__global__ void mc_emit_kernel(const float* __restrict__ vol, int nx, int n, float iso, McWs w, float* __restrict__ verts,
+                               int32_t* __restrict__ faces, int x_offset) {
+  int64_t n3 = (int64_t)nx * n * n;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n3; idx += (int64_t)gridDim.x * blockDim.x) {
     int k = (int)(idx % n);
     int64_t t = idx / n;
@@ -154,8 +156,8 @@ __global__ void mc_emit_kernel(const float* __restrict__ vol, int n, float iso, 
         if (!(flags & (1 << a))) continue;
         double f2 = (double)vol[idx + strides[a]];
         double tpar = (f2 == f1) ? 0.5 : ((double)iso - f1) / (f2 - f1);
-        float px = (float)i, py = (float)j, pz = (float)k;
-        if (a == 0) px = (float)((double)i + tpar);
+        float px = (float)(i + x_offset), py = (float)j, pz = (float)k;
+        if (a == 0) px = (float)((double)(i + x_offset) + tpar);
         if (a == 1) py = (float)((double)j + tpar);
         if (a == 2) pz = (float)((double)k + tpar);
         verts[(int64_t)vid * 3 + 0] = px;
@@ -243,31 +245,42 @@ static inline int grid_for(int64_t n) {
 
 using namespace zs;
 
-extern "C" size_t zs_mc_ws_bytes(int n) {
-  if (n < 2) return 0;
-  size_t n3 = (size_t)n * n * n, nb = (n3 + 1023) / 1024;
+extern "C" size_t zs_mc_ws_bytes(int n) { return zs_mc_slab_ws_bytes(n, n); }
+
+extern "C" size_t zs_mc_slab_ws_bytes(int nx, int n) {
+  if (n < 2 || nx < 1) return 0;
+  size_t n3 = (size_t)nx * n * n, nb = (n3 + 1023) / 1024;
   return 256 + 2 * align_up(n3 * 4, 256) + 2 * align_up(nb * 4, 256) + 2 * align_up(n3, 256);
 }
 
 extern "C" int zs_mc_count(const float* vol, int n, float iso, void* ws, int32_t* counts, void* stream) {
-  ZS_REQUIRE(vol && ws && counts && n >= 2 && n <= 1024, "zs_mc_count: bad args (n=%d)", n);
-  cudaStream_t st = as_stream(stream);
-  McWs w = carve(ws, n);
-  int64_t n3 = (int64_t)n * n * n;
-  mc_classify_kernel<<<grid_for(n3), 256, 0, st>>>(vol, n, iso, w);
-  exclusive_scan<int32_t>(w.vcnt, w.vcnt, w.vbs, n3, counts + 0, st);
-  exclusive_scan<int32_t>(w.tcnt, w.tcnt, w.tbs, n3, counts + 1, st);
-  count_launches(6);
-  ZS_CUDA_CHECK_LAUNCH("zs_mc_count");
-  return ZS_OK;
+  return zs_mc_slab_count(vol, n, n, iso, ws, counts, stream);
 }
 
 extern "C" int zs_mc_emit(const float* vol, int n, float iso, void* ws, float* verts, int32_t* faces, void* stream) {
-  ZS_REQUIRE(vol && ws && n >= 2 && n <= 1024, "zs_mc_emit: bad args");
-  McWs w = carve(ws, n);
-  int64_t n3 = (int64_t)n * n * n;
-  mc_emit_kernel<<<grid_for(n3), 256, 0, as_stream(stream)>>>(vol, n, iso, w, verts, faces);
-  ZS_CUDA_CHECK_LAUNCH("zs_mc_emit");
+  return zs_mc_slab_emit(vol, n, n, iso, ws, verts, faces, 0, stream);
+}
+
+extern "C" int zs_mc_slab_count(const float* vol, int nx, int n, float iso, void* ws, int32_t* counts, void* stream) {
+  ZS_REQUIRE(vol && ws && counts && n >= 2 && n <= 1024 && nx >= 1 && nx <= n, "zs_mc_slab_count: bad args (nx=%d n=%d)", nx, n);
+  cudaStream_t st = as_stream(stream);
+  McWs w = carve(ws, nx, n);
+  int64_t n3 = (int64_t)nx * n * n;
+  mc_classify_kernel<<<grid_for(n3), 256, 0, st>>>(vol, nx, n, iso, w);
+  exclusive_scan<int32_t>(w.vcnt, w.vcnt, w.vbs, n3, counts + 0, st);
+  exclusive_scan<int32_t>(w.tcnt, w.tcnt, w.tbs, n3, counts + 1, st);
+  count_launches(6);
+  ZS_CUDA_CHECK_LAUNCH("zs_mc_slab_count");
+  return ZS_OK;
+}
+
+extern "C" int zs_mc_slab_emit(const float* vol, int nx, int n, float iso, void* ws, float* verts, int32_t* faces, int x_offset,
+                               void* stream) {
+  ZS_REQUIRE(vol && ws && n >= 2 && n <= 1024 && nx >= 1 && nx <= n, "zs_mc_slab_emit: bad args");
+  McWs w = carve(ws, nx, n);
+  int64_t n3 = (int64_t)nx * n * n;
+  mc_emit_kernel<<<grid_for(n3), 256, 0, as_stream(stream)>>>(vol, nx, n, iso, w, verts, faces, x_offset);
+  ZS_CUDA_CHECK_LAUNCH("zs_mc_slab_emit");
   return ZS_OK;
 }
 

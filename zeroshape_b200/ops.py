@@ -585,21 +585,35 @@ def chamfer_stats(sq1, sq2, thresholds, squared=True):
     return mean1, mean2, f1, f2
 
 
-def marching_cubes(vol, iso):
-    """vol [n,n,n] fp32 CUDA -> (verts [V,3] fp32 in index units, faces [F,3] int32), both on device."""
+def marching_cubes_count(vol, iso):
+    """Pass 1 of marching cubes on vol [nx,n,n] (nx == n: the whole grid; nx < n: an x-slab): -> (workspace, counts [2] int32 on
+    the device = #vertices, #faces).  No host sync: batch several volumes, read all counts at once, then `marching_cubes_emit`."""
     _chk(vol, "vol")
-    n = vol.shape[0]
-    assert vol.shape == (n, n, n)
-    dev = vol.device
-    ws = torch.empty(lib.zs_mc_ws_bytes(n), device=dev, dtype=torch.uint8)
-    counts = torch.empty(2, device=dev, dtype=torch.int32)
-    check(lib.zs_mc_count(_p(vol), n, float(iso), _p(ws), _p(counts), _stream()), "zs_mc_count")
-    V, F = counts.tolist()   # the one host sync of the mesh path (sizes of the outputs)
-    verts = torch.empty(V, 3, device=dev, dtype=torch.float32)
-    faces = torch.empty(F, 3, device=dev, dtype=torch.int32)
+    nx, n = vol.shape[0], vol.shape[1]
+    assert vol.shape == (nx, n, n) and 1 <= nx <= n
+    ws = torch.empty(lib.zs_mc_slab_ws_bytes(nx, n), device=vol.device, dtype=torch.uint8)
+    counts = torch.empty(2, device=vol.device, dtype=torch.int32)
+    check(lib.zs_mc_slab_count(_p(vol), nx, n, float(iso), _p(ws), _p(counts), _stream()), "zs_mc_slab_count")
+    return ws, counts
+
+
+def marching_cubes_emit(vol, iso, ws, V, F, x_offset=0):
+    """Pass 2: -> (verts [V,3] fp32 in global index units, faces [F,3] int32)."""
+    nx, n = vol.shape[0], vol.shape[1]
+    verts = torch.empty(V, 3, device=vol.device, dtype=torch.float32)
+    faces = torch.empty(F, 3, device=vol.device, dtype=torch.int32)
     if V > 0:
-        check(lib.zs_mc_emit(_p(vol), n, float(iso), _p(ws), _p(verts), _p(faces), _stream()), "zs_mc_emit")
+        check(lib.zs_mc_slab_emit(_p(vol), nx, n, float(iso), _p(ws), _p(verts), _p(faces), int(x_offset), _stream()),
+              "zs_mc_slab_emit")
     return verts, faces
+
+
+def marching_cubes(vol, iso, x_offset=0):
+    """vol [n,n,n] (or an x-slab [nx,n,n] whose first slice is global slice `x_offset`) fp32 CUDA ->
+    (verts [V,3] fp32 in index units, faces [F,3] int32), both on device."""
+    ws, counts = marching_cubes_count(vol, iso)
+    V, F = counts.tolist()   # the one host sync of the mesh path (sizes of the outputs)
+    return marching_cubes_emit(vol, iso, ws, V, F, x_offset)
 
 
 def mesh_sample(verts, faces, num, vscale=1.0, voffset=0.0, seed=0):
