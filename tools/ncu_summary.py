@@ -43,10 +43,23 @@ for n, d in enumerate(data):
     print(f"| {n} | {name} | " + " | ".join(vals) + " |")
     traffic.setdefault(name, []).append(num(d, "dram__bytes_read.sum") + num(d, "dram__bytes_write.sum"))
 if len(sys.argv) > 3:
-    lin = traffic.get("chain_lin_kernel", [])
-    per = {"chain_lin[qkv]": lin[0] / pts if lin else None, "chain_lin[proj]": lin[1] / pts if len(lin) > 1 else None,
-           "attn_fused": traffic["chain_attn_kernel"][0] / pts, "chain_mlp": traffic["chain_mlp_kernel"][0] / pts,
-           "chain_occ": traffic["chain_occ_kernel"][0] / pts}
-    chain = sum(v * (1 if k == "chain_occ" else 2) for k, v in per.items())
+    # launches of one decoder pass (round-2 kernels): point_proj, 2 x (LN+qkv+attention, proj+residual, MLP), occupancy MLP.
+    # A capture that misses a launch of a repeated kernel reuses the captured one (same shapes); a missing point_proj is
+    # counted with its algorithmic bytes (12 B read + 1024 B written per point).
+    label = {"chain_qkvattn2_kernel": "chain_qkvattn", "chain_qkvattn_kernel": "chain_qkvattn", "chain_lin_kernel": "chain_lin[proj]",
+             "chain_mlp2_kernel": "chain_mlp", "chain_mlp_kernel": "chain_mlp", "chain_pmlp_kernel": "chain_pmlp",
+             "chain_occ2_kernel": "chain_occ", "chain_occ_kernel": "chain_occ", "point_proj_kernel": "point_proj",
+             "chain_attn_kernel": "attn_fused"}
+    per_pass = {"chain_qkvattn": 2, "chain_lin[proj]": 2, "chain_mlp": 2, "chain_pmlp": 2, "chain_occ": 1, "point_proj": 1, "attn_fused": 2}
+    per = {}
+    for k, v in traffic.items():
+        if k in label:
+            per[label[k]] = sum(v) / len(v) / pts
+    assumed = []
+    if "point_proj" not in per and "--no-point-proj" not in sys.argv:
+        per["point_proj"] = 1036.0
+        assumed.append("point_proj (not captured: algorithmic 1036 B/pt)")
+    chain = sum(v * per_pass[k] for k, v in per.items())
     json.dump({"source": f"{rep} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of a {pts}-point pass; tools/ncu_summary.py)",
-               "points_per_profiled_launch": pts, "bytes_per_point": per, "chain": chain}, open(sys.argv[3], "w"), indent=1)
+               "points_per_profiled_launch": pts, "bytes_per_point": per, "launches_per_pass": {k: per_pass[k] for k in per},
+               "assumed": assumed, "chain": chain}, open(sys.argv[3], "w"), indent=1)
