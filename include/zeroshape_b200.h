@@ -107,7 +107,11 @@ int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, co
  *   Kblob / Vblob / n_keys / scale: as zs_chain_attn_fwd.
  *   flags   : per-GEMM pass policy on top of precision 0: 1 = k, v columns single-pass, 2 = scores without Qh*Kl,
  *             4 = P*V without Ph*Vl (0 = every contraction three passes); 8 = keep the probabilities in tensor memory
- *             (chain_qkvattn2_kernel: P overwrites the scores in place, P*V reads its A operand from TMEM). */
+ *             (chain_qkvattn2_kernel: P overwrites the scores in place, P*V reads its A operand from TMEM);
+ *             16 (with 8) = the softmax role reads every score from tensor memory ONCE and keeps it in registers, and O is
+ *             written TILE-BLOCKED: the 16-byte chunk j (columns 4j..4j+3) of row r of 128-row tile t is float4 number
+ *             (t * 64 + j) * 128 + r, ldo is ignored and O must hold ceil(M / 128) * 128 * 256 floats (padded rows are
+ *             written too).  zs_chain_lin_fwd consumes that layout with do_ln = 2. */
 size_t zs_chain_qkvattn_blob_bytes(void);
 int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const void* Wblob, const float* bias_qkv,
                          const void* Kblob, const void* Vblob, int n_keys, float scale, float* O, int ldo,
@@ -131,7 +135,9 @@ int zs_debug_chain_variant(int v);
  * zs_chain_occ_fwd:  out = MLPBlocks([xyz, LayerNorm(x)]) (+sigmoid)  (model/shape/implicit.py:275,168-184) */
 /* zs_chain_lin_fwd:  out[M, 256*n_tiles] = LN?(x)[M,256] W^T + bias (+ res)   (qkv / proj of ImplFuncAttention,
  * model/shape/implicit.py:30,74; do_ln = the block's norm1 statistics computed in-kernel, affine folded into W / bias).
- * `blob` = zs_gemm_tc_pack image of W[256*n_tiles, 256].  `res`/`out` may alias (in-place residual update). */
+ * `blob` = zs_gemm_tc_pack image of W[256*n_tiles, 256].  `res`/`out` may alias (in-place residual update).
+ * do_ln: 0 = x as is, 1 = LayerNorm(x), 2 = x is the tile-blocked attention output of zs_chain_qkvattn_fwd (flags & 16;
+ * ldx ignored, n_tiles must be 1, no LayerNorm). */
 int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float ln_eps, const void* blob, int n_tiles,
                      const float* bias, const float* res, int ldres, float* out, int ldo, int precision, void* stream);
 size_t zs_chain_mlp_blob_bytes(void);

@@ -63,6 +63,15 @@ def test_chain_lin_matches_fp64(cuda, M):
     xc = x.clone().to(cuda)
     ops.chain_lin(a.to(cuda)[:, 8:264], ops.pack_generic(wp.to(cuda)), bp.to(cuda), 1, res=xc, out=xc)
     assert (xc.cpu().double() - ref2).abs().max().item() < 4e-6 * ref2.abs().max().item()
+    # the same proj from the tile-blocked layout the register-softmax attention kernel writes (do_ln = 2)
+    tiles = (M + 127) // 128
+    pad = torch.zeros(tiles * 128, 256)
+    pad[:M] = a[:, 8:264]
+    a_blk = pad.view(tiles, 128, 64, 4).permute(0, 2, 1, 3).contiguous().to(cuda)
+    assert torch.equal(ops.unblock_rows(a_blk, M).cpu(), a[:, 8:264])
+    xb = x.clone().to(cuda)
+    ops.chain_lin(a_blk, ops.pack_generic(wp.to(cuda)), bp.to(cuda), 1, res=xb, out=xb)
+    assert torch.equal(xb, xc)                          # same arithmetic, only the operand fetch differs
     # LinearProj3D
     pts = torch.rand(M, 3, generator=g) * 3 - 1.5
     w3, b3 = torch.randn(256, 3, generator=g), torch.randn(256, generator=g)
@@ -240,9 +249,11 @@ def test_qkvattn_kernel_matches_reference_math(cuda, M):
     kb, vb = ops.attn_pack_fused(lat_dev[0, :, C:2 * C], lat_dev[0, :, 2 * C:], H)
     wb = ops.qkvattn_pack(w.to(cuda))
     scale = ref.abs().max().item()
-    for prec, flags, tol in (("fp16x3", 0, 8e-6), ("fp16x3", 8, 8e-6), ("fp16x3", 1, 8e-4), ("fp16x3", 9, 8e-4), ("fp16x3", 7, 2e-3),
+    for prec, flags, tol in (("fp16x3", 0, 8e-6), ("fp16x3", 8, 8e-6), ("fp16x3", 24, 8e-6), ("fp16x3", 25, 8e-4), ("fp16x3", 1, 8e-4), ("fp16x3", 9, 8e-4), ("fp16x3", 7, 2e-3),
                              ("fp16x3", 15, 2e-3), ("fp16", 0, 4e-3), ("fp16", 8, 4e-3)):
         out = ops.chain_qkvattn(x.to(cuda), wb, b.to(cuda), kb, vb, L, 32 ** -0.5, ln_eps=1e-6, precision=prec, flags=flags)
+        if flags & 16:
+            out = ops.unblock_rows(out, M)
         err = (out.cpu().double() - ref).abs().max().item()
         print(f"qkvattn M={M} {prec} flags={flags}: max err {err:.3e} (scale {scale:.3f})")
         assert err < tol * scale, (prec, flags, err)
@@ -252,7 +263,7 @@ def test_qkvattn_kernel_matches_reference_math(cuda, M):
     assert (wide[:, 4:260].cpu().double() - ref).abs().max().item() < 8e-6 * scale and wide[:, :4].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("attention,flags", [("qkv", 0), ("qkv", 8), ("qkv", 1), ("qkv", 9), ("qkv", 7), ("fused", 0)])
+@pytest.mark.parametrize("attention,flags", [("qkv", 0), ("qkv", 8), ("qkv", 24), ("qkv", 1), ("qkv", 9), ("qkv", 7), ("fused", 0)])
 def test_decoder_chain_attention_variants(cuda, attention, flags):
     _need_sm100()
     from oracle.implicit import implicit_forward, implicit_init

@@ -39,7 +39,7 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    variants = [("qkv", 8, 1), ("qkv", 8, 0), ("qkv", 9, 1), ("qkv", 0, 1), ("fused", 0, 0), ("qkv", 8, 1)]
+    variants = [("qkv", 24, 1), ("qkv", 8, 1), ("qkv", 24, 1), ("qkv", 8, 1)]
     for attention, flags, mlp_variant in variants:
         fused = True
         net.attention, net.attn_flags = attention, flags

@@ -94,7 +94,7 @@ def main():
         wb = ops.qkvattn_pack(wq)
         bq = torch.zeros(768, device=dev)
         out = torch.empty(M, C, device=dev)
-        for flags in (8, 9):
+        for flags in (8, 24):
             run_traced(f"chain_qkvattn_flags{flags}", TAGS_QKVATTN,
                        lambda: ops.chain_qkvattn(x0, wb, bq, kb, vb, L, 32 ** -0.5, flags=flags, out=out))
     if "mlp" in which:

@@ -560,6 +560,31 @@ __device__ __forceinline__ void store_chunk16(uint8_t* slot, int w, int lane, co
   }
 }
 
+// The same 64-column chunk of 16 rows from a TILE-BLOCKED matrix (the attention output of chain_qkvattn2_kernel<true>: the
+// 16-byte chunk j of row r of tile t is float4 number (t * 64 + j) * 128 + r).  Lane = (row r = lane & 15, parity qq = lane >> 4),
+// instruction j covers chunks 2j + qq: two 256-byte runs per request; buf[j] = chunk 2j + qq of row 16 w + r.
+__device__ __forceinline__ void fetch_chunk16_blk(const float* __restrict__ x, int t, int w, int kc, int lane, float4* buf) {
+  const float4* base = reinterpret_cast<const float4*>(x) + ((size_t)t * 64 + kc * 16 + (lane >> 4)) * 128 + 16 * w + (lane & 15);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) buf[j] = __ldg(base + (size_t)(2 * j) * 128);
+}
+__device__ __forceinline__ void store_chunk16_blk(uint8_t* slot, int w, int lane, const float4* buf, bool split) {
+  const int r = 16 * w + (lane & 15), qq = lane >> 4;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint2 hi, lo;
+    split_f16x2(buf[j].x, buf[j].y, hi.x, lo.x);
+    split_f16x2(buf[j].z, buf[j].w, hi.y, lo.y);
+    const uint32_t off = swizzle128_offset(r, j) + (qq << 3);     // float4 chunk 2j + qq = 8-byte half qq of 16-byte fp16 chunk j
+    *reinterpret_cast<uint2*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+__device__ __forceinline__ void prefetch_tile_blk_l2(const float* __restrict__ x, int t, int w, int lane) {
+  const char* base = reinterpret_cast<const char*>(x) + (size_t)t * 131072 + w * 16384 + lane * 128;     // 128 KB per tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 4096));
+}
 
 // ===============================================================================================================
 // out[M, 256*NT] = LN?(x)[M,256] . W[256*NT, 256]^T + bias (+ res)      (qkv and proj of ImplFuncAttention,
@@ -590,25 +615,32 @@ __global__ void __launch_bounds__(LN_THREADS, 1) chain_lin_kernel(ChainParams p)
       const int m0 = t * 128 + warp * 16;
       float sc = 1.f, sh = 0.f;
       if (tr0) trace_ev(p.trace, 1, tn, 14);
+      const bool blk = p.do_ln == 2;          // A is tile-blocked (and padded to whole tiles); no LayerNorm in this mode
       if (t + (int)gridDim.x < n_tiles) {
-        prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+        if (blk) prefetch_tile_blk_l2(p.x, t + (int)gridDim.x, warp, lane);
+        else prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
         if (p.res)
           for (int nt = 0; nt < NT; ++nt) prefetch_rows16_l2(p.res, p.ldres, m0 + (int)gridDim.x * 128, p.M, nt * 256, lane);
       }
-      if (p.do_ln) warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
-      fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      if (p.do_ln == 1) warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+      if (blk) fetch_chunk16_blk(p.x, t, warp, 0, lane, buf);
+      else fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
       if (tr0) trace_ev(p.trace, 1, tn, 15);
       const int n_chunks = 4 * NT;
       for (int i = 0; i < n_chunks; ++i) {
         if (tr0) trace_ev(p.trace, 1, tn, 10);
         mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
         if (tr0) trace_ev(p.trace, 1, tn, 11);
-        store_chunk16(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, p.do_ln != 0, sc, sh, split);
+        if (blk) store_chunk16_blk(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, split);
+        else store_chunk16(smem_gen + CT_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, p.do_ln == 1, sc, sh, split);
         fence_proxy_async_smem();
         mbar_arrive(B.lfull(lr.idx));
         if (tr0) trace_ev(p.trace, 1, tn, 12);
         lr.advance();
-        if (i + 1 < n_chunks) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+        if (i + 1 < n_chunks) {
+          if (blk) fetch_chunk16_blk(p.x, t, warp, (i + 1) & 3, lane, buf);
+          else fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+        }
         if (tr0) trace_ev(p.trace, 1, tn, 13);
       }
     }
@@ -1689,7 +1721,14 @@ __device__ __forceinline__ void attn_exp_tmem(const uint32_t* rr, int k0, int n_
   }
 }
 
-__global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainParams p) {
+// REGS: third generation of the softmax role (see the comment in its branch): every score is read from tensor memory once.
+// Register pool of the REGS variant: setmaxnreg moves registers only inside the CTA's own launch allocation (USETMAXREG ...
+// CTAPOOL) and warps are allocated in groups of four, so a 576-thread CTA gets 20 x 32 x 96 registers but can use only 18 warps'
+// worth.  The variant is launched with 640 threads: warps 18-19 exist only to complete the fifth warpgroup, which hands back
+// its registers as a whole; 8 loader warps x 56 + 8 softmax warps x 152 + 4 x 56 = 1888 <= 20 x 96 = 1920.
+constexpr int QA3_THREADS = 640;
+template <bool REGS>
+__global__ void __maxnreg__(96) chain_qkvattn2_kernel(ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1708,7 +1747,7 @@ __global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainPara
     mbar_init(B.accfull(), 1); mbar_init(B.accempty(), 256);
     for (int i = 0; i < 2; ++i) { mbar_init(B.qfull(i), 128); mbar_init(B.qempty(i), 1); }
     mbar_init(B.sfull(), 1); mbar_init(B.pfull(), 256);
-    mbar_init(B.ofull(), 1); mbar_init(B.oempty(), 128);
+    mbar_init(B.ofull(), 1); mbar_init(B.oempty(), REGS ? 256 : 128);
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(B.tmem_slot(), 512);
@@ -1717,9 +1756,13 @@ __global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainPara
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (B.tmem_slot() - smem_base));
 
+  if constexpr (REGS) {
+    if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");     // MMA, W loader and the two filler warps
+  }
   if (warp < 8) {
     // ---------------- loaders: LN(x) chunks, 4 units x 4 K-chunks per tile ----------------
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if constexpr (REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     Ring lr(2);
     float4 buf[8];
     int tn = 0;
@@ -1886,6 +1929,188 @@ __global__ void __launch_bounds__(QA_THREADS, 1) chain_qkvattn2_kernel(ChainPara
             umma_commit(B.wempty(v_slot));
             trace_ev(p.trace, 0, tn, 8);
           }
+        }
+      }
+    }
+  } else if (warp >= 18) {
+    // filler warps of the REGS variant: nothing to do
+  } else if constexpr (REGS) {
+    // ---------------- softmax / epilogue warps, scores in REGISTERS: thread = (query row, half) ----------------
+    // Tensor memory is read at 64 B/clk per SM: the 128 x 208 fp32 scores of a head take ~1.7k cycles per sweep, and the
+    // two sweeps (max, then exp) of the branch below were ~3.3k of the ~11k-cycle critical path of a head.  Here a thread
+    // loads its 104 (112) scores once, keeps them in registers across the max exchange and converts them in place.  The
+    // two threads of a row meet at a 64-thread named barrier (their two warps) instead of a 256-thread one, and BOTH
+    // finish the head (16 of its 32 output columns each), which halves the serial tail O read -> normalise -> store.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    int tn = 0;
+    const bool tr0 = (warp == 8 && lane == 0);
+    const int e = warp - 8, wq = e & 3, half = e >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t acc_tm = tmem_base + lane_off, s_tm = acc_tm + 192u, o_tm = acc_tm + 400u;
+    const bool o_two = split && !pv2;
+    uint8_t* qslot = smem_gen + QB_OFF_Q;
+    uint32_t ph_accfull = 0, ph_qempty = 0, ph_sfull = 0, ph_ofull = 0;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int bar_max = 1 + wq, bar_sum = 5 + wq;
+    float s_self = 0.f;
+    float* oblk_next = nullptr;
+    // epi-1 of unit (tile t, head pair pr): runs one unit AHEAD of the heads loop -- for the first unit of the CTA in the
+    // prologue, afterwards in the shadow of the P V MMAs of the previous unit's second head (its accumulator has been
+    // ready since the softmax of that head began), so that the S MMA of the next head never waits for q.
+    auto epi1 = [&](int t, int pr) {
+        // ---- epi-1: q and the self score of this half's head; 16 value columns of BOTH heads ----
+        const int hm = 2 * pr + half;
+        // this thread's four 16-byte chunks of head 2 pr in the tile-blocked output (see zs_chain_qkvattn_fwd): chunk j of
+        // row r lives at float4 index (tile * 64 + j) * 128 + r, so a warp's 32 rows are 512 contiguous bytes per chunk
+        float* const oblk = p.out + ((size_t)t * 8192 + row) * 4 + (size_t)((2 * pr) * 8 + 4 * half) * 512;
+        oblk_next = oblk;
+        if (tr0) trace_ev(p.trace, 2, tn, 20);
+        mbar_wait(B.accfull(), ph_accfull); ph_accfull ^= 1;
+        if (tr0) trace_ev(p.trace, 2, tn, 21);
+        tc_fence_after();
+        {
+          uint32_t rq[32], rk[32];
+          tmem_ld_32x32(acc_tm + 32u * half, rq);
+          tmem_ld_32x32(acc_tm + 64u + 32u * half, rk);
+          tmem_ld_wait();
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + hm * 32);
+          const float4* bk = reinterpret_cast<const float4*>(p.bias + 256 + hm * 32);
+          float2 d2 = make_float2(0.f, 0.f);
+          mbar_wait(B.qempty(half), ph_qempty ^ 1); ph_qempty ^= 1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float4 b4 = __ldg(bq + 2 * c + j), k4 = __ldg(bk + 2 * c + j);
+              const int i = 8 * c + 4 * j;
+              const float2 qa = add2(make_float2(__uint_as_float(rq[i]), __uint_as_float(rq[i + 1])), make_float2(b4.x, b4.y));
+              const float2 qb = add2(make_float2(__uint_as_float(rq[i + 2]), __uint_as_float(rq[i + 3])), make_float2(b4.z, b4.w));
+              const float2 ka = add2(make_float2(__uint_as_float(rk[i]), __uint_as_float(rk[i + 1])), make_float2(k4.x, k4.y));
+              const float2 kb = add2(make_float2(__uint_as_float(rk[i + 2]), __uint_as_float(rk[i + 3])), make_float2(k4.z, k4.w));
+              d2 = fma2(qa, ka, d2);
+              d2 = fma2(qb, kb, d2);
+              split_f16x2(qa.x, qa.y, hi[2 * j], lo[2 * j]);
+              split_f16x2(qb.x, qb.y, hi[2 * j + 1], lo[2 * j + 1]);
+            }
+            const uint32_t off = swizzle128_offset(row, 4 * half + c);
+            *reinterpret_cast<uint4*>(qslot + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (split) *reinterpret_cast<uint4*>(qslot + CT_A_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          s_self = d2.x + d2.y;
+          fence_proxy_async_smem();
+          mbar_arrive(B.qfull(half));
+        }
+        {
+          uint32_t ra[16], rb[16];
+          tmem_ld_32x16(acc_tm + 128u + 16u * half, ra);
+          tmem_ld_32x16(acc_tm + 160u + 16u * half, rb);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(B.accempty());
+          // the points' own value rows (v + bias) wait in the OUTPUT buffer, at the very addresses the finished head will
+          // overwrite: 32 registers less across the two softmax passes (which need them for instruction-level parallelism)
+          const float4* ba = reinterpret_cast<const float4*>(p.bias + 512 + (2 * pr) * 32 + 16 * half);
+          const float4* bb = reinterpret_cast<const float4*>(p.bias + 512 + (2 * pr + 1) * 32 + 16 * half);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 a4 = __ldg(ba + j), b4 = __ldg(bb + j);
+            *reinterpret_cast<float4*>(oblk + j * 512) =
+                make_float4(__uint_as_float(ra[4 * j]) + a4.x, __uint_as_float(ra[4 * j + 1]) + a4.y,
+                            __uint_as_float(ra[4 * j + 2]) + a4.z, __uint_as_float(ra[4 * j + 3]) + a4.w);
+            *reinterpret_cast<float4*>(oblk + (8 + j) * 512) =
+                make_float4(__uint_as_float(rb[4 * j]) + b4.x, __uint_as_float(rb[4 * j + 1]) + b4.y,
+                            __uint_as_float(rb[4 * j + 2]) + b4.z, __uint_as_float(rb[4 * j + 3]) + b4.w);
+          }
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) epi1(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int pr = 0; pr < 4; ++pr) {
+        float* const oblk = oblk_next;
+        // ---- the two heads of the pair; the halves split each head's keys (half 0: 32-key blocks 0,2,4,6; half 1: 1,3,5) ----
+#pragma unroll 1
+        for (int hs = 0; hs < 2; ++hs) {
+          const int h = 2 * pr + hs;
+          const bool mine = hs == half;
+          if (tr0) trace_ev(p.trace, 2, tn, 22);
+          mbar_wait(B.sfull(), ph_sfull); ph_sfull ^= 1;
+          if (tr0) trace_ev(p.trace, 2, tn, 23);
+          tc_fence_after();
+          uint32_t sa[32], sb[32], sc3[32], sd[16];
+          const int ka = 32 * half, kb = 64 + 32 * half, kc3 = 128 + 32 * half;   // first keys of this thread's blocks
+          tmem_ld_32x32(s_tm + ka, sa);
+          tmem_ld_32x32(s_tm + kb, sb);
+          tmem_ld_32x32(s_tm + kc3, sc3);
+          if (half == 0) tmem_ld_32x16(s_tm + 192, sd);
+          tmem_ld_wait();
+          float mx = mine ? s_self : -3.0e38f;
+          mx = attn_max_block<32>(sa, ka, n_keys, mx);
+          mx = attn_max_block<32>(sb, kb, n_keys, mx);
+          mx = attn_max_block<32>(sc3, kc3, n_keys, mx);
+          if (half == 0) mx = attn_max_block<16>(sd, 192, n_keys, mx);
+          xbuf[half * 128 + row] = mx;
+          if (mine) xbuf[256 + (half ^ 1) * 128 + row] = s_self;      // the other thread of the row reads it from ITS sum slot
+          if (tr0) trace_ev(p.trace, 2, tn, 24);
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_max) : "memory");
+          if (tr0) trace_ev(p.trace, 2, tn, 25);
+          mx = fmaxf(mx, xbuf[(half ^ 1) * 128 + row]);
+          const float ss = mine ? s_self : xbuf[256 + half * 128 + row];
+          const float mxs = mx * sl2;
+          float2 sum2 = make_float2(0.f, 0.f);
+          // a block is masked only when the key count ends inside it (CTA-uniform)
+          if (ka + 32 <= n_keys) attn_exp_tmem<32, false>(sa, ka, n_keys, sl2, mxs, sum2, s_tm + ka, split);
+          else attn_exp_tmem<32, true>(sa, ka, n_keys, sl2, mxs, sum2, s_tm + ka, split);
+          if (kb + 32 <= n_keys) attn_exp_tmem<32, false>(sb, kb, n_keys, sl2, mxs, sum2, s_tm + kb, split);
+          else attn_exp_tmem<32, true>(sb, kb, n_keys, sl2, mxs, sum2, s_tm + kb, split);
+          if (kc3 + 32 <= n_keys) attn_exp_tmem<32, false>(sc3, kc3, n_keys, sl2, mxs, sum2, s_tm + kc3, split);
+          else attn_exp_tmem<32, true>(sc3, kc3, n_keys, sl2, mxs, sum2, s_tm + kc3, split);
+          if (half == 0) attn_exp_tmem<16, true>(sd, 192, n_keys, sl2, mxs, sum2, s_tm + 192, split);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(B.pfull());
+          if (tr0) trace_ev(p.trace, 2, tn, 26);
+          const float e_self = fast_ex2(fmaf(ss, sl2, -mxs));
+          const float sum = sum2.x + sum2.y + (mine ? e_self : 0.f);
+          xbuf[256 + half * 128 + row] = sum;
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_sum) : "memory");
+          if (tr0) trace_ev(p.trace, 2, tn, 27);
+          const float inv = 1.0f / (sum + xbuf[256 + (half ^ 1) * 128 + row]);
+          if (hs == 1) {          // s_self of this unit is dead (e_self is computed): the next unit's epi-1 may overwrite it
+            const int t2 = pr < 3 ? t : t + (int)gridDim.x;     // one call site: the role's code must stay small (instruction cache)
+            if (t2 < n_tiles) epi1(t2, (pr + 1) & 3);
+          }
+          float4 vs[4];                                        // the parked value chunks of this head (L2 hits, issued early)
+          float* const oh = oblk + hs * (8 * 512);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(vs[j].x), "=f"(vs[j].y), "=f"(vs[j].z), "=f"(vs[j].w) : "l"(oh + j * 512) : "memory");
+          mbar_wait(B.ofull(), ph_ofull); ph_ofull ^= 1;
+          if (tr0) trace_ev(p.trace, 2, tn, 28);
+          tc_fence_after();
+          {
+            uint32_t rr[16], r2[16];
+            tmem_ld_32x16(o_tm + 16u * half, rr);
+            if (o_two) tmem_ld_32x16(o_tm + 32u + 16u * half, r2);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(B.oempty());
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a0 = __uint_as_float(rr[4 * j]), a1 = __uint_as_float(rr[4 * j + 1]);
+              float a2 = __uint_as_float(rr[4 * j + 2]), a3 = __uint_as_float(rr[4 * j + 3]);
+              if (o_two) {
+                a0 += __uint_as_float(r2[4 * j]); a1 += __uint_as_float(r2[4 * j + 1]);
+                a2 += __uint_as_float(r2[4 * j + 2]); a3 += __uint_as_float(r2[4 * j + 3]);
+              }
+              *reinterpret_cast<float4*>(oh + j * 512) =
+                  make_float4(fmaf(e_self, vs[j].x, a0) * inv, fmaf(e_self, vs[j].y, a1) * inv,
+                              fmaf(e_self, vs[j].z, a2) * inv, fmaf(e_self, vs[j].w, a3) * inv);
+            }
+          }
+          if (tr0) trace_ev(p.trace, 2, tn, 29);
         }
       }
     }
@@ -2481,6 +2706,7 @@ extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float
                                 const float* bias, const float* res, int ldres, float* out, int ldo, int precision, void* stream) {
   ZS_REQUIRE(x && blob && out && M >= 0, "zs_chain_lin_fwd: null pointer");
   ZS_REQUIRE(n_tiles >= 1 && n_tiles <= 16, "zs_chain_lin_fwd: n_tiles must be in [1, 16]");
+  ZS_REQUIRE(do_ln >= 0 && do_ln <= 2 && (do_ln != 2 || n_tiles == 1), "zs_chain_lin_fwd: do_ln must be 0, 1 or 2 (tile-blocked x, one n-tile)");
   ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_lin_fwd: x must be 16B aligned, ldx%%4==0");
   ZS_REQUIRE(ldo >= 256 * n_tiles && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "zs_chain_lin_fwd: out must be 16B aligned, ldo%%4==0");
   ZS_REQUIRE(res == nullptr || ((ldres & 3) == 0 && ldres >= 256 * n_tiles && (reinterpret_cast<uintptr_t>(res) & 15) == 0),
@@ -2543,12 +2769,14 @@ extern "C" int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(Kblob) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(Vblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias_qkv) & 15) == 0,
              "zs_chain_qkvattn_fwd: blobs / bias must be 16-byte aligned");
-  ZS_REQUIRE((precision == 0 || precision == 1) && flags >= 0 && flags < 16, "zs_chain_qkvattn_fwd: bad precision / flags");
+  ZS_REQUIRE((precision == 0 || precision == 1) && flags >= 0 && flags < 32, "zs_chain_qkvattn_fwd: bad precision / flags");
   if (M == 0) return ZS_OK;
   ChainParams p{};
   p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.blob = reinterpret_cast<const uint8_t*>(Wblob);
   p.bias = bias_qkv; p.kblob = reinterpret_cast<const uint8_t*>(Kblob); p.vblob = reinterpret_cast<const uint8_t*>(Vblob);
   p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = ldo; p.precision = precision; p.flags = flags;
-  // flags & 8: the variant that keeps the probabilities in tensor memory (chain_qkvattn2_kernel)
-  return chain_launch((flags & 8) ? chain_qkvattn2_kernel : chain_qkvattn_kernel, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA_THREADS);
+  // flags & 8: the variant that keeps the probabilities in tensor memory (chain_qkvattn2_kernel); & 16: its softmax role with
+  // the scores held in registers (one tensor-memory sweep per head)
+  if (flags & 16) return chain_launch(chain_qkvattn2_kernel<true>, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA3_THREADS);
+  return chain_launch((flags & 8) ? chain_qkvattn2_kernel<false> : chain_qkvattn_kernel, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA_THREADS);
 }

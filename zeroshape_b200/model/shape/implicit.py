@@ -95,7 +95,7 @@ class Implicit(nn.Module):
         self.attention = "qkv"
         # zs_chain_qkvattn_fwd policy: 8 = probabilities in tensor memory (the faster kernel), every contraction three fp16
         # passes; +1 = k, v single-pass (inside the 5e-4 parity budget of profiles/r2_precision_study.md, no measured speed-up)
-        self.attn_flags = 8
+        self.attn_flags = 24       # zs_chain_qkvattn_fwd: 8 = probabilities in tensor memory, 16 = scores in registers + tile-blocked output
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
         # query points per pass of the per-layer / chained engines (bounds scratch memory: ~5 KB per point).  One pass over a whole
@@ -227,14 +227,19 @@ class Implicit(nn.Module):
             if chain and attn_out is None and self.attention == "qkv" and self.lin_fused:
                 # LayerNorm + qkv + attention of a tile in one kernel; then x += proj(a) and the MLP as below
                 packs = lat.setdefault("kv_fused", {})
-                a = torch.empty(B * P, C, device=x.device, dtype=torch.float32)
+                blocked = bool(self.attn_flags & 16)     # the attention output stays tile-blocked between the two kernels
+                a = None if blocked else torch.empty(B * P, C, device=x.device, dtype=torch.float32)
                 for b in range(B):
                     if (l, b) not in packs:
                         packs[(l, b)] = ops.attn_pack_fused(k_lat[b], v_lat[b], self.num_heads)
-                    ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
-                                      lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
-                                      flags=self.attn_flags, out=a[b * P:(b + 1) * P])
-                ops.chain_lin(a, lin_blobs[l][2], blk.attn.proj.bias, 1, res=x, out=x, precision=self.precision)   # x += proj(a)
+                    ab = ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
+                                           lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
+                                           flags=self.attn_flags, out=None if blocked else a[b * P:(b + 1) * P])
+                    if blocked:
+                        xb = x[b * P:(b + 1) * P]
+                        ops.chain_lin(ab, lin_blobs[l][2], blk.attn.proj.bias, 1, res=xb, out=xb, precision=self.precision)
+                if not blocked:
+                    ops.chain_lin(a, lin_blobs[l][2], blk.attn.proj.bias, 1, res=x, out=x, precision=self.precision)   # x += proj(a)
                 ops.chain_mlp(x, None, None, blk.norm2.eps, mlp_blobs[l], mlp_b1[l], blk.mlp.fc2.bias, self.precision)
                 continue
             if chain and self.lin_fused:    # LayerNorm statistics + qkv GEMM in one launch (norm1 affine folded into the packed weights)

@@ -177,7 +177,13 @@ def attn_fused(qkv, kblob, vblob, n_keys, scale, precision="bf16x3", out=None):
     return O
 
 
-QKVATTN_FLAGS = {"kv1": 1, "s2": 2, "pv2": 4, "tmem_p": 8}
+QKVATTN_FLAGS = {"kv1": 1, "s2": 2, "pv2": 4, "tmem_p": 8, "regs_blocked": 16}
+
+
+def unblock_rows(O_blk, M):
+    """tile-blocked attention output [tiles, 64, 128, 4] -> row-major [M, 256] (tests / debugging only)."""
+    t = O_blk.shape[0]
+    return O_blk.permute(0, 2, 1, 3).reshape(t * 128, 256)[:M]
 
 
 def qkvattn_pack(w_qkv_folded):
@@ -203,6 +209,14 @@ def chain_qkvattn(x, wblob, bias_qkv, kblob, vblob, n_keys, scale, ln_eps=1e-6, 
     assert bias_qkv.numel() == 768 and kblob.numel() == 4 * 65536 and vblob.numel() == 8 * 32768
     assert wblob.numel() == lib.zs_chain_qkvattn_blob_bytes()
     M = x.shape[0]
+    if int(flags) & 16:     # tile-blocked output (see include/zeroshape_b200.h): [ceil(M/128), 64 chunks, 128 rows, 4]
+        assert int(flags) & 8, "flags 16 (scores in registers) is a mode of the TMEM-probability kernel (flags 8)"
+        tiles = (M + 127) // 128
+        O = out if out is not None else torch.empty(tiles, 64, 128, 4, device=x.device, dtype=torch.float32)
+        assert O.is_contiguous() and O.numel() == tiles * 32768 and O.dtype == torch.float32
+        check(lib.zs_chain_qkvattn_fwd(_p(x), x.stride(0), M, ln_eps, _p(wblob), _p(bias_qkv), _p(kblob), _p(vblob), n_keys, scale,
+                                       _p(O), 256, CHAIN_PRECISIONS[precision], int(flags), _stream()), "zs_chain_qkvattn_fwd")
+        return O
     O = out if out is not None else torch.empty(M, 256, device=x.device, dtype=torch.float32)
     assert O.shape == (M, 256) and O.stride(1) == 1 and O.dtype == torch.float32
     check(lib.zs_chain_qkvattn_fwd(_p(x), x.stride(0), M, ln_eps, _p(wblob), _p(bias_qkv), _p(kblob), _p(vblob), n_keys, scale,
@@ -253,16 +267,23 @@ def point_proj(points, w, bias):
 
 def chain_lin(x, blob, bias, n_tiles, do_ln=False, ln_eps=1e-6, res=None, out=None, precision="bf16x3"):
     """out[M, 256*n_tiles] = LN?(x)[M,256] W^T + bias (+ res) on the chained tcgen05 kernel; `out` may alias `res`."""
-    assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+    blocked = x.dim() == 4        # tile-blocked attention output of chain_qkvattn(flags & 16): rows come from `res` / `out`
+    if blocked:
+        assert x.shape[1:] == (64, 128, 4) and x.is_contiguous() and x.is_cuda and x.dtype == torch.float32 and not do_ln and n_tiles == 1
+        M = (res if res is not None else out).shape[0]
+        assert (M + 127) // 128 == x.shape[0]
+        do_ln, ldx = 2, 256
+    else:
+        assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+        M, ldx = x.shape[0], x.stride(0)
     assert blob.numel() == lib.zs_gemm_tc_packed_bytes(256 * n_tiles, 256)
     _chk(bias, "bias")
-    M = x.shape[0]
     if out is None:
         out = torch.empty(M, 256 * n_tiles, device=x.device, dtype=torch.float32)
     assert out.shape == (M, 256 * n_tiles) and out.stride(1) == 1
     if res is not None:
         assert res.shape == out.shape and res.stride(1) == 1 and res.dtype == torch.float32
-    check(lib.zs_chain_lin_fwd(_p(x), x.stride(0), M, int(do_ln), ln_eps, _p(blob), n_tiles, _p(bias), _p(res),
+    check(lib.zs_chain_lin_fwd(_p(x), ldx, M, int(do_ln), ln_eps, _p(blob), n_tiles, _p(bias), _p(res),
                                res.stride(0) if res is not None else 0, _p(out), out.stride(0), CHAIN_PRECISIONS[precision], _stream()),
           "zs_chain_lin_fwd")
     return out
