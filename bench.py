@@ -227,8 +227,8 @@ def run_ours(args, rank, world, dev):
             hot_path(rgb_dev[:1], mask_dev[:1], False)
         summ = ot.summary()
     per_point_flop = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
-                      "chain_occ": 2 * 724224, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
-    per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_occ": 1, "point_proj": 1,
+                      "chain_occ": 2 * 724224, "chain_pmlp": 2 * (524288 + 65536), "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
+    per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_pmlp": 2, "chain_occ": 1, "point_proj": 1,
                           "chain_qkvattn": 2}
     tot_ms = sum(v[1] for v in summ.values())
     for k, (cnt, ms_k) in sorted(summ.items(), key=lambda kv: -kv[1][1]):

@@ -144,6 +144,13 @@ size_t zs_chain_mlp_blob_bytes(void);
 size_t zs_chain_occ_blob_bytes(void);
 int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* ln_b, float ln_eps,
                      const void* blob, const float* b1, const float* b2, int precision, void* stream);
+/* zs_chain_pmlp_fwd: x <- x' + fc2(GELU(fc1(LayerNorm(x')))) with x' = x + A proj.weight^T + proj.bias: the attention
+ * output projection + residual (model/shape/implicit.py:74, ImplFuncBlock :105) fused in front of zs_chain_mlp_fwd.
+ * a_blk = the tile-blocked attention output of zs_chain_qkvattn_fwd (flags & 16), ceil(M/128)*128*256 floats;
+ * proj_blob = zs_gemm_tc_pack_fmt(proj.weight [256,256], fmt 1); mlp_blob / b1 / b2 as zs_chain_mlp_fwd (norm2's affine
+ * folded into fc1).  The LayerNorm variance is the one-pass E[x^2] - mean^2 of pairwise-reduced fp32 sums. */
+int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, const void* proj_blob, const float* proj_bias,
+                      float ln_eps, const void* mlp_blob, const float* b1, const float* b2, int precision, void* stream);
 int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
                      float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
                      float* out, int apply_sigmoid, int precision, void* stream);

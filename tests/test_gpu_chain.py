@@ -44,6 +44,40 @@ def test_chain_mlp_matches_fp64(cuda, M):
 
 
 @pytest.mark.parametrize("M", [1, 128, 1000, 40000])
+def test_chain_pmlp_matches_fp64_and_the_two_kernel_path(cuda, M):
+    """zs_chain_pmlp_fwd: x' = x + A Wp^T + bp from the tile-blocked attention output, then the MLP, in one kernel."""
+    _need_sm100()
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(M + 11)
+    x = torch.randn(M, 256, generator=g) * 1.5 + 0.3
+    a = torch.randn(M, 256, generator=g)
+    wp, bp = torch.randn(256, 256, generator=g) / 16, torch.randn(256, generator=g) * 0.1
+    w1, b1 = torch.randn(1024, 256, generator=g) / 16, torch.randn(1024, generator=g) * 0.1
+    w2, b2 = torch.randn(256, 1024, generator=g) / 32, torch.randn(256, generator=g) * 0.1
+    x1 = x.double() + F.linear(a.double(), wp.double(), bp.double())
+    ref = x1 + F.linear(F.gelu(F.linear(F.layer_norm(x1, (256,), None, None, 1e-6), w1.double(), b1.double())), w2.double(), b2.double())
+    mats = []
+    for gi in range(4):
+        mats += [w1[256 * gi:256 * (gi + 1), :].to(cuda), w2[:, 256 * gi:256 * (gi + 1)].to(cuda)]
+    blob, pblob = ops.pack_tiles(mats), ops.pack_generic(wp.to(cuda))
+    tiles = (M + 127) // 128
+    pad = torch.zeros(tiles * 128, 256)
+    pad[:M] = a
+    a_blk = pad.view(tiles, 128, 64, 4).permute(0, 2, 1, 3).contiguous().to(cuda)
+    for prec, tol in (("fp16x3", 6e-6), ("fp16", 6e-3)):
+        xc = x.clone().to(cuda)
+        ops.chain_pmlp(xc, a_blk, pblob, bp.to(cuda), 1e-6, blob, b1.to(cuda), b2.to(cuda), prec)
+        err = (xc.cpu().double() - ref).abs().max().item()
+        x2 = x.clone().to(cuda)
+        ops.chain_lin(a_blk, pblob, bp.to(cuda), 1, res=x2, out=x2, precision=prec)
+        ops.chain_mlp(x2, None, None, 1e-6, blob, b1.to(cuda), b2.to(cuda), prec)
+        d2 = (xc - x2).abs().max().item()
+        print(f"chain_pmlp M={M} {prec}: max err {err:.3e} / scale {ref.abs().max().item():.2f}; vs chain_lin + chain_mlp {d2:.3e}")
+        assert err < tol * ref.abs().max().item(), (prec, err)
+        assert d2 < tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M", [1, 128, 1000, 40000])
 def test_chain_lin_matches_fp64(cuda, M):
     """LN + qkv (3 n-tiles) and proj + in-place residual (1 n-tile) of zs_chain_lin_fwd; zs_point_proj_f32."""
     _need_sm100()

@@ -31,7 +31,7 @@ net = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_ml
 lat_in = torch.randn(1, 197, 256, device=dev)
 pts = (torch.rand(1, P, 3, device=dev) * 3 - 1.5).contiguous()
 FLOP = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
-        "chain_occ": 2 * 724224, "gemm_tc": 0, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
+        "chain_occ": 2 * 724224, "chain_pmlp": 2 * (524288 + 65536), "gemm_tc": 0, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
 with torch.no_grad():
     lat = net.prepare_latents(lat_in)
     if ONCE:
@@ -39,10 +39,12 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    variants = [("qkv", 24, 1), ("qkv", 8, 1), ("qkv", 24, 1), ("qkv", 8, 1)]
+    variants = [("qkv", 24, 1), ("qkv", 24, 0), ("qkv", 24, 1), ("qkv", 24, 0)]     # third field: proj fused into the MLP kernel
     for attention, flags, mlp_variant in variants:
         fused = True
         net.attention, net.attn_flags = attention, flags
+        net.fuse_proj = bool(mlp_variant)
+        mlp_variant = 1
         lib.zs_debug_chain_variant(mlp_variant)
         for _ in range(3):
             net._points_chain(lat, pts, tc=True, sigmoid=True)

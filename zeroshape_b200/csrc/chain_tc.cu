@@ -47,6 +47,8 @@ struct ChainParams {
   const float* res; int ldres; int ldo; int n_tiles; int do_ln;
   // chain_qkvattn_kernel: latent key / value operand images of the image, softmax scale, per-GEMM pass policy
   const uint8_t* kblob; const uint8_t* vblob; int n_keys; float scale; int flags;
+  // chain_pmlp_kernel: tile-blocked attention output, packed proj weight (4 K-chunk pairs), proj bias
+  const float* a_blk; const uint8_t* pblob; const float* bias_p;
 };
 
 struct Bars {
@@ -2531,6 +2533,262 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_mlp2_kernel(ChainParams p
   if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ===============================================================================================================
+// Attention output projection + residual AND the MLP of an ImplFuncBlock in one kernel (model/shape/implicit.py:74,105-108):
+//     x' = x + A Wp^T + bp          (A = the tile-blocked attention output of chain_qkvattn2_kernel<true>)
+//     x  = x' + fc2(GELU(fc1(LayerNorm(x'))))
+// chain_mlp2_kernel with one more GEMM in front.  Per tile: the loaders stream the four 64-column chunks of A (512 contiguous
+// bytes per warp request in the blocked layout) through ring L, the proj MMAs accumulate into the FIRST accumulator half
+// (free since fc2 of the previous tile's last group has read it -- so they overlap that tile's final epilogue, which reads the
+// second half), and the epilogue warps finish x' = acc + bp + x in the transposed (row-segment) layout, write it back in place
+// and reduce the LayerNorm sums of every row on the way (16 values per thread, 8 lanes by shuffles, the two column halves
+// through shared memory).  The loaders then read x' back (L2 hits, ld.global.cg: it was written by other warps of this CTA)
+// exactly as chain_mlp2_kernel reads x.  HBM sees A and x once and x once more for the result: the separate proj launch
+// (4.3 KB per point, the one HBM-bound launch of the decoder) is gone.
+struct BarsP : Bars5 {
+  __device__ uint32_t xready() const { return base + 184u; }
+};
+
+// 64 columns of a TILE-BLOCKED matrix for a 32-row loader warp: instruction j = 16-byte chunk kc * 16 + j of rows 32 w + lane
+__device__ __forceinline__ void fetch_chunk32_blk(const float* __restrict__ a, int t, int w, int kc, int lane, float4* buf) {
+  const float4* base = reinterpret_cast<const float4*>(a) + ((size_t)t * 64 + kc * 16) * 128 + 32 * w + lane;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) buf[j] = __ldg(base + (size_t)j * 128);
+}
+__device__ __forceinline__ void store_chunk32_blk(uint8_t* slot, int w, int lane, const float4* buf, bool split) {
+  const int r = 32 * w + lane;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint2 hi, lo;
+    split_f16x2(buf[j].x, buf[j].y, hi.x, lo.x);
+    split_f16x2(buf[j].z, buf[j].w, hi.y, lo.y);
+    const uint32_t off = swizzle128_offset(r, j >> 1) + ((j & 1) << 3);
+    *reinterpret_cast<uint2*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+// fetch_chunk_co with L2-coherent loads (the rows were written by other warps of this CTA a moment ago)
+__device__ __forceinline__ void fetch_chunk_co_cg(const float* x, int ldx, int m0, int M, int col0, int lane, float4* buf) {
+  const int sub = lane >> 4, q = lane & 15;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int m = m0 + 2 * j + sub;
+    buf[j] = m < M ? __ldcg(reinterpret_cast<const float4*>(x + (int64_t)m * ldx + col0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  if (smem_base - smem_u32(smem_raw) > CT_SMEM - CT_SMEM_USED) __trap();
+  BarsP B{{smem_base + CT_OFF_BAR}};
+  float2* stats = reinterpret_cast<float2*>(smem_gen + CT_OFF_BAR + 256);     // [2 column halves][128 rows] (sum, sum of squares)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  if (threadIdx.x == 0) mbar_init(B.xready(), 256);
+  const uint32_t tmem_base = chain2_setup(B, smem_gen, smem_base, warp, M2_WSLOTS);
+  const int n_tiles = (p.M + 127) / 128;
+
+  if (warp < 4) {
+    // ---------------- loader: 4 chunks of A, then (after x' is written) 4 groups x 4 chunks of LayerNorm(x') ----------------
+    Ring lr(CT_LSLOTS);
+    float4 buf[16];
+    uint32_t ph_x = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = t * 128 + warp * 32;
+      if (t + (int)gridDim.x < n_tiles) {
+        const char* nb = reinterpret_cast<const char*>(p.a_blk) + (size_t)(t + gridDim.x) * 131072 + warp * 32768 + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + i * 4096));
+        prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      }
+      fetch_chunk32_blk(p.a_blk, t, warp, 0, lane, buf);
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk32_blk(smem_gen + M2_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (kc + 1 < 4) fetch_chunk32_blk(p.a_blk, t, warp, kc + 1, lane, buf);
+      }
+      mbar_wait(B.xready(), ph_x); ph_x ^= 1;
+      fetch_chunk_co_cg(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      float sc = 0.f, sh = 0.f;
+      if (m0 + lane < p.M) {
+        const float2 s0 = stats[32 * warp + lane], s1 = stats[128 + 32 * warp + lane];
+        const float mean = (s0.x + s1.x) * (1.0f / 256.0f);
+        const float var = fmaxf((s0.y + s1.y) * (1.0f / 256.0f) - mean * mean, 0.f);
+        sc = rsqrtf(var + p.ln_eps);
+        sh = -mean * sc;
+      }
+      for (int i = 0; i < 16; ++i) {
+        const int kc = i & 3;
+        mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
+        store_chunk_co(smem_gen + M2_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh,
+                       p.ln_w ? p.ln_w + kc * 64 : nullptr, p.ln_b ? p.ln_b + kc * 64 : nullptr, split);
+        fence_proxy_async_smem();
+        mbar_arrive(B.lfull(lr.idx));
+        lr.advance();
+        if (i + 1 < 16) fetch_chunk_co_cg(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      Ring wr(M2_WSLOTS);
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        w_stream2(B, smem_base, wr, p.pblob, 4, split);
+        w_stream2(B, smem_base, wr, p.blob, 32, split);
+      }
+    }
+  } else if (warp == 12) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Ring wr(M2_WSLOTS), lr(CT_LSLOTS);
+      uint32_t te_phase[2] = {0, 0}, ef_phase = 0;
+      const uint32_t d0 = tmem_base, d1 = tmem_base + 256;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int g = -1; g < 4; ++g) {            // g = -1: the projection, into the first half like an fc1 group
+          mbar_wait(B.tempty(0), te_phase[0] ^ 1); te_phase[0] ^= 1;
+          tc_fence_after();
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.lfull(lr.idx), lr.phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, false, smem_base + M2_OFF_L + lr.idx * 2 * CT_A_HALF, 0u, d0, kc == 0, split, B.lempty(lr.idx));
+            lr.advance();
+          }
+          umma_commit(B.tfull(0));
+          if (g < 0) continue;
+          if (g == 0) { mbar_wait(B.tempty(1), te_phase[1] ^ 1); te_phase[1] ^= 1; tc_fence_after(); }
+          for (int kc = 0; kc < 4; ++kc) {
+            mbar_wait(B.efull(kc), ef_phase);
+            tc_fence_after();
+            mma_chunk2(B, smem_base, wr, true, 0u, d0 + 64u * kc, d1, g == 0 && kc == 0, split, 0u);
+          }
+          ef_phase ^= 1;
+        }
+        umma_commit(B.tfull(1));
+      }
+    }
+  } else {
+    // ---------------- epilogue: 8 warps; lane quarter q, column half hsel ----------------
+    const int e = warp - 4, q = e & 3, hsel = e >> 2;
+    uint32_t tf_phase[2] = {0, 0};
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint8_t* wscr = smem_gen + M2_OFF_T + e * 4096;
+    const int sub = lane >> 3, q8 = lane & 7;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      // ---- x' = x + proj + bp, written in place; LayerNorm sums of x' ----
+      mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+      tc_fence_after();
+      float s1[8], s2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + hsel * 32;
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + lane_off + col0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        __syncwarp();
+        const int n0 = col0 + 4 * q8;
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_p + n0));
+        float4 xin[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = t * 128 + q * 32 + 4 * i + sub;
+          xin[i] = *reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + n0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub;
+          const int mm = t * 128 + q * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+          const float4 v = make_float4(xin[i].x + a.x + bv.x, xin[i].y + a.y + bv.y, xin[i].z + a.z + bv.z, xin[i].w + a.w + bv.w);
+          if (mm < p.M) *reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + n0) = v;
+          s1[i] += (v.x + v.y) + (v.z + v.w);
+          s2[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(B.tempty(0));
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+        }
+      }
+      if (q8 == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) stats[hsel * 128 + q * 32 + 4 * i + sub] = make_float2(s1[i], s2[i]);
+      }
+      __threadfence_block();
+      mbar_arrive(B.xready());
+      // ---- the MLP, as chain_mlp2_kernel ----
+      for (int g = 0; g < 4; ++g) {
+        mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          const uint32_t ta = tmem_base + lane_off + c * 64 + hsel * 32;
+          tmem_ld_32x32(ta, rr);
+          tmem_ld_wait();
+          epi_to_tmem<ZS_ACT_GELU>(ta, rr, p.bias + g * 256 + c * 64 + hsel * 32, split);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(B.efull(c));
+        }
+        tc_fence_before();
+        mbar_arrive(B.tempty(0));
+      }
+      mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = c * 64 + hsel * 32;
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + 256 + lane_off + col0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(wscr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        __syncwarp();
+        const int n0 = col0 + 4 * q8;
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0));
+        float4 xin[8];                       // x' of this thread's own earlier stores (same row / column mapping as above)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mm = t * 128 + q * 32 + 4 * i + sub;
+          xin[i] = *reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + n0);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub;
+          const int mm = t * 128 + q * 32 + rl;
+          const float4 a = *reinterpret_cast<const float4*>(wscr + rl * 128 + ((q8 ^ (rl & 7)) << 4));
+          if (mm < p.M)
+            *reinterpret_cast<float4*>(p.x + (int64_t)mm * p.ldx + n0) =
+                make_float4(xin[i].x + a.x + bv.x, xin[i].y + a.y + bv.y, xin[i].z + a.z + bv.z, xin[i].w + a.w + bv.w);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(B.tempty(1));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // logit = MLPBlocks([xyz, LN(x)]); chunk / blob order as chain_occ_kernel
 __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ2_kernel(ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -2700,6 +2958,22 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
   p.x = x; p.ldx = ldx; p.M = M; p.ln_w = ln_w; p.ln_b = ln_b; p.ln_eps = ln_eps;
   p.blob = reinterpret_cast<const uint8_t*>(blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
   return chain_launch(g_chain_variant ? chain_mlp2_kernel : chain_mlp_kernel, p, as_stream(stream), "zs_chain_mlp_fwd");
+}
+
+extern "C" int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, const void* proj_blob, const float* proj_bias,
+                                 float ln_eps, const void* mlp_blob, const float* b1, const float* b2, int precision, void* stream) {
+  ZS_REQUIRE(x && a_blk && proj_blob && proj_bias && mlp_blob && b1 && b2 && M >= 0, "zs_chain_pmlp_fwd: null pointer");
+  ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_pmlp_fwd: x must be 16B aligned, ldx%%4==0");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(a_blk) & 15) == 0 && (reinterpret_cast<uintptr_t>(proj_blob) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(mlp_blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(proj_bias) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(b1) & 15) == 0 && (reinterpret_cast<uintptr_t>(b2) & 15) == 0,
+             "zs_chain_pmlp_fwd: blobs / biases / a_blk must be 16-byte aligned");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_chain_pmlp_fwd: bad precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.x = x; p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.a_blk = a_blk; p.pblob = reinterpret_cast<const uint8_t*>(proj_blob);
+  p.bias_p = proj_bias; p.blob = reinterpret_cast<const uint8_t*>(mlp_blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
+  return chain_launch(chain_pmlp_kernel, p, as_stream(stream), "zs_chain_pmlp_fwd");
 }
 
 extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float ln_eps, const void* blob, int n_tiles,

@@ -95,6 +95,7 @@ class Implicit(nn.Module):
         self.attention = "qkv"
         # zs_chain_qkvattn_fwd policy: 8 = probabilities in tensor memory (the faster kernel), every contraction three fp16
         # passes; +1 = k, v single-pass (inside the 5e-4 parity budget of profiles/r2_precision_study.md, no measured speed-up)
+        self.fuse_proj = True      # attention output projection + residual inside the MLP kernel (zs_chain_pmlp_fwd; needs flags & 16)
         self.attn_flags = 24       # zs_chain_qkvattn_fwd: 8 = probabilities in tensor memory, 16 = scores in registers + tile-blocked output
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
         self._pw = {}                 # id(nn.Linear) -> ops.PackedWeight (tcgen05 operand images of the weights)
@@ -235,9 +236,14 @@ class Implicit(nn.Module):
                     ab = ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
                                            lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
                                            flags=self.attn_flags, out=None if blocked else a[b * P:(b + 1) * P])
-                    if blocked:
+                    if blocked and self.fuse_proj:       # x += proj(a) and the MLP in one kernel
+                        ops.chain_pmlp(x[b * P:(b + 1) * P], ab, lin_blobs[l][2], blk.attn.proj.bias, blk.norm2.eps, mlp_blobs[l],
+                                       mlp_b1[l], blk.mlp.fc2.bias, self.precision)
+                    elif blocked:
                         xb = x[b * P:(b + 1) * P]
                         ops.chain_lin(ab, lin_blobs[l][2], blk.attn.proj.bias, 1, res=xb, out=xb, precision=self.precision)
+                if blocked and self.fuse_proj:
+                    continue
                 if not blocked:
                     ops.chain_lin(a, lin_blobs[l][2], blk.attn.proj.bias, 1, res=x, out=x, precision=self.precision)   # x += proj(a)
                 ops.chain_mlp(x, None, None, blk.norm2.eps, mlp_blobs[l], mlp_b1[l], blk.mlp.fc2.bias, self.precision)

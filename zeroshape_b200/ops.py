@@ -256,6 +256,18 @@ def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
     return x
 
 
+def chain_pmlp(x, a_blk, proj_blob, proj_bias, ln_eps, mlp_blob, b1, b2, precision="fp16x3"):
+    """In place: x[M,256] <- x' + fc2(GELU(fc1(LayerNorm(x')))), x' = x + unblock(a_blk) proj^T + proj_bias (one tcgen05 kernel)."""
+    assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
+    M = x.shape[0]
+    assert a_blk.is_contiguous() and a_blk.dtype == torch.float32 and a_blk.numel() == ((M + 127) // 128) * 32768
+    assert mlp_blob.numel() == lib.zs_chain_mlp_blob_bytes() and proj_blob.numel() == lib.zs_gemm_tc_packed_bytes(256, 256)
+    _chk(proj_bias, "proj_bias"); _chk(b1, "b1"); _chk(b2, "b2")
+    check(lib.zs_chain_pmlp_fwd(_p(x), x.stride(0), M, _p(a_blk), _p(proj_blob), _p(proj_bias), ln_eps, _p(mlp_blob), _p(b1), _p(b2),
+                                CHAIN_PRECISIONS[precision], _stream()), "zs_chain_pmlp_fwd")
+    return x
+
+
 def point_proj(points, w, bias):
     """points [M,3] -> [M,C] = points @ w[C,3]^T + bias (LinearProj3D), one output-bandwidth-bound launch."""
     _chk(points, "points"); _chk(w, "w"); _chk(bias, "bias")
@@ -655,7 +667,7 @@ class OpTimer:
         with ops.OpTimer() as t:  ...run the hot path...
         t.summary() -> {op name: (launch groups, total ms)}   (synchronises)
     """
-    NAMES = ("point_proj", "chain_lin", "chain_qkvattn", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_occ", "gemm_tc", "gemm",
+    NAMES = ("point_proj", "chain_lin", "chain_qkvattn", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_pmlp", "chain_occ", "gemm_tc", "gemm",
              "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "mha", "bilinear_nhwc", "dense_grid", "axpby", "marching_cubes",
              "mesh_sample", "unproject_normalize", "concat2", "maxpool3x3s2_nhwc", "avgpool_nhwc", "chamfer_nn")
 
