@@ -205,6 +205,10 @@ int zs_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, vo
 /* Multi-head self-attention over T tokens from a packed qkv buffer [B,T,3,heads,hd] -> out [B,T,heads*hd].
  * softmax(q k^T * scale) v.  Replaces timm Attention.forward and the latent branch implicit.py:65-71. */
 int zs_mha_f32(const float* qkv, float* out, int B, int T, int heads, int hd, float scale, void* stream);
+/* The same operation on the tensor cores (csrc/mha_tc.cu): S = Q K^T and O = P V as tcgen05 MMAs with split-fp16 operands
+ * (precision 0: three passes, fp32-grade; 1: one fp16 pass), fp32 accumulation and the probabilities kept in tensor memory.
+ * T <= 208 tokens, hd 32 or 64.  The 12 ViT blocks of the DPT-hybrid backbone (timm Block, model/depth/vit.py:149-150). */
+int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int heads, int hd, float scale, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit decoder (model/shape/implicit.py:251-288), query-point side.

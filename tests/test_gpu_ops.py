@@ -120,7 +120,26 @@ def test_mha(cuda, B, T, heads, hd):
     qkv = torch.randn(B, T, 3 * C, generator=g)
     q, k, v = qkv.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
     ref = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v
-    _close(ops.mha(qkv.to(cuda), heads), ref.transpose(1, 2).reshape(B, T, C))
+    _close(ops.mha(qkv.to(cuda), heads, tc=False), ref.transpose(1, 2).reshape(B, T, C))
+
+
+@pytest.mark.parametrize("B,T,heads,hd", [(2, 197, 12, 64), (1, 197, 8, 32), (3, 50, 4, 64), (1, 1, 2, 32), (2, 208, 3, 64), (1, 129, 1, 32)])
+def test_mha_on_the_tensor_cores(cuda, B, T, heads, hd):
+    """zs_mha_tc_f32 (tcgen05, split-fp16 operands, probabilities in tensor memory) vs fp64 and vs the FFMA kernel."""
+    if torch.cuda.get_device_capability(0)[0] != 10:
+        pytest.skip("tcgen05 needs sm_100")
+    from zeroshape_b200 import ops
+    g = torch.Generator().manual_seed(T * 7 + heads)
+    C = heads * hd
+    qkv = torch.randn(B, T, 3 * C, generator=g) * 1.3
+    q, k, v = qkv.double().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C)
+    out = ops.mha(qkv.to(cuda), heads, tc=True)
+    err = (out.cpu().double() - ref).abs().max().item()
+    ffma = (ops.mha(qkv.to(cuda), heads, tc=False).cpu().double() - ref).abs().max().item()
+    one = (ops.mha(qkv.to(cuda), heads, tc=True, precision="fp16").cpu().double() - ref).abs().max().item()
+    print(f"mha_tc B={B} T={T} heads={heads} hd={hd}: max err fp16x3 {err:.2e}, fp16 {one:.2e}, FFMA kernel {ffma:.2e} (scale {ref.abs().max().item():.2f})")
+    assert err < 4e-6 * ref.abs().max().item() and one < 4e-3 * ref.abs().max().item()
 
 
 def test_geometry_glue(cuda):

@@ -34,6 +34,8 @@ FLOP = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused"
         "chain_occ": 2 * 724224, "chain_pmlp": 2 * (524288 + 65536), "gemm_tc": 0, "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
 with torch.no_grad():
     lat = net.prepare_latents(lat_in)
+    if os.environ.get("ZS_CHAIN_DBG"):
+        lib.zs_debug_chain_variant(int(os.environ["ZS_CHAIN_DBG"]))
     if ONCE:
         for _ in range(3):
             net._points_chain(lat, pts, tc=True, sigmoid=True)

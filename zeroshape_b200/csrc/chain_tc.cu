@@ -1773,7 +1773,9 @@ __global__ void __maxnreg__(96) chain_qkvattn2_kernel(ChainParams p) {
       const int m0 = t * 128 + warp * 16;
       float sc = 1.f, sh = 0.f;
       if (tr0) trace_ev(p.trace, 1, tn, 14);
-      if (t + (int)gridDim.x < n_tiles) prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+      // the REGS variant does NOT prefetch the next tile into L2: measured (ncu, 129^3 pass) 2.69 GB of DRAM reads with the prefetch
+      // against the algorithmic 2.20 GB without, at the same run time (the prefetched lines do not survive a whole tile time)
+      if (!REGS && !(p.flags & 32) && t + (int)gridDim.x < n_tiles) prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
       warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
       fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
       if (tr0) trace_ev(p.trace, 1, tn, 15);
@@ -2599,9 +2601,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p
       const int m0 = t * 128 + warp * 32;
       if (t + (int)gridDim.x < n_tiles) {
         const char* nb = reinterpret_cast<const char*>(p.a_blk) + (size_t)(t + gridDim.x) * 131072 + warp * 32768 + lane * 128;
+        // OFF by default: measured with ncu on the 129^3 pass, a whole-tile-ahead L2 prefetch of A and x nearly DOUBLES the DRAM
+        // reads of this kernel (8.19 GB vs the algorithmic 4.40 GB: the lines are evicted again before their demand loads, the
+        // working set of 148 CTAs x [A, x, x' re-read four times, next A, next x] exceeds what L2 keeps) and is 2 % slower
+        if (p.flags & 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + i * 4096));
-        prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
+          for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + i * 4096));
+        }
+        if (p.flags & 4) prefetch_rows_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
       }
       fetch_chunk32_blk(p.a_blk, t, warp, 0, lane, buf);
       for (int kc = 0; kc < 4; ++kc) {
@@ -2929,6 +2936,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ2_kernel(ChainParams p
 }
 
 static unsigned long long* g_chain_trace = nullptr;   // debug only (zs_debug_chain_trace)
+static int g_chain_dbg = 0;       // zs_debug_chain_variant bits 1.. : experiment switches (chain_pmlp_kernel: 2 = L2-prefetch the next A tile, 4 = the next x tile; 8 = chain_qkvattn2_kernel without its x prefetch)
 static int g_chain_variant = 1;   // zs_chain_mlp_fwd / zs_chain_occ_fwd: 1 = activations in tensor memory (chain_*2_kernel), 0 = ring E
 
 static int chain_launch(void (*kern)(ChainParams), ChainParams p, cudaStream_t st, const char* name, int threads = CT_THREADS) {
@@ -2973,6 +2981,7 @@ extern "C" int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, c
   ChainParams p{};
   p.x = x; p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.a_blk = a_blk; p.pblob = reinterpret_cast<const uint8_t*>(proj_blob);
   p.bias_p = proj_bias; p.blob = reinterpret_cast<const uint8_t*>(mlp_blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
+  p.flags = g_chain_dbg;
   return chain_launch(chain_pmlp_kernel, p, as_stream(stream), "zs_chain_pmlp_fwd");
 }
 
@@ -2999,7 +3008,7 @@ extern "C" int zs_chain_lin_fwd(const float* x, int ldx, int M, int do_ln, float
 // MMA thread, loader thread 0 and epilogue warp 4 lane 0 of CTA 0 into it (tools/trace_chain.py).  Not thread-safe.
 extern "C" int zs_debug_chain_trace(unsigned long long* buf) { g_chain_trace = buf; return ZS_OK; }
 // A/B switch of the two MLP kernels (tools/diag_decoder.py, tests): 1 (default) = TMEM-resident activations, 0 = smem ring E
-extern "C" int zs_debug_chain_variant(int v) { g_chain_variant = v != 0; return ZS_OK; }
+extern "C" int zs_debug_chain_variant(int v) { g_chain_variant = (v & 1) != 0; g_chain_dbg = v & ~1; return ZS_OK; }
 
 extern "C" int zs_chain_attn_fwd(const float* qkv, int ld_qkv, int M, const void* Kblob, const void* Vblob, int n_keys,
                                  float scale, float* O, int precision, void* stream) {
@@ -3048,7 +3057,7 @@ extern "C" int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps
   ChainParams p{};
   p.x = const_cast<float*>(x); p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.blob = reinterpret_cast<const uint8_t*>(Wblob);
   p.bias = bias_qkv; p.kblob = reinterpret_cast<const uint8_t*>(Kblob); p.vblob = reinterpret_cast<const uint8_t*>(Vblob);
-  p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = ldo; p.precision = precision; p.flags = flags;
+  p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = ldo; p.precision = precision; p.flags = flags | ((g_chain_dbg & 8) ? 32 : 0);
   // flags & 8: the variant that keeps the probabilities in tensor memory (chain_qkvattn2_kernel); & 16: its softmax role with
   // the scores held in registers (one tensor-memory sweep per head)
   if (flags & 16) return chain_launch(chain_qkvattn2_kernel<true>, p, as_stream(stream), "zs_chain_qkvattn_fwd", QA3_THREADS);

@@ -1,0 +1,251 @@
+// Token self-attention on the tensor cores (tcgen05 + tensor memory): softmax(q k^T * scale) v for the 12 ViT blocks of the
+// DPT-hybrid backbone (timm Attention.forward inside Block, model/depth/vit.py:149-150) and the latent branch of the implicit
+// decoder (model/shape/implicit.py:65-71).  T <= 208 tokens (197 = 14 x 14 + cls), head dim 32 or 64.
+//
+// One CTA per (image, head, 128-query tile).  All 256 threads convert the head's q tile, k and v from the packed fp32 qkv buffer
+// into split-fp16 UMMA operand tiles in shared memory (v transposed: it is the B operand of P V, K-major over the keys, stored as
+// [Vh rows | Vl rows] so that Ph Vh and Ph Vl are one instruction).  Then, the construction of chain_qkvattn2_kernel:
+//   S = Q K^T              (M = 128, N = 208, K = head dim; Qh Kh + Ql Kh + Qh Kl, fp32 accumulation in tensor memory)
+//   softmax                (4 warps, thread = query row: max sweep, then exp2 sweep that overwrites the scores IN PLACE with the
+//                           split-fp16 probabilities, 32 score columns -> 16 packed hi + 16 packed lo columns)
+//   O = P V                (A operand read from tensor memory, tcgen05.mma [d], [a], b: 13 K-steps of 16 keys)
+//   out = O / rowsum       (thread = row, 16-byte stores)
+// No pipelining: a CTA lives for one tile (~6 MFLOP); the launch fills the SMs with B x heads x 2 CTAs.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace zs {
+using namespace tc;
+
+constexpr int MT_THREADS = 256;
+constexpr int MT_OFF_Q = 0;                       // q tile  hi | lo : 2 x 128 rows x 128 B
+constexpr int MT_OFF_K = 32 * 1024;               // k       hi | lo : 2 x 208 (256) rows x 128 B
+constexpr int MT_OFF_V = MT_OFF_K + 64 * 1024;    // v^T: 4 key chunks x [Vh rows | Vl rows] x 128 B  (<= 4 x 16 KB)
+constexpr int MT_OFF_BAR = MT_OFF_V + 64 * 1024;
+constexpr int MT_SMEM = MT_OFF_BAR + 64 + 1024;   // + slack for the 1024-byte alignment of the base
+
+struct MhaTcParams {
+  const float* qkv; float* out; int B, T, heads, hd; float scale; int precision;
+};
+
+template <int NK, bool MASKED>
+__device__ __forceinline__ void mt_exp_tmem(const uint32_t* rr, int k0, int n_keys, float sl2, float mxs, float2& sum2,
+                                            uint32_t taddr, bool split) {
+  uint32_t hi[NK / 2], lo[NK / 2];
+#pragma unroll
+  for (int j = 0; j < NK / 2; ++j) {
+    const int i = 2 * j;
+    const float2 a = fma2(make_float2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), bc2(sl2), bc2(-mxs));
+    float2 v = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+    if (MASKED) { if (k0 + i >= n_keys) v.x = 0.f; if (k0 + i + 1 >= n_keys) v.y = 0.f; }
+    sum2 = add2(sum2, v);
+    split_f16x2(v.x, v.y, hi[j], lo[j]);
+  }
+  if constexpr (NK == 32) {
+    tmem_st_32x16(taddr, hi);
+    if (split) tmem_st_32x16(taddr + 16, lo);
+  } else {
+    tmem_st_32x8(taddr, hi);
+    if (split) tmem_st_32x8(taddr + 8, lo);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MT_THREADS, 1) mha_tc_kernel(MhaTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_s = smem_base + MT_OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const int T = p.T, C = p.heads * HD;
+  const int bh = blockIdx.x, b = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.y * 128;
+  constexpr int VCH = 2 * HD * 128;                 // bytes of one 64-key chunk of v^T: (Vh | Vl) rows x 128 B
+  const float* base = p.qkv + (int64_t)b * T * 3 * C + h * HD;
+
+  if (threadIdx.x == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+
+  // ---- operand tiles: thread = (token, 8 consecutive dims) ----
+  constexpr int CPR = HD / 8;                        // 16-byte fp16 chunks per row
+  for (int i = threadIdx.x; i < 128 * CPR; i += MT_THREADS) {
+    const int r = i / CPR, c = i % CPR, t = q0 + r;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (t < T) {
+      const float4* src = reinterpret_cast<const float4*>(base + (int64_t)t * 3 * C + 8 * c);
+      x0 = __ldg(src); x1 = __ldg(src + 1);
+    }
+    uint4 hi, lo;
+    split_f16x2(x0.x, x0.y, hi.x, lo.x); split_f16x2(x0.z, x0.w, hi.y, lo.y);
+    split_f16x2(x1.x, x1.y, hi.z, lo.z); split_f16x2(x1.z, x1.w, hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(r, c);
+    *reinterpret_cast<uint4*>(smem + MT_OFF_Q + off) = hi;
+    *reinterpret_cast<uint4*>(smem + MT_OFF_Q + 16384 + off) = lo;
+  }
+  for (int i = threadIdx.x; i < 208 * CPR; i += MT_THREADS) {
+    const int j = i / CPR, c = i % CPR;
+    float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, v0 = k0, v1 = k0;
+    if (j < T) {
+      const float4* ks = reinterpret_cast<const float4*>(base + (int64_t)j * 3 * C + C + 8 * c);
+      const float4* vs = reinterpret_cast<const float4*>(base + (int64_t)j * 3 * C + 2 * C + 8 * c);
+      k0 = __ldg(ks); k1 = __ldg(ks + 1); v0 = __ldg(vs); v1 = __ldg(vs + 1);
+    }
+    uint4 hi, lo;
+    split_f16x2(k0.x, k0.y, hi.x, lo.x); split_f16x2(k0.z, k0.w, hi.y, lo.y);
+    split_f16x2(k1.x, k1.y, hi.z, lo.z); split_f16x2(k1.z, k1.w, hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(j, c);
+    *reinterpret_cast<uint4*>(smem + MT_OFF_K + off) = hi;
+    *reinterpret_cast<uint4*>(smem + MT_OFF_K + 32768 + off) = lo;
+    // v^T: element (dim d, key j) -> row d (hi) / HD + d (lo) of key chunk j >> 6, fp16 column j & 63
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint8_t* vch = smem + MT_OFF_V + (j >> 6) * VCH;
+    const int kc = j & 63;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int d = 8 * c + u;
+      const __half hh = __float2half_rn(vv[u]);
+      const __half ll = __float2half_rn(vv[u] - __half2float(hh));
+      *reinterpret_cast<__half*>(vch + swizzle128_offset(d, kc >> 3) + (kc & 7) * 2) = hh;
+      *reinterpret_cast<__half*>(vch + swizzle128_offset(HD + d, kc >> 3) + (kc & 7) * 2) = ll;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MT_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_o = tmem_base + 256;
+
+  if (warp == 4 && lane == 0) {
+    // ---- S = Q K^T ----
+    const uint32_t idesc_s = umma_idesc_f16(128, 208);
+    const uint64_t qh = umma_desc_sw128(smem_base + MT_OFF_Q), ql = umma_desc_sw128(smem_base + MT_OFF_Q + 16384);
+    const uint64_t kh = umma_desc_sw128(smem_base + MT_OFF_K), kl = umma_desc_sw128(smem_base + MT_OFF_K + 32768);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) {
+      umma_bf16(d_s, qh + 2 * k, kh + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+      if (split) {
+        umma_bf16(d_s, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
+        umma_bf16(d_s, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
+      }
+    }
+    umma_commit(bar_s);
+  }
+
+  float inv = 0.f;
+  if (warp < 4) {
+    // ---- softmax: thread = query row ----
+    const uint32_t s_tm = d_s + ((uint32_t)(warp * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -3.0e38f;
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(s_tm + 32 * c, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (32 * c + j < T) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    {
+      uint32_t rr[16];
+      tmem_ld_32x16(s_tm + 192, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (192 + j < T) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    const float mxs = mx * sl2;
+    float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(s_tm + 32 * c, rr);
+      tmem_ld_wait();
+      if (32 * c + 32 <= T) mt_exp_tmem<32, false>(rr, 32 * c, T, sl2, mxs, sum2, s_tm + 32 * c, split);
+      else mt_exp_tmem<32, true>(rr, 32 * c, T, sl2, mxs, sum2, s_tm + 32 * c, split);
+    }
+    {
+      uint32_t rr[16];
+      tmem_ld_32x16(s_tm + 192, rr);
+      tmem_ld_wait();
+      mt_exp_tmem<16, true>(rr, 192, T, sl2, mxs, sum2, s_tm + 192, split);
+    }
+    tmem_st_wait();
+    inv = 1.0f / (sum2.x + sum2.y);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 4 && lane == 0) {
+    // ---- O = P V: A = the probabilities in tensor memory, B = v^T chunks; Ph [Vh | Vl] is one N = 2 HD instruction ----
+    const uint32_t idesc_hi = split ? umma_idesc_f16(128, 2 * HD) : umma_idesc_f16(128, HD), idesc_lo = umma_idesc_f16(128, HD);
+#pragma unroll 1
+    for (int j = 0; j < 13; ++j) {                  // K-step j = keys 16 j .. 16 j + 15
+      const uint32_t a_hi = d_s + 32u * (j >> 1) + 8u * (j & 1);
+      const uint32_t a_lo = a_hi + (j == 12 ? 8u : 16u);
+      const uint64_t vv = umma_desc_sw128(smem_base + MT_OFF_V + (j >> 2) * VCH) + 2 * (j & 3);
+      umma_ts(d_o, a_hi, vv, idesc_hi, j > 0 ? 1u : 0u);
+      if (split) umma_ts(d_o, a_lo, vv, idesc_lo, 1u);
+    }
+    umma_commit(bar_o);
+  }
+
+  if (warp < 4) {
+    const uint32_t o_tm = d_o + ((uint32_t)(warp * 32) << 16);
+    const int t = q0 + warp * 32 + lane;
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    float* dst = p.out + ((int64_t)b * T + (t < T ? t : 0)) * C + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rr[16], r2[16];
+      tmem_ld_32x16(o_tm + 16 * c, rr);
+      if (split) tmem_ld_32x16(o_tm + HD + 16 * c, r2);
+      tmem_ld_wait();
+      if (t < T) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = __uint_as_float(rr[4 * j + i]);
+            if (split) a += __uint_as_float(r2[4 * j + i]);
+            o[i] = a * inv;
+          }
+          *reinterpret_cast<float4*>(dst + 16 * c + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace zs
+
+using namespace zs;
+
+extern "C" int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int heads, int hd, float scale, int precision,
+                             void* stream) {
+  ZS_REQUIRE(qkv && out && B >= 0 && heads > 0, "zs_mha_tc_f32: null pointer / bad sizes");
+  ZS_REQUIRE(T >= 1 && T <= 208 && (hd == 32 || hd == 64), "zs_mha_tc_f32: T must be in [1, 208] and the head dim 32 or 64");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "zs_mha_tc_f32: qkv / out must be 16-byte aligned");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_mha_tc_f32: bad precision");
+  if (B == 0) return ZS_OK;
+  MhaTcParams p{qkv, out, B, T, heads, hd, scale, precision};
+  dim3 grid(B * heads, (T + 127) / 128);
+  if (hd == 64) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+    mha_tc_kernel<64><<<grid, MT_THREADS, MT_SMEM, as_stream(stream)>>>(p);
+  } else {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+    mha_tc_kernel<32><<<grid, MT_THREADS, MT_SMEM, as_stream(stream)>>>(p);
+  }
+  ZS_CUDA_CHECK_LAUNCH("zs_mha_tc_f32");
+  return ZS_OK;
+}

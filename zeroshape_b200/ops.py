@@ -456,13 +456,19 @@ def nhwc_to_nchw(x):
     return y
 
 
-def mha(qkv, heads):
-    """qkv [B,T,3*C] -> [B,T,C] (timm Attention core, softmax(q k^T / sqrt(hd)) v)."""
+def mha(qkv, heads, tc=None, precision="fp16x3"):
+    """qkv [B,T,3*C] -> [B,T,C] (timm Attention core, softmax(q k^T / sqrt(hd)) v).  `tc`: None = ENCODER_ENGINE policy
+    (tcgen05 kernel zs_mha_tc_f32 when the shape fits: T <= 208, head dim 32 / 64), False = the fp32 FFMA kernel."""
     _chk(qkv, "qkv")
     B, T, C3 = qkv.shape
     C = C3 // 3
     hd = C // heads
     out = torch.empty(B, T, C, device=qkv.device, dtype=torch.float32)
+    if tc is None:
+        tc = _encoder_tc()
+    if tc and T <= 208 and hd in (32, 64):
+        check(lib.zs_mha_tc_f32(_p(qkv), _p(out), B, T, heads, hd, hd ** -0.5, CHAIN_PRECISIONS[precision], _stream()), "zs_mha_tc_f32")
+        return out
     check(lib.zs_mha_f32(_p(qkv), _p(out), B, T, heads, hd, hd ** -0.5, _stream()), "zs_mha_f32")
     return out
 
