@@ -148,9 +148,20 @@ int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, const float* l
  * output projection + residual (model/shape/implicit.py:74, ImplFuncBlock :105) fused in front of zs_chain_mlp_fwd.
  * a_blk = the tile-blocked attention output of zs_chain_qkvattn_fwd (flags & 16), ceil(M/128)*128*256 floats;
  * proj_blob = zs_gemm_tc_pack_fmt(proj.weight [256,256], fmt 1); mlp_blob / b1 / b2 as zs_chain_mlp_fwd (norm2's affine
- * folded into fc1).  The LayerNorm variance is the one-pass E[x^2] - mean^2 of pairwise-reduced fp32 sums. */
+ * folded into fc1).  The LayerNorm variance is the one-pass E[x^2] - mean^2 of pairwise-reduced fp32 sums.
+ * Points mode (points, pp both non-null; the FIRST decoder block): the incoming residual stream is x = LinearProj3D(points)
+ * (model/shape/implicit.py:128-131) and is recomputed from the [M,3] points instead of being read: pp = [4][256] floats =
+ * point_proj.weight[:,0] | [:,1] | [:,2] | point_proj.bias; x is then written only (x' and the result). */
 int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, const void* proj_blob, const float* proj_bias,
-                      float ln_eps, const void* mlp_blob, const float* b1, const float* b2, int precision, void* stream);
+                      float ln_eps, const void* mlp_blob, const float* b1, const float* b2, const float* points,
+                      const float* pp, int precision, void* stream);
+/* zs_chain_qkvattn_fwd (flags 8 | 16) for the first block in points mode: LayerNorm(LinearProj3D(points)) is formed in the
+ * loader warps from the points, pp (as above) and pp_stat = 14 floats: the means m0 m1 m2 mb of the four rows of pp over the
+ * 256 channels, then their (biased) covariances C00 C11 C22 Cbb, C01 C02 C12, C0b C1b C2b -- the LayerNorm mean and variance
+ * of a row are a linear / quadratic form of its point.  No [M,256] input exists at all. */
+int zs_chain_qkvattn_pts_fwd(const float* points, int M, const float* pp, const float* pp_stat, float ln_eps, const void* Wblob,
+                             const float* bias_qkv, const void* Kblob, const void* Vblob, int n_keys, float scale, float* O,
+                             int precision, int flags, void* stream);
 int zs_chain_occ_fwd(const float* x, int ldx, const float* points, int M, const float* ln_w, const float* ln_b,
                      float ln_eps, const void* blob, const float* biases, const float* w8, float b8,
                      float* out, int apply_sigmoid, int precision, void* stream);

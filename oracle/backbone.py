@@ -223,7 +223,7 @@ def intr_param2mtx(params, H, W):
     """graph_shape.py:89-113."""
     B = len(params)
     f = 1.3875
-    K = torch.zeros(3, 3).float().unsqueeze(0).repeat(B, 1, 1)
+    K = torch.zeros(3, 3, device=params.device).float().unsqueeze(0).repeat(B, 1, 1)
     K[:, 2, 2] += 1
     sf = torch.pow(4., torch.tanh(params[:, 0]))
     K[:, 0, 0] += f * W * sf
@@ -236,7 +236,8 @@ def intr_param2mtx(params, H, W):
 def unproj_depth(depth, intr):
     """utils/camera.py:88-108."""
     B, _, H, W = depth.shape
-    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=depth.device), torch.arange(W, dtype=torch.float32, device=depth.device),
+                            indexing="ij")
     grid = torch.stack([xx, yy, torch.ones_like(yy)], dim=-1).view(-1, 3).unsqueeze(0).repeat(B, 1, 1)
     rays = torch.linalg.inv(intr).float() @ grid.permute(0, 2, 1)
     return rays.permute(0, 2, 1) * depth.view(B, H * W, 1)

@@ -291,10 +291,42 @@ def test_qkvattn_kernel_matches_reference_math(cuda, M):
         err = (out.cpu().double() - ref).abs().max().item()
         print(f"qkvattn M={M} {prec} flags={flags}: max err {err:.3e} (scale {scale:.3f})")
         assert err < tol * scale, (prec, flags, err)
+    # points mode (first decoder block): x = LinearProj3D(points) recomputed inside the kernel, LayerNorm factors in closed form
+    pts = torch.rand(M, 3, generator=g) * 3 - 1.5
+    w3, b3 = torch.randn(256, 3, generator=g), torch.randn(256, generator=g)
+    x3 = ops.point_proj(pts.to(cuda), w3.to(cuda), b3.to(cuda))
+    pp, pp_stat = ops.point_proj_tables(w3.to(cuda), b3.to(cuda))
+    o_ref = ops.unblock_rows(ops.chain_qkvattn(x3, wb, b.to(cuda), kb, vb, L, 32 ** -0.5, ln_eps=1e-6, flags=24), M)
+    o_pts = ops.unblock_rows(ops.chain_qkvattn_pts(pts.to(cuda), pp, pp_stat, wb, b.to(cuda), kb, vb, L, 32 ** -0.5, ln_eps=1e-6), M)
+    d = (o_pts - o_ref).abs().max().item()
+    print(f"qkvattn points mode M={M}: max diff to the x-reading kernel {d:.3e} (scale {o_ref.abs().max().item():.3f})")
+    assert d < 8e-6 * o_ref.abs().max().item()
     # row-strided output view
     wide = torch.zeros(M, 300, device=cuda)
     ops.chain_qkvattn(x.to(cuda), wb, b.to(cuda), kb, vb, L, 32 ** -0.5, out=wide[:, 4:260])
     assert (wide[:, 4:260].cpu().double() - ref).abs().max().item() < 8e-6 * scale and wide[:, :4].abs().max().item() == 0
+
+
+def test_decoder_chain_points_mode_equals_the_materialised_x(cuda):
+    """fold_point_proj (no point_proj launch, x recomputed in the first block's kernels) vs the path that writes x first."""
+    _need_sm100()
+    from oracle.implicit import implicit_init
+    from zeroshape_b200.model.shape.implicit import Implicit
+    sd = implicit_init(seed=16)
+    m = Implicit(196, latent_dim=256, n_channels=256, n_blocks_attn=2, n_layers_mlp=8, num_heads=8, skip_in=[2, 4, 6],
+                 pos_perlayer=False)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    m.engine = "chain"
+    g = torch.Generator().manual_seed(9)
+    lat, pts = torch.randn(2, 197, 256, generator=g).to(cuda), (torch.rand(2, 3001, 3, generator=g) * 3 - 1.5).to(cuda)
+    outs = {}
+    for fold in (True, False):
+        m.fold_point_proj = fold
+        outs[fold], _ = m(lat, None, pts, need_attn=False)
+    d = (outs[True] - outs[False]).abs().max().item()
+    print(f"points mode vs materialised x: max |diff| of the logits {d:.3e} (logit scale {outs[False].abs().max().item():.3f})")
+    assert d < 2e-5 * outs[False].abs().max().item()
 
 
 @pytest.mark.parametrize("attention,flags", [("qkv", 0), ("qkv", 8), ("qkv", 24), ("qkv", 1), ("qkv", 9), ("qkv", 7), ("fused", 0)])

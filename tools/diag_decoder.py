@@ -41,11 +41,11 @@ with torch.no_grad():
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()
         sys.exit(0)
-    variants = [("qkv", 24, 1), ("qkv", 24, 0), ("qkv", 24, 1), ("qkv", 24, 0)]     # third field: proj fused into the MLP kernel
+    variants = [("qkv", 24, 1), ("qkv", 24, 0), ("qkv", 24, 1), ("qkv", 24, 0)]     # third field: point_proj folded into the first block
     for attention, flags, mlp_variant in variants:
         fused = True
         net.attention, net.attn_flags = attention, flags
-        net.fuse_proj = bool(mlp_variant)
+        net.fold_point_proj = bool(mlp_variant)
         mlp_variant = 1
         lib.zs_debug_chain_variant(mlp_variant)
         for _ in range(3):

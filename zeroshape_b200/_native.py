@@ -72,7 +72,8 @@ SIGNATURES = {
     "zs_chain_occ_blob_bytes": (c_size_t, []),
     "zs_chain_mlp_fwd": (c_int, [P, c_int, c_int, P, P, c_float, P, P, P, c_int, P]),
     "zs_chain_occ_fwd": (c_int, [P, c_int, P, c_int, P, P, c_float, P, P, P, c_float, P, c_int, c_int, P]),
-    "zs_chain_pmlp_fwd": (c_int, [P, c_int, c_int, P, P, P, c_float, P, P, P, c_int, P]),
+    "zs_chain_pmlp_fwd": (c_int, [P, c_int, c_int, P, P, P, c_float, P, P, P, P, P, c_int, P]),
+    "zs_chain_qkvattn_pts_fwd": (c_int, [P, c_int, P, P, c_float, P, P, P, P, c_int, c_float, P, c_int, c_int, P]),
     "zs_conv2d_nhwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_conv2d_nhwc_tc": (c_int, [P, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int,

@@ -49,6 +49,11 @@ struct ChainParams {
   const uint8_t* kblob; const uint8_t* vblob; int n_keys; float scale; int flags;
   // chain_pmlp_kernel: tile-blocked attention output, packed proj weight (4 K-chunk pairs), proj bias
   const float* a_blk; const uint8_t* pblob; const float* bias_p;
+  // "points mode" of the first block (chain_qkvattn2_kernel<true> with flags & 64, chain_pmlp_kernel with pp != nullptr): the
+  // residual stream entering the block is x = LinearProj3D(points) (model/shape/implicit.py:128-131) and is RECOMPUTED from the
+  // 12-byte points instead of being read (and first written by a separate launch): pp = [4][256] = w[:,0] | w[:,1] | w[:,2] | bias,
+  // pp_stat = the 14 moments of those four rows that give the LayerNorm mean / variance of a row in closed form
+  const float* pp; const float* pp_stat;
 };
 
 struct Bars {
@@ -560,6 +565,40 @@ __device__ __forceinline__ void store_chunk16(uint8_t* slot, int w, int lane, co
     *reinterpret_cast<uint2*>(slot + off) = hi;
     if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
   }
+}
+
+// points mode: the chunk's values are LayerNorm(LinearProj3D(point)) of the rows' points, formed as four packed FMAs per pair of
+// columns with the row's LayerNorm scale folded into the point (w0 (x s) + w1 (y s) + w2 (z s) + (b s + h)); lane L < 16 holds the
+// point / LayerNorm factors of row m0 + L
+__device__ __forceinline__ void store_chunk16_pts(uint8_t* slot, int w, int lane, int kc, float px, float py, float pz, float sc, float sh,
+                                                  const float* __restrict__ pp, bool split) {
+  const int sub = lane >> 4, q = lane & 15;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(pp + kc * 64) + q), w1 = __ldg(reinterpret_cast<const float4*>(pp + 256 + kc * 64) + q);
+  const float4 w2 = __ldg(reinterpret_cast<const float4*>(pp + 512 + kc * 64) + q), bb = __ldg(reinterpret_cast<const float4*>(pp + 768 + kc * 64) + q);
+  const float xs_l = px * sc, ys_l = py * sc, zs_l = pz * sc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int rl = 2 * j + sub;
+    const float2 x = bc2(__shfl_sync(0xffffffffu, xs_l, rl)), y = bc2(__shfl_sync(0xffffffffu, ys_l, rl)), z = bc2(__shfl_sync(0xffffffffu, zs_l, rl));
+    const float2 s = bc2(__shfl_sync(0xffffffffu, sc, rl)), h = bc2(__shfl_sync(0xffffffffu, sh, rl));
+    const float2 v0 = fma2(make_float2(w2.x, w2.y), z, fma2(make_float2(w1.x, w1.y), y, fma2(make_float2(w0.x, w0.y), x, fma2(make_float2(bb.x, bb.y), s, h))));
+    const float2 v1 = fma2(make_float2(w2.z, w2.w), z, fma2(make_float2(w1.z, w1.w), y, fma2(make_float2(w0.z, w0.w), x, fma2(make_float2(bb.z, bb.w), s, h))));
+    uint2 hi, lo;
+    split_f16x2(v0.x, v0.y, hi.x, lo.x);
+    split_f16x2(v1.x, v1.y, hi.y, lo.y);
+    const uint32_t off = swizzle128_offset(16 * w + rl, q >> 1) + ((q & 1) << 3);
+    *reinterpret_cast<uint2*>(slot + off) = hi;
+    if (split) *reinterpret_cast<uint2*>(slot + CT_A_HALF + off) = lo;
+  }
+}
+// LayerNorm factors (rstd, -mean * rstd) of LinearProj3D(point) in closed form from the moments of the projection's rows
+__device__ __forceinline__ void pts_ln_factors(const float* __restrict__ st, float x, float y, float z, float eps, float& sc, float& sh) {
+  const float mean = fmaf(x, __ldg(st), fmaf(y, __ldg(st + 1), fmaf(z, __ldg(st + 2), __ldg(st + 3))));
+  float var = fmaf(x * x, __ldg(st + 4), fmaf(y * y, __ldg(st + 5), fmaf(z * z, __ldg(st + 6), __ldg(st + 7))));
+  var += 2.0f * fmaf(x * y, __ldg(st + 8), fmaf(x * z, __ldg(st + 9), fmaf(y * z, __ldg(st + 10),
+                fmaf(x, __ldg(st + 11), fmaf(y, __ldg(st + 12), z * __ldg(st + 13))))));
+  sc = rsqrtf(fmaxf(var, 0.f) + eps);
+  sh = -mean * sc;
 }
 
 // The same 64-column chunk of 16 rows from a TILE-BLOCKED matrix (the attention output of chain_qkvattn2_kernel<true>: the
@@ -1776,19 +1815,31 @@ __global__ void __maxnreg__(96) chain_qkvattn2_kernel(ChainParams p) {
       // the REGS variant does NOT prefetch the next tile into L2: measured (ncu, 129^3 pass) 2.69 GB of DRAM reads with the prefetch
       // against the algorithmic 2.20 GB without, at the same run time (the prefetched lines do not survive a whole tile time)
       if (!REGS && !(p.flags & 32) && t + (int)gridDim.x < n_tiles) prefetch_rows16_l2(p.x, p.ldx, m0 + (int)gridDim.x * 128, p.M, 0, lane);
-      warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
-      fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      const bool pts = REGS && (p.flags & 64);       // x = LinearProj3D(points), recomputed (first block)
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (pts) {
+        sc = 0.f; sh = 0.f;
+        if (lane < 16 && m0 + lane < p.M) {
+          const float* pt = p.points + (int64_t)(m0 + lane) * 3;
+          px = __ldg(pt); py = __ldg(pt + 1); pz = __ldg(pt + 2);
+          pts_ln_factors(p.pp_stat, px, py, pz, p.ln_eps, sc, sh);
+        }
+      } else {
+        warp_ln_stats16(p.x, p.ldx, m0, p.M, p.ln_eps, lane, sc, sh);
+        fetch_chunk16(p.x, p.ldx, m0, p.M, 0, lane, buf);
+      }
       if (tr0) trace_ev(p.trace, 1, tn, 15);
       for (int i = 0; i < 16; ++i) {
         if (tr0) trace_ev(p.trace, 1, tn, 10);
         mbar_wait(B.lempty(lr.idx), lr.phase ^ 1);
         if (tr0) trace_ev(p.trace, 1, tn, 11);
-        store_chunk16(smem_gen + QB_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh, split);
+        if (pts) store_chunk16_pts(smem_gen + QB_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, i & 3, px, py, pz, sc, sh, p.pp, split);
+        else store_chunk16(smem_gen + QB_OFF_L + lr.idx * 2 * CT_A_HALF, warp, lane, buf, true, sc, sh, split);
         fence_proxy_async_smem();
         mbar_arrive(B.lfull(lr.idx));
         if (tr0) trace_ev(p.trace, 1, tn, 12);
         lr.advance();
-        if (i + 1 < 16) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
+        if (!pts && i + 1 < 16) fetch_chunk16(p.x, p.ldx, m0, p.M, ((i + 1) & 3) * 64, lane, buf);
       }
     }
   } else if (warp == 17) {
@@ -2705,10 +2756,23 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p
         const int n0 = col0 + 4 * q8;
         const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_p + n0));
         float4 xin[8];
+        if (p.pp != nullptr) {              // points mode: the residual is LinearProj3D(points), recomputed (see ChainParams)
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.pp + n0)), w1 = __ldg(reinterpret_cast<const float4*>(p.pp + 256 + n0));
+          const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.pp + 512 + n0)), bb = __ldg(reinterpret_cast<const float4*>(p.pp + 768 + n0));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int mm = t * 128 + q * 32 + 4 * i + sub;
-          xin[i] = *reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + n0);
+          for (int i = 0; i < 8; ++i) {
+            const int mm = t * 128 + q * 32 + 4 * i + sub;
+            const float* pt = p.points + (int64_t)(mm < p.M ? mm : 0) * 3;
+            const float x = __ldg(pt), y = __ldg(pt + 1), z = __ldg(pt + 2);
+            xin[i] = make_float4(fmaf(w2.x, z, fmaf(w1.x, y, w0.x * x)) + bb.x, fmaf(w2.y, z, fmaf(w1.y, y, w0.y * x)) + bb.y,
+                                 fmaf(w2.z, z, fmaf(w1.z, y, w0.z * x)) + bb.z, fmaf(w2.w, z, fmaf(w1.w, y, w0.w * x)) + bb.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int mm = t * 128 + q * 32 + 4 * i + sub;
+            xin[i] = *reinterpret_cast<const float4*>(p.x + (int64_t)(mm < p.M ? mm : 0) * p.ldx + n0);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -2969,7 +3033,10 @@ extern "C" int zs_chain_mlp_fwd(float* x, int ldx, int M, const float* ln_w, con
 }
 
 extern "C" int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, const void* proj_blob, const float* proj_bias,
-                                 float ln_eps, const void* mlp_blob, const float* b1, const float* b2, int precision, void* stream) {
+                                 float ln_eps, const void* mlp_blob, const float* b1, const float* b2, const float* points,
+                                 const float* pp, int precision, void* stream) {
+  ZS_REQUIRE((points == nullptr) == (pp == nullptr) && (reinterpret_cast<uintptr_t>(pp) & 15) == 0,
+             "zs_chain_pmlp_fwd: points and pp go together; pp must be 16-byte aligned");
   ZS_REQUIRE(x && a_blk && proj_blob && proj_bias && mlp_blob && b1 && b2 && M >= 0, "zs_chain_pmlp_fwd: null pointer");
   ZS_REQUIRE(ldx >= 256 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "zs_chain_pmlp_fwd: x must be 16B aligned, ldx%%4==0");
   ZS_REQUIRE((reinterpret_cast<uintptr_t>(a_blk) & 15) == 0 && (reinterpret_cast<uintptr_t>(proj_blob) & 15) == 0 &&
@@ -2981,7 +3048,7 @@ extern "C" int zs_chain_pmlp_fwd(float* x, int ldx, int M, const float* a_blk, c
   ChainParams p{};
   p.x = x; p.ldx = ldx; p.M = M; p.ln_eps = ln_eps; p.a_blk = a_blk; p.pblob = reinterpret_cast<const uint8_t*>(proj_blob);
   p.bias_p = proj_bias; p.blob = reinterpret_cast<const uint8_t*>(mlp_blob); p.bias = b1; p.bias2 = b2; p.precision = precision;
-  p.flags = g_chain_dbg;
+  p.flags = g_chain_dbg; p.points = points; p.pp = pp;
   return chain_launch(chain_pmlp_kernel, p, as_stream(stream), "zs_chain_pmlp_fwd");
 }
 
@@ -3041,6 +3108,27 @@ extern "C" int zs_chain_occ_fwd(const float* x, int ldx, const float* points, in
 }
 
 extern "C" size_t zs_chain_qkvattn_blob_bytes(void) { return (size_t)4 * 4 * 2 * CT_TILE_BYTES; }
+
+// points mode of zs_chain_qkvattn_fwd (flags must contain 8 | 16): x = LinearProj3D(points) is recomputed inside the kernel
+extern "C" int zs_chain_qkvattn_pts_fwd(const float* points, int M, const float* pp, const float* pp_stat, float ln_eps,
+                                        const void* Wblob, const float* bias_qkv, const void* Kblob, const void* Vblob, int n_keys,
+                                        float scale, float* O, int precision, int flags, void* stream) {
+  ZS_REQUIRE(points && pp && pp_stat && Wblob && bias_qkv && Kblob && Vblob && O && M >= 0, "zs_chain_qkvattn_pts_fwd: null pointer");
+  ZS_REQUIRE(n_keys > 0 && n_keys <= 208, "zs_chain_qkvattn_pts_fwd: n_keys must be in [1, 208]");
+  ZS_REQUIRE((flags & 24) == 24 && flags >= 0 && flags < 32, "zs_chain_qkvattn_pts_fwd: flags must contain 8 | 16");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(Wblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(Kblob) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(Vblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias_qkv) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(pp) & 15) == 0 && (reinterpret_cast<uintptr_t>(O) & 15) == 0,
+             "zs_chain_qkvattn_pts_fwd: blobs / bias / pp / O must be 16-byte aligned");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_chain_qkvattn_pts_fwd: bad precision");
+  if (M == 0) return ZS_OK;
+  ChainParams p{};
+  p.points = points; p.pp = pp; p.pp_stat = pp_stat; p.ldx = 256; p.M = M; p.ln_eps = ln_eps;
+  p.blob = reinterpret_cast<const uint8_t*>(Wblob); p.bias = bias_qkv; p.kblob = reinterpret_cast<const uint8_t*>(Kblob);
+  p.vblob = reinterpret_cast<const uint8_t*>(Vblob); p.n_keys = n_keys; p.scale = scale; p.out = O; p.ldo = 256;
+  p.precision = precision; p.flags = flags | 64;
+  return chain_launch(chain_qkvattn2_kernel<true>, p, as_stream(stream), "zs_chain_qkvattn_pts_fwd", QA3_THREADS);
+}
 
 extern "C" int zs_chain_qkvattn_fwd(const float* x, int ldx, int M, float ln_eps, const void* Wblob, const float* bias_qkv,
                                     const void* Kblob, const void* Vblob, int n_keys, float scale, float* O, int ldo,

@@ -95,6 +95,7 @@ class Implicit(nn.Module):
         self.attention = "qkv"
         # zs_chain_qkvattn_fwd policy: 8 = probabilities in tensor memory (the faster kernel), every contraction three fp16
         # passes; +1 = k, v single-pass (inside the 5e-4 parity budget of profiles/r2_precision_study.md, no measured speed-up)
+        self.fold_point_proj = True   # first block recomputes LinearProj3D(points) in its kernels instead of reading x (needs fuse_proj)
         self.fuse_proj = True      # attention output projection + residual inside the MLP kernel (zs_chain_pmlp_fwd; needs flags & 16)
         self.attn_flags = 24       # zs_chain_qkvattn_fwd: 8 = probabilities in tensor memory, 16 = scores in registers + tile-blocked output
         self.lin_fused = True         # chain engine: LN+qkv and proj+residual on zs_chain_lin_fwd (False: layernorm + zs_gemm_tc_f32)
@@ -212,15 +213,31 @@ class Implicit(nn.Module):
             self._chain_cache = (key, mlp, occ, biases, w8, float(self.impl_mlp.layers[8].bias.detach()), mlp_b1, lin_blobs)
         return self._chain_cache
 
+    def _pp_tables(self):
+        w, b = self.point_proj.proj.weight, self.point_proj.proj.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device))
+        if getattr(self, "_pp_cache", None) is None or self._pp_cache[0] != key:
+            self._pp_cache = (key,) + ops.point_proj_tables(w, b)
+        return self._pp_cache[1], self._pp_cache[2]
+
     def _points_chain(self, lat, pts, attn_out=None, tc=False, sigmoid=False):
         """pts [B,P,3] contiguous -> logits [B,P]; optionally fills attn_out [B,P,L]."""
         B, P, _ = pts.shape
         C = self.n_channels
         nb = len(self.blocks_attn)
         chain = tc and self.engine != "tc" and self._chain_ok()
+        fold_pp = False
         if chain:
             _, mlp_blobs, occ_blob, occ_biases, w8, b8, mlp_b1, lin_blobs = self._chain_blobs()
-            x = ops.point_proj(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)
+            # points mode: the first block recomputes x = LinearProj3D(points) inside its two kernels (no point_proj launch, x is never
+            # read before the first block has written it)
+            fold_pp = (self.fold_point_proj and attn_out is None and self.attention == "qkv" and self.lin_fused and self.fuse_proj
+                       and (self.attn_flags & 24) == 24 and nb >= 1)
+            if fold_pp:
+                pp, pp_stat = self._pp_tables()
+                x = torch.empty(B * P, C, device=pts.device, dtype=torch.float32)
+            else:
+                x = ops.point_proj(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)
         else:
             x = ops.gemm(pts.reshape(B * P, 3), self.point_proj.proj.weight, self.point_proj.proj.bias)   # K=3: FFMA
         for l, blk in enumerate(self.blocks_attn):
@@ -233,12 +250,19 @@ class Implicit(nn.Module):
                 for b in range(B):
                     if (l, b) not in packs:
                         packs[(l, b)] = ops.attn_pack_fused(k_lat[b], v_lat[b], self.num_heads)
-                    ab = ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
-                                           lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
-                                           flags=self.attn_flags, out=None if blocked else a[b * P:(b + 1) * P])
+                    first = fold_pp and l == 0
+                    pts_b = pts[b] if first else None
+                    if first:
+                        ab = ops.chain_qkvattn_pts(pts_b, pp, pp_stat, lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
+                                                   lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
+                                                   flags=self.attn_flags)
+                    else:
+                        ab = ops.chain_qkvattn(x[b * P:(b + 1) * P], lin_blobs[l][3], lin_blobs[l][1], packs[(l, b)][0], packs[(l, b)][1],
+                                               lat["L"], (C // self.num_heads) ** -0.5, ln_eps=blk.norm1.eps, precision=self.precision,
+                                               flags=self.attn_flags, out=None if blocked else a[b * P:(b + 1) * P])
                     if blocked and self.fuse_proj:       # x += proj(a) and the MLP in one kernel
                         ops.chain_pmlp(x[b * P:(b + 1) * P], ab, lin_blobs[l][2], blk.attn.proj.bias, blk.norm2.eps, mlp_blobs[l],
-                                       mlp_b1[l], blk.mlp.fc2.bias, self.precision)
+                                       mlp_b1[l], blk.mlp.fc2.bias, self.precision, points=pts_b, pp=pp if first else None)
                     elif blocked:
                         xb = x[b * P:(b + 1) * P]
                         ops.chain_lin(ab, lin_blobs[l][2], blk.attn.proj.bias, 1, res=xb, out=xb, precision=self.precision)

@@ -256,15 +256,42 @@ def chain_mlp(x, ln_w, ln_b, ln_eps, blob, b1, b2, precision="bf16x3"):
     return x
 
 
-def chain_pmlp(x, a_blk, proj_blob, proj_bias, ln_eps, mlp_blob, b1, b2, precision="fp16x3"):
-    """In place: x[M,256] <- x' + fc2(GELU(fc1(LayerNorm(x')))), x' = x + unblock(a_blk) proj^T + proj_bias (one tcgen05 kernel)."""
+def point_proj_tables(w, bias):
+    """LinearProj3D weights [256,3] / bias [256] -> (pp [4,256] = w[:,0] | w[:,1] | w[:,2] | bias, pp_stat [16]) for the points
+    mode of chain_qkvattn / chain_pmlp (include/zeroshape_b200.h: zs_chain_qkvattn_pts_fwd)."""
+    rows = torch.cat([w.detach().t().float(), bias.detach().float().view(1, -1)], dim=0).contiguous()        # [4, 256]
+    r = rows.double()
+    m = r.mean(dim=1)
+    c = (r - m[:, None]) @ (r - m[:, None]).t() / r.shape[1]
+    st = torch.stack([m[0], m[1], m[2], m[3], c[0, 0], c[1, 1], c[2, 2], c[3, 3], c[0, 1], c[0, 2], c[1, 2], c[0, 3], c[1, 3], c[2, 3],
+                      m[0] * 0, m[0] * 0]).float().contiguous()
+    return rows, st
+
+
+def chain_qkvattn_pts(points, pp, pp_stat, wblob, bias_qkv, kblob, vblob, n_keys, scale, ln_eps=1e-6, precision="fp16x3", flags=24):
+    """chain_qkvattn of the FIRST decoder block with x = LinearProj3D(points) recomputed in the kernel -> tile-blocked output."""
+    _chk(points, "points"); _chk(bias_qkv, "bias_qkv"); _chk(pp, "pp"); _chk(pp_stat, "pp_stat")
+    assert points.dim() == 2 and points.shape[1] == 3 and pp.shape == (4, 256) and pp_stat.numel() == 16
+    M = points.shape[0]
+    O = torch.empty((M + 127) // 128, 64, 128, 4, device=points.device, dtype=torch.float32)
+    check(lib.zs_chain_qkvattn_pts_fwd(_p(points), M, _p(pp), _p(pp_stat), ln_eps, _p(wblob), _p(bias_qkv), _p(kblob), _p(vblob), n_keys,
+                                       scale, _p(O), CHAIN_PRECISIONS[precision], int(flags), _stream()), "zs_chain_qkvattn_pts_fwd")
+    return O
+
+
+def chain_pmlp(x, a_blk, proj_blob, proj_bias, ln_eps, mlp_blob, b1, b2, precision="fp16x3", points=None, pp=None):
+    """In place: x[M,256] <- x' + fc2(GELU(fc1(LayerNorm(x')))), x' = x + unblock(a_blk) proj^T + proj_bias (one tcgen05 kernel).
+    With points / pp the incoming x is LinearProj3D(points), recomputed in the kernel (x is only written)."""
     assert x.dim() == 2 and x.shape[1] == 256 and x.is_cuda and x.dtype == torch.float32 and x.stride(1) == 1
     M = x.shape[0]
     assert a_blk.is_contiguous() and a_blk.dtype == torch.float32 and a_blk.numel() == ((M + 127) // 128) * 32768
     assert mlp_blob.numel() == lib.zs_chain_mlp_blob_bytes() and proj_blob.numel() == lib.zs_gemm_tc_packed_bytes(256, 256)
     _chk(proj_bias, "proj_bias"); _chk(b1, "b1"); _chk(b2, "b2")
+    if points is not None:
+        _chk(points, "points"); _chk(pp, "pp")
+        assert points.shape == (M, 3) and pp.shape == (4, 256)
     check(lib.zs_chain_pmlp_fwd(_p(x), x.stride(0), M, _p(a_blk), _p(proj_blob), _p(proj_bias), ln_eps, _p(mlp_blob), _p(b1), _p(b2),
-                                CHAIN_PRECISIONS[precision], _stream()), "zs_chain_pmlp_fwd")
+                                _p(points), _p(pp), CHAIN_PRECISIONS[precision], _stream()), "zs_chain_pmlp_fwd")
     return x
 
 
@@ -673,7 +700,7 @@ class OpTimer:
         with ops.OpTimer() as t:  ...run the hot path...
         t.summary() -> {op name: (launch groups, total ms)}   (synchronises)
     """
-    NAMES = ("point_proj", "chain_lin", "chain_qkvattn", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_pmlp", "chain_occ", "gemm_tc", "gemm",
+    NAMES = ("point_proj", "chain_lin", "chain_qkvattn", "attn_fused", "attn_tc", "point_attention", "chain_mlp", "chain_pmlp", "chain_qkvattn_pts", "chain_occ", "gemm_tc", "gemm",
              "conv2d_nhwc", "layernorm", "groupnorm_nhwc", "mha", "bilinear_nhwc", "dense_grid", "axpby", "marching_cubes",
              "mesh_sample", "unproject_normalize", "concat2", "maxpool3x3s2_nhwc", "avgpool_nhwc", "chamfer_nn")
 
