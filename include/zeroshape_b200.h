@@ -209,6 +209,19 @@ int zs_avgpool_nhwc_f32(const float* x, float* y, int B, int HW, int C, void* st
 int zs_bilinear_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int OH, int OW,
                          int align_corners, void* stream);
 
+/* Input pipeline (csrc/preprocess.cu; reference demo.py:33-75, data/synthetic.py:178-210).
+ * zs_rgba_crop_resize_u8: PIL crop of the RGBA image [H0,W0,4] to the window (left, top, cw, ch) -- zeros outside the image, as
+ *   torchvision_F.crop on a PIL image -- then PIL `Image.resize((OW, OH))` with its default BICUBIC filter on an RGBA image
+ *   (premultiplied alpha, two 8-bit passes with 22-bit fixed-point coefficients).  bounds [out][2] = (first source index, taps),
+ *   coef [out][ksize] int32 = Pillow's normalized coefficients (host: zeroshape_b200/data/preprocess.py:resize_coeffs).  Byte-exact.
+ * zs_rgba_composite_f32: to_tensor + `rgb * mask + bgcolor * (1 - mask)`, `mask > 0.5` (demo.py:46-52) -> rgb [3,H,W], mask [1,H,W].
+ * zs_erode_square_f32: cv2.erode(mask, ones(3,3), iterations=radius) of demo.py:70-75 (minimum over the clipped square window). */
+int zs_rgba_crop_resize_u8(const uint8_t* src, int H0, int W0, int left, int top, int cw, int ch, uint8_t* out, int OH, int OW,
+                           const int* xbounds, const int* xcoef, int xksize, const int* ybounds, const int* ycoef, int yksize,
+                           void* stream);
+int zs_rgba_composite_f32(const uint8_t* img, int H, int W, int use_bgcolor, float bgcolor, float* rgb, float* mask, void* stream);
+int zs_erode_square_f32(const float* mask, float* out, int B, int H, int W, int radius, void* stream);
+
 /* NCHW <-> NHWC */
 int zs_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, float scale, float shift, void* stream);
 int zs_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);

@@ -1069,3 +1069,40 @@ def mean_axis1(x):
     out = torch.empty(A, N, device=x.device, dtype=torch.float32)
     check(lib.zs_mean_axis1_f32(_p(x), _p(out), A, M, N, _stream()), "zs_mean_axis1_f32")
     return out
+
+
+# ---- input pipeline (csrc/preprocess.cu) --------------------------------------------------------------
+def rgba_crop_resize(img, left, top, cw, ch, H, W, xbounds, xcoef, ybounds, ycoef):
+    """uint8 RGBA [H0,W0,4] -> uint8 RGBA [H,W,4]: PIL crop (zero outside) + PIL BICUBIC resize of the RGBA image, byte-exact."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 4 and img.is_contiguous()
+    for t in (xbounds, xcoef, ybounds, ycoef):
+        assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()
+    assert xbounds.shape == (W, 2) and ybounds.shape == (H, 2) and xcoef.shape[0] == W and ycoef.shape[0] == H
+    out = torch.empty(H, W, 4, dtype=torch.uint8, device=img.device)
+    check(lib.zs_rgba_crop_resize_u8(_p(img), img.shape[0], img.shape[1], int(left), int(top), int(cw), int(ch), _p(out), H, W,
+                                     _p(xbounds), _p(xcoef), xcoef.shape[1], _p(ybounds), _p(ycoef), ycoef.shape[1], _stream()),
+          "zs_rgba_crop_resize_u8")
+    return out
+
+
+def rgba_composite(img, bgcolor):
+    """uint8 RGBA [H,W,4] -> (rgb [3,H,W], mask [1,H,W]) fp32: to_tensor, then `rgb * mask + bgcolor * (1 - mask)` and
+    `mask > 0.5` when bgcolor is not None (demo.py:46-52)."""
+    assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 4 and img.is_contiguous()
+    H, W = img.shape[:2]
+    rgb = torch.empty(3, H, W, device=img.device, dtype=torch.float32)
+    mask = torch.empty(1, H, W, device=img.device, dtype=torch.float32)
+    check(lib.zs_rgba_composite_f32(_p(img), H, W, int(bgcolor is not None), float(bgcolor or 0.0), _p(rgb), _p(mask), _stream()),
+          "zs_rgba_composite_f32")
+    return rgb, mask
+
+
+def erode_square(mask, radius):
+    """mask [B,H,W] fp32 -> minimum over the (2 radius + 1)^2 window clipped to the image (cv2.erode 3x3, `radius` iterations)."""
+    _chk(mask, "mask")
+    assert mask.dim() == 3
+    out = torch.empty_like(mask)
+    check(lib.zs_erode_square_f32(_p(mask), _p(out), mask.shape[0], mask.shape[1], mask.shape[2], int(radius), _stream()),
+          "zs_erode_square_f32")
+    return out
+

@@ -62,15 +62,12 @@ class Mesh:
         self._vscale, self._voffset = 1.0, 0.0
         return self
 
-    def export(self, path):
+    def export(self, path, ascii=False):
+        """`mesh.export(fname)` of utils/util_vis.py:108: a PLY file in trimesh's default encoding (binary little endian,
+        float32 vertices, int32 faces); zeroshape_b200/data/formats.py."""
+        from ..data.formats import write_ply
         v, f = self._host()
-        with open(path, "w") as fh:
-            fh.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
-                     "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(v), len(f)))
-            for p in v:
-                fh.write("%.7g %.7g %.7g\n" % tuple(p))
-            for t in f:
-                fh.write("3 %d %d %d\n" % tuple(t))
+        write_ply(path, v, f, ascii=ascii)
 
 
 @torch.no_grad()
