@@ -227,16 +227,17 @@ def run_ours(args, rank, world, dev):
             hot_path(rgb_dev[:1], mask_dev[:1], False)
         summ = ot.summary()
     per_point_flop = {"chain_lin[qkv]": 2 * 196608, "chain_lin[proj]": 2 * 65536, "attn_fused": 2 * 2 * (50432 + 256), "chain_mlp": 2 * 524288,
-                      "chain_occ": 2 * 724224, "chain_pmlp": 2 * (524288 + 65536), "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256))}
+                      "chain_occ": 2 * 724224, "chain_pmlp": 2 * (524288 + 65536), "point_proj": 2 * 768, "chain_qkvattn": 2 * (196608 + 2 * (50432 + 256)),
+                      "chain_qkvattn_pts": 2 * (768 + 196608 + 2 * (50432 + 256))}
     per_shape_launches = {"chain_lin[qkv]": 2, "chain_lin[proj]": 2, "attn_fused": 2, "chain_mlp": 2, "chain_pmlp": 2, "chain_occ": 1, "point_proj": 1,
                           "chain_qkvattn": 2}
     tot_ms = sum(v[1] for v in summ.values())
     for k, (cnt, ms_k) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
         row = {"op": k, "launches": cnt, "ms_per_shape": ms_k, "share": ms_k / tot_ms}
         if k in per_point_flop:
-            tf = per_point_flop[k] * per_shape_launches[k] * pts / (ms_k * 1e-3) / 1e12
+            tf = per_point_flop[k] * cnt * pts / (ms_k * 1e-3) / 1e12        # cnt = launches of this op in the one-shape pass
             row.update({"algorithmic_tflops": tf, "frac_of_peak": tf / peaks["bf16_tflops"],
-                        "dram_bytes_per_point": traffic_tab.get("bytes_per_point", {}).get(k)})
+                        "dram_bytes_per_point": traffic_tab.get("bytes_per_point", {}).get("chain_qkvattn" if k == "chain_qkvattn_pts" else k)})
         kernels.append(row)
     api_leg = None
     if world == 1 and not args.no_e2e and not getattr(args, "no_extras", False):
@@ -259,9 +260,11 @@ def run_ours(args, rank, world, dev):
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                      "traffic": traffic, "peak_source": peaks["source"], "avg_launch_ms": dec_avg,
                      "algorithmic_flop_per_launch": pts * FLOP_PER_POINT,
-                     "note": "launch = the decoder launch group of one shape (9 x [point_proj, 2 x (LN+qkv, attention, proj, MLP), occupancy MLP]); "
-                             "bf16x3 executes 3x the algorithmic MMA work, so frac <= 1/3 in parity mode; `kernels` = every op of one "
-                             "shape timed live with CUDA events (encoder ops included), `traffic` = ncu DRAM bytes of the group",
+                     "note": "launch = the decoder launch group of one shape, 5 kernels: 2 x (LayerNorm + qkv + attention [points mode in "
+                             "block 0], proj + residual + MLP), occupancy MLP; fp16x3 executes 3x the algorithmic MMA work, so frac <= 1/3 "
+                             "in parity mode; `kernels` = every op of one shape timed live with CUDA events (encoder ops included), "
+                             "`traffic` = DRAM bytes of the group from the committed ncu --set full capture of the same one-pass launch "
+                             "group (profiles/decoder_traffic.json)",
                      "kernels": kernels},
         "e2e": {"value": shapes_total / (ms_e2e * 1e-3), "unit": "shapes/s",
                 "h2d_bytes_per_step": (rgb_host.numel() + mask_host.numel()) * 4, "d2h_bytes_per_step": out_host.numel() * 4},

@@ -30,7 +30,7 @@ print("| # | kernel | " + " | ".join(c[1] for c in cols) + " |")
 print("|---|---|" + "---:|" * len(cols))
 traffic = {}
 for n, d in enumerate(data):
-    name = d[idx["Kernel Name"]].split("(")[0].replace("zs::", "")
+    name = d[idx["Kernel Name"]].split("(")[0].replace("zs::", "").replace("void ", "").split("<")[0].strip()
     vals = []
     for c, _ in cols:
         v, u = d[idx[c]], units[idx[c]]
@@ -54,7 +54,7 @@ if len(sys.argv) > 3:
     per = {}
     for k, v in traffic.items():
         if k in label:
-            per[label[k]] = sum(v) / len(v) / pts
+            per[label[k]] = sum(v) / len(v) / pts          # mean over the captured launches of that kernel
     assumed = []
     if "point_proj" not in per and "--no-point-proj" not in sys.argv:
         per["point_proj"] = 1036.0
