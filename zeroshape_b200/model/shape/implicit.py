@@ -150,7 +150,7 @@ class Implicit(nn.Module):
             kv.append((qkv[..., C:2 * C], qkv[..., 2 * C:]))
             if l == nb - 1:
                 break
-            att = ops.mha(qkv, self.num_heads, tc=tc)
+            att = ops.mha(qkv, self.num_heads, tc=self._use_tc())      # tcgen05, fp16x3: the same 1.5e-6 error as the FFMA kernel
             lat = ops.linear(att, blk.attn.proj.weight, blk.attn.proj.bias, res=lat, tc=tc)
             h = ops.linear(self._ln(lat, blk.norm2), blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=ops.ACT_GELU, tc=tc)
             lat = ops.linear(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, res=lat, tc=tc)
