@@ -2384,7 +2384,8 @@ __device__ __forceinline__ uint32_t chain2_setup(const Bars5& B, uint8_t* smem_g
 // MMA thread: one 64-wide K-chunk against the next weight tile pair; A from shared memory (a_addr) or, when `ts`,
 // from tensor memory (two 32-value blocks of [16 hi | 16 lo] columns: K-step kk at a_tmem + 32 (kk >> 1) + 8 (kk & 1))
 __device__ __forceinline__ void mma_chunk2(const Bars5& B, uint32_t smem_base, Ring& wr, bool ts, uint32_t a_addr, uint32_t a_tmem,
-                                           uint32_t d_tmem, bool first, bool split, uint32_t a_empty_bar) {
+                                           uint32_t d_tmem, bool first, bool split, uint32_t a_empty_bar, int ksteps = 4) {
+  // ksteps < 4: only the first 16 * ksteps of the chunk's 64 K-columns are non-zero (the xyz chunk of the occupancy MLP: 3 columns)
   const uint32_t idesc = umma_idesc_f16(128, 256);
   const uint64_t a_hi = umma_desc_sw128(a_addr), a_lo = umma_desc_sw128(a_addr + CT_A_HALF);
   mbar_wait(B.wfull(wr.idx), wr.phase);
@@ -2393,6 +2394,7 @@ __device__ __forceinline__ void mma_chunk2(const Bars5& B, uint32_t smem_base, R
     const uint64_t w = umma_desc_sw128(smem_base + wr.idx * CT_TILE_BYTES);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (k >= ksteps) break;
       const uint32_t acc = (!first || k > 0) ? 1u : 0u;
       if (ts) {
         const uint32_t at = a_tmem + 32u * (k >> 1) + 8u * (k & 1);
@@ -2412,6 +2414,7 @@ __device__ __forceinline__ void mma_chunk2(const Bars5& B, uint32_t smem_base, R
     const uint64_t w = umma_desc_sw128(smem_base + wr.idx * CT_TILE_BYTES);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (k >= ksteps) break;
       if (ts) umma_ts(d_tmem, a_tmem + 32u * (k >> 1) + 8u * (k & 1), w + 2 * k, idesc, 1u);
       else umma_bf16(d_tmem, a_hi + 2 * k, w + 2 * k, idesc, 1u);
     }
@@ -2925,7 +2928,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_occ2_kernel(ChainParams p
           for (int i = 0; i < nL; ++i) {
             mbar_wait(B.lfull(lr.idx), lr.phase);
             tc_fence_after();
-            mma_chunk2(B, smem_base, wr, false, smem_base + O2_OFF_L + lr.idx * 2 * CT_A_HALF, 0u, d, i == 0, split, B.lempty(lr.idx));
+            mma_chunk2(B, smem_base, wr, false, smem_base + O2_OFF_L + lr.idx * 2 * CT_A_HALF, 0u, d, i == 0, split, B.lempty(lr.idx),
+                       i == 4 ? 1 : 4);      // chunk 4 = [xyz | 61 zero columns]: one K-step
             lr.advance();
           }
           for (int i = 0; i < nE; ++i) {          // A = the previous layer's activations, in place in the other half
