@@ -47,7 +47,7 @@ with torch.no_grad():
         net.attention, net.attn_flags = attention, flags
         net.fold_point_proj = bool(mlp_variant)
         mlp_variant = 1
-        lib.zs_debug_chain_variant(mlp_variant)
+        lib.zs_debug_chain_variant(mlp_variant | (int(os.environ.get("ZS_CHAIN_DBG", "0")) & ~1))
         for _ in range(3):
             net._points_chain(lat, pts, tc=True, sigmoid=True)
         torch.cuda.synchronize()

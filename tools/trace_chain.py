@@ -33,6 +33,13 @@ TAGS_QKVATTN = {
     20: "epi: wait accfull", 21: "epi: accfull ok", 22: "epi: epi-1 done / wait sfull", 23: "epi: sfull ok", 24: "epi: max pass done",
     25: "epi: bar1 passed", 26: "epi: exp pass done, pfull arrived", 27: "epi: bar2 passed", 28: "epi: ofull ok", 29: "epi: out stored",
 }
+TAGS_PMLP = {
+    1: "mma: wait lfull", 2: "mma: lfull ok", 6: "mma: fc1/proj chunk issued", 7: "mma: group start (wait tempty0)", 8: "mma: wait efull",
+    9: "mma: efull ok", 4: "mma: fc2 chunk issued",
+    10: "ld : wait lempty", 11: "ld : lempty ok", 16: "ld : A chunks done, wait xready", 17: "ld : xready ok",
+    20: "epi: wait tfull0", 21: "epi: tfull0 ok", 23: "epi: x' written, stats published", 24: "epi: GELU chunk handed over",
+    25: "epi: wait tfull1", 26: "epi: tfull1 ok", 27: "epi: x written",
+}
 NE = 512
 
 
@@ -97,7 +104,12 @@ def main():
         for flags in (8, 24):
             run_traced(f"chain_qkvattn_flags{flags}", TAGS_QKVATTN,
                        lambda: ops.chain_qkvattn(x0, wb, bq, kb, vb, L, 32 ** -0.5, flags=flags, out=out))
-    if "mlp" in which:
+    if "pmlp" in which:
+        a_blk = torch.randn(M // 128, 64, 128, 4, generator=g).to(dev)
+        wp = (torch.randn(256, 256, generator=g) / 16).to(dev)
+        xp = x0.clone()
+        run_traced("chain_pmlp", TAGS_PMLP, lambda: ops.chain_pmlp(xp, a_blk, ops.pack_generic(wp), b2, 1e-6, blob, b1, b2))
+    if "mlp" in which and "pmlp" not in which:
         x = x0.clone()
         run_traced("chain_mlp_bf16x3", TAGS_MLP, lambda: ops.chain_mlp(x, None, None, 1e-6, blob, b1, b2, "bf16x3"))
     if "lin" in which:
