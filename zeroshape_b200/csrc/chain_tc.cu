@@ -2740,7 +2740,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     uint8_t* wscr = smem_gen + M2_OFF_T + e * 4096;
     const int sub = lane >> 3, q8 = lane & 7;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // P phase of tile t: x' = x + proj + bp written in place, LayerNorm sums published.  It runs one tile AHEAD of the final epilogue
+    // (x'' of the previous tile): fc1 of tile t+1 waits for it, nothing waits for the final epilogue but fc2 of tile t+1.
+    auto p_phase = [&](int t) {
       // ---- x' = x + proj + bp, written in place; LayerNorm sums of x' ----
       mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
       tc_fence_after();
@@ -2807,6 +2809,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p
       }
       __threadfence_block();
       mbar_arrive(B.xready());
+    };
+    if ((int)blockIdx.x < n_tiles) p_phase(blockIdx.x);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       // ---- the MLP, as chain_mlp2_kernel ----
       for (int g = 0; g < 4; ++g) {
         mbar_wait(B.tfull(0), tf_phase[0]); tf_phase[0] ^= 1;
@@ -2824,6 +2829,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) chain_pmlp_kernel(ChainParams p
         tc_fence_before();
         mbar_arrive(B.tempty(0));
       }
+      if (t + (int)gridDim.x < n_tiles) p_phase(t + (int)gridDim.x);
       mbar_wait(B.tfull(1), tf_phase[1]); tf_phase[1] ^= 1;
       tc_fence_after();
 #pragma unroll 1
