@@ -123,6 +123,9 @@ int zs_debug_chain_trace(unsigned long long* buf);
  * memory, 4 / 5 weight-ring slots) when v != 0 (default) and the round-1 kernels (shared-memory ring E, 3 slots) when v == 0.
  * Identical arithmetic.  Process-wide, not thread-safe. */
 int zs_debug_chain_variant(int v);
+/* debug / A-B: 0 disables the split-K path that zs_gemm_tc_f32 / zs_conv2d_nhwc_tc take for few-tile layers (tiles * 2 <= SMs and
+ * K >= 512: up to 16 K-splits per tile, partial tiles in a stream-ordered workspace, deterministic finalize pass).  Process-wide. */
+int zs_debug_gemm_splitk(int enable);
 
 /* Chained tcgen05 kernels of the implicit decoder (consecutive layers of a 128-point tile stay on chip; see
  * csrc/chain_tc.cu).  `blob` = weight tiles in consumption order, each sub-matrix packed with zs_gemm_tc_pack

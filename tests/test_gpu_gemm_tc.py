@@ -45,6 +45,41 @@ def test_gemm_tc_bf16x3_is_fp32_grade(cuda, M, N, K):
     assert (out.cpu().double() - ref).abs().max().item() < 3e-2 * scale
 
 
+@pytest.mark.parametrize("M,N,K", [(196, 1024, 2304), (49, 2048, 512), (392, 256, 1024), (130, 70, 4608)])
+def test_gemm_tc_split_k(cuda, M, N, K):
+    """Few-tile layers take the split-K path (partial tiles in a workspace + deterministic finalize): same accuracy as the
+    one-pass kernel, bit-identical from run to run, every epilogue form."""
+    _need_sm100()
+    from zeroshape_b200 import ops
+    from zeroshape_b200._native import lib
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b, r = torch.randn(N, generator=g).to(cuda), torch.randn(M, N, generator=g).to(cuda)
+    ref = a.cpu().double() @ w.double().T + b.cpu().double()
+    pw = ops.PackedWeight(w.to(cuda))
+    scale = ref.abs().max().item()
+    try:
+        outs = {}
+        for on in (1, 0):
+            lib.zs_debug_gemm_splitk(on)
+            o1 = ops.gemm_tc(a, pw, b)
+            o2 = ops.gemm_tc(a, pw, b, res=r, res_mode=ops.RES_BEFORE_ACT, act=ops.ACT_RELU)
+            o3 = ops.gemm_tc(a, pw, b, res=r, act=ops.ACT_GELU)
+            assert (o1.cpu().double() - ref).abs().max().item() < 2e-5 * scale
+            assert (o2.cpu().double() - F.relu(ref + r.cpu().double())).abs().max().item() < 3e-5 * scale
+            assert (o3.cpu().double() - (F.gelu(ref) + r.cpu().double())).abs().max().item() < 3e-5 * scale
+            assert torch.equal(o1, ops.gemm_tc(a, pw, b))                 # deterministic (no atomics)
+            outs[on] = o1
+        assert (outs[1] - outs[0]).abs().max().item() < 2e-5 * scale
+        wide = torch.zeros(M, N + 8, device=cuda)                          # row-strided output
+        lib.zs_debug_gemm_splitk(1)
+        ops.gemm_tc(a, pw, b, out=wide[:, 4:N + 4])
+        assert torch.equal(wide[:, 4:N + 4], outs[1]) and wide[:, :4].abs().max().item() == 0 and wide[:, N + 4:].abs().max().item() == 0
+    finally:
+        lib.zs_debug_gemm_splitk(1)
+
+
 def test_gemm_tc_exact_on_small_integers(cuda):
     """Integers < 256 are exact in bf16 and their products/sums exact in fp32: any layout bug shows as a
     wrong integer, not as noise."""

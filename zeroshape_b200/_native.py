@@ -30,6 +30,7 @@ SIGNATURES = {
     "zs_attn_pv_tc": (c_int, [P, P, P, P, P, c_int, c_int, P]),
     "zs_debug_chain_trace": (c_int, [P]),
     "zs_debug_chain_variant": (c_int, [c_int]),
+    "zs_debug_gemm_splitk": (c_int, [c_int]),
     "zs_chain_attn_fwd": (c_int, [P, c_int, c_int, P, P, c_int, c_float, P, c_int, P]),
     "zs_debug_clock_mhz": (c_int, [P, P]),
     "zs_bce_logits_fwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),

@@ -50,6 +50,9 @@ struct TcParams {
   const float* rowscale;       // optional [M, n_tiles]: accumulator row scale applied before bias/residual (P.V normalisation)
   // implicit-GEMM convolution (AMODE 1): A row m = output pixel (b, oh, ow) of an NHWC image, K index = (kh, kw, ci)
   int cB, cH, cW, cCin, cKH, cKW, cStride, cPadT, cPadL, cOH, cOW, cPreRelu;
+  // split-K (few-tile layers, see tc_launch): work item = (tile, split s), split s covers K-chunks [s k_chunks / k_splits, (s+1) ...)
+  // and writes its raw fp32 partial tile to ws[s][M][N]; splitk_finalize_kernel sums them in a fixed order (deterministic)
+  int k_splits; float* ws;
 };
 
 template <int ACT>
@@ -231,6 +234,52 @@ __device__ __forceinline__ void tc_epilogue_softmax(const TcParams& p, uint32_t 
 // AMODE 2: A rows are gathered from the output gradient of a convolution (data gradient as an implicit GEMM)
 // SPLIT: compile-time copy of `precision == 0` for the A producers (single-pass bf16 skips the hi/lo residual arithmetic: the
 // producers are bound by instruction issue, profiles/r1_ncu_train_gemm.md)
+// split-K: the raw partial accumulator of split s goes to ws[s][m][n] (n in [0, N)), 128 bytes per thread and 32-column piece
+__device__ __forceinline__ void tc_epilogue_split(const TcParams& p, uint32_t taddr, int m, int nt, int hsel, int s) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    if (hsel * 128 + c0 >= p.mma_n) break;
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr + c0, rr);
+    tmem_ld_wait();
+    const int n0 = nt * TC_BN + hsel * 128 + c0;
+    const int nvalid = p.N - n0;
+    if (m < p.M && nvalid > 0) {
+      float* dst = p.ws + ((int64_t)s * p.M + m) * p.N + n0;
+      if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                                          __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = __uint_as_float(rr[j]);
+      }
+    }
+  }
+}
+
+// C = act(sum_s ws[s] + bias) combined with the residual as tc_epilogue_half does; splits summed in index order
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int ks, int M, int N, const float* __restrict__ bias,
+                                       const float* __restrict__ res, int ldres, int res_mode, int act, float* __restrict__ C, int ldc) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const int64_t m = i / N;
+    float v = ws[i];
+    for (int s = 1; s < ks; ++s) v += ws[(int64_t)s * total + i];
+    if (bias) v += __ldg(bias + n);
+    if (res_mode == ZS_RES_NONE) {
+      v = apply_act(v, act);
+    } else {
+      const float r = __ldg(res + m * ldres + n);
+      v = res_mode == ZS_RES_BEFORE_ACT ? apply_act(v + r, act) : apply_act(v, act) + r;
+    }
+    C[m * ldc + n] = v;
+  }
+}
+
 template <int AMODE, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -266,6 +315,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int ksp = p.k_splits > 1 ? p.k_splits : 1;           // entry points that never split leave the field zero
+  const int total_items = total_tiles * ksp;                 // work item w = (tile w % total_tiles, K split w / total_tiles)
+  auto kbeg = [&](int w) { return (int)((int64_t)(w / total_tiles) * p.k_chunks / ksp); };
+  auto kend = [&](int w) { return (int)((int64_t)(w / total_tiles + 1) * p.k_chunks / ksp); };
 
   if (warp < TC_PROD_WARPS) {
     // ================= A producers =================
@@ -283,10 +336,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     int cb[4] = {0, 0, 0, 0}, cih0[4] = {0, 0, 0, 0}, ciw0[4] = {0, 0, 0, 0};   // conv modes: pixel of each of the thread's rows
     bool crow_ok[4] = {false, false, false, false};
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](float4 (&buf)[4][2], int t, int kc) {
+    auto fetch = [&](float4 (&buf)[4][2], int t, int kc, bool first) {
       const int m_base = (t / p.n_tiles) * TC_BM + rb;
       const int k = kc * TC_BK + c * 8;
-      if (AMODE != 0 && kc == 0) {
+      if (AMODE != 0 && first) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int m = m_base + 32 * i;
@@ -393,15 +446,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
       if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
     };
     // fetch iterator (runs one (tile, chunk) item ahead of the consume iterator, in the same order)
-    int ft = blockIdx.x, fkc = 0;
+    int fw = blockIdx.x, fkc = fw < total_items ? kbeg(fw) : 0;
     auto fetch_next = [&](float4 (&buf)[4][2]) {
-      if (ft >= total_tiles) return;
-      fetch(buf, ft, fkc);
-      if (++fkc == p.k_chunks) { fkc = 0; ft += gridDim.x; }
+      if (fw >= total_items) return;
+      fetch(buf, fw % total_tiles, fkc, fkc == kbeg(fw));
+      if (++fkc == kend(fw)) { fw += gridDim.x; fkc = fw < total_items ? kbeg(fw) : 0; }
     };
     fetch_next(buf0);
     int64_t items = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) items += p.k_chunks;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) items += kend(w) - kbeg(w);
     for (int64_t it = 0; it < items; ++it) {
       consume(buf0);
       fetch_next(buf0);
@@ -411,9 +464,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t bytes = split ? 2u * p.w_tile_bytes : p.w_tile_bytes;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+        const int nt = (w % total_tiles) % p.n_tiles;
+        for (int kc = kbeg(w); kc < kend(w); ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint8_t* src = p.Wp + ((size_t)nt * p.k_chunks + kc) * (2u * TC_B_TILE);
           const uint32_t dst = smem_base + stage * TC_STAGE_BYTES + 2 * TC_A_TILE;
@@ -430,11 +483,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_bf16(TC_BM, (uint32_t)p.mma_n);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TC_BN;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int kb = kbeg(w), ke = kend(w);
+        for (int kc = kb; kc < ke; ++kc) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
@@ -443,14 +497,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 B along K inside the swizzle atom
-            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kc | k) != 0);
+            umma_bf16(d_tmem, a_hi + koff, b_hi + koff, idesc, (kc != kb || k != 0) ? 1u : 0u);
             if (split) {
               umma_bf16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1);
               umma_bf16(d_tmem, a_lo + koff, b_hi + koff, idesc, 1);
             }
           }
           umma_commit(empty_bar(stage));                 // smem stage reusable when these MMAs retire
-          if (kc == p.k_chunks - 1) umma_commit(tfull_bar(acc));
+          if (kc == ke - 1) umma_commit(tfull_bar(acc));
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -463,13 +517,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(TcParams p) {
     const int e = warp - TC_PROD_WARPS, q = e & 3, hsel = e >> 2;
     float* xch = reinterpret_cast<float*>(smem_gen + TC_STAGES * TC_STAGE_BYTES + 256);   // [2][128] softmax exchange
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      const int t = w % total_tiles;
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
       const int m = mt * TC_BM + q * 32 + lane;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TC_BN + ((uint32_t)(q * 32) << 16) + hsel * 128;
-      if (p.epi_mode == 1) {
+      if (p.k_splits > 1) {
+        tc_epilogue_split(p, taddr, m, nt, hsel, w / total_tiles);
+      } else if (p.epi_mode == 1) {
         tc_epilogue_softmax(p, taddr, m, nt, hsel, q * 32 + lane, xch);
       } else {
         switch (p.act) {
@@ -544,6 +601,60 @@ static void tc_narrow(zs::TcParams& p) {
   p.w_tile_bytes = (uint32_t)p.mma_n * 128u;
 }
 
+// Launch of a plain forward GEMM / convolution (epi_mode 0).  Few-tile layers -- the deep, small-image layers of the encoder: one
+// 128 x 256 tile per SM is busy for K / 64 chunk steps of ~0.8 us while most SMs idle -- are split along K: ks work items per tile,
+// raw partial tiles to a stream-ordered workspace, one deterministic finalize pass (bias / activation / residual).
+static int g_splitk_enable = 1, g_splitk_min_chunks = 4;     // at least this many 64-wide K-chunks per split
+template <int AMODE>
+static int tc_launch(zs::TcParams& p, cudaStream_t st, const char* name) {
+  using namespace zs;
+  const int tiles = p.m_tiles * p.n_tiles, sms = sm_count();
+  int ks = 1;
+  if (g_splitk_enable && p.epi_mode == 0 && p.rowscale == nullptr && tiles * 2 <= sms && p.k_chunks >= g_splitk_min_chunks * 2) {
+    ks = sms / tiles;
+    if (ks > p.k_chunks / g_splitk_min_chunks) ks = p.k_chunks / g_splitk_min_chunks;
+    if (ks > 16) ks = 16;
+    if (ks < 2) ks = 1;
+  }
+  p.k_splits = ks; p.ws = nullptr;
+  if (ks > 1) {
+    // stream-ordered workspace from the device's default memory pool; the pool must KEEP its memory across synchronisation points
+    // (release threshold 0, the default, hands it back to the driver at every sync: measured 10-100 ms per re-allocation)
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    ZS_CUDA_CALL(cudaGetDevice(&dev));
+    if (pool_dev != dev) {
+      cudaMemPool_t pool;
+      ZS_CUDA_CALL(cudaDeviceGetDefaultMemPool(&pool, dev));
+      unsigned long long keep = ~0ull;
+      ZS_CUDA_CALL(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      pool_dev = dev;
+    }
+    ZS_CUDA_CALL(cudaMallocAsync(reinterpret_cast<void**>(&p.ws), (size_t)ks * p.M * p.N * sizeof(float), st));
+  }
+  const int items = tiles * ks;
+  const int grid = items < sms ? items : sms;
+  if (p.precision == 0) gemm_tc_kernel<AMODE, true><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+  else gemm_tc_kernel<AMODE, false><<<grid, TC_THREADS, TC_SMEM, st>>>(p);
+  ZS_CUDA_CHECK_LAUNCH(name);
+  if (ks > 1) {
+    const int64_t total = (int64_t)p.M * p.N;
+    int fgrid = (int)((total + 255) / 256);
+    if (fgrid > sms * 8) fgrid = sms * 8;
+    splitk_finalize_kernel<<<fgrid, 256, 0, st>>>(p.ws, ks, p.M, p.N, p.bias, p.res, p.ldres, p.res_mode, p.act, p.C, p.ldc);
+    ZS_CUDA_CHECK_LAUNCH(name);
+    ZS_CUDA_CALL(cudaFreeAsync(p.ws, st));
+  }
+  return ZS_OK;
+}
+
+/* debug / A-B: 0 disables the split-K path of zs_gemm_tc_f32 / zs_conv2d_nhwc_tc (process-wide) */
+extern "C" int zs_debug_gemm_splitk(int enable) {      // 0 = off, 1 = on (default granularity), n >= 2 = on with n chunks per split
+  g_splitk_enable = enable != 0;
+  g_splitk_min_chunks = enable >= 2 ? enable : 4;
+  return ZS_OK;
+}
+
 extern "C" size_t zs_gemm_tc_packed_bytes(int N, int K) {
   if (N <= 0 || K <= 0) return 0;
   size_t nt = (N + TC_BN - 1) / TC_BN, kc = (K + TC_BK - 1) / TC_BK;
@@ -589,12 +700,7 @@ extern "C" int zs_gemm_tc_f32(const float* A, int lda, const void* Wpacked, cons
   p.a_nt_off = 0; p.c_nt_off = TC_BN; p.n_tile_valid = TC_BN; p.mma_n = TC_BN; p.w_tile_bytes = TC_B_TILE; p.epi_mode = 0;
   tc_narrow(p);
   p.qkv = nullptr; p.ld_qkv = 0; p.R = nullptr; p.R_inv = nullptr; p.scale = 0.f; p.n_keys = 0; p.rowscale = nullptr;
-  int tiles = p.m_tiles * p.n_tiles;
-  int grid = tiles < sm_count() ? tiles : sm_count();
-  if (p.precision == 0) gemm_tc_kernel<0, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
-  else gemm_tc_kernel<0, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
-  ZS_CUDA_CHECK_LAUNCH("zs_gemm_tc_f32");
-  return ZS_OK;
+  return tc_launch<0>(p, as_stream(stream), "zs_gemm_tc_f32");
 }
 
 // ---- implicit-GEMM convolution on the tensor cores (NHWC fp32 activations, OHWI filters packed as W[Cout, KH*KW*Cin]) ----
@@ -625,12 +731,7 @@ extern "C" int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, c
   tc_narrow(p);
   p.cB = B; p.cH = H; p.cW = W; p.cCin = Cin; p.cKH = KH; p.cKW = KW; p.cStride = stride; p.cPadT = pad_top; p.cPadL = pad_left;
   p.cOH = OH; p.cOW = OW; p.cPreRelu = pre_relu;
-  int tiles = p.m_tiles * p.n_tiles;
-  int grid = tiles < sm_count() ? tiles : sm_count();
-  if (p.precision == 0) gemm_tc_kernel<1, true><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
-  else gemm_tc_kernel<1, false><<<grid, TC_THREADS, TC_SMEM, as_stream(stream)>>>(p);
-  ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_tc");
-  return ZS_OK;
+  return tc_launch<1>(p, as_stream(stream), "zs_conv2d_nhwc_tc");
 }
 
 // ---- attention on the tensor cores (two grouped launches of gemm_tc_kernel) ------------------------------------

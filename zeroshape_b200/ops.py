@@ -5,6 +5,8 @@ Image tensors are NHWC fp32 contiguous unless noted.
 """
 import math
 
+import os
+
 import torch
 
 from . import _native
@@ -341,6 +343,9 @@ def chain_occ(x, points, ln_w, ln_b, ln_eps, blob, biases, w8, b8, sigmoid=False
 
 # Dense layers of the encoder side run on the tcgen05 kernel when the device has it ("auto"); "f32" forces the
 # bit-faithful FFMA kernels (parity pinning), "tc" requires the tensor-core path.
+if os.environ.get("ZS_GEMM_SPLITK"):              # A/B switch of the split-K path of the tcgen05 GEMM / convolution (few-tile layers)
+    lib.zs_debug_gemm_splitk(int(os.environ["ZS_GEMM_SPLITK"]))
+
 ENCODER_ENGINE = "auto"
 ENCODER_PRECISION = "bf16x3"
 
