@@ -102,7 +102,7 @@ def nhwc_to_nchw(x):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
-def mha(qkv, heads):
+def mha(qkv, heads, tc=None, precision="fp16x3"):
     B, T, C3 = qkv.shape
     C = C3 // 3
     hd = C // heads
