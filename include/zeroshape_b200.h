@@ -236,6 +236,13 @@ int zs_mha_f32(const float* qkv, float* out, int B, int T, int heads, int hd, fl
  * (precision 0: three passes, fp32-grade; 1: one fp16 pass), fp32 accumulation and the probabilities kept in tensor memory.
  * T <= 208 tokens, hd 32 or 64.  The 12 ViT blocks of the DPT-hybrid backbone (timm Block, model/depth/vit.py:149-150). */
 int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int heads, int hd, float scale, int precision, void* stream);
+/* Backward of the same operation on the tensor cores (csrc/mha_tc.cu: mha_bwd_q_kernel, mha_bwd_kv_kernel): S / dP and their
+ * transposes as tcgen05 MMAs with single-pass fp16 operands and fp32 accumulation, P and dS re-written in place in tensor memory
+ * as the A operands of dQ = dS K, dV = P^T dO, dK = dS^T Q.  Precision class of the bf16 training mode (zs_mha_bwd_f32 is the
+ * fp32-grade path).  dqkv [B,T,3C] is written completely; ws: zs_mha_bwd_tc_ws_bytes(B, T, heads), 16-byte aligned. */
+size_t zs_mha_bwd_tc_ws_bytes(int B, int T, int heads);
+int zs_mha_bwd_tc_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit decoder (model/shape/implicit.py:251-288), query-point side.

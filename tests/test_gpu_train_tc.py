@@ -129,3 +129,28 @@ def test_mha_bwd_two_pass(cuda, B, T, heads, hd):
     o.transpose(1, 2).reshape(B, T, C).backward(do.double())
     got = ops.mha_bwd(qkv.to(cuda), do.to(cuda), heads)
     assert _rel(got, qr.grad) < 2e-5, _rel(got, qr.grad)
+
+
+@pytest.mark.parametrize("B,T,heads,hd", [(2, 197, 12, 64), (3, 197, 8, 32), (1, 50, 4, 64), (2, 208, 2, 32), (1, 129, 1, 64), (1, 1, 1, 32)])
+def test_mha_bwd_on_the_tensor_cores(cuda, B, T, heads, hd):
+    """zs_mha_bwd_tc_f32 (S / dP and their transposes, dQ / dK / dV as tcgen05 MMAs, single fp16 pass): the precision class of the
+    bf16 training GEMMs, against fp64 autograd and next to the fp32 FFMA kernel."""
+    from zeroshape_b200 import ops
+    if ops.device_cc() != 100:
+        pytest.skip("tcgen05 needs sm_100")
+    g = torch.Generator().manual_seed(T * 3 + hd + heads)
+    C = heads * hd
+    qkv = torch.randn(B, T, 3 * C, generator=g) * 0.7
+    do = torch.randn(B, T, C, generator=g)
+    qr = qkv.double().requires_grad_(True)
+    q, k, v = qr.reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    o = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v
+    o.transpose(1, 2).reshape(B, T, C).backward(do.double())
+    got = ops.mha_bwd(qkv.to(cuda), do.to(cuda), heads, tc=True)
+    ffma = ops.mha_bwd(qkv.to(cuda), do.to(cuda), heads, tc=False)
+    parts = {n: _rel(got[..., i * C:(i + 1) * C], qr.grad[..., i * C:(i + 1) * C]) for i, n in enumerate("qkv")}
+    print(f"mha_bwd_tc B={B} T={T} heads={heads} hd={hd}: rel err dq {parts['q']:.2e} dk {parts['k']:.2e} dv {parts['v']:.2e}; "
+          f"FFMA kernel {_rel(ffma, qr.grad):.2e}")
+    assert max(parts.values()) < 4e-3, parts
+    assert torch.equal(got, ops.mha_bwd(qkv.to(cuda), do.to(cuda), heads, tc=True))        # deterministic
+

@@ -225,6 +225,311 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mha_tc_kernel(MhaTcParams p) {
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ===============================================================================================================
+// Backward of the token self-attention on the tensor cores (single fp16 pass, fp32 accumulation: the precision class of the
+// bf16 training mode; the FFMA kernels zs_mha_bwd_f32 stay the fp32-grade path).  With P = softmax(S), S = scale Q K^T:
+//     dV = P^T dO,   dP = dO V^T,   D = rowsum(P o dP),   dS = scale P o (dP - D),   dQ = dS K,   dK = dS^T Q.
+// Two launches, each the one-shot construction of mha_tc_kernel (operands converted by all threads, MMAs by one thread, the
+// A operands P / dS re-written IN PLACE in tensor memory as packed fp16 over the fp32 scores):
+//   mha_bwd_q_kernel  (image, head, 128-query tile): S and dP side by side in tensor memory; a thread per query row makes P, D
+//                     and dS; dQ = dS K (B operand = K^T, scatter-transposed in shared memory); row statistics (max * scale * log2 e,
+//                     1 / sum, D) to `stats` for the second launch.
+//   mha_bwd_kv_kernel (image, head, 128-key tile): the TRANSPOSED products S^T = K Q^T, dP^T = V dO^T (operands in their natural
+//                     row-major form), a thread per key row rebuilds P^T and dS^T from the per-query statistics, then dV = P^T dO and
+//                     dK = dS^T Q with dO^T / Q^T as scatter-transposed B operands; one accumulator, read out twice.
+constexpr int MB_OFF_A0 = 0;                    // q kernel: Q tile            kv kernel: K tile           (16 KB)
+constexpr int MB_OFF_A1 = 16 * 1024;            //           dO tile                      V tile           (16 KB)
+constexpr int MB_OFF_B0 = 32 * 1024;            //           K  [208 x hd]                Q  [208 x hd]    (32 KB)
+constexpr int MB_OFF_B1 = 64 * 1024;            //           V  [208 x hd]                dO [208 x hd]    (32 KB)
+constexpr int MB_OFF_T0 = 96 * 1024;            //           K^T chunks                   dO^T chunks      (32 KB)
+constexpr int MB_OFF_T1 = 128 * 1024;           //           --                           Q^T chunks       (32 KB)
+constexpr int MB_OFF_ST = 160 * 1024;           // kv kernel: [208][3] per-query statistics (2.5 KB)
+constexpr int MB_OFF_BAR = 164 * 1024;
+constexpr int MB_SMEM = MB_OFF_BAR + 64 + 1024;
+
+struct MhaBwdParams {
+  const float* qkv; const float* dO; float* dqkv; float* stats; int B, T, heads, hd; float scale;
+};
+
+// rows [r0, r0 + nrows) of a [T, hd] matrix (row stride ld floats) -> single-fp16 K-major SW128 tile; optionally also its transpose
+// as 64-column chunks (rows = dims, columns = tokens) for use as the B operand of a product that contracts over the tokens
+template <int HD, bool TRANSPOSE>
+__device__ __forceinline__ void mb_stage(const float* src, int64_t ld, int r0, int nrows, int T, uint8_t* tile, uint8_t* ttile) {
+  constexpr int CPR = HD / 8;
+  for (int i = threadIdx.x; i < nrows * CPR; i += MT_THREADS) {
+    const int r = i / CPR, c = i % CPR, t = r0 + r;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (t < T) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)t * ld + 8 * c);
+      x0 = __ldg(s4); x1 = __ldg(s4 + 1);
+    }
+    const uint4 h = make_uint4(cvt_f16x2_sat(x0.x, x0.y), cvt_f16x2_sat(x0.z, x0.w), cvt_f16x2_sat(x1.x, x1.y), cvt_f16x2_sat(x1.z, x1.w));
+    *reinterpret_cast<uint4*>(tile + swizzle128_offset(r, c)) = h;
+    if (TRANSPOSE) {
+      const float vv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      uint8_t* ch = ttile + (r >> 6) * (HD * 128);
+      const int kc = r & 63;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<__half*>(ch + swizzle128_offset(8 * c + u, kc >> 3) + (kc & 7) * 2) = __float2half_rn(vv[u]);
+    }
+  }
+}
+
+// 32 (16) fp32 values -> packed fp16 pairs in the first 16 (8) columns of their own block (A operand of a TS MMA, single pass)
+template <int NK>
+__device__ __forceinline__ void mb_store_packed(uint32_t taddr, const float* v) {
+  uint32_t h[NK / 2];
+#pragma unroll
+  for (int j = 0; j < NK / 2; ++j) h[j] = cvt_f16x2_sat(v[2 * j], v[2 * j + 1]);
+  if constexpr (NK == 32) tmem_st_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(h));
+  else tmem_st_32x8(taddr, *reinterpret_cast<uint32_t(*)[8]>(h));
+}
+
+// one thread issues D[128 x N] = A[tmem, packed fp16 over `keys` tokens] . B^T with B = the transposed chunks at tchunks
+template <int HD>
+__device__ __forceinline__ void mb_ts_product(uint32_t d_acc, uint32_t a_tm, uint32_t tchunks_addr) {
+  const uint32_t idesc = umma_idesc_f16(128, HD);
+#pragma unroll 1
+  for (int j = 0; j < 13; ++j) {
+    const uint32_t a = a_tm + 32u * (j >> 1) + 8u * (j & 1);
+    const uint64_t b = umma_desc_sw128(tchunks_addr + (j >> 2) * (HD * 128)) + 2 * (j & 3);
+    umma_ts(d_acc, a, b, idesc, j > 0 ? 1u : 0u);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MT_THREADS, 1) mha_bwd_q_kernel(MhaBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + MB_OFF_BAR, bar1 = bar0 + 8, tmem_slot = bar0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T, C = p.heads * HD;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads, q0 = blockIdx.y * 128;
+  const float* base = p.qkv + (int64_t)b * T * 3 * C + h * HD;
+  const float* dob = p.dO + (int64_t)b * T * C + h * HD;
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  mb_stage<HD, false>(base, 3 * C, q0, 128, T, smem + MB_OFF_A0, nullptr);                // Q tile
+  mb_stage<HD, false>(dob, C, q0, 128, T, smem + MB_OFF_A1, nullptr);                     // dO tile
+  mb_stage<HD, true>(base + C, 3 * C, 0, 208, T, smem + MB_OFF_B0, smem + MB_OFF_T0);     // K and K^T
+  mb_stage<HD, false>(base + 2 * C, 3 * C, 0, 208, T, smem + MB_OFF_B1, nullptr);         // V
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MB_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_p = tmem_base + 208, d_q = tmem_base + 416;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 208);
+    const uint64_t qa = umma_desc_sw128(smem_base + MB_OFF_A0), da = umma_desc_sw128(smem_base + MB_OFF_A1);
+    const uint64_t kb = umma_desc_sw128(smem_base + MB_OFF_B0), vb = umma_desc_sw128(smem_base + MB_OFF_B1);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_s, qa + 2 * k, kb + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_p, da + 2 * k, vb + 2 * k, idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar0);
+  }
+  if (warp < 4) {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t s_tm = d_s + lane_off, p_tm = d_p + lane_off;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    mbar_wait(bar0, 0);
+    tc_fence_after();
+    float mx = -3.0e38f;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rr[32];
+      if (c < 6) tmem_ld_32x32(s_tm + 32 * c, rr); else tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rr));
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j) if (32 * c + j < T) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    const float mxs = mx * sl2;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rr[32];
+      if (c < 6) tmem_ld_32x32(s_tm + 32 * c, rr); else tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rr));
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j) if (32 * c + j < T) sum += fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs));
+    }
+    const float inv = 1.0f / sum;
+    float D = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rs[32], rp[32];
+      if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+      else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j)
+        if (32 * c + j < T) D = fmaf(fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -mxs)) * inv, __uint_as_float(rp[j]), D);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rs[32], rp[32];
+      float ds[32];
+      if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+      else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pr = fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -mxs)) * inv;
+        ds[j] = (32 * c + j < T && (c < 6 || j < 16)) ? p.scale * pr * (__uint_as_float(rp[j]) - D) : 0.f;
+      }
+      if (c < 6) mb_store_packed<32>(p_tm + 32 * c, ds); else mb_store_packed<16>(p_tm + 192, ds);
+    }
+    tmem_st_wait();
+    const int t = q0 + warp * 32 + lane;
+    if (t < T) {
+      float* st = p.stats + (((int64_t)b * p.heads + h) * T + t) * 3;
+      st[0] = mxs; st[1] = inv; st[2] = D;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    mb_ts_product<HD>(d_q, d_p, smem_base + MB_OFF_T0);        // dQ = dS K
+    umma_commit(bar1);
+  }
+  if (warp < 4) {
+    const uint32_t o_tm = d_q + ((uint32_t)(warp * 32) << 16);
+    const int t = q0 + warp * 32 + lane;
+    mbar_wait(bar1, 0);
+    tc_fence_after();
+    float* dst = p.dqkv + ((int64_t)b * T + (t < T ? t : 0)) * 3 * C + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rr[16];
+      tmem_ld_32x16(o_tm + 16 * c, rr);
+      tmem_ld_wait();
+      if (t < T) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(dst + 16 * c + 4 * j) = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                                                        __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MT_THREADS, 1) mha_bwd_kv_kernel(MhaBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + MB_OFF_BAR, bar1 = bar0 + 8, bar2 = bar0 + 24, tmem_slot = bar0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.T, C = p.heads * HD;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads, k0 = blockIdx.y * 128;
+  const float* base = p.qkv + (int64_t)b * T * 3 * C + h * HD;
+  const float* dob = p.dO + (int64_t)b * T * C + h * HD;
+  float* stq = reinterpret_cast<float*>(smem + MB_OFF_ST);
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(bar2, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  mb_stage<HD, false>(base + C, 3 * C, k0, 128, T, smem + MB_OFF_A0, nullptr);            // K tile
+  mb_stage<HD, false>(base + 2 * C, 3 * C, k0, 128, T, smem + MB_OFF_A1, nullptr);        // V tile
+  mb_stage<HD, true>(base, 3 * C, 0, 208, T, smem + MB_OFF_B0, smem + MB_OFF_T1);         // Q and Q^T
+  mb_stage<HD, true>(dob, C, 0, 208, T, smem + MB_OFF_B1, smem + MB_OFF_T0);              // dO and dO^T
+  for (int i = threadIdx.x; i < 208 * 3; i += MT_THREADS)
+    stq[i] = i < T * 3 ? __ldg(p.stats + ((int64_t)b * p.heads + h) * T * 3 + i) : 0.f;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MB_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_p = tmem_base + 208, d_o = tmem_base + 416;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 208);
+    const uint64_t ka = umma_desc_sw128(smem_base + MB_OFF_A0), va = umma_desc_sw128(smem_base + MB_OFF_A1);
+    const uint64_t qb = umma_desc_sw128(smem_base + MB_OFF_B0), db = umma_desc_sw128(smem_base + MB_OFF_B1);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_s, ka + 2 * k, qb + 2 * k, idesc, k > 0 ? 1u : 0u);    // S^T  = K Q^T
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_p, va + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : 0u);    // dP^T = V dO^T
+    umma_commit(bar0);
+  }
+  if (warp < 4) {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t s_tm = d_s + lane_off, p_tm = d_p + lane_off;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    mbar_wait(bar0, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {          // columns = queries 32 c ...: P^T and dS^T from the per-query statistics
+      uint32_t rs[32], rp[32];
+      float pt[32], ds[32];
+      if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+      else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int qi = 32 * c + j;
+        const bool ok = qi < T && (c < 6 || j < 16);
+        const float* sq = stq + (ok ? qi : 0) * 3;
+        const float pr = ok ? fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -sq[0])) * sq[1] : 0.f;
+        pt[j] = pr;
+        ds[j] = ok ? p.scale * pr * (__uint_as_float(rp[j]) - sq[2]) : 0.f;
+      }
+      if (c < 6) { mb_store_packed<32>(s_tm + 32 * c, pt); mb_store_packed<32>(p_tm + 32 * c, ds); }
+      else { mb_store_packed<16>(s_tm + 192, pt); mb_store_packed<16>(p_tm + 192, ds); }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    mb_ts_product<HD>(d_o, d_s, smem_base + MB_OFF_T0);        // dV = P^T dO
+    umma_commit(bar1);
+  }
+  const int t = k0 + (warp & 3) * 32 + lane;
+  auto read_out = [&](int which) {                             // accumulator -> dqkv[b, t, which, h, :]
+    const uint32_t o_tm = d_o + ((uint32_t)(warp * 32) << 16);
+    float* dst = p.dqkv + ((int64_t)b * T + (t < T ? t : 0)) * 3 * C + which * C + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rr[16];
+      tmem_ld_32x16(o_tm + 16 * c, rr);
+      tmem_ld_wait();
+      if (t < T) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(dst + 16 * c + 4 * j) = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                                                        __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+      }
+    }
+  };
+  if (warp < 4) {
+    mbar_wait(bar1, 0);
+    tc_fence_after();
+    read_out(2);
+  }
+  tc_fence_before();
+  __syncthreads();                                             // the accumulator has been read: dK may overwrite it
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    mb_ts_product<HD>(d_o, d_p, smem_base + MB_OFF_T1);        // dK = dS^T Q
+    umma_commit(bar2);
+  }
+  if (warp < 4) {
+    mbar_wait(bar2, 0);
+    tc_fence_after();
+    read_out(1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace zs
 
 using namespace zs;
@@ -249,3 +554,36 @@ extern "C" int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int hea
   ZS_CUDA_CHECK_LAUNCH("zs_mha_tc_f32");
   return ZS_OK;
 }
+
+extern "C" size_t zs_mha_bwd_tc_ws_bytes(int B, int T, int heads) {
+  return B > 0 && T > 0 && heads > 0 ? (size_t)B * heads * T * 3 * sizeof(float) : 0;
+}
+
+extern "C" int zs_mha_bwd_tc_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale,
+                                 void* ws, void* stream) {
+  ZS_REQUIRE(qkv && dO && dqkv && ws && B >= 0 && heads > 0, "zs_mha_bwd_tc_f32: null pointer / bad sizes");
+  ZS_REQUIRE(T >= 1 && T <= 208 && (hd == 32 || hd == 64), "zs_mha_bwd_tc_f32: T must be in [1, 208] and the head dim 32 or 64");
+  ZS_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dO) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0,
+             "zs_mha_bwd_tc_f32: qkv / dO / dqkv / ws must be 16-byte aligned");
+  if (B == 0) return ZS_OK;
+  MhaBwdParams p{qkv, dO, dqkv, reinterpret_cast<float*>(ws), B, T, heads, hd, scale};
+  dim3 grid(B * heads, (T + 127) / 128);
+  cudaStream_t st = as_stream(stream);
+  if (hd == 64) {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_q_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_kv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    mha_bwd_q_kernel<64><<<grid, MT_THREADS, MB_SMEM, st>>>(p);
+    ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_tc_f32");
+    mha_bwd_kv_kernel<64><<<grid, MT_THREADS, MB_SMEM, st>>>(p);
+  } else {
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_q_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    ZS_CUDA_CALL(cudaFuncSetAttribute(mha_bwd_kv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+    mha_bwd_q_kernel<32><<<grid, MT_THREADS, MB_SMEM, st>>>(p);
+    ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_tc_f32");
+    mha_bwd_kv_kernel<32><<<grid, MT_THREADS, MB_SMEM, st>>>(p);
+  }
+  ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_tc_f32");
+  return ZS_OK;
+}
+

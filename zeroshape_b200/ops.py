@@ -861,11 +861,20 @@ def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
     return dqkv, dk, dv
 
 
-def mha_bwd(qkv, dout, heads):
+def mha_bwd(qkv, dout, heads, tc=None):
+    """Backward of `mha`: dqkv [B,T,3C].  `tc`: None = tensor cores (zs_mha_bwd_tc_f32: one fp16 pass, fp32 accumulation) when the
+    training engine is on them in its single-pass mode (TRAIN_PRECISION == "bf16") and the shape fits, else the fp32 FFMA kernels."""
     _chk(qkv, "qkv"); _chk(dout, "dout")
     B, T, C3 = qkv.shape
     C = C3 // 3
     dqkv = torch.empty_like(qkv)
+    if tc is None:
+        tc = train_tc() and TRAIN_PRECISION == "bf16"
+    if tc and T <= 208 and C // heads in (32, 64):
+        ws = torch.empty(lib.zs_mha_bwd_tc_ws_bytes(B, T, heads), device=qkv.device, dtype=torch.uint8)
+        check(lib.zs_mha_bwd_tc_f32(_p(qkv), _p(dout), _p(dqkv), B, T, heads, C // heads, (C // heads) ** -0.5, _p(ws), _stream()),
+              "zs_mha_bwd_tc_f32")
+        return dqkv
     ws = torch.empty(lib.zs_mha_bwd_ws_bytes(B, T, heads), device=qkv.device, dtype=torch.uint8)
     check(lib.zs_mha_bwd_f32(_p(qkv), _p(dout), _p(dqkv), B, T, heads, C // heads, (C // heads) ** -0.5, _p(ws), _stream()),
           "zs_mha_bwd_f32")
