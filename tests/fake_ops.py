@@ -258,11 +258,11 @@ def layernorm_bwd(dy, x, gamma, eps, dgamma=None, dbeta=None):
 layernorm_bwd_generic = layernorm_bwd
 
 
-def mha_bwd(qkv, dout, heads):
+def mha_bwd(qkv, dout, heads, tc=None):
     return _via_autograd(lambda t: mha(t, heads), qkv, dout)
 
 
-def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
+def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads, tc=None):
     qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (qkv_p, k_lat, v_lat))
     with torch.enable_grad():
         point_attention(qq, kk, vv, heads).backward(dout)

@@ -154,3 +154,36 @@ def test_mha_bwd_on_the_tensor_cores(cuda, B, T, heads, hd):
     assert max(parts.values()) < 4e-3, parts
     assert torch.equal(got, ops.mha_bwd(qkv.to(cuda), do.to(cuda), heads, tc=True))        # deterministic
 
+
+@pytest.mark.parametrize("B,P,L", [(2, 4096, 197), (1, 1000, 197), (3, 130, 50), (1, 1, 197), (1, 300, 208)])
+def test_point_attention_bwd_on_the_tensor_cores(cuda, B, P, L):
+    """zs_point_attention_bwd_tc_f32 (decoder training: points -> latents + the point's own key) against fp64 autograd of
+    ImplFuncAttention's point rows, next to the fp32 FFMA kernel; row-strided latent K / V views as the decoder passes them."""
+    from zeroshape_b200 import ops
+    if ops.device_cc() != 100:
+        pytest.skip("tcgen05 needs sm_100")
+    H, hd = 8, 32
+    C = H * hd
+    g = torch.Generator().manual_seed(P + L)
+    qkv = torch.randn(B, P, 3 * C, generator=g) * 0.7
+    lat = torch.randn(B, L, 3 * C, generator=g) * 0.7            # latent qkv buffer: K / V are column views (row stride 3C)
+    do = torch.randn(B, P, C, generator=g)
+    qr, lr = qkv.double().requires_grad_(True), lat.double().requires_grad_(True)
+    q, k, v = [t.reshape(B, P, H, hd).permute(0, 2, 1, 3) for t in (qr[..., :C], qr[..., C:2 * C], qr[..., 2 * C:])]
+    kl = lr[..., C:2 * C].reshape(B, L, H, hd).permute(0, 2, 1, 3)
+    vl = lr[..., 2 * C:].reshape(B, L, H, hd).permute(0, 2, 1, 3)
+    sc = torch.cat([q @ kl.transpose(-2, -1), (q * k).sum(-1, keepdim=True)], -1) * hd ** -0.5
+    a = sc.softmax(-1)
+    o = (a[..., :L] @ vl + a[..., L:] * v).permute(0, 2, 1, 3).reshape(B, P, C)
+    o.backward(do.double())
+    lat_d = lat.to(cuda)
+    out = o.detach().float().to(cuda)
+    res = {}
+    for tc in (True, False):
+        dqkv, dk, dv = ops.point_attention_bwd(qkv.to(cuda), lat_d[..., C:2 * C], lat_d[..., 2 * C:], out, do.to(cuda), H, tc=tc)
+        res[tc] = (_rel(dqkv[..., :C], qr.grad[..., :C]), _rel(dqkv[..., C:2 * C], qr.grad[..., C:2 * C]),
+                   _rel(dqkv[..., 2 * C:], qr.grad[..., 2 * C:]), _rel(dk, lr.grad[..., C:2 * C]), _rel(dv, lr.grad[..., 2 * C:]))
+    print(f"point_attention_bwd B={B} P={P} L={L}: rel err (dq, dk_self, dv_self, dk_lat, dv_lat) tcgen05 "
+          + " ".join(f"{e:.1e}" for e in res[True]) + " | FFMA " + " ".join(f"{e:.1e}" for e in res[False]))
+    assert max(res[True]) < 4e-3 and max(res[False]) < 2e-5
+

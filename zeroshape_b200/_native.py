@@ -92,6 +92,8 @@ SIGNATURES = {
     "zs_mha_tc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "zs_mha_bwd_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "zs_mha_bwd_tc_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
+    "zs_point_attention_bwd_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "zs_point_attention_bwd_tc_f32": (c_int, [P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P]),
     "zs_rgba_crop_resize_u8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P, c_int, P, P, c_int, P]),
     "zs_rgba_composite_f32": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P]),
     "zs_erode_square_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

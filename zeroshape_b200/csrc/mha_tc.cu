@@ -289,13 +289,13 @@ __device__ __forceinline__ void mb_store_packed(uint32_t taddr, const float* v) 
 
 // one thread issues D[128 x N] = A[tmem, packed fp16 over `keys` tokens] . B^T with B = the transposed chunks at tchunks
 template <int HD>
-__device__ __forceinline__ void mb_ts_product(uint32_t d_acc, uint32_t a_tm, uint32_t tchunks_addr) {
+__device__ __forceinline__ void mb_ts_product(uint32_t d_acc, uint32_t a_tm, uint32_t tchunks_addr, bool accumulate = false) {
   const uint32_t idesc = umma_idesc_f16(128, HD);
 #pragma unroll 1
   for (int j = 0; j < 13; ++j) {
     const uint32_t a = a_tm + 32u * (j >> 1) + 8u * (j & 1);
     const uint64_t b = umma_desc_sw128(tchunks_addr + (j >> 2) * (HD * 128)) + 2 * (j & 3);
-    umma_ts(d_acc, a, b, idesc, j > 0 ? 1u : 0u);
+    umma_ts(d_acc, a, b, idesc, (accumulate || j > 0) ? 1u : 0u);
   }
 }
 
@@ -530,6 +530,275 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mha_bwd_kv_kernel(MhaBwdParams 
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ===============================================================================================================
+// Backward of the decoder's point -> (latents + the point's own key) attention (ImplFuncAttention, model/shape/implicit.py:38-57;
+// forward: zs_point_attention_f32) on the tensor cores: the two-launch scheme of the token self-attention backward above with
+//   * queries = the P query points of an image (128 per CTA), keys = its L <= 208 latent tokens, head dim 32;
+//   * the point's OWN key / value as an extra softmax column handled per row in registers (s_self = q . k_self, its probability,
+//     dv_self = p_self dO, dk_self = ds_self q, dq += ds_self k_self);
+//   * the key-side launch looping over the points in chunks of 208 with dV and dK accumulating in tensor memory.
+// Single fp16 pass, fp32 accumulation (precision class of the bf16 training mode).
+struct PaBwdParams {
+  const float* qkv_p; const float* k_lat; const float* v_lat; int ld_lat; const float* dO;
+  float* dqkv_p; float* dk_lat; float* dv_lat; int ld_dlat; float* stats; int B, P, L, heads; float scale;
+};
+
+__global__ void __launch_bounds__(MT_THREADS, 1) pa_bwd_q_kernel(PaBwdParams p) {
+  constexpr int HD = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + MB_OFF_BAR, bar1 = bar0 + 8, tmem_slot = bar0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.P, L = p.L, C = p.heads * HD;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads, p0 = blockIdx.y * 128;
+  const float* qb = p.qkv_p + (int64_t)b * P * 3 * C + h * HD;
+  const float* dob = p.dO + (int64_t)b * P * C + h * HD;
+  const float* kl = p.k_lat + (int64_t)b * L * p.ld_lat + h * HD;
+  const float* vl = p.v_lat + (int64_t)b * L * p.ld_lat + h * HD;
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  mb_stage<HD, false>(qb, 3 * C, p0, 128, P, smem + MB_OFF_A0, nullptr);
+  mb_stage<HD, false>(dob, C, p0, 128, P, smem + MB_OFF_A1, nullptr);
+  mb_stage<HD, true>(kl, p.ld_lat, 0, 208, L, smem + MB_OFF_B0, smem + MB_OFF_T0);
+  mb_stage<HD, false>(vl, p.ld_lat, 0, 208, L, smem + MB_OFF_B1, nullptr);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MB_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_p = tmem_base + 208, d_q = tmem_base + 416;
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 208);
+    const uint64_t qa = umma_desc_sw128(smem_base + MB_OFF_A0), da = umma_desc_sw128(smem_base + MB_OFF_A1);
+    const uint64_t kb = umma_desc_sw128(smem_base + MB_OFF_B0), vb = umma_desc_sw128(smem_base + MB_OFF_B1);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_s, qa + 2 * k, kb + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) umma_bf16(d_p, da + 2 * k, vb + 2 * k, idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar0);
+  }
+  float ps = 0.f, ds_self = 0.f;
+  const int pt = p0 + (warp & 3) * 32 + lane;
+  const bool live = pt < P;
+  const float4* qrow = reinterpret_cast<const float4*>(qb + (int64_t)(live ? pt : 0) * 3 * C);
+  const float4* grow = reinterpret_cast<const float4*>(dob + (int64_t)(live ? pt : 0) * C);
+  if (warp < 4) {
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t s_tm = d_s + lane_off, p_tm = d_p + lane_off;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    // the point's own key / value: raw self score and dO . v_self
+    float s_self = 0.f, dp_self = 0.f;
+#pragma unroll
+    for (int j = 0; j < HD / 4; ++j) {
+      const float4 q4 = __ldg(qrow + j), k4 = __ldg(qrow + C / 4 + j), v4 = __ldg(qrow + 2 * C / 4 + j), g4 = __ldg(grow + j);
+      s_self = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, s_self))));
+      dp_self = fmaf(g4.x, v4.x, fmaf(g4.y, v4.y, fmaf(g4.z, v4.z, fmaf(g4.w, v4.w, dp_self))));
+    }
+    mbar_wait(bar0, 0);
+    tc_fence_after();
+    float mx = s_self;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rr[32];
+      if (c < 6) tmem_ld_32x32(s_tm + 32 * c, rr); else tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rr));
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j) if (32 * c + j < L) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    const float mxs = mx * sl2;
+    const float e_self = fast_ex2(fmaf(s_self, sl2, -mxs));
+    float sum = e_self;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rr[32];
+      if (c < 6) tmem_ld_32x32(s_tm + 32 * c, rr); else tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rr));
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j) if (32 * c + j < L) sum += fast_ex2(fmaf(__uint_as_float(rr[j]), sl2, -mxs));
+    }
+    const float inv = 1.0f / sum;
+    ps = e_self * inv;
+    float D = ps * dp_self;
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rs[32], rp[32];
+      if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+      else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+      tmem_ld_wait();
+      const int n = c < 6 ? 32 : 16;
+      for (int j = 0; j < n; ++j)
+        if (32 * c + j < L) D = fmaf(fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -mxs)) * inv, __uint_as_float(rp[j]), D);
+    }
+    ds_self = p.scale * ps * (dp_self - D);
+#pragma unroll 1
+    for (int c = 0; c < 7; ++c) {
+      uint32_t rs[32], rp[32];
+      float ds[32];
+      if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+      else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pr = fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -mxs)) * inv;
+        ds[j] = (32 * c + j < L && (c < 6 || j < 16)) ? p.scale * pr * (__uint_as_float(rp[j]) - D) : 0.f;
+      }
+      if (c < 6) mb_store_packed<32>(p_tm + 32 * c, ds); else mb_store_packed<16>(p_tm + 192, ds);
+    }
+    tmem_st_wait();
+    if (live) {
+      float* st = p.stats + (((int64_t)b * p.heads + h) * P + pt) * 3;
+      st[0] = mxs; st[1] = inv; st[2] = D;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4 && lane == 0) {
+    mb_ts_product<HD>(d_q, d_p, smem_base + MB_OFF_T0);        // dq (latent part) = dS K_lat
+    umma_commit(bar1);
+  }
+  if (warp < 4) {
+    const uint32_t o_tm = d_q + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(bar1, 0);
+    tc_fence_after();
+    float4* dst = reinterpret_cast<float4*>(p.dqkv_p + ((int64_t)b * P + (live ? pt : 0)) * 3 * C + h * HD);
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rr[16];
+      tmem_ld_32x16(o_tm + 16 * c, rr);
+      tmem_ld_wait();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int jj = 4 * c + j;
+          const float4 q4 = __ldg(qrow + jj), k4 = __ldg(qrow + C / 4 + jj), g4 = __ldg(grow + jj);
+          dst[jj] = make_float4(fmaf(ds_self, k4.x, __uint_as_float(rr[4 * j])), fmaf(ds_self, k4.y, __uint_as_float(rr[4 * j + 1])),
+                                fmaf(ds_self, k4.z, __uint_as_float(rr[4 * j + 2])), fmaf(ds_self, k4.w, __uint_as_float(rr[4 * j + 3])));
+          dst[C / 4 + jj] = make_float4(ds_self * q4.x, ds_self * q4.y, ds_self * q4.z, ds_self * q4.w);          // dk_self
+          dst[2 * C / 4 + jj] = make_float4(ps * g4.x, ps * g4.y, ps * g4.z, ps * g4.w);                          // dv_self
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+__global__ void __launch_bounds__(MT_THREADS, 1) pa_bwd_kv_kernel(PaBwdParams p) {
+  constexpr int HD = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_base + MB_OFF_BAR, bar1 = bar0 + 8, tmem_slot = bar0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.P, L = p.L, C = p.heads * HD;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads, k0 = blockIdx.y * 128;
+  const float* qb = p.qkv_p + (int64_t)b * P * 3 * C + h * HD;
+  const float* dob = p.dO + (int64_t)b * P * C + h * HD;
+  const float* kl = p.k_lat + (int64_t)b * L * p.ld_lat + h * HD;
+  const float* vl = p.v_lat + (int64_t)b * L * p.ld_lat + h * HD;
+  const float* stg = p.stats + ((int64_t)b * p.heads + h) * P * 3;
+  float* stq = reinterpret_cast<float*>(smem + MB_OFF_ST);
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  mb_stage<HD, false>(kl, p.ld_lat, k0, 128, L, smem + MB_OFF_A0, nullptr);        // this CTA's 128 latent keys / values
+  mb_stage<HD, false>(vl, p.ld_lat, k0, 128, L, smem + MB_OFF_A1, nullptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MB_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_p = tmem_base + 208, d_v = tmem_base + 416, d_k = tmem_base + 448;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int n_chunks = (P + 207) / 208;
+  uint32_t ph = 0;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int c0 = ch * 208;
+    mb_stage<HD, true>(qb, 3 * C, c0, 208, P, smem + MB_OFF_B0, smem + MB_OFF_T1);       // Q chunk and its transpose
+    mb_stage<HD, true>(dob, C, c0, 208, P, smem + MB_OFF_B1, smem + MB_OFF_T0);          // dO chunk and its transpose
+    for (int i = threadIdx.x; i < 208 * 3; i += MT_THREADS) stq[i] = c0 * 3 + i < P * 3 ? __ldg(stg + c0 * 3 + i) : 0.f;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4 && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, 208);
+      const uint64_t ka = umma_desc_sw128(smem_base + MB_OFF_A0), va = umma_desc_sw128(smem_base + MB_OFF_A1);
+      const uint64_t qd = umma_desc_sw128(smem_base + MB_OFF_B0), dd = umma_desc_sw128(smem_base + MB_OFF_B1);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_bf16(d_s, ka + 2 * k, qd + 2 * k, idesc, k > 0 ? 1u : 0u);    // S^T  = K_lat Q^T
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_bf16(d_p, va + 2 * k, dd + 2 * k, idesc, k > 0 ? 1u : 0u);    // dP^T = V_lat dO^T
+      umma_commit(bar0);
+    }
+    if (warp < 4) {
+      const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+      const uint32_t s_tm = d_s + lane_off, p_tm = d_p + lane_off;
+      mbar_wait(bar0, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 7; ++c) {
+        uint32_t rs[32], rp[32];
+        float ptv[32], ds[32];
+        if (c < 6) { tmem_ld_32x32(s_tm + 32 * c, rs); tmem_ld_32x32(p_tm + 32 * c, rp); }
+        else { tmem_ld_32x16(s_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rs)); tmem_ld_32x16(p_tm + 192, *reinterpret_cast<uint32_t(*)[16]>(rp)); }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qi = 32 * c + j;
+          const bool ok = c0 + qi < P && (c < 6 || j < 16);
+          const float* sq = stq + (ok ? qi : 0) * 3;
+          const float pr = ok ? fast_ex2(fmaf(__uint_as_float(rs[j]), sl2, -sq[0])) * sq[1] : 0.f;
+          ptv[j] = pr;
+          ds[j] = ok ? p.scale * pr * (__uint_as_float(rp[j]) - sq[2]) : 0.f;
+        }
+        if (c < 6) { mb_store_packed<32>(s_tm + 32 * c, ptv); mb_store_packed<32>(p_tm + 32 * c, ds); }
+        else { mb_store_packed<16>(s_tm + 192, ptv); mb_store_packed<16>(p_tm + 192, ds); }
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 4 && lane == 0) {
+      mb_ts_product<HD>(d_v, d_s, smem_base + MB_OFF_T0, ch > 0);        // dV += P^T dO
+      mb_ts_product<HD>(d_k, d_p, smem_base + MB_OFF_T1, ch > 0);        // dK += dS^T Q
+      umma_commit(bar1);
+    }
+    // the next chunk overwrites the operand tiles and the score columns: every thread waits for these MMAs
+    mbar_wait(bar1, ph);
+    tc_fence_after();
+    ph ^= 1;
+  }
+  if (warp < 4) {
+    const int key = k0 + warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float* dvd = p.dv_lat + ((int64_t)b * L + (key < L ? key : 0)) * p.ld_dlat + h * HD;
+    float* dkd = p.dk_lat + ((int64_t)b * L + (key < L ? key : 0)) * p.ld_dlat + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rv[16], rk[16];
+      tmem_ld_32x16(d_v + lane_off + 16 * c, rv);
+      tmem_ld_32x16(d_k + lane_off + 16 * c, rk);
+      tmem_ld_wait();
+      if (key < L) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<float4*>(dvd + 16 * c + 4 * j) = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
+                                                                        __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3]));
+          *reinterpret_cast<float4*>(dkd + 16 * c + 4 * j) = make_float4(__uint_as_float(rk[4 * j]), __uint_as_float(rk[4 * j + 1]),
+                                                                        __uint_as_float(rk[4 * j + 2]), __uint_as_float(rk[4 * j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace zs
 
 using namespace zs;
@@ -584,6 +853,29 @@ extern "C" int zs_mha_bwd_tc_f32(const float* qkv, const float* dO, float* dqkv,
     mha_bwd_kv_kernel<32><<<grid, MT_THREADS, MB_SMEM, st>>>(p);
   }
   ZS_CUDA_CHECK_LAUNCH("zs_mha_bwd_tc_f32");
+  return ZS_OK;
+}
+
+extern "C" size_t zs_point_attention_bwd_tc_ws_bytes(int B, int P, int heads) {
+  return B > 0 && P > 0 && heads > 0 ? (size_t)B * heads * P * 3 * sizeof(float) : 0;
+}
+
+extern "C" int zs_point_attention_bwd_tc_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, const float* dO,
+                                             float* dqkv_p, float* dk_lat, float* dv_lat, int ld_dlat, int B, int P, int L, int heads,
+                                             int hd, float scale, void* ws, void* stream) {
+  ZS_REQUIRE(qkv_p && k_lat && v_lat && dO && dqkv_p && dk_lat && dv_lat && ws, "zs_point_attention_bwd_tc_f32: null pointer");
+  ZS_REQUIRE(hd == 32 && B > 0 && P > 0 && L > 0 && L <= 208 && heads > 0, "zs_point_attention_bwd_tc_f32: head dim 32, 1 <= L <= 208");
+  ZS_REQUIRE((ld_lat & 3) == 0 && (ld_dlat & 3) == 0, "zs_point_attention_bwd_tc_f32: latent row strides must be multiples of 4");
+  const void* ptrs[] = {qkv_p, k_lat, v_lat, dO, dqkv_p, dk_lat, dv_lat, ws};
+  for (const void* q : ptrs) ZS_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0, "zs_point_attention_bwd_tc_f32: 16-byte alignment");
+  PaBwdParams p{qkv_p, k_lat, v_lat, ld_lat, dO, dqkv_p, dk_lat, dv_lat, ld_dlat, reinterpret_cast<float*>(ws), B, P, L, heads, scale};
+  cudaStream_t st = as_stream(stream);
+  ZS_CUDA_CALL(cudaFuncSetAttribute(pa_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  ZS_CUDA_CALL(cudaFuncSetAttribute(pa_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
+  pa_bwd_q_kernel<<<dim3(B * heads, (P + 127) / 128), MT_THREADS, MB_SMEM, st>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_point_attention_bwd_tc_f32");
+  pa_bwd_kv_kernel<<<dim3(B * heads, (L + 127) / 128), MT_THREADS, MB_SMEM, st>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_point_attention_bwd_tc_f32");
   return ZS_OK;
 }
 

@@ -845,8 +845,9 @@ def layernorm_bwd(dy, x, gamma, eps, dgamma=None, dbeta=None):
     return dx
 
 
-def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
-    """Backward of `point_attention`: -> dqkv_p [B,P,3C], dk_lat [B,L,C], dv_lat [B,L,C]."""
+def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads, tc=None):
+    """Backward of `point_attention`: -> dqkv_p [B,P,3C], dk_lat [B,L,C], dv_lat [B,L,C].  `tc`: None = tensor cores
+    (zs_point_attention_bwd_tc_f32, one fp16 pass) when the training engine is on them in its single-pass mode, else FFMA."""
     _chk(qkv_p, "qkv_p"); _chk(out, "out"); _chk(dout, "dout")
     B, Pn, C3 = qkv_p.shape
     C = C3 // 3
@@ -856,6 +857,14 @@ def point_attention_bwd(qkv_p, k_lat, v_lat, out, dout, heads):
     dqkv = torch.empty_like(qkv_p)
     dk = torch.empty(B, L, C, device=qkv_p.device, dtype=torch.float32)
     dv = torch.empty(B, L, C, device=qkv_p.device, dtype=torch.float32)
+    if tc is None:
+        tc = train_tc() and TRAIN_PRECISION == "bf16"
+    if tc and L <= 208 and C // heads == 32 and k_lat.stride(1) % 4 == 0:
+        ws = torch.empty(lib.zs_point_attention_bwd_tc_ws_bytes(B, Pn, heads), device=qkv_p.device, dtype=torch.uint8)
+        check(lib.zs_point_attention_bwd_tc_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(dout), _p(dqkv), _p(dk), _p(dv), C,
+                                                B, Pn, L, heads, C // heads, (C // heads) ** -0.5, _p(ws), _stream()),
+              "zs_point_attention_bwd_tc_f32")
+        return dqkv, dk, dv
     check(lib.zs_point_attention_bwd_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(out), _p(dout), _p(dqkv), _p(dk), _p(dv),
                                          C, B, Pn, L, heads, C // heads, (C // heads) ** -0.5, _stream()), "zs_point_attention_bwd_f32")
     return dqkv, dk, dv
