@@ -541,7 +541,8 @@ def run_train(args, rank, world, dev):
     with torch.no_grad():
         graph.intr_proj.weight.normal_(0, 0.02)        # the reference's zero init would cut the intrinsics path out of the step
     trainable = [p for p in graph.parameters() if p.requires_grad]
-    optim = FusedAdamW(trainable, lr=3e-5, betas=(0.9, 0.95), weight_decay=0.05)
+    use_graph = bool(getattr(args, "train_graph", 1))
+    optim = FusedAdamW(trainable, lr=3e-5, betas=(0.9, 0.95), weight_decay=0.05, capturable=use_graph)
     rgb_h, mask_h = synthetic_images(B, 2000 + rank)
     g = torch.Generator().manual_seed(3)
     depth_h = (1.5 + 0.3 * torch.rand(B, 1, 224, 224, generator=g)) * mask_h
@@ -551,16 +552,31 @@ def run_train(args, rank, world, dev):
     sdf_h = pts_h.norm(dim=-1) - 0.3 - 0.003
     host = [t.pin_memory() for t in (rgb_h, mask_h, depth_h, intr_h, pose_h, pts_h, sdf_h)]
 
-    def step():
-        rgb, mask, depth, intr, pose, pts, sdf = (t.to(dev, non_blocking=True) for t in host)
+    def iteration(rgb, mask, depth, intr, pose, pts, sdf):
         var = EasyDict(idx=torch.arange(B), rgb_input_map=rgb, mask_input_map=mask, depth_input_map=depth, intr=intr, pose_gt=pose,
                        gt_sample_points=pts, gt_sample_sdf=sdf)
-        var, loss = graph.forward(opt, var, training=True)
         optim.zero_grad()
+        var, loss = graph.forward(opt, var, training=True)
         loss.shape.backward()
         optim.step()
         return loss.shape
+
+    def eager_step():
+        return iteration(*(t.to(dev, non_blocking=True) for t in host))
     n_warm = max(3, args.warmup)
+    step, graph_note = eager_step, None
+    if use_graph:
+        # the whole iteration as ONE CUDA-graph launch (zeroshape_b200/graphed.py); the per-step host -> device copies of the
+        # batch stay outside the graph, in front of every replay
+        from zeroshape_b200.graphed import GraphedTrainStep
+        try:
+            gstep = GraphedTrainStep(iteration, optim, example_inputs=[t.to(dev) for t in host], warmup=n_warm)
+            step = lambda: gstep(*host)                                                       # noqa: E731
+        except Exception as e:                                                                # noqa: BLE001
+            torch.cuda.synchronize()
+            graph_note = repr(e)[:300]
+            use_graph = False
+            optim = FusedAdamW(trainable, lr=3e-5, betas=(0.9, 0.95), weight_decay=0.05)
     for _ in range(n_warm):
         step()
     torch.cuda.synchronize()
@@ -587,8 +603,9 @@ def run_train(args, rank, world, dev):
             "config": {"workload": f"BASELINE config 3: train_iteration, batch {B} synthetic images x {N} GT points, fix_dpt false, shape loss only; "
                                    "tokens = B x (197 + 197 + 4096)", "train_batch": B, "train_engine": args.train_engine,
                        "train_precision": args.train_precision},
+            "cuda_graph": use_graph, **({"cuda_graph_error": graph_note} if graph_note else {}),
             "trainable_parameters": int(sum(p.numel() for p in trainable)), "last_loss": last,
-            "gpu_launches": int(lib.zs_launch_count() - l0),
+            "gpu_launches": (args.steps * gstep.launches_per_replay if use_graph else int(lib.zs_launch_count() - l0)),
             "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
 
 
@@ -858,6 +875,8 @@ def main():
                     help="train: BASELINE config 3 (full train_iteration, fwd + loss + bwd + AdamW); train-decoder: decoder slice only")
     ap.add_argument("--eval-shapes", type=int, default=256, help="mode eval: size of the synthetic evaluation set (all ranks together)")
     ap.add_argument("--brute-force", action="store_true", help="mode eval: the 6912-rotation pose search of evaluate.py (README protocol)")
+    ap.add_argument("--train-graph", type=int, default=1, help="--mode train: 1 = the whole iteration replayed from one CUDA graph "
+                                                                "(zeroshape_b200/graphed.py), 0 = launched op by op")
     ap.add_argument("--train-batch", type=int, default=32, help="images per training step (options/shape.yaml batch 28-32)")
     ap.add_argument("--train-engine", default="tc", choices=["tc", "f32"], help="modes train / train-decoder: tcgen05 or FFMA GEMM kernels")
     ap.add_argument("--train-precision", default="bf16", choices=["bf16", "bf16x3"],

@@ -328,6 +328,11 @@ int zs_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg
  * 64-bit words {param, grad, exp_avg, exp_avg_sq (device addresses), numel}; identical arithmetic to zs_adamw_f32. */
 int zs_adamw_multi_f32(const void* table, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
                        int step, void* stream);
+/* The same update with every step-dependent scalar in device memory: hyper[7] = {lr, beta1, beta2, eps, weight_decay,
+ * 1 - beta1^step, sqrt(1 - beta2^step)}.  `host_table` is the same table in HOST memory: its rows travel by value in the kernel
+ * parameters (96 tensors per launch), so the call reads no host buffer at run time and is capturable in a CUDA graph; the host
+ * refreshes `hyper` with a stream-ordered copy before each replay (zeroshape_b200/graphed.py). */
+int zs_adamw_multi_dev_f32(const void* host_table, int n_tensors, const float* hyper, void* stream);
 
 /* Training of the seen-surface encoder (CoordEncRes: torchvision ResNet-50 + Bottleneck_Conv heads with batch-statistics
  * BatchNorm, model/shape/seen_coord_enc.py:141-194; the `optim.fix_dpt` configuration of options/shape.yaml).

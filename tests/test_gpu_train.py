@@ -464,3 +464,104 @@ def test_full_graph_training_step(cuda, engine):
         losses.append(loss.shape.item())
     print("full-graph shape loss per step:", [round(v, 4) for v in losses])
     assert losses[-1] < losses[0] and all(np.isfinite(losses))
+
+
+def test_adamw_capturable_matches_torch(cuda):
+    """FusedAdamW(capturable=True): scalars in device memory, tensor table in the kernel parameters (zs_adamw_multi_dev_f32) --
+    the same numbers as torch.optim.AdamW, two parameter groups, > 96 tensors (several launches per group)."""
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    g = torch.Generator().manual_seed(5)
+    ws = [torch.randn(int(n), generator=g) for n in torch.randint(1, 3000, (130,), generator=g)]
+    pa = [torch.nn.Parameter(w.clone().to(cuda)) for w in ws]
+    pb = [torch.nn.Parameter(w.clone()) for w in ws]
+    groups = lambda ps: [dict(params=ps[:100], lr=3e-3, weight_decay=0.05), dict(params=ps[100:], lr=1e-3, weight_decay=0.0)]   # noqa: E731
+    oa = FusedAdamW(groups(pa), betas=(0.9, 0.95), capturable=True)
+    ob = torch.optim.AdamW(groups(pb), betas=(0.9, 0.95))
+    for i in range(4):
+        for a, b in zip(pa, pb):
+            gr_ = torch.randn(a.shape, generator=g)
+            a.grad, b.grad = gr_.to(cuda), gr_.clone()
+        if i == 2:
+            for o in (oa, ob):
+                o.param_groups[0]["lr"] = 1e-3                # a scheduler step
+        oa.step(); ob.step()
+    err = max((a.detach().cpu() - b.detach()).abs().max().item() for a, b in zip(pa, pb))
+    assert err < 2e-6, err
+    assert all(oa.state[p]["step"] == 4 for p in pa)
+
+
+def test_graphed_training_step_matches_eager(cuda):
+    """zeroshape_b200/graphed.py: the whole train_iteration of options/shape.yaml (fix_dpt false) captured in ONE CUDA graph
+    and replayed -- the same loss trajectory as launching the step op by op, optimizer state / version counters advanced."""
+    from zeroshape_b200.graphed import GraphedTrainStep
+    from zeroshape_b200.model.shape.implicit_train import FusedAdamW
+    from zeroshape_b200.utils.util import EasyDict
+    from test_gpu_graph import synthetic_image_and_mask
+    _engine("tc-bf16")
+    B, N, steps, warm = 2, 512, 6, 2
+    rgb, mask = synthetic_image_and_mask(B, 72)
+    g = torch.Generator().manual_seed(73)
+    depth_gt = (1.5 + 0.3 * torch.rand(B, 1, 224, 224, generator=g)) * mask
+    intr = torch.tensor([[1.3875 * 224, 0, 112], [0, 1.3875 * 224, 112], [0, 0, 1.0]]).repeat(B, 1, 1)
+    pose = torch.cat([torch.eye(3), torch.tensor([[0.0], [0.0], [1.6]])], dim=1).repeat(B, 1, 1)
+    gt_pts = torch.rand(B, N, 3, generator=g) - 0.5
+    gt_sdf = gt_pts.norm(dim=-1) - 0.3 - 0.003
+    host = [t.pin_memory() for t in (rgb, mask, depth_gt, intr, pose, gt_pts, gt_sdf)]
+
+    def make(capturable):
+        opt, graph, _ = _graph_and_sd(cuda, 71)
+        graph.train()
+        graph.impl_network.drop_path = 0.0
+        params = [p for p in graph.parameters() if p.requires_grad]
+        # (random initialisation: a larger step kills the output ReLU of the depth head -> zero seen surface -> 0 / 0)
+        optim = FusedAdamW(params, lr=3e-6, betas=(0.9, 0.95), weight_decay=0.05, capturable=capturable)
+
+        def iteration(rgb, mask, depth, intr, pose, pts, sdf):
+            var = EasyDict(idx=torch.arange(B), rgb_input_map=rgb, mask_input_map=mask, depth_input_map=depth, intr=intr,
+                           pose_gt=pose, gt_sample_points=pts, gt_sample_sdf=sdf)
+            optim.zero_grad()
+            var, loss = graph.forward(opt, var, training=True)
+            loss.shape.backward()
+            optim.step()
+            return loss.shape
+        return graph, params, optim, iteration
+
+    graph_e, params_e, optim_e, it_e = make(False)
+    dev_in = [t.to(cuda) for t in host]
+    eager = [it_e(*dev_in).item() for _ in range(steps)]
+    graph_g, params_g, optim_g, it_g = make(True)
+    gstep = GraphedTrainStep(it_g, optim_g, example_inputs=host, warmup=warm)          # `warm` real steps, then the capture
+    assert gstep.launches_per_replay > 500
+    # (1) ONE step from a known state, replayed and launched op by op: the same loss, the same parameters afterwards
+    used = [p for p in params_g if p.grad is not None]
+    model0 = {k: v.detach().clone() for k, v in graph_g.state_dict().items()}
+    optim0 = [(optim_g.state[p]["step"], optim_g.state[p]["exp_avg"].clone(), optim_g.state[p]["exp_avg_sq"].clone()) for p in used]
+    v0 = params_g[0]._version
+    loss_r = gstep(*host).item()
+    after_r = [p.detach().clone() for p in params_g]
+    assert params_g[0]._version > v0 and all(optim_g.state[p]["step"] == warm + 1 for p in used)
+    with torch.no_grad():
+        for k, v in graph_g.state_dict().items():
+            v.copy_(model0[k])                                       # in place: the graph keeps its addresses
+        for p, (st, m, v) in zip(used, optim0):
+            optim_g.state[p]["step"] = st
+            optim_g.state[p]["exp_avg"].copy_(m)
+            optim_g.state[p]["exp_avg_sq"].copy_(v)
+    loss_e = it_g(*dev_in).item()
+    print("one step from the same state: replayed loss", loss_r, "| op by op", loss_e)
+    assert abs(loss_r - loss_e) < 1e-5 * abs(loss_e), (loss_r, loss_e)
+    num = sum(((a - b.detach()).double() ** 2).sum().item() for a, b in zip(after_r, params_g))
+    den = sum((a.double() ** 2).sum().item() for a in after_r)
+    assert (num / den) ** 0.5 < 1e-5, (num / den) ** 0.5
+    # (2) the trajectory: `warm` + 1 steps done, the rest replayed.  Loose: Adam's normalised update amplifies the run-to-run
+    # noise of the atomically accumulated gradients (an element with a ~0 gradient moves by +-lr either way)
+    graphed = [gstep(*host).item() for _ in range(steps - warm - 1)]
+    print("eager  :", [round(v, 5) for v in eager])
+    print("graphed:", [round(v, 5) for v in graphed], "| launches per replay:", gstep.launches_per_replay)
+    for a, b in zip(eager[warm + 1:], graphed):
+        assert abs(a - b) < 1e-2 * abs(a), (eager, graphed)
+    assert all(np.isfinite(eager)) and all(np.isfinite(graphed))
+    assert all(optim_g.state[p]["step"] == steps for p in used)
+    for tag, gr_ in (("eager", graph_e), ("graphed", graph_g)):
+        bad = [n for n, p in gr_.named_parameters() if not torch.isfinite(p).all()]
+        assert not bad, (tag, bad[:8])

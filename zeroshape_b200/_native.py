@@ -66,6 +66,7 @@ SIGNATURES = {
     "zs_midas_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "zs_midas_loss_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_float, P, P, P, P]),
     "zs_adamw_multi_f32": (c_int, [P, c_int, c_float, c_float, c_float, c_float, c_float, c_int, P]),
+    "zs_adamw_multi_dev_f32": (c_int, [P, c_int, P, P]),
     "zs_mean_axis1_f32": (c_int, [P, P, c_int64, c_int, c_int, P]),
     "zs_point_proj_f32": (c_int, [P, c_int64, P, P, P, c_int, P]),
     "zs_chain_lin_fwd": (c_int, [P, c_int, c_int, c_int, c_float, P, c_int, P, P, c_int, P, c_int, c_int, P]),

@@ -4,6 +4,7 @@
 //              model/shape_engine.py:248-277 (loss.backward(); optim.step()), torch autograd for every layer of
 //              model/shape/implicit.py.
 // All kernels are fp32 (gradient parity against torch autograd on the oracle); no tensor-core path yet.
+#include <cstring>
 #include "common.cuh"
 
 namespace zs {
@@ -795,9 +796,48 @@ __global__ void adamw_multi_kernel(const unsigned long long* __restrict__ table,
   }
 }
 
+// the same update with the step-dependent scalars read from device memory: hyper = {lr, beta1, beta2, eps, weight_decay,
+// 1 - beta1^step, sqrt(1 - beta2^step)}, and the tensor table passed BY VALUE in the kernel parameters.  Nothing that changes
+// from step to step is a kernel argument and no host buffer is read at run time, so the launches can sit in a CUDA graph that
+// is replayed every step while the host refreshes `hyper` with a stream-ordered copy in front of each replay.
+constexpr int ADAMW_ROWS = 96;                       // 96 x 40 B = 3840 B of kernel parameters
+struct AdamwRows { unsigned long long w[ADAMW_ROWS * 5]; };
+
+__global__ void adamw_multi_dev_kernel(const __grid_constant__ AdamwRows rows, const float* __restrict__ hyper) {
+  const unsigned long long* e = rows.w + (size_t)blockIdx.y * 5;
+  float* __restrict__ p = reinterpret_cast<float*>(e[0]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(e[1]);
+  float* __restrict__ m = reinterpret_cast<float*>(e[2]);
+  float* __restrict__ v = reinterpret_cast<float*>(e[3]);
+  const int64_t n = (int64_t)e[4];
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2_sqrt = hyper[6];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i] * (1.0f - lr * wd);
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
 }  // namespace zs
 
 using namespace zs;
+
+extern "C" int zs_adamw_multi_dev_f32(const void* host_table, int n_tensors, const float* hyper, void* stream) {
+  ZS_REQUIRE(host_table && hyper && n_tensors >= 0, "zs_adamw_multi_dev_f32: bad args");
+  const unsigned long long* t = reinterpret_cast<const unsigned long long*>(host_table);
+  for (int first = 0; first < n_tensors; first += ADAMW_ROWS) {
+    const int n = n_tensors - first < ADAMW_ROWS ? n_tensors - first : ADAMW_ROWS;
+    AdamwRows rows;
+    memcpy(rows.w, t + (size_t)first * 5, sizeof(unsigned long long) * 5 * n);
+    adamw_multi_dev_kernel<<<dim3(48, n), 256, 0, as_stream(stream)>>>(rows, hyper);
+    ZS_CUDA_CHECK_LAUNCH("zs_adamw_multi_dev_f32");
+  }
+  return ZS_OK;
+}
 
 extern "C" int zs_adamw_multi_f32(const void* table, int n_tensors, float lr, float beta1, float beta2, float eps, float weight_decay,
                                   int step, void* stream) {

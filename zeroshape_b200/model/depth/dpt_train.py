@@ -76,6 +76,16 @@ def _ws_ohwi_fn(w, eps=1e-8):
     return ((wf - mean) / torch.sqrt(var + eps)).reshape(w.shape).permute(0, 2, 3, 1)
 
 
+def _inv3x3(m):
+    """Inverse of a batch of 3x3 matrices by the adjugate (rows r0, r1, r2: columns r1 x r2, r2 x r0, r0 x r1 over the determinant).
+    Elementwise torch ops only: torch.linalg.inv reads its LU status back on the host, which stalls the step and cannot be
+    captured in a CUDA graph."""
+    r0, r1, r2 = m[:, 0], m[:, 1], m[:, 2]
+    c0, c1, c2 = torch.linalg.cross(r1, r2), torch.linalg.cross(r2, r0), torch.linalg.cross(r0, r1)
+    det = (r0 * c0).sum(-1)
+    return torch.stack([c0, c1, c2], dim=2) / det.view(-1, 1, 1)
+
+
 def _same_pad(i, k, s):
     return max((math.ceil(i / s) - 1) * s + (k - 1) + 1 - i, 0)
 
@@ -408,7 +418,7 @@ def encoder_forward(graph, opt, rgb, mask, with_intr=True, with_coord=True):
         dd, dkinv = ops.unproject_normalize_bwd(depth, mask, K, seen, scale, dseen)
         tp.add(depth_nhwc, dd.view(depth_nhwc.shape))
         # K^-1 -> K -> the three intrinsics parameters (graph_shape.py:98-112): 3x3 / 3-vector algebra per image (host glue)
-        kinv = torch.linalg.inv(K)
+        kinv = _inv3x3(K)
         dK = -(kinv.transpose(1, 2) @ dkinv @ kinv.transpose(1, 2))
         t = torch.tanh(params)
         dt = 1.0 - t * t
@@ -453,6 +463,7 @@ class EncoderTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, graph, opt, rgb, mask, *params):
+        ctx.set_materialize_grads(False)      # an output no loss uses arrives as None: no zero tensors, no host test for "all zero"
         with torch.no_grad():
             tp, out = encoder_forward(graph, opt, rgb, mask)
         ctx.tp, ctx.out, ctx.params = tp, out, params
@@ -473,10 +484,12 @@ class EncoderTrainFn(torch.autograd.Function):
 
 
 def _seed_depth_and_seen(tp, out, ddepth, dseen):
-    """Gradients arriving at depth_pred (MiDaS depth loss) and at the normalised seen surface (intrinsics loss)."""
-    if dseen is not None and out["seen"] is not None and bool((dseen != 0).any()):
+    """Gradients arriving at depth_pred (MiDaS depth loss) and at the normalised seen surface (intrinsics loss); None (the
+    Functions do not materialise the gradients of unused outputs) when no loss uses the output.  No host synchronisation:
+    the whole step stays stream-ordered (and can be captured in a CUDA graph, zeroshape_b200/graphed.py)."""
+    if dseen is not None and out["seen"] is not None:
         tp.add(out["seen"], dseen)
-    if ddepth is not None and bool((ddepth != 0).any()):
+    if ddepth is not None:
         tp.add(out["depth_nhwc"], ddepth.contiguous().view(out["depth_nhwc"].shape))      # [B,1,H,W] and [B,H,W,1] share the memory order
 
 
@@ -486,6 +499,7 @@ class DepthGraphTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, graph, opt, rgb, mask, with_intr, *params):
+        ctx.set_materialize_grads(False)
         with torch.no_grad():
             tp, out = encoder_forward(graph, opt, rgb, mask, with_intr=with_intr, with_coord=False)
         ctx.tp, ctx.out, ctx.params, ctx.with_intr = tp, out, params, with_intr

@@ -249,10 +249,40 @@ class FusedAdamW(torch.optim.Optimizer):
     A real `torch.optim.Optimizer`: `param_groups` (per-group lr / betas / eps / weight_decay, so CosineAnnealingLR and the
     reference's group construction work), per-parameter `state` {step, exp_avg, exp_avg_sq} (a parameter whose gradient is
     None in early steps gets its own bias correction), `state_dict` / `load_state_dict` (util.save_checkpoint serialises every
-    `optim*` attribute).  One launch per (group, step count) bucket."""
+    `optim*` attribute).  One launch per (group, step count) bucket.
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    `capturable=True`: the step-dependent scalars (lr, bias corrections) live in device memory and the tensor table travels in
+    the kernel parameters (zs_adamw_multi_dev_f32), so `step()` can be captured in a CUDA graph (zeroshape_b200/graphed.py).
+    Under capture `step()` records the launches without advancing the host-side step counters; every replay is preceded by
+    `prepare_replay()` (counters + 1, scalars refreshed with a stream-ordered copy) and followed by `mark_updated()`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.capturable = bool(capturable)
+        self._hyper = {}          # (group index, bucket ordinal) -> device tensor [8]
+        self._captured = []       # [(group, [params], hyper tensor)] of the captured step
+
+    @staticmethod
+    def _hyper_values(group, step):
+        import numpy as np
+        b1, b2 = np.float32(group["betas"][0]), np.float32(group["betas"][1])
+        bc1 = np.float32(1.0) - np.power(b1, np.float32(step))
+        bc2 = np.sqrt(np.float32(1.0) - np.power(b2, np.float32(step)))
+        return torch.tensor([float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                             float(bc1), float(bc2), 0.0], dtype=torch.float32)
+
+    def _hyper_buf(self, key, device):
+        if key not in self._hyper:
+            self._hyper[key] = torch.zeros(8, device=device, dtype=torch.float32)
+        return self._hyper[key]
+
+    def _ensure_state(self, p):
+        st = self.state[p]
+        if not st:
+            st["step"] = 0
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -260,25 +290,56 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        capturing = self.capturable and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if capturing:
+            self._captured = []
+        for gi, group in enumerate(self.param_groups):
             buckets = {}
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] = int(st["step"]) + 1
-                buckets.setdefault(st["step"], []).append(p)
-            for step, ps in buckets.items():
+                st = self._ensure_state(p)
+                if not capturing:
+                    st["step"] = int(st["step"]) + 1
+                buckets.setdefault(int(st["step"]) + (1 if capturing else 0), []).append(p)
+            for k, (step, ps) in enumerate(buckets.items()):
                 grads = [p.grad.contiguous() for p in ps]             # kept alive until the launch is enqueued
-                ops.adamw_step_multi([p.detach() for p in ps], grads, [self.state[p]["exp_avg"] for p in ps],
-                                     [self.state[p]["exp_avg_sq"] for p in ps], float(group["lr"]), group["betas"][0],
-                                     group["betas"][1], group["eps"], group["weight_decay"], step)
-                for p in ps:
-                    # the kernel wrote through the raw pointer: bump the version counter so that the packed-weight caches
-                    # (keyed on data_ptr / _version) re-pack, exactly as after a torch optimizer step
-                    torch.autograd.graph.increment_version(p)
+                if self.capturable:
+                    hyper = self._hyper_buf((gi, k), ps[0].device)
+                    if capturing:
+                        # (a non-contiguous gradient would be copied into a buffer of the graph's pool: fine, it is re-made per replay)
+                        self._captured.append((group, ps, hyper))
+                    else:
+                        # pageable source: staged by the runtime before the call returns, ordered on the stream, no synchronisation
+                        hyper.copy_(self._hyper_values(group, step), non_blocking=True)
+                    ops.adamw_step_multi_dev([p.detach() for p in ps], grads, [self.state[p]["exp_avg"] for p in ps],
+                                             [self.state[p]["exp_avg_sq"] for p in ps], hyper)
+                else:
+                    ops.adamw_step_multi([p.detach() for p in ps], grads, [self.state[p]["exp_avg"] for p in ps],
+                                         [self.state[p]["exp_avg_sq"] for p in ps], float(group["lr"]), group["betas"][0],
+                                         group["betas"][1], group["eps"], group["weight_decay"], step)
+                if not capturing:
+                    for p in ps:
+                        # the kernel wrote through the raw pointer: bump the version counter so that the packed-weight caches
+                        # (keyed on data_ptr / _version) re-pack, exactly as after a torch optimizer step
+                        torch.autograd.graph.increment_version(p)
         return loss
+
+    def prepare_replay(self):
+        """Before each replay of a graph that holds a captured `step()`: advance the step counters of the captured parameters
+        and refresh their device-side scalars (current group lr, bias corrections)."""
+        if not self._captured:
+            raise RuntimeError("FusedAdamW.prepare_replay: no captured step (construct with capturable=True and capture step())")
+        for group, ps, hyper in self._captured:
+            step = None
+            for p in ps:
+                st = self.state[p]
+                st["step"] = int(st["step"]) + 1
+                step = st["step"]
+            hyper.copy_(self._hyper_values(group, step), non_blocking=True)
+
+    def mark_updated(self):
+        """After a replay: the parameters changed behind autograd's back -> bump their version counters (packed-weight caches)."""
+        for _, ps, _ in self._captured:
+            for p in ps:
+                torch.autograd.graph.increment_version(p)

@@ -953,6 +953,24 @@ def adamw_step_multi(params, grads, exp_avgs, exp_avg_sqs, lr, beta1, beta2, eps
     check(lib.zs_adamw_multi_f32(_p(table), len(rows), lr, beta1, beta2, eps, weight_decay, step, _stream()), "zs_adamw_multi_f32")
 
 
+def adamw_step_multi_dev(params, grads, exp_avgs, exp_avg_sqs, hyper):
+    """The same launch with the step-dependent scalars in device memory (`hyper` = 7 fp32: lr, beta1, beta2, eps, weight decay,
+    1 - beta1^step, sqrt(1 - beta2^step)) and the tensor table passed by value: capturable in a CUDA graph (zs_adamw_multi_dev_f32)."""
+    import ctypes
+    flat = []
+    for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
+        for t, n in ((p, "param"), (g, "grad"), (m, "exp_avg"), (v, "exp_avg_sq")):
+            _chk(t, n)
+        flat += [p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()]
+    if not flat:
+        return
+    _chk(hyper, "hyper")
+    if hyper.numel() < 7:
+        raise ValueError("adamw_step_multi_dev: hyper holds 7 fp32 values")
+    table = (ctypes.c_uint64 * len(flat))(*flat)
+    check(lib.zs_adamw_multi_dev_f32(ctypes.cast(table, ctypes.c_void_p), len(flat) // 5, _p(hyper), _stream()), "zs_adamw_multi_dev_f32")
+
+
 def conv2d_nhwc_dgrad(dy, w_ohwi, in_shape, stride, pad, tc=None):
     """dx [B,H,W,Cin] of conv2d_nhwc given dy [B,OH,OW,Cout]; w_ohwi [Cout,KH,KW,Cin]; pad = (top, bottom, left, right)."""
     _chk(dy, "dy"); _chk(w_ohwi, "w")
