@@ -565,3 +565,44 @@ def test_graphed_training_step_matches_eager(cuda):
     for tag, gr_ in (("eager", graph_e), ("graphed", graph_g)):
         bad = [n for n, p in gr_.named_parameters() if not torch.isfinite(p).all()]
         assert not bad, (tag, bad[:8])
+
+
+@pytest.mark.parametrize("cfg", [(2, 14, 14, 8, 28, 28, True), (1, 7, 9, 12, 14, 18, True), (2, 24, 24, 8, 14, 14, False),
+                                 (1, 5, 6, 3, 10, 12, True), (1, 13, 11, 4, 29, 23, False), (2, 1, 1, 4, 4, 4, True)])
+def test_bilinear_forward_backward(cuda, cfg):
+    """F.interpolate(mode="bilinear") of the DPT fusion blocks / head (blocks.py: scale_factor 2, align_corners True) forward and
+    backward: the 128-bit kernels (C % 4 == 0; backward as a gather, no atomics) and the scalar ones (C = 3) against torch autograd."""
+    from zeroshape_b200 import ops
+    B, H, W, C, OH, OW, align = cfg
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(B, C, OH, OW, generator=g, dtype=torch.float64)
+    y = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=align)
+    y.backward(dy)
+    xh = x.detach().float().permute(0, 2, 3, 1).contiguous().to(cuda)
+    dyh = dy.float().permute(0, 2, 3, 1).contiguous().to(cuda)
+    yo = ops.bilinear_nhwc(xh, OH, OW, align).permute(0, 3, 1, 2).cpu().double()
+    dxo = ops.bilinear_bwd_nhwc(dyh, H, W, align).permute(0, 3, 1, 2).cpu().double()
+    assert (yo - y.detach()).abs().max() < 2e-6 * max(1.0, y.detach().abs().max().item())
+    assert (dxo - x.grad).abs().max() < 2e-6 * max(1.0, x.grad.abs().max().item()), (dxo - x.grad).abs().max()
+
+
+@pytest.mark.parametrize("cfg", [(2, 32, 32, 3, 64, 7, 3), (1, 37, 29, 3, 32, 7, 3), (2, 18, 20, 4, 16, 3, 1), (1, 224, 224, 3, 64, 7, 3)])
+def test_stem_dgrad_stride2(cuda, cfg):
+    """Data gradient of the stride-2 stem convolutions (CoordEncRes conv1: 7x7, XYZ in, 64 out; seen_coord_enc.py:148 /
+    torchvision resnet50.conv1) on the tiled kernel, against torch autograd; odd sizes exercise partial tiles."""
+    from zeroshape_b200 import ops
+    B, H, W, Cin, Cout, K, pad = cfg
+    g = torch.Generator().manual_seed(H + W + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cout, Cin, K, K, generator=g, dtype=torch.float64) * 0.1
+    y = F.conv2d(x, w, stride=2, padding=pad)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    dyh = dy.float().permute(0, 2, 3, 1).contiguous().to(cuda)
+    w_ohwi = w.float().permute(0, 2, 3, 1).contiguous().to(cuda)
+    OH, OW = y.shape[2], y.shape[3]
+    pb, pr = (OH - 1) * 2 + K - H - pad, (OW - 1) * 2 + K - W - pad
+    dx = ops.conv2d_nhwc_dgrad(dyh, w_ohwi, (B, H, W, Cin), 2, (pad, max(pb, 0), pad, max(pr, 0)), tc=False)
+    err = (dx.permute(0, 3, 1, 2).cpu().double() - x.grad).abs().max().item()
+    assert err < 2e-5 * max(1.0, x.grad.abs().max().item()), err

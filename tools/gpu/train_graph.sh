@@ -1,7 +1,7 @@
 # Training step as one CUDA graph: the parity tests, then BASELINE config 3 launched op by op and replayed from the graph.
 #   /usr/local/graft/bin/gpurun --timeout 900 -- "bash tools/gpu/train_graph.sh"
 set -x
-timeout 600 python -m pytest tests/test_gpu_train.py -x -q -m gpu -k "adamw_capturable or graphed_training or full_graph_training or kernels_match" -s 2>&1 | tail -15
+timeout 700 python -m pytest tests/test_gpu_train.py tests/test_gpu_train_tc.py tests/test_gpu_ops.py -x -q -m gpu 2>&1 | tail -8
 timeout 300 python bench.py --mode train --steps 10 --warmup 3 --train-graph 0 > gpurun_out/train32_eager.json 2> gpurun_out/train32_eager.err; echo "eager rc $?"
 timeout 300 python bench.py --mode train --steps 10 --warmup 3 --train-graph 1 > gpurun_out/train32_graph.json 2> gpurun_out/train32_graph.err; echo "graph rc $?"
 python - <<'PY'

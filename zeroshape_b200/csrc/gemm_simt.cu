@@ -414,6 +414,76 @@ __global__ void __launch_bounds__(256) conv_dgrad_smallcin_kernel(const float* _
   if (lane < Cin) dx[pix * Cin + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
 }
 
+// The stride-2 stem (7x7, Cin = 3, Cout = 64 at 224 x 224: 1.6 M input pixels per batch of 32) one 16 x 16 tile of input pixels per
+// CTA.  The dy patch the tile touches ((16 + KH) / 2 + 1 rows and columns, zero outside the image, rows padded to Cout + 4 floats
+// against bank conflicts) and the whole filter sit in shared memory.  The pixels of a warp share their parity (ih & 1, iw & 1),
+// so the taps that reach them -- kh = (ih + pad) & 1, +2, ... -- are the same for the whole warp: the filter reads are
+// broadcasts, the dy reads hit 32 different rows, and the inner loop has no bounds test and no reduction across lanes.
+constexpr int DG2_TILE = 16;
+constexpr int DG2_MAXK = 7;
+constexpr int DG2_OD = DG2_TILE / 2 + (DG2_MAXK + 1) / 2 + 1;      // 13
+
+__device__ __forceinline__ int floor_div2(int a) { return a >= 0 ? a / 2 : -((1 - a) / 2); }
+
+__global__ void __launch_bounds__(256) conv_dgrad_stem_s2_kernel(const float* __restrict__ dy, const float* __restrict__ wd,
+                                                                 float* __restrict__ dx, int B, int H, int W, int Cin, int Cout, int KH,
+                                                                 int KW, int pad_top, int pad_left, int OH, int OW) {
+  extern __shared__ __align__(16) float dg_smem[];
+  const int ldy = Cout + 4;                                        // floats per dy pixel in shared memory
+  float* sdy = dg_smem;                                            // [DG2_OD][DG2_OD][ldy]
+  float* sw = dg_smem + DG2_OD * DG2_OD * ldy;                     // [Cin][KH * KW][Cout]
+  const int tiles_w = (W + DG2_TILE - 1) / DG2_TILE, tiles_h = (H + DG2_TILE - 1) / DG2_TILE;
+  const int tw = blockIdx.x % tiles_w, th = (blockIdx.x / tiles_w) % tiles_h, b = blockIdx.x / (tiles_w * tiles_h);
+  const int ih0 = th * DG2_TILE, iw0 = tw * DG2_TILE;
+  const int oh0 = floor_div2(ih0 + pad_top - (KH - 1)), ow0 = floor_div2(iw0 + pad_left - (KW - 1));
+  const int c4 = Cout / 4, taps = KH * KW;
+  for (int i = threadIdx.x; i < DG2_OD * DG2_OD * c4; i += 256) {
+    const int q = i % c4, px = i / c4;
+    const int oh = oh0 + px / DG2_OD, ow = ow0 + px % DG2_OD;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (oh >= 0 && oh < OH && ow >= 0 && ow < OW) v = __ldg(reinterpret_cast<const float4*>(dy + (((int64_t)b * OH + oh) * OW + ow) * Cout) + q);
+    *reinterpret_cast<float4*>(sdy + px * ldy + q * 4) = v;
+  }
+  for (int i = threadIdx.x; i < Cin * taps * c4; i += 256)
+    *reinterpret_cast<float4*>(sw + i * 4) = __ldg(reinterpret_cast<const float4*>(wd) + i);
+  __syncthreads();
+  // 4 parity classes x 64 pixels: warps 2c, 2c + 1 own class c = (py, px)
+  const int cls = threadIdx.x >> 6, j = threadIdx.x & 63;
+  const int py = cls >> 1, px_ = cls & 1;
+  const int ih = ih0 + 2 * (j >> 3) + py, iw = iw0 + 2 * (j & 7) + px_;
+  float acc[4][4];
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[ci][e] = 0.f;
+  for (int kh = (ih + pad_top) & 1; kh < KH; kh += 2) {
+    const int r = (ih + pad_top - kh) / 2 - oh0;                   // exact: the numerator is even
+    for (int kw = (iw + pad_left) & 1; kw < KW; kw += 2) {
+      const int c = (iw + pad_left - kw) / 2 - ow0;
+      const float4* g = reinterpret_cast<const float4*>(sdy + (r * DG2_OD + c) * ldy);
+      const float4* wk = reinterpret_cast<const float4*>(sw + (kh * KW + kw) * Cout);
+      for (int q = 0; q < c4; ++q) {
+        const float4 gv = g[q];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci < Cin) {
+            const float4 wv = wk[ci * taps * c4 + q];
+            acc[ci][0] = fmaf(gv.x, wv.x, acc[ci][0]);
+            acc[ci][1] = fmaf(gv.y, wv.y, acc[ci][1]);
+            acc[ci][2] = fmaf(gv.z, wv.z, acc[ci][2]);
+            acc[ci][3] = fmaf(gv.w, wv.w, acc[ci][3]);
+          }
+      }
+    }
+  }
+  if (ih < H && iw < W) {
+    float* o = dx + (((int64_t)b * H + ih) * W + iw) * Cin;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+      if (ci < Cin) o[ci] = (acc[ci][0] + acc[ci][1]) + (acc[ci][2] + acc[ci][3]);
+  }
+}
+
 }  // namespace zs
 
 extern "C" int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, int Cin, const float* w_dgrad, float* dx, int Cout,
@@ -426,6 +496,20 @@ extern "C" int zs_conv2d_nhwc_dgrad_f32(const float* dy, int B, int H, int W, in
   const int64_t M64 = (int64_t)B * H * W;
   ZS_REQUIRE(M64 < (1LL << 31), "zs_conv2d_nhwc_dgrad_f32: too many pixels");
   const int M = (int)M64, K = KH * KW * Cout;
+  if (Cin <= 4 && stride == 2 && KH <= DG2_MAXK && KW <= DG2_MAXK && Cout <= 64 && (reinterpret_cast<uintptr_t>(w_dgrad) & 15) == 0) {
+    const size_t smem = sizeof(float) * ((size_t)DG2_OD * DG2_OD * (Cout + 4) + (size_t)Cin * KH * KW * Cout);
+    static bool attr_set = false;
+    if (!attr_set) {
+      ZS_CUDA_CALL(cudaFuncSetAttribute(conv_dgrad_stem_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set = true;
+    }
+    const int64_t blocks = (int64_t)B * ((H + DG2_TILE - 1) / DG2_TILE) * ((W + DG2_TILE - 1) / DG2_TILE);
+    ZS_REQUIRE(smem <= 100 * 1024 && blocks < (1LL << 31), "zs_conv2d_nhwc_dgrad_f32: stem tile does not fit");
+    conv_dgrad_stem_s2_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(dy, w_dgrad, dx, B, H, W, Cin, Cout, KH, KW, pad_top,
+                                                                                 pad_left, OH, OW);
+    ZS_CUDA_CHECK_LAUNCH("zs_conv2d_nhwc_dgrad_f32(stride-2 stem)");
+    return ZS_OK;
+  }
   if (Cin <= 4) {
     conv_dgrad_smallcin_kernel<<<(unsigned)((M64 + 7) / 8), 256, 0, as_stream(stream)>>>(dy, w_dgrad, dx, B, H, W, Cin, Cout, KH, KW, stride,
                                                                                        pad_top, pad_left, OH, OW);

@@ -668,6 +668,59 @@ __global__ void bilinear_bwd_nhwc_kernel(const float* __restrict__ dy, float* __
   }
 }
 
+// The same gradient as a GATHER, four channels per thread: every input pixel (h, w) sums the output pixels whose two taps include
+// it, found by running the forward's own source-index function over the few candidate rows / columns (an input row h is touched
+// by the outputs whose source coordinate lies in (h - 1, h + 1): ~2 x the scale factor of them).  No zero fill, no atomics,
+// deterministic; 128-bit loads of dy that stay in L1 / L2 across neighbouring pixels.
+__device__ __forceinline__ void bilinear_dst_range(int i, int in, int out, int align, int& lo, int& hi) {
+  if (in == 1 || out == 1) { lo = 0; hi = out - 1; return; }
+  float a, b;                                             // destination coordinates of the sources i - 1 and i + 1
+  if (align) {
+    const float inv = (float)(out - 1) / (float)(in - 1);
+    a = (i - 1) * inv; b = (i + 1) * inv;
+  } else {
+    const float inv = (float)out / (float)in;
+    a = (i - 0.5f) * inv - 0.5f; b = (i + 1.5f) * inv - 0.5f;
+  }
+  lo = (int)floorf(a) - 1; hi = (int)ceilf(b) + 1;        // one spare candidate on either side: its weight comes out as 0
+  if (i == 0 || lo < 0) lo = 0;                           // (sources clamped to 0 / in - 1 land on the border rows)
+  if (i == in - 1 || hi > out - 1) hi = out - 1;
+}
+
+__global__ void bilinear_bwd_gather_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int B, int H, int W, int C4,
+                                              int OH, int OW, int align) {
+  const int64_t total = (int64_t)B * H * W * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    const int pix = (int)(i / C4);
+    const int w = pix % W, t = pix / W;
+    const int h = t % H, b = t / H;
+    int oh_lo, oh_hi, ow_lo, ow_hi;
+    bilinear_dst_range(h, H, OH, align, oh_lo, oh_hi);
+    bilinear_dst_range(w, W, OW, align, ow_lo, ow_hi);
+    const float4* g = dy + (int64_t)b * OH * OW * C4 + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      int h0, h1;
+      float lh;
+      bilinear_src_t(oh, H, OH, align, h0, h1, lh);
+      const float wh = (h0 == h ? 1.f - lh : 0.f) + (h1 == h ? lh : 0.f);
+      if (wh == 0.f) continue;
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        int w0, w1;
+        float lw;
+        bilinear_src_t(ow, W, OW, align, w0, w1, lw);
+        const float ww = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+        if (ww == 0.f) continue;
+        const float4 v = __ldg(g + ((int64_t)oh * OW + ow) * C4);
+        const float k = wh * ww;
+        acc.x = fmaf(v.x, k, acc.x); acc.y = fmaf(v.y, k, acc.y); acc.z = fmaf(v.z, k, acc.z); acc.w = fmaf(v.w, k, acc.w);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // ---- unproject + normalise backward (utils/camera.py:52-108, graph_shape.py:132-141) ------------------------------
 // out_i = (X_i - m) / s for valid pixels, X_i = d_i * r_i, r_i = Kinv (u, v, 1)^T, m = mean_valid X, s = max_valid |X - m|.
 // Given g_i = dL/dout_i:  dL/dX_i = g_i / s + [i == j] * ds * n_j + dm / N,   ds = -sum_i g_i . out_i / s,  n_j = out_j,
@@ -1065,6 +1118,13 @@ extern "C" int zs_bilinear_bwd_nhwc_f32(const float* dy, float* dx, int B, int H
                                         void* stream) {
   ZS_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_bilinear_bwd_nhwc_f32: bad args");
   cudaStream_t st = as_stream(stream);
+  if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (int64_t)B * H * W < (1LL << 31) &&
+      (int64_t)B * OH * OW < (1LL << 31)) {
+    bilinear_bwd_gather_v4_kernel<<<grid_for_n((int64_t)B * H * W * (C / 4)), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), B, H, W, C / 4, OH, OW, align_corners);
+    ZS_CUDA_CHECK_LAUNCH("zs_bilinear_bwd_nhwc_f32");
+    return ZS_OK;
+  }
   ZS_CUDA_CALL(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * H * W * C, st));
   bilinear_bwd_nhwc_kernel<<<grid_for_n((int64_t)B * OH * OW * C), 256, 0, st>>>(dy, dx, B, H, W, C, OH, OW, align_corners);
   ZS_CUDA_CHECK_LAUNCH("zs_bilinear_bwd_nhwc_f32");
