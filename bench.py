@@ -951,7 +951,7 @@ def main():
                 torch.cuda.empty_cache()
                 return {k: r[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config", "gpu_launches", "clocks",
                                           "encoder_ms_per_batch", "decoder_points_per_s", "last_loss", "peak_memory_gb", "mean_cd",
-                                          "e2e", "roofline") if k in r and k != "roofline"} | (
+                                          "e2e", "roofline", "cuda_graph", "cuda_graph_error", "images_per_s") if k in r and k != "roofline"} | (
                     {"roofline_frac": r["roofline"]["frac"]} if "roofline" in r else {})
             except Exception as e:                   # noqa: BLE001
                 return {"error": repr(e)[:300]}
