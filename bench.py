@@ -150,7 +150,11 @@ def run_ours(args, rank, world, dev):
         if record:
             ee1.record()
             enc_events.append((ee0, ee1))
-        clouds = []
+        clouds, pending = [], None
+
+        def finish(fut, s):
+            v, f = fut.result()
+            clouds.append(ops.mesh_sample(v, f, 10000, (rmax - rmin) / n, rmin, seed=s))
         for s in range(B):
             l1 = var.latent_depth[s:s + 1]
             prep = net.prepare_latents(l1)
@@ -161,8 +165,13 @@ def run_ours(args, rank, world, dev):
             if record:
                 e1.record()
                 dec_events.append((e0, e1))
-            v, f = ops.marching_cubes(occ[0], 0.5)
-            clouds.append(ops.mesh_sample(v, f, 10000, (rmax - rmin) / n, rmin, seed=s))
+            # marching cubes pass 1 + async read-back of the mesh sizes now; the mesh itself once the NEXT shape's decoder is
+            # queued, so the host never drains the stream (ops.MeshFuture)
+            fut = ops.MeshFuture(occ[0], 0.5)
+            if pending is not None:
+                finish(*pending)
+            pending = (fut, s)
+        finish(*pending)
         return torch.stack(clouds)
 
     def barrier():

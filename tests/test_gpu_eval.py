@@ -35,6 +35,23 @@ def test_marching_cubes_matches_oracle_exactly(cuda, kind, n):
     np.testing.assert_allclose(v.cpu().numpy(), v_ref.astype(np.float32), rtol=0, atol=1e-5)
 
 
+def test_mesh_future_defers_the_size_readback(cuda):
+    """ops.MeshFuture: pass 1 + asynchronous size read-back at construction, pass 2 in result() -- the same mesh as
+    ops.marching_cubes, also with other work queued in between and several futures in flight."""
+    from zeroshape_b200 import ops
+    vols = [torch.from_numpy(_field(k, n)).to(cuda) for k, n in (("sphere", 33), ("torus", 41), ("sphere", 17))]
+    futures = [ops.MeshFuture(v, 0.0) for v in vols]
+    filler = torch.randn(2048, 2048, device=cuda)
+    for _ in range(4):
+        filler = filler @ filler * 1e-3                      # the "next decoder" queued between the two passes
+    for fut, vol in zip(futures, vols):
+        v, f = fut.result()
+        v0, f0 = ops.marching_cubes(vol, 0.0)
+        assert torch.equal(v, v0) and torch.equal(f, f0)
+    v, f = ops.MeshFuture(torch.full((9, 9, 9), 1.0, device=cuda), 0.0).result()
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+
+
 def test_marching_cubes_empty_and_full(cuda):
     from zeroshape_b200 import ops
     for val in (-1.0, 1.0):

@@ -679,11 +679,31 @@ def marching_cubes_emit(vol, iso, ws, V, F, x_offset=0):
     return verts, faces
 
 
+class MeshFuture:
+    """Marching cubes with the size read-back taken off the critical path: pass 1 (classify + scans) and an asynchronous copy of
+    the two counts to pinned host memory are queued at construction; `result()` waits for THAT copy only (an event, not the
+    stream), allocates the outputs and queues pass 2.  Work queued between the two calls -- the next shape's decoder -- keeps
+    the GPU busy while the host learns the sizes."""
+
+    def __init__(self, vol, iso, x_offset=0):
+        self.vol, self.iso, self.x_offset = vol, iso, x_offset
+        self.ws, counts = marching_cubes_count(vol, iso)
+        self.host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        self.host.copy_(counts, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def result(self):
+        self.event.synchronize()
+        V, F = self.host.tolist()
+        return marching_cubes_emit(self.vol, self.iso, self.ws, V, F, self.x_offset)
+
+
 def marching_cubes(vol, iso, x_offset=0):
     """vol [n,n,n] (or an x-slab [nx,n,n] whose first slice is global slice `x_offset`) fp32 CUDA ->
     (verts [V,3] fp32 in index units, faces [F,3] int32), both on device."""
     ws, counts = marching_cubes_count(vol, iso)
-    V, F = counts.tolist()   # the one host sync of the mesh path (sizes of the outputs)
+    V, F = counts.tolist()   # the one host sync of the mesh path (sizes of the outputs); MeshFuture defers it
     return marching_cubes_emit(vol, iso, ws, V, F, x_offset)
 
 

@@ -186,13 +186,14 @@ def convert_to_explicit(opt, level_grids, isoval=0., to_pointcloud=False, seed=0
     -> meshes (and [B, num_points, 3] numpy point clouds).  GPU marching cubes; vertices scaled with
     the reference's `v / S * (max-min) + min`, S = n (utils/eval_3D.py:252-255)."""
     rmin, rmax = opt.eval.range
-    meshes, clouds = [], []
-    for i, vol in enumerate(level_grids):
+    meshes, clouds, futures = [], [], []
+    for vol in level_grids:                      # pass 1 of every grid first: ONE wait for the sizes of the whole batch
         if not isinstance(vol, torch.Tensor):
             vol = torch.from_numpy(np.ascontiguousarray(vol, dtype=np.float32)).to(opt.device)
-        vol = vol.float().contiguous()
-        S = vol.shape[0]
-        v, f = ops.marching_cubes(vol, isoval)
+        futures.append(ops.MeshFuture(vol.float().contiguous(), isoval))
+    for i, fut in enumerate(futures):
+        S = fut.vol.shape[0]
+        v, f = fut.result()
         mesh = Mesh(v, f, (rmax - rmin) / S, rmin)
         meshes.append(mesh)
         if to_pointcloud:
@@ -243,8 +244,9 @@ def _predict_clouds(opt, var, impl_network, seed=0, vis_attn=False):
     # itself regenerates its points per slab and never reads this tensor)
     var.eval_vox = get_dense_3D_grid(opt, var).view(B, -1, 3)
     meshes, clouds = [], []
+    futures = [ops.MeshFuture(level_vox[b].contiguous(), 0.5) for b in range(B)]
     for b in range(B):
-        v, f = ops.marching_cubes(level_vox[b].contiguous(), 0.5)
+        v, f = futures[b].result()
         mesh = Mesh(v, f, (rmax - rmin) / points_n, rmin)
         meshes.append(mesh)
         clouds.append(mesh.sample(opt.eval.num_points, seed=seed + b, device_out=True))
