@@ -97,3 +97,112 @@ def test_resnetv2_restatement_vs_transformers_bit():
     for a, b in zip(got, want):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() < 2e-4 * max(1.0, b.abs().max().item())
+
+
+def _hf_dpt_to_reference_names(hf_sd):
+    """transformers' DPT-hybrid parameter names -> the reference's (omnidata DPTDepthModel over timm vit_base_resnet50_384)
+    names, by the inverse of the public conversion rules (transformers/models/dpt/convert_dpt_hybrid_to_pytorch.py)."""
+    out, used = {}, set()
+
+    def take(src, dst):
+        out[dst] = hf_sd[src]
+        used.add(src)
+    take("dpt.embeddings.cls_token", "pretrained.model.cls_token")
+    take("dpt.embeddings.position_embeddings", "pretrained.model.pos_embed")
+    for s in ("weight", "bias"):
+        take(f"dpt.embeddings.projection.{s}", f"pretrained.model.patch_embed.proj.{s}")
+    bb = "dpt.embeddings.backbone."
+    for k in hf_sd:
+        if not k.startswith(bb) or "num_batches" in k:
+            continue
+        kk = k[len(bb):].replace("bit.embedder.convolution.", "stem.conv.").replace("bit.embedder.norm.", "stem.norm.")
+        kk = kk.replace("bit.encoder.stages.", "stages.").replace(".layers.", ".blocks.")
+        take(k, "pretrained.model.patch_embed.backbone." + kk)
+    for i in range(12):
+        a, b = f"dpt.encoder.layer.{i}.", f"pretrained.model.blocks.{i}."
+        for s in ("weight", "bias"):
+            take(f"{a}layernorm_before.{s}", f"{b}norm1.{s}")
+            take(f"{a}layernorm_after.{s}", f"{b}norm2.{s}")
+            out[f"{b}attn.qkv.{s}"] = torch.cat([hf_sd[f"{a}attention.attention.{n}.{s}"] for n in ("query", "key", "value")], dim=0)
+            used.update(f"{a}attention.attention.{n}.{s}" for n in ("query", "key", "value"))
+            take(f"{a}attention.output.dense.{s}", f"{b}attn.proj.{s}")
+            take(f"{a}intermediate.dense.{s}", f"{b}mlp.fc1.{s}")
+            take(f"{a}output.dense.{s}", f"{b}mlp.fc2.{s}")
+    for s in ("weight", "bias"):
+        for j, n in ((2, 3), (3, 4)):
+            take(f"neck.reassemble_stage.readout_projects.{j}.0.{s}", f"pretrained.act_postprocess{n}.0.project.0.{s}")
+            take(f"neck.reassemble_stage.layers.{j}.projection.{s}", f"pretrained.act_postprocess{n}.3.{s}")
+        take(f"neck.reassemble_stage.layers.3.resize.{s}", f"pretrained.act_postprocess4.4.{s}")
+    for i in range(4):
+        take(f"neck.convs.{i}.weight", f"scratch.layer{i + 1}_rn.weight")
+        a, b = f"neck.fusion_stage.layers.{i}.", f"scratch.refinenet{4 - i}."
+        for s in ("weight", "bias"):
+            take(f"{a}projection.{s}", f"{b}out_conv.{s}")
+            for u in (1, 2):
+                for c in (1, 2):
+                    take(f"{a}residual_layer{u}.convolution{c}.{s}", f"{b}resConfUnit{u}.conv{c}.{s}")
+    for s in ("weight", "bias"):
+        for j in (0, 2, 4):
+            take(f"head.head.{j}.{s}", f"scratch.output_conv.{j}.{s}")
+    return out, used
+
+
+def test_dpt_hybrid_restatement_vs_transformers_dpt():
+    """The whole depth estimator of SURVEY.md 8 rows a1-a4 -- timm's hybrid ViT (ResNetV2 stem + 12 blocks + resized position
+    embedding), ProjectReadout / reassemble, scratch convs, four fusion blocks and the depth head -- against
+    `transformers.DPTForDepthEstimation(is_hybrid=True)`: an independent public implementation of the same published network
+    (Intel/dpt-hybrid-midas, the checkpoint family omnidata's model derives from).  timm itself is absent from this image, so
+    this is the pin of the oracle's restatement of the third-party code (the ZeroShape-specific wrapper around it is pinned by
+    the golden vectors above).  Same weights in both (names mapped by the inverse of transformers' published conversion
+    rules), a 224 x 224 input with the 24 x 24 position embedding of the 384 model resized to 14 x 14 in both."""
+    pytest.importorskip("transformers")
+    from transformers import DPTConfig, DPTForDepthEstimation
+    cfg = DPTConfig(is_hybrid=True, image_size=384, patch_size=16, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                    intermediate_size=3072, hidden_act="gelu", qkv_bias=True, layer_norm_eps=BB.VIT_LN_EPS, readout_type="project",
+                    backbone_out_indices=[2, 5, 8, 11], neck_hidden_sizes=[256, 512, 768, 768], fusion_hidden_size=256,
+                    reassemble_factors=[1, 1, 1, 0.5], neck_ignore_stages=[0, 1], backbone_featmap_shape=[1, 1024, 24, 24],
+                    head_in_index=-1, use_batch_norm_in_fusion_residual=False, add_projection=False,
+                    hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    hf = DPTForDepthEstimation(cfg).eval()
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n, p in hf.named_parameters():                       # no zero-initialised tokens / biases, norms around 1
+            if p.dim() == 1 and ("norm" in n and n.endswith("weight")):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:
+                fan_in = p[0].numel() if p.dim() > 1 else 1
+                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / fan_in) ** 0.5)
+        hf.dpt.embeddings.position_embeddings.copy_(0.2 * torch.randn(hf.dpt.embeddings.position_embeddings.shape, generator=g))
+        hf.head.head[4].bias.fill_(0.45)                         # keeps the depth inside (0, 1): neither ReLU nor the clamp hides a difference
+    hf.dpt.embeddings.image_size = (224, 224)                     # the check only; the position embedding stays the 384 one
+    image = torch.rand(1, 3, 224, 224, generator=g)
+    with torch.no_grad():                                         # scale the last 1x1 conv so the depth spreads over ~0.45 +- 0.1
+        pre = {}
+        hook = hf.head.head[4].register_forward_hook(lambda m, i, o: pre.__setitem__("y", o))
+        hf(pixel_values=image * 2 - 1)
+        hook.remove()
+        hf.head.head[4].weight.mul_(0.1 / (pre["y"] - 0.45).std())
+    hf_sd = {k: v.detach() for k, v in hf.state_dict().items()}
+    sd, used = _hf_dpt_to_reference_names(hf_sd)
+    # every parameter the reference's depth estimator owns is covered, with the reference's shapes
+    shapes = {k[len("dpt_depth."):]: v for k, v in graph_shape_param_shapes().items() if k.startswith("dpt_depth.")}
+    unused_in_reference = ("pretrained.model.norm.", "pretrained.model.head.")            # timm's classifier head: never called
+    missing = [k for k in shapes if k not in sd and not k.startswith(unused_in_reference)]
+    assert not missing, missing[:5]
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes if k in sd)
+    leftover = [k for k in hf_sd if k not in used and "num_batches" not in k and not k.startswith(("dpt.layernorm.", "dpt.pooler."))]
+    assert not leftover, leftover[:5]
+    feats = {}
+    hook = hf.neck.reassemble_stage.layers[3].register_forward_hook(lambda m, i, o: feats.__setitem__("l4", o))
+    with torch.no_grad():
+        want = hf(pixel_values=image * 2 - 1).predicted_depth                               # dpt_depth.py:116 feeds image * 2 - 1
+        got, l4 = BB.dpt_depth_forward(sd, image)
+    hook.remove()
+    want = want.clamp(0, 1).view(got.shape)
+    assert 0.05 < want.min() and want.max() < 0.95 and want.std() > 1e-3, (want.min(), want.max(), want.std())   # informative
+    print("DPT-hybrid vs transformers: depth max abs diff", (got - want).abs().max().item(), "| layer_4 feature rel",
+          ((l4 - feats["l4"]).abs().max() / feats["l4"].abs().max()).item(), "| depth range", want.min().item(), want.max().item())
+    assert (l4 - feats["l4"]).abs().max().item() < 2e-4 * feats["l4"].abs().max().item()
+    assert (got - want).abs().max().item() < 2e-5, (got - want).abs().max().item()
