@@ -614,7 +614,7 @@ def run_train(args, rank, world, dev):
                        "train_precision": args.train_precision},
             "cuda_graph": use_graph, **({"cuda_graph_error": graph_note} if graph_note else {}),
             "trainable_parameters": int(sum(p.numel() for p in trainable)), "last_loss": last,
-            "gpu_launches": (args.steps * gstep.launches_per_replay if use_graph else int(lib.zs_launch_count() - l0)),
+            "gpu_launches": int(lib.zs_launch_count() - l0),        # replays add their recorded launches (zs_launch_count_add)
             "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
 
 

@@ -50,6 +50,9 @@ int zs_abi_version(void);
 int zs_device_cc(void);
 /* number of CUDA kernels this library has launched since it was loaded (all threads) */
 long long zs_launch_count(void);
+/* Adds n to that counter: a CUDA graph replays its launches without passing through these entry points; the owner of the graph
+ * adds the count recorded at capture once per replay. */
+void zs_launch_count_add(long long n);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense building blocks (replace the cuBLAS/cuDNN calls PyTorch issues for nn.Linear / nn.Conv2d /

@@ -193,3 +193,51 @@ def test_graph_with_transformer_encoder(cuda):
     assert _rel(var.latent_depth, want) < 1e-3, _rel(var.latent_depth, want)
     logits, _ = graph.impl_network(var.latent_depth, None, torch.rand(2, 50, 3, device=cuda) - 0.5, need_attn=False)
     assert logits.shape == (2, 50) and torch.isfinite(logits).all()
+
+
+def test_graphed_inference_encoder_equals_the_eager_one(cuda):
+    """Graph.forward in eval mode replays the image -> latents encoder from a CUDA graph (graph_shape.py `_encode_graphed`): the
+    same bits as launching it op by op, for new inputs through the same capture, for another batch size, and after a weight
+    update (the capture is keyed on the parameters' version counters and re-made)."""
+    from zeroshape_b200 import ops
+    from zeroshape_b200._native import lib
+    from zeroshape_b200.utils.util import EasyDict
+    sd = seeded_state_dict(graph_shape_param_shapes(), 41)
+    graph = _graph(sd, cuda)
+    opt = make_opt(cuda)
+
+    def run(rgb, mask, graphed):
+        ops.ENCODER_CUDA_GRAPH = graphed
+        try:
+            var = EasyDict(idx=torch.arange(rgb.shape[0]), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), pose_gt=False)
+            with torch.no_grad():
+                var = graph.forward(opt, var, training=False, get_loss=False)
+        finally:
+            ops.ENCODER_CUDA_GRAPH = True
+        return {k: var[k].clone() for k in ("depth_pred", "intr_pred", "seen_points", "latent_depth", "validity_mask")}
+
+    def same(a, b):
+        return all(torch.equal(a[k], b[k]) for k in a)
+    x1, x2, x3 = (synthetic_image_and_mask(1, 42), synthetic_image_and_mask(1, 43, 100, 120, 60), synthetic_image_and_mask(2, 44, 118, 106, 74))
+    e1, e2, e3 = run(*x1, False), run(*x2, False), run(*x3, False)
+    n0 = lib.zs_launch_count()
+    g1 = run(*x1, True)                                     # warm-up + capture + first replay
+    assert len(graph._encoder_graphs) == 1
+    n1 = lib.zs_launch_count()
+    g2 = run(*x2, True)                                     # replay only, new input
+    per_replay = lib.zs_launch_count() - n1
+    assert per_replay > 100 and len(graph._encoder_graphs) == 1, per_replay      # the replayed launches are accounted for
+    g3 = run(*x3, True)                                     # another batch size: its own capture
+    assert len(graph._encoder_graphs) == 2
+    assert same(e1, g1) and same(e2, g2) and same(e3, g3)
+    assert not torch.equal(g1["latent_depth"], g2["latent_depth"])
+    # weight update -> new capture, new (correct) numbers
+    with torch.no_grad():
+        graph.intr_proj.bias.add_(0.05)
+        dict(graph.dpt_depth.named_parameters())["scratch.output_conv.4.bias"].add_(0.01)
+    e4, g4 = run(*x1, False), run(*x1, True)
+    assert same(e4, g4) and not torch.equal(g4["depth_pred"], g1["depth_pred"])
+    # the outputs handed out are copies: a later replay does not overwrite them
+    keep = g4["latent_depth"].clone()
+    run(*x2, True)
+    assert torch.equal(keep, g4["latent_depth"])

@@ -19,6 +19,7 @@ SIGNATURES = {
     "zs_abi_version": (c_int, []),
     "zs_device_cc": (c_int, []),
     "zs_launch_count": (ctypes.c_longlong, []),
+    "zs_launch_count_add": (None, [ctypes.c_longlong]),
     "zs_gemm_f32": (c_int, [P, c_int, P, c_int, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_gemm_tc_packed_bytes": (c_size_t, [c_int, c_int]),
     "zs_gemm_tc_pack": (c_int, [P, c_int, c_int, c_int, P, P]),

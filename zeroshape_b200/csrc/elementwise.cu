@@ -279,6 +279,9 @@ using namespace zs;
 extern "C" const char* zs_last_error(void) { return zs::g_err; }
 extern "C" int zs_abi_version(void) { return 1; }
 extern "C" long long zs_launch_count(void) { return zs::g_launches.load(std::memory_order_relaxed); }
+// launches replayed from a CUDA graph never pass through the entry points: the graph owners (zeroshape_b200/graphed.py, the
+// graphed inference encoder) add the number of launches recorded at capture time once per replay
+extern "C" void zs_launch_count_add(long long n) { zs::g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" int zs_device_cc(void) {
   int dev = 0, maj = 0, min = 0;
   ZS_CUDA_CALL(cudaGetDevice(&dev));

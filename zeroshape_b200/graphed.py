@@ -42,6 +42,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from ._native import lib
+        self._lib = lib
         n0 = lib.zs_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):      # the stream of the warm-up: AccumulateGrad nodes keep theirs
@@ -59,6 +60,7 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.optim.prepare_replay()
         self.graph.replay()
+        self._lib.zs_launch_count_add(self.launches_per_replay)
         self.optim.mark_updated()
         self.replays += 1
         return self.loss

@@ -76,10 +76,79 @@ class Graph(nn.Module):
         """[B,3] -> [B,3,3] (graph_shape.py:89-113)."""
         return ops.intr_param2mtx(intr_params.float().contiguous(), opt.H, opt.W)
 
+    # ---- the inference encoder (image -> depth, intrinsics, seen surface, latents) replayed from a CUDA graph ----------------
+    # ~300 launches of 5-40 us of device time each: issued one by one from Python the HOST is the limiter (a floor of ~25 us
+    # per layer whatever its size, tools/diag_encoder_layers.py).  Everything on the path is stream-ordered, so the eval-mode
+    # forward of a given input shape is captured once and replayed; the capture is dropped whenever a parameter or buffer
+    # changes (version counters / storage), the precision policy changes, or an op timer is active.
+    def _encoder_signature(self):
+        sig = [ops.ENCODER_ENGINE, ops.ENCODER_PRECISION]
+        for m in (self.dpt_depth, self.intr_head, self.intr_proj, self.coord_encoder):
+            for t in list(m.parameters()) + list(m.buffers()):
+                sig.append(t._version)
+                sig.append(t.data_ptr())
+        return tuple(sig)
+
+    def _encoder_graph_ok(self, var, full_train):
+        if full_train or not ops.ENCODER_CUDA_GRAPH or getattr(self, "_in_encoder_capture", False):
+            return False
+        rgb = var.rgb_input_map
+        return (isinstance(self.coord_encoder, CoordEncRes) and not self.coord_encoder.training and not self.dpt_depth.training
+                and isinstance(rgb, torch.Tensor) and rgb.is_cuda and not torch.cuda.is_current_stream_capturing())
+
+    def _encode_graphed(self, opt, var):
+        from ..._native import lib
+        rgb = var.rgb_input_map.float().contiguous()
+        mask = var.mask_input_map.float().contiguous()
+        key = (tuple(rgb.shape), tuple(mask.shape), rgb.device.index)
+        sig = self._encoder_signature()
+        cache = self.__dict__.setdefault("_encoder_graphs", {})
+        ent = cache.get(key)
+        if ent is None or ent["sig"] != sig:
+            cache.pop(key, None)
+            s_rgb, s_mask = rgb.clone(), mask.clone()
+
+            def run():
+                v = edict(idx=torch.arange(rgb.shape[0]), rgb_input_map=s_rgb, mask_input_map=s_mask, pose_gt=False)
+                self._in_encoder_capture = True
+                try:
+                    v = self.forward(opt, v, training=False, get_loss=False)
+                finally:
+                    self._in_encoder_capture = False
+                return {"depth_pred": v.depth_pred, "intr_pred": v.intr_pred, "seen_points": v.seen_points,
+                        "latent_depth": v.latent_depth, "validity_mask": v.validity_mask, "mean": self.last_mean,
+                        "scale": self.last_scale}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                run()                                   # packs the weights, sizes the workspace pools
+            torch.cuda.current_stream().wait_stream(side)
+            n0 = lib.zs_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                out = run()
+            ent = {"sig": self._encoder_signature(), "graph": g, "rgb": s_rgb, "mask": s_mask, "out": out,
+                   "launches": int(lib.zs_launch_count() - n0)}
+            cache[key] = ent
+        ent["rgb"].copy_(rgb)
+        ent["mask"].copy_(mask)
+        ent["graph"].replay()
+        lib.zs_launch_count_add(ent["launches"])
+        return {k: v.clone() for k, v in ent["out"].items()}     # the static outputs are overwritten by the next replay
+
     def forward(self, opt, var, training=False, get_loss=True):
         batch_size = len(var.idx)
         depth_params = [p for m in (self.dpt_depth, self.intr_head, self.intr_proj) for p in m.parameters()]
         full_train = training and torch.is_grad_enabled() and any(p.requires_grad for p in depth_params)
+        graphed = self._encoder_graph_ok(var, full_train)
+        if graphed:
+            with torch.no_grad():
+                enc = self._encode_graphed(opt, var)
+            var.latent_semantic = None
+            var.depth_pred, var.intr_pred, var.seen_points = enc["depth_pred"], enc["intr_pred"], enc["seen_points"]
+            var.latent_depth, var.validity_mask = enc["latent_depth"], enc["validity_mask"]
+            self.last_mean, self.last_scale = enc["mean"], enc["scale"]
+            mask = var.mask_input_map.float().contiguous()
         if full_train:
             # default options/shape.yaml (fix_dpt: false): the shape loss reaches the depth estimator through the seen surface.
             # One tape from the image to latent_depth (model/depth/dpt_train.py), hand-written backward for every layer.
@@ -94,7 +163,7 @@ class Graph(nn.Module):
             var.depth_pred, var.intr_pred, var.seen_points, var.latent_depth = EncoderTrainFn.apply(
                 self, opt, var.rgb_input_map, mask, *enc_params)
         with torch.no_grad():
-            if not full_train:
+            if not full_train and not graphed:
                 var.latent_semantic = None
                 var.depth_pred = self.dpt_depth(var.rgb_input_map, get_feat=False)
                 feat = self.dpt_depth.last_feat_nhwc                                   # layer_4 [B,7,7,768] NHWC

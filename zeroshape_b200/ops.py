@@ -348,6 +348,9 @@ if os.environ.get("ZS_GEMM_SPLITK"):              # A/B switch of the split-K pa
 
 ENCODER_ENGINE = "auto"
 ENCODER_PRECISION = "bf16x3"
+# Graph.forward in eval mode replays the image -> latents encoder from a CUDA graph (model/compute_graph/graph_shape.py); False =
+# launch it op by op (also forced while an OpTimer is active: it needs the individual launches)
+ENCODER_CUDA_GRAPH = os.environ.get("ZS_ENCODER_GRAPH", "1") != "0"
 
 
 def _encoder_tc():
@@ -743,6 +746,8 @@ class OpTimer:
 
     def __enter__(self):
         g = globals()
+        self.saved["ENCODER_CUDA_GRAPH"] = g["ENCODER_CUDA_GRAPH"]        # the timer needs the individual launches
+        g["ENCODER_CUDA_GRAPH"] = False
         for name in self.NAMES:
             fn = g.get(name)
             if fn is None:
