@@ -195,6 +195,12 @@ int zs_layernorm_f32(const float* x, int ldx, const float* gamma, const float* b
 /* GroupNorm (+optional ReLU) on NHWC.  Replaces timm GroupNormAct in the ResNetV2 stem/stages. */
 int zs_groupnorm_nhwc_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
                           int B, int HW, int C, int groups, float eps, int relu, void* stream);
+/* The same GroupNorm on the tiled kernels (two fully coalesced launches: per-chunk group statistics in double to `ws`, then the
+ * normalisation) when C / 4 is a power of two <= 256 and the tensors are 16-byte aligned; any other shape (or ws == NULL) takes
+ * zs_groupnorm_nhwc_f32.  ws: zs_groupnorm_ws_bytes(B, HW, C, groups) bytes, 8-byte aligned, need not be initialised. */
+size_t zs_groupnorm_ws_bytes(int B, int HW, int C, int groups);
+int zs_groupnorm_nhwc_ws_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
+                             int B, int HW, int C, int groups, float eps, int relu, void* ws, void* stream);
 
 /* Per-channel affine y = act(x*scale[c] + shift[c] (+res)) on [rows, C] (eval-mode BatchNorm). */
 int zs_channel_affine_f32(const float* x, const float* scale, const float* shift, const float* res,

@@ -89,6 +89,27 @@ def test_layernorm_groupnorm_affine(cuda):
     _close(ops.channel_affine(xh.to(cuda), sc.to(cuda), sh.to(cuda), act=ops.ACT_RELU), F.relu(xh * sc + sh))
 
 
+@pytest.mark.parametrize("cfg", [(1, 64, 112, 112, 0.0), (2, 256, 56, 56, 0.5), (3, 1024, 14, 14, 0.0), (2, 512, 28, 28, 30.0),
+                                 (1, 128, 5, 7, 1.0), (2, 96, 9, 9, 0.0), (1, 256, 3, 3, 0.0)])
+def test_groupnorm_tiled_and_fallback(cuda, cfg):
+    """timm GroupNormAct(32) of the ResNetV2 stem / stages on NHWC: the tiled kernels (C / 4 a power of two: group size 2 ... 32,
+    a mean 15 standard deviations off zero for the shifted one-pass statistics, a ragged last chunk) and the generic kernel
+    (C = 96, tiny maps) against torch in double, with and without the residual / ReLU."""
+    from zeroshape_b200 import ops
+    B, C, H, W, off = cfg
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g) * 2 + off
+    w, b = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    r = torch.randn(B, C, H, W, generator=g)
+    ref = F.group_norm(x.double(), 32, w.double(), b.double(), 1e-5)
+    xh, rh = x.permute(0, 2, 3, 1).contiguous().to(cuda), r.permute(0, 2, 3, 1).contiguous().to(cuda)
+    out = ops.groupnorm_nhwc(xh, w.to(cuda), b.to(cuda), 32, 1e-5, False).permute(0, 3, 1, 2).cpu().double()
+    assert (out - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item()), (out - ref).abs().max().item()
+    out = ops.groupnorm_nhwc(xh, w.to(cuda), b.to(cuda), 32, 1e-5, True, rh).permute(0, 3, 1, 2).cpu().double()
+    ref2 = F.relu(ref + r.double())
+    assert (out - ref2).abs().max().item() < 2e-5 * max(1.0, ref2.abs().max().item())
+
+
 def test_pooling_resize_layout(cuda):
     from zeroshape_b200 import ops
     g = torch.Generator().manual_seed(2)

@@ -83,6 +83,8 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "zs_layernorm_f32": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_float, P]),
     "zs_groupnorm_nhwc_f32": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    "zs_groupnorm_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "zs_groupnorm_nhwc_ws_f32": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P]),
     "zs_channel_affine_f32": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P]),
     "zs_axpby_f32": (c_int, [P, c_float, P, c_float, P, c_int64, c_int, P]),
     "zs_maxpool3x3s2_nhwc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -93,6 +93,98 @@ __global__ void groupnorm_nhwc_kernel(const float* __restrict__ x, const float* 
   }
 }
 
+// ---- GroupNorm NHWC, tiled (C / 4 a power of two <= 256, the ResNetV2 / DPT shapes): two launches, both fully coalesced -------------
+// The one-CTA-per-(image, group) kernel above walks 32-byte group slices with a 4 * C byte stride three times on B * 32 CTAs
+// (47 us for [1,56,56,256], a quarter of the encoder's device time).  Here every CTA streams whole pixels (all channels, 128-bit
+// loads); with 256 threads and C / 4 | 256 a thread always sees the same four channels, so its group(s), gamma and beta are fixed.
+//   stats: grid (chunks, B); per lane fp32 sums of (x - c) and (x - c)^2 with c = the group's first element of the image (a shift
+//          near the mean: no cancellation in E[d^2] - E[d]^2), combined in DOUBLE per group in shared memory, one partial per
+//          (image, chunk, group) to the workspace -- no atomics on global memory, deterministic.
+//   apply: grid (chunks', B); every CTA sums the <= GN_MAX_CHUNKS partials of its image in double -> mean, rstd per group, then
+//          y = (x - mean) * rstd * gamma + beta (+ res) (ReLU) in the original operation order.
+constexpr int GN_MAX_CHUNKS = 32;
+
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, int HW, int C,
+                                                              int groups, int pix_per_chunk) {
+  __shared__ double acc[2 * 256];                       // [group][sum, sumsq], groups <= 256
+  const int b = blockIdx.y, chunk = blockIdx.x, c4 = C >> 2, cg = C / groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += 256) acc[i] = 0.0;
+  __syncthreads();
+  const int q = threadIdx.x % c4;                       // this thread's channel quad
+  const float* xb = x + (int64_t)b * HW * C;
+  float shift[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) shift[e] = __ldg(xb + ((q * 4 + e) / cg) * cg);
+  const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* x4 = reinterpret_cast<const float4*>(xb);
+  for (int64_t i = (int64_t)p0 * c4 + threadIdx.x; i < (int64_t)p1 * c4; i += 256) {
+    const float4 v = __ldg(x4 + i);
+    const float d0 = v.x - shift[0], d1 = v.y - shift[1], d2 = v.z - shift[2], d3 = v.w - shift[3];
+    s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
+    ss[0] = fmaf(d0, d0, ss[0]); ss[1] = fmaf(d1, d1, ss[1]); ss[2] = fmaf(d2, d2, ss[2]); ss[3] = fmaf(d3, d3, ss[3]);
+  }
+  if (cg >= 4) {                                         // the quad lies inside one group
+    const int g = (q * 4) / cg;
+    atomicAdd(&acc[2 * g], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+    atomicAdd(&acc[2 * g + 1], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (q * 4 + e) / cg;
+      atomicAdd(&acc[2 * g], (double)s[e]);
+      atomicAdd(&acc[2 * g + 1], (double)ss[e]);
+    }
+  }
+  __syncthreads();
+  double* o = ws + ((int64_t)b * gridDim.x + chunk) * 2 * groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += 256) o[i] = acc[i];
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ res,
+                                                              float* __restrict__ y, const double* __restrict__ ws, int HW, int C,
+                                                              int groups, int stat_chunks, int pix_per_chunk, float eps, int relu) {
+  __shared__ float smean[256], srstd[256];
+  const int b = blockIdx.y, c4 = C >> 2, cg = C / groups;
+  const float* xb = x + (int64_t)b * HW * C;
+  for (int g = threadIdx.x; g < groups; g += 256) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < stat_chunks; ++k) {
+      const double* w = ws + ((int64_t)b * stat_chunks + k) * 2 * groups + 2 * g;
+      su += w[0]; sq += w[1];
+    }
+    const double n = (double)HW * cg, md = su / n;
+    double var = sq / n - md * md;
+    if (var < 0.0) var = 0.0;
+    smean[g] = (float)((double)__ldg(xb + g * cg) + md);
+    srstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int q = threadIdx.x % c4;
+  float mean[4], rstd[4], ga[4], be[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = q * 4 + e, g = c / cg;
+    mean[e] = smean[g]; rstd[e] = srstd[g]; ga[e] = __ldg(gamma + c); be[e] = __ldg(beta + c);
+  }
+  const int p0 = blockIdx.x * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
+  const float4* x4 = reinterpret_cast<const float4*>(xb);
+  const float4* r4 = res ? reinterpret_cast<const float4*>(res + (int64_t)b * HW * C) : nullptr;
+  float4* y4 = reinterpret_cast<float4*>(y + (int64_t)b * HW * C);
+  for (int64_t i = (int64_t)p0 * c4 + threadIdx.x; i < (int64_t)p1 * c4; i += 256) {
+    const float4 v = __ldg(x4 + i);
+    float4 o;
+    o.x = (v.x - mean[0]) * rstd[0] * ga[0] + be[0];
+    o.y = (v.y - mean[1]) * rstd[1] * ga[1] + be[1];
+    o.z = (v.z - mean[2]) * rstd[2] * ga[2] + be[2];
+    o.w = (v.w - mean[3]) * rstd[3] * ga[3] + be[3];
+    if (r4) { const float4 r = __ldg(r4 + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    y4[i] = o;
+  }
+}
+
 __global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ sc,
                                       const float* __restrict__ sh, const float* __restrict__ res,
                                       float* __restrict__ y, int64_t n, int C, int act) {
@@ -306,6 +398,45 @@ extern "C" int zs_groupnorm_nhwc_f32(const float* x, const float* gamma, const f
              "zs_groupnorm_nhwc_f32: bad args");
   groupnorm_nhwc_kernel<<<B * groups, 512, 0, as_stream(stream)>>>(x, gamma, beta, res, y, HW, C, groups, eps, relu);
   ZS_CUDA_CHECK_LAUNCH("zs_groupnorm_nhwc_f32");
+  return ZS_OK;
+}
+
+static bool gn_tiled_ok(const float* x, const float* res, const float* y, int HW, int C, int groups) {
+  const int c4 = C >> 2;
+  return (C & 3) == 0 && c4 >= 1 && c4 <= 256 && (c4 & (c4 - 1)) == 0 && groups <= 256 && HW >= 16 &&
+         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res)) & 15) == 0;
+}
+static void gn_chunks(int HW, int& chunks, int& ppc) {
+  chunks = (HW + 63) / 64;                                 // >= 64 pixels per stats CTA, at most GN_MAX_CHUNKS partials per image
+  if (chunks > zs::GN_MAX_CHUNKS) chunks = zs::GN_MAX_CHUNKS;
+  ppc = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppc - 1) / ppc;
+}
+
+extern "C" size_t zs_groupnorm_ws_bytes(int B, int HW, int C, int groups) {
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0) return 0;
+  return (size_t)B * zs::GN_MAX_CHUNKS * 2 * groups * sizeof(double);
+}
+
+extern "C" int zs_groupnorm_nhwc_ws_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
+                                        int B, int HW, int C, int groups, float eps, int relu, void* ws, void* stream) {
+  ZS_REQUIRE(x && gamma && beta && y && B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0,
+             "zs_groupnorm_nhwc_ws_f32: bad args");
+  if (!ws || !gn_tiled_ok(x, res, y, HW, C, groups) || (reinterpret_cast<uintptr_t>(ws) & 7) != 0)
+    return zs_groupnorm_nhwc_f32(x, gamma, beta, res, y, B, HW, C, groups, eps, relu, stream);
+  int chunks, ppc;
+  gn_chunks(HW, chunks, ppc);
+  cudaStream_t st = as_stream(stream);
+  groupnorm_stats_kernel<<<dim3(chunks, B), 256, 0, st>>>(x, reinterpret_cast<double*>(ws), HW, C, groups, ppc);
+  ZS_CUDA_CHECK_LAUNCH("zs_groupnorm_nhwc_ws_f32(stats)");
+  int achunks = (HW + 31) / 32;                            // apply: ~32 pixels per CTA, at most ~8 CTAs per SM in flight
+  const int cap = (8 * sm_count() + B - 1) / B;
+  if (achunks > cap) achunks = cap;
+  const int appc = (HW + achunks - 1) / achunks;
+  achunks = (HW + appc - 1) / appc;
+  groupnorm_apply_kernel<<<dim3(achunks, B), 256, 0, st>>>(x, gamma, beta, res, y, reinterpret_cast<const double*>(ws), HW, C, groups,
+                                                          chunks, appc, eps, relu);
+  ZS_CUDA_CHECK_LAUNCH("zs_groupnorm_nhwc_ws_f32(apply)");
   return ZS_OK;
 }
 

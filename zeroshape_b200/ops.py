@@ -428,8 +428,9 @@ def groupnorm_nhwc(x, gamma, beta, groups, eps, relu, res=None):
     _chk(x, "x"); _chk(res, "res")
     B, H, W, C = x.shape
     y = torch.empty_like(x)
-    check(lib.zs_groupnorm_nhwc_f32(_p(x), _p(gamma), _p(beta), _p(res), _p(y), B, H * W, C, groups, eps, int(relu),
-                                    _stream()), "zs_groupnorm_nhwc_f32")
+    ws = torch.empty(lib.zs_groupnorm_ws_bytes(B, H * W, C, groups) // 8, device=x.device, dtype=torch.float64)
+    check(lib.zs_groupnorm_nhwc_ws_f32(_p(x), _p(gamma), _p(beta), _p(res), _p(y), B, H * W, C, groups, eps, int(relu), _p(ws),
+                                       _stream()), "zs_groupnorm_nhwc_ws_f32")
     return y
 
 
