@@ -237,6 +237,12 @@ def test_graphed_inference_encoder_equals_the_eager_one(cuda):
         dict(graph.dpt_depth.named_parameters())["scratch.output_conv.4.bias"].add_(0.01)
     e4, g4 = run(*x1, False), run(*x1, True)
     assert same(e4, g4) and not torch.equal(g4["depth_pred"], g1["depth_pred"])
+    # the captures live outside the module: deepcopy / pickling of the Graph still work, the copy starts without captures
+    import copy
+    import io
+    twin = copy.deepcopy(graph)
+    assert len(twin._encoder_graphs) == 0 and len(graph._encoder_graphs) >= 1
+    torch.save(graph, io.BytesIO())
     # the outputs handed out are copies: a later replay does not overwrite them
     keep = g4["latent_depth"].clone()
     run(*x2, True)

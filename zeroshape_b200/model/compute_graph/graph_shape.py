@@ -14,6 +14,8 @@ coord_encoder + impl_network train; otherwise the whole encoder side runs on one
 shape loss reaches dpt_depth / intr_head / intr_proj through the unprojected, normalised seen surface.  The MiDaS depth loss (model/depth/midas_loss.py)
 belongs to the depth-engine row and raises.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -24,6 +26,9 @@ from ..depth.dpt_depth import DPTDepthModel
 from ..shape.implicit import Implicit
 from ..shape.seen_coord_enc import CoordEncAtt, CoordEncRes
 from ...utils.loss import Loss
+
+
+_ENCODER_GRAPHS = weakref.WeakKeyDictionary()     # Graph instance -> its captured encoder graphs (see Graph._encode_graphed)
 
 
 class Graph(nn.Module):
@@ -81,6 +86,12 @@ class Graph(nn.Module):
     # per layer whatever its size, tools/diag_encoder_layers.py).  Everything on the path is stream-ordered, so the eval-mode
     # forward of a given input shape is captured once and replayed; the capture is dropped whenever a parameter or buffer
     # changes (version counters / storage), the precision policy changes, or an op timer is active.
+    @property
+    def _encoder_graphs(self):
+        """{(input shapes, device): capture}; kept outside the module's __dict__ so that pickling / deepcopy of the Graph
+        (torch.save(graph), EMA copies) never meets a CUDAGraph object."""
+        return _ENCODER_GRAPHS.setdefault(self, {})
+
     def _encoder_signature(self):
         sig = [ops.ENCODER_ENGINE, ops.ENCODER_PRECISION]
         for m in (self.dpt_depth, self.intr_head, self.intr_proj, self.coord_encoder):
@@ -102,10 +113,12 @@ class Graph(nn.Module):
         mask = var.mask_input_map.float().contiguous()
         key = (tuple(rgb.shape), tuple(mask.shape), rgb.device.index)
         sig = self._encoder_signature()
-        cache = self.__dict__.setdefault("_encoder_graphs", {})
+        cache = self._encoder_graphs
         ent = cache.get(key)
         if ent is None or ent["sig"] != sig:
             cache.pop(key, None)
+            while len(cache) >= 4:                      # every capture owns its activations: keep the four most recent shapes
+                cache.pop(next(iter(cache)))
             s_rgb, s_mask = rgb.clone(), mask.clone()
 
             def run():
