@@ -42,5 +42,24 @@ xb, xk = (torch.from_numpy(a).to(dev) for a in resize_coeffs(110, 224))
 out = ops.rgba_crop_resize(img, -20, -15, 110, 110, 224, 224, xb, xk, xb, xk)
 ops.rgba_composite(out, 1.0)
 ops.erode_square(torch.rand(2, 33, 41, device=dev).round(), 5)
+# round 2, last session: tiled GroupNorm (ragged chunks, group size 2 and 32), stride-2 stem dgrad (partial tiles), 128-bit bilinear
+# forward / gather backward (odd sizes, both conventions), capturable AdamW (more than one parameter table per launch group),
+# attention backward kernels on ragged token / point counts
+for B, C, H, W in ((1, 64, 37, 29), (2, 256, 15, 15), (1, 1024, 5, 4), (2, 96, 9, 9)):
+    x = torch.randn(B, H, W, C, device=dev)
+    ops.groupnorm_nhwc(x, torch.ones(C, device=dev), torch.zeros(C, device=dev), 32, 1e-5, True, x.clone())
+for B, H, W, Cin, Cout, K, pad in ((1, 37, 29, 3, 64, 7, 3), (2, 18, 20, 4, 16, 3, 1), (1, 16, 16, 3, 64, 7, 3)):
+    OH, OW = (H + 2 * pad - K) // 2 + 1, (W + 2 * pad - K) // 2 + 1
+    ops.conv2d_nhwc_dgrad(torch.randn(B, OH, OW, Cout, device=dev), torch.randn(Cout, K, K, Cin, device=dev), (B, H, W, Cin), 2,
+                          (pad, pad, pad, pad), tc=False)
+for B, H, W, C, OH, OW, al in ((1, 7, 9, 12, 14, 18, True), (2, 24, 24, 8, 14, 14, False), (1, 13, 11, 4, 29, 23, False), (2, 1, 1, 4, 4, 4, True)):
+    ops.bilinear_nhwc(torch.randn(B, H, W, C, device=dev), OH, OW, al)
+    ops.bilinear_bwd_nhwc(torch.randn(B, OH, OW, C, device=dev), H, W, al)
+ps = [torch.randn(int(n), device=dev) for n in torch.randint(1, 500, (130,), generator=g)]
+hyper = torch.tensor([1e-3, 0.9, 0.95, 1e-8, 0.05, 0.1, 0.3, 0.0], device=dev)
+ops.adamw_step_multi_dev(ps, [torch.randn_like(p) for p in ps], [torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps], hyper)
+for B, T, H, hd in ((1, 197, 12, 64), (2, 50, 3, 32), (1, 130, 2, 32)):
+    qkv = torch.randn(B, T, 3 * H * hd, device=dev)
+    ops.mha_bwd(qkv, torch.randn(B, T, H * hd, device=dev), H, tc=True)
 torch.cuda.synchronize()
 print("sanitize_small: done")
