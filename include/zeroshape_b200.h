@@ -249,6 +249,11 @@ int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int heads, int hd,
  * transposes as tcgen05 MMAs with single-pass fp16 operands and fp32 accumulation, P and dS re-written in place in tensor memory
  * as the A operands of dQ = dS K, dV = P^T dO, dK = dS^T Q.  Precision class of the bf16 training mode (zs_mha_bwd_f32 is the
  * fp32-grade path).  dqkv [B,T,3C] is written completely; ws: zs_mha_bwd_tc_ws_bytes(B, T, heads), 16-byte aligned. */
+/* zs_point_attention_f32 on the tensor cores for the training tape (csrc/mha_tc.cu: pa_fwd_tc_kernel; head dim 32, L <= 208, no
+ * attention-map output): per 128-point tile S = Q K_lat^T and O = P V_lat as tcgen05 MMAs with the probabilities in tensor memory,
+ * the point's own key / value as one extra softmax column in registers.  precision 0 = split fp16 (three passes), 1 = one fp16 pass. */
+int zs_point_attention_tc_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, float* out, int B, int P, int L,
+                              int heads, int hd, float scale, int precision, void* stream);
 /* Backward of zs_point_attention_f32 on the tensor cores (csrc/mha_tc.cu: pa_bwd_q_kernel per 128-point tile, pa_bwd_kv_kernel
  * per 128 latent keys looping over the points in chunks of 208; the point's own key / value handled per row): same outputs as
  * zs_point_attention_bwd_f32 (dqkv_p [B,P,3C] complete, dk_lat / dv_lat [B,L,C] with row stride ld_dlat), single fp16 pass.

@@ -110,7 +110,7 @@ def mha(qkv, heads, tc=None, precision="fp16x3"):
     return (((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1) @ v).transpose(1, 2).reshape(B, T, C).contiguous()
 
 
-def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False):
+def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False, tc=None):
     B, P, C3 = qkv_p.shape
     C = C3 // 3
     hd = C // heads

@@ -187,3 +187,34 @@ def test_point_attention_bwd_on_the_tensor_cores(cuda, B, P, L):
           + " ".join(f"{e:.1e}" for e in res[True]) + " | FFMA " + " ".join(f"{e:.1e}" for e in res[False]))
     assert max(res[True]) < 4e-3 and max(res[False]) < 2e-5
 
+
+
+@pytest.mark.parametrize("B,P,L", [(2, 300, 197), (1, 128, 208), (3, 77, 50), (1, 4096, 197)])
+def test_point_attention_fwd_on_the_tensor_cores(cuda, B, P, L):
+    """zs_point_attention_tc_f32 (decoder training forward: points -> latents + the point's own key) against the fp64 formula of
+    ImplFuncAttention's point rows: split fp16 (fp32-grade, like the FFMA kernel) and the single fp16 pass of the bf16 training mode."""
+    from zeroshape_b200 import ops
+    if ops.device_cc() != 100:
+        pytest.skip("tcgen05 needs sm_100")
+    H, hd = 8, 32
+    C = H * hd
+    g = torch.Generator().manual_seed(P + L)
+    qkv = torch.randn(B, P, 3 * C, generator=g) * 0.7
+    lat = torch.randn(B, L, 3 * C, generator=g) * 0.7
+    q, k, v = [t.double().reshape(B, P, H, hd).permute(0, 2, 1, 3) for t in (qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:])]
+    kl = lat[..., C:2 * C].double().reshape(B, L, H, hd).permute(0, 2, 1, 3)
+    vl = lat[..., 2 * C:].double().reshape(B, L, H, hd).permute(0, 2, 1, 3)
+    a = (torch.cat([q @ kl.transpose(-2, -1), (q * k).sum(-1, keepdim=True)], -1) * hd ** -0.5).softmax(-1)
+    ref = (a[..., :L] @ vl + a[..., L:] * v).permute(0, 2, 1, 3).reshape(B, P, C)
+    lat_d, qkv_d = lat.to(cuda), qkv.to(cuda)
+    ffma = ops.point_attention(qkv_d, lat_d[..., C:2 * C], lat_d[..., 2 * C:], H, tc=False)
+    split = ops.point_attention(qkv_d, lat_d[..., C:2 * C], lat_d[..., 2 * C:], H, tc=True)
+    old = ops.TRAIN_ENGINE, ops.TRAIN_PRECISION
+    ops.TRAIN_ENGINE, ops.TRAIN_PRECISION = "tc", "bf16"
+    try:
+        single = ops.point_attention(qkv_d, lat_d[..., C:2 * C], lat_d[..., 2 * C:], H)
+    finally:
+        ops.TRAIN_ENGINE, ops.TRAIN_PRECISION = old
+    errs = [_rel(t, ref) for t in (ffma, split, single)]
+    print(f"point_attention fwd B={B} P={P} L={L}: rel err FFMA {errs[0]:.1e} | tcgen05 split fp16 {errs[1]:.1e} | single fp16 {errs[2]:.1e}")
+    assert errs[0] < 2e-6 and errs[1] < 5e-6 and errs[2] < 2e-3

@@ -94,6 +94,7 @@ SIGNATURES = {
     "zs_nhwc_to_nchw_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "zs_mha_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, P]),
     "zs_mha_tc_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_float, c_int, P]),
+    "zs_point_attention_tc_f32": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, P]),
     "zs_mha_bwd_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "zs_mha_bwd_tc_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_float, P, P]),
     "zs_point_attention_bwd_tc_ws_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -227,6 +227,207 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mha_tc_kernel(MhaTcParams p) {
 
 
 // ===============================================================================================================
+// Forward of the decoder's point attention inside the training tape (ImplFuncAttention, model/shape/implicit.py:25-79: every query
+// point attends to the image's L <= 208 latent tokens plus its OWN key / value): the construction of mha_tc_kernel with the keys and
+// values read from the latent-side buffers and one extra softmax column per row handled in registers --
+//   s_self = q . k_self (fp32), e_self = exp(scale (s_self - max)), out = (P V_lat + e_self v_self) / (sum_lat + e_self).
+// One CTA per (image, head, 128-point tile), head dim 32.  Replaces the one-thread-per-point FFMA kernel (zs_point_attention_f32)
+// when the training engine runs on the tensor cores in its single-pass mode.
+struct PaFwdParams {
+  const float* qkv_p; const float* k_lat; const float* v_lat; int ld_lat; float* out; int B, P, L, heads; float scale; int precision;
+};
+
+__global__ void __launch_bounds__(MT_THREADS, 1) pa_fwd_tc_kernel(PaFwdParams p) {
+  constexpr int HD = 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_s = smem_base + MT_OFF_BAR, bar_o = bar_s + 8, tmem_slot = bar_s + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = p.precision == 0;
+  const int L = p.L, C = p.heads * HD;
+  const int bh = blockIdx.x, b = bh / p.heads, h = bh % p.heads;
+  const int q0 = blockIdx.y * 128;
+  constexpr int VCH = 2 * HD * 128;
+  const float* qbase = p.qkv_p + (int64_t)b * p.P * 3 * C + h * HD;           // row t: q | + C: k_self | + 2 C: v_self
+  const float* kbase = p.k_lat + (int64_t)b * L * p.ld_lat + h * HD;
+  const float* vbase = p.v_lat + (int64_t)b * L * p.ld_lat + h * HD;
+
+  if (threadIdx.x == 0) { mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init(); }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+
+  constexpr int CPR = HD / 8;
+  for (int i = threadIdx.x; i < 128 * CPR; i += MT_THREADS) {
+    const int r = i / CPR, c = i % CPR, t = q0 + r;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    if (t < p.P) {
+      const float4* src = reinterpret_cast<const float4*>(qbase + (int64_t)t * 3 * C + 8 * c);
+      x0 = __ldg(src); x1 = __ldg(src + 1);
+    }
+    uint4 hi, lo;
+    split_f16x2(x0.x, x0.y, hi.x, lo.x); split_f16x2(x0.z, x0.w, hi.y, lo.y);
+    split_f16x2(x1.x, x1.y, hi.z, lo.z); split_f16x2(x1.z, x1.w, hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(r, c);
+    *reinterpret_cast<uint4*>(smem + MT_OFF_Q + off) = hi;
+    *reinterpret_cast<uint4*>(smem + MT_OFF_Q + 16384 + off) = lo;
+  }
+  for (int i = threadIdx.x; i < 208 * CPR; i += MT_THREADS) {
+    const int j = i / CPR, c = i % CPR;
+    float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, v0 = k0, v1 = k0;
+    if (j < L) {
+      const float4* ks = reinterpret_cast<const float4*>(kbase + (int64_t)j * p.ld_lat + 8 * c);
+      const float4* vs = reinterpret_cast<const float4*>(vbase + (int64_t)j * p.ld_lat + 8 * c);
+      k0 = __ldg(ks); k1 = __ldg(ks + 1); v0 = __ldg(vs); v1 = __ldg(vs + 1);
+    }
+    uint4 hi, lo;
+    split_f16x2(k0.x, k0.y, hi.x, lo.x); split_f16x2(k0.z, k0.w, hi.y, lo.y);
+    split_f16x2(k1.x, k1.y, hi.z, lo.z); split_f16x2(k1.z, k1.w, hi.w, lo.w);
+    const uint32_t off = swizzle128_offset(j, c);
+    *reinterpret_cast<uint4*>(smem + MT_OFF_K + off) = hi;
+    *reinterpret_cast<uint4*>(smem + MT_OFF_K + 32768 + off) = lo;
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint8_t* vch = smem + MT_OFF_V + (j >> 6) * VCH;
+    const int kc = j & 63;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int d = 8 * c + u;
+      const __half hh = __float2half_rn(vv[u]);
+      const __half ll = __float2half_rn(vv[u] - __half2float(hh));
+      *reinterpret_cast<__half*>(vch + swizzle128_offset(d, kc >> 3) + (kc & 7) * 2) = hh;
+      *reinterpret_cast<__half*>(vch + swizzle128_offset(HD + d, kc >> 3) + (kc & 7) * 2) = ll;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + MT_OFF_BAR + 16);
+  const uint32_t d_s = tmem_base, d_o = tmem_base + 256;
+
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc_s = umma_idesc_f16(128, 208);
+    const uint64_t qh = umma_desc_sw128(smem_base + MT_OFF_Q), ql = umma_desc_sw128(smem_base + MT_OFF_Q + 16384);
+    const uint64_t kh = umma_desc_sw128(smem_base + MT_OFF_K), kl = umma_desc_sw128(smem_base + MT_OFF_K + 32768);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) {
+      umma_bf16(d_s, qh + 2 * k, kh + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+      if (split) {
+        umma_bf16(d_s, ql + 2 * k, kh + 2 * k, idesc_s, 1u);
+        umma_bf16(d_s, qh + 2 * k, kl + 2 * k, idesc_s, 1u);
+      }
+    }
+    umma_commit(bar_s);
+  }
+
+  float inv = 0.f, e_self = 0.f;
+  const int t = q0 + (warp & 3) * 32 + lane;
+  if (warp < 4) {
+    // the point's own key: s_self in fp32 while the S product runs
+    float s_self = -3.0e38f;
+    if (t < p.P) {
+      const float4* q4 = reinterpret_cast<const float4*>(qbase + (int64_t)t * 3 * C);
+      const float4* k4 = reinterpret_cast<const float4*>(qbase + (int64_t)t * 3 * C + C);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        const float4 a = __ldg(q4 + i), kk = __ldg(k4 + i);
+        acc = fmaf(a.x, kk.x, acc); acc = fmaf(a.y, kk.y, acc); acc = fmaf(a.z, kk.z, acc); acc = fmaf(a.w, kk.w, acc);
+      }
+      s_self = acc;
+    }
+    const uint32_t s_tm = d_s + ((uint32_t)(warp * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = s_self;
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(s_tm + 32 * c, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (32 * c + j < L) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    {
+      uint32_t rr[16];
+      tmem_ld_32x16(s_tm + 192, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (192 + j < L) mx = fmaxf(mx, __uint_as_float(rr[j]));
+    }
+    const float mxs = mx * sl2;
+    float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+      uint32_t rr[32];
+      tmem_ld_32x32(s_tm + 32 * c, rr);
+      tmem_ld_wait();
+      if (32 * c + 32 <= L) mt_exp_tmem<32, false>(rr, 32 * c, L, sl2, mxs, sum2, s_tm + 32 * c, split);
+      else mt_exp_tmem<32, true>(rr, 32 * c, L, sl2, mxs, sum2, s_tm + 32 * c, split);
+    }
+    {
+      uint32_t rr[16];
+      tmem_ld_32x16(s_tm + 192, rr);
+      tmem_ld_wait();
+      mt_exp_tmem<16, true>(rr, 192, L, sl2, mxs, sum2, s_tm + 192, split);
+    }
+    tmem_st_wait();
+    e_self = t < p.P ? fast_ex2(fmaf(s_self, sl2, -mxs)) : 0.f;
+    inv = 1.0f / (sum2.x + sum2.y + e_self);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc_hi = split ? umma_idesc_f16(128, 2 * HD) : umma_idesc_f16(128, HD), idesc_lo = umma_idesc_f16(128, HD);
+#pragma unroll 1
+    for (int j = 0; j < 13; ++j) {
+      const uint32_t a_hi = d_s + 32u * (j >> 1) + 8u * (j & 1);
+      const uint32_t a_lo = a_hi + (j == 12 ? 8u : 16u);
+      const uint64_t vv = umma_desc_sw128(smem_base + MT_OFF_V + (j >> 2) * VCH) + 2 * (j & 3);
+      umma_ts(d_o, a_hi, vv, idesc_hi, j > 0 ? 1u : 0u);
+      if (split) umma_ts(d_o, a_lo, vv, idesc_lo, 1u);
+    }
+    umma_commit(bar_o);
+  }
+
+  if (warp < 4) {
+    const uint32_t o_tm = d_o + ((uint32_t)(warp * 32) << 16);
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const int tt = t < p.P ? t : 0;
+    float* dst = p.out + ((int64_t)b * p.P + tt) * C + h * HD;
+    const float4* v4 = reinterpret_cast<const float4*>(qbase + (int64_t)tt * 3 * C + 2 * C);
+#pragma unroll 1
+    for (int c = 0; c < HD / 16; ++c) {
+      uint32_t rr[16], r2[16];
+      tmem_ld_32x16(o_tm + 16 * c, rr);
+      if (split) tmem_ld_32x16(o_tm + HD + 16 * c, r2);
+      tmem_ld_wait();
+      if (t < p.P) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 vs = __ldg(v4 + 4 * c + j);
+          const float vself[4] = {vs.x, vs.y, vs.z, vs.w};
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float a = __uint_as_float(rr[4 * j + i]);
+            if (split) a += __uint_as_float(r2[4 * j + i]);
+            o[i] = fmaf(e_self, vself[i], a) * inv;
+          }
+          *reinterpret_cast<float4*>(dst + 16 * c + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ===============================================================================================================
 // Backward of the token self-attention on the tensor cores (single fp16 pass, fp32 accumulation: the precision class of the
 // bf16 training mode; the FFMA kernels zs_mha_bwd_f32 stay the fp32-grade path).  With P = softmax(S), S = scale Q K^T:
 //     dV = P^T dO,   dP = dO V^T,   D = rowsum(P o dP),   dS = scale P o (dP - D),   dQ = dS K,   dK = dS^T Q.
@@ -821,6 +1022,22 @@ extern "C" int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int hea
     mha_tc_kernel<32><<<grid, MT_THREADS, MT_SMEM, as_stream(stream)>>>(p);
   }
   ZS_CUDA_CHECK_LAUNCH("zs_mha_tc_f32");
+  return ZS_OK;
+}
+
+extern "C" int zs_point_attention_tc_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, float* out, int B,
+                                        int P, int L, int heads, int hd, float scale, int precision, void* stream) {
+  ZS_REQUIRE(qkv_p && k_lat && v_lat && out && B >= 0 && P >= 0 && heads > 0, "zs_point_attention_tc_f32: null pointer / bad sizes");
+  ZS_REQUIRE(L >= 1 && L <= 208 && hd == 32, "zs_point_attention_tc_f32: L must be in [1, 208] and the head dim 32");
+  ZS_REQUIRE(((reinterpret_cast<uintptr_t>(qkv_p) | reinterpret_cast<uintptr_t>(k_lat) | reinterpret_cast<uintptr_t>(v_lat) |
+               reinterpret_cast<uintptr_t>(out)) & 15) == 0 && (ld_lat & 3) == 0 && ld_lat >= heads * hd,
+             "zs_point_attention_tc_f32: buffers must be 16-byte aligned, ld_lat a multiple of 4");
+  ZS_REQUIRE(precision == 0 || precision == 1, "zs_point_attention_tc_f32: bad precision");
+  if (B == 0 || P == 0) return ZS_OK;
+  PaFwdParams p{qkv_p, k_lat, v_lat, ld_lat, out, B, P, L, heads, scale, precision};
+  ZS_CUDA_CALL(cudaFuncSetAttribute(pa_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
+  pa_fwd_tc_kernel<<<dim3(B * heads, (P + 127) / 128), MT_THREADS, MT_SMEM, as_stream(stream)>>>(p);
+  ZS_CUDA_CHECK_LAUNCH("zs_point_attention_tc_f32");
   return ZS_OK;
 }
 

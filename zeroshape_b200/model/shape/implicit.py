@@ -296,7 +296,7 @@ class Implicit(nn.Module):
                                 (C // self.num_heads) ** -0.5, self.precision, out=a[b * P:(b + 1) * P])
             else:
                 a = ops.point_attention(qkv.view(B, P, 3 * C), k_lat, v_lat, self.num_heads, attn=attn_out,
-                                        attn_scale=1.0 / nb, attn_accumulate=(l > 0)).view(B * P, C)
+                                        attn_scale=1.0 / nb, attn_accumulate=(l > 0), tc=False).view(B * P, C)
             del qkv
             if chain:
                 if self.lin_fused:

@@ -509,8 +509,10 @@ def mha(qkv, heads, tc=None, precision="fp16x3"):
     return out
 
 
-def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False):
-    """qkv_p [B,P,3C]; k_lat/v_lat [B,L,C] views with row stride; returns [B,P,C]."""
+def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_accumulate=False, tc=None):
+    """qkv_p [B,P,3C]; k_lat/v_lat [B,L,C] views with row stride; returns [B,P,C].  `tc`: None = tensor cores
+    (zs_point_attention_tc_f32, one fp16 pass) when the training engine is on them in its single-pass mode and no attention
+    map is asked for, else the FFMA kernel; True = tensor cores in split-fp16 (fp32-grade)."""
     _chk(qkv_p, "qkv_p")
     B, Pn, C3 = qkv_p.shape
     C = C3 // 3
@@ -519,6 +521,13 @@ def point_attention(qkv_p, k_lat, v_lat, heads, attn=None, attn_scale=1.0, attn_
     assert k_lat.stride(0) == L * k_lat.stride(1) and v_lat.stride(0) == L * v_lat.stride(1)
     out = torch.empty(B, Pn, C, device=qkv_p.device, dtype=torch.float32)
     _chk(attn, "attn")
+    single = tc is None
+    if tc is None:
+        tc = train_tc() and TRAIN_PRECISION == "bf16"
+    if tc and attn is None and L <= 208 and C // heads == 32 and k_lat.stride(1) % 4 == 0 and k_lat.data_ptr() % 16 == 0 and v_lat.data_ptr() % 16 == 0:
+        check(lib.zs_point_attention_tc_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(out), B, Pn, L, heads, C // heads,
+                                            (C // heads) ** -0.5, 1 if single else 0, _stream()), "zs_point_attention_tc_f32")
+        return out
     check(lib.zs_point_attention_f32(_p(qkv_p), _p(k_lat), _p(v_lat), k_lat.stride(1), _p(out), _p(attn), attn_scale,
                                      int(attn_accumulate), B, Pn, L, heads, C // heads, (C // heads) ** -0.5, _stream()),
           "zs_point_attention_f32")
