@@ -206,12 +206,12 @@ def test_graphed_inference_encoder_equals_the_eager_one(cuda):
     graph = _graph(sd, cuda)
     opt = make_opt(cuda)
 
-    def run(rgb, mask, graphed):
+    def run(rgb, mask, graphed, model=None):
         ops.ENCODER_CUDA_GRAPH = graphed
         try:
             var = EasyDict(idx=torch.arange(rgb.shape[0]), rgb_input_map=rgb.to(cuda), mask_input_map=mask.to(cuda), pose_gt=False)
             with torch.no_grad():
-                var = graph.forward(opt, var, training=False, get_loss=False)
+                var = (model or graph).forward(opt, var, training=False, get_loss=False)
         finally:
             ops.ENCODER_CUDA_GRAPH = True
         return {k: var[k].clone() for k in ("depth_pred", "intr_pred", "seen_points", "latent_depth", "validity_mask")}
@@ -242,7 +242,14 @@ def test_graphed_inference_encoder_equals_the_eager_one(cuda):
     import io
     twin = copy.deepcopy(graph)
     assert len(twin._encoder_graphs) == 0 and len(graph._encoder_graphs) >= 1
-    torch.save(graph, io.BytesIO())
+    buf = io.BytesIO()
+    torch.save(graph, buf)
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    with torch.no_grad():                                   # the copies own their weights (and their packed images of them)
+        dict(twin.dpt_depth.named_parameters())["scratch.output_conv.4.bias"].add_(0.02)
+    t4, l4 = run(*x1, True, twin), run(*x1, True, loaded)
+    assert same(l4, g4) and not torch.equal(t4["depth_pred"], g4["depth_pred"]) and same(run(*x1, True), g4)
     # the outputs handed out are copies: a later replay does not overwrite them
     keep = g4["latent_depth"].clone()
     run(*x2, True)

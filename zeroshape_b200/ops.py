@@ -61,6 +61,22 @@ def gemm(a, w, bias=None, res=None, res_mode=RES_NONE, act=ACT_NONE, out=None):
     return out
 
 
+def _no_cache():
+    return None
+
+
+class _LiveMatrix:
+    """The CURRENT value of a weight tensor as a matrix (weak reference: the cache object hangs off the tensor itself)."""
+
+    def __init__(self, w):
+        import weakref
+        self.ref = weakref.ref(w)
+
+    def __call__(self):
+        t = self.ref().detach()
+        return t.reshape(t.shape[0], -1) if t.dim() != 2 else t
+
+
 class PackedWeight:
     """fp32 W[N,K] packed for the tcgen05 GEMM (hi/lo bf16, UMMA swizzled tiles).  `w` may be a tensor or a zero-argument
     callable returning the CURRENT weight (e.g. `lambda: param.detach()`): the blob is re-packed whenever the live tensor's
@@ -71,6 +87,13 @@ class PackedWeight:
         self._get = w if callable(w) else (lambda: w)
         self.key = None
         self.blob = None
+
+    def __reduce_ex__(self, protocol):
+        # a cache attached to a parameter (`_packed_of`) must not travel with copy.deepcopy / torch.save of the module: the copy
+        # would keep reading the ORIGINAL tensor through the weak reference.  It unpickles as None and is rebuilt on first use.
+        if isinstance(self._get, _LiveMatrix):
+            return (_no_cache, ())
+        return super().__reduce_ex__(protocol)
 
     @property
     def src(self):
@@ -367,13 +390,7 @@ def _packed_of(w):
     on every use (PackedWeight above), so re-assigning `param.data` after a first forward cannot leave a stale image."""
     pw = getattr(w, "_zs_packed", None)
     if pw is None:
-        import weakref
-        ref = weakref.ref(w)
-
-        def live():
-            t = ref().detach()
-            return t.reshape(t.shape[0], -1) if t.dim() != 2 else t
-        pw = PackedWeight(live)
+        pw = PackedWeight(_LiveMatrix(w))
         w._zs_packed = pw
     return pw
 
