@@ -687,18 +687,36 @@ __device__ __forceinline__ void bilinear_dst_range(int i, int in, int out, int a
   if (i == in - 1 || hi > out - 1) hi = out - 1;
 }
 
+constexpr int BG_MAXT = 10;                                 // candidate rows / columns per input pixel kept in registers
 __global__ void bilinear_bwd_gather_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int B, int H, int W, int C4,
                                               int OH, int OW, int align) {
-  const int64_t total = (int64_t)B * H * W * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    const int pix = (int)(i / C4);
-    const int w = pix % W, t = pix / W;
-    const int h = t % H, b = t / H;
+  const unsigned total = (unsigned)B * H * W * C4;          // < 2^31 (checked by the caller)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / (unsigned)C4, c = i - pix * C4;
+    const unsigned t = pix / (unsigned)W;
+    const int w = (int)(pix - t * W);
+    const unsigned b = t / (unsigned)H;
+    const int h = (int)(t - b * H);
     int oh_lo, oh_hi, ow_lo, ow_hi;
     bilinear_dst_range(h, H, OH, align, oh_lo, oh_hi);
     bilinear_dst_range(w, W, OW, align, ow_lo, ow_hi);
-    const float4* g = dy + (int64_t)b * OH * OW * C4 + c;
+    // column weights once per pixel (not once per candidate row)
+    float ww[BG_MAXT];
+    const int ncol = ow_hi - ow_lo + 1;
+    const bool cached = ncol <= BG_MAXT;
+    if (cached) {
+#pragma unroll
+      for (int k = 0; k < BG_MAXT; ++k) {
+        ww[k] = 0.f;
+        if (k < ncol) {
+          int w0, w1;
+          float lw;
+          bilinear_src_t(ow_lo + k, W, OW, align, w0, w1, lw);
+          ww[k] = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+        }
+      }
+    }
+    const float4* g = dy + (size_t)b * OH * OW * C4 + c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       int h0, h1;
@@ -706,15 +724,27 @@ __global__ void bilinear_bwd_gather_v4_kernel(const float4* __restrict__ dy, flo
       bilinear_src_t(oh, H, OH, align, h0, h1, lh);
       const float wh = (h0 == h ? 1.f - lh : 0.f) + (h1 == h ? lh : 0.f);
       if (wh == 0.f) continue;
-      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        int w0, w1;
-        float lw;
-        bilinear_src_t(ow, W, OW, align, w0, w1, lw);
-        const float ww = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
-        if (ww == 0.f) continue;
-        const float4 v = __ldg(g + ((int64_t)oh * OW + ow) * C4);
-        const float k = wh * ww;
-        acc.x = fmaf(v.x, k, acc.x); acc.y = fmaf(v.y, k, acc.y); acc.z = fmaf(v.z, k, acc.z); acc.w = fmaf(v.w, k, acc.w);
+      const float4* grow = g + (size_t)oh * OW * C4;
+      if (cached) {
+#pragma unroll
+        for (int k = 0; k < BG_MAXT; ++k) {
+          if (k < ncol && ww[k] != 0.f) {
+            const float4 v = __ldg(grow + (ow_lo + k) * C4);
+            const float kk = wh * ww[k];
+            acc.x = fmaf(v.x, kk, acc.x); acc.y = fmaf(v.y, kk, acc.y); acc.z = fmaf(v.z, kk, acc.z); acc.w = fmaf(v.w, kk, acc.w);
+          }
+        }
+      } else {
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+          int w0, w1;
+          float lw;
+          bilinear_src_t(ow, W, OW, align, w0, w1, lw);
+          const float wc = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+          if (wc == 0.f) continue;
+          const float4 v = __ldg(grow + ow * C4);
+          const float kk = wh * wc;
+          acc.x = fmaf(v.x, kk, acc.x); acc.y = fmaf(v.y, kk, acc.y); acc.z = fmaf(v.z, kk, acc.z); acc.w = fmaf(v.w, kk, acc.w);
+        }
       }
     }
     dx[i] = acc;
@@ -1118,8 +1148,8 @@ extern "C" int zs_bilinear_bwd_nhwc_f32(const float* dy, float* dx, int B, int H
                                         void* stream) {
   ZS_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "zs_bilinear_bwd_nhwc_f32: bad args");
   cudaStream_t st = as_stream(stream);
-  if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (int64_t)B * H * W < (1LL << 31) &&
-      (int64_t)B * OH * OW < (1LL << 31)) {
+  if ((C & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && (int64_t)B * H * W * (C / 4) < (1LL << 31) &&
+      (int64_t)OH * OW * (C / 4) < (1LL << 31)) {
     bilinear_bwd_gather_v4_kernel<<<grid_for_n((int64_t)B * H * W * (C / 4)), 256, 0, st>>>(
         reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), B, H, W, C / 4, OH, OW, align_corners);
     ZS_CUDA_CHECK_LAUNCH("zs_bilinear_bwd_nhwc_f32");
