@@ -552,7 +552,7 @@ def test_graphed_training_step_matches_eager(cuda):
     assert abs(loss_r - loss_e) < 1e-5 * abs(loss_e), (loss_r, loss_e)
     num = sum(((a - b.detach()).double() ** 2).sum().item() for a, b in zip(after_r, params_g))
     den = sum((a.double() ** 2).sum().item() for a in after_r)
-    assert (num / den) ** 0.5 < 1e-5, (num / den) ** 0.5
+    assert (num / den) ** 0.5 < 1e-4, (num / den) ** 0.5            # (atomically accumulated gradients: elements with ~0 gradient move by +-lr)
     # (2) the trajectory: `warm` + 1 steps done, the rest replayed.  Loose: Adam's normalised update amplifies the run-to-run
     # noise of the atomically accumulated gradients (an element with a ~0 gradient moves by +-lr either way)
     graphed = [gstep(*host).item() for _ in range(steps - warm - 1)]
