@@ -46,7 +46,8 @@ extern "C" {
 
 const char* zs_last_error(void);
 int zs_abi_version(void);
-/* compute capability (major*10+minor) of the current device, or negative error */
+/* compute capability (major*10+minor) of the current device, or negative error (library plumbing: no reference counterpart;
+ * the reference asserts a CUDA device at utils/options.py:101) */
 int zs_device_cc(void);
 /* number of CUDA kernels this library has launched since it was loaded (all threads) */
 long long zs_launch_count(void);
@@ -65,7 +66,8 @@ int zs_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* b
                 const float* res, int ldres, int res_mode, float* C, int ldc,
                 int M, int N, int K, int act, void* stream);
 
-/* Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA bulk-copied weights) with the same epilogue.
+/* Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA bulk-copied weights) with the same epilogue: the F.linear calls above
+ * (model/shape/implicit.py:30,74,178-181; timm Block qkv / proj / fc1 / fc2 under model/depth/vit.py:149-150).
  * Weights are packed once (fp32 W[N,K] -> (hi,lo) bf16 tiles in the UMMA 128B-swizzled K-major smem image).
  * precision 0 = "bf16x3" (Ah*Wh + Ah*Wl + Al*Wh, ~2^-16 relative: parity mode), 1 = "bf16" (single pass). */
 size_t zs_gemm_tc_packed_bytes(int N, int K);
@@ -192,7 +194,8 @@ int zs_conv2d_nhwc_tc(const float* x, int B, int H, int W, int Cin, const void* 
 int zs_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
                      int rows, int cols, float eps, void* stream);
 
-/* GroupNorm (+optional ReLU) on NHWC.  Replaces timm GroupNormAct in the ResNetV2 stem/stages. */
+/* GroupNorm (+optional ReLU) on NHWC.  Replaces timm GroupNormAct in the ResNetV2 stem/stages of vit_base_resnet50_384
+ * (created at model/depth/vit.py:482; timm itself is third-party). */
 int zs_groupnorm_nhwc_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
                           int B, int HW, int C, int groups, float eps, int relu, void* stream);
 /* The same GroupNorm on the tiled kernels (two fully coalesced launches: per-chunk group statistics in double to `ws`, then the
@@ -202,14 +205,17 @@ size_t zs_groupnorm_ws_bytes(int B, int HW, int C, int groups);
 int zs_groupnorm_nhwc_ws_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y,
                              int B, int HW, int C, int groups, float eps, int relu, void* ws, void* stream);
 
-/* Per-channel affine y = act(x*scale[c] + shift[c] (+res)) on [rows, C] (eval-mode BatchNorm). */
+/* Per-channel affine y = act(x*scale[c] + shift[c] (+res)) on [rows, C]: eval-mode BatchNorm of Bottleneck_Conv
+ * (utils/layers.py:76-100) and of the torchvision ResNet-50 in CoordEncRes (model/shape/seen_coord_enc.py:141-194). */
 int zs_channel_affine_f32(const float* x, const float* scale, const float* shift, const float* res,
                           float* y, int64_t rows, int C, int act, void* stream);
 
-/* Elementwise: y = act(a*alpha + b*beta) (b may be NULL). */
+/* Elementwise: y = act(a*alpha + b*beta) (b may be NULL): residual adds / scalings such as model/depth/blocks.py:285,331,
+ * utils/util.py:345 (coordmap / (1 + 1e-6)), the final sigmoid of utils/eval_3D.py:43. */
 int zs_axpby_f32(const float* a, float alpha, const float* b, float beta, float* y, int64_t n, int act, void* stream);
 
-/* Max-pool 3x3 stride 2 on NHWC with explicit top/left padding (pad value -inf). */
+/* Max-pool 3x3 stride 2 on NHWC with explicit top/left padding (pad value -inf): timm MaxPool2dSame of the ResNetV2 stem and
+ * torchvision resnet50.maxpool (model/shape/seen_coord_enc.py:148-160). */
 int zs_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, int pad_top, int pad_left,
                              int OH, int OW, void* stream);
 
@@ -234,7 +240,7 @@ int zs_rgba_crop_resize_u8(const uint8_t* src, int H0, int W0, int left, int top
 int zs_rgba_composite_f32(const uint8_t* img, int H, int W, int use_bgcolor, float bgcolor, float* rgb, float* mask, void* stream);
 int zs_erode_square_f32(const float* mask, float* out, int B, int H, int W, int radius, void* stream);
 
-/* NCHW <-> NHWC */
+/* NCHW <-> NHWC (the reference keeps NCHW throughout; scale / shift fold `image * 2 - 1` of model/depth/dpt_depth.py:116) */
 int zs_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W, float scale, float shift, void* stream);
 int zs_nhwc_to_nchw_f32(const float* x, float* y, int B, int C, int H, int W, void* stream);
 
@@ -249,6 +255,9 @@ int zs_mha_tc_f32(const float* qkv, float* out, int B, int T, int heads, int hd,
  * transposes as tcgen05 MMAs with single-pass fp16 operands and fp32 accumulation, P and dS re-written in place in tensor memory
  * as the A operands of dQ = dS K, dV = P^T dO, dK = dS^T Q.  Precision class of the bf16 training mode (zs_mha_bwd_f32 is the
  * fp32-grade path).  dqkv [B,T,3C] is written completely; ws: zs_mha_bwd_tc_ws_bytes(B, T, heads), 16-byte aligned. */
+size_t zs_mha_bwd_tc_ws_bytes(int B, int T, int heads);
+int zs_mha_bwd_tc_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
+                      void* stream);
 /* zs_point_attention_f32 on the tensor cores for the training tape (csrc/mha_tc.cu: pa_fwd_tc_kernel; head dim 32, L <= 208, no
  * attention-map output): per 128-point tile S = Q K_lat^T and O = P V_lat as tcgen05 MMAs with the probabilities in tensor memory,
  * the point's own key / value as one extra softmax column in registers.  precision 0 = split fp16 (three passes), 1 = one fp16 pass. */
@@ -262,9 +271,6 @@ size_t zs_point_attention_bwd_tc_ws_bytes(int B, int P, int heads);
 int zs_point_attention_bwd_tc_f32(const float* qkv_p, const float* k_lat, const float* v_lat, int ld_lat, const float* dO,
                                   float* dqkv_p, float* dk_lat, float* dv_lat, int ld_dlat, int B, int P, int L, int heads, int hd,
                                   float scale, void* ws, void* stream);
-size_t zs_mha_bwd_tc_ws_bytes(int B, int T, int heads);
-int zs_mha_bwd_tc_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
-                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit decoder (model/shape/implicit.py:251-288), query-point side.
@@ -313,11 +319,6 @@ int zs_point_attention_bwd_f32(const float* qkv_p, const float* k_lat, const flo
 size_t zs_mha_bwd_ws_bytes(int B, int T, int heads);
 int zs_mha_bwd_f32(const float* qkv, const float* dO, float* dqkv, int B, int T, int heads, int hd, float scale, void* ws,
                    void* stream);
-/* MiDaS scale-and-shift-invariant depth loss (model/depth/midas_loss.py:145-185 as configured by utils/loss.py:14-16,30-34:
- * SSI-MAE on median / mean-absolute-deviation aligned maps + alpha x gradient matching over 4 scales of the least-squares aligned
- * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
- * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
- * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
 /* Front end of the transformer seen-surface encoder (CoordEmb.forward, model/shape/seen_coord_enc.py:49-72): per-pixel
  * Linear(3 -> C) of the XYZ map coord [B,H,W,3], `invalid` token where mask [B,H,W] <= 0.5, ws x ws window partition, the fixed
  * 2-D sin-cos embedding pos [ws*ws+1, C] local to each window and the cls row -> out [B*(H/ws)*(W/ws), ws*ws+1, C]. */
@@ -332,6 +333,11 @@ int zs_depth_metrics_f32(const float* pred, const float* gt, const float* mask, 
 /* MidasLoss.erode_mask (midas_loss.py:158-167, `training.depth_loss.mask_shrink`): out = 1 where a whole pool x pool block of the raw
  * mask [B,1,H,W] equals 1 (1 - mask -> max_pool2d -> nearest upsampling -> == 0), else 0. */
 int zs_mask_erode_f32(const float* mask, float* out, int B, int H, int W, int pool, void* stream);
+/* MiDaS scale-and-shift-invariant depth loss (model/depth/midas_loss.py:145-185 as configured by utils/loss.py:14-16,30-34:
+ * SSI-MAE on median / mean-absolute-deviation aligned maps + alpha x gradient matching over 4 scales of the least-squares aligned
+ * (inverse) depth, image-based reduction, valid = mask > 0.5) and its gradient w.r.t. the prediction.
+ * pred, gt, mask: [B, 1, H, W] fp32 contiguous; `loss`: one float on the device; `dpred` (optional): grad_scale * d loss / d pred;
+ * `ws`: zs_midas_ws_bytes(B, H, W), 8-byte aligned.  Three launches, no host sync. */
 size_t zs_midas_ws_bytes(int B, int H, int W);
 int zs_midas_loss_f32(const float* pred, const float* gt, const float* mask, int B, int H, int W, float alpha,
                       int inverse_depth, float grad_scale, void* ws, float* loss, float* dpred, void* stream);
